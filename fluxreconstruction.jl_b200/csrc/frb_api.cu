@@ -1,0 +1,484 @@
+// C ABI of libfrb200 (see include/frb200.h): contexts, problems, state movement,
+// f!(du,u,p,t), step!, hooks and measurement.  No CPU fallback anywhere: every compute
+// entry point launches sm_100a kernels or fails.
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+
+#include "frb_internal.cuh"
+
+static thread_local std::string g_err;
+
+void frb_set_error(const std::string &msg) { g_err = msg; }
+
+int frb_cuda_fail(cudaError_t e, const char *what, const char *file, int line) {
+  char buf[512];
+  snprintf(buf, sizeof buf, "CUDA error %d (%s) at %s:%d in %s", (int)e, cudaGetErrorString(e), file,
+           line, what);
+  g_err = buf;
+  return FRB_ERR_CUDA;
+}
+
+extern "C" const char *frb_last_error(frb_ctx_t) { return g_err.c_str(); }
+
+#define FRB_REQUIRE(cond, code, msg) \
+  do {                               \
+    if (!(cond)) {                   \
+      frb_set_error(msg);            \
+      return (code);                 \
+    }                                \
+  } while (0)
+
+// ---- context ------------------------------------------------------------------------
+extern "C" int32_t frb_ctx_create(int32_t device, frb_ctx_t *out) {
+  FRB_REQUIRE(out, FRB_ERR_ARG, "frb_ctx_create: out is NULL");
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) {
+    frb_set_error(std::string("no CUDA device available (libfrb200 has no CPU fallback): ") +
+                  cudaGetErrorString(e));
+    return FRB_ERR_CUDA;
+  }
+  if (device < 0) FRB_CUDA(cudaGetDevice(&device));
+  FRB_REQUIRE(device < ndev, FRB_ERR_ARG, "frb_ctx_create: device index out of range");
+  FRB_CUDA(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  FRB_CUDA(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10) {
+    frb_set_error(std::string("libfrb200 is built for sm_100a only; device is ") + prop.name);
+    return FRB_ERR_CUDA;
+  }
+  frb_ctx_t c = new frb_ctx_s();
+  c->device = device;
+  c->sm_count = prop.multiProcessorCount;
+  c->cc_major = prop.major;
+  c->cc_minor = prop.minor;
+  c->name = prop.name;
+  FRB_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  FRB_CUDA(cudaStreamCreateWithFlags(&c->copy_in, cudaStreamNonBlocking));
+  FRB_CUDA(cudaStreamCreateWithFlags(&c->copy_out, cudaStreamNonBlocking));
+  *out = c;
+  return FRB_OK;
+}
+
+extern "C" int32_t frb_ctx_destroy(frb_ctx_t c) {
+  if (!c) return FRB_OK;
+  cudaSetDevice(c->device);
+  if (c->stream) cudaStreamDestroy(c->stream);
+  if (c->copy_in) cudaStreamDestroy(c->copy_in);
+  if (c->copy_out) cudaStreamDestroy(c->copy_out);
+  delete c;
+  return FRB_OK;
+}
+
+extern "C" int32_t frb_device_info(frb_ctx_t c, int32_t *sm_count, int32_t *cc_major,
+                                   int32_t *cc_minor, char *name, int32_t name_len) {
+  FRB_REQUIRE(c, FRB_ERR_ARG, "frb_device_info: ctx is NULL");
+  if (sm_count) *sm_count = c->sm_count;
+  if (cc_major) *cc_major = c->cc_major;
+  if (cc_minor) *cc_minor = c->cc_minor;
+  if (name && name_len > 0) {
+    strncpy(name, c->name.c_str(), name_len - 1);
+    name[name_len - 1] = 0;
+  }
+  return FRB_OK;
+}
+
+// ---- problems -----------------------------------------------------------------------
+static int fill_ops(const frb_operators *o, FrbOps *dst, int *nsp_out, bool need_slopes) {
+  FRB_REQUIRE(o && o->ll && o->lr && o->lpdm && o->dgl && o->dgr, FRB_ERR_ARG,
+              "operators: ll, lr, lpdm, dgl, dgr must be non-NULL");
+  const int nsp = o->deg + 1;
+  FRB_REQUIRE(o->deg >= 1 && nsp <= FRB_NSPMAX, FRB_ERR_ARG, "operators: deg must be in 1..7");
+  FRB_REQUIRE(!need_slopes || (o->dll && o->dlr), FRB_ERR_ARG, "operators: dll/dlr required");
+  memset(dst, 0, sizeof(FrbOps));
+  for (int q = 0; q < nsp; ++q) {
+    dst->ll[q] = o->ll[q];
+    dst->lr[q] = o->lr[q];
+    dst->dgl[q] = o->dgl[q];
+    dst->dgr[q] = o->dgr[q];
+    if (o->dll) dst->dll[q] = o->dll[q];
+    if (o->dlr) dst->dlr[q] = o->dlr[q];
+    for (int k = 0; k < nsp; ++k) dst->lpdm[q * FRB_NSPMAX + k] = o->lpdm[q + nsp * k];  // [m,k] col-major
+  }
+  *nsp_out = nsp;
+  return FRB_OK;
+}
+
+static int alloc_common(frb_prob_t p) {
+  FRB_CUDA(cudaSetDevice(p->ctx->device));
+  FRB_CUDA(cudaMalloc(&p->u, sizeof(double) * p->len));
+  FRB_CUDA(cudaMalloc(&p->s1, sizeof(double) * p->len));
+  FRB_CUDA(cudaMalloc(&p->s2, sizeof(double) * p->len));
+  FRB_CUDA(cudaMemsetAsync(p->u, 0, sizeof(double) * p->len, p->ctx->stream));
+  FRB_CUDA(cudaMemsetAsync(p->s1, 0, sizeof(double) * p->len, p->ctx->stream));
+  FRB_CUDA(cudaMemsetAsync(p->s2, 0, sizeof(double) * p->len, p->ctx->stream));
+  FRB_CUDA(cudaMalloc(&p->flag, sizeof(int)));
+  FRB_CUDA(cudaEventCreate(&p->ev0));
+  FRB_CUDA(cudaEventCreate(&p->ev1));
+  FRB_CUDA(cudaStreamSynchronize(p->ctx->stream));
+  return FRB_OK;
+}
+
+static int upload_vec(frb_prob_t p, double **dst, const double *src, size_t n) {
+  FRB_CUDA(cudaMalloc(dst, sizeof(double) * n));
+  FRB_CUDA(cudaMemcpy(*dst, src, sizeof(double) * n, cudaMemcpyHostToDevice));
+  (void)p;
+  return FRB_OK;
+}
+
+extern "C" int32_t frb_prob_destroy(frb_prob_t p) {
+  if (!p) return FRB_OK;
+  cudaSetDevice(p->ctx->device);
+  cudaStreamSynchronize(p->ctx->stream);
+  frb_halo_disconnect(p);
+  frb_march_release(p);
+  cudaFree(p->u); cudaFree(p->s1); cudaFree(p->s2); cudaFree(p->du);
+  cudaFree(p->J); cudaFree(p->velo); cudaFree(p->weights); cudaFree(p->prim);
+  cudaFree(p->lim_w); cudaFree(p->flag);
+  if (p->ev0) cudaEventDestroy(p->ev0);
+  if (p->ev1) cudaEventDestroy(p->ev1);
+  delete p;
+  return FRB_OK;
+}
+
+#define FRB_TRY(expr)            \
+  do {                           \
+    int rc__ = (expr);           \
+    if (rc__ < 0) {              \
+      frb_prob_destroy(p);       \
+      return rc__;               \
+    }                            \
+  } while (0)
+
+extern "C" int32_t frb_advection1d_create(frb_ctx_t ctx, int32_t ncell, const frb_operators *ops,
+                                          const double *J, double a, int32_t bc, int32_t variant,
+                                          frb_prob_t *out) {
+  FRB_REQUIRE(ctx && out && J, FRB_ERR_ARG, "frb_advection1d_create: NULL argument");
+  FRB_REQUIRE(ncell >= 2, FRB_ERR_ARG, "frb_advection1d_create: ncell must be >= 2");
+  frb_prob_t p = new frb_prob_s();
+  p->ctx = ctx; p->kind = K_ADV1D; p->ncell = ncell; p->a = a; p->bc = bc; p->variant = variant;
+  FRB_TRY(fill_ops(ops, &p->ops, &p->nsp, false));
+  p->len = (int64_t)ncell * p->nsp;
+  p->dofs = p->len;
+  FRB_TRY(alloc_common(p));
+  FRB_TRY(upload_vec(p, &p->J, J, ncell));
+  *out = p;
+  return FRB_OK;
+}
+
+extern "C" int32_t frb_euler1d_create(frb_ctx_t ctx, int32_t ncell, const frb_operators *ops,
+                                      const double *J, double gamma, int32_t bc, frb_prob_t *out) {
+  FRB_REQUIRE(ctx && out && J, FRB_ERR_ARG, "frb_euler1d_create: NULL argument");
+  FRB_REQUIRE(ncell >= 2, FRB_ERR_ARG, "frb_euler1d_create: ncell must be >= 2");
+  frb_prob_t p = new frb_prob_s();
+  p->ctx = ctx; p->kind = K_EULER1D; p->ncell = ncell; p->gamma = gamma; p->bc = bc;
+  FRB_TRY(fill_ops(ops, &p->ops, &p->nsp, false));
+  p->len = (int64_t)ncell * p->nsp * 3;
+  p->dofs = p->len;
+  FRB_TRY(alloc_common(p));
+  FRB_TRY(upload_vec(p, &p->J, J, ncell));
+  *out = p;
+  return FRB_OK;
+}
+
+extern "C" int32_t frb_euler2d_create(frb_ctx_t ctx, int32_t nx, int32_t ny,
+                                      const frb_operators *ops, double Jx, double Jy, double gamma,
+                                      frb_prob_t *out) {
+  FRB_REQUIRE(ctx && out, FRB_ERR_ARG, "frb_euler2d_create: NULL argument");
+  FRB_REQUIRE(nx >= 1 && ny >= 1, FRB_ERR_ARG, "frb_euler2d_create: nx, ny must be >= 1");
+  FRB_REQUIRE(Jx > 0 && Jy > 0, FRB_ERR_ARG, "frb_euler2d_create: Jacobian must be positive");
+  frb_prob_t p = new frb_prob_s();
+  p->ctx = ctx; p->kind = K_EULER2D; p->nx = nx; p->ny = ny; p->Jx = Jx; p->Jy = Jy; p->gamma = gamma;
+  FRB_TRY(fill_ops(ops, &p->ops, &p->nsp, false));
+  if (p->nsp > 6) {
+    frb_set_error("frb_euler2d_create: deg must be in 1..5");
+    frb_prob_destroy(p);
+    return FRB_ERR_ARG;
+  }
+  p->len = (int64_t)(nx + 2) * (ny + 2) * p->nsp * p->nsp * 4;
+  p->dofs = (int64_t)nx * ny * p->nsp * p->nsp * 4;
+  FRB_TRY(alloc_common(p));
+  *out = p;
+  return FRB_OK;
+}
+
+extern "C" int32_t frb_bgk1d_create(frb_ctx_t ctx, int32_t ncell, int32_t nu,
+                                    const frb_operators *ops, const double *dx, const double *velo,
+                                    const double *weights, double tau, frb_prob_t *out) {
+  FRB_REQUIRE(ctx && out && dx && velo && weights, FRB_ERR_ARG, "frb_bgk1d_create: NULL argument");
+  FRB_REQUIRE(ncell >= 2 && nu >= 1 && nu <= 65535, FRB_ERR_ARG, "frb_bgk1d_create: bad sizes");
+  frb_prob_t p = new frb_prob_s();
+  p->ctx = ctx; p->kind = K_BGK1D; p->ncell = ncell; p->nu = nu; p->tau = tau;
+  FRB_TRY(fill_ops(ops, &p->ops, &p->nsp, false));
+  p->len = (int64_t)ncell * nu * p->nsp;
+  p->dofs = p->len;
+  FRB_TRY(alloc_common(p));
+  FRB_TRY(upload_vec(p, &p->J, dx, ncell));
+  FRB_TRY(upload_vec(p, &p->velo, velo, nu));
+  FRB_TRY(upload_vec(p, &p->weights, weights, nu));
+  if (cudaMalloc(&p->prim, sizeof(double) * (size_t)ncell * p->nsp * 3) != cudaSuccess) {
+    frb_prob_destroy(p);
+    frb_set_error("frb_bgk1d_create: cudaMalloc failed");
+    return FRB_ERR_CUDA;
+  }
+  *out = p;
+  return FRB_OK;
+}
+
+extern "C" int64_t frb_state_len(frb_prob_t p) { return p ? p->len : 0; }
+extern "C" int64_t frb_interior_dofs(frb_prob_t p) { return p ? p->dofs : 0; }
+
+// ---- state movement -------------------------------------------------------------------
+extern "C" int32_t frb_state_upload(frb_prob_t p, const double *u_host) {
+  FRB_REQUIRE(p && u_host, FRB_ERR_ARG, "frb_state_upload: NULL argument");
+  FRB_CUDA(cudaSetDevice(p->ctx->device));
+  cudaStream_t s = p->ctx->stream;
+  FRB_CUDA(cudaMemcpyAsync(p->u, u_host, sizeof(double) * p->len, cudaMemcpyHostToDevice, s));
+  FRB_CUDA(cudaStreamSynchronize(s));
+  return FRB_OK;
+}
+
+extern "C" int32_t frb_state_download(frb_prob_t p, double *u_host) {
+  FRB_REQUIRE(p && u_host, FRB_ERR_ARG, "frb_state_download: NULL argument");
+  FRB_CUDA(cudaSetDevice(p->ctx->device));
+  cudaStream_t s = p->ctx->stream;
+  FRB_CUDA(cudaMemcpyAsync(u_host, p->u, sizeof(double) * p->len, cudaMemcpyDeviceToHost, s));
+  FRB_CUDA(cudaStreamSynchronize(s));
+  return FRB_OK;
+}
+
+extern "C" int32_t frb_state_device_ptr(frb_prob_t p, double **dptr) {
+  FRB_REQUIRE(p && dptr, FRB_ERR_ARG, "frb_state_device_ptr: NULL argument");
+  *dptr = p->u;
+  return FRB_OK;
+}
+
+// ---- stage dispatch ---------------------------------------------------------------------
+static bool use_march(frb_prob_t p) {
+  if (p->kind != K_EULER2D) return false;
+  if (p->kernel_kind == FRB_KERNEL_GENERIC) return false;
+  return frb_euler2d_march_supported(p);
+}
+
+static int launch_stage(frb_prob_t p, const double *u, const double *ua, double *out, FrbStage st) {
+  int n;
+  switch (p->kind) {
+    case K_ADV1D: n = frb_launch_adv1d(p, u, ua, out, st); break;
+    case K_EULER1D: n = frb_launch_euler1d(p, u, ua, out, st); break;
+    case K_BGK1D: n = frb_launch_bgk1d(p, u, ua, out, st); break;
+    case K_EULER2D:
+      n = use_march(p) ? frb_launch_euler2d_march(p, u, ua, out, st)
+                       : frb_launch_euler2d_generic(p, u, ua, out, st);
+      break;
+    case K_NS2D: n = frb_launch_ns2d(p, u, ua, out, st); break;
+    default: frb_set_error("unknown problem kind"); return FRB_ERR_STATE;
+  }
+  if (n > 0) p->launches += n;
+  return n;
+}
+
+static bool is2d(frb_prob_t p) { return p->kind == K_EULER2D || p->kind == K_NS2D; }
+
+static int ensure_du(frb_prob_t p) {
+  if (!p->du) {
+    FRB_CUDA(cudaMalloc(&p->du, sizeof(double) * p->len));
+    FRB_CUDA(cudaMemsetAsync(p->du, 0, sizeof(double) * p->len, p->ctx->stream));  // du = 0 in ghosts
+  }
+  return FRB_OK;
+}
+
+extern "C" int32_t frb_rhs(frb_prob_t p, const double *u_host, double *du_host, double t) {
+  (void)t;
+  FRB_REQUIRE(p, FRB_ERR_ARG, "frb_rhs: prob is NULL");
+  FRB_CUDA(cudaSetDevice(p->ctx->device));
+  cudaStream_t s = p->ctx->stream;
+  if (int rc = ensure_du(p)) return rc;
+  if (u_host)
+    FRB_CUDA(cudaMemcpyAsync(p->u, u_host, sizeof(double) * p->len, cudaMemcpyHostToDevice, s));
+  const int64_t l0 = p->launches;
+  FRB_CUDA(cudaEventRecord(p->ev0, s));
+  FrbStage st = {0.0, 0.0, 1.0, 0, 1};
+  int n = launch_stage(p, p->u, nullptr, p->du, st);
+  if (n < 0) return n;
+  FRB_CUDA(cudaEventRecord(p->ev1, s));
+  if (du_host)
+    FRB_CUDA(cudaMemcpyAsync(du_host, p->du, sizeof(double) * p->len, cudaMemcpyDeviceToHost, s));
+  FRB_CUDA(cudaStreamSynchronize(s));
+  FRB_CUDA(cudaEventElapsedTime(&p->last_ms, p->ev0, p->ev1));
+  p->last_launches = p->launches - l0;
+  return FRB_OK;
+}
+
+// ---- hooks ------------------------------------------------------------------------------
+static int set_limiter_weights(frb_prob_t p, const double *w) {
+  const size_t n = is2d(p) ? (size_t)p->nsp * p->nsp : (size_t)p->nsp;
+  if (!p->lim_w) FRB_CUDA(cudaMalloc(&p->lim_w, sizeof(double) * n));
+  FRB_CUDA(cudaMemcpy(p->lim_w, w, sizeof(double) * n, cudaMemcpyHostToDevice));
+  return FRB_OK;
+}
+
+extern "C" int32_t frb_set_step_hooks(frb_prob_t p, int32_t ghost_mode, const double *limiter_weights) {
+  FRB_REQUIRE(p, FRB_ERR_ARG, "frb_set_step_hooks: prob is NULL");
+  FRB_REQUIRE(ghost_mode >= FRB_GHOST_NONE && ghost_mode <= FRB_GHOST_COPY, FRB_ERR_ARG,
+              "frb_set_step_hooks: unknown ghost mode");
+  FRB_REQUIRE(ghost_mode == FRB_GHOST_NONE || p->kind == K_EULER2D, FRB_ERR_STATE,
+              "frb_set_step_hooks: ghost fill applies to euler2d problems");
+  FRB_REQUIRE(!limiter_weights || p->kind == K_EULER1D || p->kind == K_EULER2D, FRB_ERR_STATE,
+              "frb_set_step_hooks: the positivity limiter applies to Euler problems");
+  FRB_CUDA(cudaSetDevice(p->ctx->device));
+  p->ghost_mode = ghost_mode;
+  p->limiter_on = limiter_weights != nullptr;
+  if (limiter_weights)
+    if (int rc = set_limiter_weights(p, limiter_weights)) return rc;
+  return FRB_OK;
+}
+
+static int run_limiter(frb_prob_t p) {
+  int n = p->kind == K_EULER1D ? frb_launch_limiter1d(p, p->u) : frb_launch_limiter2d(p, p->u);
+  if (n > 0) p->launches += n;
+  return n;
+}
+
+extern "C" int32_t frb_ghost_fill(frb_prob_t p, int32_t ghost_mode) {
+  FRB_REQUIRE(p, FRB_ERR_ARG, "frb_ghost_fill: prob is NULL");
+  FRB_REQUIRE(p->kind == K_EULER2D, FRB_ERR_STATE, "frb_ghost_fill: euler2d problems only");
+  FRB_CUDA(cudaSetDevice(p->ctx->device));
+  int n = frb_launch_ghost_fill2d(p, p->u, ghost_mode);
+  if (n < 0) return n;
+  p->launches += n;
+  FRB_CUDA(cudaStreamSynchronize(p->ctx->stream));
+  return FRB_OK;
+}
+
+extern "C" int32_t frb_limiter_positivity(frb_prob_t p, const double *weights, int32_t *nbad) {
+  FRB_REQUIRE(p && weights, FRB_ERR_ARG, "frb_limiter_positivity: NULL argument");
+  FRB_REQUIRE(p->kind == K_EULER1D || p->kind == K_EULER2D, FRB_ERR_STATE,
+              "frb_limiter_positivity: Euler problems only");
+  FRB_CUDA(cudaSetDevice(p->ctx->device));
+  if (int rc = set_limiter_weights(p, weights)) return rc;
+  FRB_CUDA(cudaMemsetAsync(p->flag, 0, sizeof(int), p->ctx->stream));
+  int n = run_limiter(p);
+  if (n < 0) return n;
+  int bad = 0;
+  FRB_CUDA(cudaMemcpyAsync(&bad, p->flag, sizeof(int), cudaMemcpyDeviceToHost, p->ctx->stream));
+  FRB_CUDA(cudaStreamSynchronize(p->ctx->stream));
+  if (nbad) *nbad = bad;
+  if (bad) {
+    frb_set_error("incorrect range of limiter parameter t");  // dissipation.jl:84
+    return FRB_ERR_NUMERIC;
+  }
+  return FRB_OK;
+}
+
+// ---- step! ------------------------------------------------------------------------------
+static int one_step(frb_prob_t p, int scheme, double dt) {
+  int n;
+  if (p->limiter_on) {
+    if ((n = run_limiter(p)) < 0) return n;
+  }
+  if (p->ghost_mode != FRB_GHOST_NONE) {
+    if ((n = frb_launch_ghost_fill2d(p, p->u, p->ghost_mode)) < 0) return n;
+    p->launches += n;
+  }
+  if (is2d(p)) {
+    // ghosts are frozen across the stages of a step (du = 0 there): give the stage
+    // buffers the same ring as u_n
+    if ((n = frb_launch_ring_copy2d(p, p->u, p->s1)) < 0) return n;
+    p->launches += n;
+    if (scheme == FRB_SCHEME_SSPRK3) {
+      if ((n = frb_launch_ring_copy2d(p, p->u, p->s2)) < 0) return n;
+      p->launches += n;
+    }
+  }
+  if (scheme == FRB_SCHEME_EULER) {
+    FrbStage st = {0.0, 1.0, dt, 0, 0};
+    if ((n = launch_stage(p, p->u, nullptr, p->s1, st)) < 0) return n;
+    std::swap(p->u, p->s1);
+  } else if (scheme == FRB_SCHEME_MIDPOINT) {
+    FrbStage a = {0.0, 1.0, 0.5 * dt, 0, 0};
+    if ((n = launch_stage(p, p->u, nullptr, p->s1, a)) < 0) return n;
+    FrbStage b = {1.0, 0.0, dt, 1, 0};
+    if ((n = launch_stage(p, p->s1, p->u, p->u, b)) < 0) return n;
+  } else if (scheme == FRB_SCHEME_SSPRK3) {
+    FrbStage a = {0.0, 1.0, dt, 0, 0};
+    if ((n = launch_stage(p, p->u, nullptr, p->s1, a)) < 0) return n;
+    FrbStage b = {0.75, 0.25, dt, 1, 0, 1};
+    if ((n = launch_stage(p, p->s1, p->u, p->s2, b)) < 0) return n;
+    FrbStage c = {1.0 / 3.0, 2.0 / 3.0, dt, 1, 0, 1};
+    if ((n = launch_stage(p, p->s2, p->u, p->u, c)) < 0) return n;
+  } else {
+    frb_set_error("frb_step: unknown scheme");
+    return FRB_ERR_ARG;
+  }
+  return FRB_OK;
+}
+
+extern "C" int32_t frb_step(frb_prob_t p, int32_t scheme, double dt, int32_t nsteps) {
+  FRB_REQUIRE(p, FRB_ERR_ARG, "frb_step: prob is NULL");
+  FRB_REQUIRE(nsteps >= 0, FRB_ERR_ARG, "frb_step: nsteps must be >= 0");
+  FRB_CUDA(cudaSetDevice(p->ctx->device));
+  cudaStream_t s = p->ctx->stream;
+  const int64_t l0 = p->launches;
+  if (p->limiter_on) FRB_CUDA(cudaMemsetAsync(p->flag, 0, sizeof(int), s));
+  FRB_CUDA(cudaEventRecord(p->ev0, s));
+  for (int it = 0; it < nsteps; ++it) {
+    int rc = one_step(p, scheme, dt);
+    if (rc < 0) return rc;
+  }
+  FRB_CUDA(cudaEventRecord(p->ev1, s));
+  int bad = 0;
+  if (p->limiter_on)
+    FRB_CUDA(cudaMemcpyAsync(&bad, p->flag, sizeof(int), cudaMemcpyDeviceToHost, s));
+  FRB_CUDA(cudaStreamSynchronize(s));
+  FRB_CUDA(cudaEventElapsedTime(&p->last_ms, p->ev0, p->ev1));
+  p->last_launches = p->launches - l0;
+  if (bad) {
+    frb_set_error("incorrect range of limiter parameter t");
+    return FRB_ERR_NUMERIC;
+  }
+  return FRB_OK;
+}
+
+// ---- measurement ------------------------------------------------------------------------
+extern "C" int32_t frb_time_stage(frb_prob_t p, int32_t stage_kind, int32_t iters, float *ms) {
+  FRB_REQUIRE(p && ms && iters > 0, FRB_ERR_ARG, "frb_time_stage: bad argument");
+  FRB_CUDA(cudaSetDevice(p->ctx->device));
+  cudaStream_t s = p->ctx->stream;
+  // scratch: u_n := s1 (copy of the state so that the arithmetic sees finite data)
+  FRB_CUDA(cudaMemcpyAsync(p->s1, p->u, sizeof(double) * p->len, cudaMemcpyDeviceToDevice, s));
+  FrbStage st = stage_kind == 0 ? FrbStage{0.0, 1.0, 1e-9, 0, 0} : FrbStage{0.75, 0.25, 0.25e-9, 1, 0};
+  const int64_t l0 = p->launches;
+  FRB_CUDA(cudaEventRecord(p->ev0, s));
+  for (int it = 0; it < iters; ++it) {
+    int n = launch_stage(p, p->u, p->s1, p->s2, st);
+    if (n < 0) return n;
+  }
+  FRB_CUDA(cudaEventRecord(p->ev1, s));
+  FRB_CUDA(cudaStreamSynchronize(s));
+  float total = 0.f;
+  FRB_CUDA(cudaEventElapsedTime(&total, p->ev0, p->ev1));
+  *ms = total / iters;
+  p->last_ms = total;
+  p->last_launches = p->launches - l0;
+  return FRB_OK;
+}
+
+extern "C" int32_t frb_last_timing(frb_prob_t p, float *ms, int64_t *kernel_launches) {
+  FRB_REQUIRE(p, FRB_ERR_ARG, "frb_last_timing: prob is NULL");
+  if (ms) *ms = p->last_ms;
+  if (kernel_launches) *kernel_launches = p->last_launches;
+  return FRB_OK;
+}
+
+extern "C" int32_t frb_set_kernel(frb_prob_t p, int32_t kind) {
+  FRB_REQUIRE(p, FRB_ERR_ARG, "frb_set_kernel: prob is NULL");
+  FRB_REQUIRE(kind >= FRB_KERNEL_AUTO && kind <= FRB_KERNEL_MARCH, FRB_ERR_ARG,
+              "frb_set_kernel: unknown kernel kind");
+  if (kind == FRB_KERNEL_MARCH)
+    FRB_REQUIRE(frb_euler2d_march_supported(p), FRB_ERR_STATE,
+                "frb_set_kernel: marching kernel needs euler2d, deg 2..3 and even nx");
+  p->kernel_kind = kind;
+  return FRB_OK;
+}

@@ -1,0 +1,450 @@
+// Fused 2-D Euler residual + RK stage: the row-marching TMA kernel (the roofline path).
+//
+// One HBM pass per stage: read u (once, plus a 1-row/1-column halo that lives in L2),
+// optionally read u_n, write u'.  Everything between -- point fluxes, the four trace
+// interpolations, the HLL common fluxes on all four faces, the lpdm derivative and the
+// dgl/dgr correction, division by the Jacobian and the stage combination -- happens on
+// chip (reference: dudt! of example/euler2d_wave.jl:35-107 + the OrdinaryDiffEq stage
+// axpys around it).
+//
+// Decomposition
+//   grid.x = strips of 30 owned elements in x (a warp's 32 lanes are elements
+//            i0-1 .. i0+30: lanes 0 and 31 are x-halo lanes that only feed traces),
+//   grid.y = row segments; the CTA marches j = ja .. jb through its segment.
+//   CTA    = NSP warps; warp t handles row  l = t in the x pass and column k = t in the
+//            y pass of every element of the strip.
+// Per row step
+//   TMA (cp.async.bulk.tensor.3d) lands the [4*NSP^2 planes] x [32 elements] block of a row
+//   in shared memory (NBUF-deep mbarrier ring), so both the row view and the column view
+//   of an element are plain conflict-free LDS -- the transpose is free.
+//   x pass: F at the row's points, x traces, left-face HLL with the left neighbour's trace
+//           by __shfl_up, right-face flux by __shfl_down, d/dr + correction -> smem.
+//   y pass: G at the column's points (1/rho and p come from the x pass through smem),
+//           y traces, top-face HLL against the bottom trace of row j+1 (already resident
+//           in the ring), d/ds + corrections; the bottom-face flux is the top-face flux
+//           carried in registers from row j-1.  u' is written fused with the RK combination.
+#include <cuda.h>
+
+#include <cstdlib>
+#include <map>
+
+#include "frb_internal.cuh"
+#include "frb_physics.cuh"
+
+namespace {
+
+constexpr int kOwn = 30;  // owned elements per strip (32 lanes - 2 halo lanes)
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+               "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra WAIT_DONE;\n"
+      "bra WAIT_LOOP;\n"
+      "WAIT_DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *map, uint64_t *bar,
+                                            int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void prefetch_l2(const void *p) {
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+}
+
+struct MarchParams {
+  const double *ua;  // u_n (may alias out)
+  double *out;
+  int nx, ny;
+  int rows_per_seg;
+  double gamma;
+  double ca, cb;
+  double cxs, cys;  // -cdt/Jx, -cdt/Jy  (L = -(dux/Jx + duy/Jy))
+  int use_a;
+};
+
+template <int NSP, int NBUF>
+struct Smem {
+  static constexpr int kPlanes = 4 * NSP * NSP;
+  static constexpr int kTile = kPlanes * 32;  // doubles
+  alignas(128) double tile[NBUF][kTile];
+  alignas(128) double xd[kPlanes * kOwn];         // x-pass derivative + correction (no 1/Jx yet)
+  alignas(128) double xrp[2 * NSP * NSP * kOwn];  // 1/rho and p at the points
+  alignas(8) uint64_t bar[NBUF];
+};
+
+// MINB = resident CTAs per SM the register budget is compiled for
+template <int NSP, int NBUF, int MINB>
+__global__ void __launch_bounds__(NSP * 32, MINB)
+euler2d_march_kernel(const __grid_constant__ CUtensorMap tmap, MarchParams P, FrbOps ops) {
+  extern __shared__ unsigned char smem_raw[];
+  using SM = Smem<NSP, NBUF>;
+  SM &S = *reinterpret_cast<SM *>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
+  constexpr int kPlanes = SM::kPlanes;
+  constexpr uint32_t kTileBytes = kPlanes * 32 * sizeof(double);
+
+  const int lane = threadIdx.x & 31;
+  const int t = threadIdx.x >> 5;  // row index in the x pass, column index in the y pass
+  const int i = blockIdx.x * kOwn + lane;  // element column of this lane (0 = ghost)
+  const int ja = 1 + blockIdx.y * P.rows_per_seg;
+  const int jb = min(P.ny, ja + P.rows_per_seg - 1);
+  if (ja > P.ny) return;
+  const int ntiles = jb - ja + 3;  // rows ja-1 .. jb+1; tile q holds row ja-1+q in buffer q % NBUF
+  const size_t NXG = P.nx + 2, NE = NXG * (size_t)(P.ny + 2);
+  const int cl = lane - 1;                     // compact lane index of the owned columns
+  const bool inner = (unsigned)cl < (unsigned)kOwn;
+  const bool owner = inner && i <= P.nx;
+  const double gamma = P.gamma, gm1 = gamma - 1.0;
+  const int c0 = blockIdx.x * kOwn;
+
+  if (threadIdx.x == 0) {
+    for (int b = 0; b < NBUF; ++b) mbar_init(&S.bar[b], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const int npre = ntiles < NBUF ? ntiles : NBUF;
+    for (int q = 0; q < npre; ++q) {
+      mbar_expect_tx(&S.bar[q], kTileBytes);
+      tma_load_3d(S.tile[q], &tmap, &S.bar[q], c0, ja - 1 + q, 0);
+    }
+  }
+
+  // ---- prologue: common flux on the bottom face of row ja from tiles 0 (row ja-1) and 1
+  double hb[4];
+  {
+    mbar_wait(&S.bar[0], 0);
+    mbar_wait(&S.bar[1 % NBUF], 0);
+    const double *U0 = S.tile[0] + lane;
+    const double *U1 = S.tile[1 % NBUF] + lane;
+    double uT[4], uB[4];
+#pragma unroll
+    for (int m = 0; m < 4; ++m) {
+      double a = U0[32 * (t + NSP * (0 + NSP * m))] * ops.lr[0];
+      double b = U1[32 * (t + NSP * (0 + NSP * m))] * ops.ll[0];
+#pragma unroll
+      for (int q = 1; q < NSP; ++q) {
+        a = fma(U0[32 * (t + NSP * (q + NSP * m))], ops.lr[q], a);
+        b = fma(U1[32 * (t + NSP * (q + NSP * m))], ops.ll[q], b);
+      }
+      uT[m] = a; uB[m] = b;
+    }
+    frb::Flux4 h = frb::hll4_y(uT[0], uT[1], uT[2], uT[3], uB[0], uB[1], uB[2], uB[3], gamma);
+    hb[0] = h.f0; hb[1] = h.f1; hb[2] = h.f2; hb[3] = h.f3;
+  }
+  {
+    // tile 0 is dead after the prologue: refill its buffer with tile NBUF
+    __syncthreads();
+    if (threadIdx.x == 0 && ntiles > NBUF) {
+      mbar_expect_tx(&S.bar[0], kTileBytes);
+      tma_load_3d(S.tile[0], &tmap, &S.bar[0], c0, ja - 1 + NBUF, 0);
+    }
+  }
+
+  for (int q = 1; q <= ntiles - 2; ++q) {  // tile q = row j
+    const int j = ja - 1 + q;
+    const int buf = q % NBUF, nbuf = (q + 1) % NBUF;
+    const double *U = S.tile[buf] + lane;
+    const double *ua_row = P.ua + i + NXG * (size_t)j;
+    if (P.use_a && owner) {
+      // pull this row's u_n into L2 now; the loads after the x pass then hit L2
+#pragma unroll
+      for (int m = 0; m < 4; ++m)
+#pragma unroll
+        for (int l = 0; l < NSP; ++l) prefetch_l2(ua_row + NE * (t + NSP * (l + NSP * m)));
+    }
+    // tile q was already waited on as the "next" tile of step q-1 (or in the prologue)
+
+    // -------------------------------------------------------------- x pass: row l = t
+    {
+      double w[NSP][4], f[NSP][4];
+#pragma unroll
+      for (int m = 0; m < 4; ++m)
+#pragma unroll
+        for (int k = 0; k < NSP; ++k) w[k][m] = U[32 * (k + NSP * (t + NSP * m))];
+#pragma unroll
+      for (int k = 0; k < NSP; ++k) {
+        double rr = 1.0 / w[k][0];
+        double vx = w[k][1] * rr, vy = w[k][2] * rr;
+        double p = gm1 * fma(-0.5, fma(w[k][1], vx, w[k][2] * vy), w[k][3]);
+        f[k][0] = w[k][1];
+        f[k][1] = fma(w[k][1], vx, p);
+        f[k][2] = w[k][1] * vy;
+        f[k][3] = (w[k][3] + p) * vx;
+        if (inner) {
+          S.xrp[kOwn * (k + NSP * t) + cl] = rr;
+          S.xrp[kOwn * (NSP * NSP + k + NSP * t) + cl] = p;
+        }
+      }
+      double uL[4], uR[4], fL[4], fR[4];
+#pragma unroll
+      for (int m = 0; m < 4; ++m) {
+        double a = w[0][m] * ops.ll[0], b = w[0][m] * ops.lr[0];
+        double c = f[0][m] * ops.ll[0], d = f[0][m] * ops.lr[0];
+#pragma unroll
+        for (int q2 = 1; q2 < NSP; ++q2) {
+          a = fma(w[q2][m], ops.ll[q2], a);
+          b = fma(w[q2][m], ops.lr[q2], b);
+          c = fma(f[q2][m], ops.ll[q2], c);
+          d = fma(f[q2][m], ops.lr[q2], d);
+        }
+        uL[m] = a; uR[m] = b; fL[m] = c; fR[m] = d;
+      }
+      // left face: HLL(u_face[i-1,j,2,l,:], u_face[i,j,4,l,:])  (euler2d_wave.jl:69-74)
+      double n0 = __shfl_up_sync(0xffffffffu, uR[0], 1), n1 = __shfl_up_sync(0xffffffffu, uR[1], 1);
+      double n2 = __shfl_up_sync(0xffffffffu, uR[2], 1), n3 = __shfl_up_sync(0xffffffffu, uR[3], 1);
+      frb::Flux4 hl = frb::hll4(n0, n1, n2, n3, uL[0], uL[1], uL[2], uL[3], gamma);
+      double hr0 = __shfl_down_sync(0xffffffffu, hl.f0, 1), hr1 = __shfl_down_sync(0xffffffffu, hl.f1, 1);
+      double hr2 = __shfl_down_sync(0xffffffffu, hl.f2, 1), hr3 = __shfl_down_sync(0xffffffffu, hl.f3, 1);
+      const double cL[4] = {hl.f0 - fL[0], hl.f1 - fL[1], hl.f2 - fL[2], hl.f3 - fL[3]};
+      const double cR[4] = {hr0 - fR[0], hr1 - fR[1], hr2 - fR[2], hr3 - fR[3]};
+      if (inner) {
+#pragma unroll
+        for (int m = 0; m < 4; ++m)
+#pragma unroll
+          for (int k = 0; k < NSP; ++k) {
+            double d = f[0][m] * ops.lpdm[k * FRB_NSPMAX];
+#pragma unroll
+            for (int q2 = 1; q2 < NSP; ++q2) d = fma(f[q2][m], ops.lpdm[k * FRB_NSPMAX + q2], d);
+            d = fma(cL[m], ops.dgl[k], d);
+            d = fma(cR[m], ops.dgr[k], d);
+            S.xd[kOwn * (k + NSP * (t + NSP * m)) + cl] = d;
+          }
+      }
+    }
+    __syncthreads();  // (A) xd / xrp of this row visible
+
+    // -------------------------------------------------------------- y pass: column k = t
+    {
+      double un[NSP][4];
+      if (P.use_a && owner) {
+#pragma unroll
+        for (int m = 0; m < 4; ++m)
+#pragma unroll
+          for (int l = 0; l < NSP; ++l) un[l][m] = __ldcs(ua_row + NE * (t + NSP * (l + NSP * m)));
+      }
+      double w[NSP][4], g[NSP][4];  // [l][m]
+#pragma unroll
+      for (int m = 0; m < 4; ++m)
+#pragma unroll
+        for (int l = 0; l < NSP; ++l) w[l][m] = U[32 * (t + NSP * (l + NSP * m))];
+      const int clc = inner ? cl : 0;
+#pragma unroll
+      for (int l = 0; l < NSP; ++l) {
+        double rr = S.xrp[kOwn * (t + NSP * l) + clc];
+        double p = S.xrp[kOwn * (NSP * NSP + t + NSP * l) + clc];
+        double vy = w[l][2] * rr;
+        g[l][0] = w[l][2];
+        g[l][1] = w[l][1] * vy;
+        g[l][2] = fma(w[l][2], vy, p);
+        g[l][3] = (w[l][3] + p) * vy;
+      }
+      // top face of row j: HLL between this row's top trace and row j+1's bottom trace
+      mbar_wait(&S.bar[nbuf], ((q + 1) / NBUF) & 1);
+      const double *Un = S.tile[nbuf] + lane;
+      double ht[4];
+      {
+        double uT[4], uB[4];
+#pragma unroll
+        for (int m = 0; m < 4; ++m) {
+          double a = w[0][m] * ops.lr[0];
+          double b = Un[32 * (t + NSP * (0 + NSP * m))] * ops.ll[0];
+#pragma unroll
+          for (int q2 = 1; q2 < NSP; ++q2) {
+            a = fma(w[q2][m], ops.lr[q2], a);
+            b = fma(Un[32 * (t + NSP * (q2 + NSP * m))], ops.ll[q2], b);
+          }
+          uT[m] = a; uB[m] = b;
+        }
+        frb::Flux4 h = frb::hll4_y(uT[0], uT[1], uT[2], uT[3], uB[0], uB[1], uB[2], uB[3], gamma);
+        ht[0] = h.f0; ht[1] = h.f1; ht[2] = h.f2; ht[3] = h.f3;
+      }
+      double *obase = P.out + i + NXG * (size_t)j;
+#pragma unroll
+      for (int m = 0; m < 4; ++m) {
+        double gB = g[0][m] * ops.ll[0], gT = g[0][m] * ops.lr[0];
+#pragma unroll
+        for (int q2 = 1; q2 < NSP; ++q2) {
+          gB = fma(g[q2][m], ops.ll[q2], gB);
+          gT = fma(g[q2][m], ops.lr[q2], gT);
+        }
+        const double cB = hb[m] - gB, cT = ht[m] - gT;
+#pragma unroll
+        for (int l = 0; l < NSP; ++l) {
+          double d = g[0][m] * ops.lpdm[l * FRB_NSPMAX];
+#pragma unroll
+          for (int q2 = 1; q2 < NSP; ++q2) d = fma(g[q2][m], ops.lpdm[l * FRB_NSPMAX + q2], d);
+          d = fma(cB, ops.dgl[l], d);
+          d = fma(cT, ops.dgr[l], d);
+          if (owner) {
+            double dx = S.xd[kOwn * (t + NSP * (l + NSP * m)) + cl];
+            double v = fma(P.cys, d, fma(P.cxs, dx, P.cb * w[l][m]));
+            if (P.use_a) v = fma(P.ca, un[l][m], v);
+            __stcs(obase + NE * (t + NSP * (l + NSP * m)), v);
+          }
+        }
+        hb[m] = ht[m];
+      }
+    }
+    __syncthreads();  // (B) every read of tile[buf], xd, xrp is done
+
+    if (threadIdx.x == 0 && q + NBUF < ntiles) {
+      mbar_expect_tx(&S.bar[buf], kTileBytes);
+      tma_load_3d(S.tile[buf], &tmap, &S.bar[buf], c0, ja - 1 + q + NBUF, 0);
+    }
+  }
+}
+
+// ---- host side: tensor-map cache and launch ---------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *,
+                                  const cuuint64_t *, const cuuint64_t *, const cuuint32_t *,
+                                  const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void *p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+struct MapCache {
+  std::map<const void *, CUtensorMap> maps;
+};
+
+int env_int(const char *name, int dflt) {
+  const char *s = getenv(name);
+  return s && *s ? atoi(s) : dflt;
+}
+
+}  // namespace
+
+bool frb_euler2d_march_supported(frb_prob_t p) {
+  // TMA needs 16-byte global strides: (nx+2)*8 bytes per row -> nx even
+  return p->kind == K_EULER2D && (p->nsp == 4 || p->nsp == 3) && (p->nx % 2 == 0);
+}
+
+void frb_march_release(frb_prob_t p) {
+  delete static_cast<MapCache *>(p->tmaps);
+  p->tmaps = nullptr;
+}
+
+static int march_rows_per_seg(frb_prob_t p, int ctas_per_sm) {
+  // choose the segment count so that the grid is close to a whole number of waves of
+  // (SMs x resident CTAs); every segment re-reads two halo rows
+  int forced = env_int("FRB_MARCH_ROWS", 0);
+  if (forced > 0) return forced < p->ny ? forced : p->ny;
+  const int strips = (p->nx + kOwn - 1) / kOwn;
+  const int slots = p->ctx->sm_count * ctas_per_sm;
+  int best_rows = p->ny;
+  double best_cost = 1e300;
+  for (int nseg = 1; nseg <= p->ny; ++nseg) {
+    int rows = (p->ny + nseg - 1) / nseg;
+    if (rows < 8 && nseg > 1) break;
+    int segs = (p->ny + rows - 1) / rows;
+    long ctas = (long)strips * segs;
+    long waves = (ctas + slots - 1) / slots;
+    double cost = (double)waves * (rows + 2.0) * (1.0 + 1e-6 * segs);
+    if (cost < best_cost) { best_cost = cost; best_rows = rows; }
+  }
+  return best_rows;
+}
+
+template <int NSP, int NBUF, int MINB>
+static int launch_march(frb_prob_t p, const CUtensorMap &map, MarchParams mp) {
+  mp.rows_per_seg = march_rows_per_seg(p, MINB);
+  const int strips = (p->nx + kOwn - 1) / kOwn;
+  const int segs = (p->ny + mp.rows_per_seg - 1) / mp.rows_per_seg;
+  const size_t smem = sizeof(Smem<NSP, NBUF>) + 128;
+  static bool attr_done = false;
+  if (!attr_done) {
+    FRB_CUDA(cudaFuncSetAttribute(euler2d_march_kernel<NSP, NBUF, MINB>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    FRB_CUDA(cudaFuncSetAttribute(euler2d_march_kernel<NSP, NBUF, MINB>,
+                                  cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    attr_done = true;
+  }
+  dim3 grd(strips, segs), blk(NSP * 32);
+  euler2d_march_kernel<NSP, NBUF, MINB><<<grd, blk, smem, p->ctx->stream>>>(map, mp, p->ops);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return frb_cuda_fail(e, "euler2d_march_kernel", __FILE__, __LINE__);
+  return 1;
+}
+
+int frb_launch_euler2d_march(frb_prob_t p, const double *u, const double *ua, double *out,
+                             FrbStage st) {
+  if (!frb_euler2d_march_supported(p)) {
+    frb_set_error("marching kernel needs deg 2 or 3 and even nx");
+    return FRB_ERR_ARG;
+  }
+  if (!p->tmaps) p->tmaps = new MapCache();
+  MapCache *mc = static_cast<MapCache *>(p->tmaps);
+  auto it = mc->maps.find(u);
+  if (it == mc->maps.end()) {
+    EncodeTiledFn enc = get_encode();
+    if (!enc) {
+      frb_set_error("cuTensorMapEncodeTiled not available from the driver");
+      return FRB_ERR_CUDA;
+    }
+    const cuuint64_t NXG = p->nx + 2, NYG = p->ny + 2, NPL = 4 * p->nsp * p->nsp;
+    cuuint64_t gdim[3] = {NXG, NYG, NPL};
+    cuuint64_t gstr[2] = {NXG * 8, NXG * NYG * 8};
+    cuuint32_t box[3] = {32, 1, (cuuint32_t)NPL};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUtensorMap m;
+    CUresult r = enc(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, const_cast<double *>(u), gdim, gstr,
+                     box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+      frb_set_error("cuTensorMapEncodeTiled failed with CUresult " + std::to_string((int)r));
+      return FRB_ERR_CUDA;
+    }
+    it = mc->maps.emplace(u, m).first;
+  }
+  MarchParams mp;
+  mp.ua = ua;
+  mp.out = out;
+  mp.nx = p->nx;
+  mp.ny = p->ny;
+  mp.rows_per_seg = 0;
+  mp.gamma = p->gamma;
+  if (st.rhs_only) {
+    mp.ca = 0.0; mp.cb = 0.0; mp.use_a = 0;
+    mp.cxs = -1.0 / p->Jx; mp.cys = -1.0 / p->Jy;
+  } else {
+    const double cdt = st.nested ? st.cb * st.cdt : st.cdt;
+    mp.ca = st.ca; mp.cb = st.cb; mp.use_a = st.use_a;
+    mp.cxs = -cdt / p->Jx; mp.cys = -cdt / p->Jy;
+  }
+  const int variant = env_int("FRB_MARCH_VARIANT", 0);  // 0: 2-deep ring, 4 CTAs/SM; 1: 3-deep, 3 CTAs/SM
+  if (p->nsp == 4) {
+    if (variant == 1) return launch_march<4, 3, 3>(p, it->second, mp);
+    return launch_march<4, 2, 4>(p, it->second, mp);
+  }
+  if (variant == 1) return launch_march<3, 3, 4>(p, it->second, mp);
+  return launch_march<3, 2, 5>(p, it->second, mp);
+}

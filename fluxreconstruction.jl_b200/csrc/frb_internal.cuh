@@ -1,0 +1,102 @@
+// Internal declarations shared by the libfrb200 translation units (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+#include <vector>
+
+#include "../../include/frb200.h"
+
+#define FRB_NSPMAX FRB_MAX_NSP
+
+// Operator arrays of one FR space, passed by value as a kernel parameter so that
+// every access is a uniform constant-bank load.  lpdm is row-major here:
+// lpdm[m * FRB_NSPMAX + k] = ps.dl[m, k].
+struct FrbOps {
+  double ll[FRB_NSPMAX], lr[FRB_NSPMAX], dgl[FRB_NSPMAX], dgr[FRB_NSPMAX];
+  double dll[FRB_NSPMAX], dlr[FRB_NSPMAX];
+  double lpdm[FRB_NSPMAX * FRB_NSPMAX];
+};
+
+// One Runge-Kutta stage in the fused form  out = ca*ua + cb*u + cdt*L(u).
+//   rhs_only : out = L(u)   (the f!(du,u,p,t) shape)
+//   use_a    : ua is read (24 B/DOF stage) or skipped (16 B/DOF stage)
+//   nested   : the combination is  ca*ua + cb*(u + cdt*L(u))  (Shu-Osher form, the order
+//              OrdinaryDiffEq's SSPRK33 and the oracle evaluate it in)
+struct FrbStage {
+  double ca, cb, cdt;
+  int use_a, rhs_only, nested;
+};
+
+enum FrbKind { K_ADV1D = 0, K_EULER1D = 1, K_EULER2D = 2, K_BGK1D = 3, K_NS2D = 4 };
+
+void frb_set_error(const std::string &msg);
+int frb_cuda_fail(cudaError_t e, const char *what, const char *file, int line);
+
+#define FRB_CUDA(call)                                                     \
+  do {                                                                     \
+    cudaError_t e__ = (call);                                              \
+    if (e__ != cudaSuccess) return frb_cuda_fail(e__, #call, __FILE__, __LINE__); \
+  } while (0)
+
+struct frb_ctx_s {
+  int device = 0;
+  int sm_count = 0;
+  int cc_major = 0, cc_minor = 0;
+  cudaStream_t stream = nullptr;
+  cudaStream_t copy_in = nullptr, copy_out = nullptr;
+  std::string name;
+};
+
+struct FrbHalo;
+
+struct frb_prob_s {
+  frb_ctx_t ctx = nullptr;
+  FrbKind kind = K_ADV1D;
+  int nsp = 0;
+  FrbOps ops;
+  // sizes
+  int ncell = 0, nu = 0;  // 1-D
+  int nx = 0, ny = 0;     // 2-D (interior)
+  int64_t len = 0, dofs = 0;
+  // physics
+  double a = 0, gamma = 0, Jx = 0, Jy = 0, tau = 0;
+  int bc = 0, variant = 0;
+  double gks_K = 0, gks_mu = 0, gks_omega = 0, gks_dt = 0, lid_u = 0, lambda_wall = 1.0;
+  // device buffers
+  double *u = nullptr;              // resident state  (u_n)
+  double *s1 = nullptr, *s2 = nullptr;  // stage buffers
+  double *du = nullptr;             // f! output (lazy)
+  double *J = nullptr;              // 1-D per-cell Jacobian / bgk dx
+  double *velo = nullptr, *weights = nullptr, *prim = nullptr;  // bgk
+  double *lim_w = nullptr;          // limiter weights (device)
+  int *flag = nullptr;              // device int for limiter nbad
+  // hooks
+  int ghost_mode = FRB_GHOST_NONE;
+  bool limiter_on = false;
+  int kernel_kind = FRB_KERNEL_AUTO;
+  // timing
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  float last_ms = 0.f;
+  int64_t last_launches = 0;
+  int64_t launches = 0;
+  // TMA descriptors for the marching kernel (opaque 128-byte CUtensorMap images)
+  void *tmaps = nullptr;  // host copy, keyed by device pointer
+  FrbHalo *halo = nullptr;
+};
+
+// ---- kernel launchers (each returns the number of kernels launched or <0) --------
+int frb_launch_adv1d(frb_prob_t p, const double *u, const double *ua, double *out, FrbStage st);
+int frb_launch_euler1d(frb_prob_t p, const double *u, const double *ua, double *out, FrbStage st);
+int frb_launch_bgk1d(frb_prob_t p, const double *u, const double *ua, double *out, FrbStage st);
+int frb_launch_euler2d_generic(frb_prob_t p, const double *u, const double *ua, double *out, FrbStage st);
+int frb_launch_euler2d_march(frb_prob_t p, const double *u, const double *ua, double *out, FrbStage st);
+bool frb_euler2d_march_supported(frb_prob_t p);
+int frb_launch_ns2d(frb_prob_t p, const double *u, const double *ua, double *out, FrbStage st);
+int frb_launch_ghost_fill2d(frb_prob_t p, double *u, int mode);
+int frb_launch_ring_copy2d(frb_prob_t p, const double *src, double *dst);
+int frb_launch_zero_ring2d(frb_prob_t p, double *dst);
+int frb_launch_limiter1d(frb_prob_t p, double *u);
+int frb_launch_limiter2d(frb_prob_t p, double *u);
+int frb_launch_dirichlet_copy1d(frb_prob_t p, const double *src, double *dst);
+void frb_march_release(frb_prob_t p);

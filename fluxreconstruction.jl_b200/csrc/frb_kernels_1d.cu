@@ -1,0 +1,320 @@
+// 1-D fused residual + RK-stage kernels: advection, Euler (HLL), BGK, positivity limiter.
+// One kernel evaluates  out = ca*ua + cb*u + cdt*L(u)  for every cell: the element's
+// nsp-point block lives in registers, the neighbour traces are recomputed from the
+// neighbour's block (L1/L2 hits), so a stage is one pass over HBM.
+//
+// Reference semantics: src/Equation/eq_advection.jl:55-175 + eq_scalar.jl:1-12,
+// example/advection_lowlevel.jl:4-47, src/Equation/eq_euler.jl:29-98,
+// example/bgk_wave.jl:69-129, src/dissipation.jl:61-123.
+#include "frb_internal.cuh"
+#include "frb_physics.cuh"
+
+namespace {
+
+// The 1-D problems are latency-bound (a few hundred KB of state), so these kernels keep
+// the reference's literal operation order -- sequential dot products, true divisions --
+// and this file is compiled with -fmad=false: the residual then agrees with the CPU
+// restatement to the last bit or two, which matters for the ill-conditioned wave-speed
+// quotient au = df/(du + 1e-8) of eq_advection.jl:130.
+template <int NSP>
+__device__ __forceinline__ double dotn(const double *a, const double *l) {
+  double s = a[0] * l[0];
+#pragma unroll
+  for (int q = 1; q < NSP; ++q) s = s + a[q] * l[q];
+  return s;
+}
+
+__device__ __forceinline__ double stage_out(const FrbStage &st, const double *ua, size_t idx,
+                                            double u, double du) {
+  if (st.rhs_only) return du;
+  double r = st.nested ? st.cb * (u + st.cdt * du) : st.cb * u + st.cdt * du;
+  if (st.use_a) r = st.ca * ua[idx] + r;
+  return r;
+}
+
+// [KB] conserve_prim / euler_flux / flux_hll! in the reference's operation order
+__device__ __forceinline__ double lambda3(double w0, double w1, double w2, double gamma) {
+  return 0.5 * w0 / (gamma - 1.0) / (w2 - 0.5 * (w1 * w1) / w0);
+}
+__device__ __forceinline__ frb::Flux3 flux3_lit(double w0, double w1, double w2, double gamma) {
+  double lam = lambda3(w0, w1, w2, gamma);
+  double p = 0.5 * w0 / lam;
+  return {w1, (w1 * w1) / w0 + p, (w2 + p) * w1 / w0};
+}
+__device__ __forceinline__ frb::Flux3 hll3_lit(double l0, double l1, double l2, double r0, double r1,
+                                               double r2, double gamma) {
+  double lamL = lambda3(l0, l1, l2, gamma), lamR = lambda3(r0, r1, r2, gamma);
+  double aL = sqrt(0.5 * gamma / lamL), aR = sqrt(0.5 * gamma / lamR);
+  double lmin = l1 / l0 - aL, lmax = r1 / r0 + aR;
+  frb::Flux3 f1 = flux3_lit(l0, l1, l2, gamma), f2 = flux3_lit(r0, r1, r2, gamma);
+  if (lmin >= 0.0) return f1;
+  if (lmax <= 0.0) return f2;
+  double fac = 1.0 / (lmax - lmin), mm = lmax * lmin;
+  return {fac * (lmax * f1.f0 - lmin * f2.f0 + mm * (r0 - l0)),
+          fac * (lmax * f1.f1 - lmin * f2.f1 + mm * (r1 - l1)),
+          fac * (lmax * f1.f2 - lmin * f2.f2 + mm * (r2 - l2))};
+}
+
+// ---------------------------------------------------------------- advection ----
+template <int NSP>
+__global__ void __launch_bounds__(128)
+adv1d_kernel(const double *__restrict__ u, const double *__restrict__ ua, double *__restrict__ out,
+             const double *__restrict__ J, int ncell, double a, int bc, double eps_seam,
+             FrbOps ops, FrbStage st) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= ncell) return;
+  const bool periodic = bc == FRB_BC_PERIOD;
+  int im = i == 0 ? ncell - 1 : i - 1;
+  int ip = i == ncell - 1 ? 0 : i + 1;
+  double uc[NSP], f[NSP], um[NSP], up[NSP], fm[NSP], fp[NSP];
+  double Jc = J[i], Jm = J[im], Jp = J[ip];
+#pragma unroll
+  for (int q = 0; q < NSP; ++q) {
+    uc[q] = u[i + (size_t)ncell * q];
+    um[q] = u[im + (size_t)ncell * q];
+    up[q] = u[ip + (size_t)ncell * q];
+    f[q] = a * uc[q] / Jc;   // advection_dflux!  eq_advection.jl:103-111
+    fm[q] = a * um[q] / Jm;
+    fp[q] = a * up[q] / Jp;
+  }
+  double uL = dotn<NSP>(uc, ops.ll), uR = dotn<NSP>(uc, ops.lr);
+  double fL = dotn<NSP>(f, ops.ll), fR = dotn<NSP>(f, ops.lr);
+  double uRm = dotn<NSP>(um, ops.lr), fRm = dotn<NSP>(fm, ops.lr);
+  double uLp = dotn<NSP>(up, ops.ll), fLp = dotn<NSP>(fp, ops.ll);
+  // interface fluxes: advection_iflux! :128-137, seam period_advection! :163-166
+  double e0 = (i == 0) ? eps_seam : 1e-8;
+  double e1 = (i == ncell - 1) ? eps_seam : 1e-8;
+  double au0 = (fL - fRm) / (uL - uRm + e0);
+  double fi0 = 0.5 * (fL + fRm) - 0.5 * fabs(au0) * (uL - uRm);
+  double au1 = (fLp - fR) / (uLp - uR + e1);
+  double fi1 = 0.5 * (fLp + fR) - 0.5 * fabs(au1) * (uLp - uR);
+  const bool frozen = !periodic && (i == 0 || i == ncell - 1);  // dirichlet_advection! :153-156
+#pragma unroll
+  for (int p = 0; p < NSP; ++p) {
+    double rhs1 = dotn<NSP>(f, &ops.lpdm[p * FRB_NSPMAX]);
+    double du = -(rhs1 + (fi0 - fL) * ops.dgl[p] + (fi1 - fR) * ops.dgr[p]);  // eq_scalar.jl:4-8
+    if (frozen) du = 0.0;
+    size_t idx = i + (size_t)ncell * p;
+    out[idx] = stage_out(st, ua, idx, uc[p], du);
+  }
+}
+
+// -------------------------------------------------------------------- Euler ----
+template <int NSP>
+__device__ __forceinline__ void load_cell3(const double *__restrict__ u, int i, int ncell,
+                                           double (&w)[3][NSP]) {
+#pragma unroll
+  for (int k = 0; k < 3; ++k)
+#pragma unroll
+    for (int q = 0; q < NSP; ++q) w[k][q] = u[i + (size_t)ncell * (q + NSP * k)];
+}
+
+template <int NSP>
+__global__ void __launch_bounds__(128)
+euler1d_kernel(const double *__restrict__ u, const double *__restrict__ ua,
+               double *__restrict__ out, const double *__restrict__ J, int ncell, double gamma,
+               int bc, FrbOps ops, FrbStage st) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= ncell) return;
+  const bool periodic = bc == FRB_BC_PERIOD;
+  int im = i == 0 ? ncell - 1 : i - 1;
+  int ip = i == ncell - 1 ? 0 : i + 1;
+  double w[3][NSP], wm[3][NSP], wp[3][NSP], f[3][NSP];
+  load_cell3<NSP>(u, i, ncell, w);
+  load_cell3<NSP>(u, im, ncell, wm);
+  load_cell3<NSP>(u, ip, ncell, wp);
+  const double Jc = J[i];
+#pragma unroll
+  for (int q = 0; q < NSP; ++q) {  // eq_euler.jl:35-39
+    frb::Flux3 F = flux3_lit(w[0][q], w[1][q], w[2][q], gamma);
+    f[0][q] = F.f0 / Jc; f[1][q] = F.f1 / Jc; f[2][q] = F.f2 / Jc;
+  }
+  double uL[3], uR[3], fL[3], fR[3], uRm[3], uLp[3];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {  // :41-49
+    uL[k] = dotn<NSP>(w[k], ops.ll); uR[k] = dotn<NSP>(w[k], ops.lr);
+    fL[k] = dotn<NSP>(f[k], ops.ll); fR[k] = dotn<NSP>(f[k], ops.lr);
+    uRm[k] = dotn<NSP>(wm[k], ops.lr); uLp[k] = dotn<NSP>(wp[k], ops.ll);
+  }
+  // :51-54 (interior faces) and :86-89 (periodic seam): HLL with dt = 1
+  frb::Flux3 h0 = hll3_lit(uRm[0], uRm[1], uRm[2], uL[0], uL[1], uL[2], gamma);
+  frb::Flux3 h1 = hll3_lit(uR[0], uR[1], uR[2], uLp[0], uLp[1], uLp[2], gamma);
+  double fi0[3] = {h0.f0, h0.f1, h0.f2}, fi1[3] = {h1.f0, h1.f1, h1.f2};
+  const bool frozen = !periodic && (i == 0 || i == ncell - 1);  // dirichlet_euler! :75-78
+#pragma unroll
+  for (int k = 0; k < 3; ++k)
+#pragma unroll
+    for (int p = 0; p < NSP; ++p) {
+      double rhs1 = dotn<NSP>(f[k], &ops.lpdm[p * FRB_NSPMAX]);  // :56-58
+      double du = -(rhs1 + (fi0[k] / Jc - fL[k]) * ops.dgl[p] + (fi1[k] / Jc - fR[k]) * ops.dgr[p]);
+      if (frozen) du = 0.0;
+      size_t idx = i + (size_t)ncell * (p + NSP * k);
+      out[idx] = stage_out(st, ua, idx, w[k][p], du);
+    }
+}
+
+// positive_limiter(u::Matrix, gamma, weights, ll, lr)  dissipation.jl:61-123, density branch.
+template <int NSP>
+__global__ void __launch_bounds__(128)
+limiter1d_kernel(double *__restrict__ u, int ncell, double gamma, const double *__restrict__ wts,
+                 FrbOps ops, int *__restrict__ nbad) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= ncell) return;
+  double w[3][NSP];
+  load_cell3<NSP>(u, i, ncell, w);
+  double um[3];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    double s = 0.0;
+#pragma unroll
+    for (int q = 0; q < NSP; ++q) s += w[k][q] * wts[q];  // :71 (mean not normalised)
+    um[k] = s;
+  }
+  double lam = 0.5 * um[0] / (gamma - 1.0) / (um[2] - 0.5 * um[1] * um[1] / um[0]);
+  double p_mean = 0.5 * um[0] * (1.0 / lam);
+  double rl = dotn<NSP>(w[0], ops.ll), rr = dotn<NSP>(w[0], ops.lr);
+  double eps = fmin(fmin(1e-13, um[0]), p_mean);  // :81
+  double rmin = fmin(rl, rr);
+#pragma unroll
+  for (int q = 0; q < NSP; ++q) rmin = fmin(rmin, w[0][q]);
+  double t1 = fmin((um[0] - eps) / (um[0] - rmin + 1e-8), 1.0);  // :83
+  if (!(t1 > 0.0 && t1 <= 1.0)) atomicAdd(nbad, 1);              // :84 @assert
+#pragma unroll
+  for (int q = 0; q < NSP; ++q) u[i + (size_t)ncell * q] = t1 * (w[0][q] - um[0]) + um[0];
+}
+
+// dirichlet cells of the stage buffers are never written by L(u)=0 updates when the
+// stage is rhs_only; nothing to do here (kept for symmetry with the 2-D ring copy).
+
+// ---------------------------------------------------------------------- BGK ----
+// moments_conserve + conserve_prim(w, 3.0): bgk_wave.jl:77-79.  prim[ncell, nsp, 3].
+__global__ void __launch_bounds__(128)
+bgk_moments_kernel(const double *__restrict__ u, double *__restrict__ prim, int ncell, int nu,
+                   int nsp, const double *__restrict__ velo, const double *__restrict__ wts) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  int k = blockIdx.y;
+  if (i >= ncell) return;
+  const double *p = u + i + (size_t)ncell * nu * k;
+  double w0 = 0.0, w1 = 0.0, w2 = 0.0;
+  for (int j = 0; j < nu; ++j) {
+    double f = p[(size_t)ncell * j];
+    double v = velo[j], wt = wts[j];
+    w0 += wt * f;
+    w1 += wt * v * f;
+    w2 += wt * (v * v) * f;
+  }
+  w2 *= 0.5;
+  double lam = 0.5 * w0 / (3.0 - 1.0) / (w2 - 0.5 * w1 * w1 / w0);
+  size_t o = i + (size_t)ncell * k;
+  prim[o] = w0;
+  prim[o + (size_t)ncell * nsp] = w1 / w0;
+  prim[o + 2 * (size_t)ncell * nsp] = lam;
+}
+
+template <int NSP>
+__global__ void __launch_bounds__(128)
+bgk1d_kernel(const double *__restrict__ u, const double *__restrict__ ua, double *__restrict__ out,
+             const double *__restrict__ prim, const double *__restrict__ dx,
+             const double *__restrict__ velo, int ncell, int nu, double tau, FrbOps ops,
+             FrbStage st) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  int j = blockIdx.y;
+  if (i >= ncell) return;
+  const double v = velo[j];
+  const double delta = v >= 0.0 ? 1.0 : 0.0;  // heaviside, bgk_wave.jl:26
+  const size_t vs = (size_t)ncell * nu;
+  int im = i == 0 ? ncell - 1 : i - 1;  // f2e / e2f periodic tables :42-67
+  int ip = i == ncell - 1 ? 0 : i + 1;
+  double uc[NSP], f[NSP], fn[NSP];
+  const double Jc = 0.5 * dx[i];
+  // only the upwind neighbour contributes: left cell for v >= 0, right cell otherwise
+  const int in = v >= 0.0 ? im : ip;
+  const double Jn = 0.5 * dx[in];
+#pragma unroll
+  for (int q = 0; q < NSP; ++q) {
+    uc[q] = u[i + (size_t)ncell * j + vs * q];
+    f[q] = v * uc[q] / Jc;  // :85-88
+    fn[q] = v * u[in + (size_t)ncell * j + vs * q] / Jn;
+  }
+  double fL = dotn<NSP>(f, ops.ll), fR = dotn<NSP>(f, ops.lr);  // interp_face! :99-101
+  double fi0, fi1;  // f_interaction at the left / right face of cell i  (:103-107)
+  if (v >= 0.0) {
+    double fRm = dotn<NSP>(fn, ops.lr);
+    fi0 = fL * (1.0 - delta) + fRm * delta;
+    fi1 = 0.0 * (1.0 - delta) + fR * delta;
+  } else {
+    double fLp = dotn<NSP>(fn, ops.ll);
+    fi0 = fL * (1.0 - delta) + 0.0 * delta;
+    fi1 = fLp * (1.0 - delta) + fR * delta;
+  }
+#pragma unroll
+  for (int p = 0; p < NSP; ++p) {
+    size_t po = i + (size_t)ncell * p;
+    double rho = prim[po], U = prim[po + (size_t)ncell * NSP], lam = prim[po + 2 * (size_t)ncell * NSP];
+    double c = v - U;
+    double M = rho * sqrt(lam / 3.14159265358979323846) * exp(-lam * (c * c));  // maxwellian
+    double rhs1 = dotn<NSP>(f, &ops.lpdm[p * FRB_NSPMAX]);  // poly_derivative! :114-116
+    double du = -(rhs1 + (fi0 - fL) * ops.dgl[p] + (fi1 - fR) * ops.dgr[p]) + (M - uc[p]) / tau;
+    size_t idx = i + (size_t)ncell * j + vs * p;
+    out[idx] = stage_out(st, ua, idx, uc[p], du);
+  }
+}
+
+}  // namespace
+
+#define FRB_NSP_SWITCH(nsp, CALL)                       \
+  switch (nsp) {                                        \
+    case 2: { constexpr int N = 2; CALL; } break;       \
+    case 3: { constexpr int N = 3; CALL; } break;       \
+    case 4: { constexpr int N = 4; CALL; } break;       \
+    case 5: { constexpr int N = 5; CALL; } break;       \
+    case 6: { constexpr int N = 6; CALL; } break;       \
+    case 7: { constexpr int N = 7; CALL; } break;       \
+    case 8: { constexpr int N = 8; CALL; } break;       \
+    default: frb_set_error("unsupported polynomial degree"); return FRB_ERR_ARG; \
+  }
+
+static int check_launch(const char *what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return frb_cuda_fail(e, what, __FILE__, __LINE__);
+  return 0;
+}
+
+int frb_launch_adv1d(frb_prob_t p, const double *u, const double *ua, double *out, FrbStage st) {
+  dim3 blk(128), grd((p->ncell + 127) / 128);
+  double eps = p->variant == FRB_ADV_LOWLEVEL ? 1e-8 : 1e-6;
+  int bc = p->variant == FRB_ADV_LOWLEVEL ? FRB_BC_PERIOD : p->bc;
+  FRB_NSP_SWITCH(p->nsp, (adv1d_kernel<N><<<grd, blk, 0, p->ctx->stream>>>(
+                             u, ua, out, p->J, p->ncell, p->a, bc, eps, p->ops, st)));
+  if (int rc = check_launch("adv1d_kernel")) return rc;
+  return 1;
+}
+
+int frb_launch_euler1d(frb_prob_t p, const double *u, const double *ua, double *out, FrbStage st) {
+  dim3 blk(128), grd((p->ncell + 127) / 128);
+  FRB_NSP_SWITCH(p->nsp, (euler1d_kernel<N><<<grd, blk, 0, p->ctx->stream>>>(
+                             u, ua, out, p->J, p->ncell, p->gamma, p->bc, p->ops, st)));
+  if (int rc = check_launch("euler1d_kernel")) return rc;
+  return 1;
+}
+
+int frb_launch_limiter1d(frb_prob_t p, double *u) {
+  dim3 blk(128), grd((p->ncell + 127) / 128);
+  FRB_NSP_SWITCH(p->nsp, (limiter1d_kernel<N><<<grd, blk, 0, p->ctx->stream>>>(
+                             u, p->ncell, p->gamma, p->lim_w, p->ops, p->flag)));
+  if (int rc = check_launch("limiter1d_kernel")) return rc;
+  return 1;
+}
+
+int frb_launch_bgk1d(frb_prob_t p, const double *u, const double *ua, double *out, FrbStage st) {
+  dim3 blk(128), g1((p->ncell + 127) / 128, p->nsp), g2((p->ncell + 127) / 128, p->nu);
+  bgk_moments_kernel<<<g1, blk, 0, p->ctx->stream>>>(u, p->prim, p->ncell, p->nu, p->nsp, p->velo,
+                                                     p->weights);
+  if (int rc = check_launch("bgk_moments_kernel")) return rc;
+  FRB_NSP_SWITCH(p->nsp, (bgk1d_kernel<N><<<g2, blk, 0, p->ctx->stream>>>(
+                             u, ua, out, p->prim, p->J, p->velo, p->ncell, p->nu, p->tau, p->ops, st)));
+  if (int rc = check_launch("bgk1d_kernel")) return rc;
+  return 2;
+}
+
+int frb_launch_dirichlet_copy1d(frb_prob_t, const double *, double *) { return 0; }

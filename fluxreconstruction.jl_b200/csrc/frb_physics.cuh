@@ -1,0 +1,87 @@
+// Pointwise physics closures (device).  These restate what the reference calls in
+// KitBase.jl on the hot path: euler_flux (eq_euler.jl:37,
+// euler2d_wave.jl:46), flux_hll! (eq_euler.jl:53; euler2d_wave.jl:73,80),
+// local_frame/global_frame (euler2d_wave.jl:78-81), conserve_prim, maxwellian.
+// Algebra is arranged for the FP64 pipe: one reciprocal and one square root per state.
+#pragma once
+#include <cuda_runtime.h>
+
+namespace frb {
+
+// 1-D Euler: w = (rho, rho*u, E).  Returns F(w); also u and a (sound speed) if wanted.
+struct Flux3 {
+  double f0, f1, f2;
+};
+__device__ __forceinline__ Flux3 euler_flux3(double w0, double w1, double w2, double gm1) {
+  double r = 1.0 / w0;
+  double v = w1 * r;
+  double p = gm1 * (w2 - 0.5 * w1 * v);
+  return {w1, fma(w1, v, p), (w2 + p) * v};
+}
+
+// flux_hll!(fw, wL, wR, gamma, 1.0), 3 components
+__device__ __forceinline__ Flux3 hll3(double l0, double l1, double l2, double r0, double r1,
+                                      double r2, double gamma) {
+  const double gm1 = gamma - 1.0;
+  double il = 1.0 / l0, ir = 1.0 / r0;
+  double ul = l1 * il, ur = r1 * ir;
+  double pl = gm1 * (l2 - 0.5 * l1 * ul), pr = gm1 * (r2 - 0.5 * r1 * ur);
+  double al = sqrt(gamma * pl * il), ar = sqrt(gamma * pr * ir);
+  double lmin = ul - al, lmax = ur + ar;
+  double fl0 = l1, fl1 = fma(l1, ul, pl), fl2 = (l2 + pl) * ul;
+  double fr0 = r1, fr1 = fma(r1, ur, pr), fr2 = (r2 + pr) * ur;
+  if (lmin >= 0.0) return {fl0, fl1, fl2};
+  if (lmax <= 0.0) return {fr0, fr1, fr2};
+  double fac = 1.0 / (lmax - lmin), mm = lmax * lmin;
+  return {fac * (lmax * fl0 - lmin * fr0 + mm * (r0 - l0)),
+          fac * (lmax * fl1 - lmin * fr1 + mm * (r1 - l1)),
+          fac * (lmax * fl2 - lmin * fr2 + mm * (r2 - l2))};
+}
+
+// 2-D Euler: w = (rho, rho*u, rho*v, E)
+struct Flux4 {
+  double f0, f1, f2, f3;
+};
+
+// F and G at a point: euler_flux(w, gamma) -> (F, G)
+__device__ __forceinline__ void euler_flux4(double w0, double w1, double w2, double w3, double gm1,
+                                            Flux4 &F, Flux4 &G) {
+  double r = 1.0 / w0;
+  double u = w1 * r, v = w2 * r;
+  double p = gm1 * (w3 - 0.5 * fma(w1, u, w2 * v));
+  double h = w3 + p;
+  F = {w1, fma(w1, u, p), w1 * v, h * u};
+  G = {w2, w2 * u, fma(w2, v, p), h * v};
+}
+
+// HLL flux normal to an x-face: states in the global frame, normal velocity = component 1.
+__device__ __forceinline__ Flux4 hll4(double l0, double l1, double l2, double l3, double r0,
+                                      double r1, double r2, double r3, double gamma) {
+  const double gm1 = gamma - 1.0;
+  double il = 1.0 / l0, ir = 1.0 / r0;
+  double ul = l1 * il, vl = l2 * il, ur = r1 * ir, vr = r2 * ir;
+  double pl = gm1 * (l3 - 0.5 * fma(l1, ul, l2 * vl));
+  double pr = gm1 * (r3 - 0.5 * fma(r1, ur, r2 * vr));
+  double al = sqrt(gamma * pl * il), ar = sqrt(gamma * pr * ir);
+  double lmin = ul - al, lmax = ur + ar;
+  double fl0 = l1, fl1 = fma(l1, ul, pl), fl2 = l1 * vl, fl3 = (l3 + pl) * ul;
+  double fr0 = r1, fr1 = fma(r1, ur, pr), fr2 = r1 * vr, fr3 = (r3 + pr) * ur;
+  if (lmin >= 0.0) return {fl0, fl1, fl2, fl3};
+  if (lmax <= 0.0) return {fr0, fr1, fr2, fr3};
+  double fac = 1.0 / (lmax - lmin), mm = lmax * lmin;
+  return {fac * (lmax * fl0 - lmin * fr0 + mm * (r0 - l0)),
+          fac * (lmax * fl1 - lmin * fr1 + mm * (r1 - l1)),
+          fac * (lmax * fl2 - lmin * fr2 + mm * (r2 - l2)),
+          fac * (lmax * fl3 - lmin * fr3 + mm * (r3 - l3))};
+}
+
+// HLL flux normal to a y-face, i.e. global_frame(flux_hll!(local_frame(wL,0,1),
+// local_frame(wR,0,1)), 0, 1) of euler2d_wave.jl:76-82: local = (w0, w2, -w1, w3),
+// global(f) = (f0, -f2, f1, f3).
+__device__ __forceinline__ Flux4 hll4_y(double l0, double l1, double l2, double l3, double r0,
+                                        double r1, double r2, double r3, double gamma) {
+  Flux4 f = hll4(l0, l2, -l1, l3, r0, r2, -r1, r3, gamma);
+  return {f.f0, -f.f2, f.f1, f.f3};
+}
+
+}  // namespace frb

@@ -1,0 +1,284 @@
+"""Host-side mirror of the reference's problem constructors and of the SciML driving
+interface, bound to libfrb200 through its C ABI.
+
+Reference API                                   here
+------------------------------------------------------------------------------------------
+FRAdvectionProblem(u, tspan, ps, a, bc)         FRAdvectionProblem(u, tspan, ps, a, bc)
+  src/Equation/eq_advection.jl:1-26
+FREulerProblem(u, tspan, ps, γ, bc)             FREulerProblem(u, tspan, ps, gamma, bc)
+  src/Equation/eq_euler.jl:1-27
+ODEProblem(dudt!, u0, tspan, p) of              Euler2DProblem(u0, tspan, ps, gamma)
+  example/euler2d_wave.jl:35-122
+ODEProblem(mol!, f0, tspan, p) of               BGKProblem(f0, tspan, ps, velo, weights, tau)
+  example/bgk_wave.jl:69-132
+prob.f(du, u, p, t)                             prob.f(du, u, p, t)      (host arrays in/out)
+init(prob, Midpoint(); adaptive=false, dt)      init(prob, Midpoint(), dt=dt)
+step!(itg); itg.u                               step_(itg); itg.u
+solve(prob, alg; adaptive=false, dt)            solve(prob, alg, dt=dt)
+positive_limiter(u, γ, weights, ll, lr)         itg.set_hooks(limiter_weights=...) / prob.limiter(...)
+
+Boundary symbols are the reference's: ``:dirichlet`` and ``:period`` (strings, with or
+without the leading colon).  State arrays are float64 in the reference's index order and
+Fortran (Julia) memory layout, ghost cells included where the reference has them.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import Context, check, fortran_ptr, lib, make_operators
+
+BC = {"dirichlet": 0, "period": 1}
+GHOST = {None: -1, "none": -1, "wave_x": 0, "wave_y": 1, "copy": 2}
+KERNEL = {"auto": 0, "generic": 1, "march": 2}
+
+
+class Euler:
+    code = 0
+    stages = 1
+
+
+class Midpoint:
+    code = 1
+    stages = 2
+
+
+class SSPRK33:
+    """Shu-Osher three-stage SSP scheme (OrdinaryDiffEq's SSPRK33); not used by the reference's
+    scripts but named by the north star."""
+
+    code = 2
+    stages = 3
+
+
+def _sym(s):
+    return str(s).lstrip(":")
+
+
+class _Problem:
+    """Common part: owns the library handle; f!(du,u,p,t); device-resident stepping."""
+
+    def __init__(self, u0, tspan, ctx=None):
+        self.ctx = ctx or Context.default()
+        self.u0 = np.array(u0, dtype=np.float64, order="F", copy=True)
+        self.tspan = (float(tspan[0]), float(tspan[1]))
+        self.h = C.c_void_p()
+        self._keep = []
+        self.p = None  # the reference passes a parameter tuple; kept for signature parity
+
+    # -- lifetime ---------------------------------------------------------------------
+    def close(self):
+        if self.h:
+            lib().frb_prob_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- sizes ------------------------------------------------------------------------
+    @property
+    def state_len(self):
+        return lib().frb_state_len(self.h)
+
+    @property
+    def dofs(self):
+        return lib().frb_interior_dofs(self.h)
+
+    # -- f!(du, u, p, t) ----------------------------------------------------------------
+    def f(self, du, u, p=None, t=0.0):
+        """The SciML in-place RHS with host arrays: uploads u, evaluates on the GPU,
+        downloads du.  Returns None like the reference."""
+        if u.shape != self.u0.shape or du.shape != self.u0.shape:
+            raise ValueError("f!: array shape does not match the problem")
+        check(lib().frb_rhs(self.h, fortran_ptr(u), fortran_ptr(du), float(t)))
+        return None
+
+    def rhs_resident(self):
+        """L(u) of the resident state, left on the device (timing / chaining)."""
+        check(lib().frb_rhs(self.h, None, None, 0.0))
+
+    # -- state --------------------------------------------------------------------------
+    def upload(self, u):
+        if u.shape != self.u0.shape:
+            raise ValueError("upload: array shape does not match the problem")
+        check(lib().frb_state_upload(self.h, fortran_ptr(np.asfortranarray(u, dtype=np.float64))))
+
+    def download(self, out=None):
+        if out is None:
+            out = np.empty(self.u0.shape, dtype=np.float64, order="F")
+        check(lib().frb_state_download(self.h, fortran_ptr(out)))
+        return out
+
+    def device_ptr(self) -> int:
+        p = C.c_void_p()
+        check(lib().frb_state_device_ptr(self.h, C.byref(p)))
+        return p.value
+
+    # -- hooks / stepping -----------------------------------------------------------------
+    def set_hooks(self, ghost=None, limiter_weights=None):
+        w = None
+        if limiter_weights is not None:
+            w = np.asfortranarray(limiter_weights, dtype=np.float64)
+        check(lib().frb_set_step_hooks(self.h, GHOST[ghost], None if w is None else _lib.dptr(w.ravel(order="F"))))
+
+    def step(self, alg, dt, nsteps=1):
+        check(lib().frb_step(self.h, alg.code, float(dt), int(nsteps)))
+
+    def ghost_fill(self, mode):
+        check(lib().frb_ghost_fill(self.h, GHOST[mode]))
+
+    def limiter(self, weights):
+        """positive_limiter on every interior cell of the resident state; raises on the
+        reference's @assert condition."""
+        w = np.asfortranarray(weights, dtype=np.float64).ravel(order="F")
+        nbad = C.c_int32()
+        check(lib().frb_limiter_positivity(self.h, _lib.dptr(w), C.byref(nbad)))
+        return nbad.value
+
+    def set_kernel(self, kind="auto"):
+        check(lib().frb_set_kernel(self.h, KERNEL[kind]))
+
+    # -- measurement ------------------------------------------------------------------------
+    def time_stage(self, stage_kind=1, iters=10) -> float:
+        ms = C.c_float()
+        check(lib().frb_time_stage(self.h, int(stage_kind), int(iters), C.byref(ms)))
+        return ms.value
+
+    def last_timing(self):
+        ms, n = C.c_float(), C.c_int64()
+        check(lib().frb_last_timing(self.h, C.byref(ms), C.byref(n)))
+        return ms.value, n.value
+
+
+def _ops_of(ps, slopes=False):
+    return make_operators(ps.deg, ps.ll, ps.lr, ps.dl, ps.dhl, ps.dhr, ps.dll if slopes else None,
+                          ps.dlr if slopes else None)
+
+
+class FRAdvectionProblem(_Problem):
+    """src/Equation/eq_advection.jl:1-26; RHS frode_advection! :55-77.  u[ncell, nsp].
+    variant="lowlevel" reproduces example/advection_lowlevel.jl:4-47 (periodic, 1e-8 seam)."""
+
+    def __init__(self, u, tspan, ps, a, bc, variant="packaged", ctx=None):
+        super().__init__(u, tspan, ctx)
+        ncell, nsp = self.u0.shape
+        if nsp != ps.deg + 1:
+            raise ValueError("u must be [ncell, deg+1]")
+        ops, self._keep = _ops_of(ps)
+        J = np.ascontiguousarray(ps.interior(ps.J) if ncell == ps.nx else ps.J, dtype=np.float64)
+        self._keep.append(J)
+        check(lib().frb_advection1d_create(self.ctx.h, ncell, C.byref(ops), _lib.dptr(J), float(a), BC[_sym(bc)],
+                                           1 if variant == "lowlevel" else 0, C.byref(self.h)))
+        self.upload(self.u0)
+
+
+class FREulerProblem(_Problem):
+    """src/Equation/eq_euler.jl:1-27; RHS frode_euler! :29-98.  u[ncell, nsp, 3]."""
+
+    def __init__(self, u, tspan, ps, gamma, bc, ctx=None):
+        super().__init__(u, tspan, ctx)
+        ncell, nsp, nv = self.u0.shape
+        if nsp != ps.deg + 1 or nv != 3:
+            raise ValueError("u must be [ncell, deg+1, 3]")
+        self.gamma = float(gamma)
+        ops, self._keep = _ops_of(ps)
+        J = np.ascontiguousarray(ps.interior(ps.J) if ncell == ps.nx else ps.J, dtype=np.float64)
+        self._keep.append(J)
+        check(lib().frb_euler1d_create(self.ctx.h, ncell, C.byref(ops), _lib.dptr(J), self.gamma, BC[_sym(bc)],
+                                       C.byref(self.h)))
+        self.upload(self.u0)
+
+
+class Euler2DProblem(_Problem):
+    """ODEProblem(dudt!, u0, tspan, p) of example/euler2d_wave.jl:35-122 on an FRPSpace2D with
+    one ghost ring.  u0[nx+2, ny+2, nsp, nsp, 4]."""
+
+    def __init__(self, u0, tspan, ps, gamma, ctx=None, kernel="auto"):
+        super().__init__(u0, tspan, ctx)
+        nsp = ps.deg + 1
+        if self.u0.shape != (ps.nx + 2, ps.ny + 2, nsp, nsp, 4):
+            raise ValueError("u0 must be [nx+2, ny+2, nsp, nsp, 4] (one ghost ring)")
+        self.gamma = float(gamma)
+        ops, self._keep = _ops_of(ps)
+        check(lib().frb_euler2d_create(self.ctx.h, ps.nx, ps.ny, C.byref(ops), ps.Jx, ps.Jy, self.gamma,
+                                       C.byref(self.h)))
+        if kernel != "auto":
+            self.set_kernel(kernel)
+        self.upload(self.u0)
+
+
+class BGKProblem(_Problem):
+    """ODEProblem(mol!, f0, tspan, p) of example/bgk_wave.jl:69-132.  f0[ncell, nu, nsp]."""
+
+    def __init__(self, f0, tspan, ps, velo, weights, tau=1e-2, ctx=None):
+        super().__init__(f0, tspan, ctx)
+        ncell, nu, nsp = self.u0.shape
+        if nsp != ps.deg + 1 or nu != len(velo):
+            raise ValueError("f0 must be [ncell, nu, deg+1]")
+        ops, self._keep = _ops_of(ps)
+        dx = np.ascontiguousarray(ps.interior(ps.dx), dtype=np.float64)
+        v = np.ascontiguousarray(velo, dtype=np.float64)
+        w = np.ascontiguousarray(weights, dtype=np.float64)
+        self._keep += [dx, v, w]
+        check(lib().frb_bgk1d_create(self.ctx.h, ncell, nu, C.byref(ops), _lib.dptr(dx), _lib.dptr(v), _lib.dptr(w),
+                                     float(tau), C.byref(self.h)))
+        self.upload(self.u0)
+
+
+class Integrator:
+    """What ``init(prob, alg; adaptive=false, dt)`` returns in the reference's scripts.
+
+    ``itg.u`` hands out a host copy of the state; because the reference's user code
+    mutates ``itg.u`` in place between steps (ghost fill, limiter, filters), a handed-out
+    array is uploaded again before the next step.  Code that wants the fast path leaves
+    ``itg.u`` alone and registers the per-step work with ``set_hooks``."""
+
+    def __init__(self, prob, alg, dt):
+        self.prob, self.alg, self.dt = prob, alg, float(dt)
+        self.t = prob.tspan[0]
+        self.iter = 0
+        self._host = None
+
+    @property
+    def u(self):
+        if self._host is None:
+            self._host = self.prob.download()
+        return self._host
+
+    def set_u(self, u):
+        self.prob.upload(u)
+        self._host = None
+
+    def set_hooks(self, ghost=None, limiter_weights=None):
+        self.prob.set_hooks(ghost, limiter_weights)
+
+    def step(self, nsteps=1):
+        if self._host is not None:
+            self.prob.upload(self._host)
+            self._host = None
+        self.prob.step(self.alg, self.dt, nsteps)
+        self.t += nsteps * self.dt
+        self.iter += nsteps
+
+
+def init(prob, alg, dt, adaptive=False, **_):
+    if adaptive:
+        raise NotImplementedError("only fixed-step integration is accelerated (SURVEY 0.1)")
+    return Integrator(prob, alg if not isinstance(alg, type) else alg(), dt)
+
+
+def step_(itg, nsteps=1):
+    """step!(itg)"""
+    itg.step(nsteps)
+
+
+def solve(prob, alg, dt, adaptive=False, **_):
+    itg = init(prob, alg, dt, adaptive)
+    n = int(round((prob.tspan[1] - prob.tspan[0]) / dt))
+    itg.step(n)
+    return itg

@@ -1,0 +1,172 @@
+/* frb200.h -- C ABI of libfrb200.so: a Blackwell (sm_100a) implementation of the
+ * FluxReconstruction.jl semi-discrete residual and explicit time step.
+ *
+ * The reference has NO foreign-function boundary on this path: it is pure Julia behind
+ * the SciML in-place right-hand side  f!(du, u, p, t)  (src/Equation/eq_euler.jl:29,
+ * src/Equation/eq_advection.jl:55, example/euler2d_wave.jl:35, example/bgk_wave.jl:69)
+ * driven by OrdinaryDiffEq init/step!/solve.  Each entry point below names the
+ * reference interface it stands in for; INTEGRATION.md shows the Julia `ccall` shim.
+ *
+ * Conventions
+ *  - every function returns an int32 status: 0 = ok, negative = error
+ *    (frb_last_error() holds the message; nothing throws, nothing calls exit);
+ *  - all arrays are Float64 in the reference's own memory layout: Julia column-major,
+ *    first index fastest, ghost cells included where the reference's array has them
+ *    (OffsetArray 0:nx+1 is passed as the plain parent array);
+ *  - host pointers are borrowed for the duration of the call only;
+ *  - operator arrays (ll, lr, lpdm, dgl, dgr) are inputs: FRPSpace1D/FRPSpace2D
+ *    (src/struct.jl:40-88,130-245) stay the single source of truth.  lpdm is the
+ *    reference's `ps.dl`, nsp x nsp column-major: element [m,k] at lpdm[m + nsp*k];
+ *  - there is no CPU fallback: without a CUDA device every compute call fails with
+ *    FRB_ERR_CUDA.
+ */
+#ifndef FRB200_H
+#define FRB200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FRB_OK 0
+#define FRB_ERR_ARG (-1)     /* bad argument / unsupported size */
+#define FRB_ERR_CUDA (-2)    /* CUDA runtime or driver error, or no device */
+#define FRB_ERR_STATE (-3)   /* call not valid for this problem kind / state */
+#define FRB_ERR_NUMERIC (-4) /* limiter parameter outside (0,1] (reference: @assert) */
+#define FRB_ERR_PEER (-5)    /* halo peer mapping / wait timeout */
+
+#define FRB_MAX_NSP 8
+
+typedef struct frb_ctx_s *frb_ctx_t;
+typedef struct frb_prob_s *frb_prob_t;
+
+/* eq_euler.jl:68-70 / eq_advection.jl:72-74: bc::Symbol -> :dirichlet | :period */
+enum { FRB_BC_DIRICHLET = 0, FRB_BC_PERIOD = 1 };
+/* OrdinaryDiffEq algorithms used by the reference at fixed dt:
+ * Euler() (ns_cavity.jl:380), Midpoint() (euler2d_wave.jl:123); SSPRK3 = Shu-Osher */
+enum { FRB_SCHEME_EULER = 0, FRB_SCHEME_MIDPOINT = 1, FRB_SCHEME_SSPRK3 = 2 };
+/* per-step ghost fill of the user loop: euler2d_wave.jl:127-132 (x wave),
+ * :159-164 (y wave), shock-vortex.jl:324-326 (copy) */
+enum { FRB_GHOST_NONE = -1, FRB_GHOST_WAVE_X = 0, FRB_GHOST_WAVE_Y = 1, FRB_GHOST_COPY = 2 };
+/* eq_advection.jl (seam epsilon 1e-6) vs example/advection_lowlevel.jl (1e-8) */
+enum { FRB_ADV_PACKAGED = 0, FRB_ADV_LOWLEVEL = 1 };
+/* 2-D Euler kernel selection: AUTO picks the fused row-marching TMA kernel when
+ * deg == 3, otherwise the generic per-element kernel */
+enum { FRB_KERNEL_AUTO = 0, FRB_KERNEL_GENERIC = 1, FRB_KERNEL_MARCH = 2 };
+
+/* the constant operator arrays of one FR space: ps.ll, ps.lr, ps.dl, ps.dhl, ps.dhr
+ * (struct.jl:49-51,63-64,182,193), plus ps.dll/ps.dlr (struct.jl:55-61, may be NULL
+ * unless the equation needs interface slopes) */
+typedef struct {
+  int32_t deg;
+  const double *ll, *lr, *lpdm, *dgl, *dgr, *dll, *dlr;
+} frb_operators;
+
+/* ---- context ------------------------------------------------------------------ */
+/* one context = one CUDA device + one stream; replaces nothing in the reference
+ * (Julia owns no device).  device < 0 selects the current device. */
+int32_t frb_ctx_create(int32_t device, frb_ctx_t *out);
+int32_t frb_ctx_destroy(frb_ctx_t ctx);
+/* message of the last failing call on this thread (ctx may be NULL) */
+const char *frb_last_error(frb_ctx_t ctx);
+/* library/ABI version, SM count and device name for logs */
+int32_t frb_device_info(frb_ctx_t ctx, int32_t *sm_count, int32_t *cc_major, int32_t *cc_minor,
+                        char *name, int32_t name_len);
+
+/* ---- problems: one per packaged/example RHS of the reference ------------------- */
+/* FRAdvectionProblem(u, tspan, ps, a, bc)  src/Equation/eq_advection.jl:1-26 and the
+ * rhs! of example/advection_lowlevel.jl:4-47.  State u[ncell, nsp]; J[ncell]. */
+int32_t frb_advection1d_create(frb_ctx_t ctx, int32_t ncell, const frb_operators *ops,
+                               const double *J, double a, int32_t bc, int32_t variant,
+                               frb_prob_t *out);
+/* FREulerProblem(u, tspan, ps, gamma, bc)  src/Equation/eq_euler.jl:1-27,
+ * RHS frode_euler! :29-98.  State u[ncell, nsp, 3]; J[ncell]. */
+int32_t frb_euler1d_create(frb_ctx_t ctx, int32_t ncell, const frb_operators *ops,
+                           const double *J, double gamma, int32_t bc, frb_prob_t *out);
+/* dudt! of example/euler2d_wave.jl:35-107 (== shock-vortex.jl:26-118) on the uniform
+ * rectangular FRPSpace2D with one ghost ring.  State u[nx+2, ny+2, nsp, nsp, 4];
+ * Jx = dx/2, Jy = dy/2 are the diagonal of ps.J[i,j][k,l] (geo_jacobi.jl:77-108). */
+int32_t frb_euler2d_create(frb_ctx_t ctx, int32_t nx, int32_t ny, const frb_operators *ops,
+                           double Jx, double Jy, double gamma, frb_prob_t *out);
+/* mol! of example/bgk_wave.jl:69-129 with its periodic e2f/f2e tables (:42-67).
+ * State u[ncell, nu, nsp]; dx[ncell]; velo, weights [nu] (VSpace1D). */
+int32_t frb_bgk1d_create(frb_ctx_t ctx, int32_t ncell, int32_t nu, const frb_operators *ops,
+                         const double *dx, const double *velo, const double *weights,
+                         double tau, frb_prob_t *out);
+/* dudt! + boundary! of example/ns_cavity.jl:147-344 (gas-kinetic flux, :49-145).
+ * State u[4, nsp, nsp, ny+2, nx+2] (variable fastest).  ops->dll/dlr required.
+ * gas = (K, gamma, mu_ref, omega); dt enters the time-averaged interface flux; lid_u is
+ * the wall speed pb[2] of :337; lambda_wall the wall 1/T of boundary!(u,p,1.0). */
+int32_t frb_ns2d_create(frb_ctx_t ctx, int32_t nx, int32_t ny, const frb_operators *ops,
+                        double Jx, double Jy, double inK, double gamma, double mu_ref,
+                        double omega, double dt, double lid_u, double lambda_wall,
+                        frb_prob_t *out);
+int32_t frb_prob_destroy(frb_prob_t prob);
+
+/* number of Float64 in the state array / of interior degrees of freedom */
+int64_t frb_state_len(frb_prob_t prob);
+int64_t frb_interior_dofs(frb_prob_t prob);
+
+/* ---- state movement (itg.u of the reference lives in host memory) --------------- */
+int32_t frb_state_upload(frb_prob_t prob, const double *u_host);
+int32_t frb_state_download(frb_prob_t prob, double *u_host);
+/* raw device address of the resident state (for zero-copy interop / peer mapping) */
+int32_t frb_state_device_ptr(frb_prob_t prob, double **dptr);
+
+/* ---- f!(du, u, p, t) ----------------------------------------------------------- */
+/* The SciML in-place RHS.  u_host == NULL evaluates the resident state; du_host ==
+ * NULL leaves du on the device.  With host pointers the call uploads u, evaluates
+ * and downloads du (H2D + D2H inside the call).  t is accepted for signature parity
+ * and unused (all reference RHS are autonomous). */
+int32_t frb_rhs(frb_prob_t prob, const double *u_host, double *du_host, double t);
+/* As frb_rhs with host pointers, but streams the 2-D state through the device in
+ * row slabs so that H2D, compute and D2H overlap (euler2d only). */
+int32_t frb_rhs_pipelined(frb_prob_t prob, const double *u_host, double *du_host, int32_t nslab);
+
+/* ---- step!(itg) ---------------------------------------------------------------- */
+/* what the user loop does around step! (euler2d_wave.jl:125-135, shock-vortex.jl:296-303):
+ * before every step, optionally positive_limiter (weights != NULL: nsp or nsp*nsp
+ * quadrature weights, already normalised as the callers do with ps.wp ./ 2 or ./ 4)
+ * and optionally a ghost fill.  Persisted on the problem. */
+int32_t frb_set_step_hooks(frb_prob_t prob, int32_t ghost_mode, const double *limiter_weights);
+/* nsteps fixed steps of the resident state, fused RHS + stage update kernels, no host
+ * synchronisation between steps.  Synchronous at return. */
+int32_t frb_step(frb_prob_t prob, int32_t scheme, double dt, int32_t nsteps);
+/* the hooks as stand-alone calls on the resident state */
+int32_t frb_ghost_fill(frb_prob_t prob, int32_t ghost_mode);
+/* positive_limiter(u, gamma, weights, ll, lr) src/dissipation.jl:61-123,125-206 on every
+ * interior cell; *nbad = cells whose parameter left (0,1] (reference: @assert) */
+int32_t frb_limiter_positivity(frb_prob_t prob, const double *weights, int32_t *nbad);
+
+/* ---- measurement (CUDA events on the library's own stream) ---------------------- */
+/* Launch `iters` back-to-back RK stages of kind `stage_kind` (0: u' = u + dt L(u), 16 B/DOF;
+ * 1: u' = a u_n + b u + c dt L(u), 24 B/DOF) on scratch buffers and return the mean
+ * device time per launch in milliseconds.  The state is not modified. */
+int32_t frb_time_stage(frb_prob_t prob, int32_t stage_kind, int32_t iters, float *ms_per_launch);
+/* device time of the last frb_step / frb_rhs call in milliseconds (events around the
+ * kernels only, excluding host<->device copies) and kernels launched by it */
+int32_t frb_last_timing(frb_prob_t prob, float *ms, int64_t *kernel_launches);
+int32_t frb_set_kernel(frb_prob_t prob, int32_t kernel_kind);
+
+/* ---- multi-GPU: element-slab partition along the slowest cell index ------------- */
+/* One process per GPU.  A rank's problem is created on its slab (2-D: ny_local rows,
+ * 1-D: ncell_local cells) and told its neighbours.  Halo rows are the neighbours'
+ * boundary rows of the *current* stage; they are written straight into the
+ * neighbour's memory by the stage kernel's epilogue over NVLink (peer mapping via
+ * CUDA IPC handles the host exchanges out of band), then a flag is raised.
+ * The reference has no distributed path: this is new surface. */
+#define FRB_IPC_HANDLE_BYTES 64
+/* export handles for this rank's halo mailbox; handle_out[FRB_IPC_HANDLE_BYTES] */
+int32_t frb_halo_export(frb_prob_t prob, unsigned char *handle_out);
+/* rank_lo / rank_hi: neighbour below / above (may be equal to self for a 1-rank ring:
+ * pass NULL handles then); periodic says whether the global seam wraps per stage or
+ * is a frozen ghost row */
+int32_t frb_halo_connect(frb_prob_t prob, int32_t rank, int32_t nranks,
+                         const unsigned char *handle_lo, const unsigned char *handle_hi);
+int32_t frb_halo_disconnect(frb_prob_t prob);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FRB200_H */

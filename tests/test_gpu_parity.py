@@ -1,0 +1,248 @@
+"""GPU parity: libfrb200 (through its C ABI) against the oracle on identical inputs.
+
+Tolerances (BASELINE.json north_star): <= 1e-12 relative per RHS evaluation, <= 1e-9 relative
+after 1000 steps.  "Relative" is the max-norm of the difference over the max-norm of the
+oracle result.
+"""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+RTOL_RHS = 1e-12
+RTOL_1000 = 1e-9
+GAMMA = 5.0 / 3.0
+
+
+def rel(a, b):
+    return np.abs(a - b).max() / max(np.abs(b).max(), 1e-300)
+
+
+def noisy(u, amp, seed):
+    rng = np.random.default_rng(seed)
+    return np.asfortranarray(u * (1.0 + amp * rng.standard_normal(u.shape)))
+
+
+# ---------------------------------------------------------------- config 1: 1-D advection
+@pytest.mark.parametrize("deg", [1, 2, 3, 5, 7])
+@pytest.mark.parametrize("bc,variant", [("period", "packaged"), ("dirichlet", "packaged"), ("period", "lowlevel")])
+def test_advection_rhs(FR, oracle, deg, bc, variant):
+    ps = FR.FRPSpace1D(-1.0, 1.0, 100, deg)
+    u = noisy(oracle.ic_advection1d(ps) + 0.3, 0.05, 7)
+    prob = FR.FRAdvectionProblem(u, (0.0, 2.0), ps, 1.0, bc, variant=variant)
+    du = np.zeros_like(u, order="F")
+    prob.f(du, u, None, 0.0)
+    ref = oracle.rhs_advection1d(u, ps, 1.0, bc, variant)
+    assert rel(du, ref) <= RTOL_RHS
+    prob.close()
+
+
+@pytest.mark.parametrize("scheme", ["euler", "midpoint", "ssprk3"])
+def test_advection_1000_steps(FR, oracle, coracle, scheme):
+    ps = FR.FRPSpace1D(-1.0, 1.0, 100, 2)
+    u0 = oracle.ic_advection1d(ps)
+    dt = 0.05 * 0.02
+    alg = {"euler": FR.Euler, "midpoint": FR.Midpoint, "ssprk3": FR.SSPRK33}[scheme]
+    prob = FR.FRAdvectionProblem(u0, (0.0, 1.0), ps, 1.0, "period", variant="lowlevel")
+    itg = FR.init(prob, alg(), dt=dt)
+    FR.step_(itg, 1000)
+    ref = coracle.integrate_advection1d(u0, ps, 1.0, "period", "lowlevel", dt, 1000, scheme)
+    assert rel(itg.u, ref) <= RTOL_1000
+    prob.close()
+
+
+# ---------------------------------------------------------------- config 2: 1-D Euler
+@pytest.mark.parametrize("deg", [1, 2, 3, 4, 7])
+@pytest.mark.parametrize("bc", ["dirichlet", "period"])
+def test_euler1d_rhs(FR, oracle, deg, bc):
+    ps = FR.FRPSpace1D(0.0, 1.0, 96, deg)
+    u = noisy(oracle.ic_sod1d(ps, GAMMA), 0.02, 11)
+    prob = FR.FREulerProblem(u, (0.0, 0.15), ps, GAMMA, bc)
+    du = np.zeros_like(u, order="F")
+    prob.f(du, u, None, 0.0)
+    ref = oracle.rhs_euler1d(u, ps, GAMMA, bc)
+    assert rel(du, ref) <= RTOL_RHS
+    prob.close()
+
+
+def test_euler1d_cfg2_full_size_with_limiter(FR, oracle, coracle):
+    """cfg2: Sod, deg 3, 4096 cells, positivity limiter (weights wp/2) before every step."""
+    ps = FR.FRPSpace1D(0.0, 1.0, 4096, 3)
+    u0 = oracle.ic_sod1d(ps, GAMMA)
+    dt = 0.05 * ps.dx[0]
+    prob = FR.FREulerProblem(u0, (0.0, 0.15), ps, GAMMA, "dirichlet")
+    itg = FR.init(prob, FR.Midpoint(), dt=dt)
+    itg.set_hooks(limiter_weights=ps.wp / 2)
+    FR.step_(itg, 1000)
+    ref = coracle.integrate_euler1d(u0, ps, GAMMA, "dirichlet", dt, 1000, "midpoint", ps.wp / 2)
+    assert np.isfinite(itg.u).all()
+    assert rel(itg.u, ref) <= RTOL_1000
+    prob.close()
+
+
+def test_limiter1d(FR, oracle):
+    ps = FR.FRPSpace1D(0.0, 1.0, 257, 3)
+    u = noisy(oracle.ic_sod1d(ps, GAMMA), 0.2, 5)
+    prob = FR.FREulerProblem(u, (0.0, 1.0), ps, GAMMA, "dirichlet")
+    prob.limiter(ps.wp / 2)
+    got = prob.download()
+    ref = u.copy(order="F")
+    oracle.positive_limiter_euler1d(ref, GAMMA, ps.wp / 2, ps.ll, ps.lr)
+    assert rel(got, ref) <= 1e-14
+    prob.close()
+
+
+# ---------------------------------------------------------------- config 3: 2-D Euler
+@pytest.mark.parametrize("kernel", ["generic", "march"])
+@pytest.mark.parametrize("nx,ny,deg", [(32, 48, 3), (30, 7, 3), (62, 33, 3), (256, 256, 3), (20, 30, 2), (64, 5, 2)])
+def test_euler2d_rhs(FR, oracle, coracle, kernel, nx, ny, deg):
+    ps = FR.FRPSpace2D(0.0, 1.0, nx, 0.0, 1.0, ny, deg, 1, 1)
+    u = noisy(oracle.ic_wave2d(ps, GAMMA, "x"), 0.02, 3)
+    u[..., 2] += 0.1 * u[..., 0]  # non-zero y momentum
+    prob = FR.Euler2DProblem(u, (0.0, 0.5), ps, GAMMA, kernel=kernel)
+    du = np.full_like(u, np.nan, order="F")
+    prob.f(du, u, None, 0.0)
+    ref = coracle.rhs_euler2d(u, ps, GAMMA)
+    assert np.isfinite(du).all()
+    assert rel(du, ref) <= RTOL_RHS
+    # du = 0 in the ghost ring (euler2d_wave.jl:36)
+    assert not du[0].any() and not du[-1].any() and not du[:, 0].any() and not du[:, -1].any()
+    prob.close()
+
+
+@pytest.mark.parametrize("deg", [1, 4, 5])
+def test_euler2d_rhs_generic_other_degrees(FR, oracle, coracle, deg):
+    ps = FR.FRPSpace2D(0.0, 1.0, 17, 0.0, 2.0, 9, deg, 1, 1)
+    u = noisy(oracle.ic_wave2d(ps, GAMMA, "y"), 0.02, 4)
+    prob = FR.Euler2DProblem(u, (0.0, 0.5), ps, GAMMA)
+    du = np.zeros_like(u, order="F")
+    prob.f(du, u, None, 0.0)
+    assert rel(du, coracle.rhs_euler2d(u, ps, GAMMA)) <= RTOL_RHS
+    prob.close()
+
+
+def test_euler2d_supersonic_branches(FR, oracle, coracle):
+    """HLL upwind branches (lambda_min >= 0, lambda_max <= 0) in both directions."""
+    ps = FR.FRPSpace2D(0.0, 1.0, 32, 0.0, 1.0, 16, 3, 1, 1)
+    for vel in [(3.0, 2.5), (-3.0, -2.5), (3.0, -2.5)]:
+        prim = np.empty(ps.xpg.shape[:-1] + (4,))
+        prim[..., 0] = 1.0 + 0.1 * np.sin(2 * np.pi * ps.xpg[..., 0]) * np.cos(2 * np.pi * ps.xpg[..., 1])
+        prim[..., 1], prim[..., 2], prim[..., 3] = vel[0], vel[1], 1.0
+        u = np.asfortranarray(oracle.prim_conserve(prim, GAMMA))
+        for kernel in ("generic", "march"):
+            prob = FR.Euler2DProblem(u, (0.0, 0.5), ps, GAMMA, kernel=kernel)
+            du = np.zeros_like(u, order="F")
+            prob.f(du, u, None, 0.0)
+            assert rel(du, coracle.rhs_euler2d(u, ps, GAMMA)) <= RTOL_RHS
+            prob.close()
+
+
+@pytest.mark.parametrize("kernel", ["generic", "march"])
+@pytest.mark.parametrize("scheme", ["euler", "midpoint", "ssprk3"])
+def test_euler2d_steps_match_oracle(FR, oracle, coracle, kernel, scheme):
+    ps = FR.FRPSpace2D(0.0, 1.0, 32, 0.0, 1.0, 48, 3, 1, 1)
+    u0 = oracle.ic_wave2d(ps, GAMMA, "x")
+    dt = 2e-4
+    alg = {"euler": FR.Euler, "midpoint": FR.Midpoint, "ssprk3": FR.SSPRK33}[scheme]
+    prob = FR.Euler2DProblem(u0, (0.0, 0.5), ps, GAMMA, kernel=kernel)
+    itg = FR.init(prob, alg(), dt=dt)
+    itg.set_hooks(ghost="wave_x")
+    FR.step_(itg, 1000)
+    ref = coracle.integrate_euler2d(u0, ps, GAMMA, dt, 1000, scheme, "wave_x")
+    assert rel(itg.u, ref) <= RTOL_1000
+    prob.close()
+
+
+def test_euler2d_user_loop_with_host_ghost_fill(FR, oracle, coracle):
+    """The reference's own loop shape: mutate itg.u on the host between steps."""
+    ps = FR.FRPSpace2D(0.0, 1.0, 20, 0.0, 1.0, 30, 2, 1, 1)
+    u0 = oracle.ic_wave2d(ps, GAMMA, "y")
+    prob = FR.Euler2DProblem(u0, (0.0, 0.5), ps, GAMMA)
+    itg = FR.init(prob, FR.Midpoint(), dt=0.002)
+    for _ in range(10):
+        oracle.ghost_fill_euler2d(itg.u, "wave_y")  # host-side mutation, as in euler2d_wave.jl:157-164
+        FR.step_(itg)
+    ref = coracle.integrate_euler2d(u0, ps, GAMMA, 0.002, 10, "midpoint", "wave_y")
+    assert rel(itg.u, ref) <= 1e-11
+    prob.close()
+
+
+@pytest.mark.parametrize("mode", ["wave_x", "wave_y", "copy"])
+def test_ghost_fill(FR, oracle, mode):
+    ps = FR.FRPSpace2D(0.0, 1.0, 12, 0.0, 1.0, 9, 3, 1, 1)
+    u = noisy(oracle.ic_wave2d(ps, GAMMA, "x"), 0.3, 9)
+    prob = FR.Euler2DProblem(u, (0.0, 0.5), ps, GAMMA)
+    prob.ghost_fill(mode)
+    got = prob.download()
+    ref = oracle.ghost_fill_euler2d(u.copy(order="F"), mode)
+    assert np.array_equal(got, ref)  # pure copies / sign flips: bit exact
+    prob.close()
+
+
+def test_limiter2d(FR, oracle):
+    ps = FR.FRPSpace2D(0.0, 1.0, 33, 0.0, 1.0, 17, 3, 1, 1)
+    u = noisy(oracle.ic_wave2d(ps, GAMMA, "x"), 0.3, 2)
+    prob = FR.Euler2DProblem(u, (0.0, 0.5), ps, GAMMA)
+    prob.limiter(ps.wp / 4)
+    got = prob.download()
+    ref = oracle.positive_limiter_euler2d(u.copy(order="F"), GAMMA, ps.wp / 4, ps.ll, ps.lr)
+    assert rel(got, ref) <= 1e-14
+    prob.close()
+
+
+def test_euler2d_freestream_and_conservation(FR, oracle):
+    """Size-independent properties at a larger size: constant state -> du == 0 to rounding;
+    periodic wave -> sum(wp * du) == 0 per variable (discrete conservation)."""
+    nx = ny = 512
+    ps = FR.FRPSpace2D(0.0, 1.0, nx, 0.0, 1.0, ny, 3, 1, 1)
+    shape = (nx + 2, ny + 2, 4, 4, 4)
+    w = oracle.prim_conserve(np.array([1.0, 0.3, -0.2, 0.8]), GAMMA)
+    u = np.empty(shape, order="F")
+    u[...] = w
+    prob = FR.Euler2DProblem(u, (0.0, 0.5), ps, GAMMA)
+    du = np.zeros(shape, order="F")
+    prob.f(du, u, None, 0.0)
+    assert np.abs(du).max() <= 1e-9  # terms are O(|F|/J) ~ 1e3: 1e-9 is ~1e-12 relative
+    u = oracle.ic_wave2d(ps, GAMMA, "x")
+    oracle.ghost_fill_euler2d(u, "wave_x")
+    prob.f(du, u, None, 0.0)
+    scale = np.abs(du).max()
+    for m in (0, 1, 3):  # y momentum is sign-flipped at the y ghosts: not conserved by design
+        tot = np.einsum("ijklm,kl->m", du[1:-1, 1:-1, :, :, m : m + 1], ps.wp)[0]
+        assert abs(tot) <= 1e-9 * scale * nx * ny
+    prob.close()
+
+
+# ---------------------------------------------------------------- config 4: 1-D BGK
+@pytest.mark.parametrize("ncell,nu,deg", [(20, 100, 2), (64, 256, 2), (33, 28, 3)])
+def test_bgk_rhs(FR, oracle, ncell, nu, deg):
+    ps = FR.FRPSpace1D(0.0, 1.0, ncell, deg)
+    velo, wts = oracle.vspace1d(-5.0, 5.0, nu)
+    f0 = noisy(oracle.ic_bgk1d(ps, velo), 0.01, 6)
+    prob = FR.BGKProblem(f0, (0.0, 1.0), ps, velo, wts, 1e-2)
+    du = np.zeros_like(f0, order="F")
+    prob.f(du, f0, None, 0.0)
+    ref = oracle.rhs_bgk1d(f0, ps.dx, velo, wts, ps.ll, ps.lr, ps.dl, ps.dhl, ps.dhr, 1e-2)
+    assert rel(du, ref) <= RTOL_RHS
+    prob.close()
+
+
+def test_bgk_steps(FR, oracle, coracle):
+    ps = FR.FRPSpace1D(0.0, 1.0, 64, 2)
+    velo, wts = oracle.vspace1d(-5.0, 5.0, 64)
+    f0 = oracle.ic_bgk1d(ps, velo)
+    dt = 0.1 * ps.dx[0] / 5.0
+    prob = FR.BGKProblem(f0, (0.0, 1.0), ps, velo, wts, 1e-2)
+    itg = FR.init(prob, FR.Midpoint(), dt=dt)
+    FR.step_(itg, 1000)
+    ref = coracle.integrate_bgk1d(f0, ps.dx, velo, wts, ps.ll, ps.lr, ps.dl, ps.dhl, ps.dhr, 1e-2, dt, 1000, "midpoint")
+    assert rel(itg.u, ref) <= RTOL_1000
+    prob.close()
+
+
+def test_no_cpu_fallback_symbols(FR):
+    """The product library must not link or reference the oracle."""
+    import subprocess
+
+    out = subprocess.run(["nm", "-D", FR.LIB_PATH], capture_output=True, text=True).stdout
+    assert "fro_" not in out
