@@ -87,19 +87,34 @@ struct Smem {
   static constexpr int kPlanes = 4 * NSP * NSP;
   static constexpr int kTile = kPlanes * 32;  // doubles
   alignas(128) double tile[NBUF][kTile];
-  alignas(128) double xd[kPlanes * kOwn];         // x-pass derivative + correction (no 1/Jx yet)
-  alignas(128) double xrp[2 * NSP * NSP * kOwn];  // 1/rho and p at the points
+  alignas(128) double xd[kTile];              // x-pass derivative + correction (no 1/Jx yet)
+  alignas(128) double xrp[2 * NSP * NSP * 32];  // 1/rho and p at the points
   alignas(8) uint64_t bar[NBUF];
 };
+
+// y traces of one column (k = t) of a tile: top (lr) or bottom (ll)
+template <int NSP>
+__device__ __forceinline__ void col_trace(const double *__restrict__ Uy, const double *l,
+                                          double (&tr)[4]) {
+#pragma unroll
+  for (int m = 0; m < 4; ++m) {
+    double a = Uy[32 * NSP * (0 + NSP * m)] * l[0];
+#pragma unroll
+    for (int q = 1; q < NSP; ++q) a = fma(Uy[32 * NSP * (q + NSP * m)], l[q], a);
+    tr[m] = a;
+  }
+}
 
 // MINB = resident CTAs per SM the register budget is compiled for
 template <int NSP, int NBUF, int MINB>
 __global__ void __launch_bounds__(NSP * 32, MINB)
 euler2d_march_kernel(const __grid_constant__ CUtensorMap tmap, MarchParams P, FrbOps ops) {
-  extern __shared__ unsigned char smem_raw[];
+  extern __shared__ __align__(128) unsigned char smem_raw[];
   using SM = Smem<NSP, NBUF>;
-  SM &S = *reinterpret_cast<SM *>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
+  // keep the pointer in the shared window (LDS/STS, not generic LD/ST): align by offset
+  SM &S = *reinterpret_cast<SM *>(smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u));
   constexpr int kPlanes = SM::kPlanes;
+  constexpr int kTile = SM::kTile;
   constexpr uint32_t kTileBytes = kPlanes * 32 * sizeof(double);
 
   const int lane = threadIdx.x & 31;
@@ -110,9 +125,7 @@ euler2d_march_kernel(const __grid_constant__ CUtensorMap tmap, MarchParams P, Fr
   if (ja > P.ny) return;
   const int ntiles = jb - ja + 3;  // rows ja-1 .. jb+1; tile q holds row ja-1+q in buffer q % NBUF
   const size_t NXG = P.nx + 2, NE = NXG * (size_t)(P.ny + 2);
-  const int cl = lane - 1;                     // compact lane index of the owned columns
-  const bool inner = (unsigned)cl < (unsigned)kOwn;
-  const bool owner = inner && i <= P.nx;
+  const bool owner = lane >= 1 && lane <= kOwn && i <= P.nx;
   const double gamma = P.gamma, gm1 = gamma - 1.0;
   const int c0 = blockIdx.x * kOwn;
 
@@ -129,26 +142,26 @@ euler2d_march_kernel(const __grid_constant__ CUtensorMap tmap, MarchParams P, Fr
     }
   }
 
+  // per-thread views: row view (x pass, l = t) and column view (y pass, k = t)
+  const int offx = 32 * NSP * t + lane;  // + 32*(k + NSP*NSP*m)
+  const int offy = 32 * t + lane;        // + 32*NSP*(l + NSP*m)
+  double *const xdx = S.xd + offx;
+  const double *const xdy = S.xd + offy;
+  double *const xrpx = S.xrp + offx;
+  const double *const xrpy = S.xrp + offy;
+  // global plane walk: plane(t, l, m) = t + NSP*(l + NSP*m)  ->  base + NE*t, step NE*NSP
+  const size_t pstep = NE * NSP;
+  const size_t goff = i + NE * (size_t)t;
+
   // ---- prologue: common flux on the bottom face of row ja from tiles 0 (row ja-1) and 1
   double hb[4];
   {
     mbar_wait(&S.bar[0], 0);
     mbar_wait(&S.bar[1 % NBUF], 0);
-    const double *U0 = S.tile[0] + lane;
-    const double *U1 = S.tile[1 % NBUF] + lane;
     double uT[4], uB[4];
-#pragma unroll
-    for (int m = 0; m < 4; ++m) {
-      double a = U0[32 * (t + NSP * (0 + NSP * m))] * ops.lr[0];
-      double b = U1[32 * (t + NSP * (0 + NSP * m))] * ops.ll[0];
-#pragma unroll
-      for (int q = 1; q < NSP; ++q) {
-        a = fma(U0[32 * (t + NSP * (q + NSP * m))], ops.lr[q], a);
-        b = fma(U1[32 * (t + NSP * (q + NSP * m))], ops.ll[q], b);
-      }
-      uT[m] = a; uB[m] = b;
-    }
-    frb::Flux4 h = frb::hll4_y(uT[0], uT[1], uT[2], uT[3], uB[0], uB[1], uB[2], uB[3], gamma);
+    col_trace<NSP>(S.tile[0] + offy, ops.lr, uT);
+    col_trace<NSP>(S.tile[1 % NBUF] + offy, ops.ll, uB);
+    frb::Flux4 h = frb::hll4_y_fast(uT[0], uT[1], uT[2], uT[3], uB[0], uB[1], uB[2], uB[3], gamma, gm1);
     hb[0] = h.f0; hb[1] = h.f1; hb[2] = h.f2; hb[3] = h.f3;
   }
   {
@@ -163,14 +176,14 @@ euler2d_march_kernel(const __grid_constant__ CUtensorMap tmap, MarchParams P, Fr
   for (int q = 1; q <= ntiles - 2; ++q) {  // tile q = row j
     const int j = ja - 1 + q;
     const int buf = q % NBUF, nbuf = (q + 1) % NBUF;
-    const double *U = S.tile[buf] + lane;
-    const double *ua_row = P.ua + i + NXG * (size_t)j;
+    const double *const Ux = S.tile[0] + buf * kTile + offx;
+    const double *const Uy = S.tile[0] + buf * kTile + offy;
+    const size_t grow = goff + NXG * (size_t)j;
     if (P.use_a && owner) {
       // pull this row's u_n into L2 now; the loads after the x pass then hit L2
+      const double *pa = P.ua + grow;
 #pragma unroll
-      for (int m = 0; m < 4; ++m)
-#pragma unroll
-        for (int l = 0; l < NSP; ++l) prefetch_l2(ua_row + NE * (t + NSP * (l + NSP * m)));
+      for (int c = 0; c < 4 * NSP; ++c, pa += pstep) prefetch_l2(pa);
     }
     // tile q was already waited on as the "next" tile of step q-1 (or in the prologue)
 
@@ -180,20 +193,18 @@ euler2d_march_kernel(const __grid_constant__ CUtensorMap tmap, MarchParams P, Fr
 #pragma unroll
       for (int m = 0; m < 4; ++m)
 #pragma unroll
-        for (int k = 0; k < NSP; ++k) w[k][m] = U[32 * (k + NSP * (t + NSP * m))];
+        for (int k = 0; k < NSP; ++k) w[k][m] = Ux[32 * (k + NSP * NSP * m)];
 #pragma unroll
       for (int k = 0; k < NSP; ++k) {
-        double rr = 1.0 / w[k][0];
+        double rr = frb::rcp_fast(w[k][0]);
         double vx = w[k][1] * rr, vy = w[k][2] * rr;
         double p = gm1 * fma(-0.5, fma(w[k][1], vx, w[k][2] * vy), w[k][3]);
         f[k][0] = w[k][1];
         f[k][1] = fma(w[k][1], vx, p);
         f[k][2] = w[k][1] * vy;
         f[k][3] = (w[k][3] + p) * vx;
-        if (inner) {
-          S.xrp[kOwn * (k + NSP * t) + cl] = rr;
-          S.xrp[kOwn * (NSP * NSP + k + NSP * t) + cl] = p;
-        }
+        xrpx[32 * k] = rr;
+        xrpx[32 * (NSP * NSP + k)] = p;
       }
       double uL[4], uR[4], fL[4], fR[4];
 #pragma unroll
@@ -212,24 +223,22 @@ euler2d_march_kernel(const __grid_constant__ CUtensorMap tmap, MarchParams P, Fr
       // left face: HLL(u_face[i-1,j,2,l,:], u_face[i,j,4,l,:])  (euler2d_wave.jl:69-74)
       double n0 = __shfl_up_sync(0xffffffffu, uR[0], 1), n1 = __shfl_up_sync(0xffffffffu, uR[1], 1);
       double n2 = __shfl_up_sync(0xffffffffu, uR[2], 1), n3 = __shfl_up_sync(0xffffffffu, uR[3], 1);
-      frb::Flux4 hl = frb::hll4(n0, n1, n2, n3, uL[0], uL[1], uL[2], uL[3], gamma);
+      frb::Flux4 hl = frb::hll4_fast(n0, n1, n2, n3, uL[0], uL[1], uL[2], uL[3], gamma, gm1);
       double hr0 = __shfl_down_sync(0xffffffffu, hl.f0, 1), hr1 = __shfl_down_sync(0xffffffffu, hl.f1, 1);
       double hr2 = __shfl_down_sync(0xffffffffu, hl.f2, 1), hr3 = __shfl_down_sync(0xffffffffu, hl.f3, 1);
       const double cL[4] = {hl.f0 - fL[0], hl.f1 - fL[1], hl.f2 - fL[2], hl.f3 - fL[3]};
       const double cR[4] = {hr0 - fR[0], hr1 - fR[1], hr2 - fR[2], hr3 - fR[3]};
-      if (inner) {
 #pragma unroll
-        for (int m = 0; m < 4; ++m)
+      for (int m = 0; m < 4; ++m)
 #pragma unroll
-          for (int k = 0; k < NSP; ++k) {
-            double d = f[0][m] * ops.lpdm[k * FRB_NSPMAX];
+        for (int k = 0; k < NSP; ++k) {
+          double d = f[0][m] * ops.lpdm[k * FRB_NSPMAX];
 #pragma unroll
-            for (int q2 = 1; q2 < NSP; ++q2) d = fma(f[q2][m], ops.lpdm[k * FRB_NSPMAX + q2], d);
-            d = fma(cL[m], ops.dgl[k], d);
-            d = fma(cR[m], ops.dgr[k], d);
-            S.xd[kOwn * (k + NSP * (t + NSP * m)) + cl] = d;
-          }
-      }
+          for (int q2 = 1; q2 < NSP; ++q2) d = fma(f[q2][m], ops.lpdm[k * FRB_NSPMAX + q2], d);
+          d = fma(cL[m], ops.dgl[k], d);
+          d = fma(cR[m], ops.dgr[k], d);
+          xdx[32 * (k + NSP * NSP * m)] = d;
+        }
     }
     __syncthreads();  // (A) xd / xrp of this row visible
 
@@ -237,21 +246,21 @@ euler2d_march_kernel(const __grid_constant__ CUtensorMap tmap, MarchParams P, Fr
     {
       double un[NSP][4];
       if (P.use_a && owner) {
+        const double *pa = P.ua + grow;
 #pragma unroll
         for (int m = 0; m < 4; ++m)
 #pragma unroll
-          for (int l = 0; l < NSP; ++l) un[l][m] = __ldcs(ua_row + NE * (t + NSP * (l + NSP * m)));
+          for (int l = 0; l < NSP; ++l, pa += pstep) un[l][m] = __ldcs(pa);
       }
       double w[NSP][4], g[NSP][4];  // [l][m]
 #pragma unroll
       for (int m = 0; m < 4; ++m)
 #pragma unroll
-        for (int l = 0; l < NSP; ++l) w[l][m] = U[32 * (t + NSP * (l + NSP * m))];
-      const int clc = inner ? cl : 0;
+        for (int l = 0; l < NSP; ++l) w[l][m] = Uy[32 * NSP * (l + NSP * m)];
 #pragma unroll
       for (int l = 0; l < NSP; ++l) {
-        double rr = S.xrp[kOwn * (t + NSP * l) + clc];
-        double p = S.xrp[kOwn * (NSP * NSP + t + NSP * l) + clc];
+        double rr = xrpy[32 * NSP * l];
+        double p = xrpy[32 * NSP * (NSP + l)];
         double vy = w[l][2] * rr;
         g[l][0] = w[l][2];
         g[l][1] = w[l][1] * vy;
@@ -260,25 +269,21 @@ euler2d_march_kernel(const __grid_constant__ CUtensorMap tmap, MarchParams P, Fr
       }
       // top face of row j: HLL between this row's top trace and row j+1's bottom trace
       mbar_wait(&S.bar[nbuf], ((q + 1) / NBUF) & 1);
-      const double *Un = S.tile[nbuf] + lane;
       double ht[4];
       {
         double uT[4], uB[4];
 #pragma unroll
         for (int m = 0; m < 4; ++m) {
           double a = w[0][m] * ops.lr[0];
-          double b = Un[32 * (t + NSP * (0 + NSP * m))] * ops.ll[0];
 #pragma unroll
-          for (int q2 = 1; q2 < NSP; ++q2) {
-            a = fma(w[q2][m], ops.lr[q2], a);
-            b = fma(Un[32 * (t + NSP * (q2 + NSP * m))], ops.ll[q2], b);
-          }
-          uT[m] = a; uB[m] = b;
+          for (int q2 = 1; q2 < NSP; ++q2) a = fma(w[q2][m], ops.lr[q2], a);
+          uT[m] = a;
         }
-        frb::Flux4 h = frb::hll4_y(uT[0], uT[1], uT[2], uT[3], uB[0], uB[1], uB[2], uB[3], gamma);
+        col_trace<NSP>(S.tile[0] + nbuf * kTile + offy, ops.ll, uB);
+        frb::Flux4 h = frb::hll4_y_fast(uT[0], uT[1], uT[2], uT[3], uB[0], uB[1], uB[2], uB[3], gamma, gm1);
         ht[0] = h.f0; ht[1] = h.f1; ht[2] = h.f2; ht[3] = h.f3;
       }
-      double *obase = P.out + i + NXG * (size_t)j;
+      double *po = P.out + grow;
 #pragma unroll
       for (int m = 0; m < 4; ++m) {
         double gB = g[0][m] * ops.ll[0], gT = g[0][m] * ops.lr[0];
@@ -289,18 +294,16 @@ euler2d_march_kernel(const __grid_constant__ CUtensorMap tmap, MarchParams P, Fr
         }
         const double cB = hb[m] - gB, cT = ht[m] - gT;
 #pragma unroll
-        for (int l = 0; l < NSP; ++l) {
+        for (int l = 0; l < NSP; ++l, po += pstep) {
           double d = g[0][m] * ops.lpdm[l * FRB_NSPMAX];
 #pragma unroll
           for (int q2 = 1; q2 < NSP; ++q2) d = fma(g[q2][m], ops.lpdm[l * FRB_NSPMAX + q2], d);
           d = fma(cB, ops.dgl[l], d);
           d = fma(cT, ops.dgr[l], d);
-          if (owner) {
-            double dx = S.xd[kOwn * (t + NSP * (l + NSP * m)) + cl];
-            double v = fma(P.cys, d, fma(P.cxs, dx, P.cb * w[l][m]));
-            if (P.use_a) v = fma(P.ca, un[l][m], v);
-            __stcs(obase + NE * (t + NSP * (l + NSP * m)), v);
-          }
+          double dx = xdy[32 * NSP * (l + NSP * m)];
+          double v = fma(P.cys, d, fma(P.cxs, dx, P.cb * w[l][m]));
+          if (P.use_a) v = fma(P.ca, un[l][m], v);
+          if (owner) __stcs(po, v);
         }
         hb[m] = ht[m];
       }
@@ -440,11 +443,6 @@ int frb_launch_euler2d_march(frb_prob_t p, const double *u, const double *ua, do
     mp.ca = st.ca; mp.cb = st.cb; mp.use_a = st.use_a;
     mp.cxs = -cdt / p->Jx; mp.cys = -cdt / p->Jy;
   }
-  const int variant = env_int("FRB_MARCH_VARIANT", 0);  // 0: 2-deep ring, 4 CTAs/SM; 1: 3-deep, 3 CTAs/SM
-  if (p->nsp == 4) {
-    if (variant == 1) return launch_march<4, 3, 3>(p, it->second, mp);
-    return launch_march<4, 2, 4>(p, it->second, mp);
-  }
-  if (variant == 1) return launch_march<3, 3, 4>(p, it->second, mp);
-  return launch_march<3, 2, 5>(p, it->second, mp);
+  if (p->nsp == 4) return launch_march<4, 3, 3>(p, it->second, mp);  // 72 KB smem, 168 regs
+  return launch_march<3, 3, 4>(p, it->second, mp);
 }
