@@ -2,10 +2,10 @@
 FluxReconstruction.jl API shapes.  Compute lives in lib/libfrb200.so (hand-written
 sm_100a CUDA, C ABI in include/frb200.h); this package is the thin host mirror of the
 reference interface.  There is no CPU fallback."""
-from ._lib import Context, FRBError, LIB_PATH, SIGNATURES, lib  # noqa: F401
+from ._lib import Context, FRBError, LIB_PATH, SIGNATURES, lib, pinned_empty, pinned_free  # noqa: F401
 from .spaces import *  # noqa: F401,F403
 from .problems import (  # noqa: F401
-    BGKProblem, Euler, Euler2DProblem, FRAdvectionProblem, FREulerProblem, Integrator, Midpoint, SSPRK33, init,
+    BGKProblem, DistributedEuler2D, Euler, Euler2DProblem, FRAdvectionProblem, FREulerProblem, Integrator, Midpoint, SSPRK33, init,
     solve, step_,
 )
 from . import partition  # noqa: F401

@@ -61,8 +61,13 @@ SIGNATURES = {
     "frb_time_stage": (C.c_int32, [C.c_void_p, C.c_int32, C.c_int32, C.POINTER(C.c_float)]),
     "frb_last_timing": (C.c_int32, [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_int64)]),
     "frb_set_kernel": (C.c_int32, [C.c_void_p, C.c_int32]),
+    "frb_set_profiling": (C.c_int32, [C.c_void_p, C.c_int32]),
+    "frb_stage_timing": (C.c_int32, [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_int64)]),
+    "frb_host_alloc": (C.c_int32, [C.c_int64, C.POINTER(C.c_void_p)]),
+    "frb_host_free": (C.c_int32, [C.c_void_p]),
     "frb_halo_export": (C.c_int32, [C.c_void_p, C.POINTER(C.c_ubyte)]),
     "frb_halo_connect": (C.c_int32, [C.c_void_p, C.c_int32, C.c_int32, C.POINTER(C.c_ubyte), C.POINTER(C.c_ubyte)]),
+    "frb_halo_sync": (C.c_int32, [C.c_void_p]),
     "frb_halo_disconnect": (C.c_int32, [C.c_void_p]),
 }
 
@@ -146,3 +151,23 @@ def make_operators(deg, ll, lr, lpdm, dgl, dgr, dll=None, dlr=None):
         keep += [a, b]
         ops.dll, ops.dlr = dptr(a), dptr(b)
     return ops, keep
+
+
+def pinned_empty(shape, order="F"):
+    """float64 array in page-locked host memory (cudaMallocHost) for the host-buffer paths."""
+    n = int(np.prod(shape))
+    p = C.c_void_p()
+    check(lib().frb_host_alloc(n * 8, C.byref(p)))
+    buf = (C.c_double * n).from_address(p.value)
+    a = np.frombuffer(buf, dtype=np.float64).reshape(shape, order=order)
+    _PINNED[a.ctypes.data] = p
+    return a
+
+
+def pinned_free(a):
+    p = _PINNED.pop(a.ctypes.data, None)
+    if p is not None:
+        check(lib().frb_host_free(p))
+
+
+_PINNED = {}

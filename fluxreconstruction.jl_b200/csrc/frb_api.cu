@@ -139,6 +139,7 @@ extern "C" int32_t frb_prob_destroy(frb_prob_t p) {
   cudaFree(p->lim_w); cudaFree(p->flag);
   if (p->ev0) cudaEventDestroy(p->ev0);
   if (p->ev1) cudaEventDestroy(p->ev1);
+  for (cudaEvent_t e : p->prof_events) cudaEventDestroy(e);
   delete p;
   return FRB_OK;
 }
@@ -262,7 +263,40 @@ static bool use_march(frb_prob_t p) {
   return frb_euler2d_march_supported(p);
 }
 
+static cudaEvent_t prof_event(frb_prob_t p) {
+  if (p->prof_used == p->prof_events.size()) {
+    cudaEvent_t e = nullptr;
+    if (cudaEventCreate(&e) != cudaSuccess) return nullptr;
+    p->prof_events.push_back(e);
+  }
+  return p->prof_events[p->prof_used++];
+}
+
+static void prof_begin(frb_prob_t p) { p->prof_used = 0; p->stage_ms = 0.f; p->stage_count = 0; }
+
+static void prof_collect(frb_prob_t p) {  // call after the stream has been synchronised
+  for (size_t q = 0; q + 1 < p->prof_used; q += 2) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, p->prof_events[q], p->prof_events[q + 1]) == cudaSuccess) {
+      p->stage_ms += ms;
+      p->stage_count += 1;
+    }
+  }
+  p->prof_used = 0;
+}
+
+static int launch_stage_inner(frb_prob_t p, const double *u, const double *ua, double *out, FrbStage st);
+
 static int launch_stage(frb_prob_t p, const double *u, const double *ua, double *out, FrbStage st) {
+  if (!p->profiling) return launch_stage_inner(p, u, ua, out, st);
+  cudaEvent_t e0 = prof_event(p), e1 = prof_event(p);
+  if (e0 && e1) cudaEventRecord(e0, p->ctx->stream);
+  int n = launch_stage_inner(p, u, ua, out, st);
+  if (e0 && e1) cudaEventRecord(e1, p->ctx->stream);
+  return n;
+}
+
+static int launch_stage_inner(frb_prob_t p, const double *u, const double *ua, double *out, FrbStage st) {
   int n;
   switch (p->kind) {
     case K_ADV1D: n = frb_launch_adv1d(p, u, ua, out, st); break;
@@ -298,6 +332,7 @@ extern "C" int32_t frb_rhs(frb_prob_t p, const double *u_host, double *du_host, 
   if (u_host)
     FRB_CUDA(cudaMemcpyAsync(p->u, u_host, sizeof(double) * p->len, cudaMemcpyHostToDevice, s));
   const int64_t l0 = p->launches;
+  prof_begin(p);
   FRB_CUDA(cudaEventRecord(p->ev0, s));
   FrbStage st = {0.0, 0.0, 1.0, 0, 1};
   int n = launch_stage(p, p->u, nullptr, p->du, st);
@@ -308,6 +343,7 @@ extern "C" int32_t frb_rhs(frb_prob_t p, const double *u_host, double *du_host, 
   FRB_CUDA(cudaStreamSynchronize(s));
   FRB_CUDA(cudaEventElapsedTime(&p->last_ms, p->ev0, p->ev1));
   p->last_launches = p->launches - l0;
+  prof_collect(p);
   return FRB_OK;
 }
 
@@ -373,41 +409,91 @@ extern "C" int32_t frb_limiter_positivity(frb_prob_t p, const double *weights, i
 }
 
 // ---- step! ------------------------------------------------------------------------------
+static int halo_wait_if_pending(frb_prob_t p) {
+  if (!p->halo_pending) return 0;
+  int n = frb_halo_wait(p);
+  if (n < 0) return n;
+  p->launches += n;
+  p->halo_pending = false;
+  return 0;
+}
+
+// one fused stage; on the slab-parallel path preceded by the wait for the neighbours' rows of
+// the previous stage and followed by the push of this stage's boundary rows + the flag
+static int stage_x(frb_prob_t p, const double *u, const double *ua, double *out, FrbStage st) {
+  int n;
+  if ((n = halo_wait_if_pending(p)) < 0) return n;
+  if ((n = launch_stage(p, u, ua, out, st)) < 0) return n;
+  if (frb_halo_active(p)) {
+    if (!use_march(p)) {  // the marching kernel stores its boundary rows to the peers itself
+      if ((n = frb_halo_push(p, out, frb_halo_role(p, out), false, -1)) < 0) return n;
+      p->launches += n;
+    }
+    if ((n = frb_halo_signal(p)) < 0) return n;
+    p->launches += n;
+    p->halo_pending = true;
+  }
+  return 0;
+}
+
 static int one_step(frb_prob_t p, int scheme, double dt) {
   int n;
+  const bool par = frb_halo_active(p);
   if (p->limiter_on) {
     if ((n = run_limiter(p)) < 0) return n;
   }
   if (p->ghost_mode != FRB_GHOST_NONE) {
-    if ((n = frb_launch_ghost_fill2d(p, p->u, p->ghost_mode)) < 0) return n;
+    if (par) {
+      if ((n = halo_wait_if_pending(p)) < 0) return n;  // neighbours are done with the last stage
+      n = frb_launch_ghost_x2d(p, p->u, p->ghost_mode);
+    } else {
+      n = frb_launch_ghost_fill2d(p, p->u, p->ghost_mode);
+    }
+    if (n < 0) return n;
     p->launches += n;
   }
   if (is2d(p)) {
-    // ghosts are frozen across the stages of a step (du = 0 there): give the stage
-    // buffers the same ring as u_n
-    if ((n = frb_launch_ring_copy2d(p, p->u, p->s1)) < 0) return n;
+    // ghosts are frozen across the stages of a step (du = 0 there): give the stage buffers the
+    // same ring as u_n.  Rows owned by a neighbouring rank are excluded (the neighbour writes them).
+    int nr = 1, rk = frb_halo_rank(p, &nr);
+    const bool seam_local = !par || p->ghost_mode == FRB_GHOST_NONE;
+    const bool row0 = !par || (rk == 0 && seam_local), rowN = !par || (rk == nr - 1 && seam_local);
+    if ((n = frb_launch_ring_copy2d(p, p->u, p->s1, row0, rowN)) < 0) return n;
     p->launches += n;
     if (scheme == FRB_SCHEME_SSPRK3) {
-      if ((n = frb_launch_ring_copy2d(p, p->u, p->s2)) < 0) return n;
+      if ((n = frb_launch_ring_copy2d(p, p->u, p->s2, row0, rowN)) < 0) return n;
       p->launches += n;
     }
   }
+  if (par && p->ghost_mode != FRB_GHOST_NONE) {
+    // the y half of the ghost fill crosses the global seam: first/last rank exchange their
+    // boundary rows (frozen for the step, so they go into all three buffers of the peer)
+    const int flip = p->ghost_mode == FRB_GHOST_WAVE_X ? 2 : -1;
+    for (int role = 0; role < 3; ++role) {
+      if ((n = frb_halo_push(p, p->u, role, true, flip)) < 0) return n;
+      p->launches += n;
+    }
+    if ((n = frb_halo_signal(p)) < 0) return n;
+    p->launches += n;
+    p->halo_pending = true;
+  }
   if (scheme == FRB_SCHEME_EULER) {
     FrbStage st = {0.0, 1.0, dt, 0, 0};
-    if ((n = launch_stage(p, p->u, nullptr, p->s1, st)) < 0) return n;
+    if ((n = stage_x(p, p->u, nullptr, p->s1, st)) < 0) return n;
     std::swap(p->u, p->s1);
+    frb_halo_swap_roles(p, 0, 1);
   } else if (scheme == FRB_SCHEME_MIDPOINT) {
     FrbStage a = {0.0, 1.0, 0.5 * dt, 0, 0};
-    if ((n = launch_stage(p, p->u, nullptr, p->s1, a)) < 0) return n;
+    if ((n = stage_x(p, p->u, nullptr, p->s1, a)) < 0) return n;
     FrbStage b = {1.0, 0.0, dt, 1, 0};
-    if ((n = launch_stage(p, p->s1, p->u, p->u, b)) < 0) return n;
+    if ((n = stage_x(p, p->s1, p->u, p->u, b)) < 0) return n;
   } else if (scheme == FRB_SCHEME_SSPRK3) {
     FrbStage a = {0.0, 1.0, dt, 0, 0};
-    if ((n = launch_stage(p, p->u, nullptr, p->s1, a)) < 0) return n;
+    if ((n = stage_x(p, p->u, nullptr, p->s1, a)) < 0) return n;
     FrbStage b = {0.75, 0.25, dt, 1, 0, 1};
-    if ((n = launch_stage(p, p->s1, p->u, p->s2, b)) < 0) return n;
+    if ((n = stage_x(p, p->s1, p->u, p->s2, b)) < 0) return n;
     FrbStage c = {1.0 / 3.0, 2.0 / 3.0, dt, 1, 0, 1};
-    if ((n = launch_stage(p, p->s2, p->u, p->u, c)) < 0) return n;
+    if ((n = stage_x(p, p->s2, p->u, p->u, c)) < 0) return n;
   } else {
     frb_set_error("frb_step: unknown scheme");
     return FRB_ERR_ARG;
@@ -421,6 +507,7 @@ extern "C" int32_t frb_step(frb_prob_t p, int32_t scheme, double dt, int32_t nst
   FRB_CUDA(cudaSetDevice(p->ctx->device));
   cudaStream_t s = p->ctx->stream;
   const int64_t l0 = p->launches;
+  prof_begin(p);
   if (p->limiter_on) FRB_CUDA(cudaMemsetAsync(p->flag, 0, sizeof(int), s));
   FRB_CUDA(cudaEventRecord(p->ev0, s));
   for (int it = 0; it < nsteps; ++it) {
@@ -434,6 +521,8 @@ extern "C" int32_t frb_step(frb_prob_t p, int32_t scheme, double dt, int32_t nst
   FRB_CUDA(cudaStreamSynchronize(s));
   FRB_CUDA(cudaEventElapsedTime(&p->last_ms, p->ev0, p->ev1));
   p->last_launches = p->launches - l0;
+  prof_collect(p);
+  if (int rc = frb_halo_check_timeout(p)) return rc;
   if (bad) {
     frb_set_error("incorrect range of limiter parameter t");
     return FRB_ERR_NUMERIC;
@@ -480,5 +569,29 @@ extern "C" int32_t frb_set_kernel(frb_prob_t p, int32_t kind) {
     FRB_REQUIRE(frb_euler2d_march_supported(p), FRB_ERR_STATE,
                 "frb_set_kernel: marching kernel needs euler2d, deg 2..3 and even nx");
   p->kernel_kind = kind;
+  return FRB_OK;
+}
+
+extern "C" int32_t frb_set_profiling(frb_prob_t p, int32_t enabled) {
+  FRB_REQUIRE(p, FRB_ERR_ARG, "frb_set_profiling: prob is NULL");
+  p->profiling = enabled != 0;
+  return FRB_OK;
+}
+
+extern "C" int32_t frb_stage_timing(frb_prob_t p, float *ms_total, int64_t *stage_launches) {
+  FRB_REQUIRE(p, FRB_ERR_ARG, "frb_stage_timing: prob is NULL");
+  if (ms_total) *ms_total = p->stage_ms;
+  if (stage_launches) *stage_launches = p->stage_count;
+  return FRB_OK;
+}
+
+extern "C" int32_t frb_host_alloc(int64_t bytes, void **ptr) {
+  FRB_REQUIRE(ptr && bytes > 0, FRB_ERR_ARG, "frb_host_alloc: bad argument");
+  FRB_CUDA(cudaMallocHost(ptr, (size_t)bytes));
+  return FRB_OK;
+}
+
+extern "C" int32_t frb_host_free(void *ptr) {
+  if (ptr) FRB_CUDA(cudaFreeHost(ptr));
   return FRB_OK;
 }

@@ -80,6 +80,10 @@ struct MarchParams {
   double ca, cb;
   double cxs, cys;  // -cdt/Jx, -cdt/Jy  (L = -(dux/Jx + duy/Jy))
   int use_a;
+  // slab-parallel path: the first / last owned row is also stored straight into the halo row
+  // of the rank below / above (peer memory over NVLink); NULL when there is no such neighbour
+  double *peer_lo, *peer_hi;
+  int nyl_lo, nyl_hi;
 };
 
 template <int NSP, int NBUF>
@@ -284,6 +288,21 @@ euler2d_march_kernel(const __grid_constant__ CUtensorMap tmap, MarchParams P, Fr
         ht[0] = h.f0; ht[1] = h.f1; ht[2] = h.f2; ht[3] = h.f3;
       }
       double *po = P.out + grow;
+      // peer halo rows (CTA-uniform conditions): row 1 -> row nyl_lo+1 below, row ny -> row 0 above
+      double *pp = nullptr;
+      size_t ppstep = 0;
+      if (j == 1 && P.peer_lo) {
+        const size_t NEl = NXG * (size_t)(P.nyl_lo + 2);
+        pp = P.peer_lo + i + NXG * (size_t)(P.nyl_lo + 1) + NEl * (size_t)t;
+        ppstep = NEl * NSP;
+      }
+      double *pq = nullptr;
+      size_t pqstep = 0;
+      if (j == P.ny && P.peer_hi) {
+        const size_t NEh = NXG * (size_t)(P.nyl_hi + 2);
+        pq = P.peer_hi + i + NEh * (size_t)t;
+        pqstep = NEh * NSP;
+      }
 #pragma unroll
       for (int m = 0; m < 4; ++m) {
         double gB = g[0][m] * ops.ll[0], gT = g[0][m] * ops.lr[0];
@@ -303,7 +322,11 @@ euler2d_march_kernel(const __grid_constant__ CUtensorMap tmap, MarchParams P, Fr
           double dx = xdy[32 * NSP * (l + NSP * m)];
           double v = fma(P.cys, d, fma(P.cxs, dx, P.cb * w[l][m]));
           if (P.use_a) v = fma(P.ca, un[l][m], v);
-          if (owner) __stcs(po, v);
+          if (owner) {
+            __stcs(po, v);
+            if (pp) { *pp = v; pp += ppstep; }
+            if (pq) { *pq = v; pq += pqstep; }
+          }
         }
         hb[m] = ht[m];
       }
@@ -435,6 +458,7 @@ int frb_launch_euler2d_march(frb_prob_t p, const double *u, const double *ua, do
   mp.ny = p->ny;
   mp.rows_per_seg = 0;
   mp.gamma = p->gamma;
+  frb_halo_stage_targets(p, out, &mp.peer_lo, &mp.peer_hi, &mp.nyl_lo, &mp.nyl_hi);
   if (st.rhs_only) {
     mp.ca = 0.0; mp.cb = 0.0; mp.use_a = 0;
     mp.cxs = -1.0 / p->Jx; mp.cys = -1.0 / p->Jy;

@@ -1,0 +1,262 @@
+// Multi-GPU halo exchange for the row-slab partition of the 2-D problems.
+//
+// One process per GPU.  Each rank owns ny_local rows; local rows 0 and ny_local+1 are halo
+// rows.  Between two ranks the halo row holds the neighbour's boundary row of the *current*
+// stage; across the global y seam it is the reference's frozen per-step ghost row
+// (example/euler2d_wave.jl:127-132).  Rows travel by direct stores into the neighbour's
+// memory over NVLink (the buffers are mapped with CUDA IPC): the marching stage kernel
+// writes its first/last owned row to the peer while it writes it locally, a one-thread
+// kernel then raises a flag in the peer's mailbox (st.release.sys), and the peer's next
+// stage is preceded by a one-thread wait kernel (ld.acquire.sys).  No host round trip, no
+// collective: the path's only exchange is nearest-neighbour.
+#include <cstring>
+
+#include "frb_internal.cuh"
+
+struct FrbHalo {
+  int rank = 0, nranks = 1;
+  int nyl_lo = 0, nyl_hi = 0;          // owned rows of the neighbours
+  double *peer_lo[3] = {nullptr, nullptr, nullptr};  // neighbour below: its u, s1, s2
+  double *peer_hi[3] = {nullptr, nullptr, nullptr};
+  unsigned long long *flags = nullptr;     // local mailbox: [0] from lo, [1] from hi, [2] error
+  unsigned long long *flags_lo = nullptr;  // neighbours' mailboxes
+  unsigned long long *flags_hi = nullptr;
+  unsigned long long epoch = 0;
+  void *opened[8] = {nullptr};
+  int nopened = 0;
+};
+
+namespace {
+
+// copy full rows (all NXG columns, every plane) into the neighbours' halo rows
+__global__ void halo_push_kernel(const double *__restrict__ src, double *__restrict__ dst_lo,
+                                 double *__restrict__ dst_hi, int nx, int nyl, int nyl_lo, int nyl_hi,
+                                 int nplanes, int npp, int flip_var_lo, int flip_var_hi) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  int p = blockIdx.y;
+  if (i > nx + 1 || p >= nplanes) return;
+  const size_t NXG = nx + 2;
+  const size_t NE = NXG * (size_t)(nyl + 2);
+  const int var = p / npp;
+  if (dst_lo) {  // my first owned row -> upper halo row of the rank below
+    const size_t NEl = NXG * (size_t)(nyl_lo + 2);
+    double v = src[i + NXG * 1 + NE * p];
+    dst_lo[i + NXG * (size_t)(nyl_lo + 1) + NEl * p] = (var == flip_var_lo) ? -v : v;
+  }
+  if (dst_hi) {  // my last owned row -> lower halo row of the rank above
+    const size_t NEh = NXG * (size_t)(nyl_hi + 2);
+    double v = src[i + NXG * (size_t)nyl + NE * p];
+    dst_hi[i + NEh * p] = (var == flip_var_hi) ? -v : v;
+  }
+}
+
+__global__ void halo_signal_kernel(unsigned long long *flag_lo, unsigned long long *flag_hi,
+                                   unsigned long long value) {
+  __threadfence_system();
+  if (flag_lo) asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(flag_lo), "l"(value) : "memory");
+  if (flag_hi) asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(flag_hi), "l"(value) : "memory");
+}
+
+__global__ void halo_wait_kernel(unsigned long long *flags, int wait_lo, int wait_hi,
+                                 unsigned long long value, unsigned long long timeout_ns) {
+  unsigned long long t0, t1;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+  for (int s = 0; s < 2; ++s) {
+    if (!(s == 0 ? wait_lo : wait_hi)) continue;
+    unsigned long long v;
+    do {
+      asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(flags + s) : "memory");
+      if (v >= value) break;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+      if (t1 - t0 > timeout_ns) {  // never hang the box: record and carry on
+        flags[2] = value;
+        break;
+      }
+      __nanosleep(200);
+    } while (true);
+  }
+}
+
+int check_launch(const char *what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return frb_cuda_fail(e, what, __FILE__, __LINE__);
+  return 0;
+}
+
+}  // namespace
+
+// export layout: 4 IPC handles (u, s1, s2, flags) + int32 ny_local
+extern "C" int32_t frb_halo_export(frb_prob_t p, unsigned char *out) {
+  if (!p || !out) { frb_set_error("frb_halo_export: NULL argument"); return FRB_ERR_ARG; }
+  if (p->kind != K_EULER2D) { frb_set_error("frb_halo_export: euler2d problems only"); return FRB_ERR_STATE; }
+  FRB_CUDA(cudaSetDevice(p->ctx->device));
+  if (!p->halo) {
+    p->halo = new FrbHalo();
+    FRB_CUDA(cudaMalloc(&p->halo->flags, 4 * sizeof(unsigned long long)));
+    FRB_CUDA(cudaMemset(p->halo->flags, 0, 4 * sizeof(unsigned long long)));
+  }
+  static_assert(sizeof(cudaIpcMemHandle_t) == FRB_IPC_HANDLE_BYTES, "IPC handle size");
+  cudaIpcMemHandle_t h;
+  void *bufs[4] = {p->u, p->s1, p->s2, p->halo->flags};
+  for (int b = 0; b < 4; ++b) {
+    FRB_CUDA(cudaIpcGetMemHandle(&h, bufs[b]));
+    memcpy(out + b * FRB_IPC_HANDLE_BYTES, &h, FRB_IPC_HANDLE_BYTES);
+  }
+  int32_t ny = p->ny;
+  memcpy(out + 4 * FRB_IPC_HANDLE_BYTES, &ny, sizeof ny);
+  return FRB_OK;
+}
+
+static int open_peer(frb_prob_t p, const unsigned char *blob, double **bufs3, unsigned long long **flags,
+                     int *nyl) {
+  FrbHalo *H = p->halo;
+  for (int b = 0; b < 4; ++b) {
+    cudaIpcMemHandle_t h;
+    memcpy(&h, blob + b * FRB_IPC_HANDLE_BYTES, FRB_IPC_HANDLE_BYTES);
+    void *ptr = nullptr;
+    FRB_CUDA(cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    H->opened[H->nopened++] = ptr;
+    if (b < 3) bufs3[b] = static_cast<double *>(ptr);
+    else *flags = static_cast<unsigned long long *>(ptr);
+  }
+  int32_t ny;
+  memcpy(&ny, blob + 4 * FRB_IPC_HANDLE_BYTES, sizeof ny);
+  *nyl = ny;
+  return FRB_OK;
+}
+
+extern "C" int32_t frb_halo_connect(frb_prob_t p, int32_t rank, int32_t nranks,
+                                    const unsigned char *blob_lo, const unsigned char *blob_hi) {
+  if (!p || !p->halo) { frb_set_error("frb_halo_connect: call frb_halo_export first"); return FRB_ERR_STATE; }
+  if (nranks < 2 || !blob_lo || !blob_hi) {
+    frb_set_error("frb_halo_connect: needs >= 2 ranks and both neighbour blobs");
+    return FRB_ERR_ARG;
+  }
+  FRB_CUDA(cudaSetDevice(p->ctx->device));
+  FrbHalo *H = p->halo;
+  H->rank = rank;
+  H->nranks = nranks;
+  if (int rc = open_peer(p, blob_lo, H->peer_lo, &H->flags_lo, &H->nyl_lo)) return rc;
+  if (nranks == 2) {  // both neighbours are the same process: map once
+    for (int b = 0; b < 3; ++b) H->peer_hi[b] = H->peer_lo[b];
+    H->flags_hi = H->flags_lo;
+    H->nyl_hi = H->nyl_lo;
+  } else {
+    if (int rc = open_peer(p, blob_hi, H->peer_hi, &H->flags_hi, &H->nyl_hi)) return rc;
+  }
+  return frb_halo_sync(p);
+}
+
+// (re)send this rank's boundary rows of the resident state to the interior neighbours; every
+// rank must call it after (re)uploading its slab (collective in effect, not in mechanism)
+extern "C" int32_t frb_halo_sync(frb_prob_t p) {
+  if (!p || !frb_halo_active(p)) { frb_set_error("frb_halo_sync: halo not connected"); return FRB_ERR_STATE; }
+  FRB_CUDA(cudaSetDevice(p->ctx->device));
+  int n = frb_halo_push(p, p->u, 0, false, -1);
+  if (n < 0) return n;
+  if ((n = frb_halo_signal(p)) < 0) return n;
+  p->halo_pending = true;
+  return FRB_OK;
+}
+
+extern "C" int32_t frb_halo_disconnect(frb_prob_t p) {
+  if (!p || !p->halo) return FRB_OK;
+  cudaSetDevice(p->ctx->device);
+  cudaStreamSynchronize(p->ctx->stream);
+  FrbHalo *H = p->halo;
+  for (int q = 0; q < H->nopened; ++q) cudaIpcCloseMemHandle(H->opened[q]);
+  cudaFree(H->flags);
+  delete H;
+  p->halo = nullptr;
+  return FRB_OK;
+}
+
+int frb_halo_rank(frb_prob_t p, int *nranks) {
+  if (nranks) *nranks = p->halo ? p->halo->nranks : 1;
+  return p->halo ? p->halo->rank : 0;
+}
+
+bool frb_halo_active(frb_prob_t p) { return p->halo && p->halo->nranks > 1 && p->halo->flags_lo; }
+
+// which local buffer is `ptr`?  (roles move with the pointer swaps of the Euler scheme)
+static int role_of(frb_prob_t p, const double *ptr) {
+  return ptr == p->u ? 0 : ptr == p->s1 ? 1 : ptr == p->s2 ? 2 : -1;
+}
+
+void frb_halo_swap_roles(frb_prob_t p, int a, int b) {
+  if (!p->halo) return;
+  std::swap(p->halo->peer_lo[a], p->halo->peer_lo[b]);
+  std::swap(p->halo->peer_hi[a], p->halo->peer_hi[b]);
+}
+
+// peer destinations of the interior slab boundaries for a stage writing `out`
+void frb_halo_stage_targets(frb_prob_t p, const double *out, double **dst_lo, double **dst_hi,
+                            int *nyl_lo, int *nyl_hi) {
+  *dst_lo = *dst_hi = nullptr;
+  *nyl_lo = *nyl_hi = 0;
+  if (!frb_halo_active(p)) return;
+  FrbHalo *H = p->halo;
+  int r = role_of(p, out);
+  if (r < 0) return;
+  if (H->rank != 0) { *dst_lo = H->peer_lo[r]; *nyl_lo = H->nyl_lo; }
+  if (H->rank != H->nranks - 1) { *dst_hi = H->peer_hi[r]; *nyl_hi = H->nyl_hi; }
+}
+
+int frb_halo_role(frb_prob_t p, const double *ptr) { return role_of(p, ptr); }
+
+// Push the boundary rows of `src` into role `dst_role` (0 = u, 1 = s1, 2 = s2) of the
+// neighbours.  seam = false: interior slab boundaries only (per stage); seam = true: only the
+// global y seam (per step, frozen ghost rows) with the sign flip of the ghost mode.
+int frb_halo_push(frb_prob_t p, const double *src, int dst_role, bool seam, int flip_var) {
+  if (!frb_halo_active(p)) return 0;
+  FrbHalo *H = p->halo;
+  if (dst_role < 0 || dst_role > 2) { frb_set_error("halo push: unknown buffer"); return FRB_ERR_STATE; }
+  const bool first = H->rank == 0, last = H->rank == H->nranks - 1;
+  double *dl = nullptr, *dh = nullptr;
+  if (!seam) {
+    if (!first) dl = H->peer_lo[dst_role];
+    if (!last) dh = H->peer_hi[dst_role];
+  } else {
+    if (first) dl = H->peer_lo[dst_role];
+    if (last) dh = H->peer_hi[dst_role];
+  }
+  if (!dl && !dh) return 0;
+  const int npp = p->nsp * p->nsp, nplanes = 4 * npp;
+  dim3 blk(128), grd((p->nx + 2 + 127) / 128, nplanes);
+  halo_push_kernel<<<grd, blk, 0, p->ctx->stream>>>(src, dl, dh, p->nx, p->ny, H->nyl_lo, H->nyl_hi,
+                                                    nplanes, npp, seam ? flip_var : -1,
+                                                    seam ? flip_var : -1);
+  if (int rc = check_launch("halo_push_kernel")) return rc;
+  return 1;
+}
+
+// raise this rank's epoch in both neighbours' mailboxes, after everything queued so far
+int frb_halo_signal(frb_prob_t p) {
+  if (!frb_halo_active(p)) return 0;
+  FrbHalo *H = p->halo;
+  H->epoch += 1;
+  // I am the "hi" neighbour of the rank below and the "lo" neighbour of the rank above
+  halo_signal_kernel<<<1, 1, 0, p->ctx->stream>>>(H->flags_lo + 1, H->flags_hi + 0, H->epoch);
+  if (int rc = check_launch("halo_signal_kernel")) return rc;
+  return 1;
+}
+
+// block the stream until both neighbours have reached this rank's current epoch
+int frb_halo_wait(frb_prob_t p) {
+  if (!frb_halo_active(p)) return 0;
+  FrbHalo *H = p->halo;
+  halo_wait_kernel<<<1, 1, 0, p->ctx->stream>>>(H->flags, 1, 1, H->epoch, 5000000000ull);
+  if (int rc = check_launch("halo_wait_kernel")) return rc;
+  return 1;
+}
+
+int frb_halo_check_timeout(frb_prob_t p) {
+  if (!frb_halo_active(p)) return 0;
+  unsigned long long err = 0;
+  FRB_CUDA(cudaMemcpy(&err, p->halo->flags + 2, sizeof err, cudaMemcpyDeviceToHost));
+  if (err) {
+    frb_set_error("halo wait timed out at epoch " + std::to_string(err) + " (a neighbour rank stalled)");
+    return FRB_ERR_PEER;
+  }
+  return 0;
+}

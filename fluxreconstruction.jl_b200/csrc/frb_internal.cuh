@@ -80,9 +80,16 @@ struct frb_prob_s {
   float last_ms = 0.f;
   int64_t last_launches = 0;
   int64_t launches = 0;
+  // per-stage profiling (event pairs around every stage launch)
+  bool profiling = false;
+  std::vector<cudaEvent_t> prof_events;  // pool
+  size_t prof_used = 0;
+  float stage_ms = 0.f;
+  int64_t stage_count = 0;
   // TMA descriptors for the marching kernel (opaque 128-byte CUtensorMap images)
   void *tmaps = nullptr;  // host copy, keyed by device pointer
   FrbHalo *halo = nullptr;
+  bool halo_pending = false;  // a signal was sent; wait for the neighbours before the next stage
 };
 
 // ---- kernel launchers (each returns the number of kernels launched or <0) --------
@@ -94,8 +101,19 @@ int frb_launch_euler2d_march(frb_prob_t p, const double *u, const double *ua, do
 bool frb_euler2d_march_supported(frb_prob_t p);
 int frb_launch_ns2d(frb_prob_t p, const double *u, const double *ua, double *out, FrbStage st);
 int frb_launch_ghost_fill2d(frb_prob_t p, double *u, int mode);
-int frb_launch_ring_copy2d(frb_prob_t p, const double *src, double *dst);
-int frb_launch_zero_ring2d(frb_prob_t p, double *dst);
+int frb_launch_ring_copy2d(frb_prob_t p, const double *src, double *dst, bool row0 = true, bool rowN = true);
+int frb_launch_ghost_x2d(frb_prob_t p, double *u, int mode);
+// frb_halo.cu
+bool frb_halo_active(frb_prob_t p);
+void frb_halo_swap_roles(frb_prob_t p, int a, int b);
+void frb_halo_stage_targets(frb_prob_t p, const double *out, double **dst_lo, double **dst_hi, int *nyl_lo,
+                            int *nyl_hi);
+int frb_halo_push(frb_prob_t p, const double *src, int dst_role, bool seam, int flip_var);
+int frb_halo_role(frb_prob_t p, const double *ptr);
+int frb_halo_signal(frb_prob_t p);
+int frb_halo_wait(frb_prob_t p);
+int frb_halo_check_timeout(frb_prob_t p);
+int frb_halo_rank(frb_prob_t p, int *nranks);
 int frb_launch_limiter1d(frb_prob_t p, double *u);
 int frb_launch_limiter2d(frb_prob_t p, double *u);
 int frb_launch_dirichlet_copy1d(frb_prob_t p, const double *src, double *dst);

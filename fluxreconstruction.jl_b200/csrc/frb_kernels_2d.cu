@@ -172,15 +172,15 @@ __global__ void ghost_y_kernel(double *__restrict__ u, int nx, int ny, int nplan
 }
 // copy (or zero) the ghost ring of every plane
 __global__ void ring_copy_kernel(const double *__restrict__ src, double *__restrict__ dst, int nx,
-                                 int ny, int nplanes) {
+                                 int ny, int nplanes, int row0, int rowN) {
   int t = blockIdx.x * blockDim.x + threadIdx.x;
   int p = blockIdx.y;
   const int NXG = nx + 2, NYG = ny + 2;
   const int nring = 2 * NXG + 2 * ny;
   if (t >= nring || p >= nplanes) return;
   int i, j;
-  if (t < NXG) { i = t; j = 0; }
-  else if (t < 2 * NXG) { i = t - NXG; j = NYG - 1; }
+  if (t < NXG) { i = t; j = 0; if (!row0) return; }
+  else if (t < 2 * NXG) { i = t - NXG; j = NYG - 1; if (!rowN) return; }
   else if (t < 2 * NXG + ny) { i = 0; j = t - 2 * NXG + 1; }
   else { i = NXG - 1; j = t - 2 * NXG - ny + 1; }
   size_t idx = i + (size_t)NXG * j + (size_t)NXG * NYG * p;
@@ -288,16 +288,33 @@ int frb_launch_ghost_fill2d(frb_prob_t p, double *u, int mode) {
   return 2;
 }
 
-int frb_launch_ring_copy2d(frb_prob_t p, const double *src, double *dst) {
+// row0 / rowN: whether the bottom / top ghost row is copied too (false for rows that a
+// neighbouring rank writes, see frb_halo.cu)
+int frb_launch_ring_copy2d(frb_prob_t p, const double *src, double *dst, bool row0, bool rowN) {
   const int nplanes = 4 * p->nsp * p->nsp;
   const int nring = 2 * (p->nx + 2) + 2 * p->ny;
   dim3 blk(128), grd((nring + 127) / 128, nplanes);
-  ring_copy_kernel<<<grd, blk, 0, p->ctx->stream>>>(src, dst, p->nx, p->ny, nplanes);
+  ring_copy_kernel<<<grd, blk, 0, p->ctx->stream>>>(src, dst, p->nx, p->ny, nplanes, row0, rowN);
   if (int rc = check_launch2("ring_copy_kernel")) return rc;
   return 1;
 }
 
-int frb_launch_zero_ring2d(frb_prob_t p, double *dst) { return frb_launch_ring_copy2d(p, nullptr, dst); }
+// the x half of the ghost fill only (all rows, halo rows included): used by the slab-parallel
+// path, where the y half is an exchange with the neighbouring ranks
+int frb_launch_ghost_x2d(frb_prob_t p, double *u, int mode) {
+  const int npp = p->nsp * p->nsp, nplanes = 4 * npp;
+  dim3 blk(128), gx((p->ny + 2 + 127) / 128, nplanes);
+  if (mode == FRB_GHOST_WAVE_X)
+    ghost_x_kernel<<<gx, blk, 0, p->ctx->stream>>>(u, p->nx, p->ny, nplanes, npp, p->nx, 1, -1, 1);
+  else if (mode == FRB_GHOST_WAVE_Y)
+    ghost_x_kernel<<<gx, blk, 0, p->ctx->stream>>>(u, p->nx, p->ny, nplanes, npp, p->nx, 1, 1, 1);
+  else {
+    frb_set_error("slab-parallel ghost fill supports the periodic wave modes");
+    return FRB_ERR_ARG;
+  }
+  if (int rc = check_launch2("ghost_x_kernel")) return rc;
+  return 1;
+}
 
 int frb_launch_limiter2d(frb_prob_t p, double *u) {
   dim3 blk(32, 4), grd((p->nx + 31) / 32, (p->ny + 3) / 4);

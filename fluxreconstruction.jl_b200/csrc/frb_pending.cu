@@ -19,13 +19,3 @@ extern "C" int32_t frb_rhs_pipelined(frb_prob_t, const double *, double *, int32
   return FRB_ERR_STATE;
 }
 
-extern "C" int32_t frb_halo_export(frb_prob_t, unsigned char *) {
-  frb_set_error("frb_halo_export: not implemented yet");
-  return FRB_ERR_STATE;
-}
-extern "C" int32_t frb_halo_connect(frb_prob_t, int32_t, int32_t, const unsigned char *,
-                                    const unsigned char *) {
-  frb_set_error("frb_halo_connect: not implemented yet");
-  return FRB_ERR_STATE;
-}
-extern "C" int32_t frb_halo_disconnect(frb_prob_t) { return FRB_OK; }

@@ -149,6 +149,15 @@ class _Problem:
         check(lib().frb_time_stage(self.h, int(stage_kind), int(iters), C.byref(ms)))
         return ms.value
 
+    def set_profiling(self, on=True):
+        check(lib().frb_set_profiling(self.h, 1 if on else 0))
+
+    def stage_timing(self):
+        """(summed device ms of the stage launches of the last step/rhs call, their count)"""
+        ms, n = C.c_float(), C.c_int64()
+        check(lib().frb_stage_timing(self.h, C.byref(ms), C.byref(n)))
+        return ms.value, n.value
+
     def last_timing(self):
         ms, n = C.c_float(), C.c_int64()
         check(lib().frb_last_timing(self.h, C.byref(ms), C.byref(n)))
@@ -282,3 +291,48 @@ def solve(prob, alg, dt, adaptive=False, **_):
     n = int(round((prob.tspan[1] - prob.tspan[0]) / dt))
     itg.step(n)
     return itg
+
+
+HALO_BLOB_BYTES = 4 * 64 + 8
+
+
+class DistributedEuler2D(Euler2DProblem):
+    """Row-slab parallel 2-D Euler problem: one process per GPU, this rank holds rows
+    ``slab.start .. slab.stop`` of the global mesh in a local array [nx+2, ny_local+2, nsp, nsp, 4].
+
+    ``dist`` is an initialised ``torch.distributed`` module (or anything with ``get_rank``,
+    ``get_world_size``, ``all_gather_object`` and ``barrier``): it is used once, to hand the
+    neighbours' CUDA-IPC blobs around.  Per-stage halo traffic never touches the host: the stage
+    kernel stores its boundary rows into the neighbour's memory over NVLink and raises a flag
+    (csrc/frb_halo.cu).  The global y seam follows the reference's frozen per-step ghost fill
+    (``ghost`` = "wave_x" / "wave_y", example/euler2d_wave.jl:127-132,159-164)."""
+
+    def __init__(self, u0_local, tspan, ps_local, gamma, dist, ctx=None, ghost="wave_x", kernel="auto"):
+        super().__init__(u0_local, tspan, ps_local, gamma, ctx=ctx, kernel=kernel)
+        self.dist = dist
+        self.rank, self.nranks = dist.get_rank(), dist.get_world_size()
+        self.set_hooks(ghost=ghost)
+        if self.nranks > 1:
+            blob = (C.c_ubyte * HALO_BLOB_BYTES)()
+            check(lib().frb_halo_export(self.h, blob))
+            blobs = [None] * self.nranks
+            dist.all_gather_object(blobs, bytes(blob))  # also orders every rank's upload before any push
+            lo = (C.c_ubyte * HALO_BLOB_BYTES).from_buffer_copy(blobs[(self.rank - 1) % self.nranks])
+            hi = (C.c_ubyte * HALO_BLOB_BYTES).from_buffer_copy(blobs[(self.rank + 1) % self.nranks])
+            check(lib().frb_halo_connect(self.h, self.rank, self.nranks, lo, hi))
+            dist.barrier()
+
+    def resync(self):
+        """after a new upload on every rank"""
+        if self.nranks > 1:
+            self.dist.barrier()
+            check(lib().frb_halo_sync(self.h))
+
+    def close(self):
+        if self.h and self.nranks > 1:
+            try:
+                self.dist.barrier()  # nobody unmaps while a neighbour may still be storing
+            except Exception:
+                pass
+            lib().frb_halo_disconnect(self.h)
+        super().close()

@@ -148,6 +148,16 @@ int32_t frb_time_stage(frb_prob_t prob, int32_t stage_kind, int32_t iters, float
  * kernels only, excluding host<->device copies) and kernels launched by it */
 int32_t frb_last_timing(frb_prob_t prob, float *ms, int64_t *kernel_launches);
 int32_t frb_set_kernel(frb_prob_t prob, int32_t kernel_kind);
+/* per-launch timing of the fused stage kernels inside frb_step / frb_rhs: when enabled,
+ * every stage launch is bracketed by CUDA events on the library stream; after the call
+ * returns, frb_stage_timing reports the summed device time of those launches and their
+ * count (the dominant-kernel figure of the roofline report). */
+int32_t frb_set_profiling(frb_prob_t prob, int32_t enabled);
+int32_t frb_stage_timing(frb_prob_t prob, float *ms_total, int64_t *stage_launches);
+
+/* ---- pinned host memory (for the host-buffer paths; replaces nothing in the reference) */
+int32_t frb_host_alloc(int64_t bytes, void **ptr);
+int32_t frb_host_free(void *ptr);
 
 /* ---- multi-GPU: element-slab partition along the slowest cell index ------------- */
 /* One process per GPU.  A rank's problem is created on its slab (2-D: ny_local rows,
@@ -157,13 +167,18 @@ int32_t frb_set_kernel(frb_prob_t prob, int32_t kernel_kind);
  * CUDA IPC handles the host exchanges out of band), then a flag is raised.
  * The reference has no distributed path: this is new surface. */
 #define FRB_IPC_HANDLE_BYTES 64
-/* export handles for this rank's halo mailbox; handle_out[FRB_IPC_HANDLE_BYTES] */
-int32_t frb_halo_export(frb_prob_t prob, unsigned char *handle_out);
-/* rank_lo / rank_hi: neighbour below / above (may be equal to self for a 1-rank ring:
- * pass NULL handles then); periodic says whether the global seam wraps per stage or
- * is a frozen ghost row */
+/* blob = 4 IPC handles (u, s1, s2, mailbox) + int32 ny_local */
+#define FRB_HALO_BLOB_BYTES (4 * FRB_IPC_HANDLE_BYTES + 8)
+/* export this rank's blob; the host exchanges blobs out of band (torch.distributed, MPI, ...) */
+int32_t frb_halo_export(frb_prob_t prob, unsigned char *blob_out);
+/* map the blobs of the rank below (rank-1 mod nranks) and above (rank+1 mod nranks) and send
+ * this rank's boundary rows of the resident state; call after every rank uploaded its slab.
+ * The global y seam (rank 0 <-> rank nranks-1) is the frozen per-step ghost row of the ghost
+ * mode set with frb_set_step_hooks; all other slab boundaries are exchanged every stage. */
 int32_t frb_halo_connect(frb_prob_t prob, int32_t rank, int32_t nranks,
-                         const unsigned char *handle_lo, const unsigned char *handle_hi);
+                         const unsigned char *blob_lo, const unsigned char *blob_hi);
+/* resend the boundary rows after a new frb_state_upload (every rank calls it) */
+int32_t frb_halo_sync(frb_prob_t prob);
 int32_t frb_halo_disconnect(frb_prob_t prob);
 
 #ifdef __cplusplus
