@@ -1,0 +1,80 @@
+"""CPU checks of the drop-in boundary: the C-ABI library builds for sm_100a, loads, exports every
+symbol include/frb200.h declares, matches the ctypes signatures, does not link the oracle, and fails
+loudly (no CPU fallback) when there is no CUDA device."""
+import ctypes
+import os
+import re
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "frb200.h")
+
+
+def declared_symbols():
+    src = open(HEADER).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(frb_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_header_symbols_are_exported(FR):
+    lib = FR.lib()
+    names = declared_symbols()
+    assert len(names) >= 30
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in frb200.h but not exported by libfrb200.so"
+
+
+def test_ctypes_signatures_cover_the_header(FR):
+    assert sorted(FR.SIGNATURES) == declared_symbols()
+
+
+def test_library_is_native_sm100a_and_free_of_the_oracle(FR):
+    nm = subprocess.run(["nm", "-D", FR.LIB_PATH], capture_output=True, text=True).stdout
+    assert "fro_" not in nm
+    ldd = subprocess.run(["ldd", FR.LIB_PATH], capture_output=True, text=True).stdout
+    assert "fr_oracle" not in ldd and "torch" not in ldd
+    sass = subprocess.run(["cuobjdump", "-lelf", FR.LIB_PATH], capture_output=True, text=True).stdout
+    assert "sm_100a" in sass
+
+
+def test_march_kernel_uses_tma_and_fp64_pipe(FR):
+    """SASS evidence (B200_PROFILING.md): UTMALDG = cp.async.bulk.tensor, DFMA = FP64 FMA."""
+    out = subprocess.run(["cuobjdump", "-sass", FR.LIB_PATH], capture_output=True, text=True).stdout
+    seg = out[out.index("euler2d_march_kernel"):]
+    assert "UTMALDG" in seg and "DFMA" in seg and "SYNCS" in seg
+
+
+def test_no_gpu_fails_loudly(FR):
+    from conftest import HAS_GPU
+
+    if HAS_GPU:
+        pytest.skip("a GPU is present")
+    with pytest.raises(FR.FRBError) as ei:
+        FR.Context()
+    assert "no CPU fallback" in str(ei.value)
+    ps = FR.FRPSpace1D(0.0, 1.0, 8, 2)
+    import numpy as np
+
+    with pytest.raises(FR.FRBError):
+        FR.FREulerProblem(np.ones((8, 3, 3), order="F"), (0, 1), ps, 5 / 3, "period")
+
+
+def test_argument_errors_do_not_need_a_gpu(FR):
+    lib = FR.lib()
+    out = ctypes.c_void_p()
+    assert lib.frb_ctx_create(0, None) == -1  # FRB_ERR_ARG
+    assert b"NULL" in lib.frb_last_error(None)
+    assert lib.frb_step(None, 0, 0.1, 1) == -1
+    assert lib.frb_state_len(None) == 0
+    assert lib.frb_prob_destroy(None) == 0
+
+
+def test_product_package_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "fluxreconstruction.jl_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                txt = open(os.path.join(dirpath, f)).read()
+                assert "fr_oracle" not in txt and "c_oracle" not in txt and "fro_" not in txt, f
