@@ -110,7 +110,7 @@ __device__ __forceinline__ void col_trace(const double *__restrict__ Uy, const d
 }
 
 // MINB = resident CTAs per SM the register budget is compiled for
-template <int NSP, int NBUF, int MINB>
+template <int NSP, int NBUF, int MINB, bool PREFETCH, bool COPYONLY = false>
 __global__ void __launch_bounds__(NSP * 32, MINB)
 euler2d_march_kernel(const __grid_constant__ CUtensorMap tmap, MarchParams P, FrbOps ops) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -183,7 +183,7 @@ euler2d_march_kernel(const __grid_constant__ CUtensorMap tmap, MarchParams P, Fr
     const double *const Ux = S.tile[0] + buf * kTile + offx;
     const double *const Uy = S.tile[0] + buf * kTile + offy;
     const size_t grow = goff + NXG * (size_t)j;
-    if (P.use_a && owner) {
+    if (PREFETCH && P.use_a && owner) {
       // pull this row's u_n into L2 now; the loads after the x pass then hit L2
       const double *pa = P.ua + grow;
 #pragma unroll
@@ -191,6 +191,24 @@ euler2d_march_kernel(const __grid_constant__ CUtensorMap tmap, MarchParams P, Fr
     }
     // tile q was already waited on as the "next" tile of step q-1 (or in the prologue)
 
+    if (COPYONLY) {  // measurement aid: the memory-access skeleton of the kernel without the math
+      __syncthreads();
+      mbar_wait(&S.bar[nbuf], ((q + 1) / NBUF) & 1);
+      const double *pa = P.ua + grow;
+      double *po = P.out + grow;
+#pragma unroll
+      for (int c = 0; c < 4 * NSP; ++c, pa += pstep, po += pstep) {
+        double v = P.cb * Uy[32 * NSP * c];
+        if (P.use_a && owner) v = fma(P.ca, __ldcs(pa), v);
+        if (owner) __stcs(po, v);
+      }
+      __syncthreads();
+      if (threadIdx.x == 0 && q + NBUF < ntiles) {
+        mbar_expect_tx(&S.bar[buf], kTileBytes);
+        tma_load_3d(S.tile[buf], &tmap, &S.bar[buf], c0, ja - 1 + q + NBUF, 0);
+      }
+      continue;
+    }
     // -------------------------------------------------------------- x pass: row l = t
     {
       double w[NSP][4], f[NSP][4];
@@ -288,21 +306,6 @@ euler2d_march_kernel(const __grid_constant__ CUtensorMap tmap, MarchParams P, Fr
         ht[0] = h.f0; ht[1] = h.f1; ht[2] = h.f2; ht[3] = h.f3;
       }
       double *po = P.out + grow;
-      // peer halo rows (CTA-uniform conditions): row 1 -> row nyl_lo+1 below, row ny -> row 0 above
-      double *pp = nullptr;
-      size_t ppstep = 0;
-      if (j == 1 && P.peer_lo) {
-        const size_t NEl = NXG * (size_t)(P.nyl_lo + 2);
-        pp = P.peer_lo + i + NXG * (size_t)(P.nyl_lo + 1) + NEl * (size_t)t;
-        ppstep = NEl * NSP;
-      }
-      double *pq = nullptr;
-      size_t pqstep = 0;
-      if (j == P.ny && P.peer_hi) {
-        const size_t NEh = NXG * (size_t)(P.nyl_hi + 2);
-        pq = P.peer_hi + i + NEh * (size_t)t;
-        pqstep = NEh * NSP;
-      }
 #pragma unroll
       for (int m = 0; m < 4; ++m) {
         double gB = g[0][m] * ops.ll[0], gT = g[0][m] * ops.lr[0];
@@ -322,13 +325,27 @@ euler2d_march_kernel(const __grid_constant__ CUtensorMap tmap, MarchParams P, Fr
           double dx = xdy[32 * NSP * (l + NSP * m)];
           double v = fma(P.cys, d, fma(P.cxs, dx, P.cb * w[l][m]));
           if (P.use_a) v = fma(P.ca, un[l][m], v);
-          if (owner) {
-            __stcs(po, v);
-            if (pp) { *pp = v; pp += ppstep; }
-            if (pq) { *pq = v; pq += pqstep; }
-          }
+          if (owner) __stcs(po, v);
         }
         hb[m] = ht[m];
+      }
+    }
+    // slab-parallel path: the first / last owned row also goes straight into the halo row of the
+    // rank below / above (peer memory over NVLink).  CTA-uniform, two rows per strip: each thread
+    // forwards the values it has just stored (its own writes, L2-hot).
+    if ((j == 1 && P.peer_lo) || (j == P.ny && P.peer_hi)) {
+      if (owner) {
+        const double *src = P.out + grow;
+        if (j == 1 && P.peer_lo) {
+          const size_t NEl = NXG * (size_t)(P.nyl_lo + 2);
+          double *dst = P.peer_lo + i + NXG * (size_t)(P.nyl_lo + 1) + NEl * (size_t)t;
+          for (int c = 0; c < 4 * NSP; ++c) dst[NEl * NSP * c] = src[pstep * c];
+        }
+        if (j == P.ny && P.peer_hi) {
+          const size_t NEh = NXG * (size_t)(P.nyl_hi + 2);
+          double *dst = P.peer_hi + i + NEh * (size_t)t;
+          for (int c = 0; c < 4 * NSP; ++c) dst[NEh * NSP * c] = src[pstep * c];
+        }
       }
     }
     __syncthreads();  // (B) every read of tile[buf], xd, xrp is done
@@ -380,27 +397,21 @@ void frb_march_release(frb_prob_t p) {
 }
 
 static int march_rows_per_seg(frb_prob_t p, int ctas_per_sm) {
-  // choose the segment count so that the grid is close to a whole number of waves of
-  // (SMs x resident CTAs); every segment re-reads two halo rows
+  // Segments of about 32 rows: every segment re-reads two halo rows (6 % extra reads at 32), and
+  // the grid (strips x segments) is then many waves of SMs x resident CTAs, so the tail is short.
+  // Measured at 2048^2, p3 on B200: 16..32 rows are within 1 % of each other, 108 rows (3 waves)
+  // is 3-4 % slower.  FRB_MARCH_ROWS overrides.
   int forced = env_int("FRB_MARCH_ROWS", 0);
   if (forced > 0) return forced < p->ny ? forced : p->ny;
   const int strips = (p->nx + kOwn - 1) / kOwn;
   const int slots = p->ctx->sm_count * ctas_per_sm;
-  int best_rows = p->ny;
-  double best_cost = 1e300;
-  for (int nseg = 1; nseg <= p->ny; ++nseg) {
-    int rows = (p->ny + nseg - 1) / nseg;
-    if (rows < 8 && nseg > 1) break;
-    int segs = (p->ny + rows - 1) / rows;
-    long ctas = (long)strips * segs;
-    long waves = (ctas + slots - 1) / slots;
-    double cost = (double)waves * (rows + 2.0) * (1.0 + 1e-6 * segs);
-    if (cost < best_cost) { best_cost = cost; best_rows = rows; }
-  }
-  return best_rows;
+  int nseg = (p->ny + 31) / 32;
+  // small meshes: make sure every SM slot gets a CTA if the row count allows it
+  while ((long)strips * nseg < slots && (p->ny + nseg) / (nseg + 1) >= 4) ++nseg;
+  return (p->ny + nseg - 1) / nseg;
 }
 
-template <int NSP, int NBUF, int MINB>
+template <int NSP, int NBUF, int MINB, bool PREFETCH, bool COPYONLY = false>
 static int launch_march(frb_prob_t p, const CUtensorMap &map, MarchParams mp) {
   mp.rows_per_seg = march_rows_per_seg(p, MINB);
   const int strips = (p->nx + kOwn - 1) / kOwn;
@@ -408,14 +419,14 @@ static int launch_march(frb_prob_t p, const CUtensorMap &map, MarchParams mp) {
   const size_t smem = sizeof(Smem<NSP, NBUF>) + 128;
   static bool attr_done = false;
   if (!attr_done) {
-    FRB_CUDA(cudaFuncSetAttribute(euler2d_march_kernel<NSP, NBUF, MINB>,
+    FRB_CUDA(cudaFuncSetAttribute(euler2d_march_kernel<NSP, NBUF, MINB, PREFETCH, COPYONLY>,
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    FRB_CUDA(cudaFuncSetAttribute(euler2d_march_kernel<NSP, NBUF, MINB>,
+    FRB_CUDA(cudaFuncSetAttribute(euler2d_march_kernel<NSP, NBUF, MINB, PREFETCH, COPYONLY>,
                                   cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     attr_done = true;
   }
   dim3 grd(strips, segs), blk(NSP * 32);
-  euler2d_march_kernel<NSP, NBUF, MINB><<<grd, blk, smem, p->ctx->stream>>>(map, mp, p->ops);
+  euler2d_march_kernel<NSP, NBUF, MINB, PREFETCH, COPYONLY><<<grd, blk, smem, p->ctx->stream>>>(map, mp, p->ops);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return frb_cuda_fail(e, "euler2d_march_kernel", __FILE__, __LINE__);
   return 1;
@@ -467,6 +478,11 @@ int frb_launch_euler2d_march(frb_prob_t p, const double *u, const double *ua, do
     mp.ca = st.ca; mp.cb = st.cb; mp.use_a = st.use_a;
     mp.cxs = -cdt / p->Jx; mp.cys = -cdt / p->Jy;
   }
-  if (p->nsp == 4) return launch_march<4, 3, 3>(p, it->second, mp);  // 72 KB smem, 168 regs
-  return launch_march<3, 3, 4>(p, it->second, mp);
+  const bool pf = env_int("FRB_MARCH_PREFETCH", 1) != 0;  // L2 prefetch of the u_n row (+10 % on 24-B stages)
+  if (p->nsp == 4) {  // 72 KB smem, 168 regs
+    if (env_int("FRB_MARCH_COPYONLY", 0)) return launch_march<4, 3, 3, true, true>(p, it->second, mp);
+    if (pf) return launch_march<4, 3, 3, true>(p, it->second, mp);
+    return launch_march<4, 3, 3, false>(p, it->second, mp);
+  }
+  return launch_march<3, 3, 4, false>(p, it->second, mp);
 }
