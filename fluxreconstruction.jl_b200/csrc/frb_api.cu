@@ -102,6 +102,10 @@ static int fill_ops(const frb_operators *o, FrbOps *dst, int *nsp_out, bool need
     if (o->dlr) dst->dlr[q] = o->dlr[q];
     for (int k = 0; k < nsp; ++k) dst->lpdm[q * FRB_NSPMAX + k] = o->lpdm[q + nsp * k];  // [m,k] col-major
   }
+  for (int k = 0; k < nsp; ++k)
+    for (int q = 0; q < nsp; ++q)
+      dst->dmod[k * FRB_NSPMAX + q] =
+          dst->lpdm[k * FRB_NSPMAX + q] - dst->dgl[k] * dst->ll[q] - dst->dgr[k] * dst->lr[q];
   *nsp_out = nsp;
   return FRB_OK;
 }

@@ -84,6 +84,7 @@ struct MarchParams {
   // of the rank below / above (peer memory over NVLink); NULL when there is no such neighbour
   double *peer_lo, *peer_hi;
   int nyl_lo, nyl_hi;
+  int pfdist;  // rows of look-ahead of the u_n L2 prefetch
 };
 
 template <int NSP, int NBUF>
@@ -157,6 +158,13 @@ euler2d_march_kernel(const __grid_constant__ CUtensorMap tmap, MarchParams P, Fr
   const size_t pstep = NE * NSP;
   const size_t goff = i + NE * (size_t)t;
 
+  if (PREFETCH && P.use_a && owner) {  // u_n rows of the first kPfDist steps
+    for (int r = 0; r < P.pfdist && ja + r <= jb; ++r) {
+      const double *pa = P.ua + goff + NXG * (size_t)(ja + r);
+      for (int c = 0; c < 4 * NSP; ++c, pa += pstep) prefetch_l2(pa);
+    }
+  }
+
   // ---- prologue: common flux on the bottom face of row ja from tiles 0 (row ja-1) and 1
   double hb[4];
   {
@@ -183,9 +191,10 @@ euler2d_march_kernel(const __grid_constant__ CUtensorMap tmap, MarchParams P, Fr
     const double *const Ux = S.tile[0] + buf * kTile + offx;
     const double *const Uy = S.tile[0] + buf * kTile + offy;
     const size_t grow = goff + NXG * (size_t)j;
-    if (PREFETCH && P.use_a && owner) {
-      // pull this row's u_n into L2 now; the loads after the x pass then hit L2
-      const double *pa = P.ua + grow;
+    if (PREFETCH && P.use_a && owner && j + P.pfdist <= jb) {
+      // pull the u_n row needed kPfDist steps from now into L2; the loads after the x pass of
+      // that step then hit L2 instead of waiting on DRAM
+      const double *pa = P.ua + grow + NXG * (size_t)P.pfdist;
 #pragma unroll
       for (int c = 0; c < 4 * NSP; ++c, pa += pstep) prefetch_l2(pa);
     }
@@ -228,37 +237,34 @@ euler2d_march_kernel(const __grid_constant__ CUtensorMap tmap, MarchParams P, Fr
         xrpx[32 * k] = rr;
         xrpx[32 * (NSP * NSP + k)] = p;
       }
-      double uL[4], uR[4], fL[4], fR[4];
+      double uL[4], uR[4];
 #pragma unroll
       for (int m = 0; m < 4; ++m) {
         double a = w[0][m] * ops.ll[0], b = w[0][m] * ops.lr[0];
-        double c = f[0][m] * ops.ll[0], d = f[0][m] * ops.lr[0];
 #pragma unroll
         for (int q2 = 1; q2 < NSP; ++q2) {
           a = fma(w[q2][m], ops.ll[q2], a);
           b = fma(w[q2][m], ops.lr[q2], b);
-          c = fma(f[q2][m], ops.ll[q2], c);
-          d = fma(f[q2][m], ops.lr[q2], d);
         }
-        uL[m] = a; uR[m] = b; fL[m] = c; fR[m] = d;
+        uL[m] = a; uR[m] = b;
       }
       // left face: HLL(u_face[i-1,j,2,l,:], u_face[i,j,4,l,:])  (euler2d_wave.jl:69-74)
       double n0 = __shfl_up_sync(0xffffffffu, uR[0], 1), n1 = __shfl_up_sync(0xffffffffu, uR[1], 1);
       double n2 = __shfl_up_sync(0xffffffffu, uR[2], 1), n3 = __shfl_up_sync(0xffffffffu, uR[3], 1);
       frb::Flux4 hl = frb::hll4_fast(n0, n1, n2, n3, uL[0], uL[1], uL[2], uL[3], gamma, gm1);
-      double hr0 = __shfl_down_sync(0xffffffffu, hl.f0, 1), hr1 = __shfl_down_sync(0xffffffffu, hl.f1, 1);
-      double hr2 = __shfl_down_sync(0xffffffffu, hl.f2, 1), hr3 = __shfl_down_sync(0xffffffffu, hl.f3, 1);
-      const double cL[4] = {hl.f0 - fL[0], hl.f1 - fL[1], hl.f2 - fL[2], hl.f3 - fL[3]};
-      const double cR[4] = {hr0 - fR[0], hr1 - fR[1], hr2 - fR[2], hr3 - fR[3]};
+      const double hL[4] = {hl.f0, hl.f1, hl.f2, hl.f3};
+      const double hR[4] = {__shfl_down_sync(0xffffffffu, hl.f0, 1), __shfl_down_sync(0xffffffffu, hl.f1, 1),
+                            __shfl_down_sync(0xffffffffu, hl.f2, 1), __shfl_down_sync(0xffffffffu, hl.f3, 1)};
+      // d/dr + correction with the flux traces folded into dmod (see FrbOps)
 #pragma unroll
       for (int m = 0; m < 4; ++m)
 #pragma unroll
         for (int k = 0; k < NSP; ++k) {
-          double d = f[0][m] * ops.lpdm[k * FRB_NSPMAX];
+          double d = f[0][m] * ops.dmod[k * FRB_NSPMAX];
 #pragma unroll
-          for (int q2 = 1; q2 < NSP; ++q2) d = fma(f[q2][m], ops.lpdm[k * FRB_NSPMAX + q2], d);
-          d = fma(cL[m], ops.dgl[k], d);
-          d = fma(cR[m], ops.dgr[k], d);
+          for (int q2 = 1; q2 < NSP; ++q2) d = fma(f[q2][m], ops.dmod[k * FRB_NSPMAX + q2], d);
+          d = fma(hL[m], ops.dgl[k], d);
+          d = fma(hR[m], ops.dgr[k], d);
           xdx[32 * (k + NSP * NSP * m)] = d;
         }
     }
@@ -308,20 +314,13 @@ euler2d_march_kernel(const __grid_constant__ CUtensorMap tmap, MarchParams P, Fr
       double *po = P.out + grow;
 #pragma unroll
       for (int m = 0; m < 4; ++m) {
-        double gB = g[0][m] * ops.ll[0], gT = g[0][m] * ops.lr[0];
-#pragma unroll
-        for (int q2 = 1; q2 < NSP; ++q2) {
-          gB = fma(g[q2][m], ops.ll[q2], gB);
-          gT = fma(g[q2][m], ops.lr[q2], gT);
-        }
-        const double cB = hb[m] - gB, cT = ht[m] - gT;
 #pragma unroll
         for (int l = 0; l < NSP; ++l, po += pstep) {
-          double d = g[0][m] * ops.lpdm[l * FRB_NSPMAX];
+          double d = g[0][m] * ops.dmod[l * FRB_NSPMAX];
 #pragma unroll
-          for (int q2 = 1; q2 < NSP; ++q2) d = fma(g[q2][m], ops.lpdm[l * FRB_NSPMAX + q2], d);
-          d = fma(cB, ops.dgl[l], d);
-          d = fma(cT, ops.dgr[l], d);
+          for (int q2 = 1; q2 < NSP; ++q2) d = fma(g[q2][m], ops.dmod[l * FRB_NSPMAX + q2], d);
+          d = fma(hb[m], ops.dgl[l], d);
+          d = fma(ht[m], ops.dgr[l], d);
           double dx = xdy[32 * NSP * (l + NSP * m)];
           double v = fma(P.cys, d, fma(P.cxs, dx, P.cb * w[l][m]));
           if (P.use_a) v = fma(P.ca, un[l][m], v);
@@ -468,6 +467,7 @@ int frb_launch_euler2d_march(frb_prob_t p, const double *u, const double *ua, do
   mp.nx = p->nx;
   mp.ny = p->ny;
   mp.rows_per_seg = 0;
+  mp.pfdist = env_int("FRB_MARCH_PFDIST", 0);
   mp.gamma = p->gamma;
   frb_halo_stage_targets(p, out, &mp.peer_lo, &mp.peer_hi, &mp.nyl_lo, &mp.nyl_hi);
   if (st.rhs_only) {

@@ -16,6 +16,11 @@ struct FrbOps {
   double ll[FRB_NSPMAX], lr[FRB_NSPMAX], dgl[FRB_NSPMAX], dgr[FRB_NSPMAX];
   double dll[FRB_NSPMAX], dlr[FRB_NSPMAX];
   double lpdm[FRB_NSPMAX * FRB_NSPMAX];
+  // lpdm with the flux-trace part of the correction folded in:
+  //   dmod[k][q] = lpdm[k][q] - dgl[k]*ll[q] - dgr[k]*lr[q]
+  // so that  sum_q lpdm[k][q] f[q] + (fhatL - f.ll) dgl[k] + (fhatR - f.lr) dgr[k]
+  //        = sum_q dmod[k][q] f[q] + fhatL dgl[k] + fhatR dgr[k]
+  double dmod[FRB_NSPMAX * FRB_NSPMAX];
 };
 
 // One Runge-Kutta stage in the fused form  out = ca*ua + cb*u + cdt*L(u).

@@ -1,0 +1,122 @@
+# FRB200.jl -- the thin Julia shim a FluxReconstruction.jl maintainer would add to route the
+# semi-discrete residual and the explicit step through libfrb200.so (include/frb200.h).
+#
+# Julia is not installed in the build image, so this file has not been executed there; it is
+# written against the header, and every call below has a ctypes twin in
+# fluxreconstruction.jl_b200/_lib.py that IS exercised by tests/.
+#
+#   using FluxReconstruction, OrdinaryDiffEq
+#   include("FRB200.jl"); using .FRB200
+#   ps   = FRPSpace2D(0.0, 1.0, 2048, 0.0, 1.0, 2048, 3, 1, 1)
+#   prob = FRB200.Euler2DProblem(u0, ps, γ)               # uploads parent(u0)
+#   ode  = ODEProblem(FRB200.rhs!(prob), u0, tspan, p)     # drop-in f!(du,u,p,t)
+#   # or, device-resident stepping (what example/euler2d_wave.jl:125-135 does, fused):
+#   FRB200.set_step_hooks!(prob; ghost = :wave_x)
+#   FRB200.step!(prob, :midpoint, dt, nt); u1 = FRB200.download(prob)
+module FRB200
+
+const lib = get(ENV, "FRB200_LIB", joinpath(@__DIR__, "..", "fluxreconstruction.jl_b200", "lib", "libfrb200.so"))
+
+struct Operators
+    deg::Int32
+    ll::Ptr{Float64}; lr::Ptr{Float64}; lpdm::Ptr{Float64}
+    dgl::Ptr{Float64}; dgr::Ptr{Float64}; dll::Ptr{Float64}; dlr::Ptr{Float64}
+end
+
+last_error() = unsafe_string(ccall((:frb_last_error, lib), Cstring, (Ptr{Cvoid},), C_NULL))
+check(rc) = rc == 0 ? nothing : error("libfrb200 error $rc: $(last_error())")
+
+mutable struct Context
+    h::Ptr{Cvoid}
+    function Context(device::Integer = -1)
+        r = Ref{Ptr{Cvoid}}(C_NULL)
+        check(ccall((:frb_ctx_create, lib), Int32, (Int32, Ref{Ptr{Cvoid}}), device, r))
+        finalizer(c -> ccall((:frb_ctx_destroy, lib), Int32, (Ptr{Cvoid},), c.h), new(r[]))
+    end
+end
+const default_ctx = Ref{Union{Nothing,Context}}(nothing)
+ctx() = (default_ctx[] === nothing && (default_ctx[] = Context()); default_ctx[])
+
+mutable struct Problem
+    h::Ptr{Cvoid}
+    dims::Dims
+    keep::Vector{Any}      # operator arrays stay rooted while the handle lives
+end
+destroy!(p::Problem) = (p.h != C_NULL && ccall((:frb_prob_destroy, lib), Int32, (Ptr{Cvoid},), p.h); p.h = C_NULL)
+
+# ps.ll, ps.lr, ps.dl, ps.dhl, ps.dhr (struct.jl:49-51,63-64) are passed as they are: FRPSpace
+# remains the single source of truth.  ps.dl is column-major [m,k], exactly what the ABI expects.
+function operators(ps)
+    keep = Any[Vector{Float64}(ps.ll), Vector{Float64}(ps.lr), Matrix{Float64}(ps.dl),
+               Vector{Float64}(ps.dhl), Vector{Float64}(ps.dhr), Vector{Float64}(ps.dll), Vector{Float64}(ps.dlr)]
+    Operators(Int32(ps.deg), map(pointer, keep)...), keep
+end
+
+# FRAdvectionProblem(u, tspan, ps, a, bc)  -- src/Equation/eq_advection.jl:1-26
+function AdvectionProblem(u::Matrix{Float64}, ps, a, bc::Symbol; variant = :packaged)
+    ops, keep = operators(ps); J = Vector{Float64}(ps.J[1:size(u, 1)]); push!(keep, J)
+    r = Ref{Ptr{Cvoid}}(C_NULL)
+    GC.@preserve keep check(ccall((:frb_advection1d_create, lib), Int32,
+        (Ptr{Cvoid}, Int32, Ref{Operators}, Ptr{Float64}, Float64, Int32, Int32, Ref{Ptr{Cvoid}}),
+        ctx().h, size(u, 1), ops, J, a, bc == :period ? 1 : 0, variant == :lowlevel ? 1 : 0, r))
+    p = finalizer(destroy!, Problem(r[], size(u), keep)); upload!(p, u); p
+end
+
+# FREulerProblem(u, tspan, ps, γ, bc)  -- src/Equation/eq_euler.jl:1-27
+function EulerProblem(u::Array{Float64,3}, ps, γ, bc::Symbol)
+    ops, keep = operators(ps); J = Vector{Float64}(ps.J[1:size(u, 1)]); push!(keep, J)
+    r = Ref{Ptr{Cvoid}}(C_NULL)
+    GC.@preserve keep check(ccall((:frb_euler1d_create, lib), Int32,
+        (Ptr{Cvoid}, Int32, Ref{Operators}, Ptr{Float64}, Float64, Int32, Ref{Ptr{Cvoid}}),
+        ctx().h, size(u, 1), ops, J, γ, bc == :period ? 1 : 0, r))
+    p = finalizer(destroy!, Problem(r[], size(u), keep)); upload!(p, u); p
+end
+
+# dudt! of example/euler2d_wave.jl:35-107; u0 is the OffsetArray 0:nx+1 x 0:ny+1 x nsp x nsp x 4
+function Euler2DProblem(u0, ps, γ)
+    A = parent(u0)::Array{Float64,5}
+    ops, keep = operators(ps)
+    r = Ref{Ptr{Cvoid}}(C_NULL)
+    Jx, Jy = ps.J[1, 1][1, 1][1, 1], ps.J[1, 1][1, 1][2, 2]     # diag of the 2x2 Jacobian (struct.jl:135)
+    GC.@preserve keep check(ccall((:frb_euler2d_create, lib), Int32,
+        (Ptr{Cvoid}, Int32, Int32, Ref{Operators}, Float64, Float64, Float64, Ref{Ptr{Cvoid}}),
+        ctx().h, size(A, 1) - 2, size(A, 2) - 2, ops, Jx, Jy, γ, r))
+    p = finalizer(destroy!, Problem(r[], size(A), keep)); upload!(p, A); p
+end
+
+# mol! of example/bgk_wave.jl:69-129
+function BGKProblem(f0::Array{Float64,3}, ps, velo, weights, τ = 1e-2)
+    ops, keep = operators(ps)
+    dx = Vector{Float64}(ps.dx[1:size(f0, 1)]); v = Vector{Float64}(velo); w = Vector{Float64}(weights)
+    append!(keep, (dx, v, w)); r = Ref{Ptr{Cvoid}}(C_NULL)
+    GC.@preserve keep check(ccall((:frb_bgk1d_create, lib), Int32,
+        (Ptr{Cvoid}, Int32, Int32, Ref{Operators}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Float64, Ref{Ptr{Cvoid}}),
+        ctx().h, size(f0, 1), size(f0, 2), ops, dx, v, w, τ, r))
+    p = finalizer(destroy!, Problem(r[], size(f0), keep)); upload!(p, f0); p
+end
+
+upload!(p::Problem, u) = GC.@preserve u check(ccall((:frb_state_upload, lib), Int32, (Ptr{Cvoid}, Ptr{Float64}), p.h, parent(u)))
+function download(p::Problem)
+    u = Array{Float64}(undef, p.dims)
+    GC.@preserve u check(ccall((:frb_state_download, lib), Int32, (Ptr{Cvoid}, Ptr{Float64}), p.h, u)); u
+end
+
+# the SciML in-place RHS: ODEProblem(rhs!(prob), u0, tspan, p)
+rhs!(prob::Problem) = function (du, u, p, t)
+    GC.@preserve du u check(ccall((:frb_rhs, lib), Int32, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Float64),
+                                  prob.h, parent(u), parent(du), t))
+    nothing
+end
+
+const SCHEME = Dict(:euler => 0, :midpoint => 1, :ssprk3 => 2)
+const GHOST = Dict(:none => -1, :wave_x => 0, :wave_y => 1, :copy => 2)
+set_step_hooks!(p::Problem; ghost = :none, limiter_weights = nothing) = check(ccall((:frb_set_step_hooks, lib), Int32,
+    (Ptr{Cvoid}, Int32, Ptr{Float64}), p.h, GHOST[ghost], limiter_weights === nothing ? C_NULL : pointer(limiter_weights)))
+step!(p::Problem, scheme::Symbol, dt, nsteps = 1) = check(ccall((:frb_step, lib), Int32,
+    (Ptr{Cvoid}, Int32, Float64, Int32), p.h, SCHEME[scheme], dt, nsteps))
+function positive_limiter!(p::Problem, weights)      # src/dissipation.jl:61-206 on every interior cell
+    nbad = Ref{Int32}(0)
+    check(ccall((:frb_limiter_positivity, lib), Int32, (Ptr{Cvoid}, Ptr{Float64}, Ref{Int32}), p.h, weights, nbad)); nbad[]
+end
+
+end # module
