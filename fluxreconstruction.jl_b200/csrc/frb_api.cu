@@ -232,6 +232,29 @@ extern "C" int32_t frb_bgk1d_create(frb_ctx_t ctx, int32_t ncell, int32_t nu,
   return FRB_OK;
 }
 
+extern "C" int32_t frb_ns2d_create(frb_ctx_t ctx, int32_t nx, int32_t ny, const frb_operators *ops,
+                                   double Jx, double Jy, double inK, double gamma, double mu_ref,
+                                   double omega, double dt, double lid_u, double lambda_wall,
+                                   frb_prob_t *out) {
+  FRB_REQUIRE(ctx && out, FRB_ERR_ARG, "frb_ns2d_create: NULL argument");
+  FRB_REQUIRE(nx >= 1 && ny >= 1 && Jx > 0 && Jy > 0 && dt > 0, FRB_ERR_ARG, "frb_ns2d_create: bad sizes");
+  frb_prob_t p = new frb_prob_s();
+  p->ctx = ctx; p->kind = K_NS2D; p->nx = nx; p->ny = ny; p->Jx = Jx; p->Jy = Jy; p->gamma = gamma;
+  p->gks_K = inK; p->gks_mu = mu_ref; p->gks_omega = omega; p->gks_dt = dt; p->lid_u = lid_u;
+  p->lambda_wall = lambda_wall;
+  FRB_TRY(fill_ops(ops, &p->ops, &p->nsp, true));
+  if (p->nsp > 4) {
+    frb_set_error("frb_ns2d_create: deg must be in 1..3");
+    frb_prob_destroy(p);
+    return FRB_ERR_ARG;
+  }
+  p->len = (int64_t)(nx + 2) * (ny + 2) * p->nsp * p->nsp * 4;
+  p->dofs = (int64_t)nx * ny * p->nsp * p->nsp * 4;
+  FRB_TRY(alloc_common(p));
+  *out = p;
+  return FRB_OK;
+}
+
 extern "C" int64_t frb_state_len(frb_prob_t p) { return p ? p->len : 0; }
 extern "C" int64_t frb_interior_dofs(frb_prob_t p) { return p ? p->dofs : 0; }
 
@@ -456,7 +479,7 @@ static int one_step(frb_prob_t p, int scheme, double dt) {
     if (n < 0) return n;
     p->launches += n;
   }
-  if (is2d(p)) {
+  if (p->kind == K_EULER2D) {
     // ghosts are frozen across the stages of a step (du = 0 there): give the stage buffers the
     // same ring as u_n.  Rows owned by a neighbouring rank are excluded (the neighbour writes them).
     int nr = 1, rk = frb_halo_rank(p, &nr);

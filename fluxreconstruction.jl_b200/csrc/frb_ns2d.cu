@@ -1,0 +1,389 @@
+// 2-D Navier-Stokes with the gas-kinetic (GKS) flux: dudt! + boundary! of
+// example/ns_cavity.jl:147-344 with the in-script flux_gks! overloads (:49-145), fused with the
+// explicit stage update.  State layout u[4, ns, nr, ny+2, nx+2] (variable fastest, element
+// contiguous: 4*nsp^2 doubles; ns_cavity.jl:33).
+//
+// The path is FP64-compute-bound (erfc, exp, pow and ~2 k flops per interface point), not
+// HBM-bound: one thread owns one element, keeps its nsp^2 x 4 block in registers/local memory,
+// recomputes the four neighbour traces and slopes it needs, and evaluates the interface flux
+// on its own four faces (each interface is therefore evaluated by both neighbours -- the
+// price of a single pass without a flux round trip through HBM).
+//
+// [KB] closures restated from KitBase.jl 0.9: gauss_moments, moments_conserve,
+// moments_conserve_slope, pdf_slope, vhs_collision_time.  Reference quirks kept: the left
+// cell's interface slope uses dll and the right cell's dlr (:213-214,:244-245); slopes are not
+// rotated on y faces (:260); Mv of the LEFT state in the right state's time slope (:102).
+#include "frb_internal.cuh"
+
+namespace {
+
+struct Prim4 {
+  double rho, U, V, lam;
+};
+__device__ __forceinline__ Prim4 conserve_prim(const double *w, double gm1) {
+  Prim4 p;
+  p.rho = w[0];
+  p.U = w[1] / w[0];
+  p.V = w[2] / w[0];
+  p.lam = 0.5 * w[0] / gm1 / (w[3] - 0.5 * (w[1] * w[1] + w[2] * w[2]) / w[0]);
+  return p;
+}
+
+// moments <u^n> of a Maxwellian: full (Mu), v (Mv) and the half-space ones (MuL: u>0, MuR: u<0)
+struct Moments {
+  double Mu[7], Mv[7], Mxi[3];
+};
+__device__ __forceinline__ void moments_v(double V, double lam, double *Mv) {
+  Mv[0] = 1.0;
+  Mv[1] = V;
+#pragma unroll
+  for (int i = 2; i <= 6; ++i) Mv[i] = V * Mv[i - 1] + 0.5 * (i - 1) * Mv[i - 2] / lam;
+}
+__device__ __forceinline__ void moments_half(double U, double lam, double *MuL, double *MuR) {
+  const double sl = sqrt(lam);
+  const double e = 0.5 * exp(-lam * U * U) / sqrt(3.14159265358979323846 * lam);
+  MuL[0] = 0.5 * erfc(-sl * U);
+  MuL[1] = U * MuL[0] + e;
+  MuR[0] = 0.5 * erfc(sl * U);
+  MuR[1] = U * MuR[0] - e;
+#pragma unroll
+  for (int i = 2; i <= 6; ++i) {
+    MuL[i] = U * MuL[i - 1] + 0.5 * (i - 1) * MuL[i - 2] / lam;
+    MuR[i] = U * MuR[i - 1] + 0.5 * (i - 1) * MuR[i - 2] / lam;
+  }
+}
+__device__ __forceinline__ void mxi(double K, double lam, double *M) {
+  M[0] = 1.0;
+  M[1] = 0.5 * K / lam;
+  M[2] = (K * K + 2.0 * K) / (4.0 * lam * lam);
+}
+// [KB] moments_conserve(Mu, Mv, Mw, a, b, d)
+__device__ __forceinline__ void mom_cons(const double *Mu, const double *Mv, const double *Mw, int a,
+                                         int b, int d, double *uv) {
+  uv[0] = Mu[a] * Mv[b] * Mw[d / 2];
+  uv[1] = Mu[a + 1] * Mv[b] * Mw[d / 2];
+  uv[2] = Mu[a] * Mv[b + 1] * Mw[d / 2];
+  uv[3] = 0.5 * (Mu[a + 2] * Mv[b] * Mw[d / 2] + Mu[a] * Mv[b + 2] * Mw[d / 2] +
+                 Mu[a] * Mv[b] * Mw[(d + 2) / 2]);
+}
+// [KB] moments_conserve_slope(sl, Mu, Mv, Mw, a, b)
+__device__ __forceinline__ void mom_slope(const double *sl, const double *Mu, const double *Mv,
+                                          const double *Mw, int a, int b, double *au) {
+  double t0[4], t1[4], t2[4], t3[4], t4[4], t5[4];
+  mom_cons(Mu, Mv, Mw, a, b, 0, t0);
+  mom_cons(Mu, Mv, Mw, a + 1, b, 0, t1);
+  mom_cons(Mu, Mv, Mw, a, b + 1, 0, t2);
+  mom_cons(Mu, Mv, Mw, a + 2, b, 0, t3);
+  mom_cons(Mu, Mv, Mw, a, b + 2, 0, t4);
+  mom_cons(Mu, Mv, Mw, a, b, 2, t5);
+#pragma unroll
+  for (int m = 0; m < 4; ++m)
+    au[m] = sl[0] * t0[m] + sl[1] * t1[m] + sl[2] * t2[m] + 0.5 * sl[3] * (t3[m] + t4[m] + t5[m]);
+}
+// [KB] pdf_slope(prim, sw, K)
+__device__ __forceinline__ void pdf_slope(const Prim4 &p, const double *sw, double K, double *sl) {
+  sl[3] = 4.0 * p.lam * p.lam / (K + 2.0) / p.rho *
+          (2.0 * sw[3] - 2.0 * p.U * sw[1] - 2.0 * p.V * sw[2] +
+           sw[0] * (p.U * p.U + p.V * p.V - 0.5 * (K + 2.0) / p.lam));
+  sl[2] = 2.0 * p.lam / p.rho * (sw[2] - p.V * sw[0]) - p.V * sl[3];
+  sl[1] = 2.0 * p.lam / p.rho * (sw[1] - p.U * sw[0]) - p.U * sl[3];
+  sl[0] = sw[0] / p.rho - p.U * sl[1] - p.V * sl[2] -
+          0.5 * (p.U * p.U + p.V * p.V + 0.5 * (K + 2.0) / p.lam) * sl[3];
+}
+
+struct GasPar {
+  double K, gamma, mu, omega, dt;
+};
+
+// flux_gks!(fw, w, K, gamma, mu, omega, zeros(4))  (ns_cavity.jl:49-73): with zero slopes
+// a = A = 0, so fw = rho * <u psi>  (the Maxwellian's own moments: Mu[0] = 1, Mu[1] = U)
+__device__ __forceinline__ void gks_point_fluxes(const double *w, const GasPar &g, double *F, double *G) {
+  const Prim4 p = conserve_prim(w, g.gamma - 1.0);
+  const double h = 0.5 / p.lam;
+  const double U2 = p.U * p.U + h, V2 = p.V * p.V + h;      // <u^2>, <v^2>
+  const double U3 = p.U * U2 + 2.0 * h * p.U;               // <u^3>
+  const double V3 = p.V * V2 + 2.0 * h * p.V;
+  const double X1 = g.K * h;                                 // <xi^2>
+  F[0] = p.rho * p.U;
+  F[1] = p.rho * U2;
+  F[2] = p.rho * p.U * p.V;
+  F[3] = p.rho * 0.5 * (U3 + p.U * V2 + p.U * X1);
+  G[0] = p.rho * p.V;
+  G[1] = p.rho * p.U * p.V;
+  G[2] = p.rho * V2;
+  G[3] = p.rho * 0.5 * (V3 + p.V * U2 + p.V * X1);
+}
+
+// flux_gks!(fw, wL, wR, K, gamma, mu, omega, dt, swL, swR)  (ns_cavity.jl:75-145), states in the
+// face-normal frame
+__device__ __noinline__ void gks_face_flux(double *fw, const double *wL, const double *wR,
+                                           const double *swL, const double *swR, GasPar g) {
+  const double gm1 = g.gamma - 1.0;
+  const Prim4 pL = conserve_prim(wL, gm1), pR = conserve_prim(wR, gm1);
+  double MuL1[7], MuR1[7], Mu1[7], Mv1[7], Mxi1[3];
+  double MuL2[7], MuR2[7], Mu2[7], Mv2[7], Mxi2[3];
+  moments_half(pL.U, pL.lam, MuL1, MuR1);
+  moments_half(pR.U, pR.lam, MuL2, MuR2);
+#pragma unroll
+  for (int i = 0; i <= 6; ++i) { Mu1[i] = MuL1[i] + MuR1[i]; Mu2[i] = MuL2[i] + MuR2[i]; }
+  moments_v(pL.V, pL.lam, Mv1);
+  moments_v(pR.V, pR.lam, Mv2);
+  mxi(g.K, pL.lam, Mxi1);
+  mxi(g.K, pR.lam, Mxi2);
+  double a0[4], b0[4], w[4];
+  mom_cons(MuL1, Mv1, Mxi1, 0, 0, 0, a0);
+  mom_cons(MuR2, Mv2, Mxi2, 0, 0, 0, b0);
+#pragma unroll
+  for (int m = 0; m < 4; ++m) w[m] = pL.rho * a0[m] + pR.rho * b0[m];
+  const Prim4 pc = conserve_prim(w, gm1);
+  const double tau = g.mu * 2.0 * pow(pc.lam, 1.0 - g.omega) / pc.rho +
+                     2.0 * g.dt * fabs(pL.rho / pL.lam - pR.rho / pR.lam) / (pL.rho / pL.lam + pR.rho / pR.lam);
+  double faL[4], faTL[4], faR[4], faTR[4], sw[4];
+  pdf_slope(pL, swL, g.K, faL);
+  mom_slope(faL, Mu1, Mv1, Mxi1, 1, 0, sw);
+#pragma unroll
+  for (int m = 0; m < 4; ++m) sw[m] = -pL.rho * sw[m];
+  pdf_slope(pL, sw, g.K, faTL);
+  pdf_slope(pR, swR, g.K, faR);
+  mom_slope(faR, Mu2, Mv1, Mxi2, 1, 0, sw);  // Mv1: as written in ns_cavity.jl:102
+#pragma unroll
+  for (int m = 0; m < 4; ++m) sw[m] = -pR.rho * sw[m];
+  pdf_slope(pR, sw, g.K, faTR);
+  // Mt[1] = dt - Mt[4] = 0: the central-state term drops out; Mt[4] = dt
+  double MuvL[4], MauL[4], MauLT[4], MuvR[4], MauR[4], MauRT[4];
+  mom_cons(MuL1, Mv1, Mxi1, 1, 0, 0, MuvL);
+  mom_slope(faL, MuL1, Mv1, Mxi1, 2, 0, MauL);
+  mom_slope(faTL, MuL1, Mv1, Mxi1, 1, 0, MauLT);
+  mom_cons(MuR2, Mv2, Mxi2, 1, 0, 0, MuvR);
+  mom_slope(faR, MuR2, Mv2, Mxi2, 2, 0, MauR);
+  mom_slope(faTR, MuR2, Mv2, Mxi2, 1, 0, MauRT);
+  const double dt = g.dt;
+#pragma unroll
+  for (int m = 0; m < 4; ++m) {
+    double f = dt * pL.rho * MuvL[m] - tau * dt * pL.rho * MauL[m] - tau * dt * pL.rho * MauLT[m] +
+               dt * pR.rho * MuvR[m] - tau * dt * pR.rho * MauR[m] - tau * dt * pR.rho * MauRT[m];
+    fw[m] = f / dt;
+  }
+}
+
+template <int NSP>
+__device__ __forceinline__ size_t eoff(int j, int i, int nyg) {
+  return (size_t)4 * NSP * NSP * ((size_t)j + (size_t)nyg * i);
+}
+
+// boundary!(u, p, lambda0): isothermal walls by mirrored ghost states; lid on the top wall
+template <int NSP>
+__global__ void ns_boundary_kernel(double *__restrict__ u, int nx, int ny, double gamma, double lam0,
+                                   double lid) {
+  const int a = blockIdx.x * blockDim.x + threadIdx.x + 1;
+  const int side = blockIdx.y;
+  const int n1 = side < 2 ? ny : nx;
+  if (a > n1) return;
+  const int nyg = ny + 2;
+  const double gm1 = gamma - 1.0;
+  int is, js, id, jd;
+  if (side == 0) { is = 1; js = a; id = 0; jd = a; }
+  else if (side == 1) { is = nx; js = a; id = nx + 1; jd = a; }
+  else if (side == 2) { is = a; js = 1; id = a; jd = 0; }
+  else { is = a; js = ny; id = a; jd = ny + 1; }
+  const double *src = u + eoff<NSP>(js, is, nyg);
+  double *dst = u + eoff<NSP>(jd, id, nyg);
+  for (int k = 0; k < NSP; ++k)
+    for (int l = 0; l < NSP; ++l) {
+      const double *w = src + 4 * (l + NSP * k);
+      const Prim4 p = conserve_prim(w, gm1);
+      const double lamb = 2.0 * lam0 - p.lam;
+      const double tmp = (p.lam - lam0) / lam0;
+      const double rb = (1.0 - tmp) / (1.0 + tmp) * p.rho;
+      const double ub = side == 3 ? lid : -p.U, vb = -p.V;
+      const int kd = side < 2 ? NSP - 1 - k : k, ld = side < 2 ? l : NSP - 1 - l;
+      double *o = dst + 4 * (ld + NSP * kd);
+      o[0] = rb;
+      o[1] = rb * ub;
+      o[2] = rb * vb;
+      o[3] = 0.5 * rb / lamb / gm1 + 0.5 * rb * (ub * ub + vb * vb);
+    }
+}
+
+template <int NSP>
+__global__ void __launch_bounds__(64)
+ns2d_kernel(const double *__restrict__ u, const double *__restrict__ ua, double *__restrict__ out,
+            int nx, int ny, double Jx, double Jy, GasPar gas, FrbOps ops, FrbStage st) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x + 1;
+  const int i = blockIdx.y + 1;
+  if (j > ny) return;
+  const int nyg = ny + 2;
+  const double *e0 = u + eoff<NSP>(j, i, nyg);
+  const double *eL = u + eoff<NSP>(j, i - 1, nyg), *eR = u + eoff<NSP>(j, i + 1, nyg);
+  const double *eB = u + eoff<NSP>(j - 1, i, nyg), *eT = u + eoff<NSP>(j + 1, i, nyg);
+#define W(e, m, l, k) (e)[(m) + 4 * ((l) + NSP * (k))]
+  double fx[NSP][NSP][4], fy[NSP][NSP][4];  // [l][k][m], already divided by Jx / Jy
+#pragma unroll
+  for (int k = 0; k < NSP; ++k)
+#pragma unroll
+    for (int l = 0; l < NSP; ++l) {  // ns_cavity.jl:169-187
+      double w[4] = {W(e0, 0, l, k), W(e0, 1, l, k), W(e0, 2, l, k), W(e0, 3, l, k)}, F[4], G[4];
+      gks_point_fluxes(w, gas, F, G);
+#pragma unroll
+      for (int m = 0; m < 4; ++m) { fx[l][k][m] = F[m] / Jx; fy[l][k][m] = G[m] / Jy; }
+    }
+  double du[NSP][NSP][4];
+#pragma unroll
+  for (int k = 0; k < NSP; ++k)
+#pragma unroll
+    for (int l = 0; l < NSP; ++l)
+#pragma unroll
+      for (int m = 0; m < 4; ++m) {  // :264-267
+        double r1 = 0.0, r2 = 0.0;
+#pragma unroll
+        for (int q = 0; q < NSP; ++q) {
+          r1 += fx[l][q][m] * ops.lpdm[k * FRB_NSPMAX + q];
+          r2 += fy[q][k][m] * ops.lpdm[l * FRB_NSPMAX + q];
+        }
+        du[l][k][m] = r1 + r2;
+      }
+  // x faces of row l: left interface (cells i-1 | i) and right interface (i | i+1)  :208-237
+  for (int l = 0; l < NSP; ++l) {
+    double uL[4], uR[4], fL[4], fR[4], nL[4], nR[4], s_own_l[4], s_own_r[4], s_nl[4], s_nr[4];
+#pragma unroll
+    for (int m = 0; m < 4; ++m) {
+      double a = 0, b = 0, c = 0, d = 0, g = 0, h = 0, p = 0, q2 = 0, r = 0, s = 0;
+#pragma unroll
+      for (int q = 0; q < NSP; ++q) {
+        const double w0 = W(e0, m, l, q);
+        a += w0 * ops.ll[q]; b += w0 * ops.lr[q];
+        c += fx[l][q][m] * ops.ll[q]; d += fx[l][q][m] * ops.lr[q];
+        g += W(eL, m, l, q) * ops.lr[q];   // ux_face[:,2,l,j,i-1]
+        h += W(eR, m, l, q) * ops.ll[q];   // ux_face[:,1,l,j,i+1]
+        p += w0 * ops.dlr[q];              // swR of the left interface (own cell is the right cell)
+        q2 += w0 * ops.dll[q];             // swL of the right interface (own cell is the left cell)
+        r += W(eL, m, l, q) * ops.dll[q];  // swL of the left interface
+        s += W(eR, m, l, q) * ops.dlr[q];  // swR of the right interface
+      }
+      uL[m] = a; uR[m] = b; fL[m] = c; fR[m] = d; nL[m] = g; nR[m] = h;
+      s_own_r[m] = p / Jx; s_own_l[m] = q2 / Jx; s_nl[m] = r / Jx; s_nr[m] = s / Jx;
+    }
+    double hl[4], hr[4];
+    gks_face_flux(hl, nL, uL, s_nl, s_own_r, gas);
+    gks_face_flux(hr, uR, nR, s_own_l, s_nr, gas);
+#pragma unroll
+    for (int m = 0; m < 4; ++m) {
+      const double cl = hl[m] / Jx - fL[m], cr = hr[m] / Jx - fR[m];
+#pragma unroll
+      for (int k = 0; k < NSP; ++k) du[l][k][m] += cl * ops.dgl[k] + cr * ops.dgr[k];  // :271-274
+    }
+  }
+  // y faces of column k  :239-262 (states rotated by local_frame(.,0,1); slopes are not)
+  for (int k = 0; k < NSP; ++k) {
+    double uB[4], uT[4], gB[4], gT[4], nB[4], nT[4], s_own_t[4], s_own_b[4], s_nb[4], s_nt[4];
+#pragma unroll
+    for (int m = 0; m < 4; ++m) {
+      double a = 0, b = 0, c = 0, d = 0, g = 0, h = 0, p = 0, q2 = 0, r = 0, s = 0;
+#pragma unroll
+      for (int q = 0; q < NSP; ++q) {
+        const double w0 = W(e0, m, q, k);
+        a += w0 * ops.ll[q]; b += w0 * ops.lr[q];
+        c += fy[q][k][m] * ops.ll[q]; d += fy[q][k][m] * ops.lr[q];
+        g += W(eB, m, q, k) * ops.lr[q];   // uy_face[:,2,k,j-1,i]
+        h += W(eT, m, q, k) * ops.ll[q];   // uy_face[:,1,k,j+1,i]
+        p += w0 * ops.dlr[q];
+        q2 += w0 * ops.dll[q];
+        r += W(eB, m, q, k) * ops.dll[q];
+        s += W(eT, m, q, k) * ops.dlr[q];
+      }
+      uB[m] = a; uT[m] = b; gB[m] = c; gT[m] = d; nB[m] = g; nT[m] = h;
+      s_own_t[m] = p / Jy; s_own_b[m] = q2 / Jy; s_nb[m] = r / Jy; s_nt[m] = s / Jy;
+    }
+    // local_frame(w, 0, 1) = (w0, w2, -w1, w3);  global_frame(f, 0, 1) = (f0, -f2, f1, f3)
+    double lb[4] = {nB[0], nB[2], -nB[1], nB[3]}, rb[4] = {uB[0], uB[2], -uB[1], uB[3]};
+    double lt[4] = {uT[0], uT[2], -uT[1], uT[3]}, rt[4] = {nT[0], nT[2], -nT[1], nT[3]};
+    double hb[4], ht[4];
+    gks_face_flux(hb, lb, rb, s_nb, s_own_t, gas);
+    gks_face_flux(ht, lt, rt, s_own_b, s_nt, gas);
+    const double hbg[4] = {hb[0], -hb[2], hb[1], hb[3]}, htg[4] = {ht[0], -ht[2], ht[1], ht[3]};
+#pragma unroll
+    for (int m = 0; m < 4; ++m) {
+      const double cb = hbg[m] / Jy - gB[m], ct = htg[m] / Jy - gT[m];
+#pragma unroll
+      for (int l = 0; l < NSP; ++l) du[l][k][m] += cb * ops.dgl[l] + ct * ops.dgr[l];  // :275-278
+    }
+  }
+  double *o = out + eoff<NSP>(j, i, nyg);
+  const double *a0 = ua ? ua + eoff<NSP>(j, i, nyg) : nullptr;
+#pragma unroll
+  for (int k = 0; k < NSP; ++k)
+#pragma unroll
+    for (int l = 0; l < NSP; ++l)
+#pragma unroll
+      for (int m = 0; m < 4; ++m) {
+        const int q = m + 4 * (l + NSP * k);
+        const double d = -du[l][k][m];
+        double r;
+        if (st.rhs_only) r = d;
+        else {
+          r = st.nested ? st.cb * (e0[q] + st.cdt * d) : st.cb * e0[q] + st.cdt * d;
+          if (st.use_a) r = st.ca * a0[q] + r;
+        }
+        o[q] = r;
+      }
+#undef W
+}
+
+// the stage combination on the ghost ring (du = 0 there): dst = ca*ua + cb*src on whole ghost
+// elements, so that the new state carries the ghosts OrdinaryDiffEq's axpys would give it
+template <int NSP>
+__global__ void ns_ring_stage_kernel(const double *src, const double *ua, double *dst, int nx, int ny,
+                                     double ca, double cb, int use_a) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const int nxg = nx + 2, nyg = ny + 2, nring = 2 * nxg + 2 * ny;
+  if (t >= nring) return;
+  int i, j;
+  if (t < nxg) { i = t; j = 0; }
+  else if (t < 2 * nxg) { i = t - nxg; j = nyg - 1; }
+  else if (t < 2 * nxg + ny) { i = 0; j = t - 2 * nxg + 1; }
+  else { i = nxg - 1; j = t - 2 * nxg - ny + 1; }
+  const size_t o = eoff<NSP>(j, i, nyg);
+  for (int q = 0; q < 4 * NSP * NSP; ++q) {
+    double v = cb * src[o + q];
+    if (use_a) v = ca * ua[o + q] + v;
+    dst[o + q] = v;
+  }
+}
+
+int check_launch(const char *what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return frb_cuda_fail(e, what, __FILE__, __LINE__);
+  return 0;
+}
+
+}  // namespace
+
+#define FRB_NS_SWITCH(nsp, CALL)                        \
+  switch (nsp) {                                        \
+    case 2: { constexpr int N = 2; CALL; } break;       \
+    case 3: { constexpr int N = 3; CALL; } break;       \
+    case 4: { constexpr int N = 4; CALL; } break;       \
+    default: frb_set_error("ns2d kernels support deg 1..3"); return FRB_ERR_ARG; \
+  }
+
+// boundary!(u) on the stage input, then the fused RHS + stage
+int frb_launch_ns2d(frb_prob_t p, const double *u, const double *ua, double *out, FrbStage st) {
+  cudaStream_t s = p->ctx->stream;
+  const int nmax = p->nx > p->ny ? p->nx : p->ny;
+  dim3 bb(64), bg((nmax + 63) / 64, 4);
+  double *uw = const_cast<double *>(u);  // boundary! rewrites the ghosts of the state it is given
+  FRB_NS_SWITCH(p->nsp, (ns_boundary_kernel<N><<<bg, bb, 0, s>>>(uw, p->nx, p->ny, p->gamma, p->lambda_wall, p->lid_u)));
+  if (int rc = check_launch("ns_boundary_kernel")) return rc;
+  int n = 1;
+  if (!st.rhs_only) {  // ghosts of the new state: the stage combination with du = 0
+    dim3 rg((2 * (p->nx + 2) + 2 * p->ny + 63) / 64);
+    FRB_NS_SWITCH(p->nsp, (ns_ring_stage_kernel<N><<<rg, bb, 0, s>>>(u, ua, out, p->nx, p->ny, st.ca, st.cb, st.use_a)));
+    if (int rc = check_launch("ns_ring_stage_kernel")) return rc;
+    n += 1;
+  }
+  GasPar gas = {p->gks_K, p->gamma, p->gks_mu, p->gks_omega, p->gks_dt};
+  dim3 blk(64), grd((p->ny + 63) / 64, p->nx);
+  FRB_NS_SWITCH(p->nsp, (ns2d_kernel<N><<<grd, blk, 0, s>>>(u, ua, out, p->nx, p->ny, p->Jx, p->Jy, gas, p->ops, st)));
+  if (int rc = check_launch("ns2d_kernel")) return rc;
+  return n + 1;
+}

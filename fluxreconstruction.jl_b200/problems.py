@@ -336,3 +336,30 @@ class DistributedEuler2D(Euler2DProblem):
                 pass
             lib().frb_halo_disconnect(self.h)
         super().close()
+
+
+def ref_vhs_vis(Kn, alpha, omega):
+    """KitBase.ref_vhs_vis(Kn, alpha, omega) (used by example/ns_cavity.jl:17,30)."""
+    import math
+
+    return 5.0 * (alpha + 1.0) * (alpha + 2.0) * math.sqrt(math.pi) / (
+        4.0 * alpha * (5.0 - 2.0 * omega) * (7.0 - 2.0 * omega)) * Kn
+
+
+class NSCavityProblem(_Problem):
+    """ODEProblem(dudt!, u0, tspan, p) of example/ns_cavity.jl:147-380: 2-D Navier-Stokes with the
+    gas-kinetic flux, isothermal walls and a moving lid.  u0[4, nsp, nsp, ny+2, nx+2] (variable
+    fastest).  ``gas`` mirrors KitBase.Gas: K, gamma, mu_ref (μᵣ), omega (ω); ``dt`` is the step that
+    enters the time-averaged interface flux; ``lid`` is pb[2] of :337; ``lambda_wall`` the λ0 of
+    boundary!(u, p, 1.0)."""
+
+    def __init__(self, u0, tspan, ps, K, gamma, mu_ref, omega, dt, lid=0.15, lambda_wall=1.0, ctx=None):
+        super().__init__(u0, tspan, ctx)
+        nsp = ps.deg + 1
+        if self.u0.shape != (4, nsp, nsp, ps.ny + 2, ps.nx + 2):
+            raise ValueError("u0 must be [4, nsp, nsp, ny+2, nx+2]")
+        ops, self._keep = _ops_of(ps, slopes=True)
+        check(lib().frb_ns2d_create(self.ctx.h, ps.nx, ps.ny, C.byref(ops), ps.Jx, ps.Jy, float(K), float(gamma),
+                                    float(mu_ref), float(omega), float(dt), float(lid), float(lambda_wall),
+                                    C.byref(self.h)))
+        self.upload(self.u0)

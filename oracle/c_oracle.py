@@ -212,3 +212,36 @@ def limiter_euler2d(u, gamma, weights, ll, lr):
     return lib().fro_limiter_euler2d(
         _p(u), u.shape[0] - 2, u.shape[1] - 2, u.shape[2], C.c_double(gamma), _p(w), _p(l1), _p(l2)
     )
+
+
+def _ns_args(ps, K, gamma, mu, omega, dt, lam0, lid):
+    ops = [np.ascontiguousarray(x, dtype=np.float64) for x in (ps.ll, ps.lr, ps.dl, ps.dhl, ps.dhr, ps.dll, ps.dlr)]
+    scal = [C.c_double(x) for x in (K, gamma, mu, omega, dt, lam0, lid)]
+    return ops, scal
+
+
+def ns_boundary(u, gamma, lam0=1.0, lid=0.15):
+    assert u.flags.f_contiguous
+    lib().fro_ns_boundary(_p(u), u.shape[4] - 2, u.shape[3] - 2, u.shape[1], C.c_double(gamma), C.c_double(lam0),
+                          C.c_double(lid))
+    return u
+
+
+def rhs_ns2d(u, ps, K, gamma, mu, omega, dt, lam0=1.0, lid=0.15):
+    """u's ghosts are rewritten in place (boundary!), as in the reference."""
+    assert u.flags.f_contiguous and u.dtype == np.float64
+    du = np.empty_like(u, order="F")
+    ops, scal = _ns_args(ps, K, gamma, mu, omega, dt, lam0, lid)
+    rc = lib().fro_rhs_ns2d(_p(u), _p(du), u.shape[4] - 2, u.shape[3] - 2, u.shape[1], C.c_double(ps.Jx),
+                            C.c_double(ps.Jy), *[_p(x) for x in ops], *scal)
+    assert rc == 0
+    return du
+
+
+def integrate_ns2d(u, ps, K, gamma, mu, omega, dt, nsteps, lam0=1.0, lid=0.15):
+    u = np.array(u, dtype=np.float64, order="F", copy=True)
+    ops, scal = _ns_args(ps, K, gamma, mu, omega, dt, lam0, lid)
+    rc = lib().fro_integrate_ns2d(_p(u), u.shape[4] - 2, u.shape[3] - 2, u.shape[1], C.c_double(ps.Jx),
+                                  C.c_double(ps.Jy), *[_p(x) for x in ops], *scal, int(nsteps))
+    assert rc == 0
+    return u

@@ -758,3 +758,207 @@ def ic_bgk1d(ps: FRPSpace1D, velo):
     for k in range(ps.deg + 1):
         f0[:, :, k] = maxwellian(velo[None, :], prim[:, k, :])
     return f0
+
+
+# ----------------------------------------------------------------------------
+# 2-D gas-kinetic Navier-Stokes (config 5): example/ns_cavity.jl
+# ----------------------------------------------------------------------------
+# Layout u[4, ns, nr, ny+2, nx+2] (variable fastest; ns_cavity.jl:33).  [KB] closures restated
+# from KitBase 0.9.  Quirks kept: see oracle/fr_oracle_gks.c header.
+
+
+def ref_vhs_vis(Kn, alpha, omega):
+    """[KB] ref_vhs_vis."""
+    return 5.0 * (alpha + 1.0) * (alpha + 2.0) * math.sqrt(math.pi) / (
+        4.0 * alpha * (5.0 - 2.0 * omega) * (7.0 - 2.0 * omega)) * Kn
+
+
+def _erfc(x):
+    from scipy.special import erfc
+
+    return erfc(x)
+
+
+def gauss_moments(prim, K):
+    """[KB] gauss_moments(prim, inK) for prim[..., 4] -> Mu, Mv, Mxi, MuL, MuR (moment index first)."""
+    U, V, lam = prim[..., 1], prim[..., 2], prim[..., 3]
+    MuL = np.empty((7,) + U.shape)
+    MuR = np.empty_like(MuL)
+    MuL[0] = 0.5 * _erfc(-np.sqrt(lam) * U)
+    MuL[1] = U * MuL[0] + 0.5 * np.exp(-lam * U * U) / np.sqrt(np.pi * lam)
+    MuR[0] = 0.5 * _erfc(np.sqrt(lam) * U)
+    MuR[1] = U * MuR[0] - 0.5 * np.exp(-lam * U * U) / np.sqrt(np.pi * lam)
+    for i in range(2, 7):
+        MuL[i] = U * MuL[i - 1] + 0.5 * (i - 1) * MuL[i - 2] / lam
+        MuR[i] = U * MuR[i - 1] + 0.5 * (i - 1) * MuR[i - 2] / lam
+    Mu = MuL + MuR
+    Mv = np.empty_like(MuL)
+    Mv[0] = 1.0
+    Mv[1] = V
+    for i in range(2, 7):
+        Mv[i] = V * Mv[i - 1] + 0.5 * (i - 1) * Mv[i - 2] / lam
+    Mxi = np.empty((3,) + U.shape)
+    Mxi[0] = 1.0
+    Mxi[1] = 0.5 * K / lam
+    Mxi[2] = (K * K + 2.0 * K) / (4.0 * lam * lam)
+    return Mu, Mv, Mxi, MuL, MuR
+
+
+def moments_conserve_2d(Mu, Mv, Mw, a, b, d):
+    """[KB] moments_conserve(Mu, Mv, Mw, alpha, beta, delta) -> [..., 4]."""
+    uv = np.empty(Mu.shape[1:] + (4,))
+    uv[..., 0] = Mu[a] * Mv[b] * Mw[d // 2]
+    uv[..., 1] = Mu[a + 1] * Mv[b] * Mw[d // 2]
+    uv[..., 2] = Mu[a] * Mv[b + 1] * Mw[d // 2]
+    uv[..., 3] = 0.5 * (Mu[a + 2] * Mv[b] * Mw[d // 2] + Mu[a] * Mv[b + 2] * Mw[d // 2]
+                        + Mu[a] * Mv[b] * Mw[(d + 2) // 2])
+    return uv
+
+
+def moments_conserve_slope_2d(sl, Mu, Mv, Mw, a, b):
+    """[KB] moments_conserve_slope."""
+    s = [sl[..., q:q + 1] for q in range(4)]
+    return (s[0] * moments_conserve_2d(Mu, Mv, Mw, a, b, 0) + s[1] * moments_conserve_2d(Mu, Mv, Mw, a + 1, b, 0)
+            + s[2] * moments_conserve_2d(Mu, Mv, Mw, a, b + 1, 0)
+            + 0.5 * s[3] * moments_conserve_2d(Mu, Mv, Mw, a + 2, b, 0)
+            + 0.5 * s[3] * moments_conserve_2d(Mu, Mv, Mw, a, b + 2, 0)
+            + 0.5 * s[3] * moments_conserve_2d(Mu, Mv, Mw, a, b, 2))
+
+
+def pdf_slope_2d(prim, sw, K):
+    """[KB] pdf_slope."""
+    rho, U, V, lam = (prim[..., q] for q in range(4))
+    sl = np.empty_like(sw)
+    sl[..., 3] = 4.0 * lam * lam / (K + 2.0) / rho * (
+        2.0 * sw[..., 3] - 2.0 * U * sw[..., 1] - 2.0 * V * sw[..., 2]
+        + sw[..., 0] * (U * U + V * V - 0.5 * (K + 2.0) / lam))
+    sl[..., 2] = 2.0 * lam / rho * (sw[..., 2] - V * sw[..., 0]) - V * sl[..., 3]
+    sl[..., 1] = 2.0 * lam / rho * (sw[..., 1] - U * sw[..., 0]) - U * sl[..., 3]
+    sl[..., 0] = sw[..., 0] / rho - U * sl[..., 1] - V * sl[..., 2] - 0.5 * (
+        U * U + V * V + 0.5 * (K + 2.0) / lam) * sl[..., 3]
+    return sl
+
+
+def vhs_collision_time(prim, mu, omega):
+    return mu * 2.0 * prim[..., 3] ** (1.0 - omega) / prim[..., 0]
+
+
+def flux_gks_point(w, K, gamma, mu, omega):
+    """ns_cavity.jl:49-73 with sw = 0."""
+    prim = conserve_prim(w, gamma)
+    Mu, Mv, Mxi, _, _ = gauss_moments(prim, K)
+    tau = vhs_collision_time(prim, mu, omega)[..., None]
+    a = pdf_slope_2d(prim, np.zeros_like(w), K)
+    dft = -prim[..., 0:1] * moments_conserve_slope_2d(a, Mu, Mv, Mxi, 1, 0)
+    A = pdf_slope_2d(prim, dft, K)
+    Muv = moments_conserve_2d(Mu, Mv, Mxi, 1, 0, 0)
+    Mau = moments_conserve_slope_2d(a, Mu, Mv, Mxi, 2, 0)
+    Mtu = moments_conserve_slope_2d(A, Mu, Mv, Mxi, 1, 0)
+    return prim[..., 0:1] * (Muv - tau * Mau - tau * Mtu)
+
+
+def flux_gks_face(wL, wR, K, gamma, mu, omega, dt, swL, swR):
+    """ns_cavity.jl:75-145."""
+    pL, pR = conserve_prim(wL, gamma), conserve_prim(wR, gamma)
+    Mu1, Mv1, Mxi1, MuL1, _ = gauss_moments(pL, K)
+    Mu2, Mv2, Mxi2, _, MuR2 = gauss_moments(pR, K)
+    w = pL[..., 0:1] * moments_conserve_2d(MuL1, Mv1, Mxi1, 0, 0, 0) + pR[..., 0:1] * moments_conserve_2d(
+        MuR2, Mv2, Mxi2, 0, 0, 0)
+    prim = conserve_prim(w, gamma)
+    tau = vhs_collision_time(prim, mu, omega) + 2.0 * dt * np.abs(
+        pL[..., 0] / pL[..., 3] - pR[..., 0] / pR[..., 3]) / (pL[..., 0] / pL[..., 3] + pR[..., 0] / pR[..., 3])
+    tau = tau[..., None]
+    faL = pdf_slope_2d(pL, swL, K)
+    faTL = pdf_slope_2d(pL, -pL[..., 0:1] * moments_conserve_slope_2d(faL, Mu1, Mv1, Mxi1, 1, 0), K)
+    faR = pdf_slope_2d(pR, swR, K)
+    faTR = pdf_slope_2d(pR, -pR[..., 0:1] * moments_conserve_slope_2d(faR, Mu2, Mv1, Mxi2, 1, 0), K)  # Mv1 (:102)
+    Mu, Mv, Mxi, _, _ = gauss_moments(prim, K)
+    Mt4 = dt
+    Mt1 = dt - Mt4
+    fw = Mt1 * prim[..., 0:1] * moments_conserve_2d(Mu, Mv, Mxi, 1, 0, 0)
+    fw = fw + (
+        Mt4 * pL[..., 0:1] * moments_conserve_2d(MuL1, Mv1, Mxi1, 1, 0, 0)
+        - tau * Mt4 * pL[..., 0:1] * moments_conserve_slope_2d(faL, MuL1, Mv1, Mxi1, 2, 0)
+        - tau * Mt4 * pL[..., 0:1] * moments_conserve_slope_2d(faTL, MuL1, Mv1, Mxi1, 1, 0)
+        + Mt4 * pR[..., 0:1] * moments_conserve_2d(MuR2, Mv2, Mxi2, 1, 0, 0)
+        - tau * Mt4 * pR[..., 0:1] * moments_conserve_slope_2d(faR, MuR2, Mv2, Mxi2, 2, 0)
+        - tau * Mt4 * pR[..., 0:1] * moments_conserve_slope_2d(faTR, MuR2, Mv2, Mxi2, 1, 0))
+    return fw / dt
+
+
+def ns_boundary(u, gamma, lam0=1.0, lid=0.15):
+    """boundary!(u, p, 1.0): ns_cavity.jl:289-344, in place.  u[4, ns, nr, ny+2, nx+2]."""
+    _, ns, nr, nyg, nxg = u.shape
+    nx, ny = nxg - 2, nyg - 2
+
+    def mirror(w, top):
+        prim = conserve_prim(w, gamma)
+        pb = np.empty_like(prim)
+        pb[..., 3] = 2 * lam0 - prim[..., 3]
+        tmp = (prim[..., 3] - lam0) / lam0
+        pb[..., 0] = (1.0 - tmp) / (1.0 + tmp) * prim[..., 0]
+        pb[..., 1] = lid if top else -prim[..., 1]
+        pb[..., 2] = -prim[..., 2]
+        return prim_conserve(pb, gamma)
+
+    # arrays as [..., 4] views: move variable axis last
+    ul = np.moveaxis(u, 0, -1)  # [ns, nr, nyg, nxg, 4]
+    ul[:, ::-1, 1:ny + 1, 0, :] = mirror(ul[:, :, 1:ny + 1, 1, :], False)
+    ul[:, ::-1, 1:ny + 1, nx + 1, :] = mirror(ul[:, :, 1:ny + 1, nx, :], False)
+    ul[::-1, :, 0, 1:nx + 1, :] = mirror(ul[:, :, 1, 1:nx + 1, :], False)
+    ul[::-1, :, ny + 1, 1:nx + 1, :] = mirror(ul[:, :, ny, 1:nx + 1, :], True)
+    return u
+
+
+def rhs_ns2d(u, ps: FRPSpace2D, K, gamma, mu, omega, dt, lam0=1.0, lid=0.15):
+    """dudt! of ns_cavity.jl:147-287 (u's ghosts are rewritten in place, as in the reference)."""
+    ns_boundary(u, gamma, lam0, lid)
+    _, ns, nr, nyg, nxg = u.shape
+    nx, ny = nxg - 2, nyg - 2
+    Jx, Jy = ps.Jx, ps.Jy
+    ul = np.moveaxis(u, 0, -1)  # [l, k, j, i, m]
+    I, Jn = slice(1, nx + 1), slice(1, ny + 1)
+    fx = np.zeros_like(ul)
+    fy = np.zeros_like(ul)
+    fx[:, :, Jn, I] = flux_gks_point(ul[:, :, Jn, I], K, gamma, mu, omega) / Jx
+    fy[:, :, Jn, I] = global_frame(flux_gks_point(local_frame(ul[:, :, Jn, I], 0.0, 1.0), K, gamma, mu, omega),
+                                   0.0, 1.0) / Jy
+
+    def con_k(a, l):  # contract the r index (axis 1)
+        return sum(a[:, q] * l[q] for q in range(nr))
+
+    def con_l(a, l):  # contract the s index (axis 0)
+        return sum(a[q] * l[q] for q in range(ns))
+
+    uxL, uxR = con_k(ul, ps.ll), con_k(ul, ps.lr)  # [l, j, i, m]
+    fxL, fxR = con_k(fx, ps.ll), con_k(fx, ps.lr)
+    uyB, uyT = con_l(ul, ps.ll), con_l(ul, ps.lr)  # [k, j, i, m]
+    fyB, fyT = con_l(fy, ps.ll), con_l(fy, ps.lr)
+    # x interfaces i = 1..nx+1 (left cell i-1, right cell i), rows j = 1..ny
+    swL = con_k(ul, ps.dll)[:, Jn, 0:nx + 1] / Jx
+    swR = con_k(ul, ps.dlr)[:, Jn, 1:nx + 2] / Jx
+    fxi = flux_gks_face(uxR[:, Jn, 0:nx + 1], uxL[:, Jn, 1:nx + 2], K, gamma, mu, omega, dt, swL, swR)  # [l, j, iface, m]
+    swL = con_l(ul, ps.dll)[:, 0:ny + 1, I] / Jy
+    swR = con_l(ul, ps.dlr)[:, 1:ny + 2, I] / Jy
+    fyi = global_frame(flux_gks_face(local_frame(uyT[:, 0:ny + 1, I], 0.0, 1.0), local_frame(uyB[:, 1:ny + 2, I], 0.0, 1.0),
+                                     K, gamma, mu, omega, dt, swL, swR), 0.0, 1.0)  # [k, jface, i, m]
+    du = np.zeros_like(ul)
+    for k in range(nr):
+        for l in range(ns):
+            r1 = sum(fx[l, q, Jn, I] * ps.dl[k, q] for q in range(nr))
+            r2 = sum(fy[q, k, Jn, I] * ps.dl[l, q] for q in range(ns))
+            du[l, k, Jn, I] = -(
+                r1 + r2
+                + (fxi[l, :, 0:nx] / Jx - fxL[l, Jn, I]) * ps.dhl[k]
+                + (fxi[l, :, 1:nx + 1] / Jx - fxR[l, Jn, I]) * ps.dhr[k]
+                + (fyi[k, 0:ny] / Jy - fyB[k, Jn, I]) * ps.dhl[l]
+                + (fyi[k, 1:ny + 1] / Jy - fyT[k, Jn, I]) * ps.dhr[l])
+    return np.asfortranarray(np.moveaxis(du, -1, 0))
+
+
+def ic_cavity(ps: FRPSpace2D, gamma=5.0 / 3.0):
+    """ns_cavity.jl:33-36: prim = [1, 0, 0, 1] everywhere."""
+    nsp = ps.deg + 1
+    u = np.empty((4, nsp, nsp, ps.ny + 2, ps.nx + 2), order="F")
+    u[...] = prim_conserve(np.array([1.0, 0.0, 0.0, 1.0]), gamma)[:, None, None, None, None]
+    return u

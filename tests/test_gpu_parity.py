@@ -246,3 +246,54 @@ def test_no_cpu_fallback_symbols(FR):
 
     out = subprocess.run(["nm", "-D", FR.LIB_PATH], capture_output=True, text=True).stdout
     assert "fro_" not in out
+
+
+# ---------------------------------------------------------------- config 5: 2-D NS, gas-kinetic flux
+def _cavity(FR, oracle, nx, ny, deg, seed=None):
+    ps = FR.FRPSpace2D(0.0, 1.0, nx, 0.0, 1.0, ny, deg, 1, 1)
+    u = oracle.ic_cavity(ps, GAMMA)
+    if seed is not None:
+        u = noisy(u, 0.02, seed)
+    mu = FR.ref_vhs_vis(1e-3, 1.0, 0.5)
+    dt = 0.1 * min(ps.dx, ps.dy) / 3.0
+    return ps, u, mu, dt
+
+
+@pytest.mark.parametrize("nx,ny,deg", [(15, 15, 2), (9, 12, 3), (33, 20, 1)])
+def test_ns_cavity_rhs(FR, oracle, coracle, nx, ny, deg):
+    ps, u, mu, dt = _cavity(FR, oracle, nx, ny, deg, seed=8)
+    prob = FR.NSCavityProblem(u, (0.0, 0.15), ps, 1.0, GAMMA, mu, 0.81, dt)
+    du = np.zeros_like(u, order="F")
+    prob.f(du, u, None, 0.0)
+    uref = u.copy(order="F")
+    ref = coracle.rhs_ns2d(uref, ps, 1.0, GAMMA, mu, 0.81, dt)
+    assert np.isfinite(du).all()
+    assert rel(du, ref) <= RTOL_RHS
+    # boundary! rewrote the ghosts of the resident state exactly like the reference does
+    got_u = prob.download()
+    assert rel(got_u[:, :, :, 1:-1, 0], uref[:, :, :, 1:-1, 0]) <= 1e-14
+    assert rel(got_u[:, :, :, -1, 1:-1], uref[:, :, :, -1, 1:-1]) <= 1e-14
+    prob.close()
+
+
+def test_ns_cavity_lid_driven_steps(FR, oracle, coracle):
+    """ns_cavity.jl:380-384: Euler forward from rest with the lid moving."""
+    ps, u0, mu, dt = _cavity(FR, oracle, 15, 15, 2)
+    prob = FR.NSCavityProblem(u0, (0.0, 0.15), ps, 1.0, GAMMA, mu, 0.81, dt)
+    itg = FR.init(prob, FR.Euler(), dt=dt)
+    FR.step_(itg, 100)
+    ref = coracle.integrate_ns2d(u0, ps, 1.0, GAMMA, mu, 0.81, dt, 100)
+    got = itg.u
+    assert np.isfinite(got).all()
+    assert np.abs(got[1]).max() > 1e-3  # the lid has set the gas in motion
+    assert rel(got[:, :, :, 1:-1, 1:-1], ref[:, :, :, 1:-1, 1:-1]) <= RTOL_1000
+    prob.close()
+
+
+def test_ns_cavity_rest_state_is_steady(FR, oracle):
+    ps, u0, mu, dt = _cavity(FR, oracle, 12, 12, 3)
+    prob = FR.NSCavityProblem(u0, (0.0, 0.15), ps, 1.0, GAMMA, mu, 0.81, dt, lid=0.0)
+    du = np.zeros_like(u0, order="F")
+    prob.f(du, u0, None, 0.0)
+    assert np.abs(du).max() <= 1e-10
+    prob.close()
