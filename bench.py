@@ -239,15 +239,16 @@ def run_ours(args):
         uh = FR.pinned_empty(u0.shape)
         dh = FR.pinned_empty(u0.shape)
         uh[...] = u0
-        prob.f(dh, uh, None, 0.0)  # warm-up
+        prob.f_pipelined(dh, uh, None, 0.0, nslab=args.e2e_slabs)  # warm-up
         k = max(1, min(args.steps, args.e2e_steps))
         t0 = time.perf_counter()
         for _ in range(k):
-            prob.f(dh, uh, None, 0.0)
+            prob.f_pipelined(dh, uh, None, 0.0, nslab=args.e2e_slabs)
         el = time.perf_counter() - t0
         nbytes = int(u0.size) * 8
         e2e = {"value": dofs * k / el, "unit": UNIT, "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": nbytes,
-               "call": "frb_rhs(prob, u_host, du_host, t): upload u, one fused RHS launch, download du",
+               "call": f"frb_rhs_pipelined(prob, u_host, du_host, {args.e2e_slabs}): the f!(du,u,p,t) shape with pinned "
+                       "host buffers; upload, fused residual and download overlapped in row slabs",
                "ms_per_call": 1e3 * el / k}
         FR.pinned_free(uh)
         FR.pinned_free(dh)
@@ -293,6 +294,7 @@ def main():
     ap.add_argument("--cpu-n", type=int, default=512)
     ap.add_argument("--cpu-evals", type=int, default=3)
     ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--e2e-slabs", type=int, default=16)
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup

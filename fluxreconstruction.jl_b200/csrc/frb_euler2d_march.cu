@@ -76,6 +76,7 @@ struct MarchParams {
   double *out;
   int nx, ny;
   int rows_per_seg;
+  int jlo, jhi;  // rows to update (1..ny for a whole-mesh launch; a sub-range for the pipelined path)
   double gamma;
   double ca, cb;
   double cxs, cys;  // -cdt/Jx, -cdt/Jy  (L = -(dux/Jx + duy/Jy))
@@ -125,9 +126,9 @@ euler2d_march_kernel(const __grid_constant__ CUtensorMap tmap, MarchParams P, Fr
   const int lane = threadIdx.x & 31;
   const int t = threadIdx.x >> 5;  // row index in the x pass, column index in the y pass
   const int i = blockIdx.x * kOwn + lane;  // element column of this lane (0 = ghost)
-  const int ja = 1 + blockIdx.y * P.rows_per_seg;
-  const int jb = min(P.ny, ja + P.rows_per_seg - 1);
-  if (ja > P.ny) return;
+  const int ja = P.jlo + blockIdx.y * P.rows_per_seg;
+  const int jb = min(P.jhi, ja + P.rows_per_seg - 1);
+  if (ja > P.jhi) return;
   const int ntiles = jb - ja + 3;  // rows ja-1 .. jb+1; tile q holds row ja-1+q in buffer q % NBUF
   const size_t NXG = P.nx + 2, NE = NXG * (size_t)(P.ny + 2);
   const bool owner = lane >= 1 && lane <= kOwn && i <= P.nx;
@@ -414,7 +415,7 @@ template <int NSP, int NBUF, int MINB, bool PREFETCH, bool COPYONLY = false>
 static int launch_march(frb_prob_t p, const CUtensorMap &map, MarchParams mp) {
   mp.rows_per_seg = march_rows_per_seg(p, MINB);
   const int strips = (p->nx + kOwn - 1) / kOwn;
-  const int segs = (p->ny + mp.rows_per_seg - 1) / mp.rows_per_seg;
+  const int segs = (mp.jhi - mp.jlo + 1 + mp.rows_per_seg - 1) / mp.rows_per_seg;
   const size_t smem = sizeof(Smem<NSP, NBUF>) + 128;
   static bool attr_done = false;
   if (!attr_done) {
@@ -467,6 +468,8 @@ int frb_launch_euler2d_march(frb_prob_t p, const double *u, const double *ua, do
   mp.nx = p->nx;
   mp.ny = p->ny;
   mp.rows_per_seg = 0;
+  mp.jlo = p->row_lo > 0 ? p->row_lo : 1;
+  mp.jhi = p->row_hi > 0 ? p->row_hi : p->ny;
   mp.pfdist = env_int("FRB_MARCH_PFDIST", 0);
   mp.gamma = p->gamma;
   frb_halo_stage_targets(p, out, &mp.peer_lo, &mp.peer_hi, &mp.nyl_lo, &mp.nyl_hi);

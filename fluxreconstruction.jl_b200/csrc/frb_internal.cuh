@@ -80,6 +80,7 @@ struct frb_prob_s {
   int ghost_mode = FRB_GHOST_NONE;
   bool limiter_on = false;
   int kernel_kind = FRB_KERNEL_AUTO;
+  int row_lo = 0, row_hi = 0;  // sub-range of rows for the next 2-D stage launch (0 = all)
   // timing
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   float last_ms = 0.f;

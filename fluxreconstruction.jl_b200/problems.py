@@ -98,6 +98,14 @@ class _Problem:
         check(lib().frb_rhs(self.h, fortran_ptr(u), fortran_ptr(du), float(t)))
         return None
 
+    def f_pipelined(self, du, u, p=None, t=0.0, nslab=16):
+        """f!(du,u,p,t) with host arrays, streamed through the device in ``nslab`` row slabs so that
+        upload, residual and download overlap (2-D Euler; other problems fall back to ``f``)."""
+        if u.shape != self.u0.shape or du.shape != self.u0.shape:
+            raise ValueError("f!: array shape does not match the problem")
+        check(lib().frb_rhs_pipelined(self.h, fortran_ptr(u), fortran_ptr(du), int(nslab)))
+        return None
+
     def rhs_resident(self):
         """L(u) of the resident state, left on the device (timing / chaining)."""
         check(lib().frb_rhs(self.h, None, None, 0.0))

@@ -297,3 +297,22 @@ def test_ns_cavity_rest_state_is_steady(FR, oracle):
     prob.f(du, u0, None, 0.0)
     assert np.abs(du).max() <= 1e-10
     prob.close()
+
+
+def test_euler2d_pipelined_host_rhs_equals_plain(FR, oracle, coracle):
+    """frb_rhs_pipelined (H2D / residual / D2H overlapped in row slabs) == frb_rhs == oracle."""
+    ps = FR.FRPSpace2D(0.0, 1.0, 64, 0.0, 1.0, 96, 3, 1, 1)
+    u = noisy(oracle.ic_wave2d(ps, GAMMA, "x"), 0.02, 13)
+    prob = FR.Euler2DProblem(u, (0.0, 0.5), ps, GAMMA)
+    d1 = np.zeros_like(u, order="F")
+    prob.f(d1, u, None, 0.0)
+    for nslab in (2, 5, 16):
+        uh, dh = FR.pinned_empty(u.shape), FR.pinned_empty(u.shape)
+        uh[...] = u
+        dh[...] = np.nan
+        prob.f_pipelined(dh, uh, None, 0.0, nslab=nslab)
+        assert np.array_equal(np.asarray(dh), d1)
+        FR.pinned_free(uh)
+        FR.pinned_free(dh)
+    assert rel(d1, coracle.rhs_euler2d(u, ps, GAMMA)) <= RTOL_RHS
+    prob.close()
