@@ -112,7 +112,7 @@ __device__ __forceinline__ void col_trace(const double *__restrict__ Uy, const d
 }
 
 // MINB = resident CTAs per SM the register budget is compiled for
-template <int NSP, int NBUF, int MINB, bool PREFETCH, bool COPYONLY = false>
+template <int NSP, int NBUF, int MINB, bool PREFETCH, bool COPYONLY = false, bool EARLYUN = false>
 __global__ void __launch_bounds__(NSP * 32, MINB)
 euler2d_march_kernel(const __grid_constant__ CUtensorMap tmap, MarchParams P, FrbOps ops) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -200,6 +200,14 @@ euler2d_march_kernel(const __grid_constant__ CUtensorMap tmap, MarchParams P, Fr
       for (int c = 0; c < 4 * NSP; ++c, pa += pstep) prefetch_l2(pa);
     }
     // tile q was already waited on as the "next" tile of step q-1 (or in the prologue)
+    double un[NSP][4];
+    if (EARLYUN && P.use_a && owner) {  // u_n of this row: issued before the x pass, used at the very end
+      const double *pa = P.ua + grow;
+#pragma unroll
+      for (int m = 0; m < 4; ++m)
+#pragma unroll
+        for (int l = 0; l < NSP; ++l, pa += pstep) un[l][m] = __ldcs(pa);
+    }
 
     if (COPYONLY) {  // measurement aid: the memory-access skeleton of the kernel without the math
       __syncthreads();
@@ -273,8 +281,7 @@ euler2d_march_kernel(const __grid_constant__ CUtensorMap tmap, MarchParams P, Fr
 
     // -------------------------------------------------------------- y pass: column k = t
     {
-      double un[NSP][4];
-      if (P.use_a && owner) {
+      if (!EARLYUN && P.use_a && owner) {
         const double *pa = P.ua + grow;
 #pragma unroll
         for (int m = 0; m < 4; ++m)
@@ -357,6 +364,8 @@ euler2d_march_kernel(const __grid_constant__ CUtensorMap tmap, MarchParams P, Fr
   }
 }
 
+#include "frb_euler2d_march4.cuh"
+
 // ---- host side: tensor-map cache and launch ---------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *,
                                   const cuuint64_t *, const cuuint64_t *, const cuuint32_t *,
@@ -411,7 +420,7 @@ static int march_rows_per_seg(frb_prob_t p, int ctas_per_sm) {
   return (p->ny + nseg - 1) / nseg;
 }
 
-template <int NSP, int NBUF, int MINB, bool PREFETCH, bool COPYONLY = false>
+template <int NSP, int NBUF, int MINB, bool PREFETCH, bool COPYONLY = false, bool EARLYUN = false>
 static int launch_march(frb_prob_t p, const CUtensorMap &map, MarchParams mp) {
   mp.rows_per_seg = march_rows_per_seg(p, MINB);
   const int strips = (p->nx + kOwn - 1) / kOwn;
@@ -419,16 +428,37 @@ static int launch_march(frb_prob_t p, const CUtensorMap &map, MarchParams mp) {
   const size_t smem = sizeof(Smem<NSP, NBUF>) + 128;
   static bool attr_done = false;
   if (!attr_done) {
-    FRB_CUDA(cudaFuncSetAttribute(euler2d_march_kernel<NSP, NBUF, MINB, PREFETCH, COPYONLY>,
+    FRB_CUDA(cudaFuncSetAttribute(euler2d_march_kernel<NSP, NBUF, MINB, PREFETCH, COPYONLY, EARLYUN>,
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    FRB_CUDA(cudaFuncSetAttribute(euler2d_march_kernel<NSP, NBUF, MINB, PREFETCH, COPYONLY>,
+    FRB_CUDA(cudaFuncSetAttribute(euler2d_march_kernel<NSP, NBUF, MINB, PREFETCH, COPYONLY, EARLYUN>,
                                   cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     attr_done = true;
   }
   dim3 grd(strips, segs), blk(NSP * 32);
-  euler2d_march_kernel<NSP, NBUF, MINB, PREFETCH, COPYONLY><<<grd, blk, smem, p->ctx->stream>>>(map, mp, p->ops);
+  euler2d_march_kernel<NSP, NBUF, MINB, PREFETCH, COPYONLY, EARLYUN><<<grd, blk, smem, p->ctx->stream>>>(map, mp, p->ops);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return frb_cuda_fail(e, "euler2d_march_kernel", __FILE__, __LINE__);
+  return 1;
+}
+
+template <int NSP, int MINB>
+static int launch_march4(frb_prob_t p, const CUtensorMap &map, MarchParams mp) {
+  mp.rows_per_seg = march_rows_per_seg(p, MINB);
+  const int strips = (p->nx + kOwn - 1) / kOwn;
+  const int segs = (mp.jhi - mp.jlo + 1 + mp.rows_per_seg - 1) / mp.rows_per_seg;
+  const size_t smem = sizeof(Smem4<NSP>) + 128;
+  static bool attr_done = false;
+  if (!attr_done) {
+    FRB_CUDA(cudaFuncSetAttribute(euler2d_march4_kernel<NSP, MINB>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    FRB_CUDA(cudaFuncSetAttribute(euler2d_march4_kernel<NSP, MINB>,
+                                  cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    attr_done = true;
+  }
+  dim3 grd(strips, segs), blk(NSP * 32);
+  euler2d_march4_kernel<NSP, MINB><<<grd, blk, smem, p->ctx->stream>>>(map, mp, p->ops);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return frb_cuda_fail(e, "euler2d_march4_kernel", __FILE__, __LINE__);
   return 1;
 }
 
@@ -482,8 +512,16 @@ int frb_launch_euler2d_march(frb_prob_t p, const double *u, const double *ua, do
     mp.cxs = -cdt / p->Jx; mp.cys = -cdt / p->Jy;
   }
   const bool pf = env_int("FRB_MARCH_PREFETCH", 1) != 0;  // L2 prefetch of the u_n row (+10 % on 24-B stages)
+  const int variant = env_int("FRB_MARCH_VARIANT", 3);
+  if (variant == 4) {
+    if (p->nsp == 4) return launch_march4<4, 3>(p, it->second, mp);
+    return launch_march4<3, 4>(p, it->second, mp);
+  }
   if (p->nsp == 4) {  // 72 KB smem, 168 regs
     if (env_int("FRB_MARCH_COPYONLY", 0)) return launch_march<4, 3, 3, true, true>(p, it->second, mp);
+    const int early = env_int("FRB_MARCH_EARLYUN", 0);
+    if (early == 1) return launch_march<4, 3, 3, false, false, true>(p, it->second, mp);
+    if (early == 2) return launch_march<4, 3, 3, true, false, true>(p, it->second, mp);
     if (pf) return launch_march<4, 3, 3, true>(p, it->second, mp);
     return launch_march<4, 3, 3, false>(p, it->second, mp);
   }
