@@ -11,7 +11,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libfrb200.so")
+# FRB200_LIB selects another build of the same ABI (kernel experiments, scripts/build_variants.py)
+LIB_PATH = os.environ.get("FRB200_LIB") or os.path.join(_HERE, "lib", "libfrb200.so")
 
 c_dp = C.POINTER(C.c_double)
 

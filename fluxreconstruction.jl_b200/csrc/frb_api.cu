@@ -7,6 +7,7 @@
 #include <cstring>
 
 #include "frb_internal.cuh"
+#include "frb_rc.cuh"
 
 static thread_local std::string g_err;
 
@@ -125,6 +126,20 @@ static int alloc_common(frb_prob_t p) {
   return FRB_OK;
 }
 
+// row-chunk mirror of the 2-D Euler state (the layout frb_step streams in, frb_rc.cuh); allocated
+// with the problem so that the multi-GPU path can export it
+static int alloc_rc(frb_prob_t p) {
+  if (!frb_euler2d_rc_supported(p) || getenv("FRB_NO_RC")) return FRB_OK;
+  const RcGeom g = rc_geom(p->nx, p->ny, p->nsp);
+  p->rc_len = g.len;
+  FRB_CUDA(cudaMalloc(&p->rc_base, sizeof(double) * 3 * g.len));
+  FRB_CUDA(cudaMemset(p->rc_base, 0, sizeof(double) * 3 * g.len));
+  p->ru = p->rc_base;
+  p->rs1 = p->rc_base + g.len;
+  p->rs2 = p->rc_base + 2 * g.len;
+  return FRB_OK;
+}
+
 static int upload_vec(frb_prob_t p, double **dst, const double *src, size_t n) {
   FRB_CUDA(cudaMalloc(dst, sizeof(double) * n));
   FRB_CUDA(cudaMemcpy(*dst, src, sizeof(double) * n, cudaMemcpyHostToDevice));
@@ -138,7 +153,7 @@ extern "C" int32_t frb_prob_destroy(frb_prob_t p) {
   cudaStreamSynchronize(p->ctx->stream);
   frb_halo_disconnect(p);
   frb_march_release(p);
-  cudaFree(p->u); cudaFree(p->s1); cudaFree(p->s2); cudaFree(p->du);
+  cudaFree(p->u); cudaFree(p->s1); cudaFree(p->s2); cudaFree(p->du); cudaFree(p->rc_base);
   cudaFree(p->J); cudaFree(p->velo); cudaFree(p->weights); cudaFree(p->prim);
   cudaFree(p->lim_w); cudaFree(p->flag);
   if (p->ev0) cudaEventDestroy(p->ev0);
@@ -205,6 +220,7 @@ extern "C" int32_t frb_euler2d_create(frb_ctx_t ctx, int32_t nx, int32_t ny,
   p->len = (int64_t)(nx + 2) * (ny + 2) * p->nsp * p->nsp * 4;
   p->dofs = (int64_t)nx * ny * p->nsp * p->nsp * 4;
   FRB_TRY(alloc_common(p));
+  FRB_TRY(alloc_rc(p));
   *out = p;
   return FRB_OK;
 }
@@ -258,6 +274,21 @@ extern "C" int32_t frb_ns2d_create(frb_ctx_t ctx, int32_t nx, int32_t ny, const 
 extern "C" int64_t frb_state_len(frb_prob_t p) { return p ? p->len : 0; }
 extern "C" int64_t frb_interior_dofs(frb_prob_t p) { return p ? p->dofs : 0; }
 
+// ---- layout bookkeeping ---------------------------------------------------------------
+// p->u (reference image) and p->ru (row-chunk mirror) are two representations of one state.
+// Every entry point that touches p->u first brings it up to date; the ones that may change it
+// invalidate the mirror.  frb_step on the RC path does the opposite.
+static int need_ref(frb_prob_t p, bool will_write) {
+  if (!p->ref_valid) {
+    int n = frb_rc_to_ref(p, p->ru, p->u);
+    if (n < 0) return n;
+    p->launches += n;
+    p->ref_valid = true;
+  }
+  if (will_write) p->rc_valid = false;
+  return FRB_OK;
+}
+
 // ---- state movement -------------------------------------------------------------------
 extern "C" int32_t frb_state_upload(frb_prob_t p, const double *u_host) {
   FRB_REQUIRE(p && u_host, FRB_ERR_ARG, "frb_state_upload: NULL argument");
@@ -265,6 +296,8 @@ extern "C" int32_t frb_state_upload(frb_prob_t p, const double *u_host) {
   cudaStream_t s = p->ctx->stream;
   FRB_CUDA(cudaMemcpyAsync(p->u, u_host, sizeof(double) * p->len, cudaMemcpyHostToDevice, s));
   FRB_CUDA(cudaStreamSynchronize(s));
+  p->ref_valid = true;
+  p->rc_valid = false;
   return FRB_OK;
 }
 
@@ -272,6 +305,7 @@ extern "C" int32_t frb_state_download(frb_prob_t p, double *u_host) {
   FRB_REQUIRE(p && u_host, FRB_ERR_ARG, "frb_state_download: NULL argument");
   FRB_CUDA(cudaSetDevice(p->ctx->device));
   cudaStream_t s = p->ctx->stream;
+  if (int rc = need_ref(p, false)) return rc;
   FRB_CUDA(cudaMemcpyAsync(u_host, p->u, sizeof(double) * p->len, cudaMemcpyDeviceToHost, s));
   FRB_CUDA(cudaStreamSynchronize(s));
   return FRB_OK;
@@ -279,6 +313,9 @@ extern "C" int32_t frb_state_download(frb_prob_t p, double *u_host) {
 
 extern "C" int32_t frb_state_device_ptr(frb_prob_t p, double **dptr) {
   FRB_REQUIRE(p && dptr, FRB_ERR_ARG, "frb_state_device_ptr: NULL argument");
+  FRB_CUDA(cudaSetDevice(p->ctx->device));
+  if (int rc = need_ref(p, true)) return rc;  // the caller may write through the pointer
+  FRB_CUDA(cudaStreamSynchronize(p->ctx->stream));
   *dptr = p->u;
   return FRB_OK;
 }
@@ -288,6 +325,13 @@ static bool use_march(frb_prob_t p) {
   if (p->kind != K_EULER2D) return false;
   if (p->kernel_kind == FRB_KERNEL_GENERIC) return false;
   return frb_euler2d_march_supported(p);
+}
+
+// frb_step streams in the row-chunk layout when it can: 2-D Euler, deg 2..3, no limiter hook
+// (the limiter kernel works on the reference image)
+static bool use_rc(frb_prob_t p) {
+  if (p->kind != K_EULER2D || !p->rc_base || p->limiter_on) return false;
+  return p->kernel_kind == FRB_KERNEL_AUTO || p->kernel_kind == FRB_KERNEL_RC;
 }
 
 static cudaEvent_t prof_event(frb_prob_t p) {
@@ -356,8 +400,13 @@ extern "C" int32_t frb_rhs(frb_prob_t p, const double *u_host, double *du_host, 
   FRB_CUDA(cudaSetDevice(p->ctx->device));
   cudaStream_t s = p->ctx->stream;
   if (int rc = ensure_du(p)) return rc;
-  if (u_host)
+  if (u_host) {
     FRB_CUDA(cudaMemcpyAsync(p->u, u_host, sizeof(double) * p->len, cudaMemcpyHostToDevice, s));
+    p->ref_valid = true;
+    p->rc_valid = false;
+  } else if (int rc = need_ref(p, false)) {
+    return rc;
+  }
   const int64_t l0 = p->launches;
   prof_begin(p);
   FRB_CUDA(cudaEventRecord(p->ev0, s));
@@ -384,6 +433,8 @@ extern "C" int32_t frb_rhs_pipelined(frb_prob_t p, const double *u_host, double 
   FRB_CUDA(cudaSetDevice(p->ctx->device));
   if (int rc = ensure_du(p)) return rc;
   cudaStream_t sc = p->ctx->stream, si = p->ctx->copy_in, so = p->ctx->copy_out;
+  p->ref_valid = true;  // p->u is overwritten slab by slab
+  p->rc_valid = false;
   FRB_CUDA(cudaStreamSynchronize(sc));  // du memset / earlier work
   const size_t NXG = p->nx + 2, NE = NXG * (size_t)(p->ny + 2);
   const int nplanes = 4 * p->nsp * p->nsp;
@@ -469,6 +520,7 @@ extern "C" int32_t frb_ghost_fill(frb_prob_t p, int32_t ghost_mode) {
   FRB_REQUIRE(p, FRB_ERR_ARG, "frb_ghost_fill: prob is NULL");
   FRB_REQUIRE(p->kind == K_EULER2D, FRB_ERR_STATE, "frb_ghost_fill: euler2d problems only");
   FRB_CUDA(cudaSetDevice(p->ctx->device));
+  if (int rc = need_ref(p, true)) return rc;
   int n = frb_launch_ghost_fill2d(p, p->u, ghost_mode);
   if (n < 0) return n;
   p->launches += n;
@@ -482,6 +534,7 @@ extern "C" int32_t frb_limiter_positivity(frb_prob_t p, const double *weights, i
               "frb_limiter_positivity: Euler problems only");
   FRB_CUDA(cudaSetDevice(p->ctx->device));
   if (int rc = set_limiter_weights(p, weights)) return rc;
+  if (int rc = need_ref(p, true)) return rc;
   FRB_CUDA(cudaMemsetAsync(p->flag, 0, sizeof(int), p->ctx->stream));
   int n = run_limiter(p);
   if (n < 0) return n;
@@ -508,12 +561,28 @@ static int halo_wait_if_pending(frb_prob_t p) {
 
 // one fused stage; on the slab-parallel path preceded by the wait for the neighbours' rows of
 // the previous stage and followed by the push of this stage's boundary rows + the flag
-static int stage_x(frb_prob_t p, const double *u, const double *ua, double *out, FrbStage st) {
+static int stage_x(frb_prob_t p, const double *u, const double *ua, double *out, FrbStage st, bool rc) {
   int n;
   if ((n = halo_wait_if_pending(p)) < 0) return n;
-  if ((n = launch_stage(p, u, ua, out, st)) < 0) return n;
+  if (rc) {
+    double *plo = nullptr, *phi = nullptr;
+    int nlo = 0, nhi = 0;
+    frb_halo_stage_targets(p, out, &plo, &phi, &nlo, &nhi);
+    if (p->profiling) {
+      cudaEvent_t e0 = prof_event(p), e1 = prof_event(p);
+      if (e0 && e1) cudaEventRecord(e0, p->ctx->stream);
+      n = frb_launch_euler2d_rc(p, u, ua, out, st, plo, phi, nlo);
+      if (e0 && e1) cudaEventRecord(e1, p->ctx->stream);
+    } else {
+      n = frb_launch_euler2d_rc(p, u, ua, out, st, plo, phi, nlo);
+    }
+    if (n < 0) return n;
+    p->launches += n;
+  } else if ((n = launch_stage(p, u, ua, out, st)) < 0) {
+    return n;
+  }
   if (frb_halo_active(p)) {
-    if (!use_march(p)) {  // the marching kernel stores its boundary rows to the peers itself
+    if (!rc && !use_march(p)) {  // the marching kernels store their boundary rows to the peers themselves
       if ((n = frb_halo_push(p, out, frb_halo_role(p, out), false, -1)) < 0) return n;
       p->launches += n;
     }
@@ -524,18 +593,19 @@ static int stage_x(frb_prob_t p, const double *u, const double *ua, double *out,
   return 0;
 }
 
-static int one_step(frb_prob_t p, int scheme, double dt) {
+static int one_step(frb_prob_t p, int scheme, double dt, bool rc) {
   int n;
   const bool par = frb_halo_active(p);
+  double *&U = rc ? p->ru : p->u, *&S1 = rc ? p->rs1 : p->s1, *&S2 = rc ? p->rs2 : p->s2;
   if (p->limiter_on) {
     if ((n = run_limiter(p)) < 0) return n;
   }
   if (p->ghost_mode != FRB_GHOST_NONE) {
     if (par) {
       if ((n = halo_wait_if_pending(p)) < 0) return n;  // neighbours are done with the last stage
-      n = frb_launch_ghost_x2d(p, p->u, p->ghost_mode);
+      n = rc ? frb_rc_ghost_x(p, U, p->ghost_mode) : frb_launch_ghost_x2d(p, U, p->ghost_mode);
     } else {
-      n = frb_launch_ghost_fill2d(p, p->u, p->ghost_mode);
+      n = rc ? frb_rc_ghost_fill(p, U, p->ghost_mode) : frb_launch_ghost_fill2d(p, U, p->ghost_mode);
     }
     if (n < 0) return n;
     p->launches += n;
@@ -546,10 +616,12 @@ static int one_step(frb_prob_t p, int scheme, double dt) {
     int nr = 1, rk = frb_halo_rank(p, &nr);
     const bool seam_local = !par || p->ghost_mode == FRB_GHOST_NONE;
     const bool row0 = !par || (rk == 0 && seam_local), rowN = !par || (rk == nr - 1 && seam_local);
-    if ((n = frb_launch_ring_copy2d(p, p->u, p->s1, row0, rowN)) < 0) return n;
+    n = rc ? frb_rc_ring_copy(p, U, S1, row0, rowN) : frb_launch_ring_copy2d(p, U, S1, row0, rowN);
+    if (n < 0) return n;
     p->launches += n;
     if (scheme == FRB_SCHEME_SSPRK3) {
-      if ((n = frb_launch_ring_copy2d(p, p->u, p->s2, row0, rowN)) < 0) return n;
+      n = rc ? frb_rc_ring_copy(p, U, S2, row0, rowN) : frb_launch_ring_copy2d(p, U, S2, row0, rowN);
+      if (n < 0) return n;
       p->launches += n;
     }
   }
@@ -558,7 +630,7 @@ static int one_step(frb_prob_t p, int scheme, double dt) {
     // boundary rows (frozen for the step, so they go into all three buffers of the peer)
     const int flip = p->ghost_mode == FRB_GHOST_WAVE_X ? 2 : -1;
     for (int role = 0; role < 3; ++role) {
-      if ((n = frb_halo_push(p, p->u, role, true, flip)) < 0) return n;
+      if ((n = frb_halo_push(p, U, role, true, flip)) < 0) return n;
       p->launches += n;
     }
     if ((n = frb_halo_signal(p)) < 0) return n;
@@ -567,24 +639,41 @@ static int one_step(frb_prob_t p, int scheme, double dt) {
   }
   if (scheme == FRB_SCHEME_EULER) {
     FrbStage st = {0.0, 1.0, dt, 0, 0};
-    if ((n = stage_x(p, p->u, nullptr, p->s1, st)) < 0) return n;
-    std::swap(p->u, p->s1);
-    frb_halo_swap_roles(p, 0, 1);
+    if ((n = stage_x(p, U, nullptr, S1, st, rc)) < 0) return n;
+    std::swap(U, S1);
+    frb_halo_swap_roles(p, 0, 1, rc);
   } else if (scheme == FRB_SCHEME_MIDPOINT) {
     FrbStage a = {0.0, 1.0, 0.5 * dt, 0, 0};
-    if ((n = stage_x(p, p->u, nullptr, p->s1, a)) < 0) return n;
+    if ((n = stage_x(p, U, nullptr, S1, a, rc)) < 0) return n;
     FrbStage b = {1.0, 0.0, dt, 1, 0};
-    if ((n = stage_x(p, p->s1, p->u, p->u, b)) < 0) return n;
+    if ((n = stage_x(p, S1, U, U, b, rc)) < 0) return n;
   } else if (scheme == FRB_SCHEME_SSPRK3) {
     FrbStage a = {0.0, 1.0, dt, 0, 0};
-    if ((n = stage_x(p, p->u, nullptr, p->s1, a)) < 0) return n;
+    if ((n = stage_x(p, U, nullptr, S1, a, rc)) < 0) return n;
     FrbStage b = {0.75, 0.25, dt, 1, 0, 1};
-    if ((n = stage_x(p, p->s1, p->u, p->s2, b)) < 0) return n;
+    if ((n = stage_x(p, S1, U, S2, b, rc)) < 0) return n;
     FrbStage c = {1.0 / 3.0, 2.0 / 3.0, dt, 1, 0, 1};
-    if ((n = stage_x(p, p->s2, p->u, p->u, c)) < 0) return n;
+    if ((n = stage_x(p, S2, U, U, c, rc)) < 0) return n;
   } else {
     frb_set_error("frb_step: unknown scheme");
     return FRB_ERR_ARG;
+  }
+  return FRB_OK;
+}
+
+// bring the row-chunk mirror up to date (first RC step after an upload / a reference-image call)
+static int need_rc(frb_prob_t p) {
+  if (p->rc_valid) return FRB_OK;
+  int n;
+  if ((n = halo_wait_if_pending(p)) < 0) return n;  // the neighbours' rows of p->u have landed
+  if ((n = frb_rc_from_ref(p, p->u, p->ru)) < 0) return n;
+  p->launches += n;
+  p->rc_valid = true;
+  if (frb_halo_active(p)) {
+    // the neighbours may store into my RC halo rows only after this conversion: one more epoch
+    if ((n = frb_halo_signal(p)) < 0) return n;
+    p->launches += n;
+    p->halo_pending = true;
   }
   return FRB_OK;
 }
@@ -595,12 +684,21 @@ extern "C" int32_t frb_step(frb_prob_t p, int32_t scheme, double dt, int32_t nst
   FRB_CUDA(cudaSetDevice(p->ctx->device));
   cudaStream_t s = p->ctx->stream;
   const int64_t l0 = p->launches;
+  const bool rc = use_rc(p);
   prof_begin(p);
+  if (nsteps > 0) {
+    if (rc) {
+      if (int r = need_rc(p)) return r;
+      p->ref_valid = false;
+    } else if (int r = need_ref(p, true)) {
+      return r;
+    }
+  }
   if (p->limiter_on) FRB_CUDA(cudaMemsetAsync(p->flag, 0, sizeof(int), s));
   FRB_CUDA(cudaEventRecord(p->ev0, s));
   for (int it = 0; it < nsteps; ++it) {
-    int rc = one_step(p, scheme, dt);
-    if (rc < 0) return rc;
+    int r = one_step(p, scheme, dt, rc);
+    if (r < 0) return r;
   }
   FRB_CUDA(cudaEventRecord(p->ev1, s));
   int bad = 0;
@@ -610,7 +708,7 @@ extern "C" int32_t frb_step(frb_prob_t p, int32_t scheme, double dt, int32_t nst
   FRB_CUDA(cudaEventElapsedTime(&p->last_ms, p->ev0, p->ev1));
   p->last_launches = p->launches - l0;
   prof_collect(p);
-  if (int rc = frb_halo_check_timeout(p)) return rc;
+  if (int r = frb_halo_check_timeout(p)) return r;
   if (bad) {
     frb_set_error("incorrect range of limiter parameter t");
     return FRB_ERR_NUMERIC;
@@ -623,14 +721,23 @@ extern "C" int32_t frb_time_stage(frb_prob_t p, int32_t stage_kind, int32_t iter
   FRB_REQUIRE(p && ms && iters > 0, FRB_ERR_ARG, "frb_time_stage: bad argument");
   FRB_CUDA(cudaSetDevice(p->ctx->device));
   cudaStream_t s = p->ctx->stream;
+  const bool rc = use_rc(p) && !frb_halo_active(p);
   // scratch: u_n := s1 (copy of the state so that the arithmetic sees finite data)
-  FRB_CUDA(cudaMemcpyAsync(p->s1, p->u, sizeof(double) * p->len, cudaMemcpyDeviceToDevice, s));
+  if (rc) {
+    if (int r = need_rc(p)) return r;
+    FRB_CUDA(cudaMemcpyAsync(p->rs1, p->ru, sizeof(double) * p->rc_len, cudaMemcpyDeviceToDevice, s));
+  } else {
+    if (int r = need_ref(p, false)) return r;
+    FRB_CUDA(cudaMemcpyAsync(p->s1, p->u, sizeof(double) * p->len, cudaMemcpyDeviceToDevice, s));
+  }
   FrbStage st = stage_kind == 0 ? FrbStage{0.0, 1.0, 1e-9, 0, 0} : FrbStage{0.75, 0.25, 0.25e-9, 1, 0};
   const int64_t l0 = p->launches;
   FRB_CUDA(cudaEventRecord(p->ev0, s));
   for (int it = 0; it < iters; ++it) {
-    int n = launch_stage(p, p->u, p->s1, p->s2, st);
+    int n = rc ? frb_launch_euler2d_rc(p, p->ru, p->rs1, p->rs2, st, nullptr, nullptr, 0)
+               : launch_stage(p, p->u, p->s1, p->s2, st);
     if (n < 0) return n;
+    if (rc) p->launches += n;
   }
   FRB_CUDA(cudaEventRecord(p->ev1, s));
   FRB_CUDA(cudaStreamSynchronize(s));
@@ -651,8 +758,10 @@ extern "C" int32_t frb_last_timing(frb_prob_t p, float *ms, int64_t *kernel_laun
 
 extern "C" int32_t frb_set_kernel(frb_prob_t p, int32_t kind) {
   FRB_REQUIRE(p, FRB_ERR_ARG, "frb_set_kernel: prob is NULL");
-  FRB_REQUIRE(kind >= FRB_KERNEL_AUTO && kind <= FRB_KERNEL_MARCH, FRB_ERR_ARG,
+  FRB_REQUIRE(kind >= FRB_KERNEL_AUTO && kind <= FRB_KERNEL_RC, FRB_ERR_ARG,
               "frb_set_kernel: unknown kernel kind");
+  if (kind == FRB_KERNEL_RC)
+    FRB_REQUIRE(p->rc_base != nullptr, FRB_ERR_STATE, "frb_set_kernel: row-chunk kernel needs euler2d, deg 2..3");
   if (kind == FRB_KERNEL_MARCH)
     FRB_REQUIRE(frb_euler2d_march_supported(p), FRB_ERR_STATE,
                 "frb_set_kernel: marching kernel needs euler2d, deg 2..3 and even nx");

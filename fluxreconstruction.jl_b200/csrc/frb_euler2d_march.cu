@@ -30,46 +30,13 @@
 
 #include "frb_internal.cuh"
 #include "frb_physics.cuh"
+#include "frb_ptx.cuh"
 
 namespace {
 
 constexpr int kOwn = 30;  // owned elements per strip (32 lanes - 2 halo lanes)
 
-__device__ __forceinline__ uint32_t smem_u32(const void *p) {
-  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
-}
-__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
-               "r"(bytes)
-               : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "WAIT_LOOP:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-      "@p bra WAIT_DONE;\n"
-      "bra WAIT_LOOP;\n"
-      "WAIT_DONE:\n"
-      "}\n" ::"r"(smem_u32(bar)),
-      "r"(parity)
-      : "memory");
-}
-__device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *map, uint64_t *bar,
-                                            int c0, int c1, int c2) {
-  asm volatile(
-      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes"
-      " [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(smem_u32(dst)),
-      "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
-      : "memory");
-}
-__device__ __forceinline__ void prefetch_l2(const void *p) {
-  asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
-}
+using namespace frbptx;
 
 struct MarchParams {
   const double *ua;  // u_n (may alias out)
@@ -79,7 +46,6 @@ struct MarchParams {
   int jlo, jhi;  // rows to update (1..ny for a whole-mesh launch; a sub-range for the pipelined path)
   double gamma;
   double ca, cb;
-  double cxs, cys;  // -cdt/Jx, -cdt/Jy  (L = -(dux/Jx + duy/Jy))
   int use_a;
   // slab-parallel path: the first / last owned row is also stored straight into the halo row
   // of the rank below / above (peer memory over NVLink); NULL when there is no such neighbour
@@ -112,9 +78,9 @@ __device__ __forceinline__ void col_trace(const double *__restrict__ Uy, const d
 }
 
 // MINB = resident CTAs per SM the register budget is compiled for
-template <int NSP, int NBUF, int MINB, bool PREFETCH, bool COPYONLY = false, bool EARLYUN = false>
+template <int NSP, int NBUF, int MINB, bool PREFETCH, bool USEA, bool SAMEJ, bool COPYONLY = false>
 __global__ void __launch_bounds__(NSP * 32, MINB)
-euler2d_march_kernel(const __grid_constant__ CUtensorMap tmap, MarchParams P, FrbOps ops) {
+euler2d_march_kernel(const __grid_constant__ CUtensorMap tmap, MarchParams P, MarchOps ops) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   using SM = Smem<NSP, NBUF>;
   // keep the pointer in the shared window (LDS/STS, not generic LD/ST): align by offset
@@ -132,6 +98,7 @@ euler2d_march_kernel(const __grid_constant__ CUtensorMap tmap, MarchParams P, Fr
   const int ntiles = jb - ja + 3;  // rows ja-1 .. jb+1; tile q holds row ja-1+q in buffer q % NBUF
   const size_t NXG = P.nx + 2, NE = NXG * (size_t)(P.ny + 2);
   const bool owner = lane >= 1 && lane <= kOwn && i <= P.nx;
+  const int own = owner ? 1 : 0;
   const double gamma = P.gamma, gm1 = gamma - 1.0;
   const int c0 = blockIdx.x * kOwn;
 
@@ -157,9 +124,11 @@ euler2d_march_kernel(const __grid_constant__ CUtensorMap tmap, MarchParams P, Fr
   const double *const xrpy = S.xrp + offy;
   // global plane walk: plane(t, l, m) = t + NSP*(l + NSP*m)  ->  base + NE*t, step NE*NSP
   const size_t pstep = NE * NSP;
-  const size_t goff = i + NE * (size_t)t;
+  // non-owner lanes never touch global memory; give them the address of an owner lane so that
+  // every address the loop forms is in bounds
+  const size_t goff = (owner ? i : (size_t)(blockIdx.x * kOwn + 1)) + NE * (size_t)t;
 
-  if (PREFETCH && P.use_a && owner) {  // u_n rows of the first kPfDist steps
+  if (PREFETCH && USEA && owner) {  // u_n rows of the first pfdist steps -> L2
     for (int r = 0; r < P.pfdist && ja + r <= jb; ++r) {
       const double *pa = P.ua + goff + NXG * (size_t)(ja + r);
       for (int c = 0; c < 4 * NSP; ++c, pa += pstep) prefetch_l2(pa);
@@ -191,23 +160,18 @@ euler2d_march_kernel(const __grid_constant__ CUtensorMap tmap, MarchParams P, Fr
     const int buf = q % NBUF, nbuf = (q + 1) % NBUF;
     const double *const Ux = S.tile[0] + buf * kTile + offx;
     const double *const Uy = S.tile[0] + buf * kTile + offy;
-    const size_t grow = goff + NXG * (size_t)j;
-    if (PREFETCH && P.use_a && owner && j + P.pfdist <= jb) {
-      // pull the u_n row needed kPfDist steps from now into L2; the loads after the x pass of
-      // that step then hit L2 instead of waiting on DRAM
+    size_t grow = goff + NXG * (size_t)j;
+    // opaque to the optimiser: otherwise it keeps one 64-bit induction variable per plane
+    // (16 planes x {load, store} -> 60+ registers of loop-carried offsets)
+    asm volatile("" : "+l"(grow));
+    // pull the u_n row needed pfdist steps from now into L2 (one bulk prefetch by one thread);
+    // the loads at the top of that step's y pass then hit L2 instead of waiting on DRAM
+    if (PREFETCH && USEA && owner && j + P.pfdist <= jb) {
       const double *pa = P.ua + grow + NXG * (size_t)P.pfdist;
 #pragma unroll
       for (int c = 0; c < 4 * NSP; ++c, pa += pstep) prefetch_l2(pa);
     }
     // tile q was already waited on as the "next" tile of step q-1 (or in the prologue)
-    double un[NSP][4];
-    if (EARLYUN && P.use_a && owner) {  // u_n of this row: issued before the x pass, used at the very end
-      const double *pa = P.ua + grow;
-#pragma unroll
-      for (int m = 0; m < 4; ++m)
-#pragma unroll
-        for (int l = 0; l < NSP; ++l, pa += pstep) un[l][m] = __ldcs(pa);
-    }
 
     if (COPYONLY) {  // measurement aid: the memory-access skeleton of the kernel without the math
       __syncthreads();
@@ -217,7 +181,7 @@ euler2d_march_kernel(const __grid_constant__ CUtensorMap tmap, MarchParams P, Fr
 #pragma unroll
       for (int c = 0; c < 4 * NSP; ++c, pa += pstep, po += pstep) {
         double v = P.cb * Uy[32 * NSP * c];
-        if (P.use_a && owner) v = fma(P.ca, __ldcs(pa), v);
+        if (USEA && owner) v = fma(P.ca, __ldcs(pa), v);
         if (owner) __stcs(po, v);
       }
       __syncthreads();
@@ -264,16 +228,17 @@ euler2d_march_kernel(const __grid_constant__ CUtensorMap tmap, MarchParams P, Fr
       const double hL[4] = {hl.f0, hl.f1, hl.f2, hl.f3};
       const double hR[4] = {__shfl_down_sync(0xffffffffu, hl.f0, 1), __shfl_down_sync(0xffffffffu, hl.f1, 1),
                             __shfl_down_sync(0xffffffffu, hl.f2, 1), __shfl_down_sync(0xffffffffu, hl.f3, 1)};
-      // d/dr + correction with the flux traces folded into dmod (see FrbOps)
+      // cb*u + (-cdt/Jx) * (d/dr + correction), flux traces folded into dmx (see MarchOps)
 #pragma unroll
       for (int m = 0; m < 4; ++m)
 #pragma unroll
         for (int k = 0; k < NSP; ++k) {
-          double d = f[0][m] * ops.dmod[k * FRB_NSPMAX];
+          // re-read (volatile: no CSE with the loads above) keeps u out of the HLL's live set
+          double d = P.cb * w[k][m];
 #pragma unroll
-          for (int q2 = 1; q2 < NSP; ++q2) d = fma(f[q2][m], ops.dmod[k * FRB_NSPMAX + q2], d);
-          d = fma(hL[m], ops.dgl[k], d);
-          d = fma(hR[m], ops.dgr[k], d);
+          for (int q2 = 0; q2 < NSP; ++q2) d = fma(f[q2][m], ops.dmx[k * 4 + q2], d);
+          d = fma(hL[m], ops.glx[k], d);
+          d = fma(hR[m], ops.grx[k], d);
           xdx[32 * (k + NSP * NSP * m)] = d;
         }
     }
@@ -281,33 +246,32 @@ euler2d_march_kernel(const __grid_constant__ CUtensorMap tmap, MarchParams P, Fr
 
     // -------------------------------------------------------------- y pass: column k = t
     {
-      if (!EARLYUN && P.use_a && owner) {
+      double un[NSP][4];
+      if (USEA) {
         const double *pa = P.ua + grow;
 #pragma unroll
         for (int m = 0; m < 4; ++m)
 #pragma unroll
           for (int l = 0; l < NSP; ++l, pa += pstep) un[l][m] = __ldcs(pa);
       }
-      double w[NSP][4], g[NSP][4];  // [l][m]
-#pragma unroll
-      for (int m = 0; m < 4; ++m)
-#pragma unroll
-        for (int l = 0; l < NSP; ++l) w[l][m] = Uy[32 * NSP * (l + NSP * m)];
-#pragma unroll
-      for (int l = 0; l < NSP; ++l) {
-        double rr = xrpy[32 * NSP * l];
-        double p = xrpy[32 * NSP * (NSP + l)];
-        double vy = w[l][2] * rr;
-        g[l][0] = w[l][2];
-        g[l][1] = w[l][1] * vy;
-        g[l][2] = fma(w[l][2], vy, p);
-        g[l][3] = (w[l][3] + p) * vy;
-      }
-      // top face of row j: HLL between this row's top trace and row j+1's bottom trace
-      mbar_wait(&S.bar[nbuf], ((q + 1) / NBUF) & 1);
-      double ht[4];
+      double g[NSP][4];  // [l][m]
+      double uT[4];
       {
-        double uT[4], uB[4];
+        double w[NSP][4];
+#pragma unroll
+        for (int m = 0; m < 4; ++m)
+#pragma unroll
+          for (int l = 0; l < NSP; ++l) w[l][m] = Uy[32 * NSP * (l + NSP * m)];
+#pragma unroll
+        for (int l = 0; l < NSP; ++l) {
+          double rr = xrpy[32 * NSP * l];
+          double p = xrpy[32 * NSP * (NSP + l)];
+          double vy = w[l][2] * rr;
+          g[l][0] = w[l][2];
+          g[l][1] = w[l][1] * vy;
+          g[l][2] = fma(w[l][2], vy, p);
+          g[l][3] = (w[l][3] + p) * vy;
+        }
 #pragma unroll
         for (int m = 0; m < 4; ++m) {
           double a = w[0][m] * ops.lr[0];
@@ -315,44 +279,34 @@ euler2d_march_kernel(const __grid_constant__ CUtensorMap tmap, MarchParams P, Fr
           for (int q2 = 1; q2 < NSP; ++q2) a = fma(w[q2][m], ops.lr[q2], a);
           uT[m] = a;
         }
+      }
+      // top face of row j: HLL between this row's top trace and row j+1's bottom trace
+      mbar_wait(&S.bar[nbuf], ((q + 1) / NBUF) & 1);
+      double ht[4];
+      {
+        double uB[4];
         col_trace<NSP>(S.tile[0] + nbuf * kTile + offy, ops.ll, uB);
         frb::Flux4 h = frb::hll4_y_fast(uT[0], uT[1], uT[2], uT[3], uB[0], uB[1], uB[2], uB[3], gamma, gm1);
         ht[0] = h.f0; ht[1] = h.f1; ht[2] = h.f2; ht[3] = h.f3;
       }
+      // four independent FMA chains per variable, stored as soon as they retire
       double *po = P.out + grow;
 #pragma unroll
       for (int m = 0; m < 4; ++m) {
+        double v[NSP];
 #pragma unroll
-        for (int l = 0; l < NSP; ++l, po += pstep) {
-          double d = g[0][m] * ops.dmod[l * FRB_NSPMAX];
+        for (int l = 0; l < NSP; ++l) {
+          double d = xdy[32 * NSP * (l + NSP * m)];
 #pragma unroll
-          for (int q2 = 1; q2 < NSP; ++q2) d = fma(g[q2][m], ops.dmod[l * FRB_NSPMAX + q2], d);
-          d = fma(hb[m], ops.dgl[l], d);
-          d = fma(ht[m], ops.dgr[l], d);
-          double dx = xdy[32 * NSP * (l + NSP * m)];
-          double v = fma(P.cys, d, fma(P.cxs, dx, P.cb * w[l][m]));
-          if (P.use_a) v = fma(P.ca, un[l][m], v);
-          if (owner) __stcs(po, v);
+          for (int q2 = 0; q2 < NSP; ++q2) d = fma(g[q2][m], (SAMEJ ? ops.dmx : ops.dmy)[l * 4 + q2], d);
+          d = fma(hb[m], (SAMEJ ? ops.glx : ops.gly)[l], d);
+          d = fma(ht[m], (SAMEJ ? ops.grx : ops.gry)[l], d);
+          if (USEA) d = fma(P.ca, un[l][m], d);
+          v[l] = d;
         }
+#pragma unroll
+        for (int l = 0; l < NSP; ++l, po += pstep) st_cs_if(po, v[l], own);
         hb[m] = ht[m];
-      }
-    }
-    // slab-parallel path: the first / last owned row also goes straight into the halo row of the
-    // rank below / above (peer memory over NVLink).  CTA-uniform, two rows per strip: each thread
-    // forwards the values it has just stored (its own writes, L2-hot).
-    if ((j == 1 && P.peer_lo) || (j == P.ny && P.peer_hi)) {
-      if (owner) {
-        const double *src = P.out + grow;
-        if (j == 1 && P.peer_lo) {
-          const size_t NEl = NXG * (size_t)(P.nyl_lo + 2);
-          double *dst = P.peer_lo + i + NXG * (size_t)(P.nyl_lo + 1) + NEl * (size_t)t;
-          for (int c = 0; c < 4 * NSP; ++c) dst[NEl * NSP * c] = src[pstep * c];
-        }
-        if (j == P.ny && P.peer_hi) {
-          const size_t NEh = NXG * (size_t)(P.nyl_hi + 2);
-          double *dst = P.peer_hi + i + NEh * (size_t)t;
-          for (int c = 0; c < 4 * NSP; ++c) dst[NEh * NSP * c] = src[pstep * c];
-        }
       }
     }
     __syncthreads();  // (B) every read of tile[buf], xd, xrp is done
@@ -362,9 +316,27 @@ euler2d_march_kernel(const __grid_constant__ CUtensorMap tmap, MarchParams P, Fr
       tma_load_3d(S.tile[buf], &tmap, &S.bar[buf], c0, ja - 1 + q + NBUF, 0);
     }
   }
+  // slab-parallel path: the first / last owned row also goes straight into the halo row of the
+  // rank below / above (peer memory over NVLink).  Each thread forwards the values it stored
+  // itself (program order, L2-hot), once per segment that owns row 1 / row ny.
+  if (owner && ((ja == 1 && P.peer_lo) || (jb == P.ny && P.peer_hi))) {
+    const size_t go = i + NE * (size_t)t;
+    if (ja == 1 && P.peer_lo) {
+      const double *src = P.out + go + NXG;
+      const size_t NEl = NXG * (size_t)(P.nyl_lo + 2);
+      double *dst = P.peer_lo + i + NXG * (size_t)(P.nyl_lo + 1) + NEl * (size_t)t;
+      for (int c = 0; c < 4 * NSP; ++c) dst[NEl * NSP * c] = src[pstep * c];
+    }
+    if (jb == P.ny && P.peer_hi) {
+      const double *src = P.out + go + NXG * (size_t)P.ny;
+      const size_t NEh = NXG * (size_t)(P.nyl_hi + 2);
+      double *dst = P.peer_hi + i + NEh * (size_t)t;
+      for (int c = 0; c < 4 * NSP; ++c) dst[NEh * NSP * c] = src[pstep * c];
+    }
+  }
 }
 
-#include "frb_euler2d_march4.cuh"
+
 
 // ---- host side: tensor-map cache and launch ---------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *,
@@ -420,54 +392,29 @@ static int march_rows_per_seg(frb_prob_t p, int ctas_per_sm) {
   return (p->ny + nseg - 1) / nseg;
 }
 
-template <int NSP, int NBUF, int MINB, bool PREFETCH, bool COPYONLY = false, bool EARLYUN = false>
-static int launch_march(frb_prob_t p, const CUtensorMap &map, MarchParams mp) {
+template <int NSP, int NBUF, int MINB, bool PREFETCH, bool USEA, bool SAMEJ, bool COPYONLY = false>
+static int launch_march(frb_prob_t p, const CUtensorMap &map, MarchParams mp, const MarchOps &mo) {
   mp.rows_per_seg = march_rows_per_seg(p, MINB);
   const int strips = (p->nx + kOwn - 1) / kOwn;
   const int segs = (mp.jhi - mp.jlo + 1 + mp.rows_per_seg - 1) / mp.rows_per_seg;
   const size_t smem = sizeof(Smem<NSP, NBUF>) + 128;
   static bool attr_done = false;
   if (!attr_done) {
-    FRB_CUDA(cudaFuncSetAttribute(euler2d_march_kernel<NSP, NBUF, MINB, PREFETCH, COPYONLY, EARLYUN>,
+    FRB_CUDA(cudaFuncSetAttribute(euler2d_march_kernel<NSP, NBUF, MINB, PREFETCH, USEA, SAMEJ, COPYONLY>,
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    FRB_CUDA(cudaFuncSetAttribute(euler2d_march_kernel<NSP, NBUF, MINB, PREFETCH, COPYONLY, EARLYUN>,
+    FRB_CUDA(cudaFuncSetAttribute(euler2d_march_kernel<NSP, NBUF, MINB, PREFETCH, USEA, SAMEJ, COPYONLY>,
                                   cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     attr_done = true;
   }
   dim3 grd(strips, segs), blk(NSP * 32);
-  euler2d_march_kernel<NSP, NBUF, MINB, PREFETCH, COPYONLY, EARLYUN><<<grd, blk, smem, p->ctx->stream>>>(map, mp, p->ops);
+  euler2d_march_kernel<NSP, NBUF, MINB, PREFETCH, USEA, SAMEJ, COPYONLY><<<grd, blk, smem, p->ctx->stream>>>(map, mp, mo);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return frb_cuda_fail(e, "euler2d_march_kernel", __FILE__, __LINE__);
   return 1;
 }
 
-template <int NSP, int MINB>
-static int launch_march4(frb_prob_t p, const CUtensorMap &map, MarchParams mp) {
-  mp.rows_per_seg = march_rows_per_seg(p, MINB);
-  const int strips = (p->nx + kOwn - 1) / kOwn;
-  const int segs = (mp.jhi - mp.jlo + 1 + mp.rows_per_seg - 1) / mp.rows_per_seg;
-  const size_t smem = sizeof(Smem4<NSP>) + 128;
-  static bool attr_done = false;
-  if (!attr_done) {
-    FRB_CUDA(cudaFuncSetAttribute(euler2d_march4_kernel<NSP, MINB>,
-                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    FRB_CUDA(cudaFuncSetAttribute(euler2d_march4_kernel<NSP, MINB>,
-                                  cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-    attr_done = true;
-  }
-  dim3 grd(strips, segs), blk(NSP * 32);
-  euler2d_march4_kernel<NSP, MINB><<<grd, blk, smem, p->ctx->stream>>>(map, mp, p->ops);
-  cudaError_t e = cudaGetLastError();
-  if (e != cudaSuccess) return frb_cuda_fail(e, "euler2d_march4_kernel", __FILE__, __LINE__);
-  return 1;
-}
-
-int frb_launch_euler2d_march(frb_prob_t p, const double *u, const double *ua, double *out,
-                             FrbStage st) {
-  if (!frb_euler2d_march_supported(p)) {
-    frb_set_error("marching kernel needs deg 2 or 3 and even nx");
-    return FRB_ERR_ARG;
-  }
+// TMA descriptor of one state buffer: dims (x, y, plane), box = 32 elements x 1 row x all planes
+static int march_tensor_map(frb_prob_t p, const double *u, const CUtensorMap **out) {
   if (!p->tmaps) p->tmaps = new MapCache();
   MapCache *mc = static_cast<MapCache *>(p->tmaps);
   auto it = mc->maps.find(u);
@@ -492,6 +439,18 @@ int frb_launch_euler2d_march(frb_prob_t p, const double *u, const double *ua, do
     }
     it = mc->maps.emplace(u, m).first;
   }
+  *out = &it->second;
+  return 0;
+}
+
+int frb_launch_euler2d_march(frb_prob_t p, const double *u, const double *ua, double *out,
+                             FrbStage st) {
+  if (!frb_euler2d_march_supported(p)) {
+    frb_set_error("marching kernel needs deg 2 or 3 and even nx");
+    return FRB_ERR_ARG;
+  }
+  const CUtensorMap *tmp = nullptr;
+  if (int rc = march_tensor_map(p, u, &tmp)) return rc;
   MarchParams mp;
   mp.ua = ua;
   mp.out = out;
@@ -503,27 +462,43 @@ int frb_launch_euler2d_march(frb_prob_t p, const double *u, const double *ua, do
   mp.pfdist = env_int("FRB_MARCH_PFDIST", 0);
   mp.gamma = p->gamma;
   frb_halo_stage_targets(p, out, &mp.peer_lo, &mp.peer_hi, &mp.nyl_lo, &mp.nyl_hi);
+  double cxs, cys;  // -cdt/Jx, -cdt/Jy  (L = -(dF/dr / Jx + dG/ds / Jy))
   if (st.rhs_only) {
     mp.ca = 0.0; mp.cb = 0.0; mp.use_a = 0;
-    mp.cxs = -1.0 / p->Jx; mp.cys = -1.0 / p->Jy;
+    cxs = -1.0 / p->Jx; cys = -1.0 / p->Jy;
   } else {
     const double cdt = st.nested ? st.cb * st.cdt : st.cdt;
     mp.ca = st.ca; mp.cb = st.cb; mp.use_a = st.use_a;
-    mp.cxs = -cdt / p->Jx; mp.cys = -cdt / p->Jy;
+    cxs = -cdt / p->Jx; cys = -cdt / p->Jy;
+  }
+  MarchOps mo;
+  const int n = p->nsp;
+  for (int k = 0; k < 4; ++k) {
+    const bool in = k < n;
+    mo.ll[k] = in ? p->ops.ll[k] : 0.0;
+    mo.lr[k] = in ? p->ops.lr[k] : 0.0;
+    mo.glx[k] = in ? cxs * p->ops.dgl[k] : 0.0;
+    mo.grx[k] = in ? cxs * p->ops.dgr[k] : 0.0;
+    mo.gly[k] = in ? cys * p->ops.dgl[k] : 0.0;
+    mo.gry[k] = in ? cys * p->ops.dgr[k] : 0.0;
+    for (int q = 0; q < 4; ++q) {
+      const double d = (in && q < n) ? p->ops.dmod[k * FRB_NSPMAX + q] : 0.0;
+      mo.dmx[k * 4 + q] = cxs * d;
+      mo.dmy[k * 4 + q] = cys * d;
+    }
   }
   const bool pf = env_int("FRB_MARCH_PREFETCH", 1) != 0;  // L2 prefetch of the u_n row (+10 % on 24-B stages)
-  const int variant = env_int("FRB_MARCH_VARIANT", 3);
-  if (variant == 4) {
-    if (p->nsp == 4) return launch_march4<4, 3>(p, it->second, mp);
-    return launch_march4<3, 4>(p, it->second, mp);
+  const bool samej = cxs == cys;  // one operator table set: no uniform-register spills
+#define FRB_MARCH_GO(NSP, NBUF, MINB, PF, UA, ...)                                         \
+  (samej ? launch_march<NSP, NBUF, MINB, PF, UA, true, ##__VA_ARGS__>(p, *tmp, mp, mo)     \
+         : launch_march<NSP, NBUF, MINB, PF, UA, false, ##__VA_ARGS__>(p, *tmp, mp, mo))
+  if (p->nsp == 4) {  // 72 KB smem -> 3 CTAs/SM
+    if (env_int("FRB_MARCH_COPYONLY", 0))
+      return mp.use_a ? launch_march<4, 3, 3, true, true, true, true>(p, *tmp, mp, mo)
+                      : launch_march<4, 3, 3, true, false, true, true>(p, *tmp, mp, mo);
+    if (mp.use_a) return pf ? FRB_MARCH_GO(4, 3, 3, true, true) : FRB_MARCH_GO(4, 3, 3, false, true);
+    return FRB_MARCH_GO(4, 3, 3, false, false);
   }
-  if (p->nsp == 4) {  // 72 KB smem, 168 regs
-    if (env_int("FRB_MARCH_COPYONLY", 0)) return launch_march<4, 3, 3, true, true>(p, it->second, mp);
-    const int early = env_int("FRB_MARCH_EARLYUN", 0);
-    if (early == 1) return launch_march<4, 3, 3, false, false, true>(p, it->second, mp);
-    if (early == 2) return launch_march<4, 3, 3, true, false, true>(p, it->second, mp);
-    if (pf) return launch_march<4, 3, 3, true>(p, it->second, mp);
-    return launch_march<4, 3, 3, false>(p, it->second, mp);
-  }
-  return launch_march<3, 3, 4, false>(p, it->second, mp);
+  return mp.use_a ? FRB_MARCH_GO(3, 3, 4, false, true) : FRB_MARCH_GO(3, 3, 4, false, false);
+#undef FRB_MARCH_GO
 }

@@ -1,0 +1,388 @@
+// Fused 2-D Euler residual + RK stage on the row-chunk layout (frb_rc.cuh): the roofline path
+// of the resident time loop (frb_step).
+//
+// Same arithmetic as frb_euler2d_march.cu (reference: dudt! of example/euler2d_wave.jl:35-107
+// + the OrdinaryDiffEq stage axpys): a CTA of NSP warps marches over the rows of one strip,
+// x pass (warp = point row l) -> shared memory -> y pass (warp = point column k), HLL once per
+// face, bottom-face flux carried in registers.  What changes is how bytes move:
+//   * u row j of the strip = ONE contiguous chunk -> one cp.async.bulk (UBLKCP) into the ring;
+//   * u_n row j = one more bulk copy into its own smem buffer, issued a whole row step before
+//     its use: no LDG latency on the critical path, no registers held for it;
+//   * u' goes out with full-line st.global.cs (a warp writes one aligned 256-B row of a plane),
+//     lanes 1 and 30 also refresh the duplicate of their column in the neighbouring chunk.
+// Shared memory (p3): 24-B stage 2 tiles + u_n + xd + xrp = 72 KB, 16-B stage 3 tiles + xd + xrp
+// = 72 KB -> 3 CTAs/SM either way.
+#include <cstdlib>
+
+#include "frb_internal.cuh"
+#include "frb_physics.cuh"
+#include "frb_ptx.cuh"
+#include "frb_rc.cuh"
+
+namespace {
+
+using namespace frbptx;
+
+struct RcParams {
+  const double *u;   // stage input (RC)
+  const double *ua;  // u_n (RC; may alias out)
+  double *out;
+  RcGeom g;
+  int rows_per_seg;
+  double gamma, ca, cb;
+  // slab-parallel path: rows 1 / ny are also stored into the halo row of the rank below / above
+  double *peer_lo, *peer_hi;
+  int nyl_lo;
+};
+
+template <int NSP, int NBUF, bool USEA>
+struct SmemRc {
+  static constexpr int kTile = 4 * NSP * NSP * 32;  // doubles
+  alignas(128) double tile[NBUF][kTile];
+  alignas(128) double un[USEA ? kTile : 16];
+  alignas(128) double xd[kTile];                 // x-pass output: cb*u (+) x derivative + correction
+  alignas(128) double xrp[2 * NSP * NSP * 32];   // 1/rho and p at the points
+  alignas(8) uint64_t bar[NBUF + 1];
+};
+
+template <int NSP>
+__device__ __forceinline__ void col_trace(const double *__restrict__ Uy, const double *l, double (&tr)[4]) {
+#pragma unroll
+  for (int m = 0; m < 4; ++m) {
+    double a = Uy[32 * NSP * (0 + NSP * m)] * l[0];
+#pragma unroll
+    for (int q = 1; q < NSP; ++q) a = fma(Uy[32 * NSP * (q + NSP * m)], l[q], a);
+    tr[m] = a;
+  }
+}
+
+template <int NSP, bool USEA, bool SAMEJ, int MINB>
+__global__ void __launch_bounds__(NSP * 32, MINB) euler2d_rc_kernel(RcParams P, MarchOps ops) {
+  constexpr int NBUF = USEA ? 2 : 3;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  using SM = SmemRc<NSP, NBUF, USEA>;
+  SM &S = *reinterpret_cast<SM *>(smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u));
+  constexpr int kTile = SM::kTile;
+  constexpr uint32_t kTileBytes = kTile * sizeof(double);
+  uint64_t *const bar_un = &S.bar[NBUF];
+
+  const RcGeom &g = P.g;
+  const int lane = threadIdx.x & 31;
+  const int t = threadIdx.x >> 5;  // point row l in the x pass, point column k in the y pass
+  const int s = blockIdx.x;
+  const int i = kRcOwn * s + lane;  // element column of this lane
+  const int ja = 1 + blockIdx.y * P.rows_per_seg;
+  const int jb = min(g.ny, ja + P.rows_per_seg - 1);
+  if (ja > g.ny) return;
+  const int ntiles = jb - ja + 3;  // rows ja-1 .. jb+1; tile q holds row ja-1+q in buffer q % NBUF
+  const bool owner = lane >= 1 && lane <= kRcOwn && i <= g.nx;
+  const int own = owner ? 1 : 0;
+  // the copy of my column in the neighbouring chunk (lane 1 -> lane 31 of strip s-1, lane 30 ->
+  // lane 0 of strip s+1)
+  const int dup = (owner && ((lane == 1 && s > 0) || (lane == kRcOwn && s < g.ns - 1))) ? 1 : 0;
+  const ptrdiff_t dup_off = lane == 1 ? (ptrdiff_t)(kRcOwn - g.chunk) : (ptrdiff_t)(g.chunk - kRcOwn);
+  const double gamma = P.gamma, gm1 = gamma - 1.0;
+  const size_t strip_off = (size_t)s * g.chunk;
+
+  if (threadIdx.x == 0) {
+    for (int b = 0; b < NBUF + 1; ++b) mbar_init(&S.bar[b], 1);
+    mbar_fence_init();
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const int npre = ntiles < NBUF ? ntiles : NBUF;
+    for (int q = 0; q < npre; ++q) {
+      mbar_expect_tx(&S.bar[q], kTileBytes);
+      bulk_load(S.tile[q], P.u + (size_t)(ja - 1 + q) * g.row + strip_off, kTileBytes, &S.bar[q]);
+    }
+    if (USEA) {
+      mbar_expect_tx(bar_un, kTileBytes);
+      bulk_load(S.un, P.ua + (size_t)ja * g.row + strip_off, kTileBytes, bar_un);
+    }
+  }
+
+  // per-thread views of a tile (= of a chunk): row view (x pass, l = t), column view (y pass, k = t)
+  const int offx = 32 * NSP * t + lane;  // + 32*(k + NSP*NSP*m)
+  const int offy = 32 * t + lane;        // + 32*NSP*(l + NSP*m)
+  double *const xdx = S.xd + offx;
+  const double *const xdy = S.xd + offy;
+  double *const xrpx = S.xrp + offx;
+  const double *const xrpy = S.xrp + offy;
+
+  // ---- prologue: common flux on the bottom face of row ja from tiles 0 (row ja-1) and 1
+  double hb[4];
+  {
+    mbar_wait(&S.bar[0], 0);
+    mbar_wait(&S.bar[1], 0);
+    double uT[4], uB[4];
+    col_trace<NSP>(S.tile[0] + offy, ops.lr, uT);
+    col_trace<NSP>(S.tile[1] + offy, ops.ll, uB);
+    frb::Flux4 h = frb::hll4_y_fast(uT[0], uT[1], uT[2], uT[3], uB[0], uB[1], uB[2], uB[3], gamma, gm1);
+    hb[0] = h.f0; hb[1] = h.f1; hb[2] = h.f2; hb[3] = h.f3;
+  }
+  {
+    // tile 0 is dead after the prologue: refill its buffer with tile NBUF
+    __syncthreads();
+    if (threadIdx.x == 0 && ntiles > NBUF) {
+      mbar_expect_tx(&S.bar[0], kTileBytes);
+      bulk_load(S.tile[0], P.u + (size_t)(ja - 1 + NBUF) * g.row + strip_off, kTileBytes, &S.bar[0]);
+    }
+  }
+
+  for (int q = 1; q <= ntiles - 2; ++q) {  // tile q = row j
+    const int j = ja - 1 + q;
+    const int buf = q % NBUF, nbuf = (q + 1) % NBUF;
+    const double *const Ux = S.tile[0] + buf * kTile + offx;
+    const double *const Uy = S.tile[0] + buf * kTile + offy;
+    // tile q was already waited on as the "next" tile of step q-1 (or in the prologue)
+
+    // -------------------------------------------------------------- x pass: row l = t
+    {
+      double w[NSP][4], f[NSP][4];
+#pragma unroll
+      for (int m = 0; m < 4; ++m)
+#pragma unroll
+        for (int k = 0; k < NSP; ++k) w[k][m] = Ux[32 * (k + NSP * NSP * m)];
+#pragma unroll
+      for (int k = 0; k < NSP; ++k) {
+        double rr = frb::rcp_fast(w[k][0]);
+        double vx = w[k][1] * rr, vy = w[k][2] * rr;
+        double p = gm1 * fma(-0.5, fma(w[k][1], vx, w[k][2] * vy), w[k][3]);
+        f[k][0] = w[k][1];
+        f[k][1] = fma(w[k][1], vx, p);
+        f[k][2] = w[k][1] * vy;
+        f[k][3] = (w[k][3] + p) * vx;
+        xrpx[32 * k] = rr;
+        xrpx[32 * (NSP * NSP + k)] = p;
+      }
+      double uL[4], uR[4];
+#pragma unroll
+      for (int m = 0; m < 4; ++m) {
+        double a = w[0][m] * ops.ll[0], b = w[0][m] * ops.lr[0];
+#pragma unroll
+        for (int q2 = 1; q2 < NSP; ++q2) {
+          a = fma(w[q2][m], ops.ll[q2], a);
+          b = fma(w[q2][m], ops.lr[q2], b);
+        }
+        uL[m] = a; uR[m] = b;
+      }
+      // left face: HLL(u_face[i-1,j,2,l,:], u_face[i,j,4,l,:])  (euler2d_wave.jl:69-74)
+      double n0 = __shfl_up_sync(0xffffffffu, uR[0], 1), n1 = __shfl_up_sync(0xffffffffu, uR[1], 1);
+      double n2 = __shfl_up_sync(0xffffffffu, uR[2], 1), n3 = __shfl_up_sync(0xffffffffu, uR[3], 1);
+      frb::Flux4 hl = frb::hll4_fast(n0, n1, n2, n3, uL[0], uL[1], uL[2], uL[3], gamma, gm1);
+      const double hL[4] = {hl.f0, hl.f1, hl.f2, hl.f3};
+      const double hR[4] = {__shfl_down_sync(0xffffffffu, hl.f0, 1), __shfl_down_sync(0xffffffffu, hl.f1, 1),
+                            __shfl_down_sync(0xffffffffu, hl.f2, 1), __shfl_down_sync(0xffffffffu, hl.f3, 1)};
+      // cb*u + (-cdt/Jx) * (d/dr + correction), flux traces folded into dmx (see MarchOps)
+#pragma unroll
+      for (int m = 0; m < 4; ++m)
+#pragma unroll
+        for (int k = 0; k < NSP; ++k) {
+          double d = P.cb * w[k][m];
+#pragma unroll
+          for (int q2 = 0; q2 < NSP; ++q2) d = fma(f[q2][m], ops.dmx[k * 4 + q2], d);
+          d = fma(hL[m], ops.glx[k], d);
+          d = fma(hR[m], ops.grx[k], d);
+          xdx[32 * (k + NSP * NSP * m)] = d;
+        }
+    }
+    __syncthreads();  // (A) xd / xrp of this row visible
+
+    // -------------------------------------------------------------- y pass: column k = t
+    {
+      double g4[NSP][4];  // G at the column's points, [l][m]
+      double uT[4];
+      {
+        double w[NSP][4];
+#pragma unroll
+        for (int m = 0; m < 4; ++m)
+#pragma unroll
+          for (int l = 0; l < NSP; ++l) w[l][m] = Uy[32 * NSP * (l + NSP * m)];
+#pragma unroll
+        for (int l = 0; l < NSP; ++l) {
+          double rr = xrpy[32 * NSP * l];
+          double p = xrpy[32 * NSP * (NSP + l)];
+          double vy = w[l][2] * rr;
+          g4[l][0] = w[l][2];
+          g4[l][1] = w[l][1] * vy;
+          g4[l][2] = fma(w[l][2], vy, p);
+          g4[l][3] = (w[l][3] + p) * vy;
+        }
+#pragma unroll
+        for (int m = 0; m < 4; ++m) {
+          double a = w[0][m] * ops.lr[0];
+#pragma unroll
+          for (int q2 = 1; q2 < NSP; ++q2) a = fma(w[q2][m], ops.lr[q2], a);
+          uT[m] = a;
+        }
+      }
+      // top face of row j: HLL between this row's top trace and row j+1's bottom trace
+      mbar_wait(&S.bar[nbuf], ((q + 1) / NBUF) & 1);
+      double ht[4];
+      {
+        double uB[4];
+        col_trace<NSP>(S.tile[0] + nbuf * kTile + offy, ops.ll, uB);
+        frb::Flux4 h = frb::hll4_y_fast(uT[0], uT[1], uT[2], uT[3], uB[0], uB[1], uB[2], uB[3], gamma, gm1);
+        ht[0] = h.f0; ht[1] = h.f1; ht[2] = h.f2; ht[3] = h.f3;
+      }
+      if (USEA) mbar_wait(bar_un, (q - 1) & 1);  // u_n row j (requested one row step ago)
+      // four independent FMA chains per variable, stored as soon as they retire; the chunk offset
+      // of a value equals its tile offset
+      double *const po = P.out + (size_t)j * g.row + strip_off + offy;
+#pragma unroll
+      for (int m = 0; m < 4; ++m) {
+        double v[NSP];
+#pragma unroll
+        for (int l = 0; l < NSP; ++l) {
+          double d = xdy[32 * NSP * (l + NSP * m)];
+#pragma unroll
+          for (int q2 = 0; q2 < NSP; ++q2) d = fma(g4[q2][m], (SAMEJ ? ops.dmx : ops.dmy)[l * 4 + q2], d);
+          d = fma(hb[m], (SAMEJ ? ops.glx : ops.gly)[l], d);
+          d = fma(ht[m], (SAMEJ ? ops.grx : ops.gry)[l], d);
+          if (USEA) d = fma(P.ca, S.un[offy + 32 * NSP * (l + NSP * m)], d);
+          v[l] = d;
+        }
+#pragma unroll
+        for (int l = 0; l < NSP; ++l) {
+          st_cs_if(po + 32 * NSP * (l + NSP * m), v[l], own);
+          st_cs_if(po + 32 * NSP * (l + NSP * m) + dup_off, v[l], dup);
+        }
+        hb[m] = ht[m];
+      }
+    }
+    __syncthreads();  // (B) every read of tile[buf], un, xd, xrp is done
+
+    if (threadIdx.x == 0) {
+      if (q + NBUF < ntiles) {
+        mbar_expect_tx(&S.bar[buf], kTileBytes);
+        bulk_load(S.tile[buf], P.u + (size_t)(ja - 1 + q + NBUF) * g.row + strip_off, kTileBytes, &S.bar[buf]);
+      }
+      if (USEA && j + 1 <= jb) {
+        mbar_expect_tx(bar_un, kTileBytes);
+        bulk_load(S.un, P.ua + (size_t)(j + 1) * g.row + strip_off, kTileBytes, bar_un);
+      }
+    }
+  }
+
+  // slab-parallel path: the first / last owned row also goes straight into the halo row of the
+  // rank below / above (peer memory over NVLink).  Each thread forwards the values it stored
+  // itself (program order, L2-hot), once per segment that owns row 1 / row ny.
+  if (owner && ((ja == 1 && P.peer_lo) || (jb == g.ny && P.peer_hi))) {
+    const size_t col = strip_off + offy;
+    if (ja == 1 && P.peer_lo) {
+      const double *src = P.out + g.row + col;
+      double *dst = P.peer_lo + (size_t)(P.nyl_lo + 1) * g.row + col;
+      for (int c = 0; c < 4 * NSP; ++c) {
+        const double v = src[32 * NSP * c];
+        dst[32 * NSP * c] = v;
+        if (dup) dst[32 * NSP * c + dup_off] = v;
+      }
+    }
+    if (jb == g.ny && P.peer_hi) {
+      const double *src = P.out + (size_t)g.ny * g.row + col;
+      double *dst = P.peer_hi + col;
+      for (int c = 0; c < 4 * NSP; ++c) {
+        const double v = src[32 * NSP * c];
+        dst[32 * NSP * c] = v;
+        if (dup) dst[32 * NSP * c + dup_off] = v;
+      }
+    }
+  }
+}
+
+int env_int_rc(const char *name, int dflt) {
+  const char *s = getenv(name);
+  return s && *s ? atoi(s) : dflt;
+}
+
+int rc_rows_per_seg(frb_prob_t p, const RcGeom &g, int ctas_per_sm) {
+  // segments of about 32 rows (each re-reads two halo rows); small meshes: enough CTAs for
+  // every SM slot if the row count allows it.  FRB_MARCH_ROWS overrides.
+  int forced = env_int_rc("FRB_MARCH_ROWS", 0);
+  if (forced > 0) return forced < g.ny ? forced : g.ny;
+  const int slots = p->ctx->sm_count * ctas_per_sm;
+  int nseg = (g.ny + 31) / 32;
+  while ((long)g.ns * nseg < slots && (g.ny + nseg) / (nseg + 1) >= 4) ++nseg;
+  return (g.ny + nseg - 1) / nseg;
+}
+
+template <int NSP, bool USEA, bool SAMEJ, int MINB>
+int launch_rc(frb_prob_t p, RcParams rp, const MarchOps &mo) {
+  constexpr int NBUF = USEA ? 2 : 3;
+  rp.rows_per_seg = rc_rows_per_seg(p, rp.g, MINB);
+  const int segs = (rp.g.ny + rp.rows_per_seg - 1) / rp.rows_per_seg;
+  const size_t smem = sizeof(SmemRc<NSP, NBUF, USEA>) + 128;
+  static bool attr_done = false;
+  if (!attr_done) {
+    FRB_CUDA(cudaFuncSetAttribute(euler2d_rc_kernel<NSP, USEA, SAMEJ, MINB>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    FRB_CUDA(cudaFuncSetAttribute(euler2d_rc_kernel<NSP, USEA, SAMEJ, MINB>,
+                                  cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    attr_done = true;
+  }
+  dim3 grd(rp.g.ns, segs), blk(NSP * 32);
+  euler2d_rc_kernel<NSP, USEA, SAMEJ, MINB><<<grd, blk, smem, p->ctx->stream>>>(rp, mo);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return frb_cuda_fail(e, "euler2d_rc_kernel", __FILE__, __LINE__);
+  return 1;
+}
+
+template <int NSP, int MINB>
+int dispatch_rc(frb_prob_t p, const RcParams &rp, const MarchOps &mo, bool usea, bool samej) {
+  if (usea) return samej ? launch_rc<NSP, true, true, MINB>(p, rp, mo) : launch_rc<NSP, true, false, MINB>(p, rp, mo);
+  return samej ? launch_rc<NSP, false, true, MINB>(p, rp, mo) : launch_rc<NSP, false, false, MINB>(p, rp, mo);
+}
+
+}  // namespace
+
+bool frb_euler2d_rc_supported(frb_prob_t p) {
+  return p->kind == K_EULER2D && (p->nsp == 4 || p->nsp == 3);
+}
+
+// u, ua, out are RC buffers (frb_rc.cuh); stage semantics as in frb_launch_euler2d_march
+int frb_launch_euler2d_rc(frb_prob_t p, const double *u, const double *ua, double *out, FrbStage st,
+                          double *peer_lo, double *peer_hi, int nyl_lo) {
+  if (!frb_euler2d_rc_supported(p)) {
+    frb_set_error("row-chunk kernel needs euler2d with deg 2 or 3");
+    return FRB_ERR_ARG;
+  }
+  RcParams rp;
+  rp.u = u;
+  rp.ua = ua;
+  rp.out = out;
+  rp.g = rc_geom(p->nx, p->ny, p->nsp);
+  rp.rows_per_seg = 0;
+  rp.gamma = p->gamma;
+  rp.peer_lo = peer_lo;
+  rp.peer_hi = peer_hi;
+  rp.nyl_lo = nyl_lo;
+  double cxs, cys;  // -cdt/Jx, -cdt/Jy  (L = -(dF/dr / Jx + dG/ds / Jy))
+  bool usea;
+  if (st.rhs_only) {
+    rp.ca = 0.0; rp.cb = 0.0; usea = false;
+    cxs = -1.0 / p->Jx; cys = -1.0 / p->Jy;
+  } else {
+    const double cdt = st.nested ? st.cb * st.cdt : st.cdt;
+    rp.ca = st.ca; rp.cb = st.cb; usea = st.use_a != 0;
+    cxs = -cdt / p->Jx; cys = -cdt / p->Jy;
+  }
+  MarchOps mo;
+  const int n = p->nsp;
+  for (int k = 0; k < 4; ++k) {
+    const bool in = k < n;
+    mo.ll[k] = in ? p->ops.ll[k] : 0.0;
+    mo.lr[k] = in ? p->ops.lr[k] : 0.0;
+    mo.glx[k] = in ? cxs * p->ops.dgl[k] : 0.0;
+    mo.grx[k] = in ? cxs * p->ops.dgr[k] : 0.0;
+    mo.gly[k] = in ? cys * p->ops.dgl[k] : 0.0;
+    mo.gry[k] = in ? cys * p->ops.dgr[k] : 0.0;
+    for (int q = 0; q < 4; ++q) {
+      const double d = (in && q < n) ? p->ops.dmod[k * FRB_NSPMAX + q] : 0.0;
+      mo.dmx[k * 4 + q] = cxs * d;
+      mo.dmy[k * 4 + q] = cys * d;
+    }
+  }
+  const bool samej = cxs == cys;
+  if (p->nsp == 4) return dispatch_rc<4, 3>(p, rp, mo, usea, samej);
+  return dispatch_rc<3, 4>(p, rp, mo, usea, samej);
+}

@@ -12,17 +12,20 @@
 #include <cstring>
 
 #include "frb_internal.cuh"
+#include "frb_rc.cuh"
 
 struct FrbHalo {
   int rank = 0, nranks = 1;
   int nyl_lo = 0, nyl_hi = 0;          // owned rows of the neighbours
   double *peer_lo[3] = {nullptr, nullptr, nullptr};  // neighbour below: its u, s1, s2
   double *peer_hi[3] = {nullptr, nullptr, nullptr};
+  double *rc_lo[3] = {nullptr, nullptr, nullptr};    // the same three roles in the row-chunk layout
+  double *rc_hi[3] = {nullptr, nullptr, nullptr};
   unsigned long long *flags = nullptr;     // local mailbox: [0] from lo, [1] from hi, [2] error
   unsigned long long *flags_lo = nullptr;  // neighbours' mailboxes
   unsigned long long *flags_hi = nullptr;
   unsigned long long epoch = 0;
-  void *opened[8] = {nullptr};
+  void *opened[10] = {nullptr};
   int nopened = 0;
 };
 
@@ -85,7 +88,7 @@ int check_launch(const char *what) {
 
 }  // namespace
 
-// export layout: 4 IPC handles (u, s1, s2, flags) + int32 ny_local
+// export layout: 5 IPC handles (u, s1, s2, flags, row-chunk buffers) + int32 ny_local + int32 has_rc
 extern "C" int32_t frb_halo_export(frb_prob_t p, unsigned char *out) {
   if (!p || !out) { frb_set_error("frb_halo_export: NULL argument"); return FRB_ERR_ARG; }
   if (p->kind != K_EULER2D) { frb_set_error("frb_halo_export: euler2d problems only"); return FRB_ERR_STATE; }
@@ -102,13 +105,18 @@ extern "C" int32_t frb_halo_export(frb_prob_t p, unsigned char *out) {
     FRB_CUDA(cudaIpcGetMemHandle(&h, bufs[b]));
     memcpy(out + b * FRB_IPC_HANDLE_BYTES, &h, FRB_IPC_HANDLE_BYTES);
   }
-  int32_t ny = p->ny;
-  memcpy(out + 4 * FRB_IPC_HANDLE_BYTES, &ny, sizeof ny);
+  int32_t tail[2] = {p->ny, p->rc_base ? 1 : 0};
+  memset(out + 4 * FRB_IPC_HANDLE_BYTES, 0, FRB_IPC_HANDLE_BYTES);
+  if (p->rc_base) {
+    FRB_CUDA(cudaIpcGetMemHandle(&h, p->rc_base));
+    memcpy(out + 4 * FRB_IPC_HANDLE_BYTES, &h, FRB_IPC_HANDLE_BYTES);
+  }
+  memcpy(out + 5 * FRB_IPC_HANDLE_BYTES, tail, sizeof tail);
   return FRB_OK;
 }
 
-static int open_peer(frb_prob_t p, const unsigned char *blob, double **bufs3, unsigned long long **flags,
-                     int *nyl) {
+static int open_peer(frb_prob_t p, const unsigned char *blob, double **bufs3, double **rc3,
+                     unsigned long long **flags, int *nyl) {
   FrbHalo *H = p->halo;
   for (int b = 0; b < 4; ++b) {
     cudaIpcMemHandle_t h;
@@ -119,9 +127,21 @@ static int open_peer(frb_prob_t p, const unsigned char *blob, double **bufs3, un
     if (b < 3) bufs3[b] = static_cast<double *>(ptr);
     else *flags = static_cast<unsigned long long *>(ptr);
   }
-  int32_t ny;
-  memcpy(&ny, blob + 4 * FRB_IPC_HANDLE_BYTES, sizeof ny);
-  *nyl = ny;
+  int32_t tail[2];
+  memcpy(tail, blob + 5 * FRB_IPC_HANDLE_BYTES, sizeof tail);
+  *nyl = tail[0];
+  if (tail[1] && p->rc_base) {  // the neighbour's ru | rs1 | rs2, sized for ITS row count
+    cudaIpcMemHandle_t h;
+    memcpy(&h, blob + 4 * FRB_IPC_HANDLE_BYTES, FRB_IPC_HANDLE_BYTES);
+    void *ptr = nullptr;
+    FRB_CUDA(cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    H->opened[H->nopened++] = ptr;
+    const size_t len = rc_geom(p->nx, tail[0], p->nsp).len;
+    for (int b = 0; b < 3; ++b) rc3[b] = static_cast<double *>(ptr) + b * len;
+  } else if (p->rc_base) {
+    frb_set_error("frb_halo_connect: neighbour has no row-chunk buffers (mixed configurations)");
+    return FRB_ERR_PEER;
+  }
   return FRB_OK;
 }
 
@@ -136,13 +156,13 @@ extern "C" int32_t frb_halo_connect(frb_prob_t p, int32_t rank, int32_t nranks,
   FrbHalo *H = p->halo;
   H->rank = rank;
   H->nranks = nranks;
-  if (int rc = open_peer(p, blob_lo, H->peer_lo, &H->flags_lo, &H->nyl_lo)) return rc;
+  if (int rc = open_peer(p, blob_lo, H->peer_lo, H->rc_lo, &H->flags_lo, &H->nyl_lo)) return rc;
   if (nranks == 2) {  // both neighbours are the same process: map once
-    for (int b = 0; b < 3; ++b) H->peer_hi[b] = H->peer_lo[b];
+    for (int b = 0; b < 3; ++b) { H->peer_hi[b] = H->peer_lo[b]; H->rc_hi[b] = H->rc_lo[b]; }
     H->flags_hi = H->flags_lo;
     H->nyl_hi = H->nyl_lo;
   } else {
-    if (int rc = open_peer(p, blob_hi, H->peer_hi, &H->flags_hi, &H->nyl_hi)) return rc;
+    if (int rc = open_peer(p, blob_hi, H->peer_hi, H->rc_hi, &H->flags_hi, &H->nyl_hi)) return rc;
   }
   return frb_halo_sync(p);
 }
@@ -179,14 +199,23 @@ int frb_halo_rank(frb_prob_t p, int *nranks) {
 bool frb_halo_active(frb_prob_t p) { return p->halo && p->halo->nranks > 1 && p->halo->flags_lo; }
 
 // which local buffer is `ptr`?  (roles move with the pointer swaps of the Euler scheme)
+static bool is_rc(frb_prob_t p, const double *ptr) {
+  return p->rc_base && (ptr == p->ru || ptr == p->rs1 || ptr == p->rs2);
+}
 static int role_of(frb_prob_t p, const double *ptr) {
+  if (is_rc(p, ptr)) return ptr == p->ru ? 0 : ptr == p->rs1 ? 1 : 2;
   return ptr == p->u ? 0 : ptr == p->s1 ? 1 : ptr == p->s2 ? 2 : -1;
 }
 
-void frb_halo_swap_roles(frb_prob_t p, int a, int b) {
+void frb_halo_swap_roles(frb_prob_t p, int a, int b, bool rc) {
   if (!p->halo) return;
-  std::swap(p->halo->peer_lo[a], p->halo->peer_lo[b]);
-  std::swap(p->halo->peer_hi[a], p->halo->peer_hi[b]);
+  if (rc) {
+    std::swap(p->halo->rc_lo[a], p->halo->rc_lo[b]);
+    std::swap(p->halo->rc_hi[a], p->halo->rc_hi[b]);
+  } else {
+    std::swap(p->halo->peer_lo[a], p->halo->peer_lo[b]);
+    std::swap(p->halo->peer_hi[a], p->halo->peer_hi[b]);
+  }
 }
 
 // peer destinations of the interior slab boundaries for a stage writing `out`
@@ -198,8 +227,9 @@ void frb_halo_stage_targets(frb_prob_t p, const double *out, double **dst_lo, do
   FrbHalo *H = p->halo;
   int r = role_of(p, out);
   if (r < 0) return;
-  if (H->rank != 0) { *dst_lo = H->peer_lo[r]; *nyl_lo = H->nyl_lo; }
-  if (H->rank != H->nranks - 1) { *dst_hi = H->peer_hi[r]; *nyl_hi = H->nyl_hi; }
+  const bool rc = is_rc(p, out);
+  if (H->rank != 0) { *dst_lo = rc ? H->rc_lo[r] : H->peer_lo[r]; *nyl_lo = H->nyl_lo; }
+  if (H->rank != H->nranks - 1) { *dst_hi = rc ? H->rc_hi[r] : H->peer_hi[r]; *nyl_hi = H->nyl_hi; }
 }
 
 int frb_halo_role(frb_prob_t p, const double *ptr) { return role_of(p, ptr); }
@@ -212,15 +242,18 @@ int frb_halo_push(frb_prob_t p, const double *src, int dst_role, bool seam, int 
   FrbHalo *H = p->halo;
   if (dst_role < 0 || dst_role > 2) { frb_set_error("halo push: unknown buffer"); return FRB_ERR_STATE; }
   const bool first = H->rank == 0, last = H->rank == H->nranks - 1;
+  const bool rc = is_rc(p, src);
+  double **plo = rc ? H->rc_lo : H->peer_lo, **phi = rc ? H->rc_hi : H->peer_hi;
   double *dl = nullptr, *dh = nullptr;
   if (!seam) {
-    if (!first) dl = H->peer_lo[dst_role];
-    if (!last) dh = H->peer_hi[dst_role];
+    if (!first) dl = plo[dst_role];
+    if (!last) dh = phi[dst_role];
   } else {
-    if (first) dl = H->peer_lo[dst_role];
-    if (last) dh = H->peer_hi[dst_role];
+    if (first) dl = plo[dst_role];
+    if (last) dh = phi[dst_role];
   }
   if (!dl && !dh) return 0;
+  if (rc) return frb_rc_row_push(p, src, dl, dh, H->nyl_lo, seam ? flip_var : -1);
   const int npp = p->nsp * p->nsp, nplanes = 4 * npp;
   dim3 blk(128), grd((p->nx + 2 + 127) / 128, nplanes);
   halo_push_kernel<<<grd, blk, 0, p->ctx->stream>>>(src, dl, dh, p->nx, p->ny, H->nyl_lo, H->nyl_hi,

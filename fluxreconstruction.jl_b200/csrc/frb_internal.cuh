@@ -72,6 +72,12 @@ struct frb_prob_s {
   double *u = nullptr;              // resident state  (u_n)
   double *s1 = nullptr, *s2 = nullptr;  // stage buffers
   double *du = nullptr;             // f! output (lazy)
+  // row-chunk mirror of the 2-D Euler state (frb_rc.cuh): the layout frb_step streams in.  u is
+  // the reference image the ABI exposes; exactly one of the two (or both) is current.
+  double *rc_base = nullptr;        // one allocation: ru | rs1 | rs2
+  double *ru = nullptr, *rs1 = nullptr, *rs2 = nullptr;
+  size_t rc_len = 0;                // doubles per RC buffer
+  bool ref_valid = true, rc_valid = false;
   double *J = nullptr;              // 1-D per-cell Jacobian / bgk dx
   double *velo = nullptr, *weights = nullptr, *prim = nullptr;  // bgk
   double *lim_w = nullptr;          // limiter weights (device)
@@ -105,13 +111,23 @@ int frb_launch_bgk1d(frb_prob_t p, const double *u, const double *ua, double *ou
 int frb_launch_euler2d_generic(frb_prob_t p, const double *u, const double *ua, double *out, FrbStage st);
 int frb_launch_euler2d_march(frb_prob_t p, const double *u, const double *ua, double *out, FrbStage st);
 bool frb_euler2d_march_supported(frb_prob_t p);
+// row-chunk path (frb_euler2d_rc.cu, frb_rc.cu); every pointer is an RC buffer unless named ref
+bool frb_euler2d_rc_supported(frb_prob_t p);
+int frb_launch_euler2d_rc(frb_prob_t p, const double *u, const double *ua, double *out, FrbStage st,
+                          double *peer_lo, double *peer_hi, int nyl_lo);
+int frb_rc_from_ref(frb_prob_t p, const double *ref, double *rc);
+int frb_rc_to_ref(frb_prob_t p, const double *rc, double *ref);
+int frb_rc_ghost_fill(frb_prob_t p, double *u, int mode);
+int frb_rc_ghost_x(frb_prob_t p, double *u, int mode);
+int frb_rc_ring_copy(frb_prob_t p, const double *src, double *dst, bool row0, bool rowN);
+int frb_rc_row_push(frb_prob_t p, const double *src, double *dst_lo, double *dst_hi, int nyl_lo, int flip_var);
 int frb_launch_ns2d(frb_prob_t p, const double *u, const double *ua, double *out, FrbStage st);
 int frb_launch_ghost_fill2d(frb_prob_t p, double *u, int mode);
 int frb_launch_ring_copy2d(frb_prob_t p, const double *src, double *dst, bool row0 = true, bool rowN = true);
 int frb_launch_ghost_x2d(frb_prob_t p, double *u, int mode);
 // frb_halo.cu
 bool frb_halo_active(frb_prob_t p);
-void frb_halo_swap_roles(frb_prob_t p, int a, int b);
+void frb_halo_swap_roles(frb_prob_t p, int a, int b, bool rc = false);
 void frb_halo_stage_targets(frb_prob_t p, const double *out, double **dst_lo, double **dst_hi, int *nyl_lo,
                             int *nyl_hi);
 int frb_halo_push(frb_prob_t p, const double *src, int dst_role, bool seam, int flip_var);

@@ -32,7 +32,7 @@ from ._lib import Context, check, fortran_ptr, lib, make_operators
 
 BC = {"dirichlet": 0, "period": 1}
 GHOST = {None: -1, "none": -1, "wave_x": 0, "wave_y": 1, "copy": 2}
-KERNEL = {"auto": 0, "generic": 1, "march": 2}
+KERNEL = {"auto": 0, "generic": 1, "march": 2, "rc": 3}
 
 
 class Euler:
@@ -301,7 +301,7 @@ def solve(prob, alg, dt, adaptive=False, **_):
     return itg
 
 
-HALO_BLOB_BYTES = 4 * 64 + 8
+HALO_BLOB_BYTES = 5 * 64 + 8
 
 
 class DistributedEuler2D(Euler2DProblem):

@@ -53,7 +53,7 @@ enum { FRB_GHOST_NONE = -1, FRB_GHOST_WAVE_X = 0, FRB_GHOST_WAVE_Y = 1, FRB_GHOS
 enum { FRB_ADV_PACKAGED = 0, FRB_ADV_LOWLEVEL = 1 };
 /* 2-D Euler kernel selection: AUTO picks the fused row-marching TMA kernel when
  * deg == 3, otherwise the generic per-element kernel */
-enum { FRB_KERNEL_AUTO = 0, FRB_KERNEL_GENERIC = 1, FRB_KERNEL_MARCH = 2 };
+enum { FRB_KERNEL_AUTO = 0, FRB_KERNEL_GENERIC = 1, FRB_KERNEL_MARCH = 2, FRB_KERNEL_RC = 3 };
 
 /* the constant operator arrays of one FR space: ps.ll, ps.lr, ps.dl, ps.dhl, ps.dhr
  * (struct.jl:49-51,63-64,182,193), plus ps.dll/ps.dlr (struct.jl:55-61, may be NULL
@@ -167,8 +167,8 @@ int32_t frb_host_free(void *ptr);
  * CUDA IPC handles the host exchanges out of band), then a flag is raised.
  * The reference has no distributed path: this is new surface. */
 #define FRB_IPC_HANDLE_BYTES 64
-/* blob = 4 IPC handles (u, s1, s2, mailbox) + int32 ny_local */
-#define FRB_HALO_BLOB_BYTES (4 * FRB_IPC_HANDLE_BYTES + 8)
+/* blob = 5 IPC handles (u, s1, s2, mailbox, row-chunk buffers) + int32 ny_local + int32 has_rc */
+#define FRB_HALO_BLOB_BYTES (5 * FRB_IPC_HANDLE_BYTES + 8)
 /* export this rank's blob; the host exchanges blobs out of band (torch.distributed, MPI, ...) */
 int32_t frb_halo_export(frb_prob_t prob, unsigned char *blob_out);
 /* map the blobs of the rank below (rank-1 mod nranks) and above (rank+1 mod nranks) and send

@@ -6,7 +6,7 @@ import numpy as np
 import frb200 as FR
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 2048
-kernels = sys.argv[2].split(",") if len(sys.argv) > 2 else ["march", "generic"]
+kernels = sys.argv[2].split(",") if len(sys.argv) > 2 else ["rc", "march", "generic"]
 g = 5.0 / 3.0
 ps = FR.FRPSpace2D(0.0, 1.0, n, 0.0, 1.0, n, 3, 1, 1)
 t0 = time.time()

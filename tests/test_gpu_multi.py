@@ -18,7 +18,8 @@ def _ngpu():
 
 
 @pytest.mark.parametrize("scheme,kernel,ghost", [("ssprk3", "auto", "wave_x"), ("midpoint", "generic", "wave_y"),
-                                                 ("euler", "auto", "wave_x")])
+                                                 ("euler", "auto", "wave_x"), ("ssprk3", "march", "wave_x"),
+                                                 ("midpoint", "rc", "wave_y")])
 def test_two_rank_slabs_match_oracle(scheme, kernel, ghost):
     if _ngpu() < 2:
         pytest.skip("needs 2 GPUs")
