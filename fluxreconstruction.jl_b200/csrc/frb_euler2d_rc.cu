@@ -295,13 +295,20 @@ int env_int_rc(const char *name, int dflt) {
   return s && *s ? atoi(s) : dflt;
 }
 
-int rc_rows_per_seg(frb_prob_t p, const RcGeom &g, int ctas_per_sm) {
-  // segments of about 32 rows (each re-reads two halo rows); small meshes: enough CTAs for
-  // every SM slot if the row count allows it.  FRB_MARCH_ROWS overrides.
+int rc_rows_per_seg(frb_prob_t p, const RcGeom &g, int ctas_per_sm, bool usea) {
+  // Short segments on purpose.  Lanes 1 and 30 store their column's duplicate into the
+  // neighbouring chunk, i.e. into a 32-B sector whose other lanes the neighbouring CTA writes;
+  // L2 merges the two partial writes only while the CTAs of adjacent strips work on the same
+  // row at about the same time.  CTAs launched together do, and drift apart as they run: with
+  // 32..64-row segments the per-launch time grows 15-25 % (DRAM read-modify-write of orphaned
+  // partial sectors).  Measured at 2048^2, p3 on B200: 16-B stage best at 10..20 rows (0.88 ms),
+  // 24-B stage at 4..6 rows (1.08 ms); the extra halo-row reads (2 per segment) are L2 hits of
+  // the segment below that started in the same wave.  FRB_MARCH_ROWS overrides.
   int forced = env_int_rc("FRB_MARCH_ROWS", 0);
   if (forced > 0) return forced < g.ny ? forced : g.ny;
   const int slots = p->ctx->sm_count * ctas_per_sm;
-  int nseg = (g.ny + 31) / 32;
+  int nseg = (g.ny + (usea ? 5 : 11)) / (usea ? 6 : 12);
+  // small meshes: enough CTAs for every SM slot if the row count allows it
   while ((long)g.ns * nseg < slots && (g.ny + nseg) / (nseg + 1) >= 4) ++nseg;
   return (g.ny + nseg - 1) / nseg;
 }
@@ -309,7 +316,7 @@ int rc_rows_per_seg(frb_prob_t p, const RcGeom &g, int ctas_per_sm) {
 template <int NSP, bool USEA, bool SAMEJ, int MINB>
 int launch_rc(frb_prob_t p, RcParams rp, const MarchOps &mo) {
   constexpr int NBUF = USEA ? 2 : 3;
-  rp.rows_per_seg = rc_rows_per_seg(p, rp.g, MINB);
+  rp.rows_per_seg = rc_rows_per_seg(p, rp.g, MINB, USEA);
   const int segs = (rp.g.ny + rp.rows_per_seg - 1) / rp.rows_per_seg;
   const size_t smem = sizeof(SmemRc<NSP, NBUF, USEA>) + 128;
   static bool attr_done = false;
