@@ -60,7 +60,7 @@ struct Smem {
   static constexpr int kTile = kPlanes * 32;  // doubles
   alignas(128) double tile[NBUF][kTile];
   alignas(128) double xd[kTile];              // x-pass derivative + correction (no 1/Jx yet)
-  alignas(128) double xrp[2 * NSP * NSP * 32];  // 1/rho and p at the points
+  alignas(128) double xrp[2 * NSP * NSP * 32];  // v_y and p at the points
   alignas(8) uint64_t bar[NBUF];
 };
 
@@ -207,7 +207,7 @@ euler2d_march_kernel(const __grid_constant__ CUtensorMap tmap, MarchParams P, Ma
         f[k][1] = fma(w[k][1], vx, p);
         f[k][2] = w[k][1] * vy;
         f[k][3] = (w[k][3] + p) * vx;
-        xrpx[32 * k] = rr;
+        xrpx[32 * k] = vy;  // the y pass needs only v_y and p of the point
         xrpx[32 * (NSP * NSP + k)] = p;
       }
       double uL[4], uR[4];
@@ -264,9 +264,8 @@ euler2d_march_kernel(const __grid_constant__ CUtensorMap tmap, MarchParams P, Ma
           for (int l = 0; l < NSP; ++l) w[l][m] = Uy[32 * NSP * (l + NSP * m)];
 #pragma unroll
         for (int l = 0; l < NSP; ++l) {
-          double rr = xrpy[32 * NSP * l];
+          double vy = xrpy[32 * NSP * l];
           double p = xrpy[32 * NSP * (NSP + l)];
-          double vy = w[l][2] * rr;
           g[l][0] = w[l][2];
           g[l][1] = w[l][1] * vy;
           g[l][2] = fma(w[l][2], vy, p);

@@ -41,7 +41,7 @@ struct SmemRc {
   alignas(128) double tile[NBUF][kTile];
   alignas(128) double un[USEA ? kTile : 16];
   alignas(128) double xd[kTile];                 // x-pass output: cb*u (+) x derivative + correction
-  alignas(128) double xrp[2 * NSP * NSP * 32];   // 1/rho and p at the points
+  alignas(128) double xrp[2 * NSP * NSP * 32];   // v_y and p at the points
   alignas(8) uint64_t bar[NBUF + 1];
 };
 
@@ -56,7 +56,8 @@ __device__ __forceinline__ void col_trace(const double *__restrict__ Uy, const d
   }
 }
 
-template <int NSP, bool USEA, bool SAMEJ, int MINB>
+// CB1: the stage has cb == 1 (u' = u + dt L(u), first stage of every scheme): no multiply
+template <int NSP, bool USEA, bool SAMEJ, int MINB, bool CB1>
 __global__ void __launch_bounds__(NSP * 32, MINB) euler2d_rc_kernel(RcParams P, MarchOps ops) {
   constexpr int NBUF = USEA ? 2 : 3;
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -152,7 +153,7 @@ __global__ void __launch_bounds__(NSP * 32, MINB) euler2d_rc_kernel(RcParams P, 
         f[k][1] = fma(w[k][1], vx, p);
         f[k][2] = w[k][1] * vy;
         f[k][3] = (w[k][3] + p) * vx;
-        xrpx[32 * k] = rr;
+        xrpx[32 * k] = vy;  // the y pass needs only v_y and p of the point
         xrpx[32 * (NSP * NSP + k)] = p;
       }
       double uL[4], uR[4];
@@ -178,7 +179,7 @@ __global__ void __launch_bounds__(NSP * 32, MINB) euler2d_rc_kernel(RcParams P, 
       for (int m = 0; m < 4; ++m)
 #pragma unroll
         for (int k = 0; k < NSP; ++k) {
-          double d = P.cb * w[k][m];
+          double d = CB1 ? w[k][m] : P.cb * w[k][m];
 #pragma unroll
           for (int q2 = 0; q2 < NSP; ++q2) d = fma(f[q2][m], ops.dmx[k * 4 + q2], d);
           d = fma(hL[m], ops.glx[k], d);
@@ -200,9 +201,8 @@ __global__ void __launch_bounds__(NSP * 32, MINB) euler2d_rc_kernel(RcParams P, 
           for (int l = 0; l < NSP; ++l) w[l][m] = Uy[32 * NSP * (l + NSP * m)];
 #pragma unroll
         for (int l = 0; l < NSP; ++l) {
-          double rr = xrpy[32 * NSP * l];
+          double vy = xrpy[32 * NSP * l];
           double p = xrpy[32 * NSP * (NSP + l)];
-          double vy = w[l][2] * rr;
           g4[l][0] = w[l][2];
           g4[l][1] = w[l][1] * vy;
           g4[l][2] = fma(w[l][2], vy, p);
@@ -313,7 +313,7 @@ int rc_rows_per_seg(frb_prob_t p, const RcGeom &g, int ctas_per_sm, bool usea) {
   return (g.ny + nseg - 1) / nseg;
 }
 
-template <int NSP, bool USEA, bool SAMEJ, int MINB>
+template <int NSP, bool USEA, bool SAMEJ, int MINB, bool CB1>
 int launch_rc(frb_prob_t p, RcParams rp, const MarchOps &mo) {
   constexpr int NBUF = USEA ? 2 : 3;
   rp.rows_per_seg = rc_rows_per_seg(p, rp.g, MINB, USEA);
@@ -321,14 +321,14 @@ int launch_rc(frb_prob_t p, RcParams rp, const MarchOps &mo) {
   const size_t smem = sizeof(SmemRc<NSP, NBUF, USEA>) + 128;
   static bool attr_done = false;
   if (!attr_done) {
-    FRB_CUDA(cudaFuncSetAttribute(euler2d_rc_kernel<NSP, USEA, SAMEJ, MINB>,
+    FRB_CUDA(cudaFuncSetAttribute(euler2d_rc_kernel<NSP, USEA, SAMEJ, MINB, CB1>,
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    FRB_CUDA(cudaFuncSetAttribute(euler2d_rc_kernel<NSP, USEA, SAMEJ, MINB>,
+    FRB_CUDA(cudaFuncSetAttribute(euler2d_rc_kernel<NSP, USEA, SAMEJ, MINB, CB1>,
                                   cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     attr_done = true;
   }
   dim3 grd(rp.g.ns, segs), blk(NSP * 32);
-  euler2d_rc_kernel<NSP, USEA, SAMEJ, MINB><<<grd, blk, smem, p->ctx->stream>>>(rp, mo);
+  euler2d_rc_kernel<NSP, USEA, SAMEJ, MINB, CB1><<<grd, blk, smem, p->ctx->stream>>>(rp, mo);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return frb_cuda_fail(e, "euler2d_rc_kernel", __FILE__, __LINE__);
   return 1;
@@ -336,8 +336,11 @@ int launch_rc(frb_prob_t p, RcParams rp, const MarchOps &mo) {
 
 template <int NSP, int MINB>
 int dispatch_rc(frb_prob_t p, const RcParams &rp, const MarchOps &mo, bool usea, bool samej) {
-  if (usea) return samej ? launch_rc<NSP, true, true, MINB>(p, rp, mo) : launch_rc<NSP, true, false, MINB>(p, rp, mo);
-  return samej ? launch_rc<NSP, false, true, MINB>(p, rp, mo) : launch_rc<NSP, false, false, MINB>(p, rp, mo);
+  if (usea)
+    return samej ? launch_rc<NSP, true, true, MINB, false>(p, rp, mo) : launch_rc<NSP, true, false, MINB, false>(p, rp, mo);
+  if (rp.cb == 1.0)
+    return samej ? launch_rc<NSP, false, true, MINB, true>(p, rp, mo) : launch_rc<NSP, false, false, MINB, true>(p, rp, mo);
+  return samej ? launch_rc<NSP, false, true, MINB, false>(p, rp, mo) : launch_rc<NSP, false, false, MINB, false>(p, rp, mo);
 }
 
 }  // namespace

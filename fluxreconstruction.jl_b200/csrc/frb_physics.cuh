@@ -109,6 +109,19 @@ __device__ __forceinline__ double sqrt_fast(double x) {
   return fma(0.5 * r, y, s);
 }
 
+// sqrt by two coupled Goldschmidt steps on (g ~ sqrt x, h ~ 1/(2 sqrt x)) from the MUFU seed:
+// 7 FP64 instructions instead of 11, result within ~2 ulp (the seed's 2^-20 squares twice).
+__device__ __forceinline__ double sqrt_gs(double x) {
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  double g = x * y, h = 0.5 * y;
+  double r = fma(-g, h, 0.5);
+  g = fma(g, r, g);
+  h = fma(h, r, h);
+  r = fma(-g, h, 0.5);
+  return fma(g, r, g);
+}
+
 __device__ __forceinline__ Flux4 hll4_fast(double l0, double l1, double l2, double l3, double r0,
                                            double r1, double r2, double r3, double gamma,
                                            double gm1) {
@@ -116,7 +129,7 @@ __device__ __forceinline__ Flux4 hll4_fast(double l0, double l1, double l2, doub
   double ul = l1 * il, vl = l2 * il, ur = r1 * ir, vr = r2 * ir;
   double pl = gm1 * fma(-0.5, fma(l1, ul, l2 * vl), l3);
   double pr = gm1 * fma(-0.5, fma(r1, ur, r2 * vr), r3);
-  double al = sqrt_fast(gamma * pl * il), ar = sqrt_fast(gamma * pr * ir);
+  double al = sqrt_gs(gamma * pl * il), ar = sqrt_gs(gamma * pr * ir);
   double lmin = ul - al, lmax = ur + ar;
   double fl0 = l1, fl1 = fma(l1, ul, pl), fl2 = l1 * vl, fl3 = (l3 + pl) * ul;
   double fr0 = r1, fr1 = fma(r1, ur, pr), fr2 = r1 * vr, fr3 = (r3 + pr) * ur;
