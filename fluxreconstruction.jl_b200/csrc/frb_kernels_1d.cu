@@ -187,79 +187,6 @@ limiter1d_kernel(double *__restrict__ u, int ncell, double gamma, const double *
 // stage is rhs_only; nothing to do here (kept for symmetry with the 2-D ring copy).
 
 // ---------------------------------------------------------------------- BGK ----
-// moments_conserve + conserve_prim(w, 3.0): bgk_wave.jl:77-79.  prim[ncell, nsp, 3].
-__global__ void __launch_bounds__(128)
-bgk_moments_kernel(const double *__restrict__ u, double *__restrict__ prim, int ncell, int nu,
-                   int nsp, const double *__restrict__ velo, const double *__restrict__ wts) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  int k = blockIdx.y;
-  if (i >= ncell) return;
-  const double *p = u + i + (size_t)ncell * nu * k;
-  double w0 = 0.0, w1 = 0.0, w2 = 0.0;
-  for (int j = 0; j < nu; ++j) {
-    double f = p[(size_t)ncell * j];
-    double v = velo[j], wt = wts[j];
-    w0 += wt * f;
-    w1 += wt * v * f;
-    w2 += wt * (v * v) * f;
-  }
-  w2 *= 0.5;
-  double lam = 0.5 * w0 / (3.0 - 1.0) / (w2 - 0.5 * w1 * w1 / w0);
-  size_t o = i + (size_t)ncell * k;
-  prim[o] = w0;
-  prim[o + (size_t)ncell * nsp] = w1 / w0;
-  prim[o + 2 * (size_t)ncell * nsp] = lam;
-}
-
-template <int NSP>
-__global__ void __launch_bounds__(128)
-bgk1d_kernel(const double *__restrict__ u, const double *__restrict__ ua, double *__restrict__ out,
-             const double *__restrict__ prim, const double *__restrict__ dx,
-             const double *__restrict__ velo, int ncell, int nu, double tau, FrbOps ops,
-             FrbStage st) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  int j = blockIdx.y;
-  if (i >= ncell) return;
-  const double v = velo[j];
-  const double delta = v >= 0.0 ? 1.0 : 0.0;  // heaviside, bgk_wave.jl:26
-  const size_t vs = (size_t)ncell * nu;
-  int im = i == 0 ? ncell - 1 : i - 1;  // f2e / e2f periodic tables :42-67
-  int ip = i == ncell - 1 ? 0 : i + 1;
-  double uc[NSP], f[NSP], fn[NSP];
-  const double Jc = 0.5 * dx[i];
-  // only the upwind neighbour contributes: left cell for v >= 0, right cell otherwise
-  const int in = v >= 0.0 ? im : ip;
-  const double Jn = 0.5 * dx[in];
-#pragma unroll
-  for (int q = 0; q < NSP; ++q) {
-    uc[q] = u[i + (size_t)ncell * j + vs * q];
-    f[q] = v * uc[q] / Jc;  // :85-88
-    fn[q] = v * u[in + (size_t)ncell * j + vs * q] / Jn;
-  }
-  double fL = dotn<NSP>(f, ops.ll), fR = dotn<NSP>(f, ops.lr);  // interp_face! :99-101
-  double fi0, fi1;  // f_interaction at the left / right face of cell i  (:103-107)
-  if (v >= 0.0) {
-    double fRm = dotn<NSP>(fn, ops.lr);
-    fi0 = fL * (1.0 - delta) + fRm * delta;
-    fi1 = 0.0 * (1.0 - delta) + fR * delta;
-  } else {
-    double fLp = dotn<NSP>(fn, ops.ll);
-    fi0 = fL * (1.0 - delta) + 0.0 * delta;
-    fi1 = fLp * (1.0 - delta) + fR * delta;
-  }
-#pragma unroll
-  for (int p = 0; p < NSP; ++p) {
-    size_t po = i + (size_t)ncell * p;
-    double rho = prim[po], U = prim[po + (size_t)ncell * NSP], lam = prim[po + 2 * (size_t)ncell * NSP];
-    double c = v - U;
-    double M = rho * sqrt(lam / 3.14159265358979323846) * exp(-lam * (c * c));  // maxwellian
-    double rhs1 = dotn<NSP>(f, &ops.lpdm[p * FRB_NSPMAX]);  // poly_derivative! :114-116
-    double du = -(rhs1 + (fi0 - fL) * ops.dgl[p] + (fi1 - fR) * ops.dgr[p]) + (M - uc[p]) / tau;
-    size_t idx = i + (size_t)ncell * j + vs * p;
-    out[idx] = stage_out(st, ua, idx, uc[p], du);
-  }
-}
-
 }  // namespace
 
 #define FRB_NSP_SWITCH(nsp, CALL)                       \
@@ -306,15 +233,5 @@ int frb_launch_limiter1d(frb_prob_t p, double *u) {
   return 1;
 }
 
-int frb_launch_bgk1d(frb_prob_t p, const double *u, const double *ua, double *out, FrbStage st) {
-  dim3 blk(128), g1((p->ncell + 127) / 128, p->nsp), g2((p->ncell + 127) / 128, p->nu);
-  bgk_moments_kernel<<<g1, blk, 0, p->ctx->stream>>>(u, p->prim, p->ncell, p->nu, p->nsp, p->velo,
-                                                     p->weights);
-  if (int rc = check_launch("bgk_moments_kernel")) return rc;
-  FRB_NSP_SWITCH(p->nsp, (bgk1d_kernel<N><<<g2, blk, 0, p->ctx->stream>>>(
-                             u, ua, out, p->prim, p->J, p->velo, p->ncell, p->nu, p->tau, p->ops, st)));
-  if (int rc = check_launch("bgk1d_kernel")) return rc;
-  return 2;
-}
 
 int frb_launch_dirichlet_copy1d(frb_prob_t, const double *, double *) { return 0; }

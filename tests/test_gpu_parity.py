@@ -395,7 +395,13 @@ def test_cfg4_full_size_bgk(FR, oracle, coracle):
     du = np.zeros_like(f0, order="F")
     prob.f(du, f0, None, 0.0)
     ref = coracle.rhs_bgk1d(f0, ps.dx, velo, wts, ps.ll, ps.lr, ps.dl, ps.dhl, ps.dhr, 1e-2)
-    assert rel(du, ref) <= RTOL_RHS
+    # This initial condition is the local Maxwellian itself: (M - u)/tau and the transport terms
+    # v u / J = O(1e4) both cancel to a residual of O(1e-6).  One ulp in a moment moves M by 1e-16 and
+    # du by 1e-14, and the order of the 256-term moment sum is not specified by the reference
+    # (Julia `sum`), so the 1e-12 bound is relative to the summed terms, as in the cfg3 test.
+    term_scale = float(np.abs(velo).max() * np.abs(f0).max() / (0.5 * ps.dx[0]))
+    assert np.abs(du - ref).max() <= RTOL_RHS * term_scale
+    assert rel(du, ref) <= 1e-6
     fs = np.asfortranarray(np.roll(f0, 1000, axis=0))
     ds = np.zeros_like(f0, order="F")
     prob.f(ds, fs, None, 0.0)
@@ -405,7 +411,7 @@ def test_cfg4_full_size_bgk(FR, oracle, coracle):
     itg.set_u(f0)
     FR.step_(itg, 20)
     ref = coracle.integrate_bgk1d(f0, ps.dx, velo, wts, ps.ll, ps.lr, ps.dl, ps.dhl, ps.dhr, 1e-2, dt, 20, "midpoint")
-    assert rel(itg.u, ref) <= 1e-11
+    assert rel(itg.u, ref) <= 1e-12
     prob.close()
 
 
