@@ -327,10 +327,9 @@ static bool use_march(frb_prob_t p) {
   return frb_euler2d_march_supported(p);
 }
 
-// frb_step streams in the row-chunk layout when it can: 2-D Euler, deg 2..3, no limiter hook
-// (the limiter kernel works on the reference image)
+// frb_step streams in the row-chunk layout when it can: 2-D Euler, deg 2..3
 static bool use_rc(frb_prob_t p) {
-  if (p->kind != K_EULER2D || !p->rc_base || p->limiter_on) return false;
+  if (p->kind != K_EULER2D || !p->rc_base) return false;
   return p->kernel_kind == FRB_KERNEL_AUTO || p->kernel_kind == FRB_KERNEL_RC;
 }
 
@@ -510,8 +509,10 @@ extern "C" int32_t frb_set_step_hooks(frb_prob_t p, int32_t ghost_mode, const do
   return FRB_OK;
 }
 
-static int run_limiter(frb_prob_t p) {
-  int n = p->kind == K_EULER1D ? frb_launch_limiter1d(p, p->u) : frb_launch_limiter2d(p, p->u);
+static int run_limiter(frb_prob_t p, bool rc = false) {
+  int n = p->kind == K_EULER1D ? frb_launch_limiter1d(p, p->u)
+          : rc                 ? frb_rc_limiter2d(p, p->ru)
+                               : frb_launch_limiter2d(p, p->u);
   if (n > 0) p->launches += n;
   return n;
 }
@@ -598,7 +599,7 @@ static int one_step(frb_prob_t p, int scheme, double dt, bool rc) {
   const bool par = frb_halo_active(p);
   double *&U = rc ? p->ru : p->u, *&S1 = rc ? p->rs1 : p->s1, *&S2 = rc ? p->rs2 : p->s2;
   if (p->limiter_on) {
-    if ((n = run_limiter(p)) < 0) return n;
+    if ((n = run_limiter(p, rc)) < 0) return n;
   }
   if (p->ghost_mode != FRB_GHOST_NONE) {
     if (par) {

@@ -120,6 +120,7 @@ int frb_rc_to_ref(frb_prob_t p, const double *rc, double *ref);
 int frb_rc_ghost_fill(frb_prob_t p, double *u, int mode);
 int frb_rc_ghost_x(frb_prob_t p, double *u, int mode);
 int frb_rc_ring_copy(frb_prob_t p, const double *src, double *dst, bool row0, bool rowN);
+int frb_rc_limiter2d(frb_prob_t p, double *u);
 int frb_rc_row_push(frb_prob_t p, const double *src, double *dst_lo, double *dst_hi, int nyl_lo, int flip_var);
 int frb_launch_ns2d(frb_prob_t p, const double *u, const double *ua, double *out, FrbStage st);
 int frb_launch_ghost_fill2d(frb_prob_t p, double *u, int mode);

@@ -10,6 +10,7 @@
 // contiguous "plane" of NE = (nx+2)(ny+2) doubles, so a warp that maps lanes to consecutive
 // i reads 256 contiguous bytes per plane.
 #include "frb_internal.cuh"
+#include "frb_rc.cuh"
 #include "frb_physics.cuh"
 
 namespace {
@@ -188,15 +189,12 @@ __global__ void ring_copy_kernel(const double *__restrict__ src, double *__restr
 }
 
 // positive_limiter(u[nsp,nsp,4], gamma, weights, ll, lr): dissipation.jl:125-206, density branch
+// One element at offset e with plane stride NE (reference image: NE = (nx+2)(ny+2); row-chunk
+// layout: NE = 32); dup >= 0 is the offset of the element's copy in the neighbouring chunk.
 template <int NSP>
-__global__ void __launch_bounds__(128)
-limiter2d_kernel(double *__restrict__ u, int nx, int ny, double gamma,
-                 const double *__restrict__ wts, FrbOps ops, int *__restrict__ nbad) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x + 1;
-  const int j = blockIdx.y * blockDim.y + threadIdx.y + 1;
-  if (i > nx || j > ny) return;
-  const size_t NXG = nx + 2, NE = NXG * (size_t)(ny + 2);
-  const size_t e = i + NXG * j;
+__device__ __forceinline__ void limit_element(double *__restrict__ u, size_t e, size_t NE, long long dup,
+                                              double gamma, const double *__restrict__ wts,
+                                              const FrbOps &ops, int *__restrict__ nbad) {
   double rho[NSP][NSP];  // [l][k]
   double um[4];
 #pragma unroll
@@ -236,7 +234,36 @@ limiter2d_kernel(double *__restrict__ u, int nx, int ny, double gamma,
   for (int l = 0; l < NSP; ++l)
 #pragma unroll
     for (int k = 0; k < NSP; ++k)
-      u[e + NE * pidx<NSP>(k, l, 0)] = t1 * (rho[l][k] - um[0]) + um[0];
+    {
+      const double v = t1 * (rho[l][k] - um[0]) + um[0];
+      u[e + NE * pidx<NSP>(k, l, 0)] = v;
+      if (dup >= 0) u[(size_t)dup + NE * pidx<NSP>(k, l, 0)] = v;
+    }
+}
+
+template <int NSP>
+__global__ void __launch_bounds__(128)
+limiter2d_kernel(double *__restrict__ u, int nx, int ny, double gamma,
+                 const double *__restrict__ wts, FrbOps ops, int *__restrict__ nbad) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x + 1;
+  const int j = blockIdx.y * blockDim.y + threadIdx.y + 1;
+  if (i > nx || j > ny) return;
+  const size_t NXG = nx + 2, NE = NXG * (size_t)(ny + 2);
+  limit_element<NSP>(u, i + NXG * j, NE, -1, gamma, wts, ops, nbad);
+}
+
+// the same limiter on the row-chunk layout (frb_rc.cuh): thread = (lane, strip, row)
+template <int NSP>
+__global__ void __launch_bounds__(128)
+limiter2d_rc_kernel(double *__restrict__ u, RcGeom g, double gamma, const double *__restrict__ wts,
+                    FrbOps ops, int *__restrict__ nbad) {
+  const int lane = threadIdx.x, s = blockIdx.x * blockDim.y + threadIdx.y, j = blockIdx.y + 1;
+  const int i = kRcOwn * s + lane;
+  if (s >= g.ns || lane < 1 || lane > kRcOwn || i > g.nx) return;
+  int s2, l2;
+  long long dup = -1;
+  if (rc_duplicate(g, s, lane, &s2, &l2)) dup = (long long)rc_index(g, j, s2, 0, l2);
+  limit_element<NSP>(u, rc_index(g, j, s, 0, lane), 32, dup, gamma, wts, ops, nbad);
 }
 
 }  // namespace
@@ -321,5 +348,14 @@ int frb_launch_limiter2d(frb_prob_t p, double *u) {
   FRB_NSP2_SWITCH(p->nsp, (limiter2d_kernel<N><<<grd, blk, 0, p->ctx->stream>>>(
                               u, p->nx, p->ny, p->gamma, p->lim_w, p->ops, p->flag)));
   if (int rc = check_launch2("limiter2d_kernel")) return rc;
+  return 1;
+}
+
+int frb_rc_limiter2d(frb_prob_t p, double *u) {
+  const RcGeom g = rc_geom(p->nx, p->ny, p->nsp);
+  dim3 blk(32, 4), grd((g.ns + 3) / 4, p->ny);
+  FRB_NSP2_SWITCH(p->nsp, (limiter2d_rc_kernel<N><<<grd, blk, 0, p->ctx->stream>>>(
+                              u, g, p->gamma, p->lim_w, p->ops, p->flag)));
+  if (int rc = check_launch2("limiter2d_rc_kernel")) return rc;
   return 1;
 }

@@ -222,6 +222,44 @@ def test_limiter2d(FR, oracle):
     prob.close()
 
 
+@pytest.mark.parametrize("kernel", ["generic", "march", "rc"])
+def test_euler2d_steps_with_limiter_hook(FR, oracle, coracle, kernel):
+    """shock-vortex.jl:298-303: positive_limiter on every element before each step, in every
+    kernel path (the row-chunk path limits in its own layout)."""
+    ps = FR.FRPSpace2D(0.0, 1.0, 64, 0.0, 1.0, 20, 3, 1, 1)
+    u0 = noisy(oracle.ic_wave2d(ps, GAMMA, "x"), 0.01, 17)
+    w = ps.wp / 4
+    prob = FR.Euler2DProblem(u0, (0.0, 0.5), ps, GAMMA, kernel=kernel)
+    itg = FR.init(prob, FR.SSPRK33(), dt=1e-4)
+    itg.set_hooks(ghost="wave_x", limiter_weights=w)
+    FR.step_(itg, 5)
+    ref = coracle.integrate_euler2d(u0, ps, GAMMA, 1e-4, 5, "ssprk3", "wave_x", limiter_weights=w)
+    assert rel(itg.u, ref) <= 1e-12
+    prob.close()
+
+
+@pytest.mark.parametrize("kernel", ["generic", "rc"])
+def test_euler2d_limiter_hook_acts_like_the_oracle_limiter(FR, oracle, kernel):
+    """Elements with a negative density point (some at strip edges: columns 30, 31, 60, 61): a
+    zero-dt step with the hook returns positive_limiter(u0) on the interior, dissipation.jl:125-206."""
+    ps = FR.FRPSpace2D(0.0, 1.0, 64, 0.0, 1.0, 20, 3, 1, 1)
+    u0 = noisy(oracle.ic_wave2d(ps, GAMMA, "x"), 0.01, 18)
+    for i, j in ((30, 3), (31, 3), (60, 9), (61, 10), (1, 1), (64, 20), (17, 11)):
+        u0[i, j, 1, 2, 0] = -0.02
+        u0[i, j, 1, 2, 1:3] = 0.0
+    w = ps.wp / 4
+    prob = FR.Euler2DProblem(u0, (0.0, 0.5), ps, GAMMA, kernel=kernel)
+    itg = FR.init(prob, FR.Euler(), dt=0.0)
+    itg.set_hooks(limiter_weights=w)
+    FR.step_(itg, 1)
+    got = itg.u
+    ref = oracle.positive_limiter_euler2d(u0.copy(order="F"), GAMMA, w, ps.ll, ps.lr)
+    assert np.isfinite(got).all()
+    assert (got[1:-1, 1:-1, :, :, 0] > 0).all() and (u0[1:-1, 1:-1, :, :, 0] < 0).any()
+    assert rel(got[1:-1, 1:-1], ref[1:-1, 1:-1]) <= 1e-14
+    prob.close()
+
+
 def test_euler2d_freestream_and_conservation(FR, oracle):
     """Size-independent properties at a larger size: constant state -> du == 0 to rounding;
     periodic wave -> sum(wp * du) == 0 per variable (discrete conservation)."""
