@@ -62,6 +62,7 @@ SIGNATURES = {
     "frb_time_stage": (C.c_int32, [C.c_void_p, C.c_int32, C.c_int32, C.POINTER(C.c_float)]),
     "frb_last_timing": (C.c_int32, [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_int64)]),
     "frb_set_kernel": (C.c_int32, [C.c_void_p, C.c_int32]),
+    "frb_set_flux": (C.c_int32, [C.c_void_p, C.c_int32]),
     "frb_set_profiling": (C.c_int32, [C.c_void_p, C.c_int32]),
     "frb_stage_timing": (C.c_int32, [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_int64)]),
     "frb_host_alloc": (C.c_int32, [C.c_int64, C.POINTER(C.c_void_p)]),

@@ -322,14 +322,14 @@ extern "C" int32_t frb_state_device_ptr(frb_prob_t p, double **dptr) {
 
 // ---- stage dispatch ---------------------------------------------------------------------
 static bool use_march(frb_prob_t p) {
-  if (p->kind != K_EULER2D) return false;
+  if (p->kind != K_EULER2D || p->flux != FRB_FLUX_HLL) return false;
   if (p->kernel_kind == FRB_KERNEL_GENERIC) return false;
   return frb_euler2d_march_supported(p);
 }
 
 // frb_step streams in the row-chunk layout when it can: 2-D Euler, deg 2..3
 static bool use_rc(frb_prob_t p) {
-  if (p->kind != K_EULER2D || !p->rc_base) return false;
+  if (p->kind != K_EULER2D || !p->rc_base || p->flux != FRB_FLUX_HLL) return false;
   return p->kernel_kind == FRB_KERNEL_AUTO || p->kernel_kind == FRB_KERNEL_RC;
 }
 
@@ -779,6 +779,14 @@ extern "C" int32_t frb_set_kernel(frb_prob_t p, int32_t kind) {
     FRB_REQUIRE(frb_euler2d_march_supported(p), FRB_ERR_STATE,
                 "frb_set_kernel: marching kernel needs euler2d, deg 2..3 and even nx");
   p->kernel_kind = kind;
+  return FRB_OK;
+}
+
+extern "C" int32_t frb_set_flux(frb_prob_t p, int32_t kind) {
+  FRB_REQUIRE(p, FRB_ERR_ARG, "frb_set_flux: prob is NULL");
+  FRB_REQUIRE(p->kind == K_EULER1D || p->kind == K_EULER2D, FRB_ERR_STATE, "frb_set_flux: Euler problems only");
+  FRB_REQUIRE(kind >= FRB_FLUX_HLL && kind <= FRB_FLUX_ROE, FRB_ERR_ARG, "frb_set_flux: unknown flux kind");
+  p->flux = kind;
   return FRB_OK;
 }
 

@@ -113,7 +113,7 @@ template <int NSP>
 __global__ void __launch_bounds__(128)
 euler1d_kernel(const double *__restrict__ u, const double *__restrict__ ua,
                double *__restrict__ out, const double *__restrict__ J, int ncell, double gamma,
-               int bc, FrbOps ops, FrbStage st) {
+               int bc, int flux, FrbOps ops, FrbStage st) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= ncell) return;
   const bool periodic = bc == FRB_BC_PERIOD;
@@ -137,8 +137,11 @@ euler1d_kernel(const double *__restrict__ u, const double *__restrict__ ua,
     uRm[k] = dotn<NSP>(wm[k], ops.lr); uLp[k] = dotn<NSP>(wp[k], ops.ll);
   }
   // :51-54 (interior faces) and :86-89 (periodic seam): HLL with dt = 1
-  frb::Flux3 h0 = hll3_lit(uRm[0], uRm[1], uRm[2], uL[0], uL[1], uL[2], gamma);
-  frb::Flux3 h1 = hll3_lit(uR[0], uR[1], uR[2], uLp[0], uLp[1], uLp[2], gamma);
+  // (flux != HLL: the oracle-defined LF / Roe extras, frb_physics.cuh)
+  frb::Flux3 h0 = flux == FRB_FLUX_HLL ? hll3_lit(uRm[0], uRm[1], uRm[2], uL[0], uL[1], uL[2], gamma)
+                                       : frb::riemann3(flux, uRm[0], uRm[1], uRm[2], uL[0], uL[1], uL[2], gamma);
+  frb::Flux3 h1 = flux == FRB_FLUX_HLL ? hll3_lit(uR[0], uR[1], uR[2], uLp[0], uLp[1], uLp[2], gamma)
+                                       : frb::riemann3(flux, uR[0], uR[1], uR[2], uLp[0], uLp[1], uLp[2], gamma);
   double fi0[3] = {h0.f0, h0.f1, h0.f2}, fi1[3] = {h1.f0, h1.f1, h1.f2};
   const bool frozen = !periodic && (i == 0 || i == ncell - 1);  // dirichlet_euler! :75-78
 #pragma unroll
@@ -220,7 +223,7 @@ int frb_launch_adv1d(frb_prob_t p, const double *u, const double *ua, double *ou
 int frb_launch_euler1d(frb_prob_t p, const double *u, const double *ua, double *out, FrbStage st) {
   dim3 blk(128), grd((p->ncell + 127) / 128);
   FRB_NSP_SWITCH(p->nsp, (euler1d_kernel<N><<<grd, blk, 0, p->ctx->stream>>>(
-                             u, ua, out, p->J, p->ncell, p->gamma, p->bc, p->ops, st)));
+                             u, ua, out, p->J, p->ncell, p->gamma, p->bc, p->flux, p->ops, st)));
   if (int rc = check_launch("euler1d_kernel")) return rc;
   return 1;
 }

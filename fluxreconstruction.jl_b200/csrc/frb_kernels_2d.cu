@@ -27,7 +27,7 @@ template <int NSP>
 __global__ void __launch_bounds__(128)
 euler2d_generic_kernel(const double *__restrict__ u, const double *__restrict__ ua,
                        double *__restrict__ out, int nx, int ny, double iJx, double iJy,
-                       double gamma, FrbOps ops, FrbStage st) {
+                       double gamma, int flux, FrbOps ops, FrbStage st) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x + 1;
   const int j = blockIdx.y * blockDim.y + threadIdx.y + 1;
   if (i > nx || j > ny) return;
@@ -89,8 +89,8 @@ euler2d_generic_kernel(const double *__restrict__ u, const double *__restrict__ 
       }
       uL[m] = a; uR[m] = b; fL[m] = c; fR[m] = d; nL[m] = g; nR[m] = h;
     }
-    frb::Flux4 hl = frb::hll4(nL[0], nL[1], nL[2], nL[3], uL[0], uL[1], uL[2], uL[3], gamma);
-    frb::Flux4 hr = frb::hll4(uR[0], uR[1], uR[2], uR[3], nR[0], nR[1], nR[2], nR[3], gamma);
+    frb::Flux4 hl = frb::riemann4(flux, nL[0], nL[1], nL[2], nL[3], uL[0], uL[1], uL[2], uL[3], gamma);
+    frb::Flux4 hr = frb::riemann4(flux, uR[0], uR[1], uR[2], uR[3], nR[0], nR[1], nR[2], nR[3], gamma);
     const double cl[4] = {hl.f0 * iJx - fL[0], hl.f1 * iJx - fL[1], hl.f2 * iJx - fL[2], hl.f3 * iJx - fL[3]};
     const double cr[4] = {hr.f0 * iJx - fR[0], hr.f1 * iJx - fR[1], hr.f2 * iJx - fR[2], hr.f3 * iJx - fR[3]};
 #pragma unroll
@@ -117,8 +117,8 @@ euler2d_generic_kernel(const double *__restrict__ u, const double *__restrict__ 
       }
       uB[m] = a; uT[m] = b; gB[m] = c; gT[m] = d; nB[m] = g; nT[m] = h;
     }
-    frb::Flux4 hb = frb::hll4_y(nB[0], nB[1], nB[2], nB[3], uB[0], uB[1], uB[2], uB[3], gamma);
-    frb::Flux4 ht = frb::hll4_y(uT[0], uT[1], uT[2], uT[3], nT[0], nT[1], nT[2], nT[3], gamma);
+    frb::Flux4 hb = frb::riemann4_y(flux, nB[0], nB[1], nB[2], nB[3], uB[0], uB[1], uB[2], uB[3], gamma);
+    frb::Flux4 ht = frb::riemann4_y(flux, uT[0], uT[1], uT[2], uT[3], nT[0], nT[1], nT[2], nT[3], gamma);
     const double cb[4] = {hb.f0 * iJy - gB[0], hb.f1 * iJy - gB[1], hb.f2 * iJy - gB[2], hb.f3 * iJy - gB[3]};
     const double ct[4] = {ht.f0 * iJy - gT[0], ht.f1 * iJy - gT[1], ht.f2 * iJy - gT[2], ht.f3 * iJy - gT[3]};
 #pragma unroll
@@ -289,7 +289,7 @@ int frb_launch_euler2d_generic(frb_prob_t p, const double *u, const double *ua, 
   dim3 blk(32, 4), grd((p->nx + 31) / 32, (p->ny + 3) / 4);
   if (st.nested) { st.cdt *= st.cb; st.nested = 0; }
   FRB_NSP2_SWITCH(p->nsp, (euler2d_generic_kernel<N><<<grd, blk, 0, p->ctx->stream>>>(
-                              u, ua, out, p->nx, p->ny, 1.0 / p->Jx, 1.0 / p->Jy, p->gamma, p->ops, st)));
+                              u, ua, out, p->nx, p->ny, 1.0 / p->Jx, 1.0 / p->Jy, p->gamma, p->flux, p->ops, st)));
   if (int rc = check_launch2("euler2d_generic_kernel")) return rc;
   return 1;
 }

@@ -84,6 +84,73 @@ __device__ __forceinline__ Flux4 hll4_y(double l0, double l1, double l2, double 
   return {f.f0, -f.f2, f.f1, f.f3};
 }
 
+// ---- extra common fluxes (the reference's live flux is HLL; LF and Roe are named by
+// the north star, have no reference implementation, and are specified in DESIGN.md section 2) ----
+// Local Lax-Friedrichs (Rusanov): 0.5 (F_L + F_R) - 0.5 alpha (w_R - w_L), alpha = max(|u|+a).
+__device__ __forceinline__ Flux4 lf4(double l0, double l1, double l2, double l3, double r0, double r1,
+                                     double r2, double r3, double gamma) {
+  const double gm1 = gamma - 1.0;
+  double il = 1.0 / l0, ir = 1.0 / r0;
+  double ul = l1 * il, vl = l2 * il, ur = r1 * ir, vr = r2 * ir;
+  double pl = gm1 * (l3 - 0.5 * fma(l1, ul, l2 * vl));
+  double pr = gm1 * (r3 - 0.5 * fma(r1, ur, r2 * vr));
+  double al = sqrt(gamma * pl * il), ar = sqrt(gamma * pr * ir);
+  double alpha = fmax(fabs(ul) + al, fabs(ur) + ar);
+  double fl0 = l1, fl1 = fma(l1, ul, pl), fl2 = l1 * vl, fl3 = (l3 + pl) * ul;
+  double fr0 = r1, fr1 = fma(r1, ur, pr), fr2 = r1 * vr, fr3 = (r3 + pr) * ur;
+  return {0.5 * (fl0 + fr0) - 0.5 * alpha * (r0 - l0), 0.5 * (fl1 + fr1) - 0.5 * alpha * (r1 - l1),
+          0.5 * (fl2 + fr2) - 0.5 * alpha * (r2 - l2), 0.5 * (fl3 + fr3) - 0.5 * alpha * (r3 - l3)};
+}
+
+// Roe flux with Harten's entropy fix on the acoustic waves (below 0.1 a~).
+__device__ __forceinline__ double roe_fix(double lam, double d) {
+  double a = fabs(lam);
+  return a < d ? (lam * lam + d * d) / (2.0 * d) : a;
+}
+__device__ __forceinline__ Flux4 roe4(double l0, double l1, double l2, double l3, double r0, double r1,
+                                      double r2, double r3, double gamma) {
+  const double gm1 = gamma - 1.0;
+  double ul = l1 / l0, vl = l2 / l0, ur = r1 / r0, vr = r2 / r0;
+  double pl = gm1 * (l3 - 0.5 * l0 * (ul * ul + vl * vl));
+  double pr = gm1 * (r3 - 0.5 * r0 * (ur * ur + vr * vr));
+  double Hl = (l3 + pl) / l0, Hr = (r3 + pr) / r0;
+  double R = sqrt(r0 / l0), iR = 1.0 / (1.0 + R);
+  double ut = (ul + R * ur) * iR, vt = (vl + R * vr) * iR, Ht = (Hl + R * Hr) * iR;
+  double q2 = ut * ut + vt * vt;
+  double a2 = gm1 * (Ht - 0.5 * q2), at = sqrt(a2), rt = R * l0;
+  double dr = r0 - l0, du = ur - ul, dv = vr - vl, dp = pr - pl;
+  double c1 = (dp - rt * at * du) / (2.0 * a2), c2 = dr - dp / a2, c3 = rt * dv;
+  double c4 = (dp + rt * at * du) / (2.0 * a2);
+  double d = 0.1 * at;
+  double e1 = roe_fix(ut - at, d) * c1, e2 = fabs(ut) * c2, e3 = fabs(ut) * c3, e4 = roe_fix(ut + at, d) * c4;
+  double fl0 = l1, fl1 = l1 * ul + pl, fl2 = l1 * vl, fl3 = (l3 + pl) * ul;
+  double fr0 = r1, fr1 = r1 * ur + pr, fr2 = r1 * vr, fr3 = (r3 + pr) * ur;
+  return {0.5 * (fl0 + fr0) - 0.5 * (e1 + e2 + e4),
+          0.5 * (fl1 + fr1) - 0.5 * (e1 * (ut - at) + e2 * ut + e4 * (ut + at)),
+          0.5 * (fl2 + fr2) - 0.5 * (e1 * vt + e2 * vt + e3 + e4 * vt),
+          0.5 * (fl3 + fr3) - 0.5 * (e1 * (Ht - ut * at) + e2 * (0.5 * q2) + e3 * vt + e4 * (Ht + ut * at))};
+}
+
+// common flux selector of the generic kernels: kind = FRB_FLUX_HLL / LF / ROE
+__device__ __forceinline__ Flux4 riemann4(int kind, double l0, double l1, double l2, double l3, double r0,
+                                          double r1, double r2, double r3, double gamma) {
+  if (kind == 1) return lf4(l0, l1, l2, l3, r0, r1, r2, r3, gamma);
+  if (kind == 2) return roe4(l0, l1, l2, l3, r0, r1, r2, r3, gamma);
+  return hll4(l0, l1, l2, l3, r0, r1, r2, r3, gamma);
+}
+// normal to a y face: local_frame(., 0, 1) -> flux -> global_frame (euler2d_wave.jl:76-82)
+__device__ __forceinline__ Flux4 riemann4_y(int kind, double l0, double l1, double l2, double l3, double r0,
+                                            double r1, double r2, double r3, double gamma) {
+  Flux4 f = riemann4(kind, l0, l2, -l1, l3, r0, r2, -r1, r3, gamma);
+  return {f.f0, -f.f2, f.f1, f.f3};
+}
+// 1-D: the 4-component flux with zero tangential momentum
+__device__ __forceinline__ Flux3 riemann3(int kind, double l0, double l1, double l2, double r0, double r1,
+                                          double r2, double gamma) {
+  Flux4 f = riemann4(kind, l0, l1, 0.0, l2, r0, r1, 0.0, r2, gamma);
+  return {f.f0, f.f1, f.f3};
+}
+
 // ---- branch-free variants for the roofline kernel -----------------------------------------
 // 1/x and sqrt(x) from the MUFU seeds (about 20 good bits) plus Newton steps on the FP64
 // pipe: no IEEE slow-path subroutine, no divergent branch.  Results are within ~1 ulp for

@@ -33,6 +33,7 @@ from ._lib import Context, check, fortran_ptr, lib, make_operators
 BC = {"dirichlet": 0, "period": 1}
 GHOST = {None: -1, "none": -1, "wave_x": 0, "wave_y": 1, "copy": 2}
 KERNEL = {"auto": 0, "generic": 1, "march": 2, "rc": 3}
+FLUX = {"hll": 0, "lf": 1, "roe": 2}
 
 
 class Euler:
@@ -147,6 +148,10 @@ class _Problem:
         nbad = C.c_int32()
         check(lib().frb_limiter_positivity(self.h, _lib.dptr(w), C.byref(nbad)))
         return nbad.value
+
+    def set_flux(self, flux="hll"):
+        """common flux of the Euler problems: "hll" (the reference's flux_hll!), "lf", "roe" """
+        check(lib().frb_set_flux(self.h, FLUX[_sym(flux)]))
 
     def set_kernel(self, kind="auto"):
         check(lib().frb_set_kernel(self.h, KERNEL[kind]))

@@ -55,6 +55,12 @@ enum { FRB_ADV_PACKAGED = 0, FRB_ADV_LOWLEVEL = 1 };
  * deg == 3, otherwise the generic per-element kernel */
 enum { FRB_KERNEL_AUTO = 0, FRB_KERNEL_GENERIC = 1, FRB_KERNEL_MARCH = 2, FRB_KERNEL_RC = 3 };
 
+/* common (Riemann) flux of the Euler problems.  HLL is what the reference calls (flux_hll!,
+ * eq_euler.jl:53, euler2d_wave.jl:73,80) and what the marching kernels implement; LF (Rusanov)
+ * and ROE (Harten entropy fix below 0.1 a~) are the north star's extras: no reference
+ * implementation exists, DESIGN.md section 2 specifies them; served by the generic kernels. */
+enum { FRB_FLUX_HLL = 0, FRB_FLUX_LF = 1, FRB_FLUX_ROE = 2 };
+
 /* the constant operator arrays of one FR space: ps.ll, ps.lr, ps.dl, ps.dhl, ps.dhr
  * (struct.jl:49-51,63-64,182,193), plus ps.dll/ps.dlr (struct.jl:55-61, may be NULL
  * unless the equation needs interface slopes) */
@@ -148,6 +154,8 @@ int32_t frb_time_stage(frb_prob_t prob, int32_t stage_kind, int32_t iters, float
  * kernels only, excluding host<->device copies) and kernels launched by it */
 int32_t frb_last_timing(frb_prob_t prob, float *ms, int64_t *kernel_launches);
 int32_t frb_set_kernel(frb_prob_t prob, int32_t kernel_kind);
+/* FRB_FLUX_*: Euler problems only (1-D and 2-D); anything but HLL runs the generic kernels */
+int32_t frb_set_flux(frb_prob_t prob, int32_t flux_kind);
 /* per-launch timing of the fused stage kernels inside frb_step / frb_rhs: when enabled,
  * every stage launch is bracketed by CUDA events on the library stream; after the call
  * returns, frb_stage_timing reports the summed device time of those launches and their

@@ -112,6 +112,9 @@ const SCHEME = Dict(:euler => 0, :midpoint => 1, :ssprk3 => 2)
 const GHOST = Dict(:none => -1, :wave_x => 0, :wave_y => 1, :copy => 2)
 set_step_hooks!(p::Problem; ghost = :none, limiter_weights = nothing) = check(ccall((:frb_set_step_hooks, lib), Int32,
     (Ptr{Cvoid}, Int32, Ptr{Float64}), p.h, GHOST[ghost], limiter_weights === nothing ? C_NULL : pointer(limiter_weights)))
+# common flux of the Euler problems: :hll (the reference's flux_hll!), :lf, :roe
+set_flux!(p::Problem, flux::Symbol) = check(ccall((:frb_set_flux, lib), Int32, (Ptr{Cvoid}, Int32), p.h,
+    Int32(Dict(:hll => 0, :lf => 1, :roe => 2)[flux])))
 step!(p::Problem, scheme::Symbol, dt, nsteps = 1) = check(ccall((:frb_step, lib), Int32,
     (Ptr{Cvoid}, Int32, Float64, Int32), p.h, SCHEME[scheme], dt, nsteps))
 function positive_limiter!(p::Problem, weights)      # src/dissipation.jl:61-206 on every interior cell

@@ -359,6 +359,79 @@ def flux_hll(wL, wR, gamma, dt=1.0, length=1.0):
     return fw * (dt * length)
 
 
+def flux_lf(wL, wR, gamma, dt=1.0, length=1.0):
+    """Local Lax-Friedrichs (Rusanov) flux normal to the face (component 1 = normal momentum):
+    0.5 (F_L + F_R) - 0.5 alpha (w_R - w_L), alpha = max(|u_L| + a_L, |u_R| + a_R).
+    Oracle-defined: the reference only sketches an LF-like flux (dev/cylinder.jl:86-88, with the
+    time step as dissipation coefficient); SURVEY 0.1 makes LF/Roe extras without a reference."""
+    wL = np.asarray(wL, dtype=np.float64)
+    wR = np.asarray(wR, dtype=np.float64)
+    primL, primR = conserve_prim(wL, gamma), conserve_prim(wR, gamma)
+    alpha = np.maximum(np.abs(primL[..., 1]) + sound_speed(primL, gamma),
+                       np.abs(primR[..., 1]) + sound_speed(primR, gamma))
+    f1, f2 = euler_flux(wL, gamma)[0], euler_flux(wR, gamma)[0]
+    return (0.5 * (f1 + f2) - 0.5 * alpha[..., None] * (wR - wL)) * (dt * length)
+
+
+def flux_roe(wL, wR, gamma, dt=1.0, length=1.0):
+    """Roe flux normal to the face with Harten's entropy fix on the acoustic waves
+    (|lam| -> (lam^2 + d^2) / (2 d) below d = 0.1 a~).  3 (1-D) or 4 (2-D) components.
+    Oracle-defined (the reference names flux_roe! only in dev/gks.jl:176-177)."""
+    wL = np.asarray(wL, dtype=np.float64)
+    wR = np.asarray(wR, dtype=np.float64)
+    nv = wL.shape[-1]
+    gm1 = gamma - 1.0
+
+    def prim(w):
+        rho = w[..., 0]
+        u = w[..., 1] / rho
+        v = w[..., 2] / rho if nv == 4 else np.zeros_like(rho)
+        E = w[..., -1]
+        p = gm1 * (E - 0.5 * rho * (u * u + v * v))
+        return rho, u, v, p, (E + p) / rho
+
+    rL, uL, vL, pL, HL = prim(wL)
+    rR, uR, vR, pR, HR = prim(wR)
+    R = np.sqrt(rR / rL)
+    ut = (uL + R * uR) / (1.0 + R)
+    vt = (vL + R * vR) / (1.0 + R)
+    Ht = (HL + R * HR) / (1.0 + R)
+    q2 = ut * ut + vt * vt
+    a2 = gm1 * (Ht - 0.5 * q2)
+    at = np.sqrt(a2)
+    rt = R * rL
+    dr, du, dv, dp = rR - rL, uR - uL, vR - vL, pR - pL
+    a1 = (dp - rt * at * du) / (2.0 * a2)
+    a2w = dr - dp / a2
+    a3 = rt * dv
+    a4 = (dp + rt * at * du) / (2.0 * a2)
+    d = 0.1 * at
+
+    def fix(lam):
+        al = np.abs(lam)
+        return np.where(al < d, (lam * lam + d * d) / (2.0 * d), al)
+
+    l1, l2, l4 = fix(ut - at), np.abs(ut), fix(ut + at)
+    one, zero = np.ones_like(ut), np.zeros_like(ut)
+    if nv == 4:
+        K1 = np.stack([one, ut - at, vt, Ht - ut * at], axis=-1)
+        K2 = np.stack([one, ut, vt, 0.5 * q2], axis=-1)
+        K3 = np.stack([zero, zero, one, vt], axis=-1)
+        K4 = np.stack([one, ut + at, vt, Ht + ut * at], axis=-1)
+        diss = ((l1 * a1)[..., None] * K1 + (l2 * a2w)[..., None] * K2 + (l2 * a3)[..., None] * K3
+                + (l4 * a4)[..., None] * K4)
+    else:
+        K1 = np.stack([one, ut - at, Ht - ut * at], axis=-1)
+        K2 = np.stack([one, ut, 0.5 * q2], axis=-1)
+        K4 = np.stack([one, ut + at, Ht + ut * at], axis=-1)
+        diss = (l1 * a1)[..., None] * K1 + (l2 * a2w)[..., None] * K2 + (l4 * a4)[..., None] * K4
+    f1, f2 = euler_flux(wL, gamma)[0], euler_flux(wR, gamma)[0]
+    return (0.5 * (f1 + f2) - 0.5 * diss) * (dt * length)
+
+
+RIEMANN = {"hll": flux_hll, "lf": flux_lf, "roe": flux_roe}
+
+
 def local_frame(w, c, s):
     w = np.asarray(w, dtype=np.float64)
     out = np.empty_like(w)
@@ -457,8 +530,9 @@ def rhs_advection1d(u, ps: FRPSpace1D, a, bc="period", variant="packaged"):
     return du
 
 
-def rhs_euler1d(u, ps: FRPSpace1D, gamma, bc="dirichlet"):
-    """src/Equation/eq_euler.jl:29-98.  u[ncell, nsp, 3]."""
+def rhs_euler1d(u, ps: FRPSpace1D, gamma, bc="dirichlet", flux="hll"):
+    """src/Equation/eq_euler.jl:29-98.  u[ncell, nsp, 3].  flux: the common flux (reference: hll)."""
+    flux_hll = RIEMANN[flux]  # noqa: F811 (the reference's call sites keep their name)
     ncell, nsp, _ = u.shape
     J = ps.J[ps.ng : ps.ng + ncell]
     f = euler_flux(u, gamma)[0] / J[:, None, None]  # :35-39
@@ -490,9 +564,10 @@ def rhs_euler1d(u, ps: FRPSpace1D, gamma, bc="dirichlet"):
     return du
 
 
-def rhs_euler2d(u, ps: FRPSpace2D, gamma):
-    """example/euler2d_wave.jl:35-107.  u[nx+2, ny+2, nsp, nsp, 4] with one ghost
+def rhs_euler2d(u, ps: FRPSpace2D, gamma, flux="hll"):
+    """example/euler2d_wave.jl:35-107.  flux: the common flux (reference: hll).  u[nx+2, ny+2, nsp, nsp, 4] with one ghost
     ring (axis index = reference index).  du is zero in ghosts (:36)."""
+    flux_hll = RIEMANN[flux]  # noqa: F811
     nxg, nyg, nsp, _, _ = u.shape
     nx, ny = nxg - 2, nyg - 2
     ll, lr, dhl, dhr, lpdm = ps.ll, ps.lr, ps.dhl, ps.dhr, ps.dl

@@ -463,3 +463,59 @@ def test_cfg5_full_size_ns_rhs(FR, oracle, coracle):
     assert np.isfinite(du).all()
     assert rel(du, ref) <= RTOL_RHS
     prob.close()
+
+
+# ---------------------------------------------------------------- LF / Roe common fluxes (oracle-defined extras)
+@pytest.mark.parametrize("flux", ["lf", "roe"])
+@pytest.mark.parametrize("bc", ["dirichlet", "period"])
+def test_euler1d_rhs_other_fluxes(FR, oracle, flux, bc):
+    ps = FR.FRPSpace1D(0.0, 1.0, 64, 3)
+    u = noisy(oracle.ic_wave1d(ps, GAMMA), 0.02, 4)
+    prob = FR.FREulerProblem(u, (0.0, 1.0), ps, GAMMA, bc)
+    prob.set_flux(flux)
+    du = np.zeros_like(u, order="F")
+    prob.f(du, u, None, 0.0)
+    assert rel(du, oracle.rhs_euler1d(u, ps, GAMMA, bc, flux=flux)) <= RTOL_RHS
+    prob.close()
+
+
+@pytest.mark.parametrize("flux", ["lf", "roe"])
+@pytest.mark.parametrize("deg", [2, 3])
+def test_euler2d_rhs_and_steps_other_fluxes(FR, oracle, flux, deg):
+    """RHS and 20 SSPRK3 steps with the LF / Roe common flux against the NumPy oracle; the stepping
+    runs through frb_step (generic kernel: the marching kernels are HLL-only)."""
+    ps = FR.FRPSpace2D(0.0, 1.0, 24, 0.0, 1.0, 18, deg, 1, 1)
+    u = noisy(oracle.ic_wave2d(ps, GAMMA, "x"), 0.02, 5)
+    u[..., 2] += 0.1 * u[..., 0]
+    oracle.ghost_fill_euler2d(u, "wave_x")
+    prob = FR.Euler2DProblem(u, (0.0, 0.5), ps, GAMMA)
+    prob.set_flux(flux)
+    du = np.zeros_like(u, order="F")
+    prob.f(du, u, None, 0.0)
+    assert rel(du, oracle.rhs_euler2d(u, ps, GAMMA, flux=flux)) <= RTOL_RHS
+    itg = FR.init(prob, FR.SSPRK33(), dt=2e-4)
+    itg.set_hooks(ghost="wave_x")
+    FR.step_(itg, 20)
+
+    def before(v):
+        oracle.ghost_fill_euler2d(v, "wave_x")
+
+    ref = oracle.integrate(u.copy(order="F"), 2e-4, 20, lambda v: oracle.rhs_euler2d(v, ps, GAMMA, flux=flux),
+                           "ssprk3", before_step=before)
+    assert rel(itg.u, ref) <= 1e-11
+    prob.close()
+
+
+def test_supersonic_roe_and_lf_are_consistent(FR, oracle):
+    """Uniform supersonic stream: every common flux returns the physical flux, du == 0."""
+    ps = FR.FRPSpace2D(0.0, 1.0, 12, 0.0, 1.0, 10, 3, 1, 1)
+    w = oracle.prim_conserve(np.array([1.0, 3.0, 2.5, 0.8]), GAMMA)
+    u = np.empty((14, 12, 4, 4, 4), order="F")
+    u[...] = w
+    for flux in ("hll", "lf", "roe"):
+        prob = FR.Euler2DProblem(u, (0.0, 0.5), ps, GAMMA)
+        prob.set_flux(flux)
+        du = np.zeros_like(u, order="F")
+        prob.f(du, u, None, 0.0)
+        assert np.abs(du).max() <= 1e-9
+        prob.close()
