@@ -59,6 +59,10 @@ SIGNATURES = {
     "frb_step": (C.c_int32, [C.c_void_p, C.c_int32, C.c_double, C.c_int32]),
     "frb_ghost_fill": (C.c_int32, [C.c_void_p, C.c_int32]),
     "frb_limiter_positivity": (C.c_int32, [C.c_void_p, c_dp, C.POINTER(C.c_int32)]),
+    "frb_filter_modal": (C.c_int32, [C.c_void_p, c_dp, c_dp, C.c_int32, C.c_double, C.c_double, C.c_double,
+                                     C.c_int32, C.POINTER(C.c_int32)]),
+    "frb_set_filter_hook": (C.c_int32, [C.c_void_p, C.c_int32, c_dp, c_dp, C.c_int32, C.c_double, C.c_double,
+                                        C.c_double, C.c_int32]),
     "frb_time_stage": (C.c_int32, [C.c_void_p, C.c_int32, C.c_int32, C.POINTER(C.c_float)]),
     "frb_last_timing": (C.c_int32, [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_int64)]),
     "frb_set_kernel": (C.c_int32, [C.c_void_p, C.c_int32]),

@@ -155,7 +155,7 @@ extern "C" int32_t frb_prob_destroy(frb_prob_t p) {
   frb_march_release(p);
   cudaFree(p->u); cudaFree(p->s1); cudaFree(p->s2); cudaFree(p->du); cudaFree(p->rc_base);
   cudaFree(p->J); cudaFree(p->velo); cudaFree(p->weights); cudaFree(p->prim);
-  cudaFree(p->lim_w); cudaFree(p->flag);
+  cudaFree(p->lim_w); cudaFree(p->flag); cudaFree(p->filt);
   if (p->ev0) cudaEventDestroy(p->ev0);
   if (p->ev1) cudaEventDestroy(p->ev1);
   for (cudaEvent_t e : p->prof_events) cudaEventDestroy(e);
@@ -330,6 +330,7 @@ static bool use_march(frb_prob_t p) {
 // frb_step streams in the row-chunk layout when it can: 2-D Euler, deg 2..3
 static bool use_rc(frb_prob_t p) {
   if (p->kind != K_EULER2D || !p->rc_base || p->flux != FRB_FLUX_HLL) return false;
+  if (p->filt_when != 0) return false;  // the filter pass works on the reference image
   return p->kernel_kind == FRB_KERNEL_AUTO || p->kernel_kind == FRB_KERNEL_RC;
 }
 
@@ -550,6 +551,64 @@ extern "C" int32_t frb_limiter_positivity(frb_prob_t p, const double *weights, i
   return FRB_OK;
 }
 
+// ---- shock sensor + modal filter ---------------------------------------------------------
+static int set_filter(frb_prob_t p, const double *iV, const double *F, int np) {
+  const int want = p->kind == K_EULER1D ? p->nsp : p->nsp * p->nsp;
+  FRB_REQUIRE(p->kind == K_EULER1D || p->kind == K_EULER2D, FRB_ERR_STATE, "modal filter: Euler problems only");
+  FRB_REQUIRE(iV && F && np == want, FRB_ERR_ARG, "modal filter: iV, F must be np x np with np = points per element");
+  if (!p->filt || p->filt_np != np) {
+    cudaFree(p->filt);
+    p->filt = nullptr;
+    FRB_CUDA(cudaMalloc(&p->filt, sizeof(double) * 2 * np * np));
+    p->filt_np = np;
+  }
+  FRB_CUDA(cudaMemcpy(p->filt, iV, sizeof(double) * np * np, cudaMemcpyHostToDevice));
+  FRB_CUDA(cudaMemcpy(p->filt + np * np, F, sizeof(double) * np * np, cudaMemcpyHostToDevice));
+  return FRB_OK;
+}
+
+static int run_filter(frb_prob_t p, int *count = nullptr) {
+  int n = frb_launch_modal_filter(p, p->u, p->filt, p->filt + p->filt_np * p->filt_np, p->filt_eps, p->filt_S0,
+                                  p->filt_kappa, p->filt_ghosts != 0, count);
+  if (n > 0) p->launches += n;
+  return n;
+}
+
+extern "C" int32_t frb_filter_modal(frb_prob_t p, const double *iV, const double *F, int32_t np, double eps,
+                                    double S0, double kappa, int32_t include_ghosts, int32_t *nfiltered) {
+  FRB_REQUIRE(p, FRB_ERR_ARG, "frb_filter_modal: prob is NULL");
+  FRB_CUDA(cudaSetDevice(p->ctx->device));
+  if (int rc = set_filter(p, iV, F, np)) return rc;
+  if (int rc = need_ref(p, true)) return rc;
+  const int when = p->filt_when;  // a stand-alone call does not disturb the hook's parameters
+  const double e0 = p->filt_eps, s0 = p->filt_S0, k0 = p->filt_kappa;
+  const int g0 = p->filt_ghosts;
+  p->filt_eps = eps; p->filt_S0 = S0; p->filt_kappa = kappa; p->filt_ghosts = include_ghosts;
+  FRB_CUDA(cudaMemsetAsync(p->flag, 0, sizeof(int), p->ctx->stream));
+  int n = run_filter(p, p->flag);
+  p->filt_eps = e0; p->filt_S0 = s0; p->filt_kappa = k0; p->filt_ghosts = g0; p->filt_when = when;
+  if (n < 0) return n;
+  int cnt = 0;
+  FRB_CUDA(cudaMemcpyAsync(&cnt, p->flag, sizeof(int), cudaMemcpyDeviceToHost, p->ctx->stream));
+  FRB_CUDA(cudaStreamSynchronize(p->ctx->stream));
+  if (nfiltered) *nfiltered = cnt;
+  return FRB_OK;
+}
+
+extern "C" int32_t frb_set_filter_hook(frb_prob_t p, int32_t when, const double *iV, const double *F, int32_t np,
+                                       double eps, double S0, double kappa, int32_t include_ghosts) {
+  FRB_REQUIRE(p, FRB_ERR_ARG, "frb_set_filter_hook: prob is NULL");
+  FRB_REQUIRE(when >= 0 && when <= 2, FRB_ERR_ARG, "frb_set_filter_hook: when must be 0, 1 or 2");
+  FRB_CUDA(cudaSetDevice(p->ctx->device));
+  if (when != 0) {
+    FRB_REQUIRE(!p->limiter_on || p->kind == K_EULER2D || p->kind == K_EULER1D, FRB_ERR_STATE, "filter hook: Euler problems only");
+    if (int rc = set_filter(p, iV, F, np)) return rc;
+    p->filt_eps = eps; p->filt_S0 = S0; p->filt_kappa = kappa; p->filt_ghosts = include_ghosts;
+  }
+  p->filt_when = when;
+  return FRB_OK;
+}
+
 // ---- step! ------------------------------------------------------------------------------
 static int halo_wait_if_pending(frb_prob_t p) {
   if (!p->halo_pending) return 0;
@@ -598,6 +657,9 @@ static int one_step(frb_prob_t p, int scheme, double dt, bool rc) {
   int n;
   const bool par = frb_halo_active(p);
   double *&U = rc ? p->ru : p->u, *&S1 = rc ? p->rs1 : p->s1, *&S2 = rc ? p->rs2 : p->s2;
+  if (p->filt_when == 1) {
+    if ((n = run_filter(p)) < 0) return n;
+  }
   if (p->limiter_on) {
     if ((n = run_limiter(p, rc)) < 0) return n;
   }
@@ -670,6 +732,9 @@ static int one_step(frb_prob_t p, int scheme, double dt, bool rc) {
   } else {
     frb_set_error("frb_step: unknown scheme");
     return FRB_ERR_ARG;
+  }
+  if (p->filt_when == 2) {
+    if ((n = run_filter(p)) < 0) return n;
   }
   return FRB_OK;
 }

@@ -82,6 +82,11 @@ struct frb_prob_s {
   double *J = nullptr;              // 1-D per-cell Jacobian / bgk dx
   double *velo = nullptr, *weights = nullptr, *prim = nullptr;  // bgk
   double *lim_w = nullptr;          // limiter weights (device)
+  // shock sensor + modal filter hook (frb_set_filter_hook): iV | F on the device, when = 0 off,
+  // 1 before every step (euler_highlevel.jl:37-52), 2 after every step (shock-vortex.jl:308-321)
+  double *filt = nullptr;
+  int filt_np = 0, filt_when = 0, filt_ghosts = 0;
+  double filt_eps = 0, filt_S0 = 0, filt_kappa = 0;
   int *flag = nullptr;              // device int for limiter nbad
   // hooks
   int ghost_mode = FRB_GHOST_NONE;
@@ -138,6 +143,8 @@ int frb_halo_signal(frb_prob_t p);
 int frb_halo_wait(frb_prob_t p);
 int frb_halo_check_timeout(frb_prob_t p);
 int frb_halo_rank(frb_prob_t p, int *nranks);
+int frb_launch_modal_filter(frb_prob_t p, double *u, const double *iV_dev, const double *F_dev, double eps,
+                            double S0, double kappa, bool include_ghosts, int *count);
 int frb_launch_limiter1d(frb_prob_t p, double *u);
 int frb_launch_limiter2d(frb_prob_t p, double *u);
 int frb_launch_dirichlet_copy1d(frb_prob_t p, const double *src, double *dst);

@@ -54,6 +54,15 @@ class SSPRK33:
     stages = 3
 
 
+def modal_filter_diag(n, lam):
+    """[KB] KitBase.modal_filter!(u, lam; filter=:l2) as a diagonal: mode k >= 1 is divided by
+    1 + lam k^2 (k+1)^2."""
+    k = np.arange(n, dtype=np.float64)
+    d = 1.0 / (1.0 + lam * (k + 1.0) ** 2 * k**2)
+    d[0] = 1.0
+    return d
+
+
 def _sym(s):
     return str(s).lstrip(":")
 
@@ -148,6 +157,29 @@ class _Problem:
         nbad = C.c_int32()
         check(lib().frb_limiter_positivity(self.h, _lib.dptr(w), C.byref(nbad)))
         return nbad.value
+
+    def modal_filter(self, ps, lam, eps=None, S0=None, kappa=None, ghosts=None, when=None):
+        """Shock sensor + modal l2 filter on every element of the resident state (Euler problems):
+        example/euler_highlevel.jl:37-52 (1-D defaults eps = 1e-6, kappa = 4) and
+        example/shock-vortex.jl:308-321 (2-D defaults eps = 0, kappa = 9, ghost cells included).
+        ``when`` = "before" / "after" registers it as a hook of every step instead (None: run now
+        and return the number of filtered elements; "off" removes the hook)."""
+        two_d = self.u0.ndim == 5
+        eps = (0.0 if two_d else 1e-6) if eps is None else eps
+        kappa = (9.0 if two_d else 4.0) if kappa is None else kappa
+        S0 = -3.0 * np.log10(ps.deg) if S0 is None else S0
+        ghosts = two_d if ghosts is None else ghosts
+        iV = np.asfortranarray(ps.iV, dtype=np.float64)
+        F = np.asfortranarray(ps.V @ np.diag(modal_filter_diag(iV.shape[0], lam)) @ ps.iV, dtype=np.float64)
+        args = (_lib.dptr(iV.ravel(order="F")), _lib.dptr(F.ravel(order="F")), iV.shape[0], float(eps), float(S0),
+                float(kappa), int(bool(ghosts)))
+        if when is None:
+            n = C.c_int32()
+            check(lib().frb_filter_modal(self.h, *args, C.byref(n)))
+            return n.value
+        code = {"off": 0, "before": 1, "after": 2}[when]
+        check(lib().frb_set_filter_hook(self.h, code, *args))
+        return None
 
     def set_flux(self, flux="hll"):
         """common flux of the Euler problems: "hll" (the reference's flux_hll!), "lf", "roe" """

@@ -190,6 +190,11 @@ class FRPSpace2D:
         self.ll, self.lr, self.dl = standard_lagrange(r)
         self.dll, self.dlr, _ = _edge_slopes(deg, r)
         self.dhl, self.dhr = dradau(deg, r)
+        # 2-D Vandermonde (struct.jl:196-205; vandermonde_matrix(Quad, ...), transform.jl:55-69):
+        # rows = points in [:] order of u[i,j,:,:,m] (k fastest), columns = modes (i, j), j fastest
+        V1 = vandermonde_matrix(deg, r)  # [point, mode]
+        self.V = np.asfortranarray(np.einsum("ka,lb->lkab", V1, V1).reshape(nsp * nsp, nsp * nsp))
+        self.iV = np.asfortranarray(np.linalg.inv(self.V))
 
     @property
     def J(self):

@@ -144,6 +144,20 @@ int32_t frb_ghost_fill(frb_prob_t prob, int32_t ghost_mode);
 /* positive_limiter(u, gamma, weights, ll, lr) src/dissipation.jl:61-123,125-206 on every
  * interior cell; *nbad = cells whose parameter left (0,1] (reference: @assert) */
 int32_t frb_limiter_positivity(frb_prob_t prob, const double *weights, int32_t *nbad);
+/* Shock sensor + modal filter on every element of the resident state (Euler problems), the pass
+ * the reference's shock cases run on the host between two step! calls
+ * (example/euler_highlevel.jl:37-52, example/shock-vortex.jl:308-321):
+ *   u_hat = iV * u[element, density];  su = u_hat[end]^2 / (sum(u_hat.^2) + eps)
+ *   if shock_detector(log10(su), deg, S0, kappa)  (src/dissipation.jl:13-23):
+ *       every variable  u <- F * u,   F = V * diag(filter) * iV   (KitBase modal_filter! on the modes)
+ * iV, F: np x np column-major (np = deg+1 in 1-D, (deg+1)^2 in 2-D, Julia's [:] order of the
+ * element block); include_ghosts != 0 runs over the ghost cells too (2-D script).
+ * *nfiltered = elements the sensor flagged. */
+int32_t frb_filter_modal(frb_prob_t prob, const double *iV, const double *F, int32_t np, double eps,
+                         double S0, double kappa, int32_t include_ghosts, int32_t *nfiltered);
+/* the same pass as a hook of frb_step: when = 1 before every step, 2 after every step, 0 off */
+int32_t frb_set_filter_hook(frb_prob_t prob, int32_t when, const double *iV, const double *F, int32_t np,
+                            double eps, double S0, double kappa, int32_t include_ghosts);
 
 /* ---- measurement (CUDA events on the library's own stream) ---------------------- */
 /* Launch `iters` back-to-back RK stages of kind `stage_kind` (0: u' = u + dt L(u), 16 B/DOF;

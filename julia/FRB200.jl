@@ -112,6 +112,13 @@ const SCHEME = Dict(:euler => 0, :midpoint => 1, :ssprk3 => 2)
 const GHOST = Dict(:none => -1, :wave_x => 0, :wave_y => 1, :copy => 2)
 set_step_hooks!(p::Problem; ghost = :none, limiter_weights = nothing) = check(ccall((:frb_set_step_hooks, lib), Int32,
     (Ptr{Cvoid}, Int32, Ptr{Float64}), p.h, GHOST[ghost], limiter_weights === nothing ? C_NULL : pointer(limiter_weights)))
+# shock sensor + modal filter on every element (euler_highlevel.jl:37-52, shock-vortex.jl:308-321):
+# F = ps.V * Diagonal(filterdiag) * ps.iV is built here from whatever KitBase filter the caller uses
+function modal_filter!(p::Problem, iV::Matrix{Float64}, F::Matrix{Float64}; eps = 1e-6, S0, kappa = 4.0, ghosts = false)
+    n = Ref{Int32}(0)
+    check(ccall((:frb_filter_modal, lib), Int32, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Int32, Float64, Float64,
+        Float64, Int32, Ref{Int32}), p.h, iV, F, size(iV, 1), eps, S0, kappa, ghosts ? 1 : 0, n)); n[]
+end
 # common flux of the Euler problems: :hll (the reference's flux_hll!), :lf, :roe
 set_flux!(p::Problem, flux::Symbol) = check(ccall((:frb_set_flux, lib), Int32, (Ptr{Cvoid}, Int32), p.h,
     Int32(Dict(:hll => 0, :lf => 1, :roe => 2)[flux])))

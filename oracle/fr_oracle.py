@@ -761,6 +761,65 @@ def positive_limiter_euler2d(u, gamma, weights, ll, lr):
 SCHEMES = ("euler", "midpoint", "ssprk3")
 
 
+# ------------------------------------------------------------------ shock sensor + modal filter
+def shock_detector(Se, deg, S0=None, kappa=4.0):
+    """src/dissipation.jl:13-23."""
+    if S0 is None:
+        S0 = -3.0 * np.log10(deg)
+    if Se < S0 - kappa:
+        sigma = 1.0
+    elif S0 - kappa <= Se < S0 + kappa:
+        sigma = 0.5 * (1.0 - np.sin(0.5 * np.pi * (Se - S0) / kappa))
+    else:
+        sigma = 0.0
+    return sigma < 0.99
+
+
+def modal_filter_l2(u_hat, lam):
+    """[KB] KitBase.modal_filter!(u, lam; filter=:l2) on a vector of modes: mode k >= 1 is divided
+    by 1 + lam k^2 (k+1)^2, mode 0 is kept."""
+    out = np.array(u_hat, dtype=np.float64)
+    for k in range(1, len(out)):
+        out[k] /= 1.0 + lam * (k + 1) ** 2 * k**2
+    return out
+
+
+def filter_pass_1d(u, V, iV, deg, lam, eps=1e-6, S0=None, kappa=4.0):
+    """example/euler_highlevel.jl:37-52 on u[ncell, nsp, 3]; returns the number of filtered cells."""
+    n = 0
+    for i in range(u.shape[0]):
+        uh = iV @ u[i, :, 0]
+        with np.errstate(divide="ignore", invalid="ignore"):
+            su = uh[-1] ** 2 / (np.sum(uh**2) + eps)
+            Se = np.log10(su)
+        if shock_detector(Se, deg, S0, kappa):
+            n += 1
+            for s in range(u.shape[2]):
+                u[i, :, s] = V @ modal_filter_l2(iV @ u[i, :, s], lam)
+    return n
+
+
+def filter_pass_2d(u, V, iV, deg, lam, eps=0.0, S0=None, kappa=9.0, ghosts=True):
+    """example/shock-vortex.jl:308-321 on u[nx+2, ny+2, nsp, nsp, 4]: the modes of the element
+    block in [:] order (first tensor index fastest) go through the *vector* l2 filter."""
+    nsp = u.shape[2]
+    n = 0
+    I = range(u.shape[0]) if ghosts else range(1, u.shape[0] - 1)
+    Jr = range(u.shape[1]) if ghosts else range(1, u.shape[1] - 1)
+    for i in I:
+        for j in Jr:
+            uh = iV @ u[i, j, :, :, 0].reshape(-1, order="F")
+            with np.errstate(divide="ignore", invalid="ignore"):
+                su = uh[-1] ** 2 / (np.sum(uh**2) + eps)
+                Se = np.log10(su)
+            if shock_detector(Se, deg, S0, kappa):
+                n += 1
+                for s in range(4):
+                    uh = iV @ u[i, j, :, :, s].reshape(-1, order="F")
+                    u[i, j, :, :, s] = (V @ modal_filter_l2(uh, lam)).reshape(nsp, nsp, order="F")
+    return n
+
+
 def step(u, dt, rhs, scheme="midpoint"):
     """One fixed step.  Euler: u+dt L(u).  Midpoint: k1=L(u), k2=L(u+dt/2 k1),
     u+dt k2.  SSPRK3: Shu-Osher convex form (not in the reference; north_star)."""

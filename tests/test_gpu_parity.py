@@ -519,3 +519,46 @@ def test_supersonic_roe_and_lf_are_consistent(FR, oracle):
         prob.f(du, u, None, 0.0)
         assert np.abs(du).max() <= 1e-9
         prob.close()
+
+
+# ---------------------------------------------------------------- shock sensor + modal filter
+def test_modal_filter_1d(FR, oracle):
+    """example/euler_highlevel.jl:37-52 on the Sod state: the cells at the jump are flagged and
+    filtered, the rest is untouched."""
+    ps = FR.FRPSpace1D(0.0, 1.0, 100, 3)
+    u = oracle.ic_wave1d(ps, GAMMA, amp=1e-6)
+    u[ps.xpg[ps.ng: ps.ng + 100] > 0.5031] *= 0.4  # jumps inside cells 51 and 78
+    u[ps.xpg[ps.ng: ps.ng + 100] > 0.7777] *= 2.0
+    u = np.asfortranarray(u)
+    prob = FR.FREulerProblem(u, (0.0, 0.15), ps, GAMMA, "dirichlet")
+    lam = 1e-4 * np.exp(0.875 * ps.deg) * 0.15
+    ref = u.copy(order="F")
+    nref = oracle.filter_pass_1d(ref, ps.V, ps.iV, ps.deg, lam)
+    n = prob.modal_filter(ps, lam)
+    assert n == nref and 0 < n < 100
+    assert rel(prob.download(), ref) <= 1e-14
+    prob.close()
+
+
+def test_modal_filter_2d_and_hook(FR, oracle, coracle):
+    """example/shock-vortex.jl:308-321: stand-alone pass == oracle; as an "after" hook, 3 Midpoint steps
+    == oracle steps with the pass after each."""
+    ps = FR.FRPSpace2D(0.0, 1.0, 20, 0.0, 1.0, 12, 2, 1, 1)
+    u = noisy(oracle.ic_wave2d(ps, GAMMA, "x"), 1e-3, 32)
+    u[8:11, 3:9] *= 1.6  # a jump: the sensor fires around it
+    prob = FR.Euler2DProblem(u, (0.0, 0.5), ps, GAMMA)
+    ref = u.copy(order="F")
+    nref = oracle.filter_pass_2d(ref, ps.V, ps.iV, ps.deg, 5e-4)
+    n = prob.modal_filter(ps, 5e-4)
+    assert n == nref and 0 < n < 22 * 14
+    assert rel(prob.download(), ref) <= 1e-14
+    prob.upload(u)
+    prob.modal_filter(ps, 5e-4, when="after")
+    itg = FR.init(prob, FR.Midpoint(), dt=1e-4)
+    FR.step_(itg, 3)
+    ref = u.copy(order="F")
+    for _ in range(3):
+        ref = coracle.integrate_euler2d(ref, ps, GAMMA, 1e-4, 1, "midpoint", None)
+        oracle.filter_pass_2d(ref, ps.V, ps.iV, ps.deg, 5e-4)
+    assert rel(itg.u, ref) <= 1e-12
+    prob.close()
