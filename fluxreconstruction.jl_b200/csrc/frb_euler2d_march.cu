@@ -30,6 +30,7 @@
 
 #include "frb_internal.cuh"
 #include "frb_physics.cuh"
+#include "frb_euler2d_passes.cuh"
 #include "frb_ptx.cuh"
 
 namespace {
@@ -37,6 +38,7 @@ namespace {
 constexpr int kOwn = 30;  // owned elements per strip (32 lanes - 2 halo lanes)
 
 using namespace frbptx;
+using namespace frbpass;
 
 struct MarchParams {
   const double *ua;  // u_n (may alias out)
@@ -63,19 +65,6 @@ struct Smem {
   alignas(128) double xrp[2 * NSP * NSP * 32];  // v_y and p at the points
   alignas(8) uint64_t bar[NBUF];
 };
-
-// y traces of one column (k = t) of a tile: top (lr) or bottom (ll)
-template <int NSP>
-__device__ __forceinline__ void col_trace(const double *__restrict__ Uy, const double *l,
-                                          double (&tr)[4]) {
-#pragma unroll
-  for (int m = 0; m < 4; ++m) {
-    double a = Uy[32 * NSP * (0 + NSP * m)] * l[0];
-#pragma unroll
-    for (int q = 1; q < NSP; ++q) a = fma(Uy[32 * NSP * (q + NSP * m)], l[q], a);
-    tr[m] = a;
-  }
-}
 
 // MINB = resident CTAs per SM the register budget is compiled for
 template <int NSP, int NBUF, int MINB, bool PREFETCH, bool USEA, bool SAMEJ, bool COPYONLY = false>
@@ -140,11 +129,9 @@ euler2d_march_kernel(const __grid_constant__ CUtensorMap tmap, MarchParams P, Ma
   {
     mbar_wait(&S.bar[0], 0);
     mbar_wait(&S.bar[1 % NBUF], 0);
-    double uT[4], uB[4];
+    double uT[4];
     col_trace<NSP>(S.tile[0] + offy, ops.lr, uT);
-    col_trace<NSP>(S.tile[1 % NBUF] + offy, ops.ll, uB);
-    frb::Flux4 h = frb::hll4_y_fast(uT[0], uT[1], uT[2], uT[3], uB[0], uB[1], uB[2], uB[3], gamma, gm1);
-    hb[0] = h.f0; hb[1] = h.f1; hb[2] = h.f2; hb[3] = h.f3;
+    face_flux_y<NSP>(uT, S.tile[1 % NBUF] + offy, ops, gamma, gm1, hb);
   }
   {
     // tile 0 is dead after the prologue: refill its buffer with tile NBUF
@@ -192,56 +179,7 @@ euler2d_march_kernel(const __grid_constant__ CUtensorMap tmap, MarchParams P, Ma
       continue;
     }
     // -------------------------------------------------------------- x pass: row l = t
-    {
-      double w[NSP][4], f[NSP][4];
-#pragma unroll
-      for (int m = 0; m < 4; ++m)
-#pragma unroll
-        for (int k = 0; k < NSP; ++k) w[k][m] = Ux[32 * (k + NSP * NSP * m)];
-#pragma unroll
-      for (int k = 0; k < NSP; ++k) {
-        double rr = frb::rcp_fast(w[k][0]);
-        double vx = w[k][1] * rr, vy = w[k][2] * rr;
-        double p = gm1 * fma(-0.5, fma(w[k][1], vx, w[k][2] * vy), w[k][3]);
-        f[k][0] = w[k][1];
-        f[k][1] = fma(w[k][1], vx, p);
-        f[k][2] = w[k][1] * vy;
-        f[k][3] = (w[k][3] + p) * vx;
-        xrpx[32 * k] = vy;  // the y pass needs only v_y and p of the point
-        xrpx[32 * (NSP * NSP + k)] = p;
-      }
-      double uL[4], uR[4];
-#pragma unroll
-      for (int m = 0; m < 4; ++m) {
-        double a = w[0][m] * ops.ll[0], b = w[0][m] * ops.lr[0];
-#pragma unroll
-        for (int q2 = 1; q2 < NSP; ++q2) {
-          a = fma(w[q2][m], ops.ll[q2], a);
-          b = fma(w[q2][m], ops.lr[q2], b);
-        }
-        uL[m] = a; uR[m] = b;
-      }
-      // left face: HLL(u_face[i-1,j,2,l,:], u_face[i,j,4,l,:])  (euler2d_wave.jl:69-74)
-      double n0 = __shfl_up_sync(0xffffffffu, uR[0], 1), n1 = __shfl_up_sync(0xffffffffu, uR[1], 1);
-      double n2 = __shfl_up_sync(0xffffffffu, uR[2], 1), n3 = __shfl_up_sync(0xffffffffu, uR[3], 1);
-      frb::Flux4 hl = frb::hll4_fast(n0, n1, n2, n3, uL[0], uL[1], uL[2], uL[3], gamma, gm1);
-      const double hL[4] = {hl.f0, hl.f1, hl.f2, hl.f3};
-      const double hR[4] = {__shfl_down_sync(0xffffffffu, hl.f0, 1), __shfl_down_sync(0xffffffffu, hl.f1, 1),
-                            __shfl_down_sync(0xffffffffu, hl.f2, 1), __shfl_down_sync(0xffffffffu, hl.f3, 1)};
-      // cb*u + (-cdt/Jx) * (d/dr + correction), flux traces folded into dmx (see MarchOps)
-#pragma unroll
-      for (int m = 0; m < 4; ++m)
-#pragma unroll
-        for (int k = 0; k < NSP; ++k) {
-          // re-read (volatile: no CSE with the loads above) keeps u out of the HLL's live set
-          double d = P.cb * w[k][m];
-#pragma unroll
-          for (int q2 = 0; q2 < NSP; ++q2) d = fma(f[q2][m], ops.dmx[k * 4 + q2], d);
-          d = fma(hL[m], ops.glx[k], d);
-          d = fma(hR[m], ops.grx[k], d);
-          xdx[32 * (k + NSP * NSP * m)] = d;
-        }
-    }
+    x_pass<NSP, false>(Ux, xdx, xrpx, ops, P.cb, gamma, gm1);
     __syncthreads();  // (A) xd / xrp of this row visible
 
     // -------------------------------------------------------------- y pass: column k = t
@@ -254,40 +192,12 @@ euler2d_march_kernel(const __grid_constant__ CUtensorMap tmap, MarchParams P, Ma
 #pragma unroll
           for (int l = 0; l < NSP; ++l, pa += pstep) un[l][m] = __ldcs(pa);
       }
-      double g[NSP][4];  // [l][m]
-      double uT[4];
-      {
-        double w[NSP][4];
-#pragma unroll
-        for (int m = 0; m < 4; ++m)
-#pragma unroll
-          for (int l = 0; l < NSP; ++l) w[l][m] = Uy[32 * NSP * (l + NSP * m)];
-#pragma unroll
-        for (int l = 0; l < NSP; ++l) {
-          double vy = xrpy[32 * NSP * l];
-          double p = xrpy[32 * NSP * (NSP + l)];
-          g[l][0] = w[l][2];
-          g[l][1] = w[l][1] * vy;
-          g[l][2] = fma(w[l][2], vy, p);
-          g[l][3] = (w[l][3] + p) * vy;
-        }
-#pragma unroll
-        for (int m = 0; m < 4; ++m) {
-          double a = w[0][m] * ops.lr[0];
-#pragma unroll
-          for (int q2 = 1; q2 < NSP; ++q2) a = fma(w[q2][m], ops.lr[q2], a);
-          uT[m] = a;
-        }
-      }
+      double g[NSP][4];  // G at the column's points, [l][m]
+      double uT[4], ht[4];
+      y_fluxes<NSP>(Uy, xrpy, ops, g, uT);
       // top face of row j: HLL between this row's top trace and row j+1's bottom trace
       mbar_wait(&S.bar[nbuf], ((q + 1) / NBUF) & 1);
-      double ht[4];
-      {
-        double uB[4];
-        col_trace<NSP>(S.tile[0] + nbuf * kTile + offy, ops.ll, uB);
-        frb::Flux4 h = frb::hll4_y_fast(uT[0], uT[1], uT[2], uT[3], uB[0], uB[1], uB[2], uB[3], gamma, gm1);
-        ht[0] = h.f0; ht[1] = h.f1; ht[2] = h.f2; ht[3] = h.f3;
-      }
+      face_flux_y<NSP>(uT, S.tile[0] + nbuf * kTile + offy, ops, gamma, gm1, ht);
       // four independent FMA chains per variable, stored as soon as they retire
       double *po = P.out + grow;
 #pragma unroll
@@ -295,11 +205,7 @@ euler2d_march_kernel(const __grid_constant__ CUtensorMap tmap, MarchParams P, Ma
         double v[NSP];
 #pragma unroll
         for (int l = 0; l < NSP; ++l) {
-          double d = xdy[32 * NSP * (l + NSP * m)];
-#pragma unroll
-          for (int q2 = 0; q2 < NSP; ++q2) d = fma(g[q2][m], (SAMEJ ? ops.dmx : ops.dmy)[l * 4 + q2], d);
-          d = fma(hb[m], (SAMEJ ? ops.glx : ops.gly)[l], d);
-          d = fma(ht[m], (SAMEJ ? ops.grx : ops.gry)[l], d);
+          double d = y_value<NSP, SAMEJ>(xdy[32 * NSP * (l + NSP * m)], g, hb[m], ht[m], ops, l, m);
           if (USEA) d = fma(P.ca, un[l][m], d);
           v[l] = d;
         }
