@@ -102,29 +102,6 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
-def bind_to_gpu_numa(device):
-    """Run this rank (and first-touch its pinned host buffers) on the CPUs local to its GPU:
-    with 8 ranks the host-buffer path otherwise crosses the socket interconnect."""
-    try:
-        bus = subprocess.run(["nvidia-smi", "--query-gpu=pci.bus_id", "--format=csv,noheader", "-i", str(device)],
-                             capture_output=True, text=True, timeout=20).stdout.strip().lower()
-        if bus.startswith("00000000:"):
-            bus = bus[4:]
-        with open(f"/sys/bus/pci/devices/{bus}/local_cpulist") as fh:
-            spec = fh.read().strip()
-        cpus = set()
-        for part in spec.split(","):
-            a, _, b = part.partition("-")
-            cpus.update(range(int(a), int(b or a) + 1))
-        cpus &= os.sched_getaffinity(0)
-        if cpus:
-            os.sched_setaffinity(0, cpus)
-            return spec
-    except Exception:
-        pass
-    return None
-
-
 def make_ic(FR, n, ny_local, y_offset_rows, ny_global):
     """isentropic x wave of euler2d_wave.jl:115-120 on this rank's slab (host, NumPy)."""
     import numpy as np
@@ -203,6 +180,12 @@ def run_reference(args):
 def run_ours(args):
     import numpy as np
 
+    # stdout carries exactly one JSON line: everything libraries print while the job runs (NCCL's
+    # version banner goes to fd 1) is sent to stderr, the line is written to the saved descriptor
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
+
     import frb200 as FR
 
     rank = int(os.environ.get("RANK", "0"))
@@ -213,12 +196,9 @@ def run_ours(args):
         import torch
         import torch.distributed as dist_mod
 
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-            os.environ["NCCL_DEBUG"] = "WARN"  # keep stdout to the one JSON line
         torch.cuda.set_device(local)
         dist_mod.init_process_group("nccl", device_id=torch.device("cuda", local))
         dist = dist_mod
-    numa = bind_to_gpu_numa(local) if world > 1 else None
     n = args.n
     ny_global = n * world
     ps, u0 = make_ic(FR, n, n, rank * n, ny_global)
@@ -287,8 +267,6 @@ def run_ours(args):
                    "host buffers; upload, fused residual and download overlapped in row slabs"
                    + (f"; {world} ranks, one slab each, concurrently" if world > 1 else ""),
            "ms_per_call": 1e3 * el / k}
-    if numa:
-        e2e["host_cpus_rank0"] = numa
     FR.pinned_free(uh)
     FR.pinned_free(dh)
 
@@ -312,7 +290,8 @@ def run_ours(args):
         }
         if world == 1 and not args.no_cpu:
             out["cpu_baseline"] = cpu_baseline(args.cpu_n, args.cpu_evals)
-        print(json.dumps(out))
+        sys.stdout.flush()
+        os.write(json_fd, (json.dumps(out) + "\n").encode())
     prob.close()
     if dist is not None:
         dist.destroy_process_group()

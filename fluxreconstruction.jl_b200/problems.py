@@ -116,9 +116,13 @@ class _Problem:
         check(lib().frb_rhs_pipelined(self.h, fortran_ptr(u), fortran_ptr(du), int(nslab)))
         return None
 
-    def rhs_resident(self):
-        """L(u) of the resident state, left on the device (timing / chaining)."""
-        check(lib().frb_rhs(self.h, None, None, 0.0))
+    def rhs_resident(self, du=None):
+        """L(u) of the resident state; left on the device (timing / chaining) unless ``du`` (a host
+        array of the state's shape) is given."""
+        if du is not None and du.shape != self.u0.shape:
+            raise ValueError("f!: array shape does not match the problem")
+        check(lib().frb_rhs(self.h, None, None if du is None else fortran_ptr(du), 0.0))
+        return du
 
     # -- state --------------------------------------------------------------------------
     def upload(self, u):

@@ -562,3 +562,23 @@ def test_modal_filter_2d_and_hook(FR, oracle, coracle):
         oracle.filter_pass_2d(ref, ps.V, ps.iV, ps.deg, 5e-4)
     assert rel(itg.u, ref) <= 1e-12
     prob.close()
+
+
+def test_euler2d_reference_image_calls_after_row_chunk_steps(FR, oracle, coracle):
+    """frb_step leaves the state in the row-chunk mirror; f!(du) on the resident state, the limiter,
+    ghost fill and download all see the current state (lazy conversion), and stepping resumes."""
+    ps = FR.FRPSpace2D(0.0, 1.0, 64, 0.0, 1.0, 40, 3, 1, 1)
+    u0 = noisy(oracle.ic_wave2d(ps, GAMMA, "x"), 0.01, 41)
+    prob = FR.Euler2DProblem(u0, (0.0, 0.5), ps, GAMMA)
+    itg = FR.init(prob, FR.SSPRK33(), dt=1e-4)
+    itg.set_hooks(ghost="wave_x")
+    prob.step(FR.SSPRK33(), 1e-4, 4)
+    ref = coracle.integrate_euler2d(u0, ps, GAMMA, 1e-4, 4, "ssprk3", "wave_x")
+    du = prob.rhs_resident(np.zeros_like(u0, order="F"))  # residual of the resident (row-chunk) state
+    assert rel(du, coracle.rhs_euler2d(ref, ps, GAMMA)) <= 1e-11
+    prob.ghost_fill("wave_y")  # writes the reference image: the mirror must be refreshed afterwards
+    oracle.ghost_fill_euler2d(ref, "wave_y")
+    prob.step(FR.SSPRK33(), 1e-4, 2)
+    ref = coracle.integrate_euler2d(ref, ps, GAMMA, 1e-4, 2, "ssprk3", "wave_x")
+    assert rel(prob.download(), ref) <= 1e-12
+    prob.close()
