@@ -155,7 +155,7 @@ extern "C" int32_t frb_prob_destroy(frb_prob_t p) {
   frb_march_release(p);
   cudaFree(p->u); cudaFree(p->s1); cudaFree(p->s2); cudaFree(p->du); cudaFree(p->rc_base);
   cudaFree(p->J); cudaFree(p->velo); cudaFree(p->weights); cudaFree(p->prim);
-  cudaFree(p->lim_w); cudaFree(p->flag); cudaFree(p->filt);
+  cudaFree(p->lim_w); cudaFree(p->flag); cudaFree(p->filt); cudaFree(p->ns_flux);
   if (p->ev0) cudaEventDestroy(p->ev0);
   if (p->ev1) cudaEventDestroy(p->ev1);
   for (cudaEvent_t e : p->prof_events) cudaEventDestroy(e);

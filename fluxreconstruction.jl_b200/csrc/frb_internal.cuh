@@ -81,6 +81,7 @@ struct frb_prob_s {
   bool ref_valid = true, rc_valid = false;
   double *J = nullptr;              // 1-D per-cell Jacobian / bgk dx
   double *velo = nullptr, *weights = nullptr, *prim = nullptr;  // bgk
+  double *ns_flux = nullptr;        // ns2d: common fluxes on the x | y faces (lazy)
   double *lim_w = nullptr;          // limiter weights (device)
   // shock sensor + modal filter hook (frb_set_filter_hook): iV | F on the device, when = 0 off,
   // 1 before every step (euler_highlevel.jl:37-52), 2 after every step (shock-vortex.jl:308-321)

@@ -4,10 +4,18 @@
 // contiguous: 4*nsp^2 doubles; ns_cavity.jl:33).
 //
 // The path is FP64-compute-bound (erfc, exp, pow and ~2 k flops per interface point), not
-// HBM-bound: one thread owns one element, keeps its nsp^2 x 4 block in registers/local memory,
-// recomputes the four neighbour traces and slopes it needs, and evaluates the interface flux
-// on its own four faces (each interface is therefore evaluated by both neighbours -- the
-// price of a single pass without a flux round trip through HBM).
+// HBM-bound, so it is split the way the north star words it and the round trip of the common
+// fluxes through HBM (268 MB at 1024^2, p3) is the cheap part:
+//   ns_boundary_kernel   boundary!: mirrored isothermal-wall ghost states (per stage, as in :148)
+//   ns_face_kernel       thread = (face, flux point): the two neighbours' traces and edge slopes
+//                        (dll / dlr) and the two-state, time-averaged GKS flux -- each interface is
+//                        evaluated ONCE, by a thread that owns nothing else
+//   ns_elem_kernel       thread = (element, solution point): point fluxes (shared through smem
+//                        inside the element), lpdm derivative, dgl/dgr correction with the stored
+//                        common fluxes, 1/J, and the RK stage -- one 32-B row of the state per
+//                        thread, fully coalesced.
+// (The first version did everything with one thread per element: 255 registers, 2.6 KB of local
+// memory, every interface flux computed by both neighbours -- 8.6 ms per stage at 1024^2 p3.)
 //
 // [KB] closures restated from KitBase.jl 0.9: gauss_moments, moments_conserve,
 // moments_conserve_slope, pdf_slope, vhs_collision_time.  Reference quirks kept: the left
@@ -33,11 +41,14 @@ __device__ __forceinline__ Prim4 conserve_prim(const double *w, double gm1) {
 struct Moments {
   double Mu[7], Mv[7], Mxi[3];
 };
+// (the recurrences multiply by h = 1/(2 lambda) instead of dividing by lambda: one reciprocal per
+// state instead of fifteen IEEE divisions; well inside the 1e-12 parity bound)
 __device__ __forceinline__ void moments_v(double V, double lam, double *Mv) {
+  const double h = 0.5 / lam;
   Mv[0] = 1.0;
   Mv[1] = V;
 #pragma unroll
-  for (int i = 2; i <= 6; ++i) Mv[i] = V * Mv[i - 1] + 0.5 * (i - 1) * Mv[i - 2] / lam;
+  for (int i = 2; i <= 6; ++i) Mv[i] = V * Mv[i - 1] + (i - 1) * h * Mv[i - 2];
 }
 __device__ __forceinline__ void moments_half(double U, double lam, double *MuL, double *MuR) {
   const double sl = sqrt(lam);
@@ -46,10 +57,11 @@ __device__ __forceinline__ void moments_half(double U, double lam, double *MuL, 
   MuL[1] = U * MuL[0] + e;
   MuR[0] = 0.5 * erfc(sl * U);
   MuR[1] = U * MuR[0] - e;
+  const double h = 0.5 / lam;
 #pragma unroll
   for (int i = 2; i <= 6; ++i) {
-    MuL[i] = U * MuL[i - 1] + 0.5 * (i - 1) * MuL[i - 2] / lam;
-    MuR[i] = U * MuR[i - 1] + 0.5 * (i - 1) * MuR[i - 2] / lam;
+    MuL[i] = U * MuL[i - 1] + (i - 1) * h * MuL[i - 2];
+    MuR[i] = U * MuR[i - 1] + (i - 1) * h * MuR[i - 2];
   }
 }
 __device__ __forceinline__ void mxi(double K, double lam, double *M) {
@@ -116,7 +128,7 @@ __device__ __forceinline__ void gks_point_fluxes(const double *w, const GasPar &
 
 // flux_gks!(fw, wL, wR, K, gamma, mu, omega, dt, swL, swR)  (ns_cavity.jl:75-145), states in the
 // face-normal frame
-__device__ __noinline__ void gks_face_flux(double *fw, const double *wL, const double *wR,
+__device__ __forceinline__ void gks_face_flux(double *fw, const double *wL, const double *wR,
                                            const double *swL, const double *swR, GasPar g) {
   const double gm1 = g.gamma - 1.0;
   const Prim4 pL = conserve_prim(wL, gm1), pR = conserve_prim(wR, gm1);
@@ -205,128 +217,114 @@ __global__ void ns_boundary_kernel(double *__restrict__ u, int nx, int ny, doubl
     }
 }
 
+// ---- common fluxes: one thread per (face, flux point) ------------------------------------
+// x faces: i = 1..nx+1 (between cells i-1 | i), j = 1..ny, row l     -> fhx[m + 4*(l + NSP*(j-1 + ny*(i-1)))]
+// y faces: i = 1..nx, j = 1..ny+1 (between cells j-1 | j), column k  -> fhy[m + 4*(k + NSP*(j-1 + (ny+1)*(i-1)))]
+// ns_cavity.jl:208-237 and :239-262 (states rotated by local_frame(., 0, 1) on y faces; slopes are not)
 template <int NSP>
-__global__ void __launch_bounds__(64)
-ns2d_kernel(const double *__restrict__ u, const double *__restrict__ ua, double *__restrict__ out,
-            int nx, int ny, double Jx, double Jy, GasPar gas, FrbOps ops, FrbStage st) {
-  const int j = blockIdx.x * blockDim.x + threadIdx.x + 1;
-  const int i = blockIdx.y + 1;
-  if (j > ny) return;
+__global__ void __launch_bounds__(128, 4)
+ns_face_kernel(const double *__restrict__ u, double *__restrict__ fhx, double *__restrict__ fhy, int nx, int ny,
+               double Jx, double Jy, GasPar gas, FrbOps ops) {
+  const long long nfx = (long long)NSP * ny * (nx + 1), nfy = (long long)NSP * (ny + 1) * nx;
+  long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (t >= nfx + nfy) return;
   const int nyg = ny + 2;
-  const double *e0 = u + eoff<NSP>(j, i, nyg);
-  const double *eL = u + eoff<NSP>(j, i - 1, nyg), *eR = u + eoff<NSP>(j, i + 1, nyg);
-  const double *eB = u + eoff<NSP>(j - 1, i, nyg), *eT = u + eoff<NSP>(j + 1, i, nyg);
-#define W(e, m, l, k) (e)[(m) + 4 * ((l) + NSP * (k))]
-  double fx[NSP][NSP][4], fy[NSP][NSP][4];  // [l][k][m], already divided by Jx / Jy
+  const bool yface = t >= nfx;
+  if (yface) t -= nfx;
+  const int r = (int)(t % NSP);  // flux point along the face
+  t /= NSP;
+  const int rows = yface ? ny + 1 : ny;
+  const int j = (int)(t % rows) + 1, i = (int)(t / rows) + 1;
+  // "left" = lower cell in the face-normal direction
+  const double *eA = u + eoff<NSP>(yface ? j - 1 : j, yface ? i : i - 1, nyg);
+  const double *eB = u + eoff<NSP>(j, i, nyg);
+  // stride of the contracted index and offset of the fixed one inside an element block
+  const int sq = yface ? 4 : 4 * NSP, base = yface ? 4 * NSP * r : 4 * r;
+  const double iJ = 1.0 / (yface ? Jy : Jx);
+  double wA[4], wB[4], sA[4], sB[4];
 #pragma unroll
-  for (int k = 0; k < NSP; ++k)
+  for (int m = 0; m < 4; ++m) {
+    double a = 0, b = 0, c = 0, d = 0;
 #pragma unroll
-    for (int l = 0; l < NSP; ++l) {  // ns_cavity.jl:169-187
-      double w[4] = {W(e0, 0, l, k), W(e0, 1, l, k), W(e0, 2, l, k), W(e0, 3, l, k)}, F[4], G[4];
-      gks_point_fluxes(w, gas, F, G);
-#pragma unroll
-      for (int m = 0; m < 4; ++m) { fx[l][k][m] = F[m] / Jx; fy[l][k][m] = G[m] / Jy; }
+    for (int q = 0; q < NSP; ++q) {
+      const double va = eA[base + sq * q + m], vb = eB[base + sq * q + m];
+      a += va * ops.lr[q];   // trace of the lower cell on its upper face
+      b += vb * ops.ll[q];   // trace of the upper cell on its lower face
+      c += va * ops.dll[q];  // swL (the left cell's slope uses dll, :213)
+      d += vb * ops.dlr[q];  // swR (:214)
     }
-  double du[NSP][NSP][4];
-#pragma unroll
-  for (int k = 0; k < NSP; ++k)
-#pragma unroll
-    for (int l = 0; l < NSP; ++l)
-#pragma unroll
-      for (int m = 0; m < 4; ++m) {  // :264-267
-        double r1 = 0.0, r2 = 0.0;
-#pragma unroll
-        for (int q = 0; q < NSP; ++q) {
-          r1 += fx[l][q][m] * ops.lpdm[k * FRB_NSPMAX + q];
-          r2 += fy[q][k][m] * ops.lpdm[l * FRB_NSPMAX + q];
-        }
-        du[l][k][m] = r1 + r2;
-      }
-  // x faces of row l: left interface (cells i-1 | i) and right interface (i | i+1)  :208-237
-  for (int l = 0; l < NSP; ++l) {
-    double uL[4], uR[4], fL[4], fR[4], nL[4], nR[4], s_own_l[4], s_own_r[4], s_nl[4], s_nr[4];
-#pragma unroll
-    for (int m = 0; m < 4; ++m) {
-      double a = 0, b = 0, c = 0, d = 0, g = 0, h = 0, p = 0, q2 = 0, r = 0, s = 0;
-#pragma unroll
-      for (int q = 0; q < NSP; ++q) {
-        const double w0 = W(e0, m, l, q);
-        a += w0 * ops.ll[q]; b += w0 * ops.lr[q];
-        c += fx[l][q][m] * ops.ll[q]; d += fx[l][q][m] * ops.lr[q];
-        g += W(eL, m, l, q) * ops.lr[q];   // ux_face[:,2,l,j,i-1]
-        h += W(eR, m, l, q) * ops.ll[q];   // ux_face[:,1,l,j,i+1]
-        p += w0 * ops.dlr[q];              // swR of the left interface (own cell is the right cell)
-        q2 += w0 * ops.dll[q];             // swL of the right interface (own cell is the left cell)
-        r += W(eL, m, l, q) * ops.dll[q];  // swL of the left interface
-        s += W(eR, m, l, q) * ops.dlr[q];  // swR of the right interface
-      }
-      uL[m] = a; uR[m] = b; fL[m] = c; fR[m] = d; nL[m] = g; nR[m] = h;
-      s_own_r[m] = p / Jx; s_own_l[m] = q2 / Jx; s_nl[m] = r / Jx; s_nr[m] = s / Jx;
-    }
-    double hl[4], hr[4];
-    gks_face_flux(hl, nL, uL, s_nl, s_own_r, gas);
-    gks_face_flux(hr, uR, nR, s_own_l, s_nr, gas);
-#pragma unroll
-    for (int m = 0; m < 4; ++m) {
-      const double cl = hl[m] / Jx - fL[m], cr = hr[m] / Jx - fR[m];
-#pragma unroll
-      for (int k = 0; k < NSP; ++k) du[l][k][m] += cl * ops.dgl[k] + cr * ops.dgr[k];  // :271-274
-    }
+    wA[m] = a; wB[m] = b; sA[m] = c * iJ; sB[m] = d * iJ;
   }
-  // y faces of column k  :239-262 (states rotated by local_frame(.,0,1); slopes are not)
-  for (int k = 0; k < NSP; ++k) {
-    double uB[4], uT[4], gB[4], gT[4], nB[4], nT[4], s_own_t[4], s_own_b[4], s_nb[4], s_nt[4];
-#pragma unroll
-    for (int m = 0; m < 4; ++m) {
-      double a = 0, b = 0, c = 0, d = 0, g = 0, h = 0, p = 0, q2 = 0, r = 0, s = 0;
-#pragma unroll
-      for (int q = 0; q < NSP; ++q) {
-        const double w0 = W(e0, m, q, k);
-        a += w0 * ops.ll[q]; b += w0 * ops.lr[q];
-        c += fy[q][k][m] * ops.ll[q]; d += fy[q][k][m] * ops.lr[q];
-        g += W(eB, m, q, k) * ops.lr[q];   // uy_face[:,2,k,j-1,i]
-        h += W(eT, m, q, k) * ops.ll[q];   // uy_face[:,1,k,j+1,i]
-        p += w0 * ops.dlr[q];
-        q2 += w0 * ops.dll[q];
-        r += W(eB, m, q, k) * ops.dll[q];
-        s += W(eT, m, q, k) * ops.dlr[q];
-      }
-      uB[m] = a; uT[m] = b; gB[m] = c; gT[m] = d; nB[m] = g; nT[m] = h;
-      s_own_t[m] = p / Jy; s_own_b[m] = q2 / Jy; s_nb[m] = r / Jy; s_nt[m] = s / Jy;
-    }
-    // local_frame(w, 0, 1) = (w0, w2, -w1, w3);  global_frame(f, 0, 1) = (f0, -f2, f1, f3)
-    double lb[4] = {nB[0], nB[2], -nB[1], nB[3]}, rb[4] = {uB[0], uB[2], -uB[1], uB[3]};
-    double lt[4] = {uT[0], uT[2], -uT[1], uT[3]}, rt[4] = {nT[0], nT[2], -nT[1], nT[3]};
-    double hb[4], ht[4];
-    gks_face_flux(hb, lb, rb, s_nb, s_own_t, gas);
-    gks_face_flux(ht, lt, rt, s_own_b, s_nt, gas);
-    const double hbg[4] = {hb[0], -hb[2], hb[1], hb[3]}, htg[4] = {ht[0], -ht[2], ht[1], ht[3]};
-#pragma unroll
-    for (int m = 0; m < 4; ++m) {
-      const double cb = hbg[m] / Jy - gB[m], ct = htg[m] / Jy - gT[m];
-#pragma unroll
-      for (int l = 0; l < NSP; ++l) du[l][k][m] += cb * ops.dgl[l] + ct * ops.dgr[l];  // :275-278
-    }
+  double fw[4];
+  if (yface) {  // local_frame(w, 0, 1) = (w0, w2, -w1, w3); global_frame(f, 0, 1) = (f0, -f2, f1, f3)
+    const double lA[4] = {wA[0], wA[2], -wA[1], wA[3]}, lB[4] = {wB[0], wB[2], -wB[1], wB[3]};
+    double h[4];
+    gks_face_flux(h, lA, lB, sA, sB, gas);
+    fw[0] = h[0]; fw[1] = -h[2]; fw[2] = h[1]; fw[3] = h[3];
+  } else {
+    gks_face_flux(fw, wA, wB, sA, sB, gas);
   }
-  double *o = out + eoff<NSP>(j, i, nyg);
-  const double *a0 = ua ? ua + eoff<NSP>(j, i, nyg) : nullptr;
+  double *o = yface ? fhy + 4 * (r + NSP * ((long long)(j - 1) + (long long)(ny + 1) * (i - 1)))
+                    : fhx + 4 * (r + NSP * ((long long)(j - 1) + (long long)ny * (i - 1)));
+  o[0] = fw[0]; o[1] = fw[1]; o[2] = fw[2]; o[3] = fw[3];
+}
+
+// ---- element kernel: thread = (solution point, element); a block holds EPB consecutive cells of a
+// column of the mesh (j fastest in memory)
+template <int NSP, int EPB>
+__global__ void __launch_bounds__(NSP * NSP * EPB)
+ns_elem_kernel(const double *__restrict__ u, const double *__restrict__ ua, double *__restrict__ out,
+               const double *__restrict__ fhx, const double *__restrict__ fhy, int nx, int ny, double Jx,
+               double Jy, GasPar gas, FrbOps ops, FrbStage st) {
+  constexpr int NP = NSP * NSP;
+  __shared__ double sF[EPB][NP][4], sG[EPB][NP][4];  // point fluxes / J of the block's elements
+  const int pt = threadIdx.x % NP, el = threadIdx.x / NP;
+  const int l = pt % NSP, k = pt / NSP;  // state index m + 4*(l + NSP*k)
+  const int j = blockIdx.x * EPB + el + 1, i = blockIdx.y + 1;
+  const int nyg = ny + 2;
+  const bool live = j <= ny;
+  double w[4] = {1.0, 0.0, 0.0, 1.0};
+  const size_t eo = eoff<NSP>(live ? j : ny, i, nyg) + 4 * pt;
+  if (live) {
 #pragma unroll
-  for (int k = 0; k < NSP; ++k)
+    for (int m = 0; m < 4; ++m) w[m] = u[eo + m];
+  }
+  {
+    double F[4], G[4];  // ns_cavity.jl:169-187
+    gks_point_fluxes(w, gas, F, G);
 #pragma unroll
-    for (int l = 0; l < NSP; ++l)
+    for (int m = 0; m < 4; ++m) { sF[el][pt][m] = F[m] / Jx; sG[el][pt][m] = G[m] / Jy; }
+  }
+  __syncthreads();
+  if (!live) return;
+  const double *hl = fhx + 4 * (l + NSP * ((long long)(j - 1) + (long long)ny * (i - 1)));
+  const double *hr = fhx + 4 * (l + NSP * ((long long)(j - 1) + (long long)ny * i));
+  const double *hb = fhy + 4 * (k + NSP * ((long long)(j - 1) + (long long)(ny + 1) * (i - 1)));
+  const double *ht = fhy + 4 * (k + NSP * ((long long)j + (long long)(ny + 1) * (i - 1)));
+  const double *a0 = ua ? ua + eo : nullptr;
 #pragma unroll
-      for (int m = 0; m < 4; ++m) {
-        const int q = m + 4 * (l + NSP * k);
-        const double d = -du[l][k][m];
-        double r;
-        if (st.rhs_only) r = d;
-        else {
-          r = st.nested ? st.cb * (e0[q] + st.cdt * d) : st.cb * e0[q] + st.cdt * d;
-          if (st.use_a) r = st.ca * a0[q] + r;
-        }
-        o[q] = r;
-      }
-#undef W
+  for (int m = 0; m < 4; ++m) {
+    double r1 = 0.0, r2 = 0.0, fL = 0.0, fR = 0.0, gB = 0.0, gT = 0.0;
+#pragma unroll
+    for (int q = 0; q < NSP; ++q) {
+      const double fx = sF[el][l + NSP * q][m], fy = sG[el][q + NSP * k][m];
+      r1 += fx * ops.lpdm[k * FRB_NSPMAX + q];  // :264-267
+      r2 += fy * ops.lpdm[l * FRB_NSPMAX + q];
+      fL += fx * ops.ll[q]; fR += fx * ops.lr[q];
+      gB += fy * ops.ll[q]; gT += fy * ops.lr[q];
+    }
+    double du = r1 + r2;
+    du += (hl[m] / Jx - fL) * ops.dgl[k] + (hr[m] / Jx - fR) * ops.dgr[k];  // :271-274
+    du += (hb[m] / Jy - gB) * ops.dgl[l] + (ht[m] / Jy - gT) * ops.dgr[l];  // :275-278
+    const double d = -du;
+    double r;
+    if (st.rhs_only) r = d;
+    else {
+      r = st.nested ? st.cb * (w[m] + st.cdt * d) : st.cb * w[m] + st.cdt * d;
+      if (st.use_a) r = st.ca * a0[m] + r;
+    }
+    out[eo + m] = r;
+  }
 }
 
 // the stage combination on the ghost ring (du = 0 there): dst = ca*ua + cb*src on whole ghost
@@ -382,8 +380,16 @@ int frb_launch_ns2d(frb_prob_t p, const double *u, const double *ua, double *out
     n += 1;
   }
   GasPar gas = {p->gks_K, p->gamma, p->gks_mu, p->gks_omega, p->gks_dt};
-  dim3 blk(64), grd((p->ny + 63) / 64, p->nx);
-  FRB_NS_SWITCH(p->nsp, (ns2d_kernel<N><<<grd, blk, 0, s>>>(u, ua, out, p->nx, p->ny, p->Jx, p->Jy, gas, p->ops, st)));
-  if (int rc = check_launch("ns2d_kernel")) return rc;
-  return n + 1;
+  const long long nfx = (long long)p->nsp * p->ny * (p->nx + 1), nfy = (long long)p->nsp * (p->ny + 1) * p->nx;
+  if (!p->ns_flux) FRB_CUDA(cudaMalloc(&p->ns_flux, sizeof(double) * 4 * (nfx + nfy)));
+  double *fhx = p->ns_flux, *fhy = p->ns_flux + 4 * nfx;
+  dim3 fb(128), fg((unsigned)((nfx + nfy + 127) / 128));
+  FRB_NS_SWITCH(p->nsp, (ns_face_kernel<N><<<fg, fb, 0, s>>>(u, fhx, fhy, p->nx, p->ny, p->Jx, p->Jy, gas, p->ops)));
+  if (int rc = check_launch("ns_face_kernel")) return rc;
+  constexpr int EPB = 8;
+  dim3 grd((p->ny + EPB - 1) / EPB, p->nx);
+  FRB_NS_SWITCH(p->nsp, (ns_elem_kernel<N, EPB><<<grd, N * N * EPB, 0, s>>>(u, ua, out, fhx, fhy, p->nx, p->ny, p->Jx,
+                                                                          p->Jy, gas, p->ops, st)));
+  if (int rc = check_launch("ns_elem_kernel")) return rc;
+  return n + 2;
 }
