@@ -303,13 +303,14 @@ static int launch_march(frb_prob_t p, const CUtensorMap &map, MarchParams mp, co
   const int strips = (p->nx + kOwn - 1) / kOwn;
   const int segs = (mp.jhi - mp.jlo + 1 + mp.rows_per_seg - 1) / mp.rows_per_seg;
   const size_t smem = sizeof(Smem<NSP, NBUF>) + 128;
-  static bool attr_done = false;
-  if (!attr_done) {
+  static unsigned long long attr_done = 0;  // per device: the attribute belongs to the device's copy of the kernel
+  const unsigned long long dev_bit = 1ull << (p->ctx->device & 63);
+  if (!(attr_done & dev_bit)) {
     FRB_CUDA(cudaFuncSetAttribute(euler2d_march_kernel<NSP, NBUF, MINB, PREFETCH, USEA, SAMEJ, COPYONLY>,
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     FRB_CUDA(cudaFuncSetAttribute(euler2d_march_kernel<NSP, NBUF, MINB, PREFETCH, USEA, SAMEJ, COPYONLY>,
                                   cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-    attr_done = true;
+    attr_done |= dev_bit;
   }
   dim3 grd(strips, segs), blk(NSP * 32);
   euler2d_march_kernel<NSP, NBUF, MINB, PREFETCH, USEA, SAMEJ, COPYONLY><<<grd, blk, smem, p->ctx->stream>>>(map, mp, mo);

@@ -228,13 +228,14 @@ int launch_rc(frb_prob_t p, RcParams rp, const MarchOps &mo) {
   rp.rows_per_seg = rc_rows_per_seg(p, rp.g, MINB, USEA);
   const int segs = (rp.g.ny + rp.rows_per_seg - 1) / rp.rows_per_seg;
   const size_t smem = sizeof(SmemRc<NSP, NBUF, USEA>) + 128;
-  static bool attr_done = false;
-  if (!attr_done) {
+  static unsigned long long attr_done = 0;  // per device: the attribute belongs to the device's copy of the kernel
+  const unsigned long long dev_bit = 1ull << (p->ctx->device & 63);
+  if (!(attr_done & dev_bit)) {
     FRB_CUDA(cudaFuncSetAttribute(euler2d_rc_kernel<NSP, USEA, SAMEJ, MINB, CB1>,
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     FRB_CUDA(cudaFuncSetAttribute(euler2d_rc_kernel<NSP, USEA, SAMEJ, MINB, CB1>,
                                   cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-    attr_done = true;
+    attr_done |= dev_bit;
   }
   dim3 grd(rp.g.ns, segs), blk(NSP * 32);
   euler2d_rc_kernel<NSP, USEA, SAMEJ, MINB, CB1><<<grd, blk, smem, p->ctx->stream>>>(rp, mo);
