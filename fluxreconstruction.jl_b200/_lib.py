@@ -47,6 +47,8 @@ SIGNATURES = {
                                      C.c_double, C.POINTER(C.c_void_p)]),
     "frb_ns2d_create": (C.c_int32, [C.c_void_p, C.c_int32, C.c_int32, C.POINTER(Operators)] + [C.c_double] * 9
                         + [C.POINTER(C.c_void_p)]),
+    "frb_tri_euler_create": (C.c_int32, [C.c_void_p, C.c_int32, C.c_int32, C.POINTER(C.c_int32), c_dp, c_dp,
+                                         C.POINTER(C.c_int32), c_dp, c_dp, c_dp, C.c_double, C.POINTER(C.c_void_p)]),
     "frb_prob_destroy": (C.c_int32, [C.c_void_p]),
     "frb_state_len": (C.c_int64, [C.c_void_p]),
     "frb_interior_dofs": (C.c_int64, [C.c_void_p]),

@@ -156,6 +156,7 @@ extern "C" int32_t frb_prob_destroy(frb_prob_t p) {
   cudaFree(p->u); cudaFree(p->s1); cudaFree(p->s2); cudaFree(p->du); cudaFree(p->rc_base);
   cudaFree(p->J); cudaFree(p->velo); cudaFree(p->weights); cudaFree(p->prim);
   cudaFree(p->lim_w); cudaFree(p->flag); cudaFree(p->filt); cudaFree(p->ns_flux);
+  cudaFree(p->tri_ops); cudaFree(p->tri_uf); cudaFree(p->tri_normals); cudaFree(p->tri_type); cudaFree(p->tri_fpn);
   if (p->ev0) cudaEventDestroy(p->ev0);
   if (p->ev1) cudaEventDestroy(p->ev1);
   for (cudaEvent_t e : p->prof_events) cudaEventDestroy(e);
@@ -271,6 +272,42 @@ extern "C" int32_t frb_ns2d_create(frb_ctx_t ctx, int32_t nx, int32_t ny, const 
   return FRB_OK;
 }
 
+extern "C" int32_t frb_tri_euler_create(frb_ctx_t ctx, int32_t ncell, int32_t deg, const int32_t *cell_type,
+                                        const double *J, const double *normals, const int32_t *fpn,
+                                        const double *lf, const double *dl, const double *phi, double gamma,
+                                        frb_prob_t *out) {
+  FRB_REQUIRE(ctx && out && cell_type && J && normals && fpn && lf && dl && phi, FRB_ERR_ARG,
+              "frb_tri_euler_create: NULL argument");
+  FRB_REQUIRE(ncell >= 1 && deg >= 1 && deg <= 3, FRB_ERR_ARG, "frb_tri_euler_create: ncell >= 1, deg in 1..3");
+  frb_prob_t p = new frb_prob_s();
+  p->ctx = ctx; p->kind = K_TRI_EULER; p->ncell = ncell; p->nsp = deg + 1; p->gamma = gamma;
+  const int np = (deg + 1) * (deg + 2) / 2, nf = deg + 1;
+  p->len = (int64_t)ncell * np * 4;
+  p->dofs = p->len;
+  FRB_TRY(alloc_common(p));
+  auto up = [&](auto **dst, const auto *src, size_t n) -> int {
+    FRB_CUDA(cudaMalloc(dst, sizeof(**dst) * n));
+    FRB_CUDA(cudaMemcpy(*dst, src, sizeof(**dst) * n, cudaMemcpyHostToDevice));
+    return FRB_OK;
+  };
+  FRB_TRY(up(&p->tri_type, cell_type, (size_t)ncell));
+  FRB_TRY(up(&p->J, J, (size_t)ncell * 4));
+  FRB_TRY(up(&p->tri_normals, normals, (size_t)ncell * 6));
+  FRB_TRY(up(&p->tri_fpn, fpn, (size_t)ncell * 3 * nf * 3));
+  std::vector<double> ops;
+  ops.insert(ops.end(), lf, lf + 3 * nf * np);
+  ops.insert(ops.end(), dl, dl + 2 * np * np);
+  ops.insert(ops.end(), phi, phi + 3 * nf * np);
+  FRB_TRY(up(&p->tri_ops, ops.data(), ops.size()));
+  if (cudaMalloc(&p->tri_uf, sizeof(double) * (size_t)ncell * 3 * nf * 4) != cudaSuccess) {
+    frb_prob_destroy(p);
+    frb_set_error("frb_tri_euler_create: cudaMalloc failed");
+    return FRB_ERR_CUDA;
+  }
+  *out = p;
+  return FRB_OK;
+}
+
 extern "C" int64_t frb_state_len(frb_prob_t p) { return p ? p->len : 0; }
 extern "C" int64_t frb_interior_dofs(frb_prob_t p) { return p ? p->dofs : 0; }
 
@@ -378,6 +415,7 @@ static int launch_stage_inner(frb_prob_t p, const double *u, const double *ua, d
                        : frb_launch_euler2d_generic(p, u, ua, out, st);
       break;
     case K_NS2D: n = frb_launch_ns2d(p, u, ua, out, st); break;
+    case K_TRI_EULER: n = frb_launch_tri_euler(p, u, ua, out, st); break;
     default: frb_set_error("unknown problem kind"); return FRB_ERR_STATE;
   }
   if (n > 0) p->launches += n;

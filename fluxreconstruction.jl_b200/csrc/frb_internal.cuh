@@ -33,7 +33,7 @@ struct FrbStage {
   int use_a, rhs_only, nested;
 };
 
-enum FrbKind { K_ADV1D = 0, K_EULER1D = 1, K_EULER2D = 2, K_BGK1D = 3, K_NS2D = 4 };
+enum FrbKind { K_ADV1D = 0, K_EULER1D = 1, K_EULER2D = 2, K_BGK1D = 3, K_NS2D = 4, K_TRI_EULER = 5 };
 
 void frb_set_error(const std::string &msg);
 int frb_cuda_fail(cudaError_t e, const char *what, const char *file, int line);
@@ -81,6 +81,9 @@ struct frb_prob_s {
   bool ref_valid = true, rc_valid = false;
   double *J = nullptr;              // 1-D per-cell Jacobian / bgk dx
   double *velo = nullptr, *weights = nullptr, *prim = nullptr;  // bgk
+  // triangles: operators (lf | dl | phi), flux-point traces, connectivity
+  double *tri_ops = nullptr, *tri_uf = nullptr, *tri_normals = nullptr;
+  int *tri_type = nullptr, *tri_fpn = nullptr;
   double *ns_flux = nullptr;        // ns2d: common fluxes on the x | y faces (lazy)
   double *lim_w = nullptr;          // limiter weights (device)
   // shock sensor + modal filter hook (frb_set_filter_hook): iV | F on the device, when = 0 off,
@@ -129,6 +132,7 @@ int frb_rc_ghost_x(frb_prob_t p, double *u, int mode);
 int frb_rc_ring_copy(frb_prob_t p, const double *src, double *dst, bool row0, bool rowN);
 int frb_rc_limiter2d(frb_prob_t p, double *u);
 int frb_rc_row_push(frb_prob_t p, const double *src, double *dst_lo, double *dst_hi, int nyl_lo, int flip_var);
+int frb_launch_tri_euler(frb_prob_t p, const double *u, const double *ua, double *out, FrbStage st);
 int frb_launch_ns2d(frb_prob_t p, const double *u, const double *ua, double *out, FrbStage st);
 int frb_launch_ghost_fill2d(frb_prob_t p, double *u, int mode);
 int frb_launch_ring_copy2d(frb_prob_t p, const double *src, double *dst, bool row0 = true, bool rowN = true);

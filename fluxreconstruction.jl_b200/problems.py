@@ -412,3 +412,29 @@ class NSCavityProblem(_Problem):
                                     float(mu_ref), float(omega), float(dt), float(lid), float(lambda_wall),
                                     C.byref(self.h)))
         self.upload(self.u0)
+
+
+class TriEulerProblem(_Problem):
+    """ODEProblem(dudt!, u0, tspan, p) of dev/sod.jl:31-130: 2-D Euler on a triangle mesh with
+    p = (ps.cellType, ps.J, ps.lf, ps.cellNormals, ps.fpn, ps.dl, ps.phi, gamma) of a TriFRPSpace
+    (struct.jl:305-352).  u0[ncell, np, 4].  ``fpn`` holds (cell, face, point) per flux point,
+    shape [ncell, 3, deg+1, 3]; ``fpn_base`` = 1 for the reference's 1-based tuples (<= 0: no
+    neighbour), 0 for 0-based arrays with -1."""
+
+    def __init__(self, u0, tspan, cell_type, J, lf, cell_normal, fpn, dl, phi, gamma, fpn_base=1, ctx=None):
+        super().__init__(u0, tspan, ctx)
+        ncell, npts, nv = self.u0.shape
+        deg = lf.shape[1] - 1
+        if nv != 4 or npts != (deg + 1) * (deg + 2) // 2:
+            raise ValueError("u0 must be [ncell, (deg+1)(deg+2)/2, 4]")
+        f32 = lambda a: np.asfortranarray(a, dtype=np.int32)  # noqa: E731
+        f64 = lambda a: np.asfortranarray(a, dtype=np.float64)  # noqa: E731
+        fp = np.asarray(fpn, dtype=np.int64) + (1 - int(fpn_base))  # -> 1-based
+        fp = f32(np.moveaxis(fp, -1, 0))  # [3, ncell, 3, deg+1]: the memory image of Julia's array of tuples
+        keep = [f32(cell_type), f64(J), f64(cell_normal), fp, f64(lf), f64(dl), f64(phi)]
+        ip = lambda a: a.ctypes.data_as(C.POINTER(C.c_int32))  # noqa: E731
+        check(lib().frb_tri_euler_create(self.ctx.h, ncell, deg, ip(keep[0]), fortran_ptr(keep[1]),
+                                         fortran_ptr(keep[2]), ip(keep[3]), fortran_ptr(keep[4]),
+                                         fortran_ptr(keep[5]), fortran_ptr(keep[6]), float(gamma), C.byref(self.h)))
+        self._keep = keep
+        self.upload(self.u0)

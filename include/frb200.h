@@ -108,6 +108,15 @@ int32_t frb_ns2d_create(frb_ctx_t ctx, int32_t nx, int32_t ny, const frb_operato
                         double Jx, double Jy, double inK, double gamma, double mu_ref,
                         double omega, double dt, double lid_u, double lambda_wall,
                         frb_prob_t *out);
+/* 2-D Euler on triangles: dudt! of dev/sod.jl:31-123 with the tuple it receives,
+ * p = (ps.cellType, ps.J, ps.lf, ps.cellNormals, ps.fpn, ps.dl, ps.phi, gamma) of a TriFRPSpace
+ * (struct.jl:305-352).  Julia layouts: cell_type[ncell] (0 interior, 1 frozen boundary, 2 mirror wall);
+ * J[ncell,2,2] (geo_jacobi.jl:32-43, flattened from the vector of matrices); normals[ncell,3,2];
+ * fpn[3, ncell, 3, deg+1] (the tuples (cell, face, point), 1-based, <= 0: no neighbour);
+ * lf[3,deg+1,np]; dl[np,np,2]; phi[3,deg+1,np]; state u[ncell, np, 4]; np = (deg+1)(deg+2)/2, deg 1..3. */
+int32_t frb_tri_euler_create(frb_ctx_t ctx, int32_t ncell, int32_t deg, const int32_t *cell_type, const double *J,
+                             const double *normals, const int32_t *fpn, const double *lf, const double *dl,
+                             const double *phi, double gamma, frb_prob_t *out);
 int32_t frb_prob_destroy(frb_prob_t prob);
 
 /* number of Float64 in the state array / of interior degrees of freedom */

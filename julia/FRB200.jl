@@ -85,6 +85,19 @@ function Euler2DProblem(u0, ps, γ)
 end
 
 # mol! of example/bgk_wave.jl:69-129
+# dev/sod.jl:124-127: p = (ps.cellType, ps.J, ps.lf, ps.cellNormals, ps.fpn, ps.∂l, ps.ϕ, γ) of a TriFRPSpace
+function TriEulerProblem(u0::Array{Float64,3}, ps, γ)
+    ncell = size(u0, 1)
+    J = [ps.J[i][a, b] for i in 1:ncell, a in 1:2, b in 1:2]                 # [ncell,2,2]
+    fpn = Int32[ps.fpn[i, j, k][c] for c in 1:3, i in 1:ncell, j in 1:3, k in 1:ps.deg+1]
+    ct, nrm = Int32.(ps.cellType), Array{Float64}(ps.cellNormals)
+    r = Ref{Ptr{Cvoid}}(C_NULL)
+    GC.@preserve ct J nrm fpn check(ccall((:frb_tri_euler_create, lib), Int32,
+        (Ptr{Cvoid}, Int32, Int32, Ptr{Int32}, Ptr{Float64}, Ptr{Float64}, Ptr{Int32}, Ptr{Float64}, Ptr{Float64},
+         Ptr{Float64}, Float64, Ref{Ptr{Cvoid}}),
+        ctx().h, ncell, ps.deg, ct, J, nrm, fpn, ps.lf, ps.∂l, ps.ϕ, γ, r))
+    p = Problem(r[], size(u0)); upload!(p, u0); p
+end
 function BGKProblem(f0::Array{Float64,3}, ps, velo, weights, τ = 1e-2)
     ops, keep = operators(ps)
     dx = Vector{Float64}(ps.dx[1:size(f0, 1)]); v = Vector{Float64}(velo); w = Vector{Float64}(weights)
