@@ -96,7 +96,7 @@ function TriEulerProblem(u0::Array{Float64,3}, ps, γ)
         (Ptr{Cvoid}, Int32, Int32, Ptr{Int32}, Ptr{Float64}, Ptr{Float64}, Ptr{Int32}, Ptr{Float64}, Ptr{Float64},
          Ptr{Float64}, Float64, Ref{Ptr{Cvoid}}),
         ctx().h, ncell, ps.deg, ct, J, nrm, fpn, ps.lf, ps.∂l, ps.ϕ, γ, r))
-    p = Problem(r[], size(u0)); upload!(p, u0); p
+    p = finalizer(destroy!, Problem(r[], size(u0), Any[ct, J, nrm, fpn])); upload!(p, u0); p
 end
 function BGKProblem(f0::Array{Float64,3}, ps, velo, weights, τ = 1e-2)
     ops, keep = operators(ps)
