@@ -794,6 +794,50 @@ static int need_rc(frb_prob_t p) {
   return FRB_OK;
 }
 
+// The time loop.  Long runs of small problems are launch-bound (cfg1: 2.4 KB of state, 5 us per
+// launch), so from 16 steps on a pair of steps is captured once into a CUDA graph and replayed:
+// two steps because the stage buffers rotate with period 2.  The first two steps run eagerly --
+// they do the lazy allocations, descriptor caches and attribute opt-ins that must not happen inside
+// a capture.  Not used with per-stage profiling (event pairs) or the slab-parallel path (the halo
+// epochs are kernel arguments that change every stage).
+static int run_steps(frb_prob_t p, int scheme, double dt, bool rc, int nsteps) {
+  cudaStream_t s = p->ctx->stream;
+  int it = 0, r;
+  const bool graphable = nsteps >= 16 && !p->profiling && !frb_halo_active(p) && !getenv("FRB_NO_GRAPH");
+  if (graphable) {
+    for (; it < 2; ++it)
+      if ((r = one_step(p, scheme, dt, rc)) < 0) return r;
+    const int pairs = (nsteps - it) / 2;
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t exec = nullptr;
+    FRB_CUDA(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+    const int64_t l0 = p->launches;
+    r = one_step(p, scheme, dt, rc);
+    if (r >= 0) r = one_step(p, scheme, dt, rc);
+    cudaError_t ce = cudaStreamEndCapture(s, &graph);  // always: leaves the stream usable
+    if (r < 0) {
+      if (graph) cudaGraphDestroy(graph);
+      return r;
+    }
+    if (ce != cudaSuccess) return frb_cuda_fail(ce, "cudaStreamEndCapture", __FILE__, __LINE__);
+    const int64_t per_pair = p->launches - l0;
+    ce = cudaGraphInstantiate(&exec, graph, 0);
+    if (ce != cudaSuccess) {
+      cudaGraphDestroy(graph);
+      return frb_cuda_fail(ce, "cudaGraphInstantiate", __FILE__, __LINE__);
+    }
+    for (int q = 0; q < pairs && ce == cudaSuccess; ++q) ce = cudaGraphLaunch(exec, s);
+    cudaGraphExecDestroy(exec);
+    cudaGraphDestroy(graph);
+    if (ce != cudaSuccess) return frb_cuda_fail(ce, "cudaGraphLaunch", __FILE__, __LINE__);
+    p->launches += per_pair * (pairs - 1);
+    it += 2 * pairs;
+  }
+  for (; it < nsteps; ++it)
+    if ((r = one_step(p, scheme, dt, rc)) < 0) return r;
+  return FRB_OK;
+}
+
 extern "C" int32_t frb_step(frb_prob_t p, int32_t scheme, double dt, int32_t nsteps) {
   FRB_REQUIRE(p, FRB_ERR_ARG, "frb_step: prob is NULL");
   FRB_REQUIRE(nsteps >= 0, FRB_ERR_ARG, "frb_step: nsteps must be >= 0");
@@ -812,10 +856,7 @@ extern "C" int32_t frb_step(frb_prob_t p, int32_t scheme, double dt, int32_t nst
   }
   if (p->limiter_on) FRB_CUDA(cudaMemsetAsync(p->flag, 0, sizeof(int), s));
   FRB_CUDA(cudaEventRecord(p->ev0, s));
-  for (int it = 0; it < nsteps; ++it) {
-    int r = one_step(p, scheme, dt, rc);
-    if (r < 0) return r;
-  }
+  if (int r = run_steps(p, scheme, dt, rc, nsteps)) return r;
   FRB_CUDA(cudaEventRecord(p->ev1, s));
   int bad = 0;
   if (p->limiter_on)
