@@ -1,0 +1,103 @@
+"""CPU checks of the oracle pieces added for the widened scope: LF / Roe common fluxes (defined in
+DESIGN.md section 2), the shock sensor + modal filter pass, the triangle Euler residual."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+import fr_oracle as o  # noqa: E402
+import fr_oracle_tri as T  # noqa: E402
+
+G = 5.0 / 3.0
+
+
+@pytest.mark.parametrize("flux", ["hll", "lf", "roe"])
+def test_common_fluxes_are_consistent_and_mirror_symmetric(flux):
+    rng = np.random.default_rng(1)
+    prim = np.stack([1 + 0.3 * rng.random(50), rng.normal(0, 0.8, 50), rng.normal(0, 0.5, 50), 0.6 + 0.4 * rng.random(50)], axis=-1)
+    wL = o.prim_conserve(prim, G)
+    wR = o.prim_conserve(prim[::-1] * np.array([1.1, 0.9, 1.0, 1.05]), G)
+    f = o.RIEMANN[flux]
+    assert np.abs(f(wL, wL, G) - o.euler_flux(wL, G)[0]).max() <= 1e-14  # f(w, w) = F(w)
+    # mirror the x axis: states swap sides, normal momentum flips -> mass/energy/tangential fluxes flip
+    m = np.array([1.0, -1.0, 1.0, 1.0])
+    a, b = f(wL, wR, G), f(wR * m, wL * m, G)
+    assert np.abs(a + b * m).max() <= 1e-13
+    # 1-D = 2-D with zero tangential momentum
+    w3L, w3R = wL[:, [0, 1, 3]].copy(), wR[:, [0, 1, 3]].copy()
+    w4L, w4R = wL.copy(), wR.copy()
+    for w4, w3 in ((w4L, w3L), (w4R, w3R)):
+        w3[:, 2] = w4[:, 3] - 0.5 * w4[:, 2] ** 2 / w4[:, 0]  # remove the tangential kinetic energy
+        w4[:, 3] = w3[:, 2]
+        w4[:, 2] = 0.0
+    assert np.abs(f(w3L, w3R, G) - f(w4L, w4R, G)[:, [0, 1, 3]]).max() <= 1e-13
+
+
+def test_roe_and_lf_upwind_supersonic_states():
+    wl = o.prim_conserve(np.array([1.0, 3.0, 0.1, 0.8]), G)
+    wr = o.prim_conserve(np.array([0.9, 3.2, -0.1, 0.7]), G)
+    assert np.abs(o.flux_roe(wl, wr, G) - o.euler_flux(wl, G)[0]).max() <= 1e-13
+    assert np.abs(o.flux_hll(wl, wr, G) - o.euler_flux(wl, G)[0]).max() <= 1e-13
+
+
+@pytest.mark.parametrize("flux", ["lf", "roe"])
+def test_euler2d_other_fluxes_freestream_and_conservation(flux):
+    ps = o.FRPSpace2D(0.0, 1.0, 8, 0.0, 1.0, 6, 3, 1, 1)
+    u = np.empty((10, 8, 4, 4, 4), order="F")
+    u[...] = o.prim_conserve(np.array([1.0, 0.3, -0.2, 0.8]), G)
+    assert np.abs(o.rhs_euler2d(u, ps, G, flux=flux)).max() <= 1e-11
+    u = o.ic_wave2d(ps, G, "x")
+    o.ghost_fill_euler2d(u, "wave_x")
+    du = o.rhs_euler2d(u, ps, G, flux=flux)
+    for m in (0, 1, 3):
+        assert abs(np.einsum("ijkl,kl->", du[1:-1, 1:-1, :, :, m], ps.wp)) <= 1e-11 * np.abs(du).max() * 48
+
+
+def test_shock_detector_branches():
+    S0 = -3.0 * np.log10(3)
+    assert not o.shock_detector(S0 - 5.0, 3)          # smooth: sigma = 1
+    assert o.shock_detector(S0 + 5.0, 3)              # rough: sigma = 0
+    assert o.shock_detector(S0, 3)                    # sigma = 0.5
+    assert not o.shock_detector(-np.inf, 3)           # su = 0
+    assert o.shock_detector(np.nan, 3)                # 0/0: falls into the else branch of dissipation.jl:19-21
+
+
+def test_modal_filter_pass_keeps_means_and_smooth_cells():
+    ps = o.FRPSpace1D(0.0, 1.0, 40, 3)
+    u = o.ic_wave1d(ps, G, amp=1e-6)
+    u[ps.xpg[ps.ng: ps.ng + 40] > 0.5031] *= 0.4
+    ref = u.copy()
+    n = o.filter_pass_1d(u, ps.V, ps.iV, ps.deg, 1e-2)
+    assert 0 < n < 5
+    changed = np.abs(u - ref).max(axis=(1, 2)) > 0
+    assert changed.sum() == n
+    w = ps.wp / 2  # the l2 filter keeps mode 0, i.e. the cell mean
+    assert np.abs(np.einsum("ipk,p->ik", u - ref, w)).max() <= 1e-14
+
+
+def test_triangle_residual_freestream_and_convergence():
+    errs = []
+    for n in (4, 8):
+        pts, cells = T.tri_mesh_rect(n, n, jitter=0.1)
+        sp = T.tri_space(pts, cells, 2)
+        if n == 4:
+            u = np.zeros((len(cells), sp["np"], 4))
+            u[:] = o.prim_conserve(np.array([1.0, 0.4, -0.3, 0.8]), G)
+            assert np.abs(T.rhs_tri_euler(u, sp, G)).max() <= 1e-12
+            # every interior flux point has exactly one partner and the pairing is an involution
+            fpn = sp["fpn"]
+            for i, j, k in zip(*np.nonzero(fpn[..., 0] >= 0)):
+                ni, nj, nk = fpn[i, j, k]
+                assert tuple(fpn[ni, nj, nk]) == (i, j, k)
+        x, y = sp["xpg"][..., 0], sp["xpg"][..., 1]
+        rho = 1 + 0.1 * np.sin(2 * np.pi * x) * np.cos(2 * np.pi * y)
+        prim = np.stack([rho, 0.5 * np.ones_like(rho), 0.25 * np.ones_like(rho), rho], axis=-1)  # p = 1/2
+        du = T.rhs_tri_euler(o.prim_conserve(prim, G), sp, G)
+        exact = -(0.5 * 0.2 * np.pi * np.cos(2 * np.pi * x) * np.cos(2 * np.pi * y)
+                  - 0.25 * 0.2 * np.pi * np.sin(2 * np.pi * x) * np.sin(2 * np.pi * y))
+        act = sp["cellType"] == 0
+        errs.append(np.abs(du[act, :, 0] - exact[act]).max())
+    assert errs[1] < 0.7 * errs[0]  # the derivative of a degree-2 reconstruction converges
