@@ -205,14 +205,15 @@ int env_int_rc(const char *name, int dflt) {
 }
 
 int rc_rows_per_seg(frb_prob_t p, const RcGeom &g, int ctas_per_sm, bool usea) {
-  // Short segments on purpose.  Lanes 1 and 30 store their column's duplicate into the
-  // neighbouring chunk, i.e. into a 32-B sector whose other lanes the neighbouring CTA writes;
-  // L2 merges the two partial writes only while the CTAs of adjacent strips work on the same
-  // row at about the same time.  CTAs launched together do, and drift apart as they run: with
-  // 32..64-row segments the per-launch time grows 15-25 % (DRAM read-modify-write of orphaned
-  // partial sectors).  Measured at 2048^2, p3 on B200: 16-B stage best at 10..20 rows (0.88 ms),
-  // 24-B stage at 4..6 rows (1.08 ms); the extra halo-row reads (2 per segment) are L2 hits of
-  // the segment below that started in the same wave.  FRB_MARCH_ROWS overrides.
+  // Short segments on purpose.  The kernel is fastest while the CTAs that run at the same time work on
+  // ADJACENT chunks -- all strips of a row are one contiguous 1.1 MB run -- which is the state the CTAs
+  // of a wave start in and drift out of.  Per-CTA globaltimer stamps: 2.5 us per row step in the first
+  // wave whatever the segment length, ~3.6 us in later waves of 64-row segments.  Measured at 2048^2, p3
+  // on B200 (16-B / 24-B stage, ms): 6 rows 0.91 / 1.085, 12: 0.88 / 1.13, 32: 1.01 / 1.16, 64: 1.11 /
+  // 1.22; the extra halo rows (2 per segment) are mostly L2 hits.  What does NOT explain it (each was
+  // built and measured): the strip-edge duplicate stores (no change without them), a tail wave alone,
+  // start-up lock-step (per-CTA jitter: no change), TLB reach (strip-major chunk order: slower).
+  // FRB_MARCH_ROWS overrides.
   int forced = env_int_rc("FRB_MARCH_ROWS", 0);
   if (forced > 0) return forced < g.ny ? forced : g.ny;
   const int slots = p->ctx->sm_count * ctas_per_sm;
