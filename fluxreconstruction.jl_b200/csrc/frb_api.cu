@@ -237,7 +237,11 @@ extern "C" int32_t frb_bgk1d_create(frb_ctx_t ctx, int32_t ncell, int32_t nu,
   p->len = (int64_t)ncell * nu * p->nsp;
   p->dofs = p->len;
   FRB_TRY(alloc_common(p));
-  FRB_TRY(upload_vec(p, &p->J, dx, ncell));
+  {
+    std::vector<double> inv_j(ncell);  // 1 / J = 2 / dx: the kernel multiplies (bgk_wave.jl:85-88 divides)
+    for (int i = 0; i < ncell; ++i) inv_j[i] = 1.0 / (0.5 * dx[i]);
+    FRB_TRY(upload_vec(p, &p->J, inv_j.data(), ncell));
+  }
   FRB_TRY(upload_vec(p, &p->velo, velo, nu));
   FRB_TRY(upload_vec(p, &p->weights, weights, nu));
   if (cudaMalloc(&p->prim, sizeof(double) * (size_t)ncell * p->nsp * 3) != cudaSuccess) {

@@ -8,8 +8,8 @@
 //   bgk_moments_kernel  thread = (cell, sp): the three moments over the nu velocities in the
 //                       reference's summation order, 16 loads in flight per thread (the sum is a
 //                       serial chain, the loads are not); writes rho*sqrt(lambda/pi), U, lambda.
-//   bgk1d_kernel        thread = (cell, velocity): own block + the upwind neighbour's block, one
-//                       reciprocal per Jacobian, one exp per point.
+//   bgk1d_kernel        thread = (cell, velocity): own block + the upwind neighbour's block, 1 / J
+//                       precomputed per cell, one exp per point.
 // Both are L2 / HBM streams of the 50 MB state; nothing here is GEMM-shaped.
 #include "frb_internal.cuh"
 
@@ -88,7 +88,7 @@ bgk_moments_kernel(const double *__restrict__ u, double *__restrict__ prim, int 
 template <int NSP>
 __global__ void __launch_bounds__(128)
 bgk1d_kernel(const double *__restrict__ u, const double *__restrict__ ua, double *__restrict__ out,
-             const double *__restrict__ prim, const double *__restrict__ dx,
+             const double *__restrict__ prim, const double *__restrict__ inv_j,
              const double *__restrict__ velo, int ncell, int nu, double inv_tau, FrbOps ops, FrbStage st) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   const int j = blockIdx.y;
@@ -98,7 +98,7 @@ bgk1d_kernel(const double *__restrict__ u, const double *__restrict__ ua, double
   const size_t vs = (size_t)ncell * nu;
   // only the upwind neighbour contributes: left cell for v >= 0, right cell otherwise (periodic)
   const int in = pos ? (i == 0 ? ncell - 1 : i - 1) : (i == ncell - 1 ? 0 : i + 1);
-  const double sc = v / (0.5 * dx[i]), sn = v / (0.5 * dx[in]);  // v / J
+  const double sc = v * inv_j[i], sn = v * inv_j[in];  // v / J
   double uc[NSP], f[NSP], fn[NSP];
 #pragma unroll
   for (int q = 0; q < NSP; ++q) {
