@@ -371,7 +371,6 @@ static bool use_march(frb_prob_t p) {
 // frb_step streams in the row-chunk layout when it can: 2-D Euler, deg 2..3
 static bool use_rc(frb_prob_t p) {
   if (p->kind != K_EULER2D || !p->rc_base || p->flux != FRB_FLUX_HLL) return false;
-  if (p->filt_when != 0) return false;  // the filter pass works on the reference image
   return p->kernel_kind == FRB_KERNEL_AUTO || p->kernel_kind == FRB_KERNEL_RC;
 }
 
@@ -609,9 +608,11 @@ static int set_filter(frb_prob_t p, const double *iV, const double *F, int np) {
   return FRB_OK;
 }
 
-static int run_filter(frb_prob_t p, int *count = nullptr) {
-  int n = frb_launch_modal_filter(p, p->u, p->filt, p->filt + p->filt_np * p->filt_np, p->filt_eps, p->filt_S0,
-                                  p->filt_kappa, p->filt_ghosts != 0, count);
+static int run_filter(frb_prob_t p, int *count = nullptr, bool rc = false) {
+  const double *iV = p->filt, *F = p->filt + p->filt_np * p->filt_np;
+  int n = rc ? frb_rc_modal_filter(p, p->ru, iV, F, p->filt_eps, p->filt_S0, p->filt_kappa, p->filt_ghosts != 0)
+             : frb_launch_modal_filter(p, p->u, iV, F, p->filt_eps, p->filt_S0, p->filt_kappa, p->filt_ghosts != 0,
+                                       count);
   if (n > 0) p->launches += n;
   return n;
 }
@@ -700,7 +701,7 @@ static int one_step(frb_prob_t p, int scheme, double dt, bool rc) {
   const bool par = frb_halo_active(p);
   double *&U = rc ? p->ru : p->u, *&S1 = rc ? p->rs1 : p->s1, *&S2 = rc ? p->rs2 : p->s2;
   if (p->filt_when == 1) {
-    if ((n = run_filter(p)) < 0) return n;
+    if ((n = run_filter(p, nullptr, rc)) < 0) return n;
   }
   if (p->limiter_on) {
     if ((n = run_limiter(p, rc)) < 0) return n;
@@ -776,7 +777,7 @@ static int one_step(frb_prob_t p, int scheme, double dt, bool rc) {
     return FRB_ERR_ARG;
   }
   if (p->filt_when == 2) {
-    if ((n = run_filter(p)) < 0) return n;
+    if ((n = run_filter(p, nullptr, rc)) < 0) return n;
   }
   return FRB_OK;
 }

@@ -9,6 +9,7 @@
 // the kernel needs iV (sensor) and F (np x np each, np = nsp or nsp^2), nothing of KitBase.
 // One thread per element; state in the reference memory image.
 #include "frb_internal.cuh"
+#include "frb_rc.cuh"
 
 namespace {
 
@@ -21,16 +22,13 @@ __device__ __forceinline__ bool shock_detector(double Se, double S0, double kapp
   return sigma < 0.99;
 }
 
-// u[e + stride*q + vstride*var], q = 0..NP-1 (the element's points in Julia's [:] order)
+// One element: u[e + stride*q + vstride*var], q = 0..NP-1 (the element's points in Julia's [:]
+// order); dup >= 0: offset of the element's copy in the neighbouring chunk (row-chunk layout).
 template <int NP>
-__global__ void __launch_bounds__(128)
-modal_filter_kernel(double *__restrict__ u, long long nelem, int row, long long pitch, long long e0,
-                    long long stride, long long vstride, int nvar, const double *__restrict__ iV,
-                    const double *__restrict__ F, double eps, double S0, double kappa, int *__restrict__ count) {
-  const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-  if (t >= nelem) return;
-  // elements are enumerated row by row: `row` consecutive ones, then a jump of `pitch`
-  const long long e = e0 + (t % row) + (t / row) * pitch;
+__device__ __forceinline__ void filter_element(double *__restrict__ u, long long e, long long dup, long long stride,
+                                               long long vstride, int nvar, const double *__restrict__ iV,
+                                               const double *__restrict__ F, double eps, double S0, double kappa,
+                                               int *__restrict__ count) {
   double w[NP];
 #pragma unroll
   for (int q = 0; q < NP; ++q) w[q] = u[e + stride * q];
@@ -61,8 +59,43 @@ modal_filter_kernel(double *__restrict__ u, long long nelem, int row, long long 
       r[m] = a;
     }
 #pragma unroll
-    for (int m = 0; m < NP; ++m) p[stride * m] = r[m];
+    for (int m = 0; m < NP; ++m) {
+      p[stride * m] = r[m];
+      if (dup >= 0) u[dup + vstride * s + stride * m] = r[m];
+    }
   }
+}
+
+template <int NP>
+__global__ void __launch_bounds__(128)
+modal_filter_kernel(double *__restrict__ u, long long nelem, int row, long long pitch, long long e0,
+                    long long stride, long long vstride, int nvar, const double *__restrict__ iV,
+                    const double *__restrict__ F, double eps, double S0, double kappa, int *__restrict__ count) {
+  const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (t >= nelem) return;
+  // elements are enumerated row by row: `row` consecutive ones, then a jump of `pitch`
+  filter_element<NP>(u, e0 + (t % row) + (t / row) * pitch, -1, stride, vstride, nvar, iV, F, eps, S0, kappa, count);
+}
+
+// the same pass on the row-chunk layout (frb_rc.cuh): thread = (lane, strip, row); every copy of a
+// column is filtered by the thread that owns it (ghost columns: the lane that holds them)
+template <int NP>
+__global__ void __launch_bounds__(128)
+modal_filter_rc_kernel(double *__restrict__ u, RcGeom g, int ghosts, const double *__restrict__ iV,
+                       const double *__restrict__ F, double eps, double S0, double kappa) {
+  const int lane = threadIdx.x, s = blockIdx.x * blockDim.y + threadIdx.y;
+  const int j = blockIdx.y + (ghosts ? 0 : 1);
+  if (s >= g.ns) return;
+  const int i = kRcOwn * s + lane;
+  if (i > g.nx + 1) return;
+  int sp, lp;
+  rc_primary(g, i, &sp, &lp);
+  if (sp != s) return;                                    // a copy: its owner filters it
+  if (!ghosts && (i == 0 || i == g.nx + 1)) return;
+  int s2, l2;
+  long long dup = -1;
+  if (rc_duplicate(g, s, lane, &s2, &l2)) dup = (long long)rc_index(g, j, s2, 0, l2);
+  filter_element<NP>(u, (long long)rc_index(g, j, s, 0, lane), dup, 32, 32LL * NP, 4, iV, F, eps, S0, kappa, nullptr);
 }
 
 }  // namespace
@@ -102,5 +135,21 @@ int frb_launch_modal_filter(frb_prob_t p, double *u, const double *iV_dev, const
 #undef FRB_FILTER_CASE
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return frb_cuda_fail(e, "modal_filter_kernel", __FILE__, __LINE__);
+  return 1;
+}
+
+// the pass on the row-chunk mirror of a 2-D Euler problem (hook of frb_step)
+int frb_rc_modal_filter(frb_prob_t p, double *u, const double *iV_dev, const double *F_dev, double eps, double S0,
+                        double kappa, bool include_ghosts) {
+  const RcGeom g = rc_geom(p->nx, p->ny, p->nsp);
+  dim3 blk(32, 4), grd((g.ns + 3) / 4, include_ghosts ? p->ny + 2 : p->ny);
+  cudaStream_t s = p->ctx->stream;
+  switch (p->nsp * p->nsp) {
+    case 9: modal_filter_rc_kernel<9><<<grd, blk, 0, s>>>(u, g, include_ghosts, iV_dev, F_dev, eps, S0, kappa); break;
+    case 16: modal_filter_rc_kernel<16><<<grd, blk, 0, s>>>(u, g, include_ghosts, iV_dev, F_dev, eps, S0, kappa); break;
+    default: frb_set_error("row-chunk modal filter: deg 2..3"); return FRB_ERR_ARG;
+  }
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return frb_cuda_fail(e, "modal_filter_rc_kernel", __FILE__, __LINE__);
   return 1;
 }

@@ -150,6 +150,8 @@ int frb_halo_check_timeout(frb_prob_t p);
 int frb_halo_rank(frb_prob_t p, int *nranks);
 int frb_launch_modal_filter(frb_prob_t p, double *u, const double *iV_dev, const double *F_dev, double eps,
                             double S0, double kappa, bool include_ghosts, int *count);
+int frb_rc_modal_filter(frb_prob_t p, double *u, const double *iV_dev, const double *F_dev, double eps, double S0,
+                        double kappa, bool include_ghosts);
 int frb_launch_limiter1d(frb_prob_t p, double *u);
 int frb_launch_limiter2d(frb_prob_t p, double *u);
 int frb_launch_dirichlet_copy1d(frb_prob_t p, const double *src, double *dst);
