@@ -130,6 +130,7 @@ static int alloc_common(frb_prob_t p) {
 // with the problem so that the multi-GPU path can export it
 static int alloc_rc(frb_prob_t p) {
   if (!frb_euler2d_rc_supported(p) || getenv("FRB_NO_RC")) return FRB_OK;
+  if (p->ny + 2 > 65535) return FRB_OK;  // grid.z / grid.y of the rc_* kernels index rows: stay on the reference image
   const RcGeom g = rc_geom(p->nx, p->ny, p->nsp);
   p->rc_len = g.len;
   FRB_CUDA(cudaMalloc(&p->rc_base, sizeof(double) * 3 * g.len));
