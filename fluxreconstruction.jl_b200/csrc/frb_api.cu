@@ -156,7 +156,7 @@ extern "C" int32_t frb_prob_destroy(frb_prob_t p) {
   frb_march_release(p);
   cudaFree(p->u); cudaFree(p->s1); cudaFree(p->s2); cudaFree(p->du); cudaFree(p->rc_base);
   cudaFree(p->J); cudaFree(p->velo); cudaFree(p->weights); cudaFree(p->prim);
-  cudaFree(p->lim_w); cudaFree(p->flag); cudaFree(p->filt); cudaFree(p->ns_flux);
+  cudaFree(p->lim_w); cudaFree(p->flag); cudaFree(p->loop_bar); cudaFree(p->filt); cudaFree(p->ns_flux);
   cudaFree(p->tri_ops); cudaFree(p->tri_uf); cudaFree(p->tri_normals); cudaFree(p->tri_type); cudaFree(p->tri_fpn);
   if (p->ev0) cudaEventDestroy(p->ev0);
   if (p->ev1) cudaEventDestroy(p->ev1);
@@ -810,6 +810,15 @@ static int run_steps(frb_prob_t p, int scheme, double dt, bool rc, int nsteps) {
   cudaStream_t s = p->ctx->stream;
   int it = 0, r;
   const bool graphable = nsteps >= 16 && !p->profiling && !frb_halo_active(p) && !getenv("FRB_NO_GRAPH");
+  if (graphable && p->filt_when == 0 && !getenv("FRB_NO_LOOP1D")) {
+    // small 1-D problems: the whole loop in one cooperative launch (grid barrier instead of launches)
+    r = frb_launch_loop1d(p, scheme, dt, nsteps);
+    if (r < 0) return r;
+    if (r > 0) {
+      p->launches += r;
+      return FRB_OK;
+    }
+  }
   if (graphable) {
     for (; it < 2; ++it)
       if ((r = one_step(p, scheme, dt, rc)) < 0) return r;

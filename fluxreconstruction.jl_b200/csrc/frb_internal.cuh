@@ -92,6 +92,7 @@ struct frb_prob_s {
   int filt_np = 0, filt_when = 0, filt_ghosts = 0;
   double filt_eps = 0, filt_S0 = 0, filt_kappa = 0;
   int *flag = nullptr;              // device int for limiter nbad
+  unsigned *loop_bar = nullptr;     // grid barrier of the one-launch 1-D time loop
   // hooks
   int ghost_mode = FRB_GHOST_NONE;
   bool limiter_on = false;
@@ -153,6 +154,7 @@ int frb_launch_modal_filter(frb_prob_t p, double *u, const double *iV_dev, const
 int frb_rc_modal_filter(frb_prob_t p, double *u, const double *iV_dev, const double *F_dev, double eps, double S0,
                         double kappa, bool include_ghosts);
 int frb_launch_limiter1d(frb_prob_t p, double *u);
+int frb_launch_loop1d(frb_prob_t p, int scheme, double dt, int nsteps);
 int frb_launch_limiter2d(frb_prob_t p, double *u);
 int frb_launch_dirichlet_copy1d(frb_prob_t p, const double *src, double *dst);
 void frb_march_release(frb_prob_t p);

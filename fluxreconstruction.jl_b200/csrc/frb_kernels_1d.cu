@@ -6,6 +6,9 @@
 // Reference semantics: src/Equation/eq_advection.jl:55-175 + eq_scalar.jl:1-12,
 // example/advection_lowlevel.jl:4-47, src/Equation/eq_euler.jl:29-98,
 // example/bgk_wave.jl:69-129, src/dissipation.jl:61-123.
+#include <cstdlib>
+#include <utility>
+
 #include "frb_internal.cuh"
 #include "frb_physics.cuh"
 
@@ -56,13 +59,21 @@ __device__ __forceinline__ frb::Flux3 hll3_lit(double l0, double l1, double l2, 
 }
 
 // ---------------------------------------------------------------- advection ----
+struct Adv1dArgs {
+  const double *J;
+  int ncell;
+  double a;
+  int bc;
+  double eps_seam;
+};
+
 template <int NSP>
-__global__ void __launch_bounds__(128)
-adv1d_kernel(const double *__restrict__ u, const double *__restrict__ ua, double *__restrict__ out,
-             const double *__restrict__ J, int ncell, double a, int bc, double eps_seam,
-             FrbOps ops, FrbStage st) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= ncell) return;
+__device__ __forceinline__ void adv1d_cell(int i, const double *__restrict__ u, const double *__restrict__ ua,
+                                           double *__restrict__ out, const Adv1dArgs &A, const FrbOps &ops,
+                                           const FrbStage &st) {
+  const double *J = A.J;
+  const int ncell = A.ncell, bc = A.bc;
+  const double a = A.a, eps_seam = A.eps_seam;
   const bool periodic = bc == FRB_BC_PERIOD;
   int im = i == 0 ? ncell - 1 : i - 1;
   int ip = i == ncell - 1 ? 0 : i + 1;
@@ -99,6 +110,14 @@ adv1d_kernel(const double *__restrict__ u, const double *__restrict__ ua, double
   }
 }
 
+template <int NSP>
+__global__ void __launch_bounds__(128)
+adv1d_kernel(const double *__restrict__ u, const double *__restrict__ ua, double *__restrict__ out, Adv1dArgs A,
+             FrbOps ops, FrbStage st) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < A.ncell) adv1d_cell<NSP>(i, u, ua, out, A, ops, st);
+}
+
 // -------------------------------------------------------------------- Euler ----
 template <int NSP>
 __device__ __forceinline__ void load_cell3(const double *__restrict__ u, int i, int ncell,
@@ -109,13 +128,20 @@ __device__ __forceinline__ void load_cell3(const double *__restrict__ u, int i, 
     for (int q = 0; q < NSP; ++q) w[k][q] = u[i + (size_t)ncell * (q + NSP * k)];
 }
 
+struct Euler1dArgs {
+  const double *J;
+  int ncell;
+  double gamma;
+  int bc, flux;
+};
+
 template <int NSP>
-__global__ void __launch_bounds__(128)
-euler1d_kernel(const double *__restrict__ u, const double *__restrict__ ua,
-               double *__restrict__ out, const double *__restrict__ J, int ncell, double gamma,
-               int bc, int flux, FrbOps ops, FrbStage st) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= ncell) return;
+__device__ __forceinline__ void euler1d_cell(int i, const double *__restrict__ u, const double *__restrict__ ua,
+                                             double *__restrict__ out, const Euler1dArgs &A, const FrbOps &ops,
+                                             const FrbStage &st) {
+  const double *J = A.J;
+  const int ncell = A.ncell, bc = A.bc, flux = A.flux;
+  const double gamma = A.gamma;
   const bool periodic = bc == FRB_BC_PERIOD;
   int im = i == 0 ? ncell - 1 : i - 1;
   int ip = i == ncell - 1 ? 0 : i + 1;
@@ -156,13 +182,19 @@ euler1d_kernel(const double *__restrict__ u, const double *__restrict__ ua,
     }
 }
 
-// positive_limiter(u::Matrix, gamma, weights, ll, lr)  dissipation.jl:61-123, density branch.
 template <int NSP>
 __global__ void __launch_bounds__(128)
-limiter1d_kernel(double *__restrict__ u, int ncell, double gamma, const double *__restrict__ wts,
-                 FrbOps ops, int *__restrict__ nbad) {
+euler1d_kernel(const double *__restrict__ u, const double *__restrict__ ua, double *__restrict__ out,
+               Euler1dArgs A, FrbOps ops, FrbStage st) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= ncell) return;
+  if (i < A.ncell) euler1d_cell<NSP>(i, u, ua, out, A, ops, st);
+}
+
+// positive_limiter(u::Matrix, gamma, weights, ll, lr)  dissipation.jl:61-123, density branch.
+template <int NSP>
+__device__ __forceinline__ void limiter1d_cell(int i, double *__restrict__ u, int ncell, double gamma,
+                                               const double *__restrict__ wts, const FrbOps &ops,
+                                               int *__restrict__ nbad) {
   double w[3][NSP];
   load_cell3<NSP>(u, i, ncell, w);
   double um[3];
@@ -184,6 +216,83 @@ limiter1d_kernel(double *__restrict__ u, int ncell, double gamma, const double *
   if (!(t1 > 0.0 && t1 <= 1.0)) atomicAdd(nbad, 1);              // :84 @assert
 #pragma unroll
   for (int q = 0; q < NSP; ++q) u[i + (size_t)ncell * q] = t1 * (w[0][q] - um[0]) + um[0];
+}
+
+template <int NSP>
+__global__ void __launch_bounds__(128)
+limiter1d_kernel(double *__restrict__ u, int ncell, double gamma, const double *__restrict__ wts,
+                 FrbOps ops, int *__restrict__ nbad) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < ncell) limiter1d_cell<NSP>(i, u, ncell, gamma, wts, ops, nbad);
+}
+
+// ---------------------------------------------------------------- whole time loop in one launch ----
+// The smallest 1-D problems of the reference (cfg1: 100 cells, 2.4 KB) are pure launch latency: a stage
+// runs for about a microsecond, a launch costs 5 us eagerly and ~3 us as a graph node.  Up to 512 cells
+// the whole time loop runs in ONE CTA with a block barrier after every pass (cfg1, SSPRK3: 9.3 -> 2.9 us
+// per step).  Same cell routines, same stage sequence and buffer roles as frb_step's host loop.  The
+// multi-CTA form (grid barrier through a global counter, cooperative launch) is kept behind
+// FRB_LOOP1D_GRID: at 32 CTAs (cfg2) a barrier costs more than the launch it replaces (28.0 vs 26.7 us per
+// step against the graph replay), so it is off by default.
+struct Loop1dArgs {
+  double *u, *s1, *s2;       // state and stage buffers (roles as on the host)
+  unsigned *bar;             // grid barrier: arrival counter
+  int nsteps, scheme;
+  double dt;
+  const double *lim_w;       // limiter hook (Euler) or nullptr
+  int *nbad;
+};
+
+// release on arrival, acquire on the poll: the CTA's writes (ordered before thread 0 by bar.sync) are
+// visible to every thread that leaves the barrier; no stand-alone membar on either side
+__device__ __forceinline__ void grid_barrier(unsigned *bar, unsigned &round) {
+  __syncthreads();
+  if (gridDim.x > 1) {
+    if (threadIdx.x == 0) {
+      round += gridDim.x;
+      asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(bar) : "memory");
+      unsigned v;
+      do {
+        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(bar) : "memory");
+      } while (v < round);
+    }
+    __syncthreads();
+  }
+}
+
+template <int NSP, bool EULER>
+__global__ void __launch_bounds__(512)
+loop1d_kernel(Loop1dArgs L, Adv1dArgs AA, Euler1dArgs EA, FrbOps ops) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int ncell = EULER ? EA.ncell : AA.ncell;
+  const bool live = i < ncell;
+  unsigned round = 0;
+  double *U = L.u, *S1 = L.s1, *S2 = L.s2;
+  auto stage = [&](const double *in, const double *ua, double *out, FrbStage st) {
+    if (live) {
+      if (EULER) euler1d_cell<NSP>(i, in, ua, out, EA, ops, st);
+      else adv1d_cell<NSP>(i, in, ua, out, AA, ops, st);
+    }
+    grid_barrier(L.bar, round);
+  };
+  for (int it = 0; it < L.nsteps; ++it) {
+    if (EULER && L.lim_w) {
+      if (live) limiter1d_cell<NSP>(i, U, ncell, EA.gamma, L.lim_w, ops, L.nbad);
+      grid_barrier(L.bar, round);
+    }
+    const double dt = L.dt;
+    if (L.scheme == FRB_SCHEME_EULER) {
+      stage(U, nullptr, S1, FrbStage{0.0, 1.0, dt, 0, 0, 0});
+      double *t = U; U = S1; S1 = t;
+    } else if (L.scheme == FRB_SCHEME_MIDPOINT) {
+      stage(U, nullptr, S1, FrbStage{0.0, 1.0, 0.5 * dt, 0, 0, 0});
+      stage(S1, U, U, FrbStage{1.0, 0.0, dt, 1, 0, 0});
+    } else {
+      stage(U, nullptr, S1, FrbStage{0.0, 1.0, dt, 0, 0, 0});
+      stage(S1, U, S2, FrbStage{0.75, 0.25, dt, 1, 0, 1});
+      stage(S2, U, U, FrbStage{1.0 / 3.0, 2.0 / 3.0, dt, 1, 0, 1});
+    }
+  }
 }
 
 // dirichlet cells of the stage buffers are never written by L(u)=0 updates when the
@@ -214,16 +323,16 @@ int frb_launch_adv1d(frb_prob_t p, const double *u, const double *ua, double *ou
   dim3 blk(128), grd((p->ncell + 127) / 128);
   double eps = p->variant == FRB_ADV_LOWLEVEL ? 1e-8 : 1e-6;
   int bc = p->variant == FRB_ADV_LOWLEVEL ? FRB_BC_PERIOD : p->bc;
-  FRB_NSP_SWITCH(p->nsp, (adv1d_kernel<N><<<grd, blk, 0, p->ctx->stream>>>(
-                             u, ua, out, p->J, p->ncell, p->a, bc, eps, p->ops, st)));
+  const Adv1dArgs A = {p->J, p->ncell, p->a, bc, eps};
+  FRB_NSP_SWITCH(p->nsp, (adv1d_kernel<N><<<grd, blk, 0, p->ctx->stream>>>(u, ua, out, A, p->ops, st)));
   if (int rc = check_launch("adv1d_kernel")) return rc;
   return 1;
 }
 
 int frb_launch_euler1d(frb_prob_t p, const double *u, const double *ua, double *out, FrbStage st) {
   dim3 blk(128), grd((p->ncell + 127) / 128);
-  FRB_NSP_SWITCH(p->nsp, (euler1d_kernel<N><<<grd, blk, 0, p->ctx->stream>>>(
-                             u, ua, out, p->J, p->ncell, p->gamma, p->bc, p->flux, p->ops, st)));
+  const Euler1dArgs A = {p->J, p->ncell, p->gamma, p->bc, p->flux};
+  FRB_NSP_SWITCH(p->nsp, (euler1d_kernel<N><<<grd, blk, 0, p->ctx->stream>>>(u, ua, out, A, p->ops, st)));
   if (int rc = check_launch("euler1d_kernel")) return rc;
   return 1;
 }
@@ -238,3 +347,42 @@ int frb_launch_limiter1d(frb_prob_t p, double *u) {
 
 
 int frb_launch_dirichlet_copy1d(frb_prob_t, const double *, double *) { return 0; }
+
+// The whole time loop of a small 1-D problem in one cooperative launch.  Returns 0 when the problem
+// does not qualify (too many cells for one CTA per SM, or the device refuses a cooperative launch):
+// the caller then runs the ordinary loop.  On success the state is in p->u with the host's buffer
+// roles (the forward-Euler scheme swaps u and s1 every step).
+int frb_launch_loop1d(frb_prob_t p, int scheme, double dt, int nsteps) {
+  if (p->kind != K_ADV1D && p->kind != K_EULER1D) return 0;
+  const bool grid_form = getenv("FRB_LOOP1D_GRID") != nullptr;
+  const int threads = grid_form ? 128 : ((p->ncell + 31) / 32) * 32;
+  const int blocks = grid_form ? (p->ncell + 127) / 128 : 1;
+  if (threads > 512 || blocks > p->ctx->sm_count || nsteps <= 0) return 0;
+  static int coop = -1;
+  if (coop < 0) cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, p->ctx->device);
+  if (!coop) return 0;
+  if (!p->loop_bar) FRB_CUDA(cudaMalloc(&p->loop_bar, sizeof(unsigned)));
+  FRB_CUDA(cudaMemsetAsync(p->loop_bar, 0, sizeof(unsigned), p->ctx->stream));
+  Loop1dArgs L = {p->u, p->s1, p->s2, p->loop_bar, nsteps, scheme, dt,
+                  (p->kind == K_EULER1D && p->limiter_on) ? p->lim_w : nullptr, p->flag};
+  const double eps = p->variant == FRB_ADV_LOWLEVEL ? 1e-8 : 1e-6;
+  Adv1dArgs AA = {p->J, p->ncell, p->a, p->variant == FRB_ADV_LOWLEVEL ? FRB_BC_PERIOD : p->bc, eps};
+  Euler1dArgs EA = {p->J, p->ncell, p->gamma, p->bc, p->flux};
+  void *args[] = {&L, &AA, &EA, &p->ops};
+  const void *fn = nullptr;
+#define FRB_LOOP_CASE(N)                                                                        \
+  case N: fn = p->kind == K_EULER1D ? (const void *)loop1d_kernel<N, true> : (const void *)loop1d_kernel<N, false>; break;
+  switch (p->nsp) {
+    FRB_LOOP_CASE(2) FRB_LOOP_CASE(3) FRB_LOOP_CASE(4) FRB_LOOP_CASE(5) FRB_LOOP_CASE(6) FRB_LOOP_CASE(7) FRB_LOOP_CASE(8)
+    default: return 0;
+  }
+#undef FRB_LOOP_CASE
+  cudaError_t e = cudaLaunchCooperativeKernel(fn, dim3(blocks), dim3(threads), args, 0, p->ctx->stream);
+  if (e == cudaErrorCooperativeLaunchTooLarge) {
+    (void)cudaGetLastError();
+    return 0;
+  }
+  if (e != cudaSuccess) return frb_cuda_fail(e, "loop1d_kernel", __FILE__, __LINE__);
+  if (scheme == FRB_SCHEME_EULER && (nsteps & 1)) std::swap(p->u, p->s1);
+  return 1;
+}
