@@ -267,6 +267,19 @@ def run_ours(args):
                    "host buffers; upload, fused residual and download overlapped in row slabs"
                    + (f"; {world} ranks, one slab each, concurrently" if world > 1 else ""),
            "ms_per_call": 1e3 * el / k}
+    if world == 1:
+        # the reference's own user-loop shape (euler2d_wave.jl:125-135): the state lives on the host and is
+        # touched between steps, so every SSPRK3 step is upload + 3 fused stages + download
+        prob.upload(uh); prob.step(alg, dt, 1); prob.download(dh)
+        t0 = time.perf_counter()
+        for _ in range(k):
+            prob.upload(uh)
+            prob.step(alg, dt, 1)
+            prob.download(dh)
+        el2 = time.perf_counter() - t0
+        e2e["user_loop"] = {"value": 3.0 * dofs * k / el2, "unit": UNIT, "ms_per_step": 1e3 * el2 / k,
+                            "call": "frb_state_upload + frb_step(SSPRK3, 1 step) + frb_state_download per step "
+                                    "(pinned host state, mutated by the user between steps)"}
     FR.pinned_free(uh)
     FR.pinned_free(dh)
 
