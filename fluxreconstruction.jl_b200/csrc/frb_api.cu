@@ -645,7 +645,6 @@ extern "C" int32_t frb_set_filter_hook(frb_prob_t p, int32_t when, const double 
   FRB_REQUIRE(when >= 0 && when <= 2, FRB_ERR_ARG, "frb_set_filter_hook: when must be 0, 1 or 2");
   FRB_CUDA(cudaSetDevice(p->ctx->device));
   if (when != 0) {
-    FRB_REQUIRE(!p->limiter_on || p->kind == K_EULER2D || p->kind == K_EULER1D, FRB_ERR_STATE, "filter hook: Euler problems only");
     if (int rc = set_filter(p, iV, F, np)) return rc;
     p->filt_eps = eps; p->filt_S0 = S0; p->filt_kappa = kappa; p->filt_ghosts = include_ghosts;
   }
