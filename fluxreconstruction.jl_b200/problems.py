@@ -438,3 +438,11 @@ class TriEulerProblem(_Problem):
                                          fortran_ptr(keep[5]), fortran_ptr(keep[6]), float(gamma), C.byref(self.h)))
         self._keep = keep
         self.upload(self.u0)
+
+    @classmethod
+    def from_space(cls, ps, u0, tspan, gamma, cell_type=None, ctx=None):
+        """ODEProblem(dudt!, u0, tspan, (ps.cellType, ps.J, ps.lf, ps.cellNormals, ps.fpn, ps.∂l, ps.ϕ, γ))
+        for a ``TriFRPSpace`` of this package (0-based ``fpn``); ``cell_type`` overrides ``ps.cellType``
+        (dev/sod.jl:7-16 retags wall cells as 2 before building the problem)."""
+        ct = ps.cellType if cell_type is None else cell_type
+        return cls(u0, tspan, ct, ps.J, ps.lf, ps.cellNormals, ps.fpn, ps.dl, ps.phi, gamma, fpn_base=0, ctx=ctx)

@@ -25,7 +25,7 @@ from numpy.polynomial import legendre as L
 __all__ = [
     "legendre_point", "gausslegendre", "lagrange_point", "dlagrange", "standard_lagrange", "dlegendre",
     "dradau", "dsd", "dhuynh", "vandermonde_matrix", "dvandermonde_matrix", "global_sp", "r_x",
-    "FRPSpace1D", "FRPSpace2D", "UnstructFRPSpace", "TriFRPSpace",
+    "FRPSpace1D", "FRPSpace2D",
 ]
 
 
@@ -204,17 +204,3 @@ class FRPSpace2D:
         J[..., 0, 0] = self.Jx
         J[..., 1, 1] = self.Jy
         return J
-
-
-class UnstructFRPSpace:
-    """Triangle spaces (struct.jl:256-352) are outside the accelerated path:
-    no BASELINE config uses them.  Constructing one fails loudly."""
-
-    def __init__(self, *a, **k):
-        raise NotImplementedError(
-            "UnstructFRPSpace/TriFRPSpace: the triangle path is a 'next' row (SURVEY.md 8f-f3); "
-            "libfrb200 accelerates the structured 1-D/2-D residuals only"
-        )
-
-
-TriFRPSpace = UnstructFRPSpace

@@ -77,3 +77,31 @@ def test_tri_euler_steps(FR, oracle, scheme):
     assert np.isfinite(itg.u).all()
     assert rel(itg.u, ref) <= 1e-10
     prob.close()
+
+
+def test_sod_from_a_mesh_file_through_the_package_space(FR, oracle, tmp_path):
+    """The whole dev/sod.jl set-up through this package: TriFRPSpace(file, 2), wall retagging (:7-16),
+    the Sod initial state (:19-30), ODEProblem + Euler() steps (:124-136) -- against the oracle running on
+    ITS OWN space for the same mesh."""
+    import fr_oracle_tri as T
+    from test_unstruct import write_msh41
+
+    pts, cells = T.tri_mesh_rect(24, 6, 0.0, 1.0, 0.0, 0.1, jitter=0.2, seed=5)
+    f = str(tmp_path / "sod_like.msh")
+    write_msh41(f, pts, cells)
+    ps = FR.TriFRPSpace(f, 2)
+    ct = ps.cellType.copy()
+    ct[(ct == 1) & ((ps.cellCenter[:, 1] < 0.014) | (ps.cellCenter[:, 1] > 0.0835))] = 2
+    left = ps.cellCenter[:, 0] < 0.5
+    prim = np.where(left[:, None, None], np.array([1.0, 0.0, 0.0, 0.5]), np.array([0.3, 0.0, 0.0, 0.625]))
+    u0 = np.asfortranarray(oracle.prim_conserve(np.broadcast_to(prim, (ct.size, ps.np, 4)), GAMMA))
+    prob = FR.TriEulerProblem.from_space(ps, u0, (0.0, 0.1), GAMMA, cell_type=ct)
+    itg = FR.init(prob, FR.Euler(), dt=5e-4)
+    FR.step_(itg, 40)
+
+    sp = T.tri_space(pts, cells, 2)
+    sp["cellType"] = ct
+    ref = oracle.integrate(u0.copy(order="F"), 5e-4, 40, lambda v: T.rhs_tri_euler(v, sp, GAMMA), "euler")
+    assert np.isfinite(itg.u).all() and np.abs(itg.u - u0).max() > 1e-2
+    assert rel(itg.u, ref) <= 1e-10
+    prob.close()

@@ -43,9 +43,9 @@ def test_keyword_constructors(FR):
     assert ps2.xpg.shape == (6, 8, 4, 4, 2)
 
 
-def test_triangle_space_is_declared_out_of_scope(FR):
-    with pytest.raises(NotImplementedError):
-        FR.TriFRPSpace("../assets/linesource.msh", 2)
+def test_triangle_space_needs_a_readable_mesh(FR):
+    with pytest.raises(OSError):
+        FR.TriFRPSpace("../assets/does_not_exist.msh", 2)  # test/runtests.jl:22 builds one from assets/
 
 
 def test_interp_and_derivative_identities(FR):

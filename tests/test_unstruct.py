@@ -1,0 +1,217 @@
+"""Host-side triangle space (fluxreconstruction.jl_b200/unstruct.py: Gmsh reader, mesh connectivity,
+TriFRPSpace of struct.jl:305-352) against the reference's golden tables (dev/check_phi.jl:60-89, WSJ
+points of qpmin.py; fixture tests/golden/tri_golden.npz) and the oracle's literal restatement."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(HERE, ".."))
+sys.path.insert(0, os.path.join(HERE, "..", "oracle"))
+
+import fr_oracle_tri as OT  # noqa: E402
+import frb200 as FR  # noqa: E402
+
+GOLD = np.load(os.path.join(HERE, "golden", "tri_golden.npz"))
+
+
+def write_msh41(path, points, tris, lines=()):
+    """A minimal MSH 4.1 ASCII writer (node tags deliberately not contiguous: 1, 3, 5, ...)."""
+    tag = lambda k: 2 * k + 1  # noqa: E731
+    with open(path, "w") as fh:
+        fh.write("$MeshFormat\n4.1 0 8\n$EndMeshFormat\n")
+        fh.write("$PhysicalNames\n1\n2 1 \"domain\"\n$EndPhysicalNames\n")
+        n = len(points)
+        half = n // 2
+        fh.write(f"$Nodes\n2 {n} 1 {tag(n - 1)}\n")
+        for lo, hi, dim in ((0, half, 1), (half, n, 2)):
+            fh.write(f"{dim} 1 0 {hi - lo}\n")
+            fh.write("".join(f"{tag(k)}\n" for k in range(lo, hi)))
+            fh.write("".join(f"{float(points[k][0])!r} {float(points[k][1])!r} 0\n" for k in range(lo, hi)))
+        fh.write("$EndNodes\n")
+        nblk = 1 + (1 if len(lines) else 0)
+        fh.write(f"$Elements\n{nblk} {len(tris) + len(lines)} 1 {len(tris) + len(lines)}\n")
+        e = 1
+        if len(lines):
+            fh.write(f"1 1 1 {len(lines)}\n")
+            for a, b in lines:
+                fh.write(f"{e} {tag(a)} {tag(b)} \n")
+                e += 1
+        fh.write(f"2 1 2 {len(tris)}\n")
+        for a, b, c in tris:
+            fh.write(f"{e} {tag(a)} {tag(b)} {tag(c)} \n")
+            e += 1
+        fh.write("$EndElements\n")
+
+
+def write_msh22(path, points, tris):
+    with open(path, "w") as fh:
+        fh.write("$MeshFormat\n2.2 0 8\n$EndMeshFormat\n$Nodes\n%d\n" % len(points))
+        for k, p in enumerate(points):
+            fh.write(f"{k + 1} {float(p[0])!r} {float(p[1])!r} 0\n")
+        fh.write("$EndNodes\n$Elements\n%d\n" % (len(tris) + 1))
+        fh.write("1 15 2 0 1 1\n")
+        for k, t in enumerate(tris):
+            fh.write(f"{k + 2} 2 2 0 1 {t[0] + 1} {t[1] + 1} {t[2] + 1}\n")
+        fh.write("$EndElements\n")
+
+
+@pytest.mark.parametrize("deg", [0, 1, 2, 3, 4])
+def test_wsj_points_reproduce_the_reference_tables(deg):
+    lam, w = FR.wsj_points(deg)
+    assert np.array_equal(lam.T.shape, GOLD[f"wsj{deg + 1}_points"].shape)
+    assert np.abs(lam.T - GOLD[f"wsj{deg + 1}_points"]).max() < 2e-16
+    assert np.abs(w - GOLD[f"wsj{deg + 1}_weights"]).max() < 1e-16
+    assert abs(w.sum() - 1.0) < 1e-14 and np.abs(lam.sum(axis=1) - 1.0).max() < 1e-15
+
+
+def test_degree2_tables_of_check_phi():
+    """dev/check_phi.jl:110,117,125 assert V, Vf and the correction field against 8-digit tables."""
+    ps = FR.TriFRPSpace(OT.tri_mesh_rect(1, 1), 2)
+    perm = [0, 2, 4, 1, 3, 5]  # the point reordering check_phi.jl applies (:107-108, :121-123)
+    assert np.abs(ps.V[perm] - GOLD["py_V"]).max() < 5e-8
+    Vf = ps.psif.reshape(9, 6)
+    assert np.abs(Vf - GOLD["py_Vf"]).max() < 5e-8
+    phi = ps.phi.reshape(9, 6).T  # phifj_ref is [np, 3*(deg+1)]
+    assert np.abs(phi[perm] - GOLD["phifj_ref"]).max() < 5e-7
+
+
+@pytest.mark.parametrize("deg", [1, 2, 3, 4])
+def test_operators_match_the_oracle(deg):
+    o = OT.tri_operators(deg)
+    ps = FR.TriFRPSpace(OT.tri_mesh_rect(2, 2), deg)
+    for mine, ref in ((ps.xpl, o["xpl"]), (ps.wp, o["wp"]), (ps.V, o["V"]), (ps.Vr, o["Vr"]), (ps.Vs, o["Vs"]),
+                      (ps.dl, o["dl"]), (ps.xfl, o["xfl"]), (ps.wf, o["wf"]), (ps.psif, o["psif"]),
+                      (ps.lf, o["lf"]), (ps.phi, o["phi"])):
+        assert mine.shape == ref.shape
+        assert np.abs(mine - ref).max() < 2e-12 * max(1.0, np.abs(ref).max())
+
+
+def test_basis_is_orthonormal_and_regular_at_the_top_vertex():
+    # Gauss x Gauss-Jacobi-free check: integrate psi_m psi_n over the triangle with a collapsed tensor rule
+    g, w = np.polynomial.legendre.leggauss(12)
+    a, b = np.meshgrid(g, g, indexing="ij")
+    r, s = 0.5 * (1 + a) * (1 - b) - 1, b
+    wt = np.outer(w, w) * 0.5 * (1 - b)
+    V = FR.simplex_vandermonde(4, r.ravel(), s.ravel())
+    G = V.T @ (wt.ravel()[:, None] * V)
+    assert np.abs(G - np.eye(15)).max() < 1e-12
+    top = FR.simplex_vandermonde(3, np.array([-1.0]), np.array([1.0]))
+    dr, ds = FR.dsimplex_vandermonde(3, np.array([-1.0]), np.array([1.0]))
+    assert np.isfinite(top).all() and np.isfinite(dr).all() and np.isfinite(ds).all()
+
+
+def test_gradient_matrices_differentiate_polynomials():
+    ps = FR.TriFRPSpace(OT.tri_mesh_rect(1, 1), 3)
+    r, s = ps.xpl[:, 0], ps.xpl[:, 1]
+    f = 1 + r - 2 * s + r * s + r**3 - s**2 * r
+    fr, fs = 1 + s + 3 * r**2 - s**2, -2 + r - 2 * s * r
+    assert np.abs(ps.dl[:, :, 0] @ f - fr).max() < 1e-12
+    assert np.abs(ps.dl[:, :, 1] @ f - fs).max() < 1e-12
+    for j in range(3):  # lf interpolates to the face points
+        ff = 1 + ps.xfl[j, :, 0] - 2 * ps.xfl[j, :, 1] + ps.xfl[j, :, 0] * ps.xfl[j, :, 1] + ps.xfl[j, :, 0] ** 3 \
+            - ps.xfl[j, :, 1] ** 2 * ps.xfl[j, :, 0]
+        assert np.abs(ps.lf[j] @ f - ff).max() < 1e-12
+
+
+@pytest.mark.parametrize("deg,jitter", [(1, 0.0), (2, 0.3), (3, 0.3)])
+def test_space_matches_the_oracle_on_a_jittered_mesh(deg, jitter):
+    pts, cid = OT.tri_mesh_rect(5, 4, 0.0, 2.0, -1.0, 1.0, jitter=jitter, seed=3)
+    o = OT.tri_space(pts, cid, deg)
+    ps = FR.TriFRPSpace((pts, cid), deg)
+    assert ps.np == o["np"] and ps.deg == deg
+    assert np.abs(ps.J - o["J"]).max() < 1e-15
+    assert np.abs(ps.xpg - o["xpg"]).max() < 1e-14
+    assert np.abs(ps.xfg - o["xfg"]).max() < 1e-14
+    assert np.abs(ps.cellNormals - o["normals"]).max() < 1e-14
+    assert np.array_equal(ps.fpn, o["fpn"])
+    assert np.array_equal(ps.cellType, o["cellType"])
+
+
+def test_connectivity_invariants():
+    pts, cid = OT.tri_mesh_rect(6, 5, jitter=0.2)
+    m = FR.UnstructPSpace(pts, cid)
+    nc, nf = cid.shape[0], m.facePoints.shape[0]
+    assert nf == 6 * 5 * 3 + 6 + 5  # Euler: interior diagonals + grid edges
+    assert (m.faceType == 1).sum() == 2 * (6 + 5)
+    assert abs(m.cellArea.sum() - 1.0) < 1e-13
+    for i in range(nc):
+        for j in range(3):
+            f = m.cellFaces[i, j]
+            assert set(m.facePoints[f]) == {cid[i, j], cid[i, (j + 1) % 3]}
+            assert i in m.faceCells[f]
+            n = m.cellNeighbors[i, j]
+            assert n == -1 or (i in m.cellNeighbors[n] and set(m.faceCells[f]) == {i, n})
+    # outward normals: sum of n_j * |e_j| over a closed cell vanishes
+    L = m.faceArea[m.cellFaces]
+    assert np.abs((m.cellNormals * L[:, :, None]).sum(axis=1)).max() < 1e-13
+    assert np.abs(np.linalg.norm(m.cellNormals, axis=2) - 1).max() < 1e-14
+
+
+def test_clockwise_cells_keep_outward_normals_and_matching_points():
+    pts, cid = OT.tri_mesh_rect(3, 3)
+    cid = cid.copy()
+    cid[::2] = cid[::2, ::-1]  # every other cell clockwise
+    ps = FR.TriFRPSpace((pts, cid), 2)
+    mid = 0.5 * (pts[cid] + pts[np.roll(cid, -1, axis=1)])
+    assert (np.sum(ps.cellNormals * (mid - ps.cellCenter[:, None]), axis=2) > 0).all()
+    i, j, k = np.nonzero(ps.fpn[..., 0] >= 0)
+    n = ps.fpn[i, j, k]
+    assert np.abs(ps.xfg[i, j, k] - ps.xfg[n[:, 0], n[:, 1], n[:, 2]]).max() < 1e-14
+
+
+@pytest.mark.parametrize("writer", ["41", "22"])
+def test_msh_reader_round_trip(tmp_path, writer):
+    pts, cid = OT.tri_mesh_rect(4, 3, jitter=0.25, seed=1)
+    f = str(tmp_path / "m.msh")
+    if writer == "41":
+        write_msh41(f, pts, cid, lines=[(0, 1), (1, 2)])
+    else:
+        write_msh22(f, pts, cid)
+    p, cells = FR.read_msh(f)
+    assert p.shape == (pts.shape[0], 3) and np.array_equal(p[:, :2], pts) and (p[:, 2] == 0).all()
+    assert np.array_equal(cells["triangle"], cid)
+    if writer == "41":
+        assert np.array_equal(cells["line"], [[0, 1], [1, 2]])
+    ps = FR.TriFRPSpace(f, 2)
+    o = OT.tri_space(pts, cid, 2)
+    assert np.array_equal(ps.fpn, o["fpn"]) and np.abs(ps.xpg - o["xpg"]).max() < 1e-14
+
+
+def test_msh_reader_rejects_what_it_cannot_read(tmp_path):
+    f = tmp_path / "bad.msh"
+    f.write_text("$MeshFormat\n4.1 1 8\n$EndMeshFormat\n$Nodes\n$EndNodes\n$Elements\n$EndElements\n")
+    with pytest.raises(ValueError, match="binary"):
+        FR.read_msh(str(f))
+    f.write_text("$MeshFormat\n4.1 0 8\n$EndMeshFormat\n$Nodes\n1 3 1 3\n2 1 0 3\n1\n2\n3\n0 0 0\n1 0 0\n0 1 0\n$EndNodes\n"
+                 "$Elements\n1 1 1 1\n2 1 9 1\n1 1 2 3 1 2 3\n$EndElements\n")
+    with pytest.raises(ValueError, match="element type 9"):
+        FR.read_msh(str(f))
+    f.write_text("hello\n")
+    with pytest.raises(ValueError, match="not a Gmsh mesh"):
+        FR.read_msh(str(f))
+
+
+@pytest.mark.parametrize("name", ["sod.msh", "linesource.msh", "square.msh", "naca0012.msh"])
+def test_reference_assets_read_here(name):
+    """test/runtests.jl:22 builds TriFRPSpace("../assets/linesource.msh", 2); the assets only exist in the
+    build container (skipped elsewhere)."""
+    path = os.path.join("/root/reference/assets", name)
+    if not os.path.exists(path):
+        pytest.skip("reference assets not present")
+    ps = FR.TriFRPSpace(path, 2)
+    nc = ps.cellid.shape[0]
+    assert nc > 100 and ps.np == 6 and ps.fpn.shape == (nc, 3, 3, 3)
+    i, j, k = np.nonzero(ps.fpn[..., 0] >= 0)
+    n = ps.fpn[i, j, k]
+    assert np.abs(ps.xfg[i, j, k] - ps.xfg[n[:, 0], n[:, 1], n[:, 2]]).max() < 1e-12
+    assert (np.linalg.det(ps.J) > 0).all()  # Gmsh writes counter-clockwise triangles
+    # the line elements of the file are boundary faces (sod.msh tags two of its four sides only)
+    nb = (ps.faceType == 1).sum()
+    assert nb >= ps.cells["line"].shape[0] > 0 and nb == (ps.fpn[:, :, 0, 0] < 0).sum()
+    edges = {tuple(sorted(e)) for e in ps.facePoints[ps.faceType == 1].tolist()}
+    assert all(tuple(sorted(e)) in edges for e in ps.cells["line"].tolist())
+    L = ps.faceArea[ps.cellFaces]
+    assert np.abs((ps.cellNormals * L[:, :, None]).sum(axis=1)).max() < 1e-12
