@@ -6,7 +6,7 @@ from ._lib import Context, FRBError, LIB_PATH, SIGNATURES, lib, pinned_empty, pi
 from .spaces import *  # noqa: F401,F403
 from .unstruct import *  # noqa: F401,F403
 from .problems import (  # noqa: F401
-    BGKProblem, DistributedEuler2D, Euler, Euler2DProblem, FRAdvectionProblem, FREulerProblem, Integrator, Midpoint, NSCavityProblem, SSPRK33, TriEulerProblem, init, ref_vhs_vis,
+    BGKProblem, DistributedEuler2D, Euler, Euler2DProblem, ExplicitRK, RK4, Tsit5, FRAdvectionProblem, FREulerProblem, Integrator, Midpoint, NSCavityProblem, SSPRK33, TriEulerProblem, init, ref_vhs_vis,
     solve, step_,
 )
 from . import partition  # noqa: F401

@@ -59,6 +59,7 @@ SIGNATURES = {
     "frb_rhs_pipelined": (C.c_int32, [C.c_void_p, c_dp, c_dp, C.c_int32]),
     "frb_set_step_hooks": (C.c_int32, [C.c_void_p, C.c_int32, c_dp]),
     "frb_step": (C.c_int32, [C.c_void_p, C.c_int32, C.c_double, C.c_int32]),
+    "frb_step_tableau": (C.c_int32, [C.c_void_p, C.c_int32, c_dp, c_dp, C.c_double, C.c_int32]),
     "frb_ghost_fill": (C.c_int32, [C.c_void_p, C.c_int32]),
     "frb_limiter_positivity": (C.c_int32, [C.c_void_p, c_dp, C.POINTER(C.c_int32)]),
     "frb_filter_modal": (C.c_int32, [C.c_void_p, c_dp, c_dp, C.c_int32, C.c_double, C.c_double, C.c_double,

@@ -782,6 +782,47 @@ static int one_step(frb_prob_t p, int scheme, double dt, bool rc) {
   return FRB_OK;
 }
 
+// One step of an explicit Runge-Kutta scheme given by its tableau, in the reference image:
+// k_i = L(u + dt sum_j a_ij k_j) through the rhs_only form of the stage kernels, combinations by
+// frb_launch_lincomb over the whole array (k_j = 0 in the ghosts: they stay frozen through the step).
+struct RkTab {
+  int ns;
+  double A[FRB_RK_MAX_STAGES * FRB_RK_MAX_STAGES], b[FRB_RK_MAX_STAGES];
+};
+
+static int tableau_step(frb_prob_t p, const RkTab &tab, double dt) {
+  int n;
+  if (p->filt_when == 1) {
+    if ((n = run_filter(p)) < 0) return n;
+  }
+  if (p->limiter_on) {
+    if ((n = run_limiter(p)) < 0) return n;
+  }
+  if (p->ghost_mode != FRB_GHOST_NONE) {
+    if ((n = frb_launch_ghost_fill2d(p, p->u, p->ghost_mode)) < 0) return n;
+    p->launches += n;
+  }
+  const FrbStage rhs = {0.0, 0.0, 1.0, 0, 1, 0};
+  for (int i = 0; i < tab.ns; ++i) {
+    const double *row = tab.A + i * tab.ns;
+    const double *src = p->u;
+    bool any = false;
+    for (int j = 0; j < i; ++j) any = any || row[j] != 0.0;
+    if (any) {
+      if ((n = frb_launch_lincomb(p, p->s1, p->u, i, p->rk_k.data(), row, dt)) < 0) return n;
+      p->launches += n;
+      src = p->s1;
+    }
+    if ((n = launch_stage(p, src, nullptr, p->rk_k[i], rhs)) < 0) return n;
+  }
+  if ((n = frb_launch_lincomb(p, p->u, p->u, tab.ns, p->rk_k.data(), tab.b, dt)) < 0) return n;
+  p->launches += n;
+  if (p->filt_when == 2) {
+    if ((n = run_filter(p)) < 0) return n;
+  }
+  return FRB_OK;
+}
+
 // bring the row-chunk mirror up to date (first RC step after an upload / a reference-image call)
 static int need_rc(frb_prob_t p) {
   if (p->rc_valid) return FRB_OK;
@@ -805,11 +846,12 @@ static int need_rc(frb_prob_t p) {
 // they do the lazy allocations, descriptor caches and attribute opt-ins that must not happen inside
 // a capture.  Not used with per-stage profiling (event pairs) or the slab-parallel path (the halo
 // epochs are kernel arguments that change every stage).
-static int run_steps(frb_prob_t p, int scheme, double dt, bool rc, int nsteps) {
+static int run_steps(frb_prob_t p, int scheme, double dt, bool rc, int nsteps, const RkTab *tab = nullptr) {
   cudaStream_t s = p->ctx->stream;
   int it = 0, r;
   const bool graphable = nsteps >= 16 && !p->profiling && !frb_halo_active(p) && !getenv("FRB_NO_GRAPH");
-  if (graphable && p->filt_when == 0 && !getenv("FRB_NO_LOOP1D")) {
+  auto step = [&]() { return tab ? tableau_step(p, *tab, dt) : one_step(p, scheme, dt, rc); };
+  if (graphable && !tab && p->filt_when == 0 && !getenv("FRB_NO_LOOP1D")) {
     // small 1-D problems: the whole loop in one cooperative launch (grid barrier instead of launches)
     r = frb_launch_loop1d(p, scheme, dt, nsteps);
     if (r < 0) return r;
@@ -820,14 +862,14 @@ static int run_steps(frb_prob_t p, int scheme, double dt, bool rc, int nsteps) {
   }
   if (graphable) {
     for (; it < 2; ++it)
-      if ((r = one_step(p, scheme, dt, rc)) < 0) return r;
+      if ((r = step()) < 0) return r;
     const int pairs = (nsteps - it) / 2;
     cudaGraph_t graph = nullptr;
     cudaGraphExec_t exec = nullptr;
     FRB_CUDA(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
     const int64_t l0 = p->launches;
-    r = one_step(p, scheme, dt, rc);
-    if (r >= 0) r = one_step(p, scheme, dt, rc);
+    r = step();
+    if (r >= 0) r = step();
     cudaError_t ce = cudaStreamEndCapture(s, &graph);  // always: leaves the stream usable
     if (r < 0) {
       if (graph) cudaGraphDestroy(graph);
@@ -848,7 +890,7 @@ static int run_steps(frb_prob_t p, int scheme, double dt, bool rc, int nsteps) {
     it += 2 * pairs;
   }
   for (; it < nsteps; ++it)
-    if ((r = one_step(p, scheme, dt, rc)) < 0) return r;
+    if ((r = step()) < 0) return r;
   return FRB_OK;
 }
 
@@ -880,6 +922,48 @@ extern "C" int32_t frb_step(frb_prob_t p, int32_t scheme, double dt, int32_t nst
   p->last_launches = p->launches - l0;
   prof_collect(p);
   if (int r = frb_halo_check_timeout(p)) return r;
+  if (bad) {
+    frb_set_error("incorrect range of limiter parameter t");
+    return FRB_ERR_NUMERIC;
+  }
+  return FRB_OK;
+}
+
+extern "C" int32_t frb_step_tableau(frb_prob_t p, int32_t ns, const double *A, const double *b, double dt,
+                                    int32_t nsteps) {
+  FRB_REQUIRE(p && A && b, FRB_ERR_ARG, "frb_step_tableau: NULL argument");
+  FRB_REQUIRE(ns >= 1 && ns <= FRB_RK_MAX_STAGES, FRB_ERR_ARG, "frb_step_tableau: nstage must be 1..8");
+  FRB_REQUIRE(nsteps >= 0, FRB_ERR_ARG, "frb_step_tableau: nsteps must be >= 0");
+  FRB_REQUIRE(!frb_halo_active(p), FRB_ERR_STATE, "frb_step_tableau: not available on the slab-parallel path");
+  FRB_CUDA(cudaSetDevice(p->ctx->device));
+  cudaStream_t s = p->ctx->stream;
+  RkTab tab;
+  tab.ns = ns;
+  for (int i = 0; i < ns; ++i) {
+    tab.b[i] = b[i];
+    for (int j = 0; j < ns; ++j) tab.A[i * ns + j] = j < i ? A[i * ns + j] : 0.0;
+  }
+  const int64_t l0 = p->launches;
+  prof_begin(p);
+  if (nsteps > 0) {
+    if (int r = need_ref(p, true)) return r;
+    while ((int)p->rk_k.size() < ns) {
+      double *k = nullptr;
+      FRB_CUDA(cudaMalloc(&k, sizeof(double) * (size_t)p->len));
+      p->rk_k.push_back(k);
+      FRB_CUDA(cudaMemsetAsync(k, 0, sizeof(double) * (size_t)p->len, s));
+    }
+  }
+  if (p->limiter_on) FRB_CUDA(cudaMemsetAsync(p->flag, 0, sizeof(int), s));
+  FRB_CUDA(cudaEventRecord(p->ev0, s));
+  if (int r = run_steps(p, -1, dt, false, nsteps, &tab)) return r;
+  FRB_CUDA(cudaEventRecord(p->ev1, s));
+  int bad = 0;
+  if (p->limiter_on) FRB_CUDA(cudaMemcpyAsync(&bad, p->flag, sizeof(int), cudaMemcpyDeviceToHost, s));
+  FRB_CUDA(cudaStreamSynchronize(s));
+  FRB_CUDA(cudaEventElapsedTime(&p->last_ms, p->ev0, p->ev1));
+  p->last_launches = p->launches - l0;
+  prof_collect(p);
   if (bad) {
     frb_set_error("incorrect range of limiter parameter t");
     return FRB_ERR_NUMERIC;

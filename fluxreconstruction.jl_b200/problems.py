@@ -54,6 +54,53 @@ class SSPRK33:
     stages = 3
 
 
+class ExplicitRK:
+    """Any explicit Runge-Kutta scheme by its Butcher tableau (``frb_step_tableau``): ``A`` strictly
+    lower triangular [s, s], ``b`` [s]."""
+
+    code = -1
+
+    def __init__(self, A, b):
+        self.A = np.ascontiguousarray(A, dtype=np.float64)
+        self.b = np.ascontiguousarray(b, dtype=np.float64)
+        self.stages = self.b.size
+        if self.A.shape != (self.stages, self.stages) or np.triu(self.A).any():
+            raise ValueError("A must be a strictly lower triangular [s, s] matrix")
+
+    @property
+    def tableau(self):
+        return self.A, self.b
+
+
+class RK4(ExplicitRK):
+    """The classical fourth-order scheme (OrdinaryDiffEq's RK4 with adaptive=false)."""
+
+    def __init__(self):
+        A = np.zeros((4, 4))
+        A[1, 0], A[2, 1], A[3, 2] = 0.5, 0.5, 1.0
+        super().__init__(A, [1 / 6, 1 / 3, 1 / 3, 1 / 6])
+
+
+class Tsit5(ExplicitRK):
+    """Tsitouras' 5(4) pair as the reference uses it: fixed step, ``adaptive=false, dt=dt``
+    (example/advection_highlevel.jl:26, example/euler1d_convergence.jl:133).  Coefficients:
+    Ch. Tsitouras, Comput. Math. Appl. 62 (2011) 770-775; the seventh (FSAL) stage only feeds the error
+    estimate and the next step's k1, so six stages are evaluated.  tests/ verify the 17 order
+    conditions up to order 5 on this table."""
+
+    def __init__(self):
+        A = np.zeros((6, 6))
+        A[1, :1] = [0.161]
+        A[2, :2] = [-0.008480655492356989, 0.335480655492357]
+        A[3, :3] = [2.8971530571054935, -6.359448489975075, 4.3622954328695815]
+        A[4, :4] = [5.325864828439257, -11.748883564062828, 7.4955393428898365, -0.09249506636175525]
+        A[5, :5] = [5.86145544294642, -12.92096931784711, 8.159367898576159, -0.071584973281401,
+                    -0.028269050394068383]
+        b = [0.09646076681806523, 0.01, 0.4798896504144996, 1.379008574103742, -3.290069515436081,
+             2.324710524099774]
+        super().__init__(A, b)
+
+
 def modal_filter_diag(n, lam):
     """[KB] KitBase.modal_filter!(u, lam; filter=:l2) as a diagonal: mode k >= 1 is divided by
     1 + lam k^2 (k+1)^2."""
@@ -149,7 +196,11 @@ class _Problem:
         check(lib().frb_set_step_hooks(self.h, GHOST[ghost], None if w is None else _lib.dptr(w.ravel(order="F"))))
 
     def step(self, alg, dt, nsteps=1):
-        check(lib().frb_step(self.h, alg.code, float(dt), int(nsteps)))
+        if hasattr(alg, "tableau"):
+            A, b = alg.tableau
+            check(lib().frb_step_tableau(self.h, b.size, _lib.dptr(A.ravel()), _lib.dptr(b), float(dt), int(nsteps)))
+        else:
+            check(lib().frb_step(self.h, alg.code, float(dt), int(nsteps)))
 
     def ghost_fill(self, mode):
         check(lib().frb_ghost_fill(self.h, GHOST[mode]))

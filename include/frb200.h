@@ -148,6 +148,14 @@ int32_t frb_set_step_hooks(frb_prob_t prob, int32_t ghost_mode, const double *li
 /* nsteps fixed steps of the resident state, fused RHS + stage update kernels, no host
  * synchronisation between steps.  Synchronous at return. */
 int32_t frb_step(frb_prob_t prob, int32_t scheme, double dt, int32_t nsteps);
+/* the same loop for any explicit Runge-Kutta scheme given by its Butcher tableau -- the fixed-step
+ * Tsit5() of example/advection_highlevel.jl:26 and example/euler1d_convergence.jl:133
+ * (adaptive=false, dt=dt), RK4, Heun, ...:  k_i = L(u + dt * sum_{j<i} A[i*nstage + j] k_j),
+ * u <- u + dt * sum_i b[i] k_i.  A is row-major nstage x nstage (strictly lower part read),
+ * nstage <= FRB_RK_MAX_STAGES.  Same per-step hooks as frb_step; single-GPU problems only. */
+#define FRB_RK_MAX_STAGES 8
+int32_t frb_step_tableau(frb_prob_t prob, int32_t nstage, const double *A, const double *b, double dt,
+                         int32_t nsteps);
 /* the hooks as stand-alone calls on the resident state */
 int32_t frb_ghost_fill(frb_prob_t prob, int32_t ghost_mode);
 /* positive_limiter(u, gamma, weights, ll, lr) src/dissipation.jl:61-123,125-206 on every

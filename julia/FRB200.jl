@@ -137,6 +137,11 @@ set_flux!(p::Problem, flux::Symbol) = check(ccall((:frb_set_flux, lib), Int32, (
     Int32(Dict(:hll => 0, :lf => 1, :roe => 2)[flux])))
 step!(p::Problem, scheme::Symbol, dt, nsteps = 1) = check(ccall((:frb_step, lib), Int32,
     (Ptr{Cvoid}, Int32, Float64, Int32), p.h, SCHEME[scheme], dt, nsteps))
+# any explicit RK scheme by its tableau, e.g. the fixed-step Tsit5() of advection_highlevel.jl:26: pass
+# OrdinaryDiffEq's constructTsitouras5() / constructRK4() tableau (A strictly lower triangular, weights b);
+# A is handed over row-major, hence the transpose
+step!(p::Problem, A::Matrix{Float64}, b::Vector{Float64}, dt, nsteps = 1) = check(ccall((:frb_step_tableau, lib),
+    Int32, (Ptr{Cvoid}, Int32, Ptr{Float64}, Ptr{Float64}, Float64, Int32), p.h, length(b), permutedims(A), b, dt, nsteps))
 function positive_limiter!(p::Problem, weights)      # src/dissipation.jl:61-206 on every interior cell
     nbad = Ref{Int32}(0)
     check(ccall((:frb_limiter_positivity, lib), Int32, (Ptr{Cvoid}, Ptr{Float64}, Ref{Int32}), p.h, weights, nbad)); nbad[]

@@ -832,7 +832,35 @@ def step(u, dt, rhs, scheme="midpoint"):
         u1 = u + dt * rhs(u)
         u2 = 0.75 * u + 0.25 * (u1 + dt * rhs(u1))
         return (1.0 / 3.0) * u + (2.0 / 3.0) * (u2 + dt * rhs(u2))
+    if scheme in RK_TABLEAUS:
+        A, b = RK_TABLEAUS[scheme]
+        k = []
+        for i in range(len(b)):
+            ui = u
+            if any(A[i][j] != 0.0 for j in range(i)):
+                ui = u + dt * sum(A[i][j] * k[j] for j in range(i) if A[i][j] != 0.0)
+            k.append(rhs(ui))
+        return u + dt * sum(b[j] * k[j] for j in range(len(b)) if b[j] != 0.0)
     raise ValueError(scheme)
+
+
+# Explicit tableaus for the schemes the reference's scripts use besides Euler / Midpoint:
+# Tsit5 with adaptive=false (advection_highlevel.jl:26, euler1d_convergence.jl:133) -- the six
+# evaluated stages of Tsitouras (2011) in OrdinaryDiffEq's u = uprev + dt * (a_i1 k1 + ...) form -- and RK4.
+RK_TABLEAUS = {
+    "rk4": ([[0, 0, 0, 0], [0.5, 0, 0, 0], [0, 0.5, 0, 0], [0, 0, 1.0, 0]], [1 / 6, 1 / 3, 1 / 3, 1 / 6]),
+    "tsit5": (
+        [
+            [0, 0, 0, 0, 0, 0],
+            [0.161, 0, 0, 0, 0, 0],
+            [-0.008480655492356989, 0.335480655492357, 0, 0, 0, 0],
+            [2.8971530571054935, -6.359448489975075, 4.3622954328695815, 0, 0, 0],
+            [5.325864828439257, -11.748883564062828, 7.4955393428898365, -0.09249506636175525, 0, 0],
+            [5.86145544294642, -12.92096931784711, 8.159367898576159, -0.071584973281401, -0.028269050394068383, 0],
+        ],
+        [0.09646076681806523, 0.01, 0.4798896504144996, 1.379008574103742, -3.290069515436081, 2.324710524099774],
+    ),
+}
 
 
 def integrate(u, dt, nsteps, rhs, scheme="midpoint", before_step=None):

@@ -606,3 +606,85 @@ def test_cfg3_full_size_1000_steps_track_the_exact_wave(FR, oracle):
     assert np.abs(c[..., 2]).max() <= 1e-9                # no y momentum
     assert np.abs(c[..., 3] - (0.5 / (GAMMA - 1.0) + 0.5 * rho)).max() <= 1e-9
     prob.close()
+
+
+# ---------------------------------------------------------------- explicit RK by tableau (Tsit5, RK4)
+def _butcher_ssprk3():
+    A = np.zeros((3, 3))
+    A[1, 0], A[2, 0], A[2, 1] = 1.0, 0.25, 0.25
+    return A, [1 / 6, 1 / 6, 2 / 3]
+
+
+def test_advection_highlevel_tsit5(FR, oracle):
+    """example/advection_highlevel.jl:14-28: FRAdvectionProblem + init(prob, Tsit5(); adaptive=false, dt)."""
+    ps = FR.FRPSpace1D(-1.0, 1.0, 100, 2)
+    u0 = oracle.ic_advection1d(ps)
+    dt = 0.05 * 0.02
+    prob = FR.FRAdvectionProblem(u0, (0.0, 1.0), ps, 1.0, "period")
+    itg = FR.init(prob, FR.Tsit5(), dt=dt)
+    FR.step_(itg, 400)
+    ref = oracle.integrate(u0, dt, 400, lambda v: oracle.rhs_advection1d(v, ps, 1.0, "period"), "tsit5")
+    assert np.abs(itg.u - u0).max() > 0.5 and rel(itg.u, ref) <= RTOL_1000
+    prob.close()
+
+
+@pytest.mark.parametrize("alg", ["tsit5", "rk4"])
+def test_euler1d_convergence_script_stepper(FR, oracle, alg):
+    """example/euler1d_convergence.jl:125-133: periodic density wave, solve(prob, Tsit5(); adaptive=false, dt)."""
+    ps = FR.FRPSpace1D(0.0, 1.0, 40, 3)
+    u0 = oracle.ic_wave1d(ps, GAMMA)
+    dt = 2e-4
+    prob = FR.FREulerProblem(u0, (0.0, 0.06), ps, GAMMA, "period")
+    itg = FR.solve(prob, {"tsit5": FR.Tsit5, "rk4": FR.RK4}[alg](), dt=dt)
+    assert itg.iter == 300
+    ref = oracle.integrate(u0, dt, 300, lambda v: oracle.rhs_euler1d(v, ps, GAMMA, "period"), alg)
+    assert rel(itg.u, ref) <= RTOL_1000
+    prob.close()
+
+
+@pytest.mark.parametrize("kernel", ["generic", "march"])
+def test_euler2d_tsit5_with_ghost_hook(FR, oracle, kernel):
+    ps = FR.FRPSpace2D(0.0, 1.0, 16, 0.0, 1.0, 12, 3, 1, 1)
+    u0 = oracle.ic_wave2d(ps, GAMMA, "x")
+    dt = 5e-4
+    prob = FR.Euler2DProblem(u0, (0.0, 0.5), ps, GAMMA, kernel=kernel)
+    itg = FR.init(prob, FR.Tsit5(), dt=dt)
+    itg.set_hooks(ghost="wave_x")
+    FR.step_(itg, 40)
+    ref = oracle.integrate(u0, dt, 40, lambda v: oracle.rhs_euler2d(v, ps, GAMMA), "tsit5",
+                           before_step=lambda v: oracle.ghost_fill_euler2d(v, "wave_x"))
+    assert rel(itg.u, ref) <= RTOL_1000
+    # and the row-chunk loop can take over afterwards (the mirror is refreshed from the reference image)
+    itg2 = FR.init(prob, FR.SSPRK33(), dt=dt)
+    FR.step_(itg2, 3)
+    ref = oracle.integrate(ref, dt, 3, lambda v: oracle.rhs_euler2d(v, ps, GAMMA), "ssprk3",
+                           before_step=lambda v: oracle.ghost_fill_euler2d(v, "wave_x"))
+    assert rel(itg2.u, ref) <= RTOL_1000
+    prob.close()
+
+
+def test_tableau_form_of_ssprk3_equals_the_fused_stages(FR, oracle):
+    """The generic path on the kinetic problem: Butcher form of SSPRK3 against the Shu-Osher stages."""
+    ps = FR.FRPSpace1D(0.0, 1.0, 48, 2)
+    velo, wts = oracle.vspace1d(-5.0, 5.0, 32)
+    f0 = oracle.ic_bgk1d(ps, velo)
+    dt = 0.1 * ps.dx[0] / 5.0
+    out = []
+    for alg in (FR.SSPRK33(), FR.ExplicitRK(*_butcher_ssprk3())):
+        prob = FR.BGKProblem(f0, (0.0, 1.0), ps, velo, wts, 1e-2)
+        itg = FR.init(prob, alg, dt=dt)
+        FR.step_(itg, 50)
+        out.append(itg.u.copy())
+        prob.close()
+    assert np.abs(out[0] - f0).max() > 1e-3 and rel(out[1], out[0]) <= 1e-12
+
+
+def test_tableau_arguments_are_checked(FR, oracle):
+    ps = FR.FRPSpace1D(-1.0, 1.0, 10, 2)
+    prob = FR.FRAdvectionProblem(oracle.ic_advection1d(ps), (0.0, 1.0), ps, 1.0, "period")
+    with pytest.raises(ValueError):
+        FR.ExplicitRK(np.ones((2, 2)), [0.5, 0.5])
+    big = FR.ExplicitRK(np.tril(np.ones((9, 9)), -1) / 9, np.ones(9) / 9)
+    with pytest.raises(FR.FRBError, match="nstage"):
+        prob.step(big, 1e-3, 1)
+    prob.close()

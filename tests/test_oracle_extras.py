@@ -101,3 +101,46 @@ def test_triangle_residual_freestream_and_convergence():
         act = sp["cellType"] == 0
         errs.append(np.abs(du[act, :, 0] - exact[act]).max())
     assert errs[1] < 0.7 * errs[0]  # the derivative of a degree-2 reconstruction converges
+
+
+# ------------------------------------------------------------------ explicit RK tableaus (Tsit5, RK4)
+def _order_conditions(A, b):
+    A, b = np.array(A, dtype=np.float64), np.array(b, dtype=np.float64)
+    c = A.sum(axis=1)
+    Ac = A @ c
+    return [
+        (b.sum(), 1), (b @ c, 1 / 2), (b @ c**2, 1 / 3), (b @ Ac, 1 / 6),
+        (b @ c**3, 1 / 4), (b @ (c * Ac), 1 / 8), (b @ (A @ c**2), 1 / 12), (b @ (A @ Ac), 1 / 24),
+        (b @ c**4, 1 / 5), (b @ (c**2 * Ac), 1 / 10), (b @ (Ac * Ac), 1 / 20), (b @ (c * (A @ c**2)), 1 / 15),
+        (b @ (A @ c**3), 1 / 20), (b @ (c * (A @ Ac)), 1 / 30), (b @ (A @ (c * Ac)), 1 / 40),
+        (b @ (A @ (A @ c**2)), 1 / 60), (b @ (A @ (A @ Ac)), 1 / 120),
+    ]
+
+
+def test_tsit5_tableau_satisfies_all_order_conditions_up_to_5():
+    """No Julia here to print OrdinaryDiffEq's table: the 17 rooted-tree conditions pin the digits."""
+    import fr_oracle as O
+    import frb200 as FR
+
+    for A, b in (O.RK_TABLEAUS["tsit5"], FR.Tsit5().tableau):
+        for got, want in _order_conditions(A, b):
+            assert abs(got - want) < 3e-14  # coefficients of size 12 cancel
+        c = np.array(A).sum(axis=1)
+        assert np.allclose(c, [0, 0.161, 0.327, 0.9, 0.9800255409045097, 1.0], atol=1e-15)
+    for got, want in _order_conditions(*O.RK_TABLEAUS["rk4"])[:8]:
+        assert abs(got - want) < 1e-15
+    assert np.array_equal(FR.RK4().A, np.array(O.RK_TABLEAUS["rk4"][0]))
+
+
+def test_tableau_stepping_converges_at_design_order():
+    import fr_oracle as O
+
+    rhs = lambda u: np.array([u[1], -u[0]])  # noqa: E731  harmonic oscillator
+    exact = np.array([np.sin(1.0), np.cos(1.0)])
+    for scheme, order in (("rk4", 4), ("tsit5", 5)):
+        err = []
+        for n in (8, 16, 32):
+            u = O.integrate(np.array([0.0, 1.0]), 1.0 / n, n, rhs, scheme)
+            err.append(np.abs(u - exact).max())
+        rates = np.log2(np.array(err[:-1]) / np.array(err[1:]))
+        assert (rates > order - 0.3).all(), (scheme, err, rates)
