@@ -21,7 +21,7 @@ FLAGS = [
 ]
 
 # the latency-bound 1-D kernels keep the reference's literal operation order (see the file header)
-PER_FILE_FLAGS = {"frb_kernels_1d.cu": ["-fmad=false"]}
+PER_FILE_FLAGS = {"frb_kernels_1d.cu": ["-fmad=false"], "frb_rk.cu": ["-fmad=false"]}
 
 
 def sources():
