@@ -230,13 +230,20 @@ limiter1d_kernel(double *__restrict__ u, int ncell, double gamma, const double *
 // The smallest 1-D problems of the reference (cfg1: 100 cells, 2.4 KB) are pure launch latency: a stage
 // runs for about a microsecond, a launch costs 5 us eagerly and ~3 us as a graph node.  Up to 512 cells
 // the whole time loop runs in ONE CTA with a block barrier after every pass (cfg1, SSPRK3: 9.3 -> 2.9 us
-// per step).  Same cell routines, same stage sequence and buffer roles as frb_step's host loop.  The
-// multi-CTA form (grid barrier through a global counter, cooperative launch) is kept behind
-// FRB_LOOP1D_GRID: at 32 CTAs (cfg2) a barrier costs more than the launch it replaces (28.0 vs 26.7 us per
-// step against the graph replay), so it is off by default.
+// per step).  Same cell routines, same stage sequence and buffer roles as frb_step's host loop.
+// Two multi-CTA forms exist behind environment switches, both measured slower than the CUDA-graph replay
+// of the host loop at cfg2 (4096 cells, Midpoint + limiter: 26.7 us per step as a graph):
+//   FRB_LOOP1D_CLUSTER  one thread-block cluster of up to 16 CTAs, hardware cluster barrier
+//                       (barrier.cluster.arrive.release / wait.acquire) after every pass: 34.6 us per step
+//                       with 8 CTAs x 512 cells, 32.2 us with 16 x 256 -- the barrier is cheap, but a pass
+//                       is one long FP64 dependency chain per cell (IEEE divisions and square roots in the
+//                       reference's operation order) and the 512-thread register budget (128, spills)
+//                       lengthens it: ~11 us per pass against ~6 us for the 128-thread stage kernel;
+//   FRB_LOOP1D_GRID     cooperative launch, grid barrier through a global counter: 28.0 us per step.
 struct Loop1dArgs {
   double *u, *s1, *s2;       // state and stage buffers (roles as on the host)
   unsigned *bar;             // grid barrier: arrival counter
+  int cluster;               // the grid is one cluster: hardware barrier
   int nsteps, scheme;
   double dt;
   const double *lim_w;       // limiter hook (Euler) or nullptr
@@ -245,7 +252,11 @@ struct Loop1dArgs {
 
 // release on arrival, acquire on the poll: the CTA's writes (ordered before thread 0 by bar.sync) are
 // visible to every thread that leaves the barrier; no stand-alone membar on either side
-__device__ __forceinline__ void grid_barrier(unsigned *bar, unsigned &round) {
+__device__ __forceinline__ void grid_barrier(unsigned *bar, unsigned &round, int cluster) {
+  if (cluster) {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+    return;
+  }
   __syncthreads();
   if (gridDim.x > 1) {
     if (threadIdx.x == 0) {
@@ -273,12 +284,12 @@ loop1d_kernel(Loop1dArgs L, Adv1dArgs AA, Euler1dArgs EA, FrbOps ops) {
       if (EULER) euler1d_cell<NSP>(i, in, ua, out, EA, ops, st);
       else adv1d_cell<NSP>(i, in, ua, out, AA, ops, st);
     }
-    grid_barrier(L.bar, round);
+    grid_barrier(L.bar, round, L.cluster);
   };
   for (int it = 0; it < L.nsteps; ++it) {
     if (EULER && L.lim_w) {
       if (live) limiter1d_cell<NSP>(i, U, ncell, EA.gamma, L.lim_w, ops, L.nbad);
-      grid_barrier(L.bar, round);
+      grid_barrier(L.bar, round, L.cluster);
     }
     const double dt = L.dt;
     if (L.scheme == FRB_SCHEME_EULER) {
@@ -355,15 +366,24 @@ int frb_launch_dirichlet_copy1d(frb_prob_t, const double *, double *) { return 0
 int frb_launch_loop1d(frb_prob_t p, int scheme, double dt, int nsteps) {
   if (p->kind != K_ADV1D && p->kind != K_EULER1D) return 0;
   const bool grid_form = getenv("FRB_LOOP1D_GRID") != nullptr;
-  const int threads = grid_form ? 128 : ((p->ncell + 31) / 32) * 32;
-  const int blocks = grid_form ? (p->ncell + 127) / 128 : 1;
+  const bool cluster_form = !grid_form && p->ncell > 512 && getenv("FRB_LOOP1D_CLUSTER") != nullptr;
+  int threads = grid_form ? 128 : ((p->ncell + 31) / 32) * 32;
+  int blocks = grid_form ? (p->ncell + 127) / 128 : 1;
+  if (cluster_form) {
+    const char *e = getenv("FRB_CLUSTER1D_CTAS");
+    const int want = e ? atoi(e) : 16;
+    blocks = (p->ncell + 511) / 512;
+    if (blocks > 16) return 0;
+    if (want > blocks && want <= 16) blocks = want;  // spread over more SMs: the passes are FP64 bound
+    threads = (((p->ncell + blocks - 1) / blocks + 31) / 32) * 32;
+  }
   if (threads > 512 || blocks > p->ctx->sm_count || nsteps <= 0) return 0;
   static int coop = -1;
   if (coop < 0) cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, p->ctx->device);
-  if (!coop) return 0;
+  if (!coop && !cluster_form) return 0;
   if (!p->loop_bar) FRB_CUDA(cudaMalloc(&p->loop_bar, sizeof(unsigned)));
   FRB_CUDA(cudaMemsetAsync(p->loop_bar, 0, sizeof(unsigned), p->ctx->stream));
-  Loop1dArgs L = {p->u, p->s1, p->s2, p->loop_bar, nsteps, scheme, dt,
+  Loop1dArgs L = {p->u, p->s1, p->s2, p->loop_bar, cluster_form ? 1 : 0, nsteps, scheme, dt,
                   (p->kind == K_EULER1D && p->limiter_on) ? p->lim_w : nullptr, p->flag};
   const double eps = p->variant == FRB_ADV_LOWLEVEL ? 1e-8 : 1e-6;
   Adv1dArgs AA = {p->J, p->ncell, p->a, p->variant == FRB_ADV_LOWLEVEL ? FRB_BC_PERIOD : p->bc, eps};
@@ -377,7 +397,38 @@ int frb_launch_loop1d(frb_prob_t p, int scheme, double dt, int nsteps) {
     default: return 0;
   }
 #undef FRB_LOOP_CASE
-  cudaError_t e = cudaLaunchCooperativeKernel(fn, dim3(blocks), dim3(threads), args, 0, p->ctx->stream);
+  cudaError_t e;
+  if (cluster_form) {
+    if (blocks > 8) {  // more than the portable cluster size: opt in, fall back if the device refuses
+      if (cudaFuncSetAttribute(fn, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) {
+        (void)cudaGetLastError();
+        return 0;
+      }
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(blocks);
+    cfg.blockDim = dim3(threads);
+    cfg.stream = p->ctx->stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = blocks;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    int fits = 0;  // can one such cluster be resident?
+    if (cudaOccupancyMaxActiveClusters(&fits, fn, &cfg) != cudaSuccess || fits < 1) {
+      (void)cudaGetLastError();
+      return 0;
+    }
+    e = cudaLaunchKernelExC(&cfg, fn, args);
+    if (e == cudaErrorInvalidClusterSize || e == cudaErrorLaunchOutOfResources) {
+      (void)cudaGetLastError();
+      return 0;
+    }
+  } else {
+    e = cudaLaunchCooperativeKernel(fn, dim3(blocks), dim3(threads), args, 0, p->ctx->stream);
+  }
   if (e == cudaErrorCooperativeLaunchTooLarge) {
     (void)cudaGetLastError();
     return 0;
