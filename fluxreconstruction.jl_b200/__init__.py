@@ -5,6 +5,7 @@ reference interface.  There is no CPU fallback."""
 from ._lib import Context, FRBError, LIB_PATH, SIGNATURES, lib, pinned_empty, pinned_free  # noqa: F401
 from .spaces import *  # noqa: F401,F403
 from .unstruct import *  # noqa: F401,F403
+from .tools import *  # noqa: F401,F403
 from .problems import (  # noqa: F401
     BGKProblem, DistributedEuler2D, Euler, Euler2DProblem, ExplicitRK, RK4, Tsit5, FRAdvectionProblem, FREulerProblem, Integrator, Midpoint, NSCavityProblem, SSPRK33, TriEulerProblem, init, ref_vhs_vis,
     solve, step_,

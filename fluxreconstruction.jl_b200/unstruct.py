@@ -77,14 +77,28 @@ def wsj_points(deg: int):
     return np.array(pts, dtype=np.float64), np.array(w, dtype=np.float64)
 
 
-def tri_quadrature(deg: int):
-    """Solution points of the right reference triangle (-1,-1), (1,-1), (-1,1) and their weights
-    (quadrature.jl:14-71 with transform = true): the barycentric point (x, y, z) sits at
-    x*v1 + y*v2 + z*v3."""
+def tri_quadrature(deg: int, vertices=None, transform=True):
+    """Solution points and weights (quadrature.jl:14-71).  Default: the points in the right reference
+    triangle (-1,-1), (1,-1), (-1,1) -- the barycentric point (x, y, z) sits at x*v1 + y*v2 + z*v3.
+    With ``vertices`` = three corner points the reference's route is taken: trilinear -> Cartesian
+    coordinates in that triangle, then (``transform``) the equilateral -> right-triangle map ``xy_rs``."""
     lam, w = wsj_points(deg)
-    r = -lam[:, 0] + lam[:, 1] - lam[:, 2]
-    s = -lam[:, 0] - lam[:, 1] + lam[:, 2]
-    return np.stack([r, s], axis=1), w
+    if vertices is None and transform:
+        r = -lam[:, 0] + lam[:, 1] - lam[:, 2]
+        s = -lam[:, 0] - lam[:, 1] + lam[:, 2]
+        return np.stack([r, s], axis=1), w
+    if vertices is None:
+        vertices = ((-1.0, -1.0 / np.sqrt(3.0)), (1.0, -1.0 / np.sqrt(3.0)), (0.0, 2.0 / np.sqrt(3.0)))
+    p1, p2, p3 = (np.asarray(v, dtype=np.float64) for v in vertices)
+    side = np.array([np.linalg.norm(p2 - p3), np.linalg.norm(p3 - p1), np.linalg.norm(p2 - p1)])
+    t = lam * side  # trilinear coordinates weighted by the opposite side lengths
+    pts = (t[:, :1] * p1 + t[:, 1:2] * p2 + t[:, 2:] * p3) / t.sum(axis=1, keepdims=True)
+    if transform:
+        from .tools import xy_rs
+
+        r, s = xy_rs(pts[:, 0], pts[:, 1])
+        pts = np.stack([r, s], axis=1)
+    return pts, w
 
 
 def triface_quadrature(deg: int):

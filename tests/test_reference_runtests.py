@@ -1,0 +1,161 @@
+"""The reference's own test script (test/runtests.jl, test/test_triangle.jl) restated against the Python
+mirror, line for line where a line has a counterpart: the same calls with the same arguments, plus the
+value checks the Julia file leaves out (it mostly only checks that the calls run)."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(HERE, "..", "oracle"))
+import fr_oracle as O  # noqa: E402
+import fr_oracle_tri as OT  # noqa: E402
+
+
+def test_test_triangle_jl(FR):
+    deg = 3  # test_triangle.jl:1-5
+    pl, wl = FR.tri_quadrature(deg)
+    V = FR.simplex_vandermonde(deg, pl[:, 0], pl[:, 1])
+    Vr, Vs = FR.dsimplex_vandermonde(deg, pl[:, 0], pl[:, 1])
+    dl = np.stack([Vr @ np.linalg.inv(V), Vs @ np.linalg.inv(V)], axis=2)
+    assert V.shape == (10, 10) and dl.shape == (10, 10, 2)
+    a, b = FR.rs_ab(pl[:, 0], pl[:, 1])  # :7
+    assert np.allclose(b, pl[:, 1]) and np.allclose((a + 1) * (1 - b) / 2 - 1, pl[:, 0])
+    p = ((-1.0, -1 / np.sqrt(3)), (1.0, -1 / np.sqrt(3)), (0.0, 2 / np.sqrt(3)))  # :9-13
+    points, weights = FR.tri_quadrature(3, vertices=p)
+    assert np.abs(points - pl).max() < 1e-15  # :15 (== there: both sides take the same route)
+    assert np.array_equal(weights, wl)  # :16
+    xy, _ = FR.tri_quadrature(3, vertices=p, transform=False)
+    r, s = FR.xy_rs(xy)  # :18-20
+    a, b = FR.rs_ab(r, s)
+    V2 = FR.simplex_vandermonde(3, r, s)
+    assert np.abs(V2 - V).max() < 1e-13
+    o = OT.tri_operators(3)  # the oracle's literal restatement of the same lines
+    assert np.abs(V - o["V"]).max() < 1e-13 and np.abs(dl - o["dl"]).max() < 1e-11
+
+
+def test_error_norms(FR):
+    rng = np.random.default_rng(0)  # runtests.jl:6-10
+    u, u0 = rng.random(3), rng.random(3)
+    d = np.abs(u - u0) * 0.1
+    assert FR.L1_error(u, u0, 0.1) == pytest.approx(d.sum(), rel=1e-15)
+    assert FR.L2_error(u, u0, 0.1) == pytest.approx(np.sqrt((d**2).sum()), rel=1e-15)
+    assert FR.Linf_error(u, u0, 0.1) == pytest.approx(d.max(), rel=1e-15)
+
+
+def test_shock_detector_calls(FR):
+    assert FR.shock_detector(-np.inf, 3) is False  # runtests.jl:12-14
+    assert FR.shock_detector(np.log10(0.1), 3) is True
+    assert FR.shock_detector(np.log10(1e5), 3) is True
+    for Se in (-np.inf, -9.0, -5.5, -1.5, 0.3, 2.6, 5.0):
+        for deg in (2, 3, 5):
+            assert FR.shock_detector(Se, deg) == O.shock_detector(Se, deg)
+            assert FR.shock_detector(Se, deg, -2.0, 9.0) == O.shock_detector(Se, deg, -2.0, 9.0)
+
+
+def test_spaces_and_quadrilateral_jacobians(FR):
+    deg = 5  # runtests.jl:16-17
+    ps2 = FR.FRPSpace2D(0.0, 1.0, 20, 0.0, 1.0, 20, deg, 1, 1)
+    q = np.array([[0, 0], [np.sqrt(3), -1], [np.sqrt(3) + 1, np.sqrt(3) - 1], [1, np.sqrt(3)]])
+    J = FR.rs_jacobi(ps2.xpl, q)  # :19 -- a square of side 2 turned by -30 degrees: constant Jacobian
+    assert J.shape == (6, 6, 2, 2)
+    c, s_ = np.cos(-np.pi / 6), np.sin(-np.pi / 6)
+    assert np.abs(J - np.array([[c, -s_], [s_, c]])).max() < 1e-14
+    rng = np.random.default_rng(1)
+    v = rng.random((3, 3, 4, 2))  # :20
+    Jv = FR.rs_jacobi(ps2.xpl, v)
+    assert Jv.shape == (3, 3, 6, 6, 2, 2)
+    # against a finite difference of the bilinear map of one of them
+    vert = v[1, 2]
+    X = lambda r, s: ((1 - r) * (1 - s) * vert[0] + (1 + r) * (1 - s) * vert[1] + (1 + r) * (1 + s) * vert[2]  # noqa: E731
+                      + (1 - r) * (1 + s) * vert[3]) / 4
+    r0, s0, h = ps2.xpl[2], ps2.xpl[4], 1e-6
+    fd = np.stack([(X(r0 + h, s0) - X(r0 - h, s0)) / (2 * h), (X(r0, s0 + h) - X(r0, s0 - h)) / (2 * h)], axis=1)
+    assert np.abs(Jv[1, 2, 2, 4] - fd).max() < 1e-9
+    assert np.abs(FR.rs_jacobi(r0, s0, vert) - fd).max() < 1e-9
+    ps = FR.FRPSpace1D(0.0, 1.0, 20, deg)  # :23
+    assert ps.xpg.shape == (20, 6)
+
+
+def test_triangle_space_from_the_asset(FR):
+    path = "/root/reference/assets/linesource.msh"  # runtests.jl:22
+    if not os.path.exists(path):
+        pytest.skip("reference assets not present")
+    ps1 = FR.TriFRPSpace(path, 2)
+    assert ps1.np == 6 and ps1.fpn.shape[1:] == (3, 3, 3)
+
+
+def test_positive_limiter_calls(FR):
+    ps = FR.FRPSpace1D(0.0, 1.0, 20, 5)
+    u = np.ones(6)  # runtests.jl:25: constant states are left alone
+    FR.positive_limiter(u, 1 / 6, ps.ll, ps.lr)
+    assert np.array_equal(u, np.ones(6))
+    U = np.ones((6, 3))  # :26
+    FR.positive_limiter(U, 5 / 3, 1 / 6, ps.ll, ps.lr)
+    assert np.abs(U - 1.0).max() < 1e-15
+    # a cell with an undershoot, against the oracle's whole-array restatement of the same method
+    rng = np.random.default_rng(2)
+    prim = np.stack([0.05 + 0.1 * rng.random(6), 0.1 * rng.standard_normal(6), 1.0 + rng.random(6)], axis=1)
+    cell = FR.prim_conserve(prim, 5 / 3)
+    cell[2, 0] = -0.02
+    mine, ref = cell.copy(), cell[None].copy()
+    FR.positive_limiter(mine, 5 / 3, ps.wp / 2, ps.ll, ps.lr)
+    O.positive_limiter_euler1d(ref, 5 / 3, ps.wp / 2, ps.ll, ps.lr)
+    assert mine[:, 0].min() > 0 and np.abs(mine - ref[0]).max() < 1e-15
+    ps2 = FR.FRPSpace2D(0.0, 1.0, 2, 0.0, 1.0, 2, 3, 1, 1)
+    prim = np.stack([0.05 + 0.1 * rng.random((4, 4)), 0.1 * rng.standard_normal((4, 4)),
+                     0.1 * rng.standard_normal((4, 4)), 1.0 + rng.random((4, 4))], axis=2)
+    cell = FR.prim_conserve(prim, 5 / 3)
+    cell[1, 2, 0] = -0.01
+    w2 = np.outer(ps2.wp if ps2.wp.ndim == 1 else ps2.wp[:, 0], ps2.wp if ps2.wp.ndim == 1 else ps2.wp[:, 0]) / 4
+    mine = cell.copy()
+    ref = np.zeros((3, 3, 4, 4, 4))
+    ref[...] = FR.prim_conserve(np.array([1.0, 0.0, 0.0, 1.0]), 5 / 3)
+    ref[1, 1] = cell
+    FR.positive_limiter(mine, 5 / 3, w2, ps2.ll, ps2.lr)
+    O.positive_limiter_euler2d(ref, 5 / 3, w2, ps2.ll, ps2.lr)
+    assert mine[..., 0].min() > 0 and np.abs(mine - ref[1, 1]).max() < 1e-15
+    with pytest.raises(AssertionError, match="incorrect range"):
+        FR.positive_limiter(-np.ones(6), 1 / 6, ps.ll, ps.lr)
+
+
+def test_filters(FR):
+    deg = 5
+    ps = FR.FRPSpace1D(0.0, 1.0, 20, deg)
+    ell = FR.basis_norm(deg)  # runtests.jl:29
+    assert ell.shape == (6,) and abs(ell[0] - 2 * np.sqrt(0.5) * 100 / 99) < 1e-12
+    F = FR.filter_exp(2, 10, np.asarray(ps.V)[:3, :3])  # :31 (the reference passes a 6x6 V with N = 2 and
+    assert F.shape == (3, 3)  # falls through both branches; a 3x3 block is the call that is defined)
+    V = np.asarray(ps.V)
+    F = FR.filter_exp(deg, 10, V)
+    assert np.abs(F @ np.ones(6) - 1.0).max() < 1e-13  # the mean mode is kept
+    d = FR.filter_exp1d(deg, 10)
+    assert d[0] == 1.0 and abs(d[-1] - np.finfo(float).eps) < 1e-30 and (np.diff(d) <= 0).all()
+    tri = FR.TriFRPSpace(OT.tri_mesh_rect(1, 1), 3)
+    d2 = FR.filter_exp2d(3, 4)
+    assert d2.shape == (10,) and d2[0] == 1.0 and abs(d2[3] - np.finfo(float).eps) < 1e-30  # mode (0, 3)
+    F2 = FR.filter_exp(3, 4, tri.V)
+    assert np.abs(F2 @ np.ones(10) - 1.0).max() < 1e-12
+    u = np.random.default_rng(3).random((deg + 1, deg + 1))  # :34-37, filter = :l2 ([KB], vector form)
+    from frb200.problems import modal_filter_diag
+
+    diag = modal_filter_diag(deg + 1, 1e-6)
+    assert np.allclose(diag * u[:, 0], O.modal_filter_l2(u[:, 0], 1e-6))
+
+
+def test_interp_face_and_derivative(FR):
+    ps = FR.FRPSpace1D(0.0, 1.0, 20, 5)
+    rng = np.random.default_rng(4)
+    f = rng.standard_normal((5, 6))  # runtests.jl:40-42
+    fd = rng.standard_normal((5, 2))
+    FR.interp_face_(fd, f, ps.ll, ps.lr)
+    assert np.allclose(fd[:, 0], f @ ps.ll) and np.allclose(fd[:, 1], f @ ps.lr)
+    one = np.zeros(2)
+    FR.interp_face_(one, f[0], ps.ll, ps.lr)
+    assert np.allclose(one, fd[0])
+    df = np.zeros(6)
+    FR.poly_derivative_(df, ps.xpl**3, ps.dl)
+    assert np.allclose(df, 3 * ps.xpl**2)
+    L = FR.standard_lagrange(ps.xpl)  # :44
+    assert L is not None
