@@ -43,6 +43,8 @@ SIGNATURES = {
                                        C.POINTER(C.c_void_p)]),
     "frb_euler2d_create": (C.c_int32, [C.c_void_p, C.c_int32, C.c_int32, C.POINTER(Operators), C.c_double,
                                        C.c_double, C.c_double, C.POINTER(C.c_void_p)]),
+    "frb_euler2d_curv_create": (C.c_int32, [C.c_void_p, C.c_int32, C.c_int32, C.POINTER(Operators), c_dp, c_dp, c_dp,
+                                            c_dp, C.c_int32, C.c_double, C.POINTER(C.c_void_p)]),
     "frb_bgk1d_create": (C.c_int32, [C.c_void_p, C.c_int32, C.c_int32, C.POINTER(Operators), c_dp, c_dp, c_dp,
                                      C.c_double, C.POINTER(C.c_void_p)]),
     "frb_ns2d_create": (C.c_int32, [C.c_void_p, C.c_int32, C.c_int32, C.POINTER(Operators)] + [C.c_double] * 9

@@ -157,6 +157,7 @@ extern "C" int32_t frb_prob_destroy(frb_prob_t p) {
   cudaFree(p->u); cudaFree(p->s1); cudaFree(p->s2); cudaFree(p->du); cudaFree(p->rc_base);
   cudaFree(p->J); cudaFree(p->velo); cudaFree(p->weights); cudaFree(p->prim);
   cudaFree(p->lim_w); cudaFree(p->flag); cudaFree(p->loop_bar); cudaFree(p->filt); cudaFree(p->ns_flux);
+  cudaFree(p->curv_iJ); cudaFree(p->curv_n1); cudaFree(p->curv_n2); cudaFree(p->curv_fpc); cudaFree(p->curv_flux);
   cudaFree(p->tri_ops); cudaFree(p->tri_uf); cudaFree(p->tri_normals); cudaFree(p->tri_type); cudaFree(p->tri_fpn);
   if (p->ev0) cudaEventDestroy(p->ev0);
   if (p->ev1) cudaEventDestroy(p->ev1);
@@ -223,6 +224,34 @@ extern "C" int32_t frb_euler2d_create(frb_ctx_t ctx, int32_t nx, int32_t ny,
   p->dofs = (int64_t)nx * ny * p->nsp * p->nsp * 4;
   FRB_TRY(alloc_common(p));
   FRB_TRY(alloc_rc(p));
+  *out = p;
+  return FRB_OK;
+}
+
+extern "C" int32_t frb_euler2d_curv_create(frb_ctx_t ctx, int32_t nx, int32_t ny, const frb_operators *ops,
+                                           const double *iJ, const double *n1, const double *n2,
+                                           const double *fpc, int32_t flags, double gamma, frb_prob_t *out) {
+  FRB_REQUIRE(ctx && out && iJ && n1 && n2, FRB_ERR_ARG, "frb_euler2d_curv_create: NULL argument");
+  FRB_REQUIRE(nx >= 1 && ny >= 1, FRB_ERR_ARG, "frb_euler2d_curv_create: nx, ny must be >= 1");
+  FRB_REQUIRE((flags & ~(FRB_CURV_FY_ROW_INDEX | FRB_CURV_WALL_XLO)) == 0, FRB_ERR_ARG,
+              "frb_euler2d_curv_create: unknown flag");
+  frb_prob_t p = new frb_prob_s();
+  p->ctx = ctx; p->kind = K_EULER2D; p->nx = nx; p->ny = ny; p->Jx = 1.0; p->Jy = 1.0; p->gamma = gamma;
+  p->curv_flags = flags;
+  FRB_TRY(fill_ops(ops, &p->ops, &p->nsp, false));
+  if (p->nsp > 4) {
+    frb_set_error("frb_euler2d_curv_create: deg must be in 1..3");
+    frb_prob_destroy(p);
+    return FRB_ERR_ARG;
+  }
+  const size_t npp = (size_t)p->nsp * p->nsp, ne = (size_t)(nx + 2) * (ny + 2);
+  p->len = (int64_t)(ne * npp * 4);
+  p->dofs = (int64_t)nx * ny * (int64_t)npp * 4;
+  FRB_TRY(alloc_common(p));
+  FRB_TRY(upload_vec(p, &p->curv_iJ, iJ, ne * npp * 4));
+  FRB_TRY(upload_vec(p, &p->curv_n1, n1, (size_t)(nx + 1) * ny * 2));
+  FRB_TRY(upload_vec(p, &p->curv_n2, n2, (size_t)nx * (ny + 1) * 2));
+  if (fpc) FRB_TRY(upload_vec(p, &p->curv_fpc, fpc, (size_t)nx * ny * p->nsp * 4));
   *out = p;
   return FRB_OK;
 }
@@ -415,8 +444,9 @@ static int launch_stage_inner(frb_prob_t p, const double *u, const double *ua, d
     case K_EULER1D: n = frb_launch_euler1d(p, u, ua, out, st); break;
     case K_BGK1D: n = frb_launch_bgk1d(p, u, ua, out, st); break;
     case K_EULER2D:
-      n = use_march(p) ? frb_launch_euler2d_march(p, u, ua, out, st)
-                       : frb_launch_euler2d_generic(p, u, ua, out, st);
+      n = p->curv_iJ   ? frb_launch_euler2d_curv(p, u, ua, out, st)
+          : use_march(p) ? frb_launch_euler2d_march(p, u, ua, out, st)
+                         : frb_launch_euler2d_generic(p, u, ua, out, st);
       break;
     case K_NS2D: n = frb_launch_ns2d(p, u, ua, out, st); break;
     case K_TRI_EULER: n = frb_launch_tri_euler(p, u, ua, out, st); break;
@@ -538,8 +568,10 @@ static int set_limiter_weights(frb_prob_t p, const double *w) {
 
 extern "C" int32_t frb_set_step_hooks(frb_prob_t p, int32_t ghost_mode, const double *limiter_weights) {
   FRB_REQUIRE(p, FRB_ERR_ARG, "frb_set_step_hooks: prob is NULL");
-  FRB_REQUIRE(ghost_mode >= FRB_GHOST_NONE && ghost_mode <= FRB_GHOST_COPY, FRB_ERR_ARG,
+  FRB_REQUIRE(ghost_mode >= FRB_GHOST_NONE && ghost_mode <= FRB_GHOST_CYLINDER, FRB_ERR_ARG,
               "frb_set_step_hooks: unknown ghost mode");
+  FRB_REQUIRE(ghost_mode != FRB_GHOST_CYLINDER || p->curv_iJ, FRB_ERR_STATE,
+              "frb_set_step_hooks: the cylinder ghost fill applies to curvilinear euler2d problems");
   FRB_REQUIRE(ghost_mode == FRB_GHOST_NONE || p->kind == K_EULER2D, FRB_ERR_STATE,
               "frb_set_step_hooks: ghost fill applies to euler2d problems");
   FRB_REQUIRE(!limiter_weights || p->kind == K_EULER1D || p->kind == K_EULER2D, FRB_ERR_STATE,
@@ -1028,6 +1060,7 @@ extern "C" int32_t frb_set_flux(frb_prob_t p, int32_t kind) {
   FRB_REQUIRE(p, FRB_ERR_ARG, "frb_set_flux: prob is NULL");
   FRB_REQUIRE(p->kind == K_EULER1D || p->kind == K_EULER2D, FRB_ERR_STATE, "frb_set_flux: Euler problems only");
   FRB_REQUIRE(kind >= FRB_FLUX_HLL && kind <= FRB_FLUX_ROE, FRB_ERR_ARG, "frb_set_flux: unknown flux kind");
+  FRB_REQUIRE(kind == FRB_FLUX_HLL || !p->curv_iJ, FRB_ERR_STATE, "frb_set_flux: curvilinear problems are HLL only");
   p->flux = kind;
   return FRB_OK;
 }

@@ -1,0 +1,116 @@
+// 2-D Euler on curvilinear structured quadrilaterals: fused residual + RK stage, one thread
+// per interior element, lanes along i so that every state / metric plane is read in 256-byte runs.
+// The arithmetic lives in frb_euler2d_curv_elem.cuh (reference: dev/parallelogram.jl:80-165,
+// dev/cylinder2.jl:52-164).
+//
+// Algorithmic bytes per DOF-update: the state terms of the rectangular path (16 B / 24 B) plus the
+// metric, which no longer is two scalars: 4 doubles of iJ per solution point shared by the 4 variables
+// = 8 B per DOF (+ normals and flux-point factors, O(1/nsp) of that).
+#include "frb_euler2d_curv_elem.cuh"
+
+namespace {
+
+// blockIdx.z < NSP: x faces, flux point z;  >= NSP: y faces, flux point z - NSP.  Lanes along i.
+template <int NSP>
+__global__ void __launch_bounds__(128)
+euler2d_curv_face_kernel(const double *__restrict__ u, double *__restrict__ fx, double *__restrict__ fy,
+                         CurvGeom g, double gamma, FrbOps ops) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x + 1;
+  const int j = blockIdx.y + 1;
+  const int z = blockIdx.z;
+  if (z < NSP) {
+    if (i <= g.nx + 1 && j <= g.ny) frbcurv::face_x<NSP>(i, j, z, u, fx, g, gamma, ops);
+  } else {
+    if (i <= g.nx && j <= g.ny + 1) frbcurv::face_y<NSP>(i, j, z - NSP, u, fy, g, gamma, ops);
+  }
+}
+
+// thread = (element i, variable m = threadIdx.y); one block row per j
+template <int NSP>
+__global__ void __launch_bounds__(128)
+euler2d_curv_elem_kernel(const double *__restrict__ u, const double *__restrict__ ua,
+                         const double *__restrict__ fx, const double *__restrict__ fy, double *__restrict__ out,
+                         CurvGeom g, double gamma, FrbOps ops, FrbStage st) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x + 1;
+  const int j = blockIdx.y + 1;
+  if (i > g.nx) return;
+  frbcurv::element_var<NSP>(i, j, threadIdx.y, u, ua, fx, fy, out, g, gamma, ops, st);
+}
+
+// Per-step boundary fill of dev/cylinder2.jl:176-187 on the ring-embedded array (interior nx = nr - 1,
+// column nx+1 = the script's cell nr).  theta ghosts: u[i, 0, k, l, :] = flip_y(u[i, 1, nsp+1-k, nsp+1-l, :]),
+// u[i, ny+1, k, l, :] = flip_y(u[i, ny, nsp+1-k, nsp+1-l, :]) for i = 1..nx+1 (the script's "4 - k" at deg 2).
+__global__ void ghost_cyl_theta_kernel(double *__restrict__ u, int nx, int ny, int nsp) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x + 1;
+  const int p = blockIdx.y;  // k + nsp (l + nsp m)
+  if (i > nx + 1) return;
+  const int k = p % nsp, l = (p / nsp) % nsp, m = p / (nsp * nsp);
+  const int ps = (nsp - 1 - k) + nsp * ((nsp - 1 - l) + nsp * m);
+  const size_t NXG = nx + 2, NE = NXG * (size_t)(ny + 2);
+  const double sg = m == 2 ? -1.0 : 1.0;
+  u[i + NE * p] = sg * u[i + NXG * 1 + NE * ps];
+  u[i + NXG * (size_t)(ny + 1) + NE * p] = sg * u[i + NXG * (size_t)ny + NE * ps];
+}
+// outer column: u[nx+1, j, :] = u[nx, j, :] for j = 1..ny/2
+__global__ void ghost_cyl_outer_kernel(double *__restrict__ u, int nx, int ny) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x + 1;
+  const int p = blockIdx.y;
+  if (j > ny / 2) return;
+  const size_t NXG = nx + 2, NE = NXG * (size_t)(ny + 2);
+  u[nx + 1 + NXG * j + NE * p] = u[nx + NXG * j + NE * p];
+}
+
+}  // namespace
+
+int frb_launch_ghost_cylinder(frb_prob_t p, double *u) {
+  const int nplanes = 4 * p->nsp * p->nsp;
+  cudaStream_t s = p->ctx->stream;
+  dim3 blk(128), g1((p->nx + 1 + 127) / 128, nplanes), g2((p->ny / 2 + 127) / 128, nplanes);
+  ghost_cyl_theta_kernel<<<g1, blk, 0, s>>>(u, p->nx, p->ny, p->nsp);
+  int n = 1;
+  if (p->ny / 2 > 0) {
+    ghost_cyl_outer_kernel<<<g2, blk, 0, s>>>(u, p->nx, p->ny);
+    ++n;
+  }
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return frb_cuda_fail(e, "ghost_cyl kernels", __FILE__, __LINE__);
+  return n;
+}
+
+int frb_launch_euler2d_curv(frb_prob_t p, const double *u, const double *ua, double *out, FrbStage st) {
+  if (u == out) {  // neighbours' blocks are read: never in place
+    frb_set_error("euler2d_curv: the stage cannot run in place");
+    return FRB_ERR_STATE;
+  }
+  if (p->ny + 1 > 65535) {
+    frb_set_error("euler2d_curv: ny must be < 65535");
+    return FRB_ERR_ARG;
+  }
+  const size_t nfx = (size_t)(p->nx + 1) * p->ny * p->nsp * 4, nfy = (size_t)p->nx * (p->ny + 1) * p->nsp * 4;
+  if (!p->curv_flux) FRB_CUDA(cudaMalloc(&p->curv_flux, sizeof(double) * (nfx + nfy)));
+  double *fx = p->curv_flux, *fy = p->curv_flux + nfx;
+  CurvGeom g;
+  g.nx = p->nx; g.ny = p->ny;
+  g.iJ = p->curv_iJ; g.n1 = p->curv_n1; g.n2 = p->curv_n2; g.fpc = p->curv_fpc;
+  g.fy_row = (p->curv_flags & FRB_CURV_FY_ROW_INDEX) ? 1 : 0;
+  g.wall_xlo = (p->curv_flags & FRB_CURV_WALL_XLO) ? 1 : 0;
+  if (st.nested) { st.cdt *= st.cb; st.nested = 0; }
+  cudaStream_t s = p->ctx->stream;
+  dim3 fb(128), fg((p->nx + 1 + 127) / 128, p->ny + 1, 2 * p->nsp);
+  dim3 eb(32, 4), eg((p->nx + 31) / 32, p->ny);
+  switch (p->nsp) {
+#define FRB_CURV_CASE(N)                                                                                  \
+  case N:                                                                                                 \
+    euler2d_curv_face_kernel<N><<<fg, fb, 0, s>>>(u, fx, fy, g, p->gamma, p->ops);                         \
+    euler2d_curv_elem_kernel<N><<<eg, eb, 0, s>>>(u, ua, fx, fy, out, g, p->gamma, p->ops, st);            \
+    break;
+    FRB_CURV_CASE(2)
+    FRB_CURV_CASE(3)
+    FRB_CURV_CASE(4)
+#undef FRB_CURV_CASE
+    default: frb_set_error("euler2d_curv: deg must be in 1..3"); return FRB_ERR_ARG;
+  }
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return frb_cuda_fail(e, "euler2d_curv kernels", __FILE__, __LINE__);
+  return 2;
+}

@@ -1,0 +1,257 @@
+// 2-D Euler residual + RK stage of ONE element of a curvilinear structured quadrilateral mesh
+// (SURVEY 8f-2): metric terms per solution point, unit normals per face, correction factors either from
+// the solution-point inverse Jacobian or from a flux-point table.
+//
+// Reference semantics: dudt! of dev/parallelogram.jl:80-165 (factors (iJ[i,j][k,l] * n)[c], :145-148) and
+// of dev/cylinder2.jl:52-164 (factors (inv(Ji[i,j][face,pt]) * n)[c], :155-158; mirror wall on the inner
+// radial face, :100-120).  Both scripts index the y common flux with the row index l in the correction
+// (parallelogram.jl:147-148) where the rectangular scripts use the flux-point index k
+// (example/euler2d_wave.jl:100-103); CurvGeom::fy_row selects the scripts' form.
+//
+// Two passes per stage (the split the north star words: a face kernel over the face connectivity, an
+// element kernel that fuses derivative, correction and the RK update):
+//   face_x / face_y  thread = one interface flux point: both traces from the two neighbouring element
+//                    blocks, HLL in the face frame, all 4 components -> fx[nx+1, ny, nsp, 4], fy[nx, ny+1, nsp, 4]
+//   element_var      thread = (element, variable m): point fluxes iJ [F; G] of its variable, lpdm derivative,
+//                    correction, stage update; ~60 live doubles at deg 3, nothing spills
+//
+// The routines are __host__ __device__ so that tests/harness/curv_host.cu can run the very same code on the
+// CPU against the NumPy oracle (the build box has no GPU); the library only ever calls it from a kernel.
+//
+// Layouts (Julia column-major, one ghost ring, NE = (nx+2)(ny+2), e = i + (nx+2) j):
+//   u  [nx+2, ny+2, nsp, nsp, 4]     u[e + NE (k + nsp (l + nsp m))]
+//   iJ [nx+2, ny+2, nsp, nsp, 2, 2]  iJ[e + NE (k + nsp (l + nsp (a + 2 b)))] = ps.iJ[i,j][k,l][a,b]
+//   n1 [nx+1, ny, 2]  unit normal of x face i (between elements i-1 and i) in row j: n1[i-1 + (nx+1)(j-1 + ny c)]
+//   n2 [nx, ny+1, 2]  unit normal of y face j (between rows j-1 and j) in column i:  n2[i-1 + nx (j-1 + (ny+1) c)]
+//   fpc[nx, ny, nsp, 4] (optional) flux-point factors (xL by l, xR by l, yL by k, yR by k):
+//                     fpc[i-1 + nx (j-1 + ny (q + nsp c))]
+#pragma once
+#include <math.h>
+
+#include "frb_internal.cuh"
+
+#if defined(__CUDACC__)
+#define FRB_HD __host__ __device__ __forceinline__
+#else
+#define FRB_HD inline
+#endif
+
+struct CurvGeom {
+  int nx, ny;
+  const double *iJ, *n1, *n2, *fpc;  // fpc == nullptr: solution-point factors
+  int fy_row;    // 1: y common flux indexed by the row l (the scripts' literal form)
+  int wall_xlo;  // 1: x face 1 is the mirror wall of dev/cylinder2.jl:100-120
+};
+
+namespace frbcurv {
+
+struct W4 {
+  double a, b, c, d;
+};
+
+// local_frame -> flux_hll!(fw, wL, wR, gamma, 1.0) -> global_frame about the unit normal (c, s)
+// (parallelogram.jl:119-123).  wall != 0 replaces the left state by the mirror state of the right one
+// in the face frame (cylinder2.jl:103-114).
+FRB_HD W4 hll_normal(W4 L, W4 R, double c, double s, double gamma, int wall) {
+  const double gm1 = gamma - 1.0;
+  double l0 = L.a, l1 = fma(L.c, s, L.b * c), l2 = fma(-L.b, s, L.c * c), l3 = L.d;
+  const double r0 = R.a, r1 = fma(R.c, s, R.b * c), r2 = fma(-R.b, s, R.c * c), r3 = R.d;
+  if (wall) {
+    // prim = conserve_prim(ul) = (rho, U, V, lambda);  pn = ((1-t)/(1+t) rho, -U, V, 2 - lambda), t = lambda - 1
+    const double U = r1 / r0, V = r2 / r0;
+    const double lam = 0.5 * r0 / gm1 / (r3 - 0.5 * (r1 * r1 + r2 * r2) / r0);
+    const double t = lam - 1.0;
+    const double rn = (1.0 - t) / (1.0 + t) * r0, ln = 2.0 - lam;
+    l0 = rn;
+    l1 = rn * (-U);
+    l2 = rn * V;
+    l3 = 0.5 * rn / ln / gm1 + 0.5 * rn * (U * U + V * V);
+  }
+  const double il = 1.0 / l0, ir = 1.0 / r0;
+  const double ul = l1 * il, vl = l2 * il, ur = r1 * ir, vr = r2 * ir;
+  const double pl = gm1 * (l3 - 0.5 * fma(l1, ul, l2 * vl));
+  const double pr = gm1 * (r3 - 0.5 * fma(r1, ur, r2 * vr));
+  const double al = sqrt(gamma * pl * il), ar = sqrt(gamma * pr * ir);
+  const double lmin = ul - al, lmax = ur + ar;
+  const double fl0 = l1, fl1 = fma(l1, ul, pl), fl2 = l1 * vl, fl3 = (l3 + pl) * ul;
+  const double fr0 = r1, fr1 = fma(r1, ur, pr), fr2 = r1 * vr, fr3 = (r3 + pr) * ur;
+  double f0, f1, f2, f3;
+  if (lmin >= 0.0) {
+    f0 = fl0; f1 = fl1; f2 = fl2; f3 = fl3;
+  } else if (lmax <= 0.0) {
+    f0 = fr0; f1 = fr1; f2 = fr2; f3 = fr3;
+  } else {
+    const double fac = 1.0 / (lmax - lmin), mm = lmax * lmin;
+    f0 = fac * (lmax * fl0 - lmin * fr0 + mm * (r0 - l0));
+    f1 = fac * (lmax * fl1 - lmin * fr1 + mm * (r1 - l1));
+    f2 = fac * (lmax * fl2 - lmin * fr2 + mm * (r2 - l2));
+    f3 = fac * (lmax * fl3 - lmin * fr3 + mm * (r3 - l3));
+  }
+  return {f0, fma(-f2, s, f1 * c), fma(f1, s, f2 * c), f3};
+}
+
+template <int NSP>
+FRB_HD size_t plane(int k, int l, int m) {
+  return (size_t)(k + NSP * (l + NSP * m));
+}
+
+template <int NSP>
+FRB_HD void load_trace_x(const double *__restrict__ u, size_t e, size_t NE, int p, const double *lq, double w[4]) {
+#pragma unroll
+  for (int m = 0; m < 4; ++m) {  // dot(u[i,j,:,p,m], lq)
+    double a = 0;
+#pragma unroll
+    for (int q = 0; q < NSP; ++q) a = fma(u[e + NE * plane<NSP>(q, p, m)], lq[q], a);
+    w[m] = a;
+  }
+}
+template <int NSP>
+FRB_HD void load_trace_y(const double *__restrict__ u, size_t e, size_t NE, int p, const double *lq, double w[4]) {
+#pragma unroll
+  for (int m = 0; m < 4; ++m) {  // dot(u[i,j,p,:,m], lq)
+    double a = 0;
+#pragma unroll
+    for (int q = 0; q < NSP; ++q) a = fma(u[e + NE * plane<NSP>(p, q, m)], lq[q], a);
+    w[m] = a;
+  }
+}
+
+// x face i (1..nx+1) of row j (1..ny), flux point p (0..NSP-1): parallelogram.jl:115-125
+// fx[i-1 + (nx+1)(j-1 + ny (p + NSP m))]
+template <int NSP>
+FRB_HD void face_x(int i, int j, int p, const double *__restrict__ u, double *__restrict__ fx, const CurvGeom &g,
+                   double gamma, const FrbOps &ops) {
+  const size_t NXG = g.nx + 2, NE = NXG * (size_t)(g.ny + 2);
+  const size_t e = i + NXG * j;
+  double L[4], R[4];
+  load_trace_x<NSP>(u, e - 1, NE, p, ops.lr, L);  // u_face[i-1, j, 2, p, :]
+  load_trace_x<NSP>(u, e, NE, p, ops.ll, R);      // u_face[i, j, 4, p, :]
+  const size_t f = (size_t)(i - 1) + (size_t)(g.nx + 1) * (j - 1), sf = (size_t)(g.nx + 1) * g.ny;
+  const W4 h = hll_normal({L[0], L[1], L[2], L[3]}, {R[0], R[1], R[2], R[3]}, g.n1[f], g.n1[f + sf], gamma,
+                          g.wall_xlo && i == 1);
+  fx[f + sf * (p + NSP * 0)] = h.a;
+  fx[f + sf * (p + NSP * 1)] = h.b;
+  fx[f + sf * (p + NSP * 2)] = h.c;
+  fx[f + sf * (p + NSP * 3)] = h.d;
+}
+
+// y face j (1..ny+1) of column i (1..nx), flux point p: parallelogram.jl:126-136
+// fy[i-1 + nx (j-1 + (ny+1)(p + NSP m))]
+template <int NSP>
+FRB_HD void face_y(int i, int j, int p, const double *__restrict__ u, double *__restrict__ fy, const CurvGeom &g,
+                   double gamma, const FrbOps &ops) {
+  const size_t NXG = g.nx + 2, NE = NXG * (size_t)(g.ny + 2);
+  const size_t e = i + NXG * j;
+  double L[4], R[4];
+  load_trace_y<NSP>(u, e - NXG, NE, p, ops.lr, L);  // u_face[i, j-1, 3, p, :]
+  load_trace_y<NSP>(u, e, NE, p, ops.ll, R);        // u_face[i, j, 1, p, :]
+  const size_t f = (size_t)(i - 1) + (size_t)g.nx * (j - 1), sf = (size_t)g.nx * (g.ny + 1);
+  const W4 h = hll_normal({L[0], L[1], L[2], L[3]}, {R[0], R[1], R[2], R[3]}, g.n2[f], g.n2[f + sf], gamma, 0);
+  fy[f + sf * (p + NSP * 0)] = h.a;
+  fy[f + sf * (p + NSP * 1)] = h.b;
+  fy[f + sf * (p + NSP * 2)] = h.c;
+  fy[f + sf * (p + NSP * 3)] = h.d;
+}
+
+// component m of F and G at a point
+FRB_HD void flux_component(int m, double w0, double w1, double w2, double w3, double gm1, double &F, double &G) {
+  const double r = 1.0 / w0, vx = w1 * r, vy = w2 * r;
+  const double p = gm1 * (w3 - 0.5 * fma(w1, vx, w2 * vy));
+  if (m == 0) { F = w1; G = w2; }
+  else if (m == 1) { F = fma(w1, vx, p); G = w2 * vx; }
+  else if (m == 2) { F = w1 * vy; G = fma(w2, vy, p); }
+  else { const double h = w3 + p; F = h * vx; G = h * vy; }
+}
+
+// Variable m of interior element (i, j), 1-based like the reference: parallelogram.jl:88-96,138-163.
+template <int NSP>
+FRB_HD void element_var(int i, int j, int m, const double *__restrict__ u, const double *__restrict__ ua,
+                        const double *__restrict__ fx, const double *__restrict__ fy, double *__restrict__ out,
+                        const CurvGeom &g, double gamma, const FrbOps &ops, const FrbStage &st) {
+  const int nx = g.nx, ny = g.ny;
+  const size_t NXG = nx + 2, NE = NXG * (size_t)(ny + 2);
+  const size_t e = i + NXG * j;
+  const double gm1 = gamma - 1.0;
+
+  double f1[NSP][NSP], f2[NSP][NSP];  // [l][k]: (iJ [F_m; G_m])[1], [2]
+#pragma unroll
+  for (int l = 0; l < NSP; ++l)
+#pragma unroll
+    for (int k = 0; k < NSP; ++k) {
+      const double w0 = u[e + NE * plane<NSP>(k, l, 0)], w1 = u[e + NE * plane<NSP>(k, l, 1)];
+      const double w2 = u[e + NE * plane<NSP>(k, l, 2)], w3 = u[e + NE * plane<NSP>(k, l, 3)];
+      const double a11 = g.iJ[e + NE * plane<NSP>(k, l, 0)], a21 = g.iJ[e + NE * plane<NSP>(k, l, 1)];
+      const double a12 = g.iJ[e + NE * plane<NSP>(k, l, 2)], a22 = g.iJ[e + NE * plane<NSP>(k, l, 3)];
+      double F, G;
+      flux_component(m, w0, w1, w2, w3, gm1, F, G);
+      f1[l][k] = fma(a12, G, a11 * F);
+      f2[l][k] = fma(a22, G, a21 * F);
+    }
+
+  // face normals and the 4 x NSP common-flux values of this variable
+  const size_t i1 = (size_t)(i - 1) + (size_t)(nx + 1) * (j - 1), s1 = (size_t)(nx + 1) * ny;
+  const double nxl_c = g.n1[i1], nxl_s = g.n1[i1 + s1], nxr_c = g.n1[i1 + 1], nxr_s = g.n1[i1 + 1 + s1];
+  const size_t i2 = (size_t)(i - 1) + (size_t)nx * (j - 1), s2 = (size_t)nx * (ny + 1);
+  const double nyb_c = g.n2[i2], nyb_s = g.n2[i2 + s2], nyt_c = g.n2[i2 + nx], nyt_s = g.n2[i2 + nx + s2];
+  const size_t ifp = (size_t)(i - 1) + (size_t)nx * (j - 1), sfp = (size_t)nx * ny;
+  double FxL[NSP], FxR[NSP], FyB[NSP], FyT[NSP], tx4[NSP], tx2[NSP], ty1[NSP], ty3[NSP];
+#pragma unroll
+  for (int p = 0; p < NSP; ++p) {
+    FxL[p] = fx[i1 + s1 * (p + NSP * m)];
+    FxR[p] = fx[i1 + 1 + s1 * (p + NSP * m)];
+    FyB[p] = fy[i2 + s2 * (p + NSP * m)];
+    FyT[p] = fy[i2 + nx + s2 * (p + NSP * m)];
+    double t4 = 0, t2 = 0, t1 = 0, t3 = 0;
+#pragma unroll
+    for (int q = 0; q < NSP; ++q) {
+      t4 = fma(f1[p][q], ops.ll[q], t4);  // f_face[i,j,4,p,m,1]
+      t2 = fma(f1[p][q], ops.lr[q], t2);  // f_face[i,j,2,p,m,1]
+      t1 = fma(f2[q][p], ops.ll[q], t1);  // f_face[i,j,1,p,m,2]
+      t3 = fma(f2[q][p], ops.lr[q], t3);  // f_face[i,j,3,p,m,2]
+    }
+    tx4[p] = t4; tx2[p] = t2; ty1[p] = t1; ty3[p] = t3;
+  }
+
+#pragma unroll
+  for (int l = 0; l < NSP; ++l)
+#pragma unroll
+    for (int k = 0; k < NSP; ++k) {
+      double a = f1[l][0] * ops.lpdm[k * FRB_NSPMAX];
+      double b = f2[0][k] * ops.lpdm[l * FRB_NSPMAX];
+#pragma unroll
+      for (int q = 1; q < NSP; ++q) {
+        a = fma(f1[l][q], ops.lpdm[k * FRB_NSPMAX + q], a);
+        b = fma(f2[q][k], ops.lpdm[l * FRB_NSPMAX + q], b);
+      }
+      double cxL, cxR, cyL, cyR;
+      if (g.fpc) {  // cylinder2.jl:155-158
+        cxL = g.fpc[ifp + sfp * (l + NSP * 0)];
+        cxR = g.fpc[ifp + sfp * (l + NSP * 1)];
+        cyL = g.fpc[ifp + sfp * (k + NSP * 2)];
+        cyR = g.fpc[ifp + sfp * (k + NSP * 3)];
+      } else {  // parallelogram.jl:145-148
+        const double a11 = g.iJ[e + NE * plane<NSP>(k, l, 0)], a21 = g.iJ[e + NE * plane<NSP>(k, l, 1)];
+        const double a12 = g.iJ[e + NE * plane<NSP>(k, l, 2)], a22 = g.iJ[e + NE * plane<NSP>(k, l, 3)];
+        cxL = fma(a12, nxl_s, a11 * nxl_c);
+        cxR = fma(a12, nxr_s, a11 * nxr_c);
+        cyL = fma(a22, nyb_s, a21 * nyb_c);
+        cyR = fma(a22, nyt_s, a21 * nyt_c);
+      }
+      double d = a + b;
+      d += (cxL * FxL[l] - tx4[l]) * ops.dgl[k];
+      d += (cxR * FxR[l] - tx2[l]) * ops.dgr[k];
+      d += (cyL * (g.fy_row ? FyB[l] : FyB[k]) - ty1[k]) * ops.dgl[l];
+      d += (cyR * (g.fy_row ? FyT[l] : FyT[k]) - ty3[k]) * ops.dgr[l];
+      d = -d;
+      const size_t idx = e + NE * plane<NSP>(k, l, m);
+      double r;
+      if (st.rhs_only) r = d;
+      else {
+        r = fma(st.cdt, d, st.cb * u[idx]);
+        if (st.use_a) r = fma(st.ca, ua[idx], r);
+      }
+      out[idx] = r;
+    }
+}
+
+}  // namespace frbcurv

@@ -274,7 +274,7 @@ int env_int(const char *name, int dflt) {
 
 bool frb_euler2d_march_supported(frb_prob_t p) {
   // TMA needs 16-byte global strides: (nx+2)*8 bytes per row -> nx even
-  return p->kind == K_EULER2D && (p->nsp == 4 || p->nsp == 3) && (p->nx % 2 == 0);
+  return p->kind == K_EULER2D && !p->curv_iJ && (p->nsp == 4 || p->nsp == 3) && (p->nx % 2 == 0);
 }
 
 void frb_march_release(frb_prob_t p) {

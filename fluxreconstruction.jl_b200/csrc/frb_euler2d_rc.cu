@@ -257,7 +257,7 @@ int dispatch_rc(frb_prob_t p, const RcParams &rp, const MarchOps &mo, bool usea,
 }  // namespace
 
 bool frb_euler2d_rc_supported(frb_prob_t p) {
-  return p->kind == K_EULER2D && (p->nsp == 4 || p->nsp == 3);
+  return p->kind == K_EULER2D && !p->curv_iJ && (p->nsp == 4 || p->nsp == 3);
 }
 
 // u, ua, out are RC buffers (frb_rc.cuh); stage semantics as in frb_launch_euler2d_march

@@ -91,7 +91,10 @@ int check_launch(const char *what) {
 // export layout: 5 IPC handles (u, s1, s2, flags, row-chunk buffers) + int32 ny_local + int32 has_rc
 extern "C" int32_t frb_halo_export(frb_prob_t p, unsigned char *out) {
   if (!p || !out) { frb_set_error("frb_halo_export: NULL argument"); return FRB_ERR_ARG; }
-  if (p->kind != K_EULER2D) { frb_set_error("frb_halo_export: euler2d problems only"); return FRB_ERR_STATE; }
+  if (p->kind != K_EULER2D || p->curv_iJ) {
+    frb_set_error("frb_halo_export: rectangular euler2d problems only");
+    return FRB_ERR_STATE;
+  }
   FRB_CUDA(cudaSetDevice(p->ctx->device));
   if (!p->halo) {
     p->halo = new FrbHalo();

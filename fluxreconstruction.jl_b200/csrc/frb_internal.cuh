@@ -86,6 +86,11 @@ struct frb_prob_s {
   double *tri_ops = nullptr, *tri_uf = nullptr, *tri_normals = nullptr;
   int *tri_type = nullptr, *tri_fpn = nullptr;
   double *ns_flux = nullptr;        // ns2d: common fluxes on the x | y faces (lazy)
+  // curvilinear quadrilaterals (frb_euler2d_curv_create): metric planes, face normals, optional
+  // flux-point correction factors; curv_iJ != nullptr marks the problem
+  double *curv_iJ = nullptr, *curv_n1 = nullptr, *curv_n2 = nullptr, *curv_fpc = nullptr;
+  double *curv_flux = nullptr;      // common fluxes on the x | y faces (lazy)
+  int curv_flags = 0;
   double *lim_w = nullptr;          // limiter weights (device)
   // shock sensor + modal filter hook (frb_set_filter_hook): iV | F on the device, when = 0 off,
   // 1 before every step (euler_highlevel.jl:37-52), 2 after every step (shock-vortex.jl:308-321)
@@ -121,6 +126,8 @@ int frb_launch_adv1d(frb_prob_t p, const double *u, const double *ua, double *ou
 int frb_launch_euler1d(frb_prob_t p, const double *u, const double *ua, double *out, FrbStage st);
 int frb_launch_bgk1d(frb_prob_t p, const double *u, const double *ua, double *out, FrbStage st);
 int frb_launch_euler2d_generic(frb_prob_t p, const double *u, const double *ua, double *out, FrbStage st);
+int frb_launch_euler2d_curv(frb_prob_t p, const double *u, const double *ua, double *out, FrbStage st);
+int frb_launch_ghost_cylinder(frb_prob_t p, double *u);
 int frb_launch_euler2d_march(frb_prob_t p, const double *u, const double *ua, double *out, FrbStage st);
 bool frb_euler2d_march_supported(frb_prob_t p);
 // row-chunk path (frb_euler2d_rc.cu, frb_rc.cu); every pointer is an RC buffer unless named ref

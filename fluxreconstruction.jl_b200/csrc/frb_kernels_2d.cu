@@ -307,6 +307,11 @@ int frb_launch_ghost_fill2d(frb_prob_t p, double *u, int mode) {
   } else if (mode == FRB_GHOST_COPY) {  // shock-vortex.jl:324-326
     ghost_y_kernel<<<gy, blk, 0, s>>>(u, p->nx, p->ny, nplanes, npp, 1, p->ny, -1);
     ghost_x_kernel<<<gx, blk, 0, s>>>(u, p->nx, p->ny, nplanes, npp, 0, p->nx, -1, 0);
+  } else if (mode == FRB_GHOST_PERIODIC) {  // dev/parallelogram.jl:201-205
+    ghost_x_kernel<<<gx, blk, 0, s>>>(u, p->nx, p->ny, nplanes, npp, p->nx, 1, -1, 1);
+    ghost_y_kernel<<<gy, blk, 0, s>>>(u, p->nx, p->ny, nplanes, npp, p->ny, 1, -1);
+  } else if (mode == FRB_GHOST_CYLINDER) {  // dev/cylinder2.jl:176-187
+    return frb_launch_ghost_cylinder(p, u);
   } else {
     frb_set_error("unknown ghost mode");
     return FRB_ERR_ARG;

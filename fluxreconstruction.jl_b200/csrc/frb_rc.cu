@@ -146,6 +146,9 @@ int frb_rc_ghost_fill(frb_prob_t p, double *u, int mode) {
   } else if (mode == FRB_GHOST_COPY) {
     if ((r = rc_ghost_y(p, u, g, 1, p->ny, -1))) return r;
     if ((r = rc_ghost_x(p, u, g, 0, p->nx, -1, 0))) return r;
+  } else if (mode == FRB_GHOST_PERIODIC) {
+    if ((r = rc_ghost_x(p, u, g, p->nx, 1, -1, 1))) return r;
+    if ((r = rc_ghost_y(p, u, g, p->ny, 1, -1))) return r;
   } else {
     frb_set_error("unknown ghost mode");
     return FRB_ERR_ARG;

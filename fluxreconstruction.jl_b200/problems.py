@@ -31,7 +31,7 @@ from . import _lib
 from ._lib import Context, check, fortran_ptr, lib, make_operators
 
 BC = {"dirichlet": 0, "period": 1}
-GHOST = {None: -1, "none": -1, "wave_x": 0, "wave_y": 1, "copy": 2}
+GHOST = {None: -1, "none": -1, "wave_x": 0, "wave_y": 1, "copy": 2, "periodic": 3, "cylinder": 4}
 KERNEL = {"auto": 0, "generic": 1, "march": 2, "rc": 3}
 FLUX = {"hll": 0, "lf": 1, "roe": 2}
 
@@ -318,6 +318,44 @@ class Euler2DProblem(_Problem):
                                        C.byref(self.h)))
         if kernel != "auto":
             self.set_kernel(kernel)
+        self.upload(self.u0)
+
+
+class Euler2DCurvProblem(_Problem):
+    """ODEProblem(dudt!, u0, tspan, p) of the curvilinear scratch scripts: dev/parallelogram.jl:80-194
+    (``corr="sp"``: correction factors from the solution-point ``ps.iJ``) and dev/cylinder2.jl:52-170
+    (``corr="fp"``: factors from the flux-point ``ps.Ji``; ``wall_xlo=True``: mirror wall on x face 1).
+    ``ps = FRPSpace2D(base, deg)`` with one ghost ring; ``n1[nx+1, ny, 2]``, ``n2[nx, ny+1, 2]`` are the unit
+    face normals the scripts keep as globals (default: ``face_normals(ps.vertices)``).  ``fy_index="l"``
+    reproduces the scripts' ``fy_interaction[i, j, l, m]`` (parallelogram.jl:147-148); the default ``"k"`` is
+    the index the rectangular scripts use (euler2d_wave.jl:100-103).  u0[nx+2, ny+2, nsp, nsp, 4]."""
+
+    def __init__(self, u0, tspan, ps, gamma, n1=None, n2=None, corr="sp", fy_index="k", wall_xlo=False, ctx=None):
+        super().__init__(u0, tspan, ctx)
+        from .spaces import correction_factors_fp, face_normals
+
+        nsp = ps.deg + 1
+        if ps.ngx != 1 or ps.ngy != 1:
+            raise ValueError("the space must carry one ghost ring (embed ghost-less directions first)")
+        if self.u0.shape != (ps.nx + 2, ps.ny + 2, nsp, nsp, 4):
+            raise ValueError("u0 must be [nx+2, ny+2, nsp, nsp, 4] (one ghost ring)")
+        if n1 is None or n2 is None:
+            n1, n2 = face_normals(ps.vertices)
+        n1, n2 = np.asfortranarray(n1, dtype=np.float64), np.asfortranarray(n2, dtype=np.float64)
+        if n1.shape != (ps.nx + 1, ps.ny, 2) or n2.shape != (ps.nx, ps.ny + 1, 2):
+            raise ValueError("n1 must be [nx+1, ny, 2] and n2 [nx, ny+1, 2]")
+        self.gamma = float(gamma)
+        iJ = np.asfortranarray(ps.iJ, dtype=np.float64)
+        fpc = None
+        if corr == "fp":
+            fpc = correction_factors_fp(ps.Ji, n1, n2)
+        elif corr != "sp":
+            raise ValueError("corr must be 'sp' or 'fp'")
+        flags = (1 if fy_index == "l" else 0) | (2 if wall_xlo else 0)
+        ops, self._keep = _ops_of(ps)
+        check(lib().frb_euler2d_curv_create(self.ctx.h, ps.nx, ps.ny, C.byref(ops), _lib.dptr(iJ), _lib.dptr(n1),
+                                            _lib.dptr(n2), None if fpc is None else _lib.dptr(fpc), flags,
+                                            self.gamma, C.byref(self.h)))
         self.upload(self.u0)
 
 

@@ -25,7 +25,8 @@ from numpy.polynomial import legendre as L
 __all__ = [
     "legendre_point", "gausslegendre", "lagrange_point", "dlagrange", "standard_lagrange", "dlegendre",
     "dradau", "dsd", "dhuynh", "vandermonde_matrix", "dvandermonde_matrix", "global_sp", "r_x",
-    "FRPSpace1D", "FRPSpace2D",
+    "FRPSpace1D", "FRPSpace2D", "PSpace2D", "CSpace2D", "quad_jacobians", "face_normals",
+    "correction_factors_fp", "embed_ghostless_x",
 ]
 
 
@@ -159,11 +160,136 @@ class FRPSpace1D:
         return a[self.ng : self.ng + self.nx]
 
 
+class PSpace2D:
+    """[KB-recall] KitBase.PSpace2D: the structured physical space the 2-D scripts build, either uniform
+    ``PSpace2D(x0, x1, nx, y0, y1, ny, ngx, ngy)`` or from explicit cell data
+    ``PSpace2D(x0, x1, nx, y0, y1, ny, x, y, dx, dy, vertices)`` (dev/parallelogram.jl:71).  Arrays cover
+    the ghost cells (index 0 = reference index 1 - ng); ``vertices[i, j, 4, 2]`` run counter-clockwise from
+    the lower left corner (geo_jacobi.jl:50-66)."""
+
+    def __init__(self, x0, x1, nx, y0, y1, ny, *rest):
+        self.x0, self.x1, self.nx = float(x0), float(x1), int(nx)
+        self.y0, self.y1, self.ny = float(y0), float(y1), int(ny)
+        if len(rest) == 5:
+            self.x, self.y, self.dx, self.dy, self.vertices = (np.asfortranarray(a, dtype=np.float64) for a in rest)
+            self.ngx = (self.vertices.shape[0] - self.nx) // 2
+            self.ngy = (self.vertices.shape[1] - self.ny) // 2
+            return
+        ngx, ngy = (list(rest) + [0, 0])[:2]
+        self.ngx, self.ngy = int(ngx), int(ngy)
+        dx, dy = (self.x1 - self.x0) / self.nx, (self.y1 - self.y0) / self.ny
+        xc = self.x0 + (np.arange(1 - self.ngx, self.nx + self.ngx + 1) - 0.5) * dx
+        yc = self.y0 + (np.arange(1 - self.ngy, self.ny + self.ngy + 1) - 0.5) * dy
+        self.x, self.y = (np.asfortranarray(a) for a in np.meshgrid(xc, yc, indexing="ij"))
+        self.dx, self.dy = np.full_like(self.x, dx), np.full_like(self.x, dy)
+        sx, sy = np.array([-0.5, 0.5, 0.5, -0.5]), np.array([-0.5, -0.5, 0.5, 0.5])
+        self.vertices = np.asfortranarray(np.stack(
+            [self.x[..., None] + sx * dx, self.y[..., None] + sy * dy], axis=-1))
+
+
+class CSpace2D:
+    """[KB-recall] KitBase.CSpace2D(r0, r1, nr, th0, th1, nth, ngr, ngth) (dev/cylinder2.jl:22): polar
+    cells, centre (r0 + (i - 1/2) dr, th0 + (j - 1/2) dth), vertices at (r -+ dr/2, th -+ dth/2)."""
+
+    def __init__(self, r0, r1, nr, th0, th1, nth, ngr=0, ngth=0):
+        self.r0, self.r1, self.nr = float(r0), float(r1), int(nr)
+        self.th0, self.th1, self.nth = float(th0), float(th1), int(nth)
+        self.ngr, self.ngth = int(ngr), int(ngth)
+        self.nx, self.ny, self.ngx, self.ngy = self.nr, self.nth, self.ngr, self.ngth
+        dr, dth = (self.r1 - self.r0) / self.nr, (self.th1 - self.th0) / self.nth
+        rc = self.r0 + (np.arange(1 - ngr, nr + ngr + 1) - 0.5) * dr
+        tc = self.th0 + (np.arange(1 - ngth, nth + ngth + 1) - 0.5) * dth
+        self.r, self.theta = (np.asfortranarray(a) for a in np.meshgrid(rc, tc, indexing="ij"))
+        self.dr, self.dtheta = np.full_like(self.r, dr), np.full_like(self.r, dth)
+        self.x, self.y = self.r * np.cos(self.theta), self.r * np.sin(self.theta)
+        sr, st = np.array([-0.5, 0.5, 0.5, -0.5]), np.array([-0.5, -0.5, 0.5, 0.5])
+        rv, tv = self.r[..., None] + sr * dr, self.theta[..., None] + st * dth
+        self.vertices = np.asfortranarray(np.stack([rv * np.cos(tv), rv * np.sin(tv)], axis=-1))
+
+
+def embed_ghostless_x(base):
+    """The cylinder scripts hold every array over i = 1:nr without radial ghosts (CSpace2D(..., 0, 1),
+    dev/cylinder2.jl:22,33) while the ABI wants a full ghost ring.  Cell nr is never updated there
+    (cylinder2.jl:154 runs i over 1:nx-1) and only feeds face nr: it *is* the outer ghost column.  This
+    returns the same cells as a PSpace2D with nx = nr - 1 interior columns, column nr as the upper ghost and a
+    dummy copy of column 1 as the lower ghost (never read when x face 1 is the mirror wall).  States are
+    embedded the same way: ``np.concatenate([u[:1], u])``."""
+    if base.ngx != 0 or base.ngy != 1:
+        raise ValueError("expects a space without ghosts in x and with one ghost layer in y")
+    cat = lambda a: np.asfortranarray(np.concatenate([a[:1], a], axis=0))  # noqa: E731
+    dx = getattr(base, "dx", getattr(base, "dr", None))
+    dy = getattr(base, "dy", getattr(base, "dtheta", None))
+    lo = getattr(base, "x0", getattr(base, "r0", 0.0)), getattr(base, "y0", getattr(base, "th0", 0.0))
+    hi = getattr(base, "x1", getattr(base, "r1", 0.0)), getattr(base, "y1", getattr(base, "th1", 0.0))
+    return PSpace2D(lo[0], hi[0], base.nx - 1, lo[1], hi[1], base.ny, cat(base.x), cat(base.y), cat(dx), cat(dy),
+                    cat(base.vertices))
+
+
+# derivatives of the bilinear shape functions lambda^1..4 (geo_jacobi.jl:55-66) as tables in (r, s)
+def _shape_derivatives(r, s):
+    r, s = np.asarray(r, dtype=np.float64), np.asarray(s, dtype=np.float64)
+    d_r = np.stack([s - 1.0, 1.0 - s, s + 1.0, -(s + 1.0)], axis=-1) / 4.0
+    d_s = np.stack([r - 1.0, -(r + 1.0), r + 1.0, 1.0 - r], axis=-1) / 4.0
+    return d_r, d_s
+
+
+def quad_jacobians(vertices, r, s):
+    """J[i, j, ..., (x,y), (r,s)] of the bilinear map of every cell at the points (r[...], s[...])."""
+    d_r, d_s = _shape_derivatives(r, s)
+    D = np.stack([d_r, d_s], axis=-1)  # [..., vertex, (r, s)]
+    return np.einsum("ijvc,...vd->ij...cd", np.asarray(vertices, dtype=np.float64), D)
+
+
+def _inv2(J):
+    det = J[..., 0, 0] * J[..., 1, 1] - J[..., 0, 1] * J[..., 1, 0]
+    adj = np.stack([np.stack([J[..., 1, 1], -J[..., 0, 1]], -1), np.stack([-J[..., 1, 0], J[..., 0, 0]], -1)], -2)
+    return adj / det[..., None, None]
+
+
+def face_normals(vertices, ng=1):
+    """Unit normals of the interior-and-boundary faces of a structured quad mesh, in the layout of the
+    scripts' hand-built tables: n1[nx+1, ny, 2] (x faces, pointing towards +r) and n2[nx, ny+1, 2]
+    (y faces, towards +s).  For the parallelogram and the polar mesh this reproduces
+    dev/parallelogram.jl:176-186 and dev/cylinder2.jl:39-49 (theta0 = 0)."""
+    v = np.asarray(vertices, dtype=np.float64)
+    nx, ny = v.shape[0] - 2 * ng, v.shape[1] - 2 * ng
+    I, Jn = slice(ng, ng + nx), slice(ng, ng + ny)
+    # x face i = left edge (vertex 1 -> 4) of cell i; the last one = right edge (2 -> 3) of cell nx
+    t = np.concatenate([v[I, Jn, 3] - v[I, Jn, 0], (v[ng + nx - 1, Jn, 2] - v[ng + nx - 1, Jn, 1])[None]], axis=0)
+    n1 = np.stack([t[..., 1], -t[..., 0]], axis=-1)
+    n1 /= np.linalg.norm(n1, axis=-1, keepdims=True)
+    # y face j = bottom edge (1 -> 2) of cell j; the last one = top edge (4 -> 3) of cell ny
+    t = np.concatenate([v[I, Jn, 1] - v[I, Jn, 0], (v[I, ng + ny - 1, 2] - v[I, ng + ny - 1, 3])[:, None]], axis=1)
+    n2 = np.stack([-t[..., 1], t[..., 0]], axis=-1)
+    n2 /= np.linalg.norm(n2, axis=-1, keepdims=True)
+    return np.asfortranarray(n1), np.asfortranarray(n2)
+
+
+def correction_factors_fp(Ji, n1, n2, ng=1):
+    """The flux-point correction factors of dev/cylinder2.jl:155-158 for the ABI's ``fpc[nx, ny, nsp, 4]``:
+    (inv(Ji[i,j][4,l]) n1[i,j])[1], (inv(Ji[i,j][2,l]) n1[i+1,j])[1], (inv(Ji[i,j][1,k]) n2[i,j])[2],
+    (inv(Ji[i,j][3,k]) n2[i,j+1])[2]."""
+    nx, ny = n1.shape[0] - 1, n2.shape[1] - 1
+    iJi = _inv2(Ji[ng : ng + nx, ng : ng + ny])  # [nx, ny, face, pt, 2, 2]
+    row = lambda face, c, n: np.einsum("ijpd,ijd->ijp", iJi[:, :, face, :, c, :], n)  # noqa: E731
+    return np.asfortranarray(np.stack(
+        [row(3, 0, n1[:-1]), row(1, 0, n1[1:]), row(0, 1, n2[:, :-1]), row(2, 1, n2[:, 1:])], axis=-1))
+
+
 class FRPSpace2D:
     """FRPSpace2D(x0, x1, nx, y0, y1, ny, deg, ngx, ngy) on the uniform rectangular PSpace2D
-    (struct.jl:130-245).  ``J[i,j][k,l]`` is diag(dx/2, dy/2) here and kept as Jx, Jy."""
+    (struct.jl:130-245).  ``J[i,j][k,l]`` is diag(dx/2, dy/2) there and kept as Jx, Jy.
 
-    def __init__(self, x0, x1, nx, y0, y1, ny, deg, ngx=0, ngy=0, **_):
+    ``FRPSpace2D(base, deg)`` (struct.jl:130) with a base space that carries ``vertices`` (PSpace2D from
+    explicit cell data, CSpace2D) builds the point-wise metric instead: ``J``, ``iJ`` as
+    [nxg, nyg, nsp, nsp, 2, 2] and ``Ji`` [nxg, nyg, 4, nsp, 2, 2].  ``literal_Ji=True`` (default) keeps the
+    reference's flux-point tables as they are (struct.jl:145-158 puts 0.0 where -1.0 is meant and
+    geo_jacobi.jl:93-94 takes one Jacobian per face); ``False`` evaluates at the real flux points."""
+
+    def __init__(self, x0, x1=None, nx=None, y0=None, y1=None, ny=None, deg=None, ngx=0, ngy=0, literal_Ji=True, **_):
+        if hasattr(x0, "vertices"):
+            self._init_from_base(x0, int(x1), literal_Ji)
+            return
         self.x0, self.x1, self.nx = float(x0), float(x1), int(nx)
         self.y0, self.y1, self.ny = float(y0), float(y1), int(ny)
         self.deg, self.ngx, self.ngy = int(deg), int(ngx), int(ngy)
@@ -196,9 +322,41 @@ class FRPSpace2D:
         self.V = np.asfortranarray(np.einsum("ka,lb->lkab", V1, V1).reshape(nsp * nsp, nsp * nsp))
         self.iV = np.asfortranarray(np.linalg.inv(self.V))
 
+    def _init_from_base(self, base, deg, literal_Ji):
+        self.base, self.deg = base, deg
+        self.nx, self.ny, self.ngx, self.ngy = base.nx, base.ny, base.ngx, base.ngy
+        self.x, self.y, self.vertices = base.x, base.y, np.asarray(base.vertices, dtype=np.float64)
+        nsp = deg + 1
+        self.np = nsp * nsp
+        r = legendre_point(deg)
+        self.xpl = r
+        rr, ss = np.meshgrid(r, r, indexing="ij")  # [k, l]: k <-> r, l <-> s (struct.jl:169-174)
+        self._J = np.asfortranarray(quad_jacobians(self.vertices, rr, ss))
+        self.iJ = np.asfortranarray(_inv2(self._J))
+        if literal_Ji:  # one point per face: (ri[face, 1], si[face, 1]) of the tables at struct.jl:145-155
+            fr = np.repeat(np.array([r[0], 1.0, r[-1], 0.0])[:, None], nsp, axis=1)
+            fs = np.repeat(np.array([0.0, r[0], 1.0, r[-1]])[:, None], nsp, axis=1)
+        else:  # faces 1..4: s = -1, r = +1, s = +1, r = -1, points in trace order
+            one = np.ones(nsp)
+            fr, fs = np.stack([r, one, r, -one]), np.stack([-one, r, one, r])
+        self.Ji = np.asfortranarray(quad_jacobians(self.vertices, fr, fs))
+        # bilinear map of the solution points (struct.jl:161-175)
+        N = np.stack([(rr - 1) * (ss - 1), (rr + 1) * (1 - ss), (rr + 1) * (ss + 1), (1 - rr) * (ss + 1)], -1) / 4.0
+        self.xpg = np.asfortranarray(np.einsum("ijvc,klv->ijklc", self.vertices, N))
+        w = gausslegendre(nsp)[1]
+        self.wp = np.asfortranarray(np.outer(w, w))
+        self.ll, self.lr, self.dl = standard_lagrange(r)
+        self.dll, self.dlr, _ = _edge_slopes(deg, r)
+        self.dhl, self.dhr = dradau(deg, r)
+        V1 = vandermonde_matrix(deg, r)
+        self.V = np.asfortranarray(np.einsum("ka,lb->lkab", V1, V1).reshape(nsp * nsp, nsp * nsp))
+        self.iV = np.asfortranarray(np.linalg.inv(self.V))
+
     @property
     def J(self):
         """ps.J[i,j][k,l] of the reference, materialised lazily: (nxg, nyg, nsp, nsp, 2, 2)."""
+        if hasattr(self, "_J"):
+            return self._J
         nsp = self.deg + 1
         J = np.zeros((self.nx + 2 * self.ngx, self.ny + 2 * self.ngy, nsp, nsp, 2, 2), order="F")
         J[..., 0, 0] = self.Jx

@@ -48,7 +48,12 @@ enum { FRB_BC_DIRICHLET = 0, FRB_BC_PERIOD = 1 };
 enum { FRB_SCHEME_EULER = 0, FRB_SCHEME_MIDPOINT = 1, FRB_SCHEME_SSPRK3 = 2 };
 /* per-step ghost fill of the user loop: euler2d_wave.jl:127-132 (x wave),
  * :159-164 (y wave), shock-vortex.jl:324-326 (copy) */
-enum { FRB_GHOST_NONE = -1, FRB_GHOST_WAVE_X = 0, FRB_GHOST_WAVE_Y = 1, FRB_GHOST_COPY = 2 };
+enum { FRB_GHOST_NONE = -1, FRB_GHOST_WAVE_X = 0, FRB_GHOST_WAVE_Y = 1, FRB_GHOST_COPY = 2,
+       /* plain periodic copies in both directions: dev/parallelogram.jl:201-205 */
+       FRB_GHOST_PERIODIC = 3,
+       /* dev/cylinder2.jl:176-187: theta ghost rows = point-reversed mirror images with flipped y momentum,
+        * outer radial column copied from its neighbour over the first half of the rows */
+       FRB_GHOST_CYLINDER = 4 };
 /* eq_advection.jl (seam epsilon 1e-6) vs example/advection_lowlevel.jl (1e-8) */
 enum { FRB_ADV_PACKAGED = 0, FRB_ADV_LOWLEVEL = 1 };
 /* 2-D Euler kernel selection: AUTO picks the fused row-marching TMA kernel when
@@ -95,6 +100,24 @@ int32_t frb_euler1d_create(frb_ctx_t ctx, int32_t ncell, const frb_operators *op
  * Jx = dx/2, Jy = dy/2 are the diagonal of ps.J[i,j][k,l] (geo_jacobi.jl:77-108). */
 int32_t frb_euler2d_create(frb_ctx_t ctx, int32_t nx, int32_t ny, const frb_operators *ops,
                            double Jx, double Jy, double gamma, frb_prob_t *out);
+/* dudt! on a curvilinear structured quadrilateral FRPSpace2D(base, deg) (src/struct.jl:130-227): the
+ * scratch scripts dev/parallelogram.jl:80-165 and dev/cylinder2.jl:52-164.  State as in
+ * frb_euler2d_create, u[nx+2, ny+2, nsp, nsp, 4].  Metric and normals, Julia column-major:
+ *   iJ [nx+2, ny+2, nsp, nsp, 2, 2] = ps.iJ[i,j][k,l][a,b] flattened (struct.jl:137-142; ghost entries unused)
+ *   n1 [nx+1, ny, 2], n2 [nx, ny+1, 2] = the scripts' unit face normals (parallelogram.jl:176-186)
+ *   fpc[nx, ny, nsp, 4] or NULL: correction factors at the flux points,
+ *       (inv(Ji[i,j][4,l]) n1[i,j])[1], (inv(Ji[i,j][2,l]) n1[i+1,j])[1],
+ *       (inv(Ji[i,j][1,k]) n2[i,j])[2], (inv(Ji[i,j][3,k]) n2[i,j+1])[2]      (cylinder2.jl:155-158);
+ *       NULL: factors from the solution-point inverse Jacobian, (iJ[i,j][k,l] n)[c] (parallelogram.jl:145-148)
+ * flags: FRB_CURV_FY_ROW_INDEX reproduces the scripts' fy_interaction[i,j,l,m] (row index where the
+ * rectangular scripts use the flux-point index k, euler2d_wave.jl:100-103); FRB_CURV_WALL_XLO makes x face 1
+ * the mirror wall of cylinder2.jl:100-120 (ghost column 0 is then never read).  HLL flux, deg 1..3, single
+ * GPU; every frb_* call of an euler2d problem applies (f!, step, tableau, limiter, filter, ghost fill). */
+#define FRB_CURV_FY_ROW_INDEX 1
+#define FRB_CURV_WALL_XLO 2
+int32_t frb_euler2d_curv_create(frb_ctx_t ctx, int32_t nx, int32_t ny, const frb_operators *ops,
+                                const double *iJ, const double *n1, const double *n2, const double *fpc,
+                                int32_t flags, double gamma, frb_prob_t *out);
 /* mol! of example/bgk_wave.jl:69-129 with its periodic e2f/f2e tables (:42-67).
  * State u[ncell, nu, nsp]; dx[ncell]; velo, weights [nu] (VSpace1D). */
 int32_t frb_bgk1d_create(frb_ctx_t ctx, int32_t ncell, int32_t nu, const frb_operators *ops,

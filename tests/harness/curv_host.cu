@@ -1,0 +1,47 @@
+// TEST HARNESS (not part of libfrb200.so): runs the __host__ __device__ element routines of
+// csrc/frb_euler2d_curv_elem.cuh in plain CPU loops, so that the arithmetic and the index maps of the
+// curvilinear kernels can be checked against the NumPy oracle on a box without a GPU
+// (tests/test_curv_host.py).  Built by tests/harness/build.py with nvcc as host code only.
+#include <string.h>
+
+#include "../../fluxreconstruction.jl_b200/csrc/frb_euler2d_curv_elem.cuh"
+
+template <int NSP>
+static void run(const double *u, const double *ua, double *out, double *fx, double *fy, const CurvGeom &g,
+                double gamma, const FrbOps &ops, const FrbStage &st) {
+  for (int j = 1; j <= g.ny + 1; ++j)
+    for (int i = 1; i <= g.nx + 1; ++i)
+      for (int p = 0; p < NSP; ++p) {
+        if (j <= g.ny) frbcurv::face_x<NSP>(i, j, p, u, fx, g, gamma, ops);
+        if (i <= g.nx) frbcurv::face_y<NSP>(i, j, p, u, fy, g, gamma, ops);
+      }
+  for (int j = 1; j <= g.ny; ++j)
+    for (int i = 1; i <= g.nx; ++i)
+      for (int m = 0; m < 4; ++m) frbcurv::element_var<NSP>(i, j, m, u, ua, fx, fy, out, g, gamma, ops, st);
+}
+
+// operators as the ABI takes them (lpdm column-major nsp x nsp); stage = (ca, cb, cdt, use_a, rhs_only)
+extern "C" int curv_host_stage(int nx, int ny, int nsp, const double *u, const double *ua, double *out, double *fx,
+                               double *fy, const double *iJ, const double *n1, const double *n2, const double *fpc,
+                               int flags, double gamma, const double *ll, const double *lr, const double *lpdm,
+                               const double *dgl, const double *dgr, double ca, double cb, double cdt, int use_a,
+                               int rhs_only) {
+  FrbOps ops;
+  memset(&ops, 0, sizeof ops);
+  for (int q = 0; q < nsp; ++q) {
+    ops.ll[q] = ll[q]; ops.lr[q] = lr[q]; ops.dgl[q] = dgl[q]; ops.dgr[q] = dgr[q];
+    for (int k = 0; k < nsp; ++k) ops.lpdm[q * FRB_NSPMAX + k] = lpdm[q + nsp * k];
+  }
+  CurvGeom g;
+  g.nx = nx; g.ny = ny; g.iJ = iJ; g.n1 = n1; g.n2 = n2; g.fpc = fpc;
+  g.fy_row = (flags & FRB_CURV_FY_ROW_INDEX) ? 1 : 0;
+  g.wall_xlo = (flags & FRB_CURV_WALL_XLO) ? 1 : 0;
+  FrbStage st = {ca, cb, cdt, use_a, rhs_only, 0};
+  switch (nsp) {
+    case 2: run<2>(u, ua, out, fx, fy, g, gamma, ops, st); break;
+    case 3: run<3>(u, ua, out, fx, fy, g, gamma, ops, st); break;
+    case 4: run<4>(u, ua, out, fx, fy, g, gamma, ops, st); break;
+    default: return -1;
+  }
+  return 0;
+}
