@@ -1060,7 +1060,6 @@ extern "C" int32_t frb_set_flux(frb_prob_t p, int32_t kind) {
   FRB_REQUIRE(p, FRB_ERR_ARG, "frb_set_flux: prob is NULL");
   FRB_REQUIRE(p->kind == K_EULER1D || p->kind == K_EULER2D, FRB_ERR_STATE, "frb_set_flux: Euler problems only");
   FRB_REQUIRE(kind >= FRB_FLUX_HLL && kind <= FRB_FLUX_ROE, FRB_ERR_ARG, "frb_set_flux: unknown flux kind");
-  FRB_REQUIRE(kind == FRB_FLUX_HLL || !p->curv_iJ, FRB_ERR_STATE, "frb_set_flux: curvilinear problems are HLL only");
   p->flux = kind;
   return FRB_OK;
 }

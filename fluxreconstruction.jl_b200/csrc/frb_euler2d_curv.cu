@@ -94,6 +94,7 @@ int frb_launch_euler2d_curv(frb_prob_t p, const double *u, const double *ua, dou
   g.iJ = p->curv_iJ; g.n1 = p->curv_n1; g.n2 = p->curv_n2; g.fpc = p->curv_fpc;
   g.fy_row = (p->curv_flags & FRB_CURV_FY_ROW_INDEX) ? 1 : 0;
   g.wall_xlo = (p->curv_flags & FRB_CURV_WALL_XLO) ? 1 : 0;
+  g.flux = p->flux;
   if (st.nested) { st.cdt *= st.cb; st.nested = 0; }
   cudaStream_t s = p->ctx->stream;
   dim3 fb(128), fg((p->nx + 1 + 127) / 128, p->ny + 1, 2 * p->nsp);

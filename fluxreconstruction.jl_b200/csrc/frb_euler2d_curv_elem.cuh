@@ -29,6 +29,7 @@
 #include <math.h>
 
 #include "frb_internal.cuh"
+#include "frb_physics.cuh"
 
 #if defined(__CUDACC__)
 #define FRB_HD __host__ __device__ __forceinline__
@@ -41,6 +42,7 @@ struct CurvGeom {
   const double *iJ, *n1, *n2, *fpc;  // fpc == nullptr: solution-point factors
   int fy_row;    // 1: y common flux indexed by the row l (the scripts' literal form)
   int wall_xlo;  // 1: x face 1 is the mirror wall of dev/cylinder2.jl:100-120
+  int flux;      // FRB_FLUX_HLL (the scripts) | LF | ROE
 };
 
 namespace frbcurv {
@@ -49,10 +51,10 @@ struct W4 {
   double a, b, c, d;
 };
 
-// local_frame -> flux_hll!(fw, wL, wR, gamma, 1.0) -> global_frame about the unit normal (c, s)
-// (parallelogram.jl:119-123).  wall != 0 replaces the left state by the mirror state of the right one
-// in the face frame (cylinder2.jl:103-114).
-FRB_HD W4 hll_normal(W4 L, W4 R, double c, double s, double gamma, int wall) {
+// local_frame -> common flux (flux_hll!(fw, wL, wR, gamma, 1.0) in the scripts; LF / Roe as defined in
+// DESIGN.md section 2) -> global_frame about the unit normal (c, s) (parallelogram.jl:119-123).  wall != 0
+// replaces the left state by the mirror state of the right one in the face frame (cylinder2.jl:103-114).
+FRB_HD W4 flux_normal(int kind, W4 L, W4 R, double c, double s, double gamma, int wall) {
   const double gm1 = gamma - 1.0;
   double l0 = L.a, l1 = fma(L.c, s, L.b * c), l2 = fma(-L.b, s, L.c * c), l3 = L.d;
   const double r0 = R.a, r1 = fma(R.c, s, R.b * c), r2 = fma(-R.b, s, R.c * c), r3 = R.d;
@@ -67,27 +69,8 @@ FRB_HD W4 hll_normal(W4 L, W4 R, double c, double s, double gamma, int wall) {
     l2 = rn * V;
     l3 = 0.5 * rn / ln / gm1 + 0.5 * rn * (U * U + V * V);
   }
-  const double il = 1.0 / l0, ir = 1.0 / r0;
-  const double ul = l1 * il, vl = l2 * il, ur = r1 * ir, vr = r2 * ir;
-  const double pl = gm1 * (l3 - 0.5 * fma(l1, ul, l2 * vl));
-  const double pr = gm1 * (r3 - 0.5 * fma(r1, ur, r2 * vr));
-  const double al = sqrt(gamma * pl * il), ar = sqrt(gamma * pr * ir);
-  const double lmin = ul - al, lmax = ur + ar;
-  const double fl0 = l1, fl1 = fma(l1, ul, pl), fl2 = l1 * vl, fl3 = (l3 + pl) * ul;
-  const double fr0 = r1, fr1 = fma(r1, ur, pr), fr2 = r1 * vr, fr3 = (r3 + pr) * ur;
-  double f0, f1, f2, f3;
-  if (lmin >= 0.0) {
-    f0 = fl0; f1 = fl1; f2 = fl2; f3 = fl3;
-  } else if (lmax <= 0.0) {
-    f0 = fr0; f1 = fr1; f2 = fr2; f3 = fr3;
-  } else {
-    const double fac = 1.0 / (lmax - lmin), mm = lmax * lmin;
-    f0 = fac * (lmax * fl0 - lmin * fr0 + mm * (r0 - l0));
-    f1 = fac * (lmax * fl1 - lmin * fr1 + mm * (r1 - l1));
-    f2 = fac * (lmax * fl2 - lmin * fr2 + mm * (r2 - l2));
-    f3 = fac * (lmax * fl3 - lmin * fr3 + mm * (r3 - l3));
-  }
-  return {f0, fma(-f2, s, f1 * c), fma(f1, s, f2 * c), f3};
+  const frb::Flux4 f = frb::riemann4(kind, l0, l1, l2, l3, r0, r1, r2, r3, gamma);
+  return {f.f0, fma(-f.f2, s, f.f1 * c), fma(f.f1, s, f.f2 * c), f.f3};
 }
 
 template <int NSP>
@@ -127,7 +110,7 @@ FRB_HD void face_x(int i, int j, int p, const double *__restrict__ u, double *__
   load_trace_x<NSP>(u, e - 1, NE, p, ops.lr, L);  // u_face[i-1, j, 2, p, :]
   load_trace_x<NSP>(u, e, NE, p, ops.ll, R);      // u_face[i, j, 4, p, :]
   const size_t f = (size_t)(i - 1) + (size_t)(g.nx + 1) * (j - 1), sf = (size_t)(g.nx + 1) * g.ny;
-  const W4 h = hll_normal({L[0], L[1], L[2], L[3]}, {R[0], R[1], R[2], R[3]}, g.n1[f], g.n1[f + sf], gamma,
+  const W4 h = flux_normal(g.flux, {L[0], L[1], L[2], L[3]}, {R[0], R[1], R[2], R[3]}, g.n1[f], g.n1[f + sf], gamma,
                           g.wall_xlo && i == 1);
   fx[f + sf * (p + NSP * 0)] = h.a;
   fx[f + sf * (p + NSP * 1)] = h.b;
@@ -146,7 +129,7 @@ FRB_HD void face_y(int i, int j, int p, const double *__restrict__ u, double *__
   load_trace_y<NSP>(u, e - NXG, NE, p, ops.lr, L);  // u_face[i, j-1, 3, p, :]
   load_trace_y<NSP>(u, e, NE, p, ops.ll, R);        // u_face[i, j, 1, p, :]
   const size_t f = (size_t)(i - 1) + (size_t)g.nx * (j - 1), sf = (size_t)g.nx * (g.ny + 1);
-  const W4 h = hll_normal({L[0], L[1], L[2], L[3]}, {R[0], R[1], R[2], R[3]}, g.n2[f], g.n2[f + sf], gamma, 0);
+  const W4 h = flux_normal(g.flux, {L[0], L[1], L[2], L[3]}, {R[0], R[1], R[2], R[3]}, g.n2[f], g.n2[f + sf], gamma, 0);
   fy[f + sf * (p + NSP * 0)] = h.a;
   fy[f + sf * (p + NSP * 1)] = h.b;
   fy[f + sf * (p + NSP * 2)] = h.c;

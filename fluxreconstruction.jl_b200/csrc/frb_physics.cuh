@@ -6,6 +6,10 @@
 #pragma once
 #include <cuda_runtime.h>
 
+// the portable closures are also callable from host code: tests/harness runs the curvilinear element
+// routines (frb_euler2d_curv_elem.cuh) on the CPU; device code generation is unaffected
+#define FRB_PHYS_HD __host__ __device__ __forceinline__
+
 namespace frb {
 
 // 1-D Euler: w = (rho, rho*u, E).  Returns F(w); also u and a (sound speed) if wanted.
@@ -44,7 +48,7 @@ struct Flux4 {
 };
 
 // F and G at a point: euler_flux(w, gamma) -> (F, G)
-__device__ __forceinline__ void euler_flux4(double w0, double w1, double w2, double w3, double gm1,
+FRB_PHYS_HD void euler_flux4(double w0, double w1, double w2, double w3, double gm1,
                                             Flux4 &F, Flux4 &G) {
   double r = 1.0 / w0;
   double u = w1 * r, v = w2 * r;
@@ -55,7 +59,7 @@ __device__ __forceinline__ void euler_flux4(double w0, double w1, double w2, dou
 }
 
 // HLL flux normal to an x-face: states in the global frame, normal velocity = component 1.
-__device__ __forceinline__ Flux4 hll4(double l0, double l1, double l2, double l3, double r0,
+FRB_PHYS_HD Flux4 hll4(double l0, double l1, double l2, double l3, double r0,
                                       double r1, double r2, double r3, double gamma) {
   const double gm1 = gamma - 1.0;
   double il = 1.0 / l0, ir = 1.0 / r0;
@@ -87,7 +91,7 @@ __device__ __forceinline__ Flux4 hll4_y(double l0, double l1, double l2, double 
 // ---- extra common fluxes (the reference's live flux is HLL; LF and Roe are named by
 // the north star, have no reference implementation, and are specified in DESIGN.md section 2) ----
 // Local Lax-Friedrichs (Rusanov): 0.5 (F_L + F_R) - 0.5 alpha (w_R - w_L), alpha = max(|u|+a).
-__device__ __forceinline__ Flux4 lf4(double l0, double l1, double l2, double l3, double r0, double r1,
+FRB_PHYS_HD Flux4 lf4(double l0, double l1, double l2, double l3, double r0, double r1,
                                      double r2, double r3, double gamma) {
   const double gm1 = gamma - 1.0;
   double il = 1.0 / l0, ir = 1.0 / r0;
@@ -103,11 +107,11 @@ __device__ __forceinline__ Flux4 lf4(double l0, double l1, double l2, double l3,
 }
 
 // Roe flux with Harten's entropy fix on the acoustic waves (below 0.1 a~).
-__device__ __forceinline__ double roe_fix(double lam, double d) {
+FRB_PHYS_HD double roe_fix(double lam, double d) {
   double a = fabs(lam);
   return a < d ? (lam * lam + d * d) / (2.0 * d) : a;
 }
-__device__ __forceinline__ Flux4 roe4(double l0, double l1, double l2, double l3, double r0, double r1,
+FRB_PHYS_HD Flux4 roe4(double l0, double l1, double l2, double l3, double r0, double r1,
                                       double r2, double r3, double gamma) {
   const double gm1 = gamma - 1.0;
   double ul = l1 / l0, vl = l2 / l0, ur = r1 / r0, vr = r2 / r0;
@@ -132,7 +136,7 @@ __device__ __forceinline__ Flux4 roe4(double l0, double l1, double l2, double l3
 }
 
 // common flux selector of the generic kernels: kind = FRB_FLUX_HLL / LF / ROE
-__device__ __forceinline__ Flux4 riemann4(int kind, double l0, double l1, double l2, double l3, double r0,
+FRB_PHYS_HD Flux4 riemann4(int kind, double l0, double l1, double l2, double l3, double r0,
                                           double r1, double r2, double r3, double gamma) {
   if (kind == 1) return lf4(l0, l1, l2, l3, r0, r1, r2, r3, gamma);
   if (kind == 2) return roe4(l0, l1, l2, l3, r0, r1, r2, r3, gamma);

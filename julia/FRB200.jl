@@ -84,6 +84,30 @@ function Euler2DProblem(u0, ps, γ)
     p = finalizer(destroy!, Problem(r[], size(A), keep)); upload!(p, A); p
 end
 
+# dudt! of dev/parallelogram.jl:80-165 (fp = false: correction factors from ps.iJ) and dev/cylinder2.jl:52-164
+# (fp = true: factors from the flux-point ps.Ji; wall = true: mirror wall on x face 1).  u0 and ps.iJ / ps.Ji are
+# OffsetArrays over 0:nx+1 x 0:ny+1 (a space without radial ghosts is embedded first, DESIGN.md 4.4);
+# n1[i, j], n2[i, j] are the scripts' global tables of unit normals.  literal_fy = true keeps the scripts'
+# fy_interaction[i, j, l, m] (parallelogram.jl:147-148).
+function Euler2DCurvProblem(u0, ps, γ, n1, n2; fp = false, wall = false, literal_fy = false)
+    A = parent(u0)::Array{Float64,5}
+    nx, ny, nsp = size(A, 1) - 2, size(A, 2) - 2, size(A, 3)
+    ops, keep = operators(ps)
+    PJ, PJi = parent(ps.iJ), parent(ps.Ji)
+    iJ = [PJ[i, j][k, l][a, b] for i in 1:nx+2, j in 1:ny+2, k in 1:nsp, l in 1:nsp, a in 1:2, b in 1:2]
+    N1 = [n1[i, j][c] for i in 1:nx+1, j in 1:ny, c in 1:2]
+    N2 = [n2[i, j][c] for i in 1:nx, j in 1:ny+1, c in 1:2]
+    fpc = fp ? [q == 1 ? (inv(PJi[i+1, j+1][4, p]) * n1[i, j])[1] : q == 2 ? (inv(PJi[i+1, j+1][2, p]) * n1[i+1, j])[1] :
+                q == 3 ? (inv(PJi[i+1, j+1][1, p]) * n2[i, j])[2] : (inv(PJi[i+1, j+1][3, p]) * n2[i, j+1])[2]
+                for i in 1:nx, j in 1:ny, p in 1:nsp, q in 1:4] : nothing
+    r = Ref{Ptr{Cvoid}}(C_NULL)
+    GC.@preserve keep iJ N1 N2 fpc check(ccall((:frb_euler2d_curv_create, lib), Int32,
+        (Ptr{Cvoid}, Int32, Int32, Ref{Operators}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Int32,
+         Float64, Ref{Ptr{Cvoid}}),
+        ctx().h, nx, ny, ops, iJ, N1, N2, fp ? pointer(fpc) : C_NULL, (literal_fy ? 1 : 0) | (wall ? 2 : 0), γ, r))
+    p = finalizer(destroy!, Problem(r[], size(A), keep)); upload!(p, A); p
+end
+
 # mol! of example/bgk_wave.jl:69-129
 # dev/sod.jl:124-127: p = (ps.cellType, ps.J, ps.lf, ps.cellNormals, ps.fpn, ps.∂l, ps.ϕ, γ) of a TriFRPSpace
 function TriEulerProblem(u0::Array{Float64,3}, ps, γ)
@@ -122,7 +146,7 @@ rhs!(prob::Problem) = function (du, u, p, t)
 end
 
 const SCHEME = Dict(:euler => 0, :midpoint => 1, :ssprk3 => 2)
-const GHOST = Dict(:none => -1, :wave_x => 0, :wave_y => 1, :copy => 2)
+const GHOST = Dict(:none => -1, :wave_x => 0, :wave_y => 1, :copy => 2, :periodic => 3, :cylinder => 4)
 set_step_hooks!(p::Problem; ghost = :none, limiter_weights = nothing) = check(ccall((:frb_set_step_hooks, lib), Int32,
     (Ptr{Cvoid}, Int32, Ptr{Float64}), p.h, GHOST[ghost], limiter_weights === nothing ? C_NULL : pointer(limiter_weights)))
 # shock sensor + modal filter on every element (euler_highlevel.jl:37-52, shock-vortex.jl:308-321):

@@ -288,10 +288,13 @@ def wall_state(ul, gamma):
     return o.prim_conserve(pn, gamma)
 
 
-def rhs_euler2d_curv(u, ps, n1, n2, gamma, corr="sp", fpc=None, fy_index="l", wall_xlo=False):
+def rhs_euler2d_curv(u, ps, n1, n2, gamma, corr="sp", fpc=None, fy_index="l", wall_xlo=False, flux="hll"):
     """dudt! of dev/parallelogram.jl:80-165 (corr="sp") / dev/cylinder2.jl:52-164 (corr="fp",
     wall_xlo=True).  u[nx+2, ny+2, nsp, nsp, 4] with one ghost ring; n1[nx+1, ny, 2], n2[nx, ny+1, 2];
-    fpc: flux-point correction factors (corr_factors_fp) when corr == "fp".  du = 0 in the ghosts."""
+    fpc: flux-point correction factors (corr_factors_fp) when corr == "fp".  du = 0 in the ghosts.
+    flux: the common flux in the face frame -- "hll" is what the scripts call; "lf" / "roe" are the north
+    star's extras as defined in fr_oracle.flux_lf / flux_roe."""
+    riemann = o.RIEMANN[flux]
     nxg, nyg, nsp, _, _ = u.shape
     nx, ny = nxg - 2, nyg - 2
     ll, lr, dhl, dhr, lpdm = ps.ll, ps.lr, ps.dhl, ps.dhr, ps.dl
@@ -323,12 +326,12 @@ def rhs_euler2d_curv(u, ps, n1, n2, gamma, corr="sp", fpc=None, fy_index="l", wa
     uR = o.local_frame(u4[1 : nx + 2, 1 : ny + 1], c, s)
     if wall_xlo:  # cylinder2.jl:100-120: face 1 is flux_hll!(fw, ub, ul)
         uL[0] = wall_state(uR[0], gamma)
-    fx = o.global_frame(o.flux_hll(uL, uR, gamma, 1.0), c, s)
+    fx = o.global_frame(riemann(uL, uR, gamma, 1.0), c, s)
     # y faces j = 1..ny+1 (:126-136)
     c, s = n2[:, :, None, 0], n2[:, :, None, 1]
     uL = o.local_frame(u3[1 : nx + 1, 0 : ny + 1], c, s)
     uR = o.local_frame(u1[1 : nx + 1, 1 : ny + 2], c, s)
-    fy = o.global_frame(o.flux_hll(uL, uR, gamma, 1.0), c, s)
+    fy = o.global_frame(riemann(uL, uR, gamma, 1.0), c, s)
 
     if corr == "sp":
         cf = corr_factors_sp(iJ, n1, n2)

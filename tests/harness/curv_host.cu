@@ -36,6 +36,7 @@ extern "C" int curv_host_stage(int nx, int ny, int nsp, const double *u, const d
   g.nx = nx; g.ny = ny; g.iJ = iJ; g.n1 = n1; g.n2 = n2; g.fpc = fpc;
   g.fy_row = (flags & FRB_CURV_FY_ROW_INDEX) ? 1 : 0;
   g.wall_xlo = (flags & FRB_CURV_WALL_XLO) ? 1 : 0;
+  g.flux = (flags >> 8) & 3;  // test-only: the flux kind rides in bits 8..9
   FrbStage st = {ca, cb, cdt, use_a, rhs_only, 0};
   switch (nsp) {
     case 2: run<2>(u, ua, out, fx, fy, g, gamma, ops, st); break;

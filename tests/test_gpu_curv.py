@@ -78,6 +78,21 @@ def test_cylinder_rhs(FR, deg, fy):
     prob.close()
 
 
+@pytest.mark.parametrize("flux", ["lf", "roe"])
+def test_extra_fluxes_in_the_face_frame(FR, flux):
+    nr, nth, deg = 12, 16, 2
+    ps, po, (n1, n2) = cylinder(FR, nr, nth, deg)
+    u = rand_state((nr + 1, nth + 2, deg + 1, deg + 1), 18)
+    prob = FR.Euler2DCurvProblem(u, (0.0, 1.0), ps, GAMMA, corr="fp", fy_index="k", wall_xlo=True)
+    prob.set_flux(flux)
+    du = np.zeros_like(u, order="F")
+    prob.f(du, u, None, 0.0)
+    fpc = c.corr_factors_fp(po.Ji, n1, n2)
+    ref = c.rhs_euler2d_curv(u, po, n1, n2, GAMMA, corr="fp", fpc=fpc, fy_index="k", wall_xlo=True, flux=flux)
+    assert rel(du, ref) <= RTOL_RHS
+    prob.close()
+
+
 def test_rectangular_mesh_equals_the_rectangular_problem(FR):
     nx, ny, deg = 40, 24, 3
     ps = FR.FRPSpace2D(FR.PSpace2D(0.0, 1.0, nx, 0.0, 0.5, ny, 1, 1), deg)
@@ -179,8 +194,6 @@ def test_unsupported_combinations_fail_loudly(FR):
     ps, _, (n1, n2) = parallelogram(FR, nx, ny, deg)
     u = rand_state((nx + 2, ny + 2, deg + 1, deg + 1), 17)
     prob = FR.Euler2DCurvProblem(u, (0.0, 1.0), ps, GAMMA, n1, n2)
-    with pytest.raises(FR.FRBError):
-        prob.set_flux("roe")
     with pytest.raises(FR.FRBError):
         prob.set_kernel("march")
     prob.close()

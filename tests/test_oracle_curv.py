@@ -238,6 +238,9 @@ def test_device_routines_on_the_cpu(host_stage, deg):
     for fy, flags in (("l", 3), ("k", 2)):
         ref = c.rhs_euler2d_curv(u, ps, n1, n2, GAMMA, corr="fp", fpc=fpc, fy_index=fy, wall_xlo=True)
         assert rel(host_stage(u, ps, n1, n2, fpc, flags), ref) < 1e-14
+    for kind, name in ((1, "lf"), (2, "roe")):  # the extra common fluxes, in the face frame
+        ref = c.rhs_euler2d_curv(u, ps, n1, n2, GAMMA, corr="fp", fpc=fpc, fy_index="k", wall_xlo=True, flux=name)
+        assert rel(host_stage(u, ps, n1, n2, fpc, 2 | (kind << 8)), ref) < 1e-13
     ua = rand_state(u.shape[:-1], 7)
     ref = 0.75 * ua + 0.25 * u + 0.25e-3 * c.rhs_euler2d_curv(u, ps, n1, n2, GAMMA, corr="fp", fpc=fpc, fy_index="k",
                                                                wall_xlo=True)
