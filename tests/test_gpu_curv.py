@@ -220,3 +220,34 @@ def test_large_mesh(FR):
     ms, n = prob.last_timing()
     assert n == 2  # face kernel + element kernel
     prob.close()
+
+
+def test_golden_vectors(FR):
+    """The committed fixtures of tests/golden/curv_golden.npz (make_curv_golden.py) through the C ABI."""
+    import os
+
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "curv_golden.npz"))
+    deg = 2
+    ps, _, (n1, n2) = parallelogram(FR, 6, 4, deg)
+    u = np.asfortranarray(g["para_u"])
+    for fy in "kl":
+        prob = FR.Euler2DCurvProblem(u, (0.0, 1.0), ps, GAMMA, n1, n2, corr="sp", fy_index=fy)
+        du = np.zeros_like(u, order="F")
+        prob.f(du, u, None, 0.0)
+        assert rel(du, g[f"para_du_{fy}"]) <= RTOL_RHS
+        if fy == "l":
+            itg = FR.init(prob, FR.Euler(), dt=0.001)
+            itg.set_hooks(ghost="periodic")
+            FR.step_(itg, 5)
+            assert rel(itg.u, g["para_u5"]) <= 1e-12
+        prob.close()
+    ps, _, _ = cylinder(FR, 5, 6, deg)
+    u = np.asfortranarray(g["cyl_u"])
+    for fy in "kl":
+        prob = FR.Euler2DCurvProblem(u, (0.0, 1.0), ps, GAMMA, corr="fp", fy_index=fy, wall_xlo=True)
+        du = np.zeros_like(u, order="F")
+        prob.f(du, u, None, 0.0)
+        assert rel(du, g[f"cyl_du_{fy}"]) <= RTOL_RHS
+        prob.ghost_fill("cylinder")
+        assert np.array_equal(prob.download()[1:], g["cyl_ghost"][1:])
+        prob.close()

@@ -246,3 +246,35 @@ def test_device_routines_on_the_cpu(host_stage, deg):
                                                                wall_xlo=True)
     got = host_stage(u, ps, n1, n2, fpc, 2, stage=(0.75, 0.25, 0.25e-3, 1, 0), ua=ua)
     assert np.abs(got[1:-1, 1:-1] - ref[1:-1, 1:-1]).max() < 1e-14
+
+
+# ------------------------------------------------------------------------------- committed fixtures
+def _golden():
+    import os
+
+    return np.load(os.path.join(os.path.dirname(__file__), "golden", "curv_golden.npz"))
+
+
+def test_oracle_reproduces_the_golden_vectors(host_stage):
+    """tests/golden/curv_golden.npz (make_curv_golden.py): the oracle and the device routines on the CPU."""
+    g, deg = _golden(), 2
+    nx, ny = 6, 4
+    ps = c.CurvSpace2D(c.parallelogram_vertices(nx, ny), deg)
+    n1, n2 = c.parallelogram_normals(nx, ny)
+    u = np.asfortranarray(g["para_u"])
+    for fy, flags in (("k", 0), ("l", 1)):
+        assert rel(c.rhs_euler2d_curv(u, ps, n1, n2, GAMMA, corr="sp", fy_index=fy), g[f"para_du_{fy}"]) < 1e-14
+        assert rel(host_stage(u, ps, n1, n2, None, flags), g[f"para_du_{fy}"]) < 1e-13
+    nr, nth = 5, 6
+    vv, dth = c.cspace2d_vertices(1.0, 6.0, nr, 0.0, np.pi, nth, 0, 1)
+    ps = c.CurvSpace2D(c.embed_cylinder(vv), deg)
+    n1, n2 = c.cylinder_normals(nr, nth, dth[0])
+    n1, n2 = n1[:nr], n2[: nr - 1]
+    fpc = c.corr_factors_fp(ps.Ji, n1, n2)
+    assert np.abs(fpc - g["cyl_fpc"]).max() < 1e-14
+    u = np.asfortranarray(g["cyl_u"])
+    for fy, flags in (("k", 2), ("l", 3)):
+        ref = g[f"cyl_du_{fy}"]
+        assert rel(c.rhs_euler2d_curv(u, ps, n1, n2, GAMMA, corr="fp", fpc=fpc, fy_index=fy, wall_xlo=True), ref) < 1e-14
+        assert rel(host_stage(u, ps, n1, n2, fpc, flags), ref) < 1e-13
+    assert np.array_equal(c.ghost_fill_cylinder(u.copy(), deg + 1), g["cyl_ghost"])
