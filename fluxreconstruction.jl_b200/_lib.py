@@ -47,6 +47,7 @@ SIGNATURES = {
                                             c_dp, C.c_int32, C.c_double, C.POINTER(C.c_void_p)]),
     "frb_bgk1d_create": (C.c_int32, [C.c_void_p, C.c_int32, C.c_int32, C.POINTER(Operators), c_dp, c_dp, c_dp,
                                      C.c_double, C.POINTER(C.c_void_p)]),
+    "frb_bgk1d_set_model": (C.c_int32, [C.c_void_p, C.c_int32, C.c_double]),
     "frb_ns2d_create": (C.c_int32, [C.c_void_p, C.c_int32, C.c_int32, C.POINTER(Operators)] + [C.c_double] * 9
                         + [C.POINTER(C.c_void_p)]),
     "frb_tri_euler_create": (C.c_int32, [C.c_void_p, C.c_int32, C.c_int32, C.POINTER(C.c_int32), c_dp, c_dp,

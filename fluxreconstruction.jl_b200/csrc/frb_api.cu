@@ -283,6 +283,16 @@ extern "C" int32_t frb_bgk1d_create(frb_ctx_t ctx, int32_t ncell, int32_t nu,
   return FRB_OK;
 }
 
+extern "C" int32_t frb_bgk1d_set_model(frb_prob_t p, int32_t model, double a) {
+  FRB_REQUIRE(p, FRB_ERR_ARG, "frb_bgk1d_set_model: prob is NULL");
+  FRB_REQUIRE(p->kind == K_BGK1D, FRB_ERR_STATE, "frb_bgk1d_set_model: bgk1d problems only");
+  FRB_REQUIRE(model == FRB_BGK_WAVE || model == FRB_BGK_KINETIC_ADVECTION, FRB_ERR_ARG,
+              "frb_bgk1d_set_model: unknown model");
+  p->bgk_model = model;
+  p->a = a;
+  return FRB_OK;
+}
+
 extern "C" int32_t frb_ns2d_create(frb_ctx_t ctx, int32_t nx, int32_t ny, const frb_operators *ops,
                                    double Jx, double Jy, double inK, double gamma, double mu_ref,
                                    double omega, double dt, double lid_u, double lambda_wall,

@@ -10,6 +10,8 @@
 //                       serial chain, the loads are not); writes rho*sqrt(lambda/pi), U, lambda.
 //   bgk1d_kernel        thread = (cell, velocity): own block + the upwind neighbour's block, 1 / J
 //                       precomputed per cell, one exp per point.
+// model FRB_BGK_KINETIC_ADVECTION is the mol! of example/advection_kinetic.jl:73-128: the same residual with the
+// Maxwellian of prim = [rho, a, 1] (:80-88) -- only the epilogue of the moments kernel differs.
 // Both are L2 / HBM streams of the 50 MB state; nothing here is GEMM-shaped.
 #include "frb_internal.cuh"
 
@@ -37,7 +39,7 @@ __device__ __forceinline__ double stage_out(const FrbStage &st, const double *ua
 constexpr int kMomGroups = 8;
 __global__ void __launch_bounds__(32 * kMomGroups)
 bgk_moments_kernel(const double *__restrict__ u, double *__restrict__ prim, int ncell, int nu, int nsp,
-                   const double *__restrict__ velo, const double *__restrict__ wts) {
+                   const double *__restrict__ velo, const double *__restrict__ wts, int model, double a) {
   __shared__ double part[kMomGroups][3][32];
   const int lane = threadIdx.x & 31, grp = threadIdx.x >> 5;
   const int i = blockIdx.x * 32 + lane;
@@ -77,9 +79,16 @@ bgk_moments_kernel(const double *__restrict__ u, double *__restrict__ prim, int 
     w1 += part[g][1][lane];
     w2 += part[g][2][lane];
   }
+  const size_t o = i + (size_t)ncell * k;
+  if (model == FRB_BGK_KINETIC_ADVECTION) {
+    // example/advection_kinetic.jl:80-88: rho = sum(u .* weights), prim = [rho, a, 1.0]
+    prim[o] = w0 * sqrt(1.0 / 3.14159265358979323846);
+    prim[o + (size_t)ncell * nsp] = a;
+    prim[o + 2 * (size_t)ncell * nsp] = 1.0;
+    return;
+  }
   w2 *= 0.5;
   const double lam = 0.5 * w0 / (3.0 - 1.0) / (w2 - 0.5 * w1 * w1 / w0);
-  const size_t o = i + (size_t)ncell * k;
   prim[o] = w0 * sqrt(lam / 3.14159265358979323846);  // maxwellian prefactor rho*sqrt(lambda/pi)
   prim[o + (size_t)ncell * nsp] = w1 / w0;
   prim[o + 2 * (size_t)ncell * nsp] = lam;
@@ -127,7 +136,8 @@ bgk1d_kernel(const double *__restrict__ u, const double *__restrict__ ua, double
 
 int frb_launch_bgk1d(frb_prob_t p, const double *u, const double *ua, double *out, FrbStage st) {
   dim3 blk(128), g1((p->ncell + 31) / 32, p->nsp), g2((p->ncell + 127) / 128, p->nu);
-  bgk_moments_kernel<<<g1, 32 * kMomGroups, 0, p->ctx->stream>>>(u, p->prim, p->ncell, p->nu, p->nsp, p->velo, p->weights);
+  bgk_moments_kernel<<<g1, 32 * kMomGroups, 0, p->ctx->stream>>>(u, p->prim, p->ncell, p->nu, p->nsp, p->velo, p->weights,
+                                                                  p->bgk_model, p->a);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return frb_cuda_fail(e, "bgk_moments_kernel", __FILE__, __LINE__);
   const double it = 1.0 / p->tau;

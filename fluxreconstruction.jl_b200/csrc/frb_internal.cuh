@@ -67,6 +67,7 @@ struct frb_prob_s {
   // physics
   double a = 0, gamma = 0, Jx = 0, Jy = 0, tau = 0;
   int bc = 0, variant = 0;
+  int bgk_model = 0;  // FRB_BGK_* (frb_bgk1d_set_model); the advection speed of the kinetic model is `a`
   int flux = FRB_FLUX_HLL;  // common flux of the Euler problems (frb_set_flux)
   double gks_K = 0, gks_mu = 0, gks_omega = 0, gks_dt = 0, lid_u = 0, lambda_wall = 1.0;
   // device buffers

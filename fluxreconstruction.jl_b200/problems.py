@@ -360,9 +360,11 @@ class Euler2DCurvProblem(_Problem):
 
 
 class BGKProblem(_Problem):
-    """ODEProblem(mol!, f0, tspan, p) of example/bgk_wave.jl:69-132.  f0[ncell, nu, nsp]."""
+    """ODEProblem(mol!, f0, tspan, p) of example/bgk_wave.jl:69-132.  f0[ncell, nu, nsp].
+    ``model="advection"`` is the mol! of example/advection_kinetic.jl:73-132 instead: the same residual relaxing
+    towards the Maxwellian of prim = [rho, a, 1] (the script's tau is 2e-3)."""
 
-    def __init__(self, f0, tspan, ps, velo, weights, tau=1e-2, ctx=None):
+    def __init__(self, f0, tspan, ps, velo, weights, tau=1e-2, ctx=None, model="bgk", a=1.0):
         super().__init__(f0, tspan, ctx)
         ncell, nu, nsp = self.u0.shape
         if nsp != ps.deg + 1 or nu != len(velo):
@@ -374,6 +376,8 @@ class BGKProblem(_Problem):
         self._keep += [dx, v, w]
         check(lib().frb_bgk1d_create(self.ctx.h, ncell, nu, C.byref(ops), _lib.dptr(dx), _lib.dptr(v), _lib.dptr(w),
                                      float(tau), C.byref(self.h)))
+        if model != "bgk":
+            check(lib().frb_bgk1d_set_model(self.h, {"bgk": 0, "advection": 1}[model], float(a)))
         self.upload(self.u0)
 
 

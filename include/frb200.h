@@ -123,6 +123,12 @@ int32_t frb_euler2d_curv_create(frb_ctx_t ctx, int32_t nx, int32_t ny, const frb
 int32_t frb_bgk1d_create(frb_ctx_t ctx, int32_t ncell, int32_t nu, const frb_operators *ops,
                          const double *dx, const double *velo, const double *weights,
                          double tau, frb_prob_t *out);
+/* relaxation model of a bgk1d problem.  FRB_BGK_WAVE: Maxwellian from the three moments, conserve_prim(w, 3.0)
+ * (bgk_wave.jl:77-81).  FRB_BGK_KINETIC_ADVECTION: the mol! of example/advection_kinetic.jl:73-128 -- the same
+ * residual with rho = sum(u .* weights), prim = [rho, a, 1.0] (:80-88); tau is the one given at creation
+ * (the script: 2.0 * 0.001, :89). */
+enum { FRB_BGK_WAVE = 0, FRB_BGK_KINETIC_ADVECTION = 1 };
+int32_t frb_bgk1d_set_model(frb_prob_t prob, int32_t model, double a);
 /* dudt! + boundary! of example/ns_cavity.jl:147-344 (gas-kinetic flux, :49-145).
  * State u[4, nsp, nsp, ny+2, nx+2] (variable fastest).  ops->dll/dlr required.
  * gas = (K, gamma, mu_ref, omega); dt enters the time-averaged interface flux; lid_u is

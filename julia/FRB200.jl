@@ -122,6 +122,9 @@ function TriEulerProblem(u0::Array{Float64,3}, ps, γ)
         ctx().h, ncell, ps.deg, ct, J, nrm, fpn, ps.lf, ps.∂l, ps.ϕ, γ, r))
     p = finalizer(destroy!, Problem(r[], size(u0), Any[ct, J, nrm, fpn])); upload!(p, u0); p
 end
+# example/advection_kinetic.jl:73-128: the same mol! relaxing towards the Maxwellian of prim = [ρ, a, 1.0]
+kinetic_advection!(p::Problem, a = 1.0) = check(ccall((:frb_bgk1d_set_model, lib), Int32,
+    (Ptr{Cvoid}, Int32, Float64), p.h, 1, a))
 function BGKProblem(f0::Array{Float64,3}, ps, velo, weights, τ = 1e-2)
     ops, keep = operators(ps)
     dx = Vector{Float64}(ps.dx[1:size(f0, 1)]); v = Vector{Float64}(velo); w = Vector{Float64}(weights)

@@ -649,15 +649,19 @@ def ghost_fill_euler2d(u, mode="wave_x"):
     return u
 
 
-def rhs_bgk1d(u, dx, velo, weights, ll, lr, lpdm, dgl, dgr, tau=1e-2):
+def rhs_bgk1d(u, dx, velo, weights, ll, lr, lpdm, dgl, dgr, tau=1e-2, model="bgk", a=1.0):
     """example/bgk_wave.jl:69-129 with the periodic e2f/f2e tables of :42-67.
-    u[ncell, nu, nsp]."""
+    u[ncell, nu, nsp].  model="advection": mol! of example/advection_kinetic.jl:73-128 -- identical but for the
+    Maxwellian, built from rho = sum(u .* weights) and prim = [rho, a, 1.0] (:80-88; tau = 2e-3 there)."""
     ncell, nu, nsp = u.shape
     delta = heaviside(velo)
     M = np.empty_like(u)
     for k in range(nsp):
         w = moments_conserve_1v(u[:, :, k], velo, weights)
-        prim = conserve_prim(w, 3.0)
+        if model == "advection":
+            prim = np.stack([w[..., 0], np.full_like(w[..., 0], a), np.ones_like(w[..., 0])], axis=-1)
+        else:
+            prim = conserve_prim(w, 3.0)
         M[:, :, k] = maxwellian(velo[None, :], prim)
     J = 0.5 * np.asarray(dx)
     f = velo[None, :, None] * u / J[:, None, None]
@@ -916,6 +920,18 @@ def ic_bgk1d(ps: FRPSpace1D, velo):
     rho = 1.0 + 0.1 * np.sin(2.0 * np.pi * x)
     T = 2 * 0.5 / rho
     prim = np.stack([rho, np.ones_like(rho), 1.0 / T], axis=-1)  # [ncell, nsp, 3]
+    f0 = np.empty((ps.nx, len(velo), ps.deg + 1), order="F")
+    for k in range(ps.deg + 1):
+        f0[:, :, k] = maxwellian(velo[None, :], prim[:, k, :])
+    return f0
+
+
+def ic_kinetic_advection1d(ps: FRPSpace1D, velo, a=1.0):
+    """advection_kinetic.jl:37-45: u = 1 - sin(pi x), f = maxwellian(v, [u, a, 1]) ([KB-recall]: the scalar
+    conserve_prim(u, a) the script calls is the triple the mol! spells out at :84)."""
+    x = ps.xpg[ps.ng : ps.ng + ps.nx]
+    rho = 1.0 - np.sin(np.pi * x)
+    prim = np.stack([rho, np.full_like(rho, a), np.ones_like(rho)], axis=-1)
     f0 = np.empty((ps.nx, len(velo), ps.deg + 1), order="F")
     for k in range(ps.deg + 1):
         f0[:, :, k] = maxwellian(velo[None, :], prim[:, k, :])

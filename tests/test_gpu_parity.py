@@ -310,6 +310,25 @@ def test_bgk_steps(FR, oracle, coracle):
     prob.close()
 
 
+@pytest.mark.parametrize("deg", [2, 3])
+def test_kinetic_advection(FR, oracle, deg):
+    """mol! of example/advection_kinetic.jl:73-128 (nx = 100, nu = 28, tau = 2e-3): RHS and 200 Midpoint steps."""
+    ps = FR.FRPSpace1D(-1.0, 1.0, 100, deg)
+    velo, wts = oracle.vspace1d(-5.0, 5.0, 28)
+    f0 = noisy(oracle.ic_kinetic_advection1d(ps, velo, 1.0), 0.01, 9)
+    prob = FR.BGKProblem(f0, (0.0, 0.5), ps, velo, wts, 2e-3, model="advection", a=1.0)
+    du = np.zeros_like(f0, order="F")
+    prob.f(du, f0, None, 0.0)
+    args = (ps.dx, velo, wts, ps.ll, ps.lr, ps.dl, ps.dhl, ps.dhr, 2e-3)
+    rhs = lambda w: oracle.rhs_bgk1d(w, *args, model="advection", a=1.0)  # noqa: E731
+    assert rel(du, rhs(f0)) <= RTOL_RHS
+    itg = FR.init(prob, FR.Midpoint(), dt=0.0005)  # the script's dt (:138)
+    FR.step_(itg, 200)
+    ref = oracle.integrate(f0, 0.0005, 200, rhs, "midpoint")
+    assert rel(itg.u, ref) <= RTOL_1000
+    prob.close()
+
+
 def test_no_cpu_fallback_symbols(FR):
     """The product library must not link or reference the oracle."""
     import subprocess

@@ -144,3 +144,30 @@ def test_tableau_stepping_converges_at_design_order():
             err.append(np.abs(u - exact).max())
         rates = np.log2(np.array(err[:-1]) / np.array(err[1:]))
         assert (rates > order - 0.3).all(), (scheme, err, rates)
+
+
+# ---------------------------------------------------------------- example/advection_kinetic.jl
+def test_kinetic_advection_model(oracle):
+    """mol! of example/advection_kinetic.jl:73-128 = the BGK residual with the Maxwellian of [rho, a, 1]:
+    the relaxation term vanishes on that Maxwellian's own moments, mass is conserved, and the transport part
+    equals the bgk_wave residual's (the two differ by the relaxation term only)."""
+    ps = oracle.FRPSpace1D(-1.0, 1.0, 40, 2)
+    velo, wts = oracle.vspace1d(-5.0, 5.0, 28)  # advection_kinetic.jl:13-16,24
+    f0 = oracle.ic_kinetic_advection1d(ps, velo, 1.0)
+    args = (ps.dx, velo, wts, ps.ll, ps.lr, ps.dl, ps.dhl, ps.dhr)
+    du = oracle.rhs_bgk1d(f0, *args, 2e-3, model="advection", a=1.0)
+    du_slow = oracle.rhs_bgk1d(f0, *args, 2e3, model="advection", a=1.0)
+    # the midpoint rule on 28 nodes reproduces rho to ~1e-10, so the stiff term is small against 1/tau
+    assert np.abs(du - du_slow).max() < 1e-6 / 2e-3
+    # mass of the transport part (periodic, conservative interface flux); the relaxation term conserves mass only
+    # up to the quadrature error of the discrete Maxwellian (28 midpoint nodes), which 1/tau = 500 amplifies
+    mass = np.einsum("ijk,j,k->", du_slow, wts, ps.wp) * ps.J[0]
+    assert abs(mass) < 1e-9
+    assert abs(np.einsum("ijk,j,k->", du, wts, ps.wp) * ps.J[0]) < 1e-4
+    # against the bgk_wave model on the same state only the Maxwellian changes
+    d_bgk = oracle.rhs_bgk1d(f0, *args, 2e-3)
+    k = 1
+    w = oracle.moments_conserve_1v(f0[:, :, k], velo, wts)
+    M_adv = oracle.maxwellian(velo[None, :], np.stack([w[:, 0], np.ones(40), np.ones(40)], axis=-1))
+    M_bgk = oracle.maxwellian(velo[None, :], oracle.conserve_prim(w, 3.0))
+    assert np.allclose((du - d_bgk)[:, :, k], (M_adv - M_bgk) / 2e-3, rtol=1e-9, atol=1e-9)
