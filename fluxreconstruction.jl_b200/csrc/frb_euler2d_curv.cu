@@ -6,6 +6,8 @@
 // Algorithmic bytes per DOF-update: the state terms of the rectangular path (16 B / 24 B) plus the
 // metric, which no longer is two scalars: 4 doubles of iJ per solution point shared by the 4 variables
 // = 8 B per DOF (+ normals and flux-point factors, O(1/nsp) of that).
+#include <stdlib.h>
+
 #include "frb_euler2d_curv_elem.cuh"
 
 namespace {
@@ -25,16 +27,22 @@ euler2d_curv_face_kernel(const double *__restrict__ u, double *__restrict__ fx, 
   }
 }
 
-// thread = (element i, variable m = threadIdx.y); one block row per j
-template <int NSP>
-__global__ void __launch_bounds__(128)
+// thread = (element i = lane, point row l = threadIdx.y); one block = 32 consecutive elements of row j.
+// The tile holds f2 = (iJ [F; G])[2] of the block's elements: [l][k][m][lane], conflict-free in both passes.
+template <int NSP, int MINB>
+__global__ void __launch_bounds__(32 * NSP, MINB)
 euler2d_curv_elem_kernel(const double *__restrict__ u, const double *__restrict__ ua,
                          const double *__restrict__ fx, const double *__restrict__ fy, double *__restrict__ out,
                          CurvGeom g, double gamma, FrbOps ops, FrbStage st) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x + 1;
+  __shared__ double tile[NSP * NSP * 4 * 32];
+  const int lane = threadIdx.x, l = threadIdx.y;
+  const int i = blockIdx.x * 32 + lane + 1;
   const int j = blockIdx.y + 1;
-  if (i > g.nx) return;
-  frbcurv::element_var<NSP>(i, j, threadIdx.y, u, ua, fx, fy, out, g, gamma, ops, st);
+  const bool active = i <= g.nx;
+  frbcurv::RowCarry<NSP> c;
+  if (active) frbcurv::row_xpass<NSP>(i, j, l, u, fx, g, gamma, ops, tile + lane, 32, c);
+  __syncthreads();
+  if (active) frbcurv::row_ypass<NSP>(i, j, l, u, ua, fy, out, g, ops, st, tile + lane, 32, c);
 }
 
 // Per-step boundary fill of dev/cylinder2.jl:176-187 on the ring-embedded array (interior nx = nr - 1,
@@ -98,12 +106,16 @@ int frb_launch_euler2d_curv(frb_prob_t p, const double *u, const double *ua, dou
   if (st.nested) { st.cdt *= st.cb; st.nested = 0; }
   cudaStream_t s = p->ctx->stream;
   dim3 fb(128), fg((p->nx + 1 + 127) / 128, p->ny + 1, 2 * p->nsp);
-  dim3 eb(32, 4), eg((p->nx + 31) / 32, p->ny);
+  dim3 eb(32, p->nsp), eg((p->nx + 31) / 32, p->ny);
+  static const bool minb4 = getenv("FRB_CURV_MINB4") != nullptr;  // occupancy experiment
   switch (p->nsp) {
 #define FRB_CURV_CASE(N)                                                                                  \
   case N:                                                                                                 \
     euler2d_curv_face_kernel<N><<<fg, fb, 0, s>>>(u, fx, fy, g, p->gamma, p->ops);                         \
-    euler2d_curv_elem_kernel<N><<<eg, eb, 0, s>>>(u, ua, fx, fy, out, g, p->gamma, p->ops, st);            \
+    if (minb4)                                                                                            \
+      euler2d_curv_elem_kernel<N, 4><<<eg, eb, 0, s>>>(u, ua, fx, fy, out, g, p->gamma, p->ops, st);       \
+    else                                                                                                  \
+      euler2d_curv_elem_kernel<N, 3><<<eg, eb, 0, s>>>(u, ua, fx, fy, out, g, p->gamma, p->ops, st);       \
     break;
     FRB_CURV_CASE(2)
     FRB_CURV_CASE(3)

@@ -12,8 +12,9 @@
 // element kernel that fuses derivative, correction and the RK update):
 //   face_x / face_y  thread = one interface flux point: both traces from the two neighbouring element
 //                    blocks, HLL in the face frame, all 4 components -> fx[nx+1, ny, nsp, 4], fy[nx, ny+1, nsp, 4]
-//   element_var      thread = (element, variable m): point fluxes iJ [F; G] of its variable, lpdm derivative,
-//                    correction, stage update; ~60 live doubles at deg 3, nothing spills
+//   row_xpass /      thread = (element, point row l), a block = 32 elements x NSP rows: point fluxes iJ [F; G] of
+//   row_ypass        the row, r-derivative + x corrections in registers, f2 through a shared-memory tile, then the
+//                    s-derivative + y corrections + stage update of the same row
 //
 // The routines are __host__ __device__ so that tests/harness/curv_host.cu can run the very same code on the
 // CPU against the NumPy oracle (the build box has no GPU); the library only ever calls it from a kernel.
@@ -136,95 +137,109 @@ FRB_HD void face_y(int i, int j, int p, const double *__restrict__ u, double *__
   fy[f + sf * (p + NSP * 3)] = h.d;
 }
 
-// component m of F and G at a point
-FRB_HD void flux_component(int m, double w0, double w1, double w2, double w3, double gm1, double &F, double &G) {
-  const double r = 1.0 / w0, vx = w1 * r, vy = w2 * r;
-  const double p = gm1 * (w3 - 0.5 * fma(w1, vx, w2 * vy));
-  if (m == 0) { F = w1; G = w2; }
-  else if (m == 1) { F = fma(w1, vx, p); G = w2 * vx; }
-  else if (m == 2) { F = w1 * vy; G = fma(w2, vy, p); }
-  else { const double h = w3 + p; F = h * vx; G = h * vy; }
-}
-
-// Variable m of interior element (i, j), 1-based like the reference: parallelogram.jl:88-96,138-163.
+// What a row owner carries from its x pass to its y pass (registers on the device).
 template <int NSP>
-FRB_HD void element_var(int i, int j, int m, const double *__restrict__ u, const double *__restrict__ ua,
-                        const double *__restrict__ fx, const double *__restrict__ fy, double *__restrict__ out,
-                        const CurvGeom &g, double gamma, const FrbOps &ops, const FrbStage &st) {
+struct RowCarry {
+  double d[NSP][4];          // rhs1 + x-face corrections at (k, l = row), per variable
+  double cyL[NSP], cyR[NSP]; // y correction factors at (k, l)
+};
+
+// Element (i, j), point row l -- x pass: point fluxes iJ [F; G] of the row's NSP points (parallelogram.jl:88-96),
+// the r-derivative and the x-face corrections of f1 in registers (:138-142,150-157), f2 of the row into the
+// element's tile for the y pass: tile[((l NSP + k) 4 + m) ts] (ts = 32 lanes on the device, 1 on the host).
+template <int NSP>
+FRB_HD void row_xpass(int i, int j, int l, const double *__restrict__ u, const double *__restrict__ fx,
+                      const CurvGeom &g, double gamma, const FrbOps &ops, double *__restrict__ tile, int ts,
+                      RowCarry<NSP> &c) {
   const int nx = g.nx, ny = g.ny;
   const size_t NXG = nx + 2, NE = NXG * (size_t)(ny + 2);
   const size_t e = i + NXG * j;
   const double gm1 = gamma - 1.0;
-
-  double f1[NSP][NSP], f2[NSP][NSP];  // [l][k]: (iJ [F_m; G_m])[1], [2]
-#pragma unroll
-  for (int l = 0; l < NSP; ++l)
-#pragma unroll
-    for (int k = 0; k < NSP; ++k) {
-      const double w0 = u[e + NE * plane<NSP>(k, l, 0)], w1 = u[e + NE * plane<NSP>(k, l, 1)];
-      const double w2 = u[e + NE * plane<NSP>(k, l, 2)], w3 = u[e + NE * plane<NSP>(k, l, 3)];
-      const double a11 = g.iJ[e + NE * plane<NSP>(k, l, 0)], a21 = g.iJ[e + NE * plane<NSP>(k, l, 1)];
-      const double a12 = g.iJ[e + NE * plane<NSP>(k, l, 2)], a22 = g.iJ[e + NE * plane<NSP>(k, l, 3)];
-      double F, G;
-      flux_component(m, w0, w1, w2, w3, gm1, F, G);
-      f1[l][k] = fma(a12, G, a11 * F);
-      f2[l][k] = fma(a22, G, a21 * F);
-    }
-
-  // face normals and the 4 x NSP common-flux values of this variable
   const size_t i1 = (size_t)(i - 1) + (size_t)(nx + 1) * (j - 1), s1 = (size_t)(nx + 1) * ny;
-  const double nxl_c = g.n1[i1], nxl_s = g.n1[i1 + s1], nxr_c = g.n1[i1 + 1], nxr_s = g.n1[i1 + 1 + s1];
   const size_t i2 = (size_t)(i - 1) + (size_t)nx * (j - 1), s2 = (size_t)nx * (ny + 1);
-  const double nyb_c = g.n2[i2], nyb_s = g.n2[i2 + s2], nyt_c = g.n2[i2 + nx], nyt_s = g.n2[i2 + nx + s2];
   const size_t ifp = (size_t)(i - 1) + (size_t)nx * (j - 1), sfp = (size_t)nx * ny;
-  double FxL[NSP], FxR[NSP], FyB[NSP], FyT[NSP], tx4[NSP], tx2[NSP], ty1[NSP], ty3[NSP];
+  const double nxl_c = g.n1[i1], nxl_s = g.n1[i1 + s1], nxr_c = g.n1[i1 + 1], nxr_s = g.n1[i1 + 1 + s1];
+  const double nyb_c = g.n2[i2], nyb_s = g.n2[i2 + s2], nyt_c = g.n2[i2 + nx], nyt_s = g.n2[i2 + nx + s2];
+
+  double f1[NSP][4], cxL[NSP], cxR[NSP];
 #pragma unroll
-  for (int p = 0; p < NSP; ++p) {
-    FxL[p] = fx[i1 + s1 * (p + NSP * m)];
-    FxR[p] = fx[i1 + 1 + s1 * (p + NSP * m)];
-    FyB[p] = fy[i2 + s2 * (p + NSP * m)];
-    FyT[p] = fy[i2 + nx + s2 * (p + NSP * m)];
-    double t4 = 0, t2 = 0, t1 = 0, t3 = 0;
+  for (int k = 0; k < NSP; ++k) {
+    const double w0 = u[e + NE * plane<NSP>(k, l, 0)], w1 = u[e + NE * plane<NSP>(k, l, 1)];
+    const double w2 = u[e + NE * plane<NSP>(k, l, 2)], w3 = u[e + NE * plane<NSP>(k, l, 3)];
+    const double a11 = g.iJ[e + NE * plane<NSP>(k, l, 0)], a21 = g.iJ[e + NE * plane<NSP>(k, l, 1)];
+    const double a12 = g.iJ[e + NE * plane<NSP>(k, l, 2)], a22 = g.iJ[e + NE * plane<NSP>(k, l, 3)];
+    const double r = 1.0 / w0, vx = w1 * r, vy = w2 * r;
+    const double p = gm1 * (w3 - 0.5 * fma(w1, vx, w2 * vy));
+    const double h = w3 + p;
+    const double F[4] = {w1, fma(w1, vx, p), w1 * vy, h * vx};
+    const double G[4] = {w2, w2 * vx, fma(w2, vy, p), h * vy};
+#pragma unroll
+    for (int m = 0; m < 4; ++m) {
+      f1[k][m] = fma(a12, G[m], a11 * F[m]);
+      tile[(size_t)(((l * NSP + k) * 4) + m) * ts] = fma(a22, G[m], a21 * F[m]);
+    }
+    if (g.fpc) {  // cylinder2.jl:155-158
+      cxL[k] = g.fpc[ifp + sfp * (l + NSP * 0)];
+      cxR[k] = g.fpc[ifp + sfp * (l + NSP * 1)];
+      c.cyL[k] = g.fpc[ifp + sfp * (k + NSP * 2)];
+      c.cyR[k] = g.fpc[ifp + sfp * (k + NSP * 3)];
+    } else {  // parallelogram.jl:145-148
+      cxL[k] = fma(a12, nxl_s, a11 * nxl_c);
+      cxR[k] = fma(a12, nxr_s, a11 * nxr_c);
+      c.cyL[k] = fma(a22, nyb_s, a21 * nyb_c);
+      c.cyR[k] = fma(a22, nyt_s, a21 * nyt_c);
+    }
+  }
+#pragma unroll
+  for (int m = 0; m < 4; ++m) {
+    double t4 = 0, t2 = 0;  // f_face[i,j,4,l,m,1], f_face[i,j,2,l,m,1]
 #pragma unroll
     for (int q = 0; q < NSP; ++q) {
-      t4 = fma(f1[p][q], ops.ll[q], t4);  // f_face[i,j,4,p,m,1]
-      t2 = fma(f1[p][q], ops.lr[q], t2);  // f_face[i,j,2,p,m,1]
-      t1 = fma(f2[q][p], ops.ll[q], t1);  // f_face[i,j,1,p,m,2]
-      t3 = fma(f2[q][p], ops.lr[q], t3);  // f_face[i,j,3,p,m,2]
+      t4 = fma(f1[q][m], ops.ll[q], t4);
+      t2 = fma(f1[q][m], ops.lr[q], t2);
     }
-    tx4[p] = t4; tx2[p] = t2; ty1[p] = t1; ty3[p] = t3;
-  }
-
-#pragma unroll
-  for (int l = 0; l < NSP; ++l)
+    const double FxL = fx[i1 + s1 * (l + NSP * m)], FxR = fx[i1 + 1 + s1 * (l + NSP * m)];
 #pragma unroll
     for (int k = 0; k < NSP; ++k) {
-      double a = f1[l][0] * ops.lpdm[k * FRB_NSPMAX];
-      double b = f2[0][k] * ops.lpdm[l * FRB_NSPMAX];
+      double a = f1[0][m] * ops.lpdm[k * FRB_NSPMAX];
 #pragma unroll
-      for (int q = 1; q < NSP; ++q) {
-        a = fma(f1[l][q], ops.lpdm[k * FRB_NSPMAX + q], a);
-        b = fma(f2[q][k], ops.lpdm[l * FRB_NSPMAX + q], b);
+      for (int q = 1; q < NSP; ++q) a = fma(f1[q][m], ops.lpdm[k * FRB_NSPMAX + q], a);
+      a += (cxL[k] * FxL - t4) * ops.dgl[k];
+      a += (cxR[k] * FxR - t2) * ops.dgr[k];
+      c.d[k][m] = a;
+    }
+  }
+}
+
+// y pass of the same row owner, after every row of the element has written its f2 into the tile:
+// s-derivative (:143-149), y-face corrections (:158-163; the common flux indexed by k, or by l in the scripts'
+// literal form) and the stage update.
+template <int NSP>
+FRB_HD void row_ypass(int i, int j, int l, const double *__restrict__ u, const double *__restrict__ ua,
+                      const double *__restrict__ fy, double *__restrict__ out, const CurvGeom &g,
+                      const FrbOps &ops, const FrbStage &st, const double *__restrict__ tile, int ts,
+                      const RowCarry<NSP> &c) {
+  const int nx = g.nx, ny = g.ny;
+  const size_t NXG = nx + 2, NE = NXG * (size_t)(ny + 2);
+  const size_t e = i + NXG * j;
+  const size_t i2 = (size_t)(i - 1) + (size_t)nx * (j - 1), s2 = (size_t)nx * (ny + 1);
+#pragma unroll
+  for (int k = 0; k < NSP; ++k) {
+    const int yi = g.fy_row ? l : k;
+#pragma unroll
+    for (int m = 0; m < 4; ++m) {
+      double b = 0, t1 = 0, t3 = 0;  // rhs2, f_face[i,j,1,k,m,2], f_face[i,j,3,k,m,2]
+#pragma unroll
+      for (int q = 0; q < NSP; ++q) {
+        const double f2 = tile[(size_t)(((q * NSP + k) * 4) + m) * ts];
+        b = fma(f2, ops.lpdm[l * FRB_NSPMAX + q], b);
+        t1 = fma(f2, ops.ll[q], t1);
+        t3 = fma(f2, ops.lr[q], t3);
       }
-      double cxL, cxR, cyL, cyR;
-      if (g.fpc) {  // cylinder2.jl:155-158
-        cxL = g.fpc[ifp + sfp * (l + NSP * 0)];
-        cxR = g.fpc[ifp + sfp * (l + NSP * 1)];
-        cyL = g.fpc[ifp + sfp * (k + NSP * 2)];
-        cyR = g.fpc[ifp + sfp * (k + NSP * 3)];
-      } else {  // parallelogram.jl:145-148
-        const double a11 = g.iJ[e + NE * plane<NSP>(k, l, 0)], a21 = g.iJ[e + NE * plane<NSP>(k, l, 1)];
-        const double a12 = g.iJ[e + NE * plane<NSP>(k, l, 2)], a22 = g.iJ[e + NE * plane<NSP>(k, l, 3)];
-        cxL = fma(a12, nxl_s, a11 * nxl_c);
-        cxR = fma(a12, nxr_s, a11 * nxr_c);
-        cyL = fma(a22, nyb_s, a21 * nyb_c);
-        cyR = fma(a22, nyt_s, a21 * nyt_c);
-      }
-      double d = a + b;
-      d += (cxL * FxL[l] - tx4[l]) * ops.dgl[k];
-      d += (cxR * FxR[l] - tx2[l]) * ops.dgr[k];
-      d += (cyL * (g.fy_row ? FyB[l] : FyB[k]) - ty1[k]) * ops.dgl[l];
-      d += (cyR * (g.fy_row ? FyT[l] : FyT[k]) - ty3[k]) * ops.dgr[l];
+      const double FyB = fy[i2 + s2 * (yi + NSP * m)], FyT = fy[i2 + nx + s2 * (yi + NSP * m)];
+      double d = c.d[k][m] + b;
+      d += (c.cyL[k] * FyB - t1) * ops.dgl[l];
+      d += (c.cyR[k] * FyT - t3) * ops.dgr[l];
       d = -d;
       const size_t idx = e + NE * plane<NSP>(k, l, m);
       double r;
@@ -235,6 +250,7 @@ FRB_HD void element_var(int i, int j, int m, const double *__restrict__ u, const
       }
       out[idx] = r;
     }
+  }
 }
 
 }  // namespace frbcurv

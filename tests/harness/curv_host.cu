@@ -15,9 +15,13 @@ static void run(const double *u, const double *ua, double *out, double *fx, doub
         if (j <= g.ny) frbcurv::face_x<NSP>(i, j, p, u, fx, g, gamma, ops);
         if (i <= g.nx) frbcurv::face_y<NSP>(i, j, p, u, fy, g, gamma, ops);
       }
+  double tile[NSP * NSP * 4];
+  frbcurv::RowCarry<NSP> c[NSP];
   for (int j = 1; j <= g.ny; ++j)
-    for (int i = 1; i <= g.nx; ++i)
-      for (int m = 0; m < 4; ++m) frbcurv::element_var<NSP>(i, j, m, u, ua, fx, fy, out, g, gamma, ops, st);
+    for (int i = 1; i <= g.nx; ++i) {  // the block barrier of the kernel = the boundary between the two loops
+      for (int l = 0; l < NSP; ++l) frbcurv::row_xpass<NSP>(i, j, l, u, fx, g, gamma, ops, tile, 1, c[l]);
+      for (int l = 0; l < NSP; ++l) frbcurv::row_ypass<NSP>(i, j, l, u, ua, fy, out, g, ops, st, tile, 1, c[l]);
+    }
 }
 
 // operators as the ABI takes them (lpdm column-major nsp x nsp); stage = (ca, cb, cdt, use_a, rhs_only)
