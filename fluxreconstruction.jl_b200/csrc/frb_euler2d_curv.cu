@@ -28,21 +28,23 @@ euler2d_curv_face_kernel(const double *__restrict__ u, double *__restrict__ fx, 
 }
 
 // thread = (element i = lane, point row l = threadIdx.y); one block = 32 consecutive elements of row j.
-// The tile holds f2 = (iJ [F; G])[2] of the block's elements: [l][k][m][lane], conflict-free in both passes.
+// tile holds f2 = (iJ [F; G])[2] of the block's elements, [l][k][m][lane], fyt the y common fluxes of their
+// bottom / top faces, [side][p][m][lane]; both conflict-free (lane fastest).
 template <int NSP, int MINB>
 __global__ void __launch_bounds__(32 * NSP, MINB)
 euler2d_curv_elem_kernel(const double *__restrict__ u, const double *__restrict__ ua,
                          const double *__restrict__ fx, const double *__restrict__ fy, double *__restrict__ out,
                          CurvGeom g, double gamma, FrbOps ops, FrbStage st) {
   __shared__ double tile[NSP * NSP * 4 * 32];
+  __shared__ double fyt[2 * NSP * 4 * 32];
   const int lane = threadIdx.x, l = threadIdx.y;
   const int i = blockIdx.x * 32 + lane + 1;
   const int j = blockIdx.y + 1;
   const bool active = i <= g.nx;
   frbcurv::RowCarry<NSP> c;
-  if (active) frbcurv::row_xpass<NSP>(i, j, l, u, fx, g, gamma, ops, tile + lane, 32, c);
+  if (active) frbcurv::row_xpass<NSP>(i, j, l, u, fx, fy, g, gamma, ops, tile + lane, fyt + lane, 32, c);
   __syncthreads();
-  if (active) frbcurv::row_ypass<NSP>(i, j, l, u, ua, fy, out, g, ops, st, tile + lane, 32, c);
+  if (active) frbcurv::row_ypass<NSP>(i, j, l, ua, out, g, ops, st, tile + lane, fyt + lane, 32, c);
 }
 
 // Per-step boundary fill of dev/cylinder2.jl:176-187 on the ring-embedded array (interior nx = nr - 1,
@@ -104,6 +106,8 @@ int frb_launch_euler2d_curv(frb_prob_t p, const double *u, const double *ua, dou
   g.wall_xlo = (p->curv_flags & FRB_CURV_WALL_XLO) ? 1 : 0;
   g.flux = p->flux;
   if (st.nested) { st.cdt *= st.cb; st.nested = 0; }
+  if (st.rhs_only) { st.ca = 0.0; st.cb = 0.0; st.cdt = 1.0; st.use_a = 0; }  // out = L(u), branch-free in the kernel
+  if (!st.use_a) st.ca = 0.0;
   cudaStream_t s = p->ctx->stream;
   dim3 fb(128), fg((p->nx + 1 + 127) / 128, p->ny + 1, 2 * p->nsp);
   dim3 eb(32, p->nsp), eg((p->nx + 31) / 32, p->ny);

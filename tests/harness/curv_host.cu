@@ -15,12 +15,15 @@ static void run(const double *u, const double *ua, double *out, double *fx, doub
         if (j <= g.ny) frbcurv::face_x<NSP>(i, j, p, u, fx, g, gamma, ops);
         if (i <= g.nx) frbcurv::face_y<NSP>(i, j, p, u, fy, g, gamma, ops);
       }
-  double tile[NSP * NSP * 4];
+  double tile[NSP * NSP * 4], fyt[2 * NSP * 4];
+  FrbStage sk = st;  // the launcher's mapping of rhs_only (frb_launch_euler2d_curv)
+  if (sk.rhs_only) { sk.ca = 0.0; sk.cb = 0.0; sk.cdt = 1.0; sk.use_a = 0; }
+  if (!sk.use_a) sk.ca = 0.0;
   frbcurv::RowCarry<NSP> c[NSP];
   for (int j = 1; j <= g.ny; ++j)
     for (int i = 1; i <= g.nx; ++i) {  // the block barrier of the kernel = the boundary between the two loops
-      for (int l = 0; l < NSP; ++l) frbcurv::row_xpass<NSP>(i, j, l, u, fx, g, gamma, ops, tile, 1, c[l]);
-      for (int l = 0; l < NSP; ++l) frbcurv::row_ypass<NSP>(i, j, l, u, ua, fy, out, g, ops, st, tile, 1, c[l]);
+      for (int l = 0; l < NSP; ++l) frbcurv::row_xpass<NSP>(i, j, l, u, fx, fy, g, gamma, ops, tile, fyt, 1, c[l]);
+      for (int l = 0; l < NSP; ++l) frbcurv::row_ypass<NSP>(i, j, l, ua, out, g, ops, sk, tile, fyt, 1, c[l]);
     }
 }
 
