@@ -45,6 +45,7 @@ SIGNATURES = {
                                        C.c_double, C.c_double, C.POINTER(C.c_void_p)]),
     "frb_euler2d_curv_create": (C.c_int32, [C.c_void_p, C.c_int32, C.c_int32, C.POINTER(Operators), c_dp, c_dp, c_dp,
                                             c_dp, C.c_int32, C.c_double, C.POINTER(C.c_void_p)]),
+    "frb_euler2d_curv_set_vertices": (C.c_int32, [C.c_void_p, c_dp, c_dp]),
     "frb_bgk1d_create": (C.c_int32, [C.c_void_p, C.c_int32, C.c_int32, C.POINTER(Operators), c_dp, c_dp, c_dp,
                                      C.c_double, C.POINTER(C.c_void_p)]),
     "frb_bgk1d_set_model": (C.c_int32, [C.c_void_p, C.c_int32, C.c_double]),

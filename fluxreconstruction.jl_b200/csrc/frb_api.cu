@@ -157,7 +157,7 @@ extern "C" int32_t frb_prob_destroy(frb_prob_t p) {
   cudaFree(p->u); cudaFree(p->s1); cudaFree(p->s2); cudaFree(p->du); cudaFree(p->rc_base);
   cudaFree(p->J); cudaFree(p->velo); cudaFree(p->weights); cudaFree(p->prim);
   cudaFree(p->lim_w); cudaFree(p->flag); cudaFree(p->loop_bar); cudaFree(p->filt); cudaFree(p->ns_flux);
-  cudaFree(p->curv_iJ); cudaFree(p->curv_n1); cudaFree(p->curv_n2); cudaFree(p->curv_fpc); cudaFree(p->curv_flux);
+  cudaFree(p->curv_iJ); cudaFree(p->curv_n1); cudaFree(p->curv_n2); cudaFree(p->curv_fpc); cudaFree(p->curv_flux); cudaFree(p->curv_vert);
   cudaFree(p->tri_ops); cudaFree(p->tri_uf); cudaFree(p->tri_normals); cudaFree(p->tri_type); cudaFree(p->tri_fpn);
   if (p->ev0) cudaEventDestroy(p->ev0);
   if (p->ev1) cudaEventDestroy(p->ev1);
@@ -253,6 +253,23 @@ extern "C" int32_t frb_euler2d_curv_create(frb_ctx_t ctx, int32_t nx, int32_t ny
   FRB_TRY(upload_vec(p, &p->curv_n2, n2, (size_t)nx * (ny + 1) * 2));
   if (fpc) FRB_TRY(upload_vec(p, &p->curv_fpc, fpc, (size_t)nx * ny * p->nsp * 4));
   *out = p;
+  return FRB_OK;
+}
+
+extern "C" int32_t frb_euler2d_curv_set_vertices(frb_prob_t p, const double *vertices, const double *r) {
+  FRB_REQUIRE(p && p->curv_iJ, FRB_ERR_STATE, "frb_euler2d_curv_set_vertices: curvilinear euler2d problems only");
+  FRB_CUDA(cudaSetDevice(p->ctx->device));
+  FRB_CUDA(cudaStreamSynchronize(p->ctx->stream));
+  if (!vertices) {  // back to the stored metric
+    cudaFree(p->curv_vert);
+    p->curv_vert = nullptr;
+    return FRB_OK;
+  }
+  FRB_REQUIRE(r, FRB_ERR_ARG, "frb_euler2d_curv_set_vertices: r is NULL");
+  const size_t n = (size_t)(p->nx + 2) * (p->ny + 2) * 8;
+  if (!p->curv_vert) FRB_CUDA(cudaMalloc(&p->curv_vert, sizeof(double) * n));
+  FRB_CUDA(cudaMemcpy(p->curv_vert, vertices, sizeof(double) * n, cudaMemcpyHostToDevice));
+  for (int q = 0; q < p->nsp; ++q) p->curv_r[q] = r[q];
   return FRB_OK;
 }
 

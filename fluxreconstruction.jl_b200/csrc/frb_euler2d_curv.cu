@@ -12,19 +12,19 @@
 
 namespace {
 
-// blockIdx.z < NSP: x faces, flux point z;  >= NSP: y faces, flux point z - NSP.  Lanes along i.
+// thread = (element i = lane, flux point p = threadIdx.y) computes the x face left of the element and the y face
+// below it.  The NSP point threads of a block read every value of their elements twice (as a row for the x trace,
+// as a column for the y trace): one DRAM pass, the second read is an L1 hit; the left neighbour is the next lane,
+// the lower neighbour's block ran just before (L2).
 template <int NSP>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(32 * NSP)
 euler2d_curv_face_kernel(const double *__restrict__ u, double *__restrict__ fx, double *__restrict__ fy,
                          CurvGeom g, double gamma, FrbOps ops) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x + 1;
+  const int i = blockIdx.x * 32 + threadIdx.x + 1;
   const int j = blockIdx.y + 1;
-  const int z = blockIdx.z;
-  if (z < NSP) {
-    if (i <= g.nx + 1 && j <= g.ny) frbcurv::face_x<NSP>(i, j, z, u, fx, g, gamma, ops);
-  } else {
-    if (i <= g.nx && j <= g.ny + 1) frbcurv::face_y<NSP>(i, j, z - NSP, u, fy, g, gamma, ops);
-  }
+  const int p = threadIdx.y;
+  if (i > g.nx + 1) return;
+  frbcurv::face_xy<NSP>(i, j, p, j <= g.ny, i <= g.nx, u, fx, fy, g, gamma, ops);
 }
 
 // thread = (element i = lane, point row l = threadIdx.y); one block = 32 consecutive elements of row j.
@@ -105,11 +105,13 @@ int frb_launch_euler2d_curv(frb_prob_t p, const double *u, const double *ua, dou
   g.fy_row = (p->curv_flags & FRB_CURV_FY_ROW_INDEX) ? 1 : 0;
   g.wall_xlo = (p->curv_flags & FRB_CURV_WALL_XLO) ? 1 : 0;
   g.flux = p->flux;
+  g.vert = p->curv_vert;
+  for (int q = 0; q < FRB_NSPMAX; ++q) g.r[q] = p->curv_r[q];
   if (st.nested) { st.cdt *= st.cb; st.nested = 0; }
   if (st.rhs_only) { st.ca = 0.0; st.cb = 0.0; st.cdt = 1.0; st.use_a = 0; }  // out = L(u), branch-free in the kernel
   if (!st.use_a) st.ca = 0.0;
   cudaStream_t s = p->ctx->stream;
-  dim3 fb(128), fg((p->nx + 1 + 127) / 128, p->ny + 1, 2 * p->nsp);
+  dim3 fb(32, p->nsp), fg((p->nx + 1 + 31) / 32, p->ny + 1);
   dim3 eb(32, p->nsp), eg((p->nx + 31) / 32, p->ny);
   static const bool minb4 = getenv("FRB_CURV_MINB4") != nullptr;  // occupancy experiment
   switch (p->nsp) {

@@ -10,8 +10,9 @@
 //
 // Two passes per stage (the split the north star words: a face kernel over the face connectivity, an
 // element kernel that fuses derivative, correction and the RK update):
-//   face_x / face_y  thread = one interface flux point: both traces from the two neighbouring element
-//                    blocks, HLL in the face frame, all 4 components -> fx[nx+1, ny, nsp, 4], fy[nx, ny+1, nsp, 4]
+//   face_xy          thread = (element, flux point p): the x face left of the element and the y face below it --
+//                    traces from the neighbouring element blocks, common flux in the face frame, all 4
+//                    components -> fx[nx+1, ny, nsp, 4], fy[nx, ny+1, nsp, 4]
 //   row_xpass /      thread = (element, point row l), a block = 32 elements x NSP rows: point fluxes iJ [F; G] of
 //   row_ypass        the row, r-derivative + x corrections in registers, f2 through a shared-memory tile, then the
 //                    s-derivative + y corrections + stage update of the same row
@@ -41,6 +42,8 @@
 struct CurvGeom {
   int nx, ny;
   const double *iJ, *n1, *n2, *fpc;  // fpc == nullptr: solution-point factors
+  const double *vert;                // != nullptr: iJ is evaluated from the cell vertices [nx+2, ny+2, 4, 2]
+  double r[FRB_NSPMAX];              // solution points ps.xpl (used with vert)
   int fy_row;    // 1: y common flux indexed by the row l (the scripts' literal form)
   int wall_xlo;  // 1: x face 1 is the mirror wall of dev/cylinder2.jl:100-120
   int flux;      // FRB_FLUX_HLL (the scripts) | LF | ROE
@@ -100,41 +103,41 @@ FRB_HD void load_trace_y(const double *__restrict__ u, size_t e, size_t NE, int 
   }
 }
 
-// x face i (1..nx+1) of row j (1..ny), flux point p (0..NSP-1): parallelogram.jl:115-125
-// fx[i-1 + (nx+1)(j-1 + ny (p + NSP m))]
+// Common fluxes: fx[i-1 + (nx+1)(j-1 + ny (p + NSP m))] for x face i (1..nx+1) of row j (parallelogram.jl:115-125),
+//                fy[i-1 + nx (j-1 + (ny+1)(p + NSP m))] for y face j (1..ny+1) of column i (:126-136).
+// The x face left of element (i, j) and the y face below it, flux point p, in one go: the four traces first
+// (64 loads without control flow in between, clamped to valid cells for the threads that own only one of the two
+// faces), then the two common fluxes.  do_x / do_y say which results exist (i <= nx + 1, j <= ny / i <= nx, j <= ny + 1).
 template <int NSP>
-FRB_HD void face_x(int i, int j, int p, const double *__restrict__ u, double *__restrict__ fx, const CurvGeom &g,
-                   double gamma, const FrbOps &ops) {
+FRB_HD void face_xy(int i, int j, int p, bool do_x, bool do_y, const double *__restrict__ u,
+                    double *__restrict__ fx, double *__restrict__ fy, const CurvGeom &g, double gamma,
+                    const FrbOps &ops) {
   const size_t NXG = g.nx + 2, NE = NXG * (size_t)(g.ny + 2);
-  const size_t e = i + NXG * j;
-  double L[4], R[4];
-  load_trace_x<NSP>(u, e - 1, NE, p, ops.lr, L);  // u_face[i-1, j, 2, p, :]
-  load_trace_x<NSP>(u, e, NE, p, ops.ll, R);      // u_face[i, j, 4, p, :]
-  const size_t f = (size_t)(i - 1) + (size_t)(g.nx + 1) * (j - 1), sf = (size_t)(g.nx + 1) * g.ny;
-  const W4 h = flux_normal(g.flux, {L[0], L[1], L[2], L[3]}, {R[0], R[1], R[2], R[3]}, g.n1[f], g.n1[f + sf], gamma,
-                          g.wall_xlo && i == 1);
-  fx[f + sf * (p + NSP * 0)] = h.a;
-  fx[f + sf * (p + NSP * 1)] = h.b;
-  fx[f + sf * (p + NSP * 2)] = h.c;
-  fx[f + sf * (p + NSP * 3)] = h.d;
-}
-
-// y face j (1..ny+1) of column i (1..nx), flux point p: parallelogram.jl:126-136
-// fy[i-1 + nx (j-1 + (ny+1)(p + NSP m))]
-template <int NSP>
-FRB_HD void face_y(int i, int j, int p, const double *__restrict__ u, double *__restrict__ fy, const CurvGeom &g,
-                   double gamma, const FrbOps &ops) {
-  const size_t NXG = g.nx + 2, NE = NXG * (size_t)(g.ny + 2);
-  const size_t e = i + NXG * j;
-  double L[4], R[4];
-  load_trace_y<NSP>(u, e - NXG, NE, p, ops.lr, L);  // u_face[i, j-1, 3, p, :]
-  load_trace_y<NSP>(u, e, NE, p, ops.ll, R);        // u_face[i, j, 1, p, :]
-  const size_t f = (size_t)(i - 1) + (size_t)g.nx * (j - 1), sf = (size_t)g.nx * (g.ny + 1);
-  const W4 h = flux_normal(g.flux, {L[0], L[1], L[2], L[3]}, {R[0], R[1], R[2], R[3]}, g.n2[f], g.n2[f + sf], gamma, 0);
-  fy[f + sf * (p + NSP * 0)] = h.a;
-  fy[f + sf * (p + NSP * 1)] = h.b;
-  fy[f + sf * (p + NSP * 2)] = h.c;
-  fy[f + sf * (p + NSP * 3)] = h.d;
+  const int jx = j <= g.ny ? j : g.ny, iy = i <= g.nx ? i : g.nx;
+  const size_t ex = i + NXG * jx, ey = iy + NXG * j;
+  double xl[4], xr[4], yl[4], yr[4];
+  load_trace_x<NSP>(u, ex - 1, NE, p, ops.lr, xl);    // u_face[i-1, j, 2, p, :]
+  load_trace_x<NSP>(u, ex, NE, p, ops.ll, xr);        // u_face[i, j, 4, p, :]
+  load_trace_y<NSP>(u, ey - NXG, NE, p, ops.lr, yl);  // u_face[i, j-1, 3, p, :]
+  load_trace_y<NSP>(u, ey, NE, p, ops.ll, yr);        // u_face[i, j, 1, p, :]
+  const size_t f1 = (size_t)(i - 1) + (size_t)(g.nx + 1) * (jx - 1), s1 = (size_t)(g.nx + 1) * g.ny;
+  const size_t f2 = (size_t)(iy - 1) + (size_t)g.nx * (j - 1), s2 = (size_t)g.nx * (g.ny + 1);
+  const double c1 = g.n1[f1], d1 = g.n1[f1 + s1], c2 = g.n2[f2], d2 = g.n2[f2 + s2];
+  const W4 hx = flux_normal(g.flux, {xl[0], xl[1], xl[2], xl[3]}, {xr[0], xr[1], xr[2], xr[3]}, c1, d1, gamma,
+                            g.wall_xlo && i == 1);
+  const W4 hy = flux_normal(g.flux, {yl[0], yl[1], yl[2], yl[3]}, {yr[0], yr[1], yr[2], yr[3]}, c2, d2, gamma, 0);
+  if (do_x) {
+    fx[f1 + s1 * (p + NSP * 0)] = hx.a;
+    fx[f1 + s1 * (p + NSP * 1)] = hx.b;
+    fx[f1 + s1 * (p + NSP * 2)] = hx.c;
+    fx[f1 + s1 * (p + NSP * 3)] = hx.d;
+  }
+  if (do_y) {
+    fy[f2 + s2 * (p + NSP * 0)] = hy.a;
+    fy[f2 + s2 * (p + NSP * 1)] = hy.b;
+    fy[f2 + s2 * (p + NSP * 2)] = hy.c;
+    fy[f2 + s2 * (p + NSP * 3)] = hy.d;
+  }
 }
 
 // 1 / x: on the device the branch-free MUFU seed + two Newton steps of frb_physics.cuh (within ~1 ulp; no
@@ -178,16 +181,45 @@ FRB_HD void row_xpass(int i, int j, int l, const double *__restrict__ u, const d
 #pragma unroll
   for (int k = 0; k < NSP; ++k)
 #pragma unroll
-    for (int m = 0; m < 4; ++m) {
-      c.w[k][m] = u[e + NE * plane<NSP>(k, l, m)];
-      a[k][m] = g.iJ[e + NE * plane<NSP>(k, l, m)];  // a11, a21, a12, a22
-    }
+    for (int m = 0; m < 4; ++m) c.w[k][m] = u[e + NE * plane<NSP>(k, l, m)];
 #pragma unroll
   for (int m = 0; m < 4; ++m) {
     FxL[m] = fx[i1 + s1 * (l + NSP * m)];
     FxR[m] = fx[i1 + 1 + s1 * (l + NSP * m)];
     FyB[m] = fy[i2 + s2 * (l + NSP * m)];
     FyT[m] = fy[i2 + nx + s2 * (l + NSP * m)];
+  }
+  if (g.vert) {
+    // iJ[i,j][k,l] = inv(rs_jacobi(r_k, r_l, vertices[i,j])) (struct.jl:135-142, geo_jacobi.jl:77-88) from the 8
+    // vertex coordinates of the element instead of 4 stored doubles per solution point
+    double vx[4], vy[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      vx[q] = g.vert[e + NE * q];
+      vy[q] = g.vert[e + NE * (q + 4)];
+    }
+    double rl = 0.0;  // g.r[l] by selects: a dynamic index would move the parameter array to local memory
+#pragma unroll
+    for (int q = 0; q < NSP; ++q) rl = q == l ? g.r[q] : rl;
+    const double sm = rl - 1.0, sp = rl + 1.0;
+    const double xr = 0.25 * (sm * vx[0] - sm * vx[1] + sp * vx[2] - sp * vx[3]);
+    const double yr = 0.25 * (sm * vy[0] - sm * vy[1] + sp * vy[2] - sp * vy[3]);
+#pragma unroll
+    for (int k = 0; k < NSP; ++k) {
+      const double rm = g.r[k] - 1.0, rp = g.r[k] + 1.0;
+      const double xs = 0.25 * (rm * vx[0] - rp * vx[1] + rp * vx[2] - rm * vx[3]);
+      const double ys = 0.25 * (rm * vy[0] - rp * vy[1] + rp * vy[2] - rm * vy[3]);
+      const double id = rcp(xr * ys - xs * yr);
+      a[k][0] = ys * id;   // a11
+      a[k][1] = -yr * id;  // a21
+      a[k][2] = -xs * id;  // a12
+      a[k][3] = xr * id;   // a22
+    }
+  } else {
+#pragma unroll
+    for (int k = 0; k < NSP; ++k)
+#pragma unroll
+      for (int m = 0; m < 4; ++m) a[k][m] = g.iJ[e + NE * plane<NSP>(k, l, m)];  // a11, a21, a12, a22
   }
   if (g.fpc) {  // cylinder2.jl:155-158
     const double xl = g.fpc[ifp + sfp * (l + NSP * 0)], xr = g.fpc[ifp + sfp * (l + NSP * 1)];

@@ -90,6 +90,8 @@ struct frb_prob_s {
   // curvilinear quadrilaterals (frb_euler2d_curv_create): metric planes, face normals, optional
   // flux-point correction factors; curv_iJ != nullptr marks the problem
   double *curv_iJ = nullptr, *curv_n1 = nullptr, *curv_n2 = nullptr, *curv_fpc = nullptr;
+  double *curv_vert = nullptr;      // cell vertices (frb_euler2d_curv_set_vertices): metric evaluated on the fly
+  double curv_r[FRB_NSPMAX] = {0};  // solution points
   double *curv_flux = nullptr;      // common fluxes on the x | y faces (lazy)
   int curv_flags = 0;
   double *lim_w = nullptr;          // limiter weights (device)

@@ -330,7 +330,8 @@ class Euler2DCurvProblem(_Problem):
     reproduces the scripts' ``fy_interaction[i, j, l, m]`` (parallelogram.jl:147-148); the default ``"k"`` is
     the index the rectangular scripts use (euler2d_wave.jl:100-103).  u0[nx+2, ny+2, nsp, nsp, 4]."""
 
-    def __init__(self, u0, tspan, ps, gamma, n1=None, n2=None, corr="sp", fy_index="k", wall_xlo=False, ctx=None):
+    def __init__(self, u0, tspan, ps, gamma, n1=None, n2=None, corr="sp", fy_index="k", wall_xlo=False, ctx=None,
+                 metric="stored"):
         super().__init__(u0, tspan, ctx)
         from .spaces import correction_factors_fp, face_normals
 
@@ -356,7 +357,22 @@ class Euler2DCurvProblem(_Problem):
         check(lib().frb_euler2d_curv_create(self.ctx.h, ps.nx, ps.ny, C.byref(ops), _lib.dptr(iJ), _lib.dptr(n1),
                                             _lib.dptr(n2), None if fpc is None else _lib.dptr(fpc), flags,
                                             self.gamma, C.byref(self.h)))
+        self._ps = ps
+        if metric != "stored":
+            self.set_metric(metric)
         self.upload(self.u0)
+
+    def set_metric(self, metric):
+        """"stored": the kernels read ps.iJ (the reference's array); "vertices": they evaluate it from
+        ps.vertices and ps.xpl on the fly (frb_euler2d_curv_set_vertices)."""
+        if metric == "vertices":
+            v = np.asfortranarray(self._ps.vertices, dtype=np.float64)
+            r = np.ascontiguousarray(self._ps.xpl, dtype=np.float64)
+            check(lib().frb_euler2d_curv_set_vertices(self.h, _lib.dptr(v), _lib.dptr(r)))
+        elif metric == "stored":
+            check(lib().frb_euler2d_curv_set_vertices(self.h, None, None))
+        else:
+            raise ValueError("metric must be 'stored' or 'vertices'")
 
 
 class BGKProblem(_Problem):

@@ -118,6 +118,11 @@ int32_t frb_euler2d_create(frb_ctx_t ctx, int32_t nx, int32_t ny, const frb_oper
 int32_t frb_euler2d_curv_create(frb_ctx_t ctx, int32_t nx, int32_t ny, const frb_operators *ops,
                                 const double *iJ, const double *n1, const double *n2, const double *fpc,
                                 int32_t flags, double gamma, frb_prob_t *out);
+/* Optional: hand the library what ps.iJ is computed from -- vertices[nx+2, ny+2, 4, 2] = ps.base.vertices and
+ * r[nsp] = ps.xpl (struct.jl:133-142) -- and the kernels evaluate iJ[i,j][k,l] = inv(rs_jacobi(r_k, r_l,
+ * vertices[i,j])) (geo_jacobi.jl:77-88) on the fly: 8 doubles per element instead of 4 per solution point
+ * cross HBM.  Equal to the stored metric up to rounding.  vertices == NULL returns to the stored copy. */
+int32_t frb_euler2d_curv_set_vertices(frb_prob_t prob, const double *vertices, const double *r);
 /* mol! of example/bgk_wave.jl:69-129 with its periodic e2f/f2e tables (:42-67).
  * State u[ncell, nu, nsp]; dx[ncell]; velo, weights [nu] (VSpace1D). */
 int32_t frb_bgk1d_create(frb_ctx_t ctx, int32_t ncell, int32_t nu, const frb_operators *ops,

@@ -28,14 +28,15 @@ def main():
     rho = 1.0 + 0.1 * np.sin(2 * np.pi * x)
     prim = np.stack([rho, np.ones_like(rho), 0.2 * np.ones_like(rho), rho], axis=-1)
     u = np.asfortranarray(FR.prim_conserve(prim, g))
-    for corr in ("sp", "fp"):
-        prob = FR.Euler2DCurvProblem(u, (0.0, 1.0), ps, g, corr=corr)
+    for corr, metric in (("sp", "stored"), ("fp", "stored"), ("sp", "vertices")):
+        prob = FR.Euler2DCurvProblem(u, (0.0, 1.0), ps, g, corr=corr, metric=metric)
         dofs = prob.dofs
         for kind, state_bytes in ((0, 16), (1, 24)):
             prob.time_stage(kind, 3)
             ms = prob.time_stage(kind, iters)
             print(json.dumps({
-                "workload": f"curv euler2d {nx}x{ny} p{deg} corr={corr}", "stage_bytes_per_dof": state_bytes + 8,
+                "workload": f"curv euler2d {nx}x{ny} p{deg} corr={corr} metric={metric}",
+                "stage_bytes_per_dof": state_bytes + 8,
                 "ms_per_stage": round(ms, 4), "gdof_per_s": round(dofs / ms / 1e6, 2),
                 "algorithmic_GBps": round(dofs * (state_bytes + 8) / ms / 1e6, 1)}), flush=True)
         prob.close()

@@ -11,10 +11,7 @@ static void run(const double *u, const double *ua, double *out, double *fx, doub
                 double gamma, const FrbOps &ops, const FrbStage &st) {
   for (int j = 1; j <= g.ny + 1; ++j)
     for (int i = 1; i <= g.nx + 1; ++i)
-      for (int p = 0; p < NSP; ++p) {
-        if (j <= g.ny) frbcurv::face_x<NSP>(i, j, p, u, fx, g, gamma, ops);
-        if (i <= g.nx) frbcurv::face_y<NSP>(i, j, p, u, fy, g, gamma, ops);
-      }
+      for (int p = 0; p < NSP; ++p) frbcurv::face_xy<NSP>(i, j, p, j <= g.ny, i <= g.nx, u, fx, fy, g, gamma, ops);
   double tile[NSP * NSP * 4], fyt[2 * NSP * 4];
   FrbStage sk = st;  // the launcher's mapping of rhs_only (frb_launch_euler2d_curv)
   if (sk.rhs_only) { sk.ca = 0.0; sk.cb = 0.0; sk.cdt = 1.0; sk.use_a = 0; }
@@ -30,7 +27,7 @@ static void run(const double *u, const double *ua, double *out, double *fx, doub
 // operators as the ABI takes them (lpdm column-major nsp x nsp); stage = (ca, cb, cdt, use_a, rhs_only)
 extern "C" int curv_host_stage(int nx, int ny, int nsp, const double *u, const double *ua, double *out, double *fx,
                                double *fy, const double *iJ, const double *n1, const double *n2, const double *fpc,
-                               int flags, double gamma, const double *ll, const double *lr, const double *lpdm,
+                               const double *vert, const double *r, int flags, double gamma, const double *ll, const double *lr, const double *lpdm,
                                const double *dgl, const double *dgr, double ca, double cb, double cdt, int use_a,
                                int rhs_only) {
   FrbOps ops;
@@ -40,7 +37,8 @@ extern "C" int curv_host_stage(int nx, int ny, int nsp, const double *u, const d
     for (int k = 0; k < nsp; ++k) ops.lpdm[q * FRB_NSPMAX + k] = lpdm[q + nsp * k];
   }
   CurvGeom g;
-  g.nx = nx; g.ny = ny; g.iJ = iJ; g.n1 = n1; g.n2 = n2; g.fpc = fpc;
+  g.nx = nx; g.ny = ny; g.iJ = iJ; g.n1 = n1; g.n2 = n2; g.fpc = fpc; g.vert = vert;
+  for (int q = 0; q < FRB_NSPMAX; ++q) g.r[q] = (r && q < nsp) ? r[q] : 0.0;
   g.fy_row = (flags & FRB_CURV_FY_ROW_INDEX) ? 1 : 0;
   g.wall_xlo = (flags & FRB_CURV_WALL_XLO) ? 1 : 0;
   g.flux = (flags >> 8) & 3;  // test-only: the flux kind rides in bits 8..9

@@ -93,6 +93,26 @@ def test_extra_fluxes_in_the_face_frame(FR, flux):
     prob.close()
 
 
+@pytest.mark.parametrize("deg", [1, 2, 3])
+def test_metric_from_vertices(FR, deg):
+    """frb_euler2d_curv_set_vertices: iJ evaluated on the fly from the cell vertices (trapezoids: J varies)."""
+    nr, nth = 20, 24
+    ps, po, (n1, n2) = cylinder(FR, nr, nth, deg)
+    u = rand_state((nr + 1, nth + 2, deg + 1, deg + 1), 19)
+    fpc = c.corr_factors_fp(po.Ji, n1, n2)
+    for corr in ("sp", "fp"):
+        prob = FR.Euler2DCurvProblem(u, (0.0, 1.0), ps, GAMMA, corr=corr, wall_xlo=True, metric="vertices")
+        du = np.zeros_like(u, order="F")
+        prob.f(du, u, None, 0.0)
+        ref = c.rhs_euler2d_curv(u, po, n1, n2, GAMMA, corr=corr, fpc=fpc, fy_index="k", wall_xlo=True)
+        assert rel(du, ref) <= RTOL_RHS
+        prob.set_metric("stored")
+        du2 = np.zeros_like(u, order="F")
+        prob.f(du2, u, None, 0.0)
+        assert rel(du2, ref) <= RTOL_RHS
+        prob.close()
+
+
 def test_rectangular_mesh_equals_the_rectangular_problem(FR):
     nx, ny, deg = 40, 24, 3
     ps = FR.FRPSpace2D(FR.PSpace2D(0.0, 1.0, nx, 0.0, 0.5, ny, 1, 1), deg)

@@ -196,21 +196,22 @@ def host_stage():
 
     lib = ctypes.CDLL(hb.build())
     D = ctypes.POINTER(ctypes.c_double)
-    lib.curv_host_stage.argtypes = ([ctypes.c_int] * 3 + [D] * 9 + [ctypes.c_int, ctypes.c_double] + [D] * 5
+    lib.curv_host_stage.argtypes = ([ctypes.c_int] * 3 + [D] * 11 + [ctypes.c_int, ctypes.c_double] + [D] * 5
                                     + [ctypes.c_double] * 3 + [ctypes.c_int] * 2)
 
     def P(a):
         return None if a is None else a.ctypes.data_as(D)
 
-    def run(u, ps, n1, n2, fpc, flags, stage=(0.0, 0.0, 1.0, 0, 1), ua=None):
+    def run(u, ps, n1, n2, fpc, flags, stage=(0.0, 0.0, 1.0, 0, 1), ua=None, vertices=False):
         nx, ny, nsp = u.shape[0] - 2, u.shape[1] - 2, u.shape[2]
         out = np.zeros_like(u, order="F")
         keep = [np.asfortranarray(ps.iJ), np.asfortranarray(n1), np.asfortranarray(n2),
                 None if fpc is None else np.asfortranarray(fpc), np.zeros((nx + 1) * ny * nsp * 4),
-                np.zeros(nx * (ny + 1) * nsp * 4), np.asfortranarray(ps.dl)]
+                np.zeros(nx * (ny + 1) * nsp * 4), np.asfortranarray(ps.dl),
+                np.asfortranarray(ps.vertices) if vertices else None, np.ascontiguousarray(ps.xpl)]
         ops = [np.ascontiguousarray(a) for a in (ps.ll, ps.lr)] + [keep[6]] + [np.ascontiguousarray(a) for a in (ps.dhl, ps.dhr)]
         rc = lib.curv_host_stage(nx, ny, nsp, P(u), P(ua), P(out), P(keep[4]), P(keep[5]), P(keep[0]), P(keep[1]),
-                                 P(keep[2]), P(keep[3]), flags, GAMMA, *[P(a) for a in ops],
+                                 P(keep[2]), P(keep[3]), P(keep[7]), P(keep[8]), flags, GAMMA, *[P(a) for a in ops],
                                  float(stage[0]), float(stage[1]), float(stage[2]), int(stage[3]), int(stage[4]))
         assert rc == 0
         return out
@@ -238,6 +239,9 @@ def test_device_routines_on_the_cpu(host_stage, deg):
     for fy, flags in (("l", 3), ("k", 2)):
         ref = c.rhs_euler2d_curv(u, ps, n1, n2, GAMMA, corr="fp", fpc=fpc, fy_index=fy, wall_xlo=True)
         assert rel(host_stage(u, ps, n1, n2, fpc, flags), ref) < 1e-14
+    # the metric evaluated from the vertices on the fly (frb_euler2d_curv_set_vertices) instead of the stored iJ
+    ref = c.rhs_euler2d_curv(u, ps, n1, n2, GAMMA, corr="fp", fpc=fpc, fy_index="k", wall_xlo=True)
+    assert rel(host_stage(u, ps, n1, n2, fpc, 2, vertices=True), ref) < 1e-13
     for kind, name in ((1, "lf"), (2, "roe")):  # the extra common fluxes, in the face frame
         ref = c.rhs_euler2d_curv(u, ps, n1, n2, GAMMA, corr="fp", fpc=fpc, fy_index="k", wall_xlo=True, flux=name)
         assert rel(host_stage(u, ps, n1, n2, fpc, 2 | (kind << 8)), ref) < 1e-13
