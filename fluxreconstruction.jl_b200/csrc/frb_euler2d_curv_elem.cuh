@@ -73,7 +73,14 @@ FRB_HD W4 flux_normal(int kind, W4 L, W4 R, double c, double s, double gamma, in
     l2 = rn * V;
     l3 = 0.5 * rn / ln / gm1 + 0.5 * rn * (U * U + V * V);
   }
+#if defined(__CUDA_ARCH__)
+  // HLL on the device: the branch-free form of the roofline kernels (MUFU-seeded reciprocal / square root,
+  // selects instead of early returns; within ~2 ulp of the IEEE form the host harness runs)
+  const frb::Flux4 f = kind == FRB_FLUX_HLL ? frb::hll4_fast(l0, l1, l2, l3, r0, r1, r2, r3, gamma, gm1)
+                                            : frb::riemann4(kind, l0, l1, l2, l3, r0, r1, r2, r3, gamma);
+#else
   const frb::Flux4 f = frb::riemann4(kind, l0, l1, l2, l3, r0, r1, r2, r3, gamma);
+#endif
   return {f.f0, fma(-f.f2, s, f.f1 * c), fma(f.f1, s, f.f2 * c), f.f3};
 }
 
