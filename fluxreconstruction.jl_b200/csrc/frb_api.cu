@@ -493,6 +493,8 @@ static int ensure_du(frb_prob_t p) {
   return FRB_OK;
 }
 
+static int halo_wait_if_pending(frb_prob_t p);
+
 extern "C" int32_t frb_rhs(frb_prob_t p, const double *u_host, double *du_host, double t) {
   (void)t;
   FRB_REQUIRE(p, FRB_ERR_ARG, "frb_rhs: prob is NULL");
@@ -510,6 +512,7 @@ extern "C" int32_t frb_rhs(frb_prob_t p, const double *u_host, double *du_host, 
   prof_begin(p);
   FRB_CUDA(cudaEventRecord(p->ev0, s));
   FrbStage st = {0.0, 0.0, 1.0, 0, 1};
+  if (int rc = halo_wait_if_pending(p)) return rc;  // slab-parallel: the neighbours' rows of p->u have landed
   int n = launch_stage(p, p->u, nullptr, p->du, st);
   if (n < 0) return n;
   FRB_CUDA(cudaEventRecord(p->ev1, s));

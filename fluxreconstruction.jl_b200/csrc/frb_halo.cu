@@ -53,6 +53,17 @@ __global__ void halo_push_kernel(const double *__restrict__ src, double *__restr
   }
 }
 
+// cfg5 (u[4, nsp, nsp, ny+2, nx+2], slabs along the slowest index i): a column of cells is one contiguous run
+// of `col` doubles.  My first owned column -> the upper halo column of the rank below, my last owned column -> the
+// lower halo column of the rank above.
+__global__ void halo_push_cols_kernel(const double *__restrict__ src, double *__restrict__ dst_lo,
+                                      double *__restrict__ dst_hi, size_t col, int nxl, int nxl_lo) {
+  const size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (t >= col) return;
+  if (dst_lo) dst_lo[col * (size_t)(nxl_lo + 1) + t] = src[col * 1 + t];
+  if (dst_hi) dst_hi[t] = src[col * (size_t)nxl + t];
+}
+
 __global__ void halo_signal_kernel(unsigned long long *flag_lo, unsigned long long *flag_hi,
                                    unsigned long long value) {
   __threadfence_system();
@@ -91,8 +102,8 @@ int check_launch(const char *what) {
 // export layout: 5 IPC handles (u, s1, s2, flags, row-chunk buffers) + int32 ny_local + int32 has_rc
 extern "C" int32_t frb_halo_export(frb_prob_t p, unsigned char *out) {
   if (!p || !out) { frb_set_error("frb_halo_export: NULL argument"); return FRB_ERR_ARG; }
-  if (p->kind != K_EULER2D || p->curv_iJ) {
-    frb_set_error("frb_halo_export: rectangular euler2d problems only");
+  if (!((p->kind == K_EULER2D && !p->curv_iJ) || p->kind == K_NS2D)) {
+    frb_set_error("frb_halo_export: rectangular euler2d and ns2d problems only");
     return FRB_ERR_STATE;
   }
   FRB_CUDA(cudaSetDevice(p->ctx->device));
@@ -108,7 +119,8 @@ extern "C" int32_t frb_halo_export(frb_prob_t p, unsigned char *out) {
     FRB_CUDA(cudaIpcGetMemHandle(&h, bufs[b]));
     memcpy(out + b * FRB_IPC_HANDLE_BYTES, &h, FRB_IPC_HANDLE_BYTES);
   }
-  int32_t tail[2] = {p->ny, p->rc_base ? 1 : 0};
+  // extent of the slab along the partitioned index: rows (euler2d, slabs along j) or columns (ns2d, along i)
+  int32_t tail[2] = {p->kind == K_NS2D ? p->nx : p->ny, p->rc_base ? 1 : 0};
   memset(out + 4 * FRB_IPC_HANDLE_BYTES, 0, FRB_IPC_HANDLE_BYTES);
   if (p->rc_base) {
     FRB_CUDA(cudaIpcGetMemHandle(&h, p->rc_base));
@@ -256,6 +268,14 @@ int frb_halo_push(frb_prob_t p, const double *src, int dst_role, bool seam, int 
     if (last) dh = phi[dst_role];
   }
   if (!dl && !dh) return 0;
+  if (p->kind == K_NS2D) {  // no periodic seam in the cavity: interior slab boundaries only
+    if (seam) return 0;
+    const size_t col = (size_t)4 * p->nsp * p->nsp * (p->ny + 2);
+    halo_push_cols_kernel<<<(unsigned)((col + 255) / 256), 256, 0, p->ctx->stream>>>(src, dl, dh, col, p->nx,
+                                                                                     H->nyl_lo);
+    if (int r = check_launch("halo_push_cols_kernel")) return r;
+    return 1;
+  }
   if (rc) return frb_rc_row_push(p, src, dl, dh, H->nyl_lo, seam ? flip_var : -1);
   const int npp = p->nsp * p->nsp, nplanes = 4 * npp;
   dim3 blk(128), grd((p->nx + 2 + 127) / 128, nplanes);

@@ -186,11 +186,13 @@ __device__ __forceinline__ size_t eoff(int j, int i, int nyg) {
 // boundary!(u, p, lambda0): isothermal walls by mirrored ghost states; lid on the top wall
 template <int NSP>
 __global__ void ns_boundary_kernel(double *__restrict__ u, int nx, int ny, double gamma, double lam0,
-                                   double lid) {
+                                   double lid, int halo_lo, int halo_hi) {
   const int a = blockIdx.x * blockDim.x + threadIdx.x + 1;
   const int side = blockIdx.y;
   const int n1 = side < 2 ? ny : nx;
   if (a > n1) return;
+  // slab-parallel runs: column 0 / nx+1 of an interior slab boundary is the neighbour's data, not a wall
+  if ((side == 0 && halo_lo) || (side == 1 && halo_hi)) return;
   const int nyg = ny + 2;
   const double gm1 = gamma - 1.0;
   int is, js, id, jd;
@@ -331,7 +333,7 @@ ns_elem_kernel(const double *__restrict__ u, const double *__restrict__ ua, doub
 // elements, so that the new state carries the ghosts OrdinaryDiffEq's axpys would give it
 template <int NSP>
 __global__ void ns_ring_stage_kernel(const double *src, const double *ua, double *dst, int nx, int ny,
-                                     double ca, double cb, int use_a) {
+                                     double ca, double cb, int use_a, int halo_lo, int halo_hi) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   const int nxg = nx + 2, nyg = ny + 2, nring = 2 * nxg + 2 * ny;
   if (t >= nring) return;
@@ -340,6 +342,7 @@ __global__ void ns_ring_stage_kernel(const double *src, const double *ua, double
   else if (t < 2 * nxg) { i = t - nxg; j = nyg - 1; }
   else if (t < 2 * nxg + ny) { i = 0; j = t - 2 * nxg + 1; }
   else { i = nxg - 1; j = t - 2 * nxg - ny + 1; }
+  if ((i == 0 && halo_lo) || (i == nxg - 1 && halo_hi)) return;  // the neighbouring rank writes that column
   const size_t o = eoff<NSP>(j, i, nyg);
   for (int q = 0; q < 4 * NSP * NSP; ++q) {
     double v = cb * src[o + q];
@@ -370,12 +373,17 @@ int frb_launch_ns2d(frb_prob_t p, const double *u, const double *ua, double *out
   const int nmax = p->nx > p->ny ? p->nx : p->ny;
   dim3 bb(64), bg((nmax + 63) / 64, 4);
   double *uw = const_cast<double *>(u);  // boundary! rewrites the ghosts of the state it is given
-  FRB_NS_SWITCH(p->nsp, (ns_boundary_kernel<N><<<bg, bb, 0, s>>>(uw, p->nx, p->ny, p->gamma, p->lambda_wall, p->lid_u)));
+  int nranks = 1;
+  const int rank = frb_halo_rank(p, &nranks);
+  const int halo_lo = frb_halo_active(p) && rank > 0, halo_hi = frb_halo_active(p) && rank < nranks - 1;
+  FRB_NS_SWITCH(p->nsp, (ns_boundary_kernel<N><<<bg, bb, 0, s>>>(uw, p->nx, p->ny, p->gamma, p->lambda_wall, p->lid_u,
+                                                                halo_lo, halo_hi)));
   if (int rc = check_launch("ns_boundary_kernel")) return rc;
   int n = 1;
   if (!st.rhs_only) {  // ghosts of the new state: the stage combination with du = 0
     dim3 rg((2 * (p->nx + 2) + 2 * p->ny + 63) / 64);
-    FRB_NS_SWITCH(p->nsp, (ns_ring_stage_kernel<N><<<rg, bb, 0, s>>>(u, ua, out, p->nx, p->ny, st.ca, st.cb, st.use_a)));
+    FRB_NS_SWITCH(p->nsp, (ns_ring_stage_kernel<N><<<rg, bb, 0, s>>>(u, ua, out, p->nx, p->ny, st.ca, st.cb, st.use_a,
+                                                                  halo_lo, halo_hi)));
     if (int rc = check_launch("ns_ring_stage_kernel")) return rc;
     n += 1;
   }

@@ -467,9 +467,12 @@ class DistributedEuler2D(Euler2DProblem):
 
     def __init__(self, u0_local, tspan, ps_local, gamma, dist, ctx=None, ghost="wave_x", kernel="auto"):
         super().__init__(u0_local, tspan, ps_local, gamma, ctx=ctx, kernel=kernel)
+        self.set_hooks(ghost=ghost)
+        self._connect(dist)
+
+    def _connect(self, dist):
         self.dist = dist
         self.rank, self.nranks = dist.get_rank(), dist.get_world_size()
-        self.set_hooks(ghost=ghost)
         if self.nranks > 1:
             blob = (C.c_ubyte * HALO_BLOB_BYTES)()
             check(lib().frb_halo_export(self.h, blob))
@@ -502,6 +505,22 @@ def ref_vhs_vis(Kn, alpha, omega):
 
     return 5.0 * (alpha + 1.0) * (alpha + 2.0) * math.sqrt(math.pi) / (
         4.0 * alpha * (5.0 - 2.0 * omega) * (7.0 - 2.0 * omega)) * Kn
+
+
+class _SlabMixin:
+    """The halo plumbing shared by the slab-parallel problems (see DistributedEuler2D)."""
+
+    _connect = DistributedEuler2D._connect
+    resync = DistributedEuler2D.resync
+
+    def close(self):
+        if self.h and self.nranks > 1:
+            try:
+                self.dist.barrier()
+            except Exception:
+                pass
+            lib().frb_halo_disconnect(self.h)
+        super().close()
 
 
 class NSCavityProblem(_Problem):
@@ -555,3 +574,18 @@ class TriEulerProblem(_Problem):
         (dev/sod.jl:7-16 retags wall cells as 2 before building the problem)."""
         ct = ps.cellType if cell_type is None else cell_type
         return cls(u0, tspan, ct, ps.J, ps.lf, ps.cellNormals, ps.fpn, ps.dl, ps.phi, gamma, fpn_base=0, ctx=ctx)
+
+
+class DistributedNSCavity(_SlabMixin, NSCavityProblem):
+    """Column-slab parallel cavity (cfg5): one process per GPU, this rank holds columns ``slab.start .. slab.stop``
+    of the global mesh in a local array [4, nsp, nsp, ny+2, nx_local+2] (``i`` is the slowest index of the
+    reference's layout, so a slab and each of its halo columns are contiguous).  The walls of the slab's interior
+    boundaries are replaced by the neighbour's boundary column of the current stage, stored into this rank's memory
+    over NVLink after every stage (csrc/frb_halo.cu); the x walls stay with the first / last rank, the y walls and
+    the lid with everybody."""
+
+    def __init__(self, u0_local, tspan, ps_local, K, gamma, mu_ref, omega, dt, dist, lid=0.15, lambda_wall=1.0,
+                 ctx=None):
+        super().__init__(u0_local, tspan, ps_local, K, gamma, mu_ref, omega, dt, lid=lid, lambda_wall=lambda_wall,
+                         ctx=ctx)
+        self._connect(dist)

@@ -115,3 +115,84 @@ def test_two_rank_gloo_slab_exchange_matches_single_domain():
         p.join(180)
         assert p.exitcode == 0
     assert q.get(timeout=5) < 1e-13
+
+
+def _worker_ns(rank, world, port, q):
+    """cfg5 in column slabs (the slowest index of u[4, ns, nr, ny+2, nx+2]): walls only where the slab touches the
+    cavity's x walls, the neighbour's boundary column of the current stage everywhere else."""
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import torch
+    import torch.distributed as dist
+
+    import fr_oracle as o
+    import frb200 as FR
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    g, nxg, ny, deg, nsteps = 5.0 / 3.0, 7, 5, 2, 3
+    psg = o.FRPSpace2D(0.0, 1.0, nxg, 0.0, 1.0, ny, deg, 1, 1)
+    rng = np.random.default_rng(12)
+    ug = o.ic_cavity(psg, g)
+    ug = np.asfortranarray(ug * (1 + 0.02 * rng.standard_normal(ug.shape)))
+    mu = FR.ref_vhs_vis(1e-3, 1.0, 0.5)
+    dt = 0.1 * min(psg.dx, psg.dy) / 3.0
+    sl = FR.partition.slab(nxg, world, rank)
+    u = np.asfortranarray(ug[..., sl.start - 1: sl.stop + 2].copy())
+    psl = o.FRPSpace2D(0.0, sl.count / nxg, sl.count, 0.0, 1.0, ny, deg, 1, 1)
+    walls = o.ns_boundary
+
+    def slab_boundary(a, gamma, lam0=1.0, lid=0.15):  # boundary! without the walls a neighbour stands in for
+        lo, hi = a[..., 0].copy(), a[..., -1].copy()
+        walls(a, gamma, lam0, lid)
+        if not sl.is_first:
+            a[..., 0] = lo
+        if not sl.is_last:
+            a[..., -1] = hi
+        return a
+
+    o.ns_boundary = slab_boundary
+
+    def exchange(a):
+        reqs, bufs = [], []
+        for peer, send_col, recv_col in FR.partition.stage_exchange_plan(sl):
+            s = torch.from_numpy(np.ascontiguousarray(a[..., send_col]))
+            r = torch.empty_like(s)
+            reqs += [dist.isend(s, peer), dist.irecv(r, peer)]
+            bufs.append((recv_col, r))
+        for rq in reqs:
+            rq.wait()
+        for recv_col, r in bufs:
+            a[..., recv_col] = r.numpy()
+
+    exchange(u)
+    for _ in range(nsteps):  # Euler forward, ns_cavity.jl:380
+        u = np.asfortranarray(u + dt * o.rhs_ns2d(u, psl, 1.0, g, mu, 0.81, dt))
+        exchange(u)
+    parts = [None] * world
+    dist.all_gather_object(parts, (sl.start, sl.count, u[..., 1:-1].copy()))
+    if rank == 0:
+        o.ns_boundary = walls
+        ref = ug.copy(order="F")
+        for _ in range(nsteps):
+            ref = np.asfortranarray(ref + dt * o.rhs_ns2d(ref, psg, 1.0, g, mu, 0.81, dt))
+        got = np.zeros_like(ref)
+        for st, cnt, arr in parts:
+            got[..., st: st + cnt] = arr
+        q.put(float(np.abs(got[..., 1:-1, 1:-1] - ref[..., 1:-1, 1:-1]).max()))
+    dist.destroy_process_group()
+
+
+def test_two_rank_gloo_cavity_column_slabs_match_single_domain():
+    import torch.multiprocessing as mp
+
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29900 + os.getpid() % 90
+    procs = [ctx.Process(target=_worker_ns, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(180)
+        assert p.exitcode == 0
+    assert q.get(timeout=5) < 1e-13
