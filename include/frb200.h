@@ -238,6 +238,9 @@ int32_t frb_host_free(void *ptr);
  * boundary rows of the *current* stage; they are written straight into the
  * neighbour's memory by the stage kernel's epilogue over NVLink (peer mapping via
  * CUDA IPC handles the host exchanges out of band), then a flag is raised.
+ * ns2d problems (cfg5) are split the same way along the slowest index of their layout, i: a rank owns nx_local
+ * columns, columns 0 / nx_local+1 of an interior slab boundary are halo columns that replace the wall ghosts
+ * of boundary! there (no periodic seam); the same four calls apply.
  * The reference has no distributed path: this is new surface. */
 #define FRB_IPC_HANDLE_BYTES 64
 /* blob = 5 IPC handles (u, s1, s2, mailbox, row-chunk buffers) + int32 ny_local + int32 has_rc */
