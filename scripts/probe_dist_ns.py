@@ -1,10 +1,12 @@
 """Weak-scaling probe of the cfg5 column slabs: every rank holds nx_local x ny elements of the cavity.
 
-  python scripts/probe_dist_ns.py [nx_local ny deg nsteps]                                  # 1 GPU
+  python scripts/probe_dist_ns.py [nx_local ny deg nsteps lid]                              # 1 GPU
   python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
       --master-port 29521 scripts/probe_dist_ns.py [nx_local ny deg nsteps]                 # N GPUs
 
 Prints one JSON line on rank 0: device ms per Euler step (max over ranks) and whole-job DOF-updates/s.
+The gas starts at rest; lid (default 0: the state stays at rest and finite, the kernels do the same work
+whatever the data) is the wall speed of ns_cavity.jl:337.
 """
 import json
 import os
@@ -27,7 +29,8 @@ class _Solo:
 
 
 def main():
-    nxl, ny, deg, nsteps = (int(a) for a in (sys.argv[1:5] + ["1024", "1024", "3", "20"][len(sys.argv) - 1:]))
+    nxl, ny, deg, nsteps = (int(a) for a in (sys.argv[1:5] + ["1024", "1024", "3", "20"][len(sys.argv) - 1:])[:4])
+    lid = float(sys.argv[5]) if len(sys.argv) > 5 else 0.0
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if world > 1:
@@ -48,7 +51,7 @@ def main():
     u[...] = FR.prim_conserve(np.array([1.0, 0.0, 0.0, 1.0]), g)[:, None, None, None, None]
     mu = FR.ref_vhs_vis(1e-3, 1.0, 0.5)
     dt = 0.1 * min(dx, 1.0 / ny) / 3.0
-    prob = FR.DistributedNSCavity(u, (0.0, 1.0), ps, 1.0, g, mu, 0.81, dt, dist, ctx=FR.Context(local))
+    prob = FR.DistributedNSCavity(u, (0.0, 1.0), ps, 1.0, g, mu, 0.81, dt, dist, lid=lid, ctx=FR.Context(local))
     prob.step(FR.Euler(), dt, 3)
     if world > 1:
         dist.barrier()
@@ -65,7 +68,7 @@ def main():
         dofs = prob.dofs * world
         print(json.dumps({"workload": f"cfg5 cavity {nxl}x{ny} p{deg} per GPU, column slabs", "n_gpus": world,
                           "ms_per_step": round(ms / nsteps, 4), "gdof_per_s": round(dofs * nsteps / ms / 1e6, 2),
-                          "kernels_per_step": launches / nsteps, "finite": fin}), flush=True)
+                          "kernels_per_step": launches / nsteps, "lid": lid, "finite": fin}), flush=True)
     prob.close()
     if world > 1:
         dist.destroy_process_group()
