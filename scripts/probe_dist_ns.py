@@ -63,12 +63,15 @@ def main():
         t = torch.tensor([ms], device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
-    fin = bool(np.isfinite(prob.download()).all())
+    res = prob.download()
+    fin = bool(np.isfinite(res[:, :, :, 1:-1, 1:-1]).all())  # owned elements (ghost corners are never written)
+    bad_ring = int((~np.isfinite(res)).sum() - (~np.isfinite(res[:, :, :, 1:-1, 1:-1])).sum())
     if rank == 0:
         dofs = prob.dofs * world
         print(json.dumps({"workload": f"cfg5 cavity {nxl}x{ny} p{deg} per GPU, column slabs", "n_gpus": world,
                           "ms_per_step": round(ms / nsteps, 4), "gdof_per_s": round(dofs * nsteps / ms / 1e6, 2),
-                          "kernels_per_step": launches / nsteps, "lid": lid, "finite": fin}), flush=True)
+                          "kernels_per_step": launches / nsteps, "lid": lid, "finite": fin, "nonfinite_ghost_values": bad_ring,
+                          "max_momentum": float(np.nanmax(np.abs(res[1:3, :, :, 1:-1, 1:-1])))}), flush=True)
     prob.close()
     if world > 1:
         dist.destroy_process_group()
