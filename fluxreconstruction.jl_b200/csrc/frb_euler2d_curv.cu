@@ -1,13 +1,11 @@
-// 2-D Euler on curvilinear structured quadrilaterals: fused residual + RK stage, one thread
-// per interior element, lanes along i so that every state / metric plane is read in 256-byte runs.
-// The arithmetic lives in frb_euler2d_curv_elem.cuh (reference: dev/parallelogram.jl:80-165,
-// dev/cylinder2.jl:52-164).
+// 2-D Euler on curvilinear structured quadrilaterals: a face kernel (common fluxes over the face
+// connectivity) and an element kernel (derivative + correction + RK stage) per stage, lanes along i so that every
+// state / metric plane is read in 256-byte runs.  The arithmetic lives in frb_euler2d_curv_elem.cuh
+// (reference: dev/parallelogram.jl:80-165, dev/cylinder2.jl:52-164); measurements in profiles/r01_curv.md.
 //
 // Algorithmic bytes per DOF-update: the state terms of the rectangular path (16 B / 24 B) plus the
 // metric, which no longer is two scalars: 4 doubles of iJ per solution point shared by the 4 variables
 // = 8 B per DOF (+ normals and flux-point factors, O(1/nsp) of that).
-#include <stdlib.h>
-
 #include "frb_euler2d_curv_elem.cuh"
 
 namespace {
@@ -30,8 +28,9 @@ euler2d_curv_face_kernel(const double *__restrict__ u, double *__restrict__ fx, 
 // thread = (element i = lane, point row l = threadIdx.y); one block = 32 consecutive elements of row j.
 // tile holds f2 = (iJ [F; G])[2] of the block's elements, [l][k][m][lane], fyt the y common fluxes of their
 // bottom / top faces, [side][p][m][lane]; both conflict-free (lane fastest).
-template <int NSP, int MINB>
-__global__ void __launch_bounds__(32 * NSP, MINB)
+// 3 blocks / SM (168 registers at p3) measured faster than 4 (128 registers, spills): profiles/r01_curv.md.
+template <int NSP>
+__global__ void __launch_bounds__(32 * NSP, 3)
 euler2d_curv_elem_kernel(const double *__restrict__ u, const double *__restrict__ ua,
                          const double *__restrict__ fx, const double *__restrict__ fy, double *__restrict__ out,
                          CurvGeom g, double gamma, FrbOps ops, FrbStage st) {
@@ -113,15 +112,11 @@ int frb_launch_euler2d_curv(frb_prob_t p, const double *u, const double *ua, dou
   cudaStream_t s = p->ctx->stream;
   dim3 fb(32, p->nsp), fg((p->nx + 1 + 31) / 32, p->ny + 1);
   dim3 eb(32, p->nsp), eg((p->nx + 31) / 32, p->ny);
-  static const bool minb4 = getenv("FRB_CURV_MINB4") != nullptr;  // occupancy experiment
   switch (p->nsp) {
 #define FRB_CURV_CASE(N)                                                                                  \
   case N:                                                                                                 \
     euler2d_curv_face_kernel<N><<<fg, fb, 0, s>>>(u, fx, fy, g, p->gamma, p->ops);                         \
-    if (minb4)                                                                                            \
-      euler2d_curv_elem_kernel<N, 4><<<eg, eb, 0, s>>>(u, ua, fx, fy, out, g, p->gamma, p->ops, st);       \
-    else                                                                                                  \
-      euler2d_curv_elem_kernel<N, 3><<<eg, eb, 0, s>>>(u, ua, fx, fy, out, g, p->gamma, p->ops, st);       \
+    euler2d_curv_elem_kernel<N><<<eg, eb, 0, s>>>(u, ua, fx, fy, out, g, p->gamma, p->ops, st);            \
     break;
     FRB_CURV_CASE(2)
     FRB_CURV_CASE(3)
