@@ -69,6 +69,22 @@ def test_argument_errors_do_not_need_a_gpu(FR):
     assert lib.frb_step(None, 0, 0.1, 1) == -1
     assert lib.frb_state_len(None) == 0
     assert lib.frb_prob_destroy(None) == 0
+    # the entry points added for the curvilinear path, the kinetic model and the column slabs
+    assert lib.frb_euler2d_curv_create(None, 4, 4, None, None, None, None, None, 0, 1.4, ctypes.byref(out)) == -1
+    assert b"NULL" in lib.frb_last_error(None)
+    assert lib.frb_euler2d_curv_set_vertices(None, None, None) == -3  # FRB_ERR_STATE: not a curvilinear problem
+    assert lib.frb_bgk1d_set_model(None, 1, 1.0) == -1
+    assert lib.frb_halo_export(None, None) == -1
+
+
+def test_curv_kernels_are_in_the_library(FR):
+    """The curvilinear path is CUDA in libfrb200.so (face + element kernel), not host code."""
+    out = subprocess.run(["cuobjdump", "-sass", FR.LIB_PATH], capture_output=True, text=True).stdout
+    for name in ("euler2d_curv_face_kernel", "euler2d_curv_elem_kernel", "ghost_cyl_theta_kernel",
+                 "halo_push_cols_kernel"):
+        assert name in out, name
+    seg = out[out.index("euler2d_curv_elem_kernel"):]
+    assert "DFMA" in seg[:400000] and "BAR.SYNC" in seg[:400000]
 
 
 def test_product_package_never_imports_the_oracle():
