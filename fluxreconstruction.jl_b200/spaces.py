@@ -104,8 +104,22 @@ def dhuynh(p: int, x):
 _CORRECTION = {"radau": dradau, "sd": dsd, "huynh": dhuynh}
 
 
-def vandermonde_matrix(N: int, r):
-    """Orthonormal-Legendre Vandermonde matrix (src/Transform/transform.jl:18-26)."""
+def vandermonde_matrix(N, r, *rest):
+    """Orthonormal-Legendre Vandermonde matrix (src/Transform/transform.jl:18-26), or -- with the reference's
+    shape tag first -- ``vandermonde_matrix(Line, N, r)``, ``vandermonde_matrix(Tri, N, r, s)`` (:36-51) and
+    ``vandermonde_matrix(Quad, N, r, s)`` (:55-69, modes (i, j), j fastest)."""
+    if isinstance(N, type):
+        from . import unstruct as un
+
+        shape, N, r, rest = N, r, rest[0], rest[1:]
+        if shape is un.Line:
+            return vandermonde_matrix(N, r)
+        if shape is un.Tri:
+            return un.simplex_vandermonde(N, r, rest[0])
+        if shape is un.Quad:
+            Vr, Vs = vandermonde_matrix(N, r), vandermonde_matrix(N, rest[0])
+            return np.einsum("pa,pb->pab", Vr, Vs).reshape(len(np.atleast_1d(r)), (N + 1) ** 2)
+        raise NotImplementedError(f"vandermonde_matrix for {shape.__name__}")
     r = np.asarray(r, dtype=np.float64)
     return np.stack([np.sqrt((2 * j + 1) / 2.0) * L.Legendre.basis(j)(r) for j in range(N + 1)], axis=1)
 

@@ -32,6 +32,9 @@ from .spaces import gausslegendre
 __all__ = [
     "read_msh", "UnstructPSpace", "UnstructFRPSpace", "TriFRPSpace", "tri_quadrature", "triface_quadrature",
     "simplex_vandermonde", "dsimplex_vandermonde", "rs_xy", "wsj_points",
+    "AbstractElementShape", "Line", "Quad", "Tri", "Hex", "Wed", "Pyr", "Tet",
+    "JacobiP", "dJacobiP", "simplex_basis", "dsimplex_basis", "correction_field", "global_fp", "global_sp_tri",
+    "neighbor_fpidx",
 ]
 
 # ------------------------------------------------------------------------------------------------
@@ -182,6 +185,125 @@ def simplex_vandermonde(deg: int, r, s):
 def dsimplex_vandermonde(deg: int, r, s):
     """∂vandermonde_matrix(Tri, N, r, s) -> (Vr, Vs)."""
     return _simplex(deg, r, s, True)
+
+
+# ------------------------------------------------------------------------------------------------
+# the reference's exported names for the same objects (src/FluxReconstruction.jl:19-51), on top of the
+# constructions above: setup-time helpers, nothing here runs per stage
+class AbstractElementShape:
+    """src/data.jl:4-11: tags the reference dispatches ``vandermonde_matrix(Tri, N, r, s)`` etc. on."""
+
+
+class Line(AbstractElementShape):
+    pass
+
+
+class Quad(AbstractElementShape):
+    pass
+
+
+class Tri(AbstractElementShape):
+    pass
+
+
+class Hex(AbstractElementShape):
+    pass
+
+
+class Wed(AbstractElementShape):
+    pass
+
+
+class Pyr(AbstractElementShape):
+    pass
+
+
+class Tet(AbstractElementShape):
+    pass
+
+
+def _jacobi_norm(n: int, alpha: float, beta: float) -> float:
+    """gamma_n = int_{-1}^{1} (1-x)^alpha (1+x)^beta P_n^2 dx of the classical polynomial."""
+    from math import exp, lgamma, log
+
+    ab = alpha + beta
+    lg = (ab + 1.0) * log(2.0) - log(2.0 * n + ab + 1.0) + lgamma(n + alpha + 1.0) + lgamma(n + beta + 1.0) \
+        - lgamma(n + ab + 1.0) - lgamma(n + 1.0)
+    return exp(lg)
+
+
+def JacobiP(x, alpha, beta, N):
+    """JacobiP(x, alpha, beta, N) (src/Polynomial/poly_jacobi.jl:7-84): the *orthonormal* Jacobi polynomial
+    of degree N at x (scalar or array) -- the classical one divided by sqrt(gamma_N)."""
+    return _jacobi(int(N), float(alpha), float(beta), x) / np.sqrt(_jacobi_norm(int(N), float(alpha), float(beta)))
+
+
+def dJacobiP(r, alpha, beta, N):
+    """∂JacobiP (poly_jacobi.jl:88-110): sqrt(N (N + alpha + beta + 1)) JacobiP(r, alpha+1, beta+1, N-1)."""
+    r = np.asarray(r, dtype=np.float64)
+    if N == 0:
+        return np.zeros_like(r)
+    return np.sqrt(N * (N + alpha + beta + 1.0)) * JacobiP(r, alpha + 1.0, beta + 1.0, N - 1)
+
+
+def simplex_basis(a, b, i, j):
+    """simplex_basis(a, b, i, j) (src/Transform/transform_triangle.jl:8-20): mode (i, j) of the orthonormal
+    triangle basis in collapsed coordinates (a, b) = rs_ab(r, s)."""
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    return np.sqrt(2.0) * JacobiP(a, 0, 0, i) * JacobiP(b, 2 * i + 1, 0, j) * (1.0 - b) ** i
+
+
+def dsimplex_basis(a, b, i, j):
+    """∂simplex_basis(a, b, id, jd) -> (d/dr, d/ds) (transform_triangle.jl:22-69)."""
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    fa, dfa = JacobiP(a, 0, 0, i), dJacobiP(a, 0, 0, i)
+    gb, dgb = JacobiP(b, 2 * i + 1, 0, j), dJacobiP(b, 2 * i + 1, 0, j)
+    h = 0.5 * (1.0 - b)
+    hp = h ** (i - 1) if i > 0 else 1.0
+    dr = dfa * gb * hp
+    ds = dfa * gb * 0.5 * (1.0 + a) * hp
+    tmp = dgb * h**i
+    if i > 0:
+        tmp = tmp - 0.5 * i * gb * h ** (i - 1)
+    ds = ds + fa * tmp
+    return 2.0 ** (i + 0.5) * dr, 2.0 ** (i + 0.5) * ds
+
+
+def correction_field(N, V=None):
+    """correction_field(N, V) (src/Polynomial/poly_triangle.jl:1-28): phi[f, j, i] = sum_m wf[f, j]
+    psi_m(x_fj) psi_m(x_i) on the WSJ solution points (the argument V is recomputed there as well)."""
+    pl, _ = tri_quadrature(N)
+    pf, wf = triface_quadrature(N)
+    psif = simplex_vandermonde(N, pf[:, :, 0], pf[:, :, 1])
+    Vl = simplex_vandermonde(N, pl[:, 0], pl[:, 1])
+    return np.einsum("fj,fjm,im->fji", wf, psif, Vl)
+
+
+def global_sp_tri(points, cellid, N):
+    """global_sp(points, cellid, N) for triangles (src/Geometry/geo_points.jl:56-70): [ncell, np, 2];
+    cellid 0-based."""
+    pl, _ = tri_quadrature(N)
+    xy, cid = np.asarray(points, dtype=np.float64)[:, :2], np.asarray(cellid)
+    v1, v2, v3 = (xy[cid[:, k]][:, None, :] for k in range(3))
+    return rs_xy(pl[None, :, 0], pl[None, :, 1], v1, v2, v3)
+
+
+def global_fp(points, cellid, N):
+    """global_fp(points, cellid, N) (geo_points.jl:101-115): flux points [ncell, 3, N+1, 2]; cellid 0-based."""
+    pf, _ = triface_quadrature(N)
+    xy, cid = np.asarray(points, dtype=np.float64)[:, :2], np.asarray(cellid)
+    v1, v2, v3 = (xy[cid[:, k]][:, None, None, :] for k in range(3))
+    return rs_xy(pf[None, :, :, 0], pf[None, :, :, 1], v1, v2, v3)
+
+
+def neighbor_fpidx(IDs, ps, fpg=None):
+    """neighbor_fpidx((cell, face, point), ps, fpg) (src/Geometry/geo_neighbor.jl:8-60): the flux point of the
+    neighbouring cell that coincides with mine, as (cell, face, point) -- 0-based here, (-1, -1, -1) on a
+    boundary face (the reference returns (neighbor_cid <= 0, -1, -1)).  The reference searches the neighbour's
+    flux-point coordinates for an exact match; the space has the answer from the edge orientation already
+    (``ps.fpn``), which is what the kernels consume; ``fpg`` is accepted for signature parity."""
+    c, f, k = IDs
+    return tuple(int(v) for v in ps.fpn[c, f, k])
 
 
 def rs_xy(r, s, v1, v2, v3):

@@ -215,3 +215,51 @@ def test_reference_assets_read_here(name):
     assert all(tuple(sorted(e)) in edges for e in ps.cells["line"].tolist())
     L = ps.faceArea[ps.cellFaces]
     assert np.abs((ps.cellNormals * L[:, :, None]).sum(axis=1)).max() < 1e-12
+
+
+# ---------------------------------------------------------------- the reference's exported names
+def test_reference_exported_names_match_the_oracle_restatement(FR):
+    """JacobiP / ∂JacobiP / simplex_basis / ∂simplex_basis / correction_field / vandermonde_matrix(shape, ...) /
+    global_fp / neighbor_fpidx under the names src/FluxReconstruction.jl:19-51 exports, against the literal
+    restatements of oracle/fr_oracle.py and oracle/fr_oracle_tri.py."""
+    import fr_oracle as o
+    import fr_oracle_tri as t
+
+    x = np.linspace(-0.9, 0.9, 7)
+    for a, b, N in ((0, 0, 3), (1, 0, 2), (3, 0, 4), (2, 1, 0)):
+        assert np.abs(FR.JacobiP(x, a, b, N) - o.jacobi_p(x, a, b, N)).max() < 1e-13
+        assert np.abs(FR.dJacobiP(x, a, b, N) - o.djacobi_p(x, a, b, N)).max() < 1e-12
+    aa, bb = np.linspace(-0.8, 0.7, 5), np.linspace(-0.9, 0.6, 5)
+    for i, j in ((0, 0), (1, 0), (0, 2), (2, 1), (3, 0)):
+        assert np.abs(FR.simplex_basis(aa, bb, i, j) - np.ravel(t.simplex_basis(aa, bb, i, j))).max() < 1e-13
+        d, (dr, ds) = t.dsimplex_basis(aa, bb, i, j), FR.dsimplex_basis(aa, bb, i, j)
+        assert np.abs(dr - np.ravel(d[0])).max() < 1e-12 and np.abs(ds - np.ravel(d[1])).max() < 1e-12
+    for N in (1, 2, 3):
+        assert np.abs(FR.correction_field(N) - t.correction_field(N)).max() < 1e-12
+    # shape-tagged Vandermonde matrices (src/Transform/transform.jl:31-69)
+    r = FR.legendre_point(2)
+    rr, ss = np.meshgrid(r, r, indexing="ij")
+    ps2 = FR.FRPSpace2D(0.0, 1.0, 2, 0.0, 1.0, 2, 2, 1, 1)
+    assert np.abs(FR.vandermonde_matrix(FR.Quad, 2, rr.ravel(order="F"), ss.ravel(order="F")) - ps2.V).max() < 1e-14
+    assert np.array_equal(FR.vandermonde_matrix(FR.Line, 2, r), FR.vandermonde_matrix(2, r))
+    assert np.abs(FR.vandermonde_matrix(FR.Tri, 2, aa, bb) - t.vandermonde_tri(2, aa, bb)).max() < 1e-13
+    assert issubclass(FR.Tri, FR.AbstractElementShape) and issubclass(FR.Hex, FR.AbstractElementShape)
+
+
+def test_global_fp_and_neighbor_fpidx(FR):
+    pts = np.array([[0.0, 0.0], [1.0, 0.0], [1.0, 1.0], [0.0, 1.0]])
+    cid = np.array([[0, 1, 2], [0, 2, 3]])
+    ps = FR.UnstructFRPSpace((pts, cid), 2)
+    fpg = FR.global_fp(pts, cid, 2)
+    assert np.abs(fpg - ps.xfg).max() < 1e-15
+    assert np.abs(FR.global_sp_tri(pts, cid, 2) - ps.xpg).max() < 1e-15
+    # the coincident flux point of the neighbour: found by the reference through a coordinate search
+    for c in range(2):
+        for f in range(3):
+            for k in range(3):
+                nc, nf, nk = FR.neighbor_fpidx((c, f, k), ps, fpg)
+                if nc < 0:
+                    assert (nf, nk) == (-1, -1)
+                else:
+                    assert np.abs(fpg[nc, nf, nk] - fpg[c, f, k]).max() < 1e-14
+    assert sum(FR.neighbor_fpidx((c, f, 0), ps)[0] >= 0 for c in range(2) for f in range(3)) == 2
