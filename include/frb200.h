@@ -111,8 +111,9 @@ int32_t frb_euler2d_create(frb_ctx_t ctx, int32_t nx, int32_t ny, const frb_oper
  *       NULL: factors from the solution-point inverse Jacobian, (iJ[i,j][k,l] n)[c] (parallelogram.jl:145-148)
  * flags: FRB_CURV_FY_ROW_INDEX reproduces the scripts' fy_interaction[i,j,l,m] (row index where the
  * rectangular scripts use the flux-point index k, euler2d_wave.jl:100-103); FRB_CURV_WALL_XLO makes x face 1
- * the mirror wall of cylinder2.jl:100-120 (ghost column 0 is then never read).  HLL flux, deg 1..3, single
- * GPU; every frb_* call of an euler2d problem applies (f!, step, tableau, limiter, filter, ghost fill). */
+ * the mirror wall of cylinder2.jl:100-120 (ghost column 0 is then never read).  deg 1..3, single GPU; every
+ * frb_* call of an euler2d problem applies (f!, step, tableau, limiter, filter, ghost fill, frb_set_flux:
+ * the common flux acts in the face frame of the unit normal). */
 #define FRB_CURV_FY_ROW_INDEX 1
 #define FRB_CURV_WALL_XLO 2
 int32_t frb_euler2d_curv_create(frb_ctx_t ctx, int32_t nx, int32_t ny, const frb_operators *ops,
