@@ -25,8 +25,9 @@ Reference quirks that are restated literally and can be switched off:
 * both scripts index the y common flux with the *row* index in the correction step,
   ``fy_interaction[i, j, l, m]`` (parallelogram.jl:147-148, cylinder2.jl:157-158), where the rectangular
   scripts use the flux-point index ``k`` (euler2d_wave.jl:100-103) -- ``fy_index="l"`` is the scripts'
-  form, ``"k"`` the consistent one.  (parallelogram.jl:12: "Instability is somehow detected for order
-  larger than 2".)
+  form, ``"k"`` the consistent one.  With ``"l"`` the scheme is not conservative (sum of wp det(J) du over a
+  periodic sheared mesh is O(0.1) instead of 1e-16, tests/test_oracle_curv.py) -- parallelogram.jl:12:
+  "Instability is somehow detected for order larger than 2".
 * ``Ji``: ``rs_jacobi(ri, si, vertices)`` with matrix arguments evaluates ``rs_jacobi(r[i], s[i], ...)``
   with the *linear* index ``i`` over the 4 faces for every flux point ``j`` (geo_jacobi.jl:93-94), and the
   face tables put 0.0 where -1.0 is meant (struct.jl:149,152).  ``flux_point_jacobi(..., literal=True)``

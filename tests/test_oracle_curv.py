@@ -96,6 +96,27 @@ def test_free_stream_on_the_parallelogram(deg, fy):
     assert np.abs(du).max() < 1e-12
 
 
+@pytest.mark.parametrize("deg", [1, 2, 3])
+def test_conservation_on_a_periodic_sheared_mesh(deg):
+    """sum over the mesh of wp det(J) du vanishes for every variable when the y common flux is indexed by the
+    flux point (k); the scripts' row index (l, dev/parallelogram.jl:147-148) loses conservation at O(1) -- what
+    the script's header reports as "instability is somehow detected for order larger than 2"."""
+    nx, ny = 6, 5
+    ps = c.CurvSpace2D(sheared_vertices(nx, ny, 1.0, 0.5, 1.0), deg)
+    n1 = np.empty((nx + 1, ny, 2))
+    n1[..., 0], n1[..., 1] = np.cos(-np.pi / 4), np.sin(-np.pi / 4)
+    n2 = np.zeros((nx, ny + 1, 2))
+    n2[..., 1] = 1.0
+    u = c.ghost_fill_periodic(rand_state((nx + 2, ny + 2, deg + 1, deg + 1), 5))
+    det = ps.J[..., 0, 0] * ps.J[..., 1, 1] - ps.J[..., 0, 1] * ps.J[..., 1, 0]
+    total = {}
+    for fy in "kl":
+        du = c.rhs_euler2d_curv(u, ps, n1, n2, GAMMA, fy_index=fy)
+        total[fy] = np.einsum("ijklm,kl,ijkl->m", du[1:-1, 1:-1], ps.wp, det[1:-1, 1:-1])
+    assert np.abs(total["k"]).max() < 1e-13
+    assert np.abs(total["l"]).max() > 1e-2
+
+
 def test_converges_to_the_flux_divergence_on_a_sheared_mesh():
     """rho_t = -(U rho_x + V rho_y) for a density wave carried by a uniform flow at constant pressure."""
     U, V, deg = 0.8, 0.5, 2
