@@ -2,8 +2,11 @@
 
     python scripts/probe_curv.py [nx ny deg iters]
 
-Prints one JSON line per stage kind: ms per fused stage (face + element kernel), DOF-updates/s and the
-algorithmic bandwidth (16 / 24 B of state + 8 B of metric per DOF-update).
+Prints one JSON line per stage kind: ms per fused stage (face + element kernel), DOF-updates/s and a
+`roofline` object like bench.py's: achieved = algorithmic bytes (16 / 24 B of state + 8 B of metric per
+DOF-update) / stage time, peak = the measured HBM copy bandwidth of MEASURED_PEAKS.json
+(fallback: B200_PROFILING.md), traffic = the DRAM bytes per stage of the committed ncu capture
+(profiles/r01_curv.md; 1024^2 p3, 16-B stage only).
 """
 import json
 import os
@@ -14,6 +17,25 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import frb200 as FR  # noqa: E402
+
+
+def measured_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
+            return float(json.load(fh)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def line(workload, dofs, state_bytes, ms, traffic=None):
+    """The JSON record of one measurement (pure function: tests/test_bench_contract.py checks it on the CPU)."""
+    peak, src = measured_peak()
+    achieved = dofs * (state_bytes + 8) / ms / 1e6  # GB/s
+    return {"workload": workload, "stage_bytes_per_dof": state_bytes + 8, "ms_per_stage": round(ms, 4),
+            "gdof_per_s": round(dofs / ms / 1e6, 2), "algorithmic_GBps": round(achieved, 1),
+            "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
+                         "frac": round(achieved / peak, 4), "traffic": traffic, "peak_source": src,
+                         "kernel": "euler2d_curv_face_kernel + euler2d_curv_elem_kernel (2 launches per stage)"}}
 
 
 def main():
@@ -34,11 +56,9 @@ def main():
         for kind, state_bytes in ((0, 16), (1, 24)):
             prob.time_stage(kind, 3)
             ms = prob.time_stage(kind, iters)
-            print(json.dumps({
-                "workload": f"curv euler2d {nx}x{ny} p{deg} corr={corr} metric={metric}",
-                "stage_bytes_per_dof": state_bytes + 8,
-                "ms_per_stage": round(ms, 4), "gdof_per_s": round(dofs / ms / 1e6, 2),
-                "algorithmic_GBps": round(dofs * (state_bytes + 8) / ms / 1e6, 1)}), flush=True)
+            captured = (nx, ny, deg, kind, corr, metric) == (1024, 1024, 3, 0, "sp", "stored")
+            print(json.dumps(line(f"curv euler2d {nx}x{ny} p{deg} corr={corr} metric={metric}", dofs, state_bytes, ms,
+                                  2.709e9 if captured else None)), flush=True)
         prob.close()
 
 

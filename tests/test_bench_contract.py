@@ -27,3 +27,19 @@ def test_reference_arm_is_silent_on_other_ranks():
     r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1",
                         "--warmup", "0", "--ref-n", "32"], capture_output=True, text=True, timeout=600, env=env)
     assert r.returncode == 0 and r.stdout.strip() == ""
+
+
+def test_curv_probe_record_has_the_roofline_object():
+    """scripts/probe_curv.py prints bench.py's roofline object for the curvilinear path (pure function, no GPU)."""
+    import importlib.util as u
+    import os
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = u.spec_from_file_location("probe_curv", os.path.join(root, "scripts", "probe_curv.py"))
+    m = u.module_from_spec(spec)
+    spec.loader.exec_module(m)
+    rec = m.line("w", 67108864, 16, 0.5, 2.7e9)
+    roof = rec["roofline"]
+    assert rec["stage_bytes_per_dof"] == 24 and abs(rec["gdof_per_s"] - 134.22) < 0.01
+    assert roof["bound"] == "hbm" and roof["unit"] == "GB/s" and roof["traffic"] == 2.7e9
+    assert abs(roof["frac"] - roof["achieved"] / roof["peak"]) < 1e-4 and 3000 < roof["achieved"] < 3400
