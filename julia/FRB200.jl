@@ -108,7 +108,6 @@ function Euler2DCurvProblem(u0, ps, γ, n1, n2; fp = false, wall = false, litera
     p = finalizer(destroy!, Problem(r[], size(A), keep)); upload!(p, A); p
 end
 
-# mol! of example/bgk_wave.jl:69-129
 # dev/sod.jl:124-127: p = (ps.cellType, ps.J, ps.lf, ps.cellNormals, ps.fpn, ps.∂l, ps.ϕ, γ) of a TriFRPSpace
 function TriEulerProblem(u0::Array{Float64,3}, ps, γ)
     ncell = size(u0, 1)
@@ -125,6 +124,7 @@ end
 # example/advection_kinetic.jl:73-128: the same mol! relaxing towards the Maxwellian of prim = [ρ, a, 1.0]
 kinetic_advection!(p::Problem, a = 1.0) = check(ccall((:frb_bgk1d_set_model, lib), Int32,
     (Ptr{Cvoid}, Int32, Float64), p.h, 1, a))
+# mol! of example/bgk_wave.jl:69-129
 function BGKProblem(f0::Array{Float64,3}, ps, velo, weights, τ = 1e-2)
     ops, keep = operators(ps)
     dx = Vector{Float64}(ps.dx[1:size(f0, 1)]); v = Vector{Float64}(velo); w = Vector{Float64}(weights)
@@ -133,6 +133,41 @@ function BGKProblem(f0::Array{Float64,3}, ps, velo, weights, τ = 1e-2)
         (Ptr{Cvoid}, Int32, Int32, Ref{Operators}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Float64, Ref{Ptr{Cvoid}}),
         ctx().h, size(f0, 1), size(f0, 2), ops, dx, v, w, τ, r))
     p = finalizer(destroy!, Problem(r[], size(f0), keep)); upload!(p, f0); p
+end
+
+# dudt! + boundary! of example/ns_cavity.jl:147-344 (gas-kinetic flux :49-145).  u0 is the OffsetArray
+# 4 x nsp x nsp x 0:ny+1 x 0:nx+1 of the script (:33); gas = ks.gas (K, γ, μᵣ, ω); dt enters the time-averaged
+# interface flux; lid = pb[2] of :337; λ0 the wall 1/T of boundary!(u, p, 1.0)
+function NSCavityProblem(u0, ps, gas, dt; lid = 0.15, λ0 = 1.0)
+    A = parent(u0)::Array{Float64,5}
+    ops, keep = operators(ps)
+    Jx, Jy = ps.J[1, 1][1, 1][1, 1], ps.J[1, 1][1, 1][2, 2]
+    r = Ref{Ptr{Cvoid}}(C_NULL)
+    GC.@preserve keep check(ccall((:frb_ns2d_create, lib), Int32,
+        (Ptr{Cvoid}, Int32, Int32, Ref{Operators}, Float64, Float64, Float64, Float64, Float64, Float64, Float64,
+         Float64, Float64, Ref{Ptr{Cvoid}}),
+        ctx().h, size(A, 5) - 2, size(A, 4) - 2, ops, Jx, Jy, gas.K, gas.γ, gas.μᵣ, gas.ω, dt, lid, λ0, r))
+    p = finalizer(destroy!, Problem(r[], size(A), keep)); upload!(p, A); p
+end
+
+# the curvilinear metric evaluated on the fly from ps.base.vertices and ps.xpl instead of the stored ps.iJ
+function set_vertices!(p::Problem, ps)
+    V = Array{Float64}(parent(ps.base.vertices)); r = Vector{Float64}(ps.xpl)
+    GC.@preserve V r check(ccall((:frb_euler2d_curv_set_vertices, lib), Int32,
+        (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}), p.h, V, r))
+end
+
+state_len(p::Problem) = ccall((:frb_state_len, lib), Int64, (Ptr{Cvoid},), p.h)
+interior_dofs(p::Problem) = ccall((:frb_interior_dofs, lib), Int64, (Ptr{Cvoid},), p.h)
+function device_ptr(p::Problem)      # raw device address of the resident state (CUDA.jl interop: unsafe_wrap(CuArray, ...))
+    r = Ref{Ptr{Float64}}(C_NULL)
+    check(ccall((:frb_state_device_ptr, lib), Int32, (Ptr{Cvoid}, Ref{Ptr{Float64}}), p.h, r)); r[]
+end
+function device_info(c::Context = ctx())
+    sm, ma, mi = Ref{Int32}(0), Ref{Int32}(0), Ref{Int32}(0); name = zeros(UInt8, 128)
+    check(ccall((:frb_device_info, lib), Int32, (Ptr{Cvoid}, Ref{Int32}, Ref{Int32}, Ref{Int32}, Ptr{UInt8}, Int32),
+                c.h, sm, ma, mi, name, 128))
+    (sm_count = sm[], cc = (ma[], mi[]), name = unsafe_string(pointer(name)))
 end
 
 upload!(p::Problem, u) = GC.@preserve u check(ccall((:frb_state_upload, lib), Int32, (Ptr{Cvoid}, Ptr{Float64}), p.h, parent(u)))
@@ -148,16 +183,39 @@ rhs!(prob::Problem) = function (du, u, p, t)
     nothing
 end
 
+# the same with pinned host buffers streamed through the device in row slabs (2-D Euler): upload, residual and
+# download overlap
+rhs_pipelined!(prob::Problem; nslab = 32) = function (du, u, p, t)
+    GC.@preserve du u check(ccall((:frb_rhs_pipelined, lib), Int32, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Int32),
+                                  prob.h, parent(u), parent(du), nslab))
+    nothing
+end
+# page-locked host arrays for the host-buffer paths
+function host_array(dims::Dims)
+    r = Ref{Ptr{Cvoid}}(C_NULL)
+    check(ccall((:frb_host_alloc, lib), Int32, (Int64, Ref{Ptr{Cvoid}}), 8 * prod(dims), r))
+    unsafe_wrap(Array, Ptr{Float64}(r[]), dims)
+end
+host_free(a::Array{Float64}) = check(ccall((:frb_host_free, lib), Int32, (Ptr{Cvoid},), pointer(a)))
+
 const SCHEME = Dict(:euler => 0, :midpoint => 1, :ssprk3 => 2)
 const GHOST = Dict(:none => -1, :wave_x => 0, :wave_y => 1, :copy => 2, :periodic => 3, :cylinder => 4)
 set_step_hooks!(p::Problem; ghost = :none, limiter_weights = nothing) = check(ccall((:frb_set_step_hooks, lib), Int32,
     (Ptr{Cvoid}, Int32, Ptr{Float64}), p.h, GHOST[ghost], limiter_weights === nothing ? C_NULL : pointer(limiter_weights)))
+ghost_fill!(p::Problem, mode::Symbol) = check(ccall((:frb_ghost_fill, lib), Int32, (Ptr{Cvoid}, Int32), p.h, GHOST[mode]))
 # shock sensor + modal filter on every element (euler_highlevel.jl:37-52, shock-vortex.jl:308-321):
 # F = ps.V * Diagonal(filterdiag) * ps.iV is built here from whatever KitBase filter the caller uses
 function modal_filter!(p::Problem, iV::Matrix{Float64}, F::Matrix{Float64}; eps = 1e-6, S0, kappa = 4.0, ghosts = false)
     n = Ref{Int32}(0)
     check(ccall((:frb_filter_modal, lib), Int32, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Int32, Float64, Float64,
         Float64, Int32, Ref{Int32}), p.h, iV, F, size(iV, 1), eps, S0, kappa, ghosts ? 1 : 0, n)); n[]
+end
+# the same pass as a hook of step!: when = :before (euler_highlevel.jl:37-52), :after (shock-vortex.jl:308-321), :off
+function set_filter_hook!(p::Problem, when::Symbol, iV::Matrix{Float64}, F::Matrix{Float64}; eps = 1e-6, S0, kappa = 4.0,
+                          ghosts = false)
+    check(ccall((:frb_set_filter_hook, lib), Int32, (Ptr{Cvoid}, Int32, Ptr{Float64}, Ptr{Float64}, Int32, Float64,
+        Float64, Float64, Int32), p.h, Dict(:off => 0, :before => 1, :after => 2)[when], iV, F, size(iV, 1), eps, S0,
+        kappa, ghosts ? 1 : 0))
 end
 # common flux of the Euler problems: :hll (the reference's flux_hll!), :lf, :roe
 set_flux!(p::Problem, flux::Symbol) = check(ccall((:frb_set_flux, lib), Int32, (Ptr{Cvoid}, Int32), p.h,
@@ -173,5 +231,37 @@ function positive_limiter!(p::Problem, weights)      # src/dissipation.jl:61-206
     nbad = Ref{Int32}(0)
     check(ccall((:frb_limiter_positivity, lib), Int32, (Ptr{Cvoid}, Ptr{Float64}, Ref{Int32}), p.h, weights, nbad)); nbad[]
 end
+
+
+# ---- measurement ----------------------------------------------------------------------------------------------
+set_kernel!(p::Problem, kind::Symbol) = check(ccall((:frb_set_kernel, lib), Int32, (Ptr{Cvoid}, Int32), p.h,
+    Int32(Dict(:auto => 0, :generic => 1, :march => 2, :rc => 3)[kind])))
+function time_stage(p::Problem, stage_kind::Integer = 1, iters::Integer = 10)   # ms per fused stage launch
+    ms = Ref{Float32}(0)
+    check(ccall((:frb_time_stage, lib), Int32, (Ptr{Cvoid}, Int32, Int32, Ref{Float32}), p.h, stage_kind, iters, ms)); ms[]
+end
+function last_timing(p::Problem)                                                # (device ms, kernels) of the last call
+    ms, n = Ref{Float32}(0), Ref{Int64}(0)
+    check(ccall((:frb_last_timing, lib), Int32, (Ptr{Cvoid}, Ref{Float32}, Ref{Int64}), p.h, ms, n)); (ms[], n[])
+end
+set_profiling!(p::Problem, on::Bool = true) = check(ccall((:frb_set_profiling, lib), Int32, (Ptr{Cvoid}, Int32), p.h, on ? 1 : 0))
+function stage_timing(p::Problem)
+    ms, n = Ref{Float32}(0), Ref{Int64}(0)
+    check(ccall((:frb_stage_timing, lib), Int32, (Ptr{Cvoid}, Ref{Float32}, Ref{Int64}), p.h, ms, n)); (ms[], n[])
+end
+
+# ---- multi-GPU: one Julia process per GPU (e.g. under MPI.jl), slabs along the slowest cell index ---------------
+# euler2d problems: rows; ns2d problems: columns.  Exchange the 328-byte blobs by any means (MPI.Allgather), then
+# connect to the ranks below (rank-1 mod n) and above (rank+1 mod n); per-stage halo traffic never touches the host.
+const HALO_BLOB_BYTES = 5 * 64 + 8
+function halo_export(p::Problem)
+    blob = zeros(UInt8, HALO_BLOB_BYTES)
+    check(ccall((:frb_halo_export, lib), Int32, (Ptr{Cvoid}, Ptr{UInt8}), p.h, blob)); blob
+end
+halo_connect!(p::Problem, rank::Integer, nranks::Integer, blob_lo::Vector{UInt8}, blob_hi::Vector{UInt8}) =
+    check(ccall((:frb_halo_connect, lib), Int32, (Ptr{Cvoid}, Int32, Int32, Ptr{UInt8}, Ptr{UInt8}),
+                p.h, rank, nranks, blob_lo, blob_hi))
+halo_sync!(p::Problem) = check(ccall((:frb_halo_sync, lib), Int32, (Ptr{Cvoid},), p.h))        # after a new upload!
+halo_disconnect!(p::Problem) = check(ccall((:frb_halo_disconnect, lib), Int32, (Ptr{Cvoid},), p.h))
 
 end # module

@@ -94,3 +94,45 @@ def test_product_package_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 txt = open(os.path.join(dirpath, f)).read()
                 assert "fr_oracle" not in txt and "c_oracle" not in txt and "fro_" not in txt, f
+
+
+def test_julia_shim_binds_every_entry_point():
+    """julia/FRB200.jl (the host language the north star names; Julia is not in the image, so the file cannot
+    be executed here) has a ccall for every function include/frb200.h declares, with as many argument types as
+    the ctypes twin that the tests exercise."""
+    import re as _re
+
+    src = open(os.path.join(ROOT, "julia", "FRB200.jl")).read()
+    for name in declared_symbols():
+        assert f"(:{name}, lib)" in src, f"{name} has no ccall in julia/FRB200.jl"
+    assert src.count("(") == src.count(")") and src.count("[") == src.count("]")
+
+    def split_top(t):
+        out, d, cur = [], 0, ""
+        for ch in t:
+            d += ch in "([{"
+            d -= ch in ")]}"
+            if ch == "," and d == 0:
+                out.append(cur.strip())
+                cur = ""
+            else:
+                cur += ch
+        return out + ([cur.strip()] if cur.strip() else [])
+
+    import frb200 as FR
+
+    for m in _re.finditer(r"ccall\(\(:(frb_[a-z0-9_]+), lib\),", src):
+        i = j = m.start() + len("ccall")
+        d = 0
+        while True:  # the matching parenthesis of ccall(
+            d += src[j] == "("
+            d -= src[j] == ")"
+            if d == 0:
+                break
+            j += 1
+        parts = split_top(src[i + 1: j])  # (:name, lib), Ret, (types...), args...
+        want = len(FR.SIGNATURES[m.group(1)][1])
+        assert len(split_top(parts[2][1:-1])) == want and len(parts) - 3 == want, m.group(1)
+    blocks = len(_re.findall(r"^\s*(?:function|struct|mutable struct|module)\b", src, flags=_re.M))
+    blocks += len(_re.findall(r"=\s*function\s*\(", src))
+    assert blocks == len(_re.findall(r"^\s*end\b", src, flags=_re.M))
