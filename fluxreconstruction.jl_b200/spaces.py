@@ -346,14 +346,14 @@ class FRPSpace2D:
         self.xpl = r
         rr, ss = np.meshgrid(r, r, indexing="ij")  # [k, l]: k <-> r, l <-> s (struct.jl:169-174)
         self._J = np.asfortranarray(quad_jacobians(self.vertices, rr, ss))
-        self.iJ = np.asfortranarray(_inv2(self._J))
+        self._iJ = np.asfortranarray(_inv2(self._J))
         if literal_Ji:  # one point per face: (ri[face, 1], si[face, 1]) of the tables at struct.jl:145-155
             fr = np.repeat(np.array([r[0], 1.0, r[-1], 0.0])[:, None], nsp, axis=1)
             fs = np.repeat(np.array([0.0, r[0], 1.0, r[-1]])[:, None], nsp, axis=1)
         else:  # faces 1..4: s = -1, r = +1, s = +1, r = -1, points in trace order
             one = np.ones(nsp)
             fr, fs = np.stack([r, one, r, -one]), np.stack([-one, r, one, r])
-        self.Ji = np.asfortranarray(quad_jacobians(self.vertices, fr, fs))
+        self._Ji = np.asfortranarray(quad_jacobians(self.vertices, fr, fs))
         # bilinear map of the solution points (struct.jl:161-175)
         N = np.stack([(rr - 1) * (ss - 1), (rr + 1) * (1 - ss), (rr + 1) * (ss + 1), (1 - rr) * (ss + 1)], -1) / 4.0
         self.xpg = np.asfortranarray(np.einsum("ijvc,klv->ijklc", self.vertices, N))
@@ -376,3 +376,36 @@ class FRPSpace2D:
         J[..., 0, 0] = self.Jx
         J[..., 1, 1] = self.Jy
         return J
+
+    @property
+    def vertices(self):
+        """ps.vertices[i, j, 4, 2] (forwarded from the base space, tools.jl:5-22), counter-clockwise from the
+        lower left corner."""
+        if "_vertices" not in self.__dict__:
+            self._vertices = PSpace2D(self.x0, self.x1, self.nx, self.y0, self.y1, self.ny, self.ngx, self.ngy).vertices
+        return self._vertices
+
+    @vertices.setter
+    def vertices(self, v):
+        self._vertices = v
+
+    @property
+    def iJ(self):
+        """ps.iJ[i,j][k,l] (struct.jl:137-142): the point-wise inverse, (nxg, nyg, nsp, nsp, 2, 2)."""
+        if hasattr(self, "_iJ"):
+            return self._iJ
+        iJ = np.zeros_like(self.J)
+        iJ[..., 0, 0] = 1.0 / self.Jx
+        iJ[..., 1, 1] = 1.0 / self.Jy
+        return iJ
+
+    @property
+    def Ji(self):
+        """ps.Ji[i,j][face, pt] (struct.jl:145-158): Jacobians at the flux points, (nxg, nyg, 4, nsp, 2, 2)."""
+        if hasattr(self, "_Ji"):
+            return self._Ji
+        nsp = self.deg + 1
+        Ji = np.zeros((self.nx + 2 * self.ngx, self.ny + 2 * self.ngy, 4, nsp, 2, 2), order="F")
+        Ji[..., 0, 0] = self.Jx
+        Ji[..., 1, 1] = self.Jy
+        return Ji

@@ -56,3 +56,16 @@ def test_interp_and_derivative_identities(FR):
         assert abs(r**q @ ps.ll - (-1.0) ** q) < 1e-13 and abs(r**q @ ps.lr - 1.0) < 1e-13
         d = ps.dl @ r**q
         assert np.allclose(d, q * r ** max(q - 1, 0) if q else 0 * r, atol=1e-12)
+
+
+def test_rectangular_space_carries_the_pointwise_metric(FR):
+    """ps.iJ, ps.Ji and ps.vertices exist on the rectangular FRPSpace2D too (struct.jl:99-128; example/shock-vortex.jl
+    reads ps.iJ) and equal what FRPSpace2D(base, deg) computes from the vertices."""
+    ps = FR.FRPSpace2D(0.0, 1.0, 6, 0.0, 0.5, 4, 2, 1, 1)
+    pb = FR.FRPSpace2D(FR.PSpace2D(0.0, 1.0, 6, 0.0, 0.5, 4, 1, 1), 2)
+    assert ps.iJ.shape == (8, 6, 3, 3, 2, 2) and ps.Ji.shape == (8, 6, 4, 3, 2, 2)
+    for name in ("J", "iJ", "Ji", "vertices", "xpg"):
+        a, b = getattr(ps, name), getattr(pb, name)
+        assert np.abs(a - b).max() <= 1e-14 * np.abs(b).max(), name
+    n1, n2 = FR.face_normals(ps.vertices)
+    assert np.allclose(n1, [1.0, 0.0]) and np.allclose(n2, [0.0, 1.0])
