@@ -148,6 +148,27 @@ def test_parallelogram_steps(FR, scheme):
     prob.close()
 
 
+def test_parallelogram_1000_steps(FR):
+    """The north star's second tolerance on this path: <= 1e-9 relative after 1000 steps (the script's Euler forward,
+    dt = 0.001, to t = 1).  With the flux-point index k the run is stable (a 1e-15 perturbation of the data grows 12 x);
+    the scripts' row index l turns non-finite before t = 1 in the oracle as well, so there is nothing to compare."""
+    nx, ny, deg, dt, nsteps = 30, 15, 1, 0.001, 1000
+    ps, po, (n1, n2) = parallelogram(FR, nx, ny, deg)
+    u0 = np.empty((nx + 2, ny + 2, deg + 1, deg + 1, 4), order="F")
+    for i in range(nx + 2):
+        rho = 1.0 + 0.1 * np.sin(2 * np.pi * i / nx)
+        u0[i] = o.prim_conserve(np.array([rho, 1.0, 0.0, rho]), GAMMA)
+    prob = FR.Euler2DCurvProblem(u0, (0.0, 1.0), ps, GAMMA, n1, n2, corr="sp", fy_index="k")
+    itg = FR.init(prob, FR.Euler(), dt=dt)
+    itg.set_hooks(ghost="periodic")
+    FR.step_(itg, nsteps)
+    rhs = lambda w: c.rhs_euler2d_curv(w, po, n1, n2, GAMMA, corr="sp", fy_index="k")  # noqa: E731
+    ref = o.integrate(u0, dt, nsteps, rhs, "euler", before_step=c.ghost_fill_periodic)
+    assert np.isfinite(ref).all()
+    assert rel(itg.u, ref) <= 1e-9
+    prob.close()
+
+
 def test_cylinder_steps(FR):
     """dev/cylinder2.jl:170-190: mirror rows in theta, outflow copy on half of the outer column, Euler steps.
     The script's own case (uniform Mach-1 flow against the wall) loses positivity next to the wall at its 17th
