@@ -19,7 +19,7 @@ _dp = C.POINTER(C.c_double)
 
 def build(force: bool = False) -> str:
     so = os.path.join(_HERE, "libfr_oracle.so")
-    srcs = [os.path.join(_HERE, f) for f in ("fr_oracle.c", "fr_oracle_gks.c", "Makefile")]
+    srcs = [os.path.join(_HERE, f) for f in ("fr_oracle.c", "fr_oracle_gks.c", "fr_oracle_curv.c", "Makefile")]
     stale = (not os.path.exists(so)) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs)
     if force or stale:
         subprocess.run(["make", "-C", _HERE, "-B", "libfr_oracle.so"], check=True, capture_output=True)
@@ -245,3 +245,25 @@ def integrate_ns2d(u, ps, K, gamma, mu, omega, dt, nsteps, lam0=1.0, lid=0.15):
                                   C.c_double(ps.Jy), *[_p(x) for x in ops], *scal, int(nsteps))
     assert rc == 0
     return u
+
+
+def rhs_euler2d_curv(u, ps, n1, n2, gamma, corr="sp", fpc=None, fy_index="l", wall_xlo=False):
+    """dudt! of dev/parallelogram.jl:80-165 / dev/cylinder2.jl:52-164 (oracle/fr_oracle_curv.c); same arguments
+    as fr_oracle_curv.rhs_euler2d_curv (HLL)."""
+    u = np.asfortranarray(u, dtype=np.float64)
+    du = np.zeros_like(u, order="F")
+    nx, ny, nsp = u.shape[0] - 2, u.shape[1] - 2, u.shape[2]
+    iJ = np.asfortranarray(ps.iJ, dtype=np.float64)
+    n1, n2 = np.asfortranarray(n1, dtype=np.float64), np.asfortranarray(n2, dtype=np.float64)
+    assert iJ.shape == u.shape[:4] + (2, 2) and n1.shape == (nx + 1, ny, 2) and n2.shape == (nx, ny + 1, 2)
+    fp = None
+    if corr == "fp":
+        fp = np.asfortranarray(fpc, dtype=np.float64)
+        assert fp.shape == (nx, ny, nsp, 4)
+    ll, lr, dl, dhl, dhr = _ops(ps)
+    fn = lib().fro_rhs_euler2d_curv
+    fn.argtypes = [_dp, _dp, C.c_int, C.c_int, C.c_int, _dp, _dp, _dp, _dp, C.c_int, C.c_double] + [_dp] * 5
+    rc = fn(_p(u), _p(du), nx, ny, nsp, _p(iJ), _p(n1), _p(n2), None if fp is None else _p(fp),
+            (1 if fy_index == "l" else 0) | (2 if wall_xlo else 0), gamma, _p(ll), _p(lr), _p(dl), _p(dhl), _p(dhr))
+    assert rc == 0
+    return du

@@ -168,6 +168,28 @@ def test_cylinder_ghost_fill():
     assert np.array_equal(u[nr, nth // 2 + 1 : nth + 1], ref[nr, nth // 2 + 1 : nth + 1])
 
 
+@pytest.mark.parametrize("deg", [1, 2, 3])
+def test_c_restatement_equals_the_numpy_one(coracle, deg):
+    """oracle/fr_oracle_curv.c (the fast checker for large meshes) against oracle/fr_oracle_curv.py."""
+    nx, ny = 7, 5
+    ps = c.CurvSpace2D(c.parallelogram_vertices(nx, ny), deg)
+    n1, n2 = c.parallelogram_normals(nx, ny)
+    u = rand_state((nx + 2, ny + 2, deg + 1, deg + 1), 21)
+    for fy in "kl":
+        a = c.rhs_euler2d_curv(u, ps, n1, n2, GAMMA, corr="sp", fy_index=fy)
+        assert rel(coracle.rhs_euler2d_curv(u, ps, n1, n2, GAMMA, corr="sp", fy_index=fy), a) < 1e-14
+    nr, nth = 6, 8
+    vv, dth = c.cspace2d_vertices(1.0, 6.0, nr, 0.0, np.pi, nth, 0, 1)
+    ps = c.CurvSpace2D(c.embed_cylinder(vv), deg)
+    n1, n2 = c.cylinder_normals(nr, nth, dth[0])
+    n1, n2 = n1[:nr], n2[: nr - 1]
+    fpc = c.corr_factors_fp(ps.Ji, n1, n2)
+    u = rand_state((nr + 1, nth + 2, deg + 1, deg + 1), 22)
+    for fy in "kl":
+        kw = dict(corr="fp", fpc=fpc, fy_index=fy, wall_xlo=True)
+        assert rel(coracle.rhs_euler2d_curv(u, ps, n1, n2, GAMMA, **kw), c.rhs_euler2d_curv(u, ps, n1, n2, GAMMA, **kw)) < 1e-14
+
+
 # ------------------------------------------------------------------------------- host mirror
 @pytest.mark.parametrize("deg", [1, 2, 3])
 def test_host_space_matches_the_oracle(FR, deg):
