@@ -30,7 +30,7 @@ import numpy as np
 from .spaces import gausslegendre
 
 __all__ = [
-    "read_msh", "UnstructPSpace", "UnstructFRPSpace", "TriFRPSpace", "tri_quadrature", "triface_quadrature",
+    "read_msh", "read_su2", "read_mesh", "UnstructPSpace", "UnstructFRPSpace", "TriFRPSpace", "tri_quadrature", "triface_quadrature",
     "simplex_vandermonde", "dsimplex_vandermonde", "rs_xy", "wsj_points",
     "AbstractElementShape", "Line", "Quad", "Tri", "Hex", "Wed", "Pyr", "Tet",
     "JacobiP", "dJacobiP", "simplex_basis", "dsimplex_basis", "correction_field", "global_fp", "global_sp_tri",
@@ -396,6 +396,68 @@ def read_msh(path):
     return points, cells
 
 
+# SU2 native mesh format (the reference ships assets/linesource.su2; KitBase reads it through meshio):
+# NDIME / NELEM + connectivity rows "vtk_type n0 n1 ... [index]" / NPOIN + coordinate rows "x y [z] [index]" /
+# NMARK, then per marker MARKER_TAG, MARKER_ELEMS and its boundary elements.  0-based node indices.
+_SU2_NODES = {3: ("line", 2), 5: ("triangle", 3), 9: ("quad", 4)}
+
+
+def read_su2(path):
+    """Reads an ASCII .su2 mesh with first-order lines / triangles / quadrilaterals; same return value as
+    ``read_msh`` (the marker elements of every MARKER_TAG are the ``line`` cells)."""
+    with open(path, "r") as fh:
+        lines = [ln.split("%")[0].strip() for ln in fh]
+    lines = [ln for ln in lines if ln]
+    ndim, pos, found, xyz = None, 0, {}, None
+
+    def key(ln):
+        return ln.split("=")[0].strip().upper() if "=" in ln else None
+
+    def val(ln):
+        return ln.split("=")[1].strip()
+
+    def rows(start, n, sink):
+        for ln in lines[start:start + n]:
+            f = ln.split()
+            et = int(f[0])
+            if et not in _SU2_NODES:
+                raise ValueError(f"{path}: element type {et} is not a first-order line/triangle/quad")
+            name, nn = _SU2_NODES[et]
+            sink.setdefault(name, []).append([int(x) for x in f[1:1 + nn]])
+
+    while pos < len(lines):
+        k = key(lines[pos])
+        if k == "NDIME":
+            ndim = int(val(lines[pos]))
+            pos += 1
+        elif k == "NELEM":
+            n = int(val(lines[pos]))
+            rows(pos + 1, n, found)
+            pos += 1 + n
+        elif k == "NPOIN":
+            n = int(val(lines[pos]).split()[0])
+            if ndim is None:
+                raise ValueError(f"{path}: NPOIN before NDIME")
+            xyz = np.zeros((n, 3))
+            for q, ln in enumerate(lines[pos + 1:pos + 1 + n]):
+                xyz[q, :ndim] = [float(x) for x in ln.split()[:ndim]]
+            pos += 1 + n
+        elif k == "MARKER_ELEMS":
+            n = int(val(lines[pos]))
+            rows(pos + 1, n, found)
+            pos += 1 + n
+        else:  # NMARK, MARKER_TAG and anything this reader has no use for
+            pos += 1
+    if xyz is None or not found:
+        raise ValueError(f"{path}: not an SU2 mesh (NPOIN / NELEM missing)")
+    return xyz, {k: np.array(v, dtype=np.int64) for k, v in found.items()}
+
+
+def read_mesh(path):
+    """KitBase.read_mesh(file): by extension, ``.msh`` (Gmsh 4.1 / 2.2) or ``.su2``."""
+    return read_su2(path) if str(path).lower().endswith(".su2") else read_msh(path)
+
+
 # ------------------------------------------------------------------------------------------------
 class UnstructPSpace:
     """The mesh fields of KitBase's ``UnstructPSpace`` the FR path reads (struct.jl:270-286), for a
@@ -408,7 +470,7 @@ class UnstructPSpace:
 
     def __init__(self, points, cellid=None):
         if cellid is None:
-            points, cells = read_msh(points)
+            points, cells = read_mesh(points)
             if "triangle" not in cells:
                 raise ValueError("the mesh holds no triangles")
             cellid = cells["triangle"]

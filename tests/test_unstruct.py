@@ -217,6 +217,41 @@ def test_reference_assets_read_here(name):
     assert np.abs((ps.cellNormals * L[:, :, None]).sum(axis=1)).max() < 1e-12
 
 
+def test_su2_reader(tmp_path):
+    """The SU2 twin of a two-triangle square with its four boundary edges as one marker."""
+    f = tmp_path / "sq.su2"
+    f.write_text("% comment\nNDIME= 2\nNELEM= 2\n5 0 1 2 0\n5 0 2 3 1\nNPOIN= 4\n0 0 0\n1 0 1\n1 1 2\n0 1 3\n"
+                 "NMARK= 1\nMARKER_TAG= wall\nMARKER_ELEMS= 4\n3 0 1\n3 1 2\n3 2 3\n3 3 0\n")
+    pts, cells = FR.read_su2(str(f))
+    assert pts.shape == (4, 3) and cells["triangle"].tolist() == [[0, 1, 2], [0, 2, 3]] and cells["line"].shape == (4, 2)
+    ps = FR.TriFRPSpace(str(f), 2)  # UnstructPSpace picks the reader by extension, like KitBase.read_mesh
+    ref = FR.UnstructFRPSpace((pts[:, :2], cells["triangle"]), 2)
+    assert np.array_equal(ps.fpn, ref.fpn) and np.abs(ps.xpg - ref.xpg).max() == 0.0
+    assert (ps.faceType == 1).sum() == 4
+    f.write_text("NDIME= 2\nNELEM= 1\n10 0 1 2 3 0\nNPOIN= 4\n0 0\n1 0\n1 1\n0 1\n")
+    with pytest.raises(ValueError, match="element type 10"):
+        FR.read_su2(str(f))
+    f.write_text("hello\n")
+    with pytest.raises(ValueError, match="not an SU2 mesh"):
+        FR.read_su2(str(f))
+
+
+def test_reference_su2_asset_reads_here():
+    """assets/linesource.su2, the one SU2 file the reference ships (build container only)."""
+    path = "/root/reference/assets/linesource.su2"
+    if not os.path.exists(path):
+        pytest.skip("reference assets not present")
+    ps = FR.TriFRPSpace(path, 2)
+    nc = ps.cellid.shape[0]
+    assert nc == 8442 and ps.points.shape[0] == 4342 and ps.cells["line"].shape == (240, 2)
+    assert (np.linalg.det(ps.J) > 0).all()
+    nb = (ps.faceType == 1).sum()
+    assert nb == 240 == (ps.fpn[:, :, 0, 0] < 0).sum()
+    i, j, k = np.nonzero(ps.fpn[..., 0] >= 0)
+    n = ps.fpn[i, j, k]
+    assert np.abs(ps.xfg[i, j, k] - ps.xfg[n[:, 0], n[:, 1], n[:, 2]]).max() < 1e-12
+
+
 # ---------------------------------------------------------------- the reference's exported names
 def test_reference_exported_names_match_the_oracle_restatement(FR):
     """JacobiP / ∂JacobiP / simplex_basis / ∂simplex_basis / correction_field / vandermonde_matrix(shape, ...) /
