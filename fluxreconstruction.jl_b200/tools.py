@@ -16,7 +16,7 @@ import numpy as np
 __all__ = [
     "L1_error", "L2_error", "Linf_error", "shock_detector", "positive_limiter", "filter_exp", "filter_exp1d",
     "filter_exp2d", "basis_norm", "interp_face_", "poly_derivative_", "rs_jacobi", "rs_ab", "xy_rs", "conserve_prim",
-    "prim_conserve",
+    "prim_conserve", "VSpace1D", "maxwellian", "moments_conserve", "heaviside", "euler_flux", "sound_speed",
 ]
 
 
@@ -50,6 +50,56 @@ def prim_conserve(prim, gamma):
     vel = p[..., 1:-1]
     E = 0.5 * rho / lam / (gamma - 1.0) + 0.5 * rho * np.sum(vel * vel, axis=-1)
     return np.concatenate([rho[..., None], rho[..., None] * vel, E[..., None]], axis=-1)
+
+
+def sound_speed(prim, gamma):
+    """[KB] sound_speed(prim, gamma) = sqrt(gamma / (2 lambda))."""
+    return np.sqrt(0.5 * gamma / np.asarray(prim, dtype=np.float64)[..., -1])
+
+
+def euler_flux(w, gamma):
+    """[KB] euler_flux(w, gamma): (F,) for 1-D states (3 variables), (F, G) for 2-D ones (4 variables)."""
+    w = np.asarray(w, dtype=np.float64)
+    rho, E = w[..., 0], w[..., -1]
+    vel = w[..., 1:-1] / rho[..., None]
+    p = (gamma - 1.0) * (E - 0.5 * rho * np.sum(vel * vel, axis=-1))
+    out = []
+    for d in range(vel.shape[-1]):
+        vd = vel[..., d]
+        mom = [w[..., 1 + c] * vd + (p if c == d else 0.0) for c in range(vel.shape[-1])]
+        out.append(np.stack([w[..., 1 + d], *mom, (E + p) * vd], axis=-1))
+    return tuple(out)
+
+
+# ------------------------------------------------------------------ [KB] 1-D velocity space and moments
+class VSpace1D:
+    """[KB] VSpace1D(u0, u1, nu) (example/bgk_wave.jl:25): midpoint nodes ``u`` and uniform ``weights``."""
+
+    def __init__(self, u0, u1, nu):
+        self.u0, self.u1, self.nu = float(u0), float(u1), int(nu)
+        du = (self.u1 - self.u0) / self.nu
+        self.u = self.u0 + (np.arange(1, self.nu + 1) - 0.5) * du
+        self.du = np.full(self.nu, du)
+        self.weights = np.full(self.nu, du)
+
+
+def maxwellian(v, prim):
+    """[KB] maxwellian(u, prim), 1-D1V: rho sqrt(lambda / pi) exp(-lambda (u - U)^2); prim[..., 3] broadcasts
+    against v[..., nu]."""
+    prim = np.asarray(prim, dtype=np.float64)
+    rho, U, lam = prim[..., 0:1], prim[..., 1:2], prim[..., 2:3]
+    return rho * np.sqrt(lam / np.pi) * np.exp(-lam * (np.asarray(v, dtype=np.float64) - U) ** 2)
+
+
+def moments_conserve(f, v, w):
+    """[KB] moments_conserve(f, u, weights) = [sum w f, sum w u f, 1/2 sum w u^2 f] over the last axis."""
+    f, v, w = (np.asarray(a, dtype=np.float64) for a in (f, v, w))
+    return np.stack([np.sum(w * f, -1), np.sum(v * w * f, -1), 0.5 * np.sum(v * v * w * f, -1)], axis=-1)
+
+
+def heaviside(x):
+    """[KB] heaviside(x): 1 for x >= 0 (bgk_wave.jl:26 builds the upwind switch with it)."""
+    return (np.asarray(x) >= 0).astype(np.float64)
 
 
 # ------------------------------------------------------------------ dissipation.jl

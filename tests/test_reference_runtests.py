@@ -159,3 +159,25 @@ def test_interp_face_and_derivative(FR):
     assert np.allclose(df, 3 * ps.xpl**2)
     L = FR.standard_lagrange(ps.xpl)  # :44
     assert L is not None
+
+
+def test_kitbase_closures_of_the_scripts(FR):
+    """[KB-recall] the KitBase pieces the example scripts build their inputs with (bgk_wave.jl:23-40,
+    euler2d_wave.jl:115-120): host mirrors against the oracle's restatements."""
+    import fr_oracle as o
+
+    vs = FR.VSpace1D(-5.0, 5.0, 28)
+    u, w = o.vspace1d(-5.0, 5.0, 28)
+    assert np.array_equal(vs.u, u) and np.array_equal(vs.weights, w)
+    prim = np.array([[1.1, 0.3, 0.9], [0.8, -0.2, 1.3]])
+    M = FR.maxwellian(vs.u[None, :], prim)
+    assert np.abs(M - o.maxwellian(u[None, :], prim)).max() < 1e-16
+    assert np.abs(FR.moments_conserve(M, vs.u, vs.weights) - o.moments_conserve_1v(M, u, w)).max() < 1e-15
+    assert np.array_equal(FR.heaviside(vs.u), o.heaviside(u))
+    rng = np.random.default_rng(3)
+    for nv in (3, 4):
+        p = np.abs(rng.standard_normal((5, nv))) + 0.5
+        wv = FR.prim_conserve(p, 5 / 3)
+        for a, b in zip(FR.euler_flux(wv, 5 / 3), o.euler_flux(wv, 5 / 3)):
+            assert np.abs(a - b).max() < 1e-13
+        assert np.abs(FR.sound_speed(p, 5 / 3) - o.sound_speed(p, 5 / 3)).max() < 1e-15
