@@ -10,6 +10,6 @@ from .problems import (  # noqa: F401
     BGKProblem, DistributedEuler2D, DistributedNSCavity, Euler, Euler2DProblem, Euler2DCurvProblem, ExplicitRK, RK4, Tsit5, FRAdvectionProblem, FREulerProblem, Integrator, Midpoint, NSCavityProblem, SSPRK33, TriEulerProblem, init, ref_vhs_vis,
     solve, step_,
 )
-from . import partition  # noqa: F401
+from . import examples, partition  # noqa: F401
 
 __version__ = "0.1.0"

@@ -1,9 +1,10 @@
 """cfg5 stage timing only (for ncu): 2-D NS cavity, gas-kinetic flux, p3."""
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "oracle"))
-import fr_oracle as o
+sys.path.insert(0, ROOT)
 import frb200 as FR
+
+o = FR.examples  # the example scripts' initial conditions (host mirror)
 G = 5.0 / 3.0
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 1024
 ps = FR.FRPSpace2D(0.0, 1.0, n, 0.0, 1.0, n, 3, 1, 1)

@@ -1,7 +1,6 @@
 """Quick device-time probe of the 2-D Euler stage kernels (not the bench contract)."""
 import os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle"))
 import numpy as np
 import frb200 as FR
 

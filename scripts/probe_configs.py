@@ -2,10 +2,11 @@
 (not the bench contract; feeds the per-config table of profiles/ and DESIGN.md)."""
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "oracle"))
+sys.path.insert(0, ROOT)
 import numpy as np
-import fr_oracle as o
 import frb200 as FR
+
+o = FR.examples  # the example scripts' initial conditions (host mirror)
 
 G = 5.0 / 3.0
 
@@ -24,7 +25,8 @@ report("cfg1 adv1d p2 100 cells", FR.FRAdvectionProblem(np.asfortranarray(np.sin
 ps = FR.FRPSpace1D(0.0, 1.0, 4096, 3)
 report("cfg2 euler1d p3 4096 cells", FR.FREulerProblem(o.ic_sod1d(ps, G), (0, 1), ps, G, "dirichlet"), 16, 24, "(latency-bound: 393 KB)")
 ps = FR.FRPSpace1D(0.0, 1.0, 8192, 2)
-velo, wts = o.vspace1d(-5.0, 5.0, 256)
+vs = FR.VSpace1D(-5.0, 5.0, 256)
+velo, wts = vs.u, vs.weights
 report("cfg4 bgk1d p2 8192x256", FR.BGKProblem(o.ic_bgk1d(ps, velo), (0, 1), ps, velo, wts, 1e-2), 16, 24, "(50 MB: L2-resident; 2 launches)")
 n = int(os.environ.get("NS_N", "1024"))
 ps = FR.FRPSpace2D(0.0, 1.0, n, 0.0, 1.0, n, 3, 1, 1)

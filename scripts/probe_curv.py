@@ -1,12 +1,13 @@
 """Stage timing of the curvilinear-quadrilateral kernels (frb_euler2d_curv_create) on a sheared mesh.
 
-    python scripts/probe_curv.py [nx ny deg iters] [--cpu]
+    python scripts/probe_curv.py [nx ny deg iters]
 
 Prints one JSON line per stage kind: ms per fused stage (face + element kernel), DOF-updates/s and a
 `roofline` object like bench.py's: achieved = algorithmic bytes (16 / 24 B of state + 8 B of metric per
 DOF-update) / stage time, peak = the measured HBM copy bandwidth of MEASURED_PEAKS.json
 (fallback: B200_PROFILING.md), traffic = the DRAM bytes per stage of the committed ncu capture
-(profiles/r01_curv.md; 1024^2 p3, 16-B stage only).
+(profiles/r01_curv.md; 1024^2 p3, 16-B stage only).  The CPU restatement of the same residual is timed by
+tests/harness/cpu_baseline_curv.py (only tests/ may execute the oracle).
 """
 import json
 import os
@@ -38,37 +39,7 @@ def line(workload, dofs, state_bytes, ms, traffic=None):
                          "kernel": "euler2d_curv_face_kernel + euler2d_curv_elem_kernel (2 launches per stage)"}}
 
 
-def cpu_baseline(deg, nx=512, ny=256, evals=3):
-    """The reference's CPU path for this residual -- its C / OpenMP restatement, oracle/fr_oracle_curv.c (Julia is not
-    in the image: kind "port") -- timed on a bounded sample with all host threads.  The checker is only timed here,
-    never used by the product."""
-    import time
-
-    sys.path.insert(0, os.path.join(ROOT, "oracle"))
-    import c_oracle
-
-    base = FR.PSpace2D(0.0, 1.0, nx, 0.0, 1.0, ny, 1, 1)
-    v = base.vertices.copy()
-    v[..., 0] += v[..., 1]
-    z = np.zeros((nx + 2, ny + 2))
-    ps = FR.FRPSpace2D(FR.PSpace2D(0.0, 1.0, nx, 0.0, 1.0, ny, z, z, z, z, v), deg)
-    n1, n2 = FR.face_normals(ps.vertices)
-    rho = 1.0 + 0.1 * np.sin(2 * np.pi * (ps.xpg[..., 0] - ps.xpg[..., 1]))
-    u = np.asfortranarray(FR.prim_conserve(np.stack([rho, np.ones_like(rho), 0.2 * np.ones_like(rho), rho], -1), 5.0 / 3.0))
-    c_oracle.rhs_euler2d_curv(u, ps, n1, n2, 5.0 / 3.0, fy_index="k")
-    t0 = time.perf_counter()
-    for _ in range(evals):
-        c_oracle.rhs_euler2d_curv(u, ps, n1, n2, 5.0 / 3.0, fy_index="k")
-    dt = (time.perf_counter() - t0) / evals
-    dofs = nx * ny * (deg + 1) ** 2 * 4
-    return {"value": dofs / dt, "unit": "DOF-updates/s", "cores": c_oracle.num_threads(), "kind": "port",
-            "sample": f"{evals} RHS evaluations of the curvilinear residual on {nx}x{ny} p{deg} sheared elements, "
-                      "C/OpenMP restatement of dev/parallelogram.jl:80-165"}
-
-
 def main():
-    want_cpu = "--cpu" in sys.argv
-    sys.argv = [a for a in sys.argv if a != "--cpu"]
     nx, ny, deg, iters = (int(a) for a in (sys.argv[1:5] + ["1024", "1024", "3", "20"][len(sys.argv) - 1:]))
     g = 5.0 / 3.0
     base = FR.PSpace2D(0.0, 1.0, nx, 0.0, 1.0, ny, 1, 1)
@@ -90,8 +61,6 @@ def main():
             print(json.dumps(line(f"curv euler2d {nx}x{ny} p{deg} corr={corr} metric={metric}", dofs, state_bytes, ms,
                                   2.709e9 if captured else None)), flush=True)
         prob.close()
-    if want_cpu:
-        print(json.dumps({"cpu_baseline": cpu_baseline(deg)}), flush=True)
 
 
 if __name__ == "__main__":

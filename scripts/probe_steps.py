@@ -1,10 +1,11 @@
 """Wall / device time of long time loops of the small configs (launch-bound): cfg1, cfg2, cfg4."""
 import os, sys, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "oracle"))
+sys.path.insert(0, ROOT)
 import numpy as np
-import fr_oracle as o
 import frb200 as FR
+
+o = FR.examples  # the example scripts' initial conditions (host mirror)
 G = 5.0 / 3.0
 
 
@@ -24,5 +25,6 @@ run("cfg1 adv1d ssprk3", FR.FRAdvectionProblem(np.asfortranarray(np.sin(np.pi * 
 ps = FR.FRPSpace1D(0.0, 1.0, 4096, 3)
 run("cfg2 euler1d midpoint+limiter", FR.FREulerProblem(o.ic_sod1d(ps, G), (0, 1), ps, G, "dirichlet"), FR.Midpoint(), 0.05 * ps.dx[0], 1000, {"limiter_weights": ps.wp / 2})
 ps = FR.FRPSpace1D(0.0, 1.0, 8192, 2)
-velo, wts = o.vspace1d(-5.0, 5.0, 256)
+vs = FR.VSpace1D(-5.0, 5.0, 256)
+velo, wts = vs.u, vs.weights
 run("cfg4 bgk1d midpoint", FR.BGKProblem(o.ic_bgk1d(ps, velo), (0, 1), ps, velo, wts, 1e-2), FR.Midpoint(), 0.1 * ps.dx[0] / 5.0, 200)

@@ -1,13 +1,13 @@
-"""Slab-parallel parity check (run under torchrun, one rank per GPU):
+"""Test worker (imports the oracle: test infrastructure).  Slab-parallel parity check (run under torchrun, one rank per GPU):
 the N-rank result must equal the single-domain oracle on the same global mesh.
 
   python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 \
-      --master-port 29511 scripts/check_dist.py [nx ny_global nsteps scheme kernel ghost]
+      --master-port 29511 tests/dist/check_dist.py [nx ny_global nsteps scheme kernel ghost]
 """
 import os
 import sys
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "oracle"))
 import numpy as np

@@ -1,13 +1,13 @@
-"""Column-slab parallel cavity (cfg5) parity check (run under torchrun, one rank per GPU): the N-rank result must
+"""Test worker (imports the oracle: test infrastructure).  Column-slab parallel cavity (cfg5) parity check (run under torchrun, one rank per GPU): the N-rank result must
 equal the single-domain C oracle of example/ns_cavity.jl on the same global mesh.
 
   python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 \
-      --master-port 29513 scripts/check_dist_ns.py [nx_global ny deg nsteps]
+      --master-port 29513 tests/dist/check_dist_ns.py [nx_global ny deg nsteps]
 """
 import os
 import sys
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "oracle"))
 import numpy as np

@@ -136,3 +136,21 @@ def test_julia_shim_binds_every_entry_point():
     blocks = len(_re.findall(r"^\s*(?:function|struct|mutable struct|module)\b", src, flags=_re.M))
     blocks += len(_re.findall(r"=\s*function\s*\(", src))
     assert blocks == len(_re.findall(r"^\s*end\b", src, flags=_re.M))
+
+
+def test_only_test_infrastructure_touches_the_oracle():
+    """oracle/ is test infrastructure: besides tests/, only __graft_entry__ (build + smoke) and the CPU legs of
+    bench.py may import it -- no script, no package module."""
+    offenders = []
+    for dirpath, dirs, files in os.walk(ROOT):
+        dirs[:] = [d for d in dirs if d not in (".git", "oracle", "tests", "gpurun_out", "__pycache__", "lib")]
+        for f in files:
+            if not f.endswith((".py", ".sh", ".jl", ".cu", ".cuh", ".h")):
+                continue
+            path = os.path.join(dirpath, f)
+            if os.path.relpath(path, ROOT) in ("bench.py", "__graft_entry__.py"):
+                continue
+            txt = open(path).read()
+            if "fr_oracle" in txt or "c_oracle" in txt or 'os.path.join(ROOT, "oracle")' in txt:
+                offenders.append(os.path.relpath(path, ROOT))
+    assert offenders == []

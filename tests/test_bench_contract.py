@@ -43,5 +43,9 @@ def test_curv_probe_record_has_the_roofline_object():
     assert rec["stage_bytes_per_dof"] == 24 and abs(rec["gdof_per_s"] - 134.22) < 0.01
     assert roof["bound"] == "hbm" and roof["unit"] == "GB/s" and roof["traffic"] == 2.7e9
     assert abs(roof["frac"] - roof["achieved"] / roof["peak"]) < 1e-4 and 3000 < roof["achieved"] < 3400
-    cpu = m.cpu_baseline(2, 48, 32, 1)  # the C/OpenMP restatement of the same residual, timed (tiny sample here)
+    assert "oracle" not in open(os.path.join(root, "scripts", "probe_curv.py")).read().replace("only tests/ may execute the oracle", "")
+    spec = u.spec_from_file_location("cpu_baseline_curv", os.path.join(root, "tests", "harness", "cpu_baseline_curv.py"))
+    c = u.module_from_spec(spec)
+    spec.loader.exec_module(c)
+    cpu = c.cpu_baseline(2, 48, 32, 1)  # the C/OpenMP restatement of the same residual, timed (tiny sample here)
     assert cpu["kind"] == "port" and cpu["unit"] == "DOF-updates/s" and cpu["value"] > 0 and cpu["cores"] >= 1

@@ -24,7 +24,7 @@ def test_two_rank_slabs_match_oracle(scheme, kernel, ghost):
     if _ngpu() < 2:
         pytest.skip("needs 2 GPUs")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
-           "127.0.0.1", "--master-port", "29517", os.path.join(ROOT, "scripts", "check_dist.py"), "64", "96", "20",
+           "127.0.0.1", "--master-port", "29517", os.path.join(ROOT, "tests", "dist", "check_dist.py"), "64", "96", "20",
            scheme, kernel, ghost]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
@@ -36,7 +36,7 @@ def test_two_rank_cavity_slabs_match_oracle(nx, ny, deg):
     if _ngpu() < 2:
         pytest.skip("needs 2 GPUs")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
-           "127.0.0.1", "--master-port", "29519", os.path.join(ROOT, "scripts", "check_dist_ns.py"), str(nx), str(ny),
+           "127.0.0.1", "--master-port", "29519", os.path.join(ROOT, "tests", "dist", "check_dist_ns.py"), str(nx), str(ny),
            str(deg), "30"]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
