@@ -118,12 +118,18 @@ class _Problem:
     """Common part: owns the library handle; f!(du,u,p,t); device-resident stepping."""
 
     def __init__(self, u0, tspan, ctx=None):
-        self.ctx = ctx or Context.default()
+        self._ctx = ctx  # the device context is opened on first use, after the arguments have been checked
         self.u0 = np.array(u0, dtype=np.float64, order="F", copy=True)
         self.tspan = (float(tspan[0]), float(tspan[1]))
         self.h = C.c_void_p()
         self._keep = []
         self.p = None  # the reference passes a parameter tuple; kept for signature parity
+
+    @property
+    def ctx(self):
+        if self._ctx is None:
+            self._ctx = Context.default()
+        return self._ctx
 
     # -- lifetime ---------------------------------------------------------------------
     def close(self):

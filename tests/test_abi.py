@@ -154,3 +154,31 @@ def test_only_test_infrastructure_touches_the_oracle():
             if "fr_oracle" in txt or "c_oracle" in txt or 'os.path.join(ROOT, "oracle")' in txt:
                 offenders.append(os.path.relpath(path, ROOT))
     assert offenders == []
+
+
+def test_argument_checks_of_the_host_mirror_come_before_the_device(FR):
+    """Wrong array shapes are ValueErrors of the host mirror (the reference: BoundsError / DimensionMismatch) and
+    are raised before a device context is opened, so they can be checked here."""
+    import numpy as np
+
+    g = 5.0 / 3.0
+    ps1 = FR.FRPSpace1D(0.0, 1.0, 8, 2)
+    with pytest.raises(ValueError):
+        FR.FREulerProblem(np.ones((8, 4, 3), order="F"), (0, 1), ps1, g, "period")  # nsp = 3 expected
+    with pytest.raises(ValueError):
+        FR.FRAdvectionProblem(np.ones((8, 2), order="F"), (0, 1), ps1, 1.0, "period")
+    vs = FR.VSpace1D(-5.0, 5.0, 16)
+    with pytest.raises(ValueError):
+        FR.BGKProblem(np.ones((8, 12, 3), order="F"), (0, 1), ps1, vs.u, vs.weights)  # 12 velocities vs 16
+    ps2 = FR.FRPSpace2D(0.0, 1.0, 6, 0.0, 1.0, 4, 2, 1, 1)
+    with pytest.raises(ValueError):
+        FR.Euler2DProblem(np.ones((6, 4, 3, 3, 4), order="F"), (0, 1), ps2, g)  # ghost ring missing
+    with pytest.raises(ValueError):
+        FR.NSCavityProblem(np.ones((4, 3, 3, 4, 6), order="F"), (0, 1), ps2, 1.0, g, 1e-3, 0.81, 1e-4)
+    u = np.ones((8, 6, 3, 3, 4), order="F")
+    with pytest.raises(ValueError):
+        FR.Euler2DCurvProblem(u, (0, 1), ps2, g, n1=np.zeros((6, 4, 2)), n2=np.zeros((6, 5, 2)))  # n1 is [nx+1, ny, 2]
+    with pytest.raises(ValueError):
+        FR.Euler2DCurvProblem(u, (0, 1), ps2, g, corr="nodal")
+    with pytest.raises(ValueError):
+        FR.Euler2DCurvProblem(u, (0, 1), FR.FRPSpace2D(0.0, 1.0, 8, 0.0, 1.0, 6, 2, 0, 0), g)  # no ghost ring
