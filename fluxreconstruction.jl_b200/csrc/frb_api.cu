@@ -162,6 +162,8 @@ extern "C" int32_t frb_prob_destroy(frb_prob_t p) {
   if (p->ev0) cudaEventDestroy(p->ev0);
   if (p->ev1) cudaEventDestroy(p->ev1);
   for (cudaEvent_t e : p->prof_events) cudaEventDestroy(e);
+  for (cudaEvent_t e : p->pipe_events) cudaEventDestroy(e);
+  for (double *k : p->rk_k) cudaFree(k);
   delete p;
   return FRB_OK;
 }
@@ -494,6 +496,16 @@ static int ensure_du(frb_prob_t p) {
 }
 
 static int halo_wait_if_pending(frb_prob_t p);
+static int halo_republish(frb_prob_t p, const double *U);
+
+// Does f!(du,u,p,t) of the resident state go through the row-chunk kernel (the one frb_step and bench.py
+// run)?  Always when FRB_KERNEL_RC is selected; under AUTO when the resident state already lives in that
+// layout (a call between steps: no conversion of the state, only of du).
+static bool rhs_via_rc(frb_prob_t p, bool host_u) {
+  if (!use_rc(p) || frb_halo_active(p)) return false;
+  if (p->kernel_kind == FRB_KERNEL_RC) return true;
+  return !host_u && p->rc_valid;
+}
 
 extern "C" int32_t frb_rhs(frb_prob_t p, const double *u_host, double *du_host, double t) {
   (void)t;
@@ -501,20 +513,43 @@ extern "C" int32_t frb_rhs(frb_prob_t p, const double *u_host, double *du_host, 
   FRB_CUDA(cudaSetDevice(p->ctx->device));
   cudaStream_t s = p->ctx->stream;
   if (int rc = ensure_du(p)) return rc;
+  const bool via_rc = rhs_via_rc(p, u_host != nullptr);
+  // f! is pure with respect to the integrator (SciML contract): a caller-supplied u goes into the idle
+  // stage buffer s1, the resident state p->u / p->ru stays what the last upload / step left
+  const double *src = p->u;
   if (u_host) {
-    FRB_CUDA(cudaMemcpyAsync(p->u, u_host, sizeof(double) * p->len, cudaMemcpyHostToDevice, s));
-    p->ref_valid = true;
-    p->rc_valid = false;
-  } else if (int rc = need_ref(p, false)) {
-    return rc;
+    FRB_CUDA(cudaMemcpyAsync(p->s1, u_host, sizeof(double) * p->len, cudaMemcpyHostToDevice, s));
+    src = p->s1;
+  } else if (!via_rc || !p->rc_valid) {
+    if (int rc = need_ref(p, false)) return rc;
   }
   const int64_t l0 = p->launches;
   prof_begin(p);
   FRB_CUDA(cudaEventRecord(p->ev0, s));
   FrbStage st = {0.0, 0.0, 1.0, 0, 1};
   if (int rc = halo_wait_if_pending(p)) return rc;  // slab-parallel: the neighbours' rows of p->u have landed
-  int n = launch_stage(p, p->u, nullptr, p->du, st);
-  if (n < 0) return n;
+  int n;
+  if (via_rc) {
+    // row-chunk kernel: state in RC (resident mirror, or the caller's u converted into rs1), L(u) into
+    // rs2, interior of rs2 back into the reference image of du (du = 0 in the ghosts)
+    const double *rsrc = p->ru;
+    if (u_host || !p->rc_valid) {
+      if ((n = frb_rc_from_ref(p, src, p->rs1)) < 0) return n;
+      p->launches += n;
+      rsrc = p->rs1;
+    }
+    cudaEvent_t e0 = p->profiling ? prof_event(p) : nullptr, e1 = p->profiling ? prof_event(p) : nullptr;
+    if (e0 && e1) cudaEventRecord(e0, s);
+    n = frb_launch_euler2d_rc(p, rsrc, nullptr, p->rs2, st, nullptr, nullptr, 0);
+    if (e0 && e1) cudaEventRecord(e1, s);
+    if (n < 0) return n;
+    p->launches += n;
+    if ((n = frb_rc_to_ref(p, p->rs2, p->du, true)) < 0) return n;
+    p->launches += n;
+  } else {
+    n = launch_stage(p, src, nullptr, p->du, st);
+    if (n < 0) return n;
+  }
   FRB_CUDA(cudaEventRecord(p->ev1, s));
   if (du_host)
     FRB_CUDA(cudaMemcpyAsync(du_host, p->du, sizeof(double) * p->len, cudaMemcpyDeviceToHost, s));
@@ -535,18 +570,19 @@ extern "C" int32_t frb_rhs_pipelined(frb_prob_t p, const double *u_host, double 
   FRB_CUDA(cudaSetDevice(p->ctx->device));
   if (int rc = ensure_du(p)) return rc;
   cudaStream_t sc = p->ctx->stream, si = p->ctx->copy_in, so = p->ctx->copy_out;
-  p->ref_valid = true;  // p->u is overwritten slab by slab
-  p->rc_valid = false;
+  double *const U = p->s1;  // the caller's u streams through the idle stage buffer: the resident state survives
   FRB_CUDA(cudaStreamSynchronize(sc));  // du memset / earlier work
   const size_t NXG = p->nx + 2, NE = NXG * (size_t)(p->ny + 2);
   const int nplanes = 4 * p->nsp * p->nsp;
   const size_t pitch = NE * sizeof(double);
   const int rows = (p->ny + nslab - 1) / nslab;
-  std::vector<cudaEvent_t> ev_in(nslab), ev_c(nslab);
-  for (int s = 0; s < nslab; ++s) {
-    FRB_CUDA(cudaEventCreateWithFlags(&ev_in[s], cudaEventDisableTiming));
-    FRB_CUDA(cudaEventCreateWithFlags(&ev_c[s], cudaEventDisableTiming));
+  // per-slab events live with the problem (created once, reused by every call)
+  while ((int)p->pipe_events.size() < 2 * nslab) {
+    cudaEvent_t e = nullptr;
+    FRB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    p->pipe_events.push_back(e);
   }
+  cudaEvent_t *const ev_in = p->pipe_events.data(), *const ev_c = p->pipe_events.data() + nslab;
   const int64_t l0 = p->launches;
   prof_begin(p);
   FRB_CUDA(cudaEventRecord(p->ev0, sc));
@@ -558,7 +594,7 @@ extern "C" int32_t frb_rhs_pipelined(frb_prob_t p, const double *u_host, double 
     const int up_to = b + 1;  // rows a-1 .. b+1 are needed
     if (up_to >= up_next) {
       const size_t off = NXG * (size_t)up_next, w = NXG * (size_t)(up_to - up_next + 1) * sizeof(double);
-      FRB_CUDA(cudaMemcpy2DAsync(p->u + off, pitch, u_host + off, pitch, w, nplanes, cudaMemcpyHostToDevice, si));
+      FRB_CUDA(cudaMemcpy2DAsync(U + off, pitch, u_host + off, pitch, w, nplanes, cudaMemcpyHostToDevice, si));
       up_next = up_to + 1;
     }
     FRB_CUDA(cudaEventRecord(ev_in[s], si));
@@ -566,7 +602,7 @@ extern "C" int32_t frb_rhs_pipelined(frb_prob_t p, const double *u_host, double 
     p->row_lo = a;
     p->row_hi = b;
     FrbStage st = {0.0, 0.0, 1.0, 0, 1, 0};
-    int n = launch_stage(p, p->u, nullptr, p->du, st);
+    int n = launch_stage(p, U, nullptr, p->du, st);
     p->row_lo = p->row_hi = 0;
     if (n < 0) { rc = n; break; }
     FRB_CUDA(cudaEventRecord(ev_c[s], sc));
@@ -580,7 +616,6 @@ extern "C" int32_t frb_rhs_pipelined(frb_prob_t p, const double *u_host, double 
   FRB_CUDA(cudaStreamSynchronize(si));
   FRB_CUDA(cudaStreamSynchronize(sc));
   FRB_CUDA(cudaStreamSynchronize(so));
-  for (int s = 0; s < nslab; ++s) { cudaEventDestroy(ev_in[s]); cudaEventDestroy(ev_c[s]); }
   if (rc != FRB_OK) return rc;
   FRB_CUDA(cudaEventElapsedTime(&p->last_ms, p->ev0, p->ev1));
   p->last_launches = p->launches - l0;
@@ -627,9 +662,20 @@ extern "C" int32_t frb_ghost_fill(frb_prob_t p, int32_t ghost_mode) {
   FRB_REQUIRE(p->kind == K_EULER2D, FRB_ERR_STATE, "frb_ghost_fill: euler2d problems only");
   FRB_CUDA(cudaSetDevice(p->ctx->device));
   if (int rc = need_ref(p, true)) return rc;
-  int n = frb_launch_ghost_fill2d(p, p->u, ghost_mode);
-  if (n < 0) return n;
-  p->launches += n;
+  int n;
+  if (frb_halo_active(p)) {
+    // slab-parallel: rows 0 / ny+1 are the neighbours' rows, not ghosts -- the x half runs locally, the y half
+    // is the exchange across the global seam (first / last rank), as in the per-step hook of frb_step
+    if ((n = halo_wait_if_pending(p)) < 0) return n;
+    if ((n = frb_launch_ghost_x2d(p, p->u, ghost_mode)) < 0) return n;
+    p->launches += n;
+    if ((n = frb_halo_push(p, p->u, 0, true, ghost_mode == FRB_GHOST_WAVE_X ? 2 : -1)) < 0) return n;
+    p->launches += n;
+    if ((n = halo_republish(p, p->u)) < 0) return n;
+  } else {
+    if ((n = frb_launch_ghost_fill2d(p, p->u, ghost_mode)) < 0) return n;
+    p->launches += n;
+  }
   FRB_CUDA(cudaStreamSynchronize(p->ctx->stream));
   return FRB_OK;
 }
@@ -644,6 +690,7 @@ extern "C" int32_t frb_limiter_positivity(frb_prob_t p, const double *weights, i
   FRB_CUDA(cudaMemsetAsync(p->flag, 0, sizeof(int), p->ctx->stream));
   int n = run_limiter(p);
   if (n < 0) return n;
+  if ((n = halo_republish(p, p->u)) < 0) return n;
   int bad = 0;
   FRB_CUDA(cudaMemcpyAsync(&bad, p->flag, sizeof(int), cudaMemcpyDeviceToHost, p->ctx->stream));
   FRB_CUDA(cudaStreamSynchronize(p->ctx->stream));
@@ -692,6 +739,10 @@ extern "C" int32_t frb_filter_modal(frb_prob_t p, const double *iV, const double
   p->filt_eps = eps; p->filt_S0 = S0; p->filt_kappa = kappa; p->filt_ghosts = include_ghosts;
   FRB_CUDA(cudaMemsetAsync(p->flag, 0, sizeof(int), p->ctx->stream));
   int n = run_filter(p, p->flag);
+  if (n >= 0) {
+    int r = halo_republish(p, p->u);
+    if (r < 0) n = r;
+  }
   p->filt_eps = e0; p->filt_S0 = s0; p->filt_kappa = k0; p->filt_ghosts = g0; p->filt_when = when;
   if (n < 0) return n;
   int cnt = 0;
@@ -721,6 +772,25 @@ static int halo_wait_if_pending(frb_prob_t p) {
   if (n < 0) return n;
   p->launches += n;
   p->halo_pending = false;
+  return 0;
+}
+
+// Slab-parallel path: something other than a stage (limiter, modal filter) has just rewritten rows of U that
+// the neighbours hold copies of in their halo rows.  A neighbour barrier (everybody is done rewriting -- the
+// filter may also touch its own halo cells), then the boundary rows go out again, then the usual epoch.
+static int halo_republish(frb_prob_t p, const double *U) {
+  if (!frb_halo_active(p)) return 0;
+  int n;
+  if ((n = halo_wait_if_pending(p)) < 0) return n;
+  if ((n = frb_halo_signal(p)) < 0) return n;
+  p->launches += n;
+  p->halo_pending = true;
+  if ((n = halo_wait_if_pending(p)) < 0) return n;
+  if ((n = frb_halo_push(p, U, 0, false, -1)) < 0) return n;
+  p->launches += n;
+  if ((n = frb_halo_signal(p)) < 0) return n;
+  p->launches += n;
+  p->halo_pending = true;
   return 0;
 }
 
@@ -767,6 +837,9 @@ static int one_step(frb_prob_t p, int scheme, double dt, bool rc) {
   }
   if (p->limiter_on) {
     if ((n = run_limiter(p, rc)) < 0) return n;
+  }
+  if (par && (p->filt_when == 1 || p->limiter_on)) {
+    if ((n = halo_republish(p, U)) < 0) return n;  // the neighbours' halo copies of my rows 1 / ny are stale
   }
   if (p->ghost_mode != FRB_GHOST_NONE) {
     if (par) {
@@ -840,6 +913,7 @@ static int one_step(frb_prob_t p, int scheme, double dt, bool rc) {
   }
   if (p->filt_when == 2) {
     if ((n = run_filter(p, nullptr, rc)) < 0) return n;
+    if (par && (n = halo_republish(p, U)) < 0) return n;
   }
   return FRB_OK;
 }
@@ -959,6 +1033,7 @@ static int run_steps(frb_prob_t p, int scheme, double dt, bool rc, int nsteps, c
 extern "C" int32_t frb_step(frb_prob_t p, int32_t scheme, double dt, int32_t nsteps) {
   FRB_REQUIRE(p, FRB_ERR_ARG, "frb_step: prob is NULL");
   FRB_REQUIRE(nsteps >= 0, FRB_ERR_ARG, "frb_step: nsteps must be >= 0");
+  FRB_REQUIRE(scheme >= FRB_SCHEME_EULER && scheme <= FRB_SCHEME_SSPRK3, FRB_ERR_ARG, "frb_step: unknown scheme");
   FRB_CUDA(cudaSetDevice(p->ctx->device));
   cudaStream_t s = p->ctx->stream;
   const int64_t l0 = p->launches;

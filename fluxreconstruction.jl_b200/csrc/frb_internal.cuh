@@ -115,6 +115,7 @@ struct frb_prob_s {
   // per-stage profiling (event pairs around every stage launch)
   bool profiling = false;
   std::vector<cudaEvent_t> prof_events;  // pool
+  std::vector<cudaEvent_t> pipe_events;  // per-slab events of frb_rhs_pipelined (created once)
   size_t prof_used = 0;
   float stage_ms = 0.f;
   int64_t stage_count = 0;
@@ -138,7 +139,7 @@ bool frb_euler2d_rc_supported(frb_prob_t p);
 int frb_launch_euler2d_rc(frb_prob_t p, const double *u, const double *ua, double *out, FrbStage st,
                           double *peer_lo, double *peer_hi, int nyl_lo);
 int frb_rc_from_ref(frb_prob_t p, const double *ref, double *rc);
-int frb_rc_to_ref(frb_prob_t p, const double *rc, double *ref);
+int frb_rc_to_ref(frb_prob_t p, const double *rc, double *ref, bool interior_only = false);
 int frb_rc_ghost_fill(frb_prob_t p, double *u, int mode);
 int frb_rc_ghost_x(frb_prob_t p, double *u, int mode);
 int frb_rc_ring_copy(frb_prob_t p, const double *src, double *dst, bool row0, bool rowN);

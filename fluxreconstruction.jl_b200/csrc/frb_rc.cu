@@ -20,13 +20,15 @@ __global__ void rc_from_ref_kernel(const double *__restrict__ ref, double *__res
   rc[rc_index(g, j, s, plane, lane)] = v;
 }
 
-__global__ void rc_to_ref_kernel(const double *__restrict__ rc, double *__restrict__ ref, RcGeom g) {
+// interior: only the owned elements (du of f!: the ghosts of du stay 0)
+__global__ void rc_to_ref_kernel(const double *__restrict__ rc, double *__restrict__ ref, RcGeom g, int interior) {
   const int lane = threadIdx.x & 31;
   const int plane = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int s = blockIdx.y, j = blockIdx.z;
   if (plane >= g.nplanes) return;
   const int i = kRcOwn * s + lane;
   if (i > g.nx + 1) return;
+  if (interior && (i == 0 || i == g.nx + 1 || j == 0 || j == g.ny + 1)) return;
   int sp, lp;
   rc_primary(g, i, &sp, &lp);
   if (sp != s) return;  // a duplicate: the primary copy is written by its own strip
@@ -114,10 +116,10 @@ int frb_rc_from_ref(frb_prob_t p, const double *ref, double *rc) {
   return 1;
 }
 
-int frb_rc_to_ref(frb_prob_t p, const double *rc, double *ref) {
+int frb_rc_to_ref(frb_prob_t p, const double *rc, double *ref, bool interior_only) {
   const RcGeom g = geom_of(p);
   dim3 blk(256), grd((g.nplanes + 7) / 8, g.ns, g.ny + 2);
-  rc_to_ref_kernel<<<grd, blk, 0, p->ctx->stream>>>(rc, ref, g);
+  rc_to_ref_kernel<<<grd, blk, 0, p->ctx->stream>>>(rc, ref, g, interior_only ? 1 : 0);
   if (int r = check_launch_rc("rc_to_ref_kernel")) return r;
   return 1;
 }

@@ -451,9 +451,19 @@ def step_(itg, nsteps=1):
 
 
 def solve(prob, alg, dt, adaptive=False, **_):
+    """solve(prob, alg; adaptive=false, dt): full steps of dt and, like OrdinaryDiffEq, a shortened last step
+    that lands exactly on tspan[2] when dt does not divide the span."""
     itg = init(prob, alg, dt, adaptive)
-    n = int(round((prob.tspan[1] - prob.tspan[0]) / dt))
-    itg.step(n)
+    span = prob.tspan[1] - prob.tspan[0]
+    n = int(np.floor(span / dt * (1.0 + 4.0 * np.finfo(float).eps) + 1e-12))
+    if n > 0:
+        itg.step(n)
+    rest = span - n * dt
+    if rest > 1e-12 * max(abs(span), abs(dt)):
+        itg.dt = rest
+        itg.step(1)
+        itg.dt = float(dt)
+    itg.t = prob.tspan[1]
     return itg
 
 

@@ -167,8 +167,15 @@ int32_t frb_state_device_ptr(frb_prob_t prob, double **dptr);
 /* ---- f!(du, u, p, t) ----------------------------------------------------------- */
 /* The SciML in-place RHS.  u_host == NULL evaluates the resident state; du_host ==
  * NULL leaves du on the device.  With host pointers the call uploads u, evaluates
- * and downloads du (H2D + D2H inside the call).  t is accepted for signature parity
- * and unused (all reference RHS are autonomous). */
+ * and downloads du (H2D + D2H inside the call).  f! is PURE with respect to the
+ * integrator, as in the reference (eq_euler.jl:29: du is the only output): a
+ * caller-supplied u is evaluated from a scratch buffer and the resident state that
+ * frb_step advances is left as the last upload / step put it.  (ns2d: boundary!
+ * rewrites the ghost cells of the device copy only, never the host array.)
+ * With FRB_KERNEL_RC selected -- and, under AUTO, whenever the resident state already
+ * lives in the row-chunk layout -- the 2-D Euler residual is evaluated by the same
+ * euler2d_rc_kernel that frb_step launches (its rhs_only form).  t is accepted for
+ * signature parity and unused (all reference RHS are autonomous). */
 int32_t frb_rhs(frb_prob_t prob, const double *u_host, double *du_host, double t);
 /* As frb_rhs with host pointers, but streams the 2-D state through the device in
  * row slabs so that H2D, compute and D2H overlap (euler2d only). */

@@ -19,7 +19,7 @@ _dp = C.POINTER(C.c_double)
 
 def build(force: bool = False) -> str:
     so = os.path.join(_HERE, "libfr_oracle.so")
-    srcs = [os.path.join(_HERE, f) for f in ("fr_oracle.c", "fr_oracle_gks.c", "fr_oracle_curv.c", "Makefile")]
+    srcs = [os.path.join(_HERE, f) for f in ("fr_oracle.c", "fr_oracle_gks.c", "fr_oracle_curv.c", "fr_arbiter.c", "Makefile")]
     stale = (not os.path.exists(so)) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs)
     if force or stale:
         subprocess.run(["make", "-C", _HERE, "-B", "libfr_oracle.so"], check=True, capture_output=True)
@@ -267,3 +267,33 @@ def rhs_euler2d_curv(u, ps, n1, n2, gamma, corr="sp", fpc=None, fy_index="l", wa
             (1 if fy_index == "l" else 0) | (2 if wall_xlo else 0), gamma, _p(ll), _p(lr), _p(dl), _p(dhl), _p(dhr))
     assert rc == 0
     return du
+
+
+# ---- extended-precision arbiter (oracle/fr_arbiter.c): x87 long double, cell-local --------------------
+def arbiter_euler2d_cells(u, ps, gamma, cells):
+    """du of the cells ``cells`` [(i, j), ...] (1-based interior indices of the ghosted array) evaluated in
+    long double from the double inputs; returns [ncells, nsp, nsp, 4] (k, l, m)."""
+    u = np.asfortranarray(u, dtype=np.float64)
+    nx, ny, nsp = u.shape[0] - 2, u.shape[1] - 2, u.shape[2]
+    cells = np.ascontiguousarray(cells, dtype=np.int32).reshape(-1, 2)
+    assert cells[:, 0].min() >= 1 and cells[:, 0].max() <= nx and cells[:, 1].min() >= 1 and cells[:, 1].max() <= ny
+    out = np.empty((cells.shape[0], 4, nsp, nsp), dtype=np.float64)
+    ll, lr, dl, dhl, dhr = _ops(ps)
+    rc = lib().fra_rhs_euler2d_cells(
+        _p(u), nx, ny, nsp, C.c_double(ps.Jx), C.c_double(ps.Jy), _p(ll), _p(lr), _p(dl), _p(dhl), _p(dhr),
+        C.c_double(gamma), cells.ctypes.data_as(C.POINTER(C.c_int32)), int(cells.shape[0]), _p(out))
+    assert rc == 0
+    return out.transpose(0, 3, 2, 1)  # memory order k fastest -> [c, k, l, m]
+
+
+def arbiter_bgk1d_cells(u, dx, velo, weights, ll, lr, lpdm, dgl, dgr, tau, cells):
+    """du[cell, :, :] of the listed cells (0-based) in long double; returns [ncells, nu, nsp]."""
+    u = np.asfortranarray(u, dtype=np.float64)
+    ncell, nu, nsp = u.shape
+    cells = np.ascontiguousarray(cells, dtype=np.int32).ravel()
+    out = np.empty((cells.size, nsp, nu), dtype=np.float64)
+    a = [np.ascontiguousarray(x, dtype=np.float64) for x in (dx, velo, weights, ll, lr, lpdm, dgl, dgr)]
+    rc = lib().fra_rhs_bgk1d_cells(_p(u), ncell, nu, nsp, *[_p(x) for x in a], C.c_double(tau),
+                                   cells.ctypes.data_as(C.POINTER(C.c_int32)), int(cells.size), _p(out))
+    assert rc == 0
+    return out.transpose(0, 2, 1)
