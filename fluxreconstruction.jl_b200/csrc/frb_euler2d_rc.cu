@@ -12,7 +12,9 @@
 //     lanes 1 and 30 also refresh the duplicate of their column in the neighbouring chunk.
 // Shared memory (p3): 24-B stage 2 tiles + u_n + xd + xrp = 72 KB, 16-B stage 3 tiles + xd + xrp
 // = 72 KB -> 3 CTAs/SM either way.
+#include <atomic>
 #include <cstdlib>
+#include <cstring>
 
 #include "frb_internal.cuh"
 #include "frb_physics.cuh"
@@ -32,10 +34,35 @@ struct RcParams {
   RcGeom g;
   int rows_per_seg;
   double gamma, ca, cb;
-  // slab-parallel path: rows 1 / ny are also stored into the halo row of the rank below / above
-  double *peer_lo, *peer_hi;
-  int nyl_lo;
+  RcHalo h;  // slab-parallel path: the exchange with the neighbouring ranks (frb_rc.cuh)
 };
+
+// thread 0 of a boundary CTA: wait until the neighbour has raised mailbox[side] to `want` (its boundary row of
+// the stage that produced this stage's input is in the local slot).  Never hangs the box: after 5 s the time-out
+// is recorded in mailbox[2] (frb_halo_check_timeout -> FRB_ERR_PEER) and the launch carries on.
+__device__ __noinline__ void halo_poll(unsigned long long *mailbox, int side, unsigned long long want) {
+  if (!want) return;
+  const unsigned long long t0 = globaltimer_ns();
+  while (ld_acquire_sys(mailbox + side) < want) {
+    if (globaltimer_ns() - t0 > 5000000000ull) {
+      mailbox[2] = want;
+      break;
+    }
+    __nanosleep(100);
+  }
+}
+
+// thread 0, after the CTA's stores of a boundary row (peer stores included) and a block barrier: count the strip;
+// the last strip of the launch raises the neighbour's mailbox (fence / atomic / fence / release: the peer stores
+// of every strip are ordered before the flag)
+__device__ __forceinline__ void halo_raise(unsigned int *count, int ns, unsigned long long *flag,
+                                           unsigned long long epoch) {
+  const unsigned int old = atomicAdd(count, 1u);
+  if ((old + 1u) % (unsigned)ns == 0u) {
+    __threadfence_system();
+    st_release_sys(flag, epoch);
+  }
+}
 
 template <int NSP, int NBUF, bool USEA>
 struct SmemRc {
@@ -63,9 +90,22 @@ __global__ void __launch_bounds__(NSP * 32, MINB) euler2d_rc_kernel(RcParams P, 
   const int t = threadIdx.x >> 5;  // point row l in the x pass, point column k in the y pass
   const int s = blockIdx.x;
   const int i = kRcOwn * s + lane;  // element column of this lane
-  const int ja = 1 + blockIdx.y * P.rows_per_seg;
-  const int jb = min(g.ny, ja + P.rows_per_seg - 1);
-  if (ja > g.ny) return;
+  // row segment of this CTA.  Slab-parallel launches: rows 1 and ny are one-row segments of their own, first in
+  // launch order, so that the rows the neighbours wait for leave in the first microseconds of the launch
+  int ja, jb;
+  if (!P.h.active) {
+    ja = 1 + blockIdx.y * P.rows_per_seg;
+    jb = min(g.ny, ja + P.rows_per_seg - 1);
+  } else if (blockIdx.y == 0) {
+    ja = jb = 1;
+  } else if (blockIdx.y == 1) {
+    ja = jb = g.ny > 1 ? g.ny : 0;
+    if (g.ny < 2) return;
+  } else {
+    ja = 2 + (blockIdx.y - 2) * P.rows_per_seg;
+    jb = min(g.ny - 1, ja + P.rows_per_seg - 1);
+  }
+  if (ja > jb) return;
   const int ntiles = jb - ja + 3;  // rows ja-1 .. jb+1; tile q holds row ja-1+q in buffer q % NBUF
   const bool owner = lane >= 1 && lane <= kRcOwn && i <= g.nx;
   const int own = owner ? 1 : 0;
@@ -76,21 +116,47 @@ __global__ void __launch_bounds__(NSP * 32, MINB) euler2d_rc_kernel(RcParams P, 
   const double gamma = P.gamma, gm1 = gamma - 1.0;
   const size_t strip_off = (size_t)s * g.chunk;
 
+  // Where row r of the input comes from: the array itself, or -- rows 0 / ny+1 of a slab whose neighbour stores
+  // its boundary row into this rank's halo ring -- the local slot of the stage that produced the input.
+  auto is_slot = [&](int r) -> bool {
+    return P.h.active && ((r == 0 && P.h.src_lo != nullptr) || (r == g.ny + 1 && P.h.src_hi != nullptr));
+  };
+  // thread 0: one bulk copy of the strip's chunk of row r into ring buffer b
+  auto issue_bulk = [&](int b, int r) {
+    mbar_expect_tx(&S.bar[b], kTileBytes);
+    bulk_load(S.tile[b], P.u + (size_t)r * g.row + strip_off, kTileBytes, &S.bar[b]);
+  };
+  // ALL threads (CTA-uniform call): a halo slot row.  Thread 0 waits for the neighbour's flag, then the CTA copies
+  // the chunk with L2 loads (ld.global.cg: written by the peer GPU during this launch, never through L1) and
+  // completes the tile's barrier phase by hand.
+  auto fetch_slot = [&](int b, int r) {
+    if (threadIdx.x == 0) halo_poll(P.h.mailbox, r == 0 ? 0 : 1, r == 0 ? P.h.wait_lo : P.h.wait_hi);
+    __syncthreads();
+    const double2 *src = reinterpret_cast<const double2 *>((r == 0 ? P.h.src_lo : P.h.src_hi) + strip_off);
+    double2 *dst = reinterpret_cast<double2 *>(S.tile[b]);
+    for (int q = threadIdx.x; q < kTile / 2; q += NSP * 32) dst[q] = __ldcg(src + q);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // a bulk copy may refill this buffer later
+    __syncthreads();
+    if (threadIdx.x == 0) mbar_arrive(&S.bar[b]);
+  };
+
   if (threadIdx.x == 0) {
     for (int b = 0; b < NBUF + 1; ++b) mbar_init(&S.bar[b], 1);
     mbar_fence_init();
   }
   __syncthreads();
-  if (threadIdx.x == 0) {
+  {
     const int npre = ntiles < NBUF ? ntiles : NBUF;
-    for (int q = 0; q < npre; ++q) {
-      mbar_expect_tx(&S.bar[q], kTileBytes);
-      bulk_load(S.tile[q], P.u + (size_t)(ja - 1 + q) * g.row + strip_off, kTileBytes, &S.bar[q]);
+    if (threadIdx.x == 0) {
+      for (int q = 0; q < npre; ++q)
+        if (!is_slot(ja - 1 + q)) issue_bulk(q, ja - 1 + q);
+      if (USEA) {
+        mbar_expect_tx(bar_un, kTileBytes);
+        bulk_load(S.un, P.ua + (size_t)ja * g.row + strip_off, kTileBytes, bar_un);
+      }
     }
-    if (USEA) {
-      mbar_expect_tx(bar_un, kTileBytes);
-      bulk_load(S.un, P.ua + (size_t)ja * g.row + strip_off, kTileBytes, bar_un);
-    }
+    for (int q = 0; q < npre; ++q)  // after the bulk copies are in flight: these may have to wait for a neighbour
+      if (is_slot(ja - 1 + q)) fetch_slot(q, ja - 1 + q);
   }
 
   // per-thread views of a tile (= of a chunk): row view (x pass, l = t), column view (y pass, k = t)
@@ -113,9 +179,9 @@ __global__ void __launch_bounds__(NSP * 32, MINB) euler2d_rc_kernel(RcParams P, 
   {
     // tile 0 is dead after the prologue: refill its buffer with tile NBUF
     __syncthreads();
-    if (threadIdx.x == 0 && ntiles > NBUF) {
-      mbar_expect_tx(&S.bar[0], kTileBytes);
-      bulk_load(S.tile[0], P.u + (size_t)(ja - 1 + NBUF) * g.row + strip_off, kTileBytes, &S.bar[0]);
+    if (ntiles > NBUF) {
+      if (is_slot(ja - 1 + NBUF)) fetch_slot(0, ja - 1 + NBUF);
+      else if (threadIdx.x == 0) issue_bulk(0, ja - 1 + NBUF);
     }
   }
 
@@ -142,6 +208,8 @@ __global__ void __launch_bounds__(NSP * 32, MINB) euler2d_rc_kernel(RcParams P, 
       // four independent FMA chains per variable, stored as soon as they retire; the chunk offset
       // of a value equals its tile offset
       double *const po = P.out + (size_t)j * g.row + strip_off + offy;
+      // slab-parallel: row 1 / row ny also goes into the neighbour's halo ring (peer memory), warp-uniform
+      const bool to_lo = P.h.dst_lo != nullptr && j == 1, to_hi = P.h.dst_hi != nullptr && j == g.ny;
 #pragma unroll
       for (int m = 0; m < 4; ++m) {
         double v[NSP];
@@ -156,47 +224,45 @@ __global__ void __launch_bounds__(NSP * 32, MINB) euler2d_rc_kernel(RcParams P, 
           st_cs_if(po + 32 * NSP * (l + NSP * m), v[l], own);
           st_cs_if(po + 32 * NSP * (l + NSP * m) + dup_off, v[l], dup);
         }
+        if (to_lo) {
+          double *const pp = P.h.dst_lo + strip_off + offy;
+#pragma unroll
+          for (int l = 0; l < NSP; ++l) {
+            st_if(pp + 32 * NSP * (l + NSP * m), v[l], own);
+            st_if(pp + 32 * NSP * (l + NSP * m) + dup_off, v[l], dup);
+          }
+        }
+        if (to_hi) {
+          double *const pp = P.h.dst_hi + strip_off + offy;
+#pragma unroll
+          for (int l = 0; l < NSP; ++l) {
+            st_if(pp + 32 * NSP * (l + NSP * m), v[l], own);
+            st_if(pp + 32 * NSP * (l + NSP * m) + dup_off, v[l], dup);
+          }
+        }
         hb[m] = ht[m];
       }
     }
-    __syncthreads();  // (B) every read of tile[buf], un, xd, xrp is done
+    __syncthreads();  // (B) every read of tile[buf], un, xd, xrp is done; every store of row j is issued
 
-    if (threadIdx.x == 0) {
-      if (q + NBUF < ntiles) {
-        mbar_expect_tx(&S.bar[buf], kTileBytes);
-        bulk_load(S.tile[buf], P.u + (size_t)(ja - 1 + q + NBUF) * g.row + strip_off, kTileBytes, &S.bar[buf]);
-      }
-      if (USEA && j + 1 <= jb) {
-        mbar_expect_tx(bar_un, kTileBytes);
-        bulk_load(S.un, P.ua + (size_t)(j + 1) * g.row + strip_off, kTileBytes, bar_un);
-      }
+    if (P.h.active && threadIdx.x == 0 && (j == 1 || j == g.ny)) {
+      // this strip's part of a boundary row is out (locally and in the neighbour's ring), and the halo row next
+      // to it has been consumed: count it, the last strip raises the neighbour's flag
+      __threadfence_system();
+      if (j == 1) halo_raise(P.h.count + 0, g.ns, P.h.flag_lo, P.h.epoch);
+      if (j == g.ny) halo_raise(P.h.count + 1, g.ns, P.h.flag_hi, P.h.epoch);
+    }
+    if (threadIdx.x == 0 && USEA && j + 1 <= jb) {
+      mbar_expect_tx(bar_un, kTileBytes);
+      bulk_load(S.un, P.ua + (size_t)(j + 1) * g.row + strip_off, kTileBytes, bar_un);
+    }
+    if (q + NBUF < ntiles) {
+      const int r = ja - 1 + q + NBUF;
+      if (is_slot(r)) fetch_slot(buf, r);
+      else if (threadIdx.x == 0) issue_bulk(buf, r);
     }
   }
 
-  // slab-parallel path: the first / last owned row also goes straight into the halo row of the
-  // rank below / above (peer memory over NVLink).  Each thread forwards the values it stored
-  // itself (program order, L2-hot), once per segment that owns row 1 / row ny.
-  if (owner && ((ja == 1 && P.peer_lo) || (jb == g.ny && P.peer_hi))) {
-    const size_t col = strip_off + offy;
-    if (ja == 1 && P.peer_lo) {
-      const double *src = P.out + g.row + col;
-      double *dst = P.peer_lo + (size_t)(P.nyl_lo + 1) * g.row + col;
-      for (int c = 0; c < 4 * NSP; ++c) {
-        const double v = src[32 * NSP * c];
-        dst[32 * NSP * c] = v;
-        if (dup) dst[32 * NSP * c + dup_off] = v;
-      }
-    }
-    if (jb == g.ny && P.peer_hi) {
-      const double *src = P.out + (size_t)g.ny * g.row + col;
-      double *dst = P.peer_hi + col;
-      for (int c = 0; c < 4 * NSP; ++c) {
-        const double v = src[32 * NSP * c];
-        dst[32 * NSP * c] = v;
-        if (dup) dst[32 * NSP * c + dup_off] = v;
-      }
-    }
-  }
 }
 
 int env_int_rc(const char *name, int dflt) {
@@ -214,7 +280,7 @@ int rc_rows_per_seg(frb_prob_t p, const RcGeom &g, int ctas_per_sm, bool usea) {
   // built and measured): the strip-edge duplicate stores (no change without them), a tail wave alone,
   // start-up lock-step (per-CTA jitter: no change), TLB reach (strip-major chunk order: slower).
   // FRB_MARCH_ROWS overrides.
-  int forced = env_int_rc("FRB_MARCH_ROWS", 0);
+  static const int forced = env_int_rc("FRB_MARCH_ROWS", 0);  // read once (thread-safe static initialisation)
   if (forced > 0) return forced < g.ny ? forced : g.ny;
   const int slots = p->ctx->sm_count * ctas_per_sm;
   int nseg = (g.ny + (usea ? 5 : 11)) / (usea ? 6 : 12);
@@ -227,16 +293,23 @@ template <int NSP, bool USEA, bool SAMEJ, int MINB, bool CB1>
 int launch_rc(frb_prob_t p, RcParams rp, const MarchOps &mo) {
   constexpr int NBUF = USEA ? 2 : 3;
   rp.rows_per_seg = rc_rows_per_seg(p, rp.g, MINB, USEA);
-  const int segs = (rp.g.ny + rp.rows_per_seg - 1) / rp.rows_per_seg;
+  int segs = (rp.g.ny + rp.rows_per_seg - 1) / rp.rows_per_seg;
+  if (rp.h.active) {  // rows 1 and ny as one-row segments (blockIdx.y 0, 1), rows 2 .. ny-1 in normal segments
+    const int inner = rp.g.ny - 2;
+    segs = (rp.g.ny >= 2 ? 2 : 1) + (inner > 0 ? (inner + rp.rows_per_seg - 1) / rp.rows_per_seg : 0);
+  }
   const size_t smem = sizeof(SmemRc<NSP, NBUF, USEA>) + 128;
-  static unsigned long long attr_done = 0;  // per device: the attribute belongs to the device's copy of the kernel
+  // per device: the attribute belongs to the device's copy of the kernel.  Atomic bit mask: problems on different
+  // handles may launch from different host threads (frb200.h: re-entrant across handles); setting the attribute
+  // twice is harmless, missing it is not.
+  static std::atomic<unsigned long long> attr_done{0};
   const unsigned long long dev_bit = 1ull << (p->ctx->device & 63);
-  if (!(attr_done & dev_bit)) {
+  if (!(attr_done.load(std::memory_order_acquire) & dev_bit)) {
     FRB_CUDA(cudaFuncSetAttribute(euler2d_rc_kernel<NSP, USEA, SAMEJ, MINB, CB1>,
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     FRB_CUDA(cudaFuncSetAttribute(euler2d_rc_kernel<NSP, USEA, SAMEJ, MINB, CB1>,
                                   cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-    attr_done |= dev_bit;
+    attr_done.fetch_or(dev_bit, std::memory_order_release);
   }
   dim3 grd(rp.g.ns, segs), blk(NSP * 32);
   euler2d_rc_kernel<NSP, USEA, SAMEJ, MINB, CB1><<<grd, blk, smem, p->ctx->stream>>>(rp, mo);
@@ -262,7 +335,7 @@ bool frb_euler2d_rc_supported(frb_prob_t p) {
 
 // u, ua, out are RC buffers (frb_rc.cuh); stage semantics as in frb_launch_euler2d_march
 int frb_launch_euler2d_rc(frb_prob_t p, const double *u, const double *ua, double *out, FrbStage st,
-                          double *peer_lo, double *peer_hi, int nyl_lo) {
+                          const RcHalo *halo) {
   if (!frb_euler2d_rc_supported(p)) {
     frb_set_error("row-chunk kernel needs euler2d with deg 2 or 3");
     return FRB_ERR_ARG;
@@ -274,9 +347,8 @@ int frb_launch_euler2d_rc(frb_prob_t p, const double *u, const double *ua, doubl
   rp.g = rc_geom(p->nx, p->ny, p->nsp);
   rp.rows_per_seg = 0;
   rp.gamma = p->gamma;
-  rp.peer_lo = peer_lo;
-  rp.peer_hi = peer_hi;
-  rp.nyl_lo = nyl_lo;
+  if (halo) rp.h = *halo;
+  else memset(&rp.h, 0, sizeof rp.h);
   double cxs, cys;  // -cdt/Jx, -cdt/Jy  (L = -(dF/dr / Jx + dG/ds / Jy))
   bool usea;
   if (st.rhs_only) {

@@ -123,6 +123,7 @@ struct frb_prob_s {
   void *tmaps = nullptr;  // host copy, keyed by device pointer
   FrbHalo *halo = nullptr;
   bool halo_pending = false;  // a signal was sent; wait for the neighbours before the next stage
+  bool halo_pending_legacy = false;  // ... by a signal kernel (rows pushed into the arrays themselves, not the ring)
 };
 
 // ---- kernel launchers (each returns the number of kernels launched or <0) --------
@@ -136,8 +137,9 @@ int frb_launch_euler2d_march(frb_prob_t p, const double *u, const double *ua, do
 bool frb_euler2d_march_supported(frb_prob_t p);
 // row-chunk path (frb_euler2d_rc.cu, frb_rc.cu); every pointer is an RC buffer unless named ref
 bool frb_euler2d_rc_supported(frb_prob_t p);
+struct RcHalo;
 int frb_launch_euler2d_rc(frb_prob_t p, const double *u, const double *ua, double *out, FrbStage st,
-                          double *peer_lo, double *peer_hi, int nyl_lo);
+                          const RcHalo *halo = nullptr);
 int frb_rc_from_ref(frb_prob_t p, const double *ref, double *rc);
 int frb_rc_to_ref(frb_prob_t p, const double *rc, double *ref, bool interior_only = false);
 int frb_rc_ghost_fill(frb_prob_t p, double *u, int mode);
@@ -157,6 +159,12 @@ bool frb_halo_active(frb_prob_t p);
 void frb_halo_swap_roles(frb_prob_t p, int a, int b, bool rc = false);
 void frb_halo_stage_targets(frb_prob_t p, const double *out, double **dst_lo, double **dst_hi, int *nyl_lo,
                             int *nyl_hi);
+// in-kernel exchange of the row-chunk stage kernel (frb_rc.cuh: RcHalo)
+bool frb_halo_rc_inkernel(frb_prob_t p);
+bool frb_halo_rc_input_in_array(frb_prob_t p, const double *u);
+int frb_halo_rc_stage(frb_prob_t p, const double *u, const double *out, RcHalo *h);
+int frb_halo_rc_flush(frb_prob_t p, double *U);
+void frb_halo_rc_reset(frb_prob_t p);
 int frb_halo_push(frb_prob_t p, const double *src, int dst_role, bool seam, int flip_var);
 int frb_halo_role(frb_prob_t p, const double *ptr);
 int frb_halo_signal(frb_prob_t p);

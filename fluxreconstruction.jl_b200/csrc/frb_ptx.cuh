@@ -74,6 +74,34 @@ __device__ __forceinline__ void st_cs_if(double *p, double v, int pred) {
       : "memory");
 }
 
+// predicated plain store (peer memory: no cache hint)
+__device__ __forceinline__ void st_if(double *p, double v, int pred) {
+  asm volatile(
+      "{\n"
+      ".reg .pred q;\n"
+      "setp.ne.s32 q, %2, 0;\n"
+      "@q st.global.f64 [%0], %1;\n"
+      "}\n" ::"l"(p),
+      "d"(v), "r"(pred)
+      : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+
 }  // namespace frbptx
 
 // Operators as the marching kernels consume them: the derivative matrix with the flux-trace

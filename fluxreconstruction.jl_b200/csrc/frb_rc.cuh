@@ -60,3 +60,26 @@ __host__ __device__ inline bool rc_duplicate(const RcGeom &g, int s, int lane, i
   if (lane == kRcOwn && s < g.ns - 1) { *s2 = s + 1; *lane2 = 0; return true; }
   return false;
 }
+
+// Slab-parallel arguments of one launch of the row-chunk stage kernel (frb_euler2d_rc.cu).  The exchange with the
+// neighbouring ranks happens INSIDE the stage kernel:
+//   * the CTAs that own row 1 / row ny also store it into a slot of the neighbour's halo ring (peer memory over
+//     NVLink); when all strips of the row are out, the last CTA raises the neighbour's mailbox (st.release.sys);
+//   * the CTAs that need row 0 / row ny+1 poll the local mailbox (ld.acquire.sys) and take the row from the local
+//     slot; every other CTA starts at once, so the exchange overlaps the interior rows;
+//   * rows 1 and ny are one-row segments scheduled first (blockIdx.y 0 and 1): the flags go up a few
+//     microseconds into the launch and the neighbour has a whole stage of slack.
+// kRcSlots slots per side: the writer is at most one stage ahead of the reader, who reads the slot of the stage
+// before its own -> three live slots.
+constexpr int kRcSlots = 4;
+
+struct RcHalo {
+  int active;                             // 0: single-domain launch, everything below unused
+  const double *src_lo, *src_hi;          // local slot row replacing row 0 / ny+1 of u (nullptr: the array's own row)
+  unsigned long long wait_lo, wait_hi;    // mailbox value to wait for before reading src_lo / src_hi
+  unsigned long long *mailbox;            // local mailbox: [0] from lo, [1] from hi, [2] time-out record
+  double *dst_lo, *dst_hi;                // peer slot row for my row 1 / ny (nullptr: global seam, no data)
+  unsigned long long *flag_lo, *flag_hi;  // the neighbours' mailbox words to raise
+  unsigned long long epoch;               // value to raise them to
+  unsigned int *count;                    // local completion counters [2] (monotonic, +ns per launch)
+};

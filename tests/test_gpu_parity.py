@@ -418,7 +418,12 @@ def test_ns_cavity_rhs(FR, oracle, coracle, nx, ny, deg):
     ref = coracle.rhs_ns2d(uref, ps, 1.0, GAMMA, mu, 0.81, dt)
     assert np.isfinite(du).all()
     assert rel(du, ref) <= RTOL_RHS
-    # boundary! rewrote the ghosts of the resident state exactly like the reference does
+    # f! of the resident state (the integrator's own u, as OrdinaryDiffEq calls dudt!): boundary! rewrote its
+    # ghosts exactly like the reference does (ns_cavity.jl:148); with a caller-supplied u only the device copy is
+    assert np.array_equal(prob.download(), u)
+    d2 = np.zeros_like(u, order="F")
+    prob.rhs_resident(d2)
+    assert np.array_equal(d2, du)
     got_u = prob.download()
     assert rel(got_u[:, :, :, 1:-1, 0], uref[:, :, :, 1:-1, 0]) <= 1e-14
     assert rel(got_u[:, :, :, -1, 1:-1], uref[:, :, :, -1, 1:-1]) <= 1e-14
