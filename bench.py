@@ -1,17 +1,24 @@
 #!/usr/bin/env python
 """bench.py -- FP64 DOF-updates/s per RK stage of the fused FR residual + explicit stage.
 
-Workload (BASELINE.json configs[2], the configuration the metric is quoted on): 2-D Euler
-isentropic wave, FRPSpace2D deg 3, 2048 x 2048 elements per GPU (weak scaling: N GPUs hold a
-2048 x 2048N mesh split in row slabs), HLL, SSPRK3, fixed dt, ghost fill as
-example/euler2d_wave.jl:127-132.
+Default workload (BASELINE.json configs[2], the configuration the metric is quoted on): 2-D Euler
+isentropic wave, FRPSpace2D deg 3, 2048 x 2048 elements per GPU, HLL, SSPRK3, fixed dt, ghost fill as
+example/euler2d_wave.jl:127-132.  With N GPUs the mesh is split in row slabs:
 
-A "step" is one SSPRK3 time step of the resident state = 3 fused RHS+stage kernel launches
-(16 + 24 + 24 algorithmic bytes per DOF) plus the per-step ghost fill; `value` is
-3 * interior DOFs * K / (device time of the K steps, max over ranks).
+  --scaling weak   (default) every GPU holds 2048 x 2048 elements: a 2048 x 2048N global mesh
+  --scaling strong the 2048 x 2048 mesh itself is split: 2048 / N rows per GPU (256 at N = 8)
 
-  python bench.py --gpus N --steps K --warmup W            # this framework
-  python bench.py --impl reference --steps K --warmup W    # CPU restatement of the reference path
+and a weak line at N > 1 also carries the strong-scaling measurement of the same launch as `"strong": {...}`.
+
+A "step" is one SSPRK3 time step of the resident state = 3 fused RHS+stage kernel launches (16 + 24 + 24
+algorithmic bytes per DOF) plus the per-step ghost fill; `value` is 3 * interior DOFs * K / (device time of the
+K steps, max over ranks).  Every line carries a `parity` object: the state after the timed steps against a
+single-GPU run (rows next to the global seam, bit for bit at N > 1; against the independent generic kernel at
+N = 1) and the y-independence of the x wave across all slab boundaries.
+
+  python bench.py --gpus N --steps K --warmup W [--scaling strong]   # this framework, cfg3
+  python bench.py --config {1,2,4,5,f2} --steps K --warmup W         # the other BASELINE configurations (1 GPU)
+  python bench.py --impl reference --steps K --warmup W              # CPU restatement of the reference path
 
 Prints ONE JSON line on rank 0.
 """
@@ -42,13 +49,16 @@ def measured_peak():
         return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def ncu_traffic():
-    """dram bytes per launch of the dominant kernel from the committed ncu capture, or None."""
+def ncu_traffic(key="dram_bytes_per_launch"):
+    """dram bytes per launch of the dominant kernel from the committed ncu capture (a constant of the build, not
+    measured in this run -- `traffic_source` says so), or None."""
     try:
         with open(os.path.join(ROOT, "profiles", "dominant_kernel.json")) as fh:
-            return json.load(fh).get("dram_bytes_per_launch")
+            d = json.load(fh)
+            return d.get(key), "profiles/dominant_kernel.json (ncu --set full capture of the same kernel and size, " \
+                               "committed; not re-measured in this run)"
     except Exception:
-        return None
+        return None, None
 
 
 class ClockSampler:
@@ -102,11 +112,12 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
-def make_ic(FR, n, ny_local, y_offset_rows, ny_global):
-    """isentropic x wave of euler2d_wave.jl:115-120 on this rank's slab (host, NumPy)."""
+def make_ic(FR, n, ny_local):
+    """isentropic x wave of euler2d_wave.jl:115-120 on a slab of ny_local rows (host, NumPy); dx = dy = 1/n.
+    The wave does not depend on y, so every slab of a global mesh carries the same array."""
     import numpy as np
 
-    ps = FR.FRPSpace2D(0.0, 1.0, n, 0.0, ny_global / n, ny_local, 3, 1, 1)  # dx = dy = 1/n
+    ps = FR.FRPSpace2D(0.0, 1.0, n, 0.0, ny_local / n, ny_local, 3, 1, 1)
     rho = 1.0 + 0.1 * np.sin(2 * np.pi * ps.xpg[..., 0])
     u0 = np.empty(rho.shape + (4,), order="F")
     u0[..., 0] = rho                     # prim = [rho, 1, 0, lambda=rho]  ->  p = 1/2
@@ -116,65 +127,217 @@ def make_ic(FR, n, ny_local, y_offset_rows, ny_global):
     return ps, u0
 
 
-def cpu_baseline(sample_n=512, evals=3):
-    """The C restatement of the reference CPU path (oracle, kind 'port'), all host threads,
-    on a bounded sample of the same workload: RHS + one stage axpy per evaluation."""
-    import numpy as np
-
+def _oracle():
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import c_oracle
+
+    # torchrun exports OMP_NUM_THREADS=1: the reference arm and the CPU baseline use every host core
+    c_oracle.set_num_threads(os.cpu_count() or 1)
+    return c_oracle
+
+
+def host_bytes_needed(n):
+    """the reference-style temporaries of the CPU path (f, u_face, f_face, rhs1, rhs2, common fluxes) plus the state
+    and stage arrays of an SSPRK3 step: ~12.5 state-sized arrays of (n+2)^2 * 64 doubles"""
+    return int(12.5 * (n + 2) ** 2 * 64 * 8)
+
+
+def host_memory_fits(n):
+    try:
+        with open("/proc/meminfo") as fh:
+            for ln in fh:
+                if ln.startswith("MemAvailable:"):
+                    return int(ln.split()[1]) * 1024 > 1.3 * host_bytes_needed(n)
+    except OSError:
+        pass
+    return True
+
+
+def cpu_baseline(sample_n=2048, evals=3):
+    """The C restatement of the reference CPU path (oracle, kind 'port'), all host threads, on a bounded sample
+    of the same workload: RHS + one stage axpy per evaluation, on the workload's own mesh when memory allows."""
+    import numpy as np
+
+    c_oracle = _oracle()
     import frb200 as FR
 
-    ps, u0 = make_ic(FR, sample_n, sample_n, 0, sample_n)
+    note = ""
+    if not host_memory_fits(sample_n):
+        note = f" ({sample_n}x{sample_n} needs ~{host_bytes_needed(sample_n) / 1e9:.0f} GB of host memory: 1024x1024 instead)"
+        sample_n = 1024
+    ps, u0 = make_ic(FR, sample_n, sample_n)
     work = c_oracle.Work2D(sample_n, sample_n, 4)
     du = np.empty_like(u0, order="F")
     c_oracle.rhs_euler2d(u0, ps, GAMMA, work, du)  # warm-up (page faults, thread pool)
     t0 = time.perf_counter()
     for _ in range(evals):
         c_oracle.rhs_euler2d(u0, ps, GAMMA, work, du)
-        u1 = u0 + 1e-9 * du  # the stage update OrdinaryDiffEq does outside f!
+        np.multiply(du, 1e-9, out=du)  # the stage update OrdinaryDiffEq does outside f!
+        np.add(du, u0, out=du)
     dt = time.perf_counter() - t0
     dofs = sample_n * sample_n * 64
-    del u1
     return {"value": dofs * evals / dt, "unit": UNIT, "cores": c_oracle.num_threads(), "kind": "port",
-            "sample": f"{evals} RHS+stage evaluations of the same workload at {sample_n}x{sample_n} elements "
-                      f"(1/{(2048 // sample_n) ** 2} of the per-GPU mesh), C/OpenMP restatement of "
-                      "example/shock-vortex.jl:26-118 (Julia is not installed)"}
+            "sample": f"{evals} RHS+stage evaluations of the same workload at {sample_n}x{sample_n} elements{note}, "
+                      "C/OpenMP restatement of example/shock-vortex.jl:26-118 (Julia is not installed)"}
 
 
 def run_reference(args):
-    """--impl reference: the reference's CPU path (C restatement, all host threads)."""
+    """--impl reference: the reference's CPU path (C restatement, all host threads) on the workload's own mesh."""
     if int(os.environ.get("RANK", "0")) != 0:
         return
+    if args.config != "3":
+        import bench_configs
+
+        return bench_configs.run_reference(args)
     import numpy as np
 
-    sys.path.insert(0, os.path.join(ROOT, "oracle"))
-    import c_oracle
+    c_oracle = _oracle()
     import frb200 as FR
 
     n = args.ref_n
-    ps, u = make_ic(FR, n, n, 0, n)
+    note = ""
+    if not host_memory_fits(n):
+        note = f"; {n}x{n} needs ~{host_bytes_needed(n) / 1e9:.0f} GB of host memory, fell back to 1024x1024"
+        n = 1024
+    ps, u = make_ic(FR, n, n)
     dt = 1e-5 * 2048 / n
+    # caches preallocated by the first call and kept (as shock-vortex.jl does), state advanced in place
+    c_oracle.integrate_euler2d(u, ps, GAMMA, dt, 0, "ssprk3", "wave_x", inplace=True)
     for _ in range(args.warmup):
-        u = c_oracle.integrate_euler2d(u, ps, GAMMA, dt, 1, "ssprk3", "wave_x")
+        c_oracle.integrate_euler2d(u, ps, GAMMA, dt, 1, "ssprk3", "wave_x", inplace=True)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        u = c_oracle.integrate_euler2d(u, ps, GAMMA, dt, 1, "ssprk3", "wave_x")
+        c_oracle.integrate_euler2d(u, ps, GAMMA, dt, 1, "ssprk3", "wave_x", inplace=True)
     el = time.perf_counter() - t0
     dofs = n * n * 64
     value = 3.0 * dofs * args.steps / el
     cores = c_oracle.num_threads()
-    sample = (f"each step = one SSPRK3 step (3 RHS + stage axpys) at {n}x{n} elements, a bounded sample of the "
-              "2048x2048 workload; C/OpenMP restatement of the reference CPU path (Julia not installed)")
+    same = n == 2048
+    sample = (f"each step = one SSPRK3 step (3 RHS + stage axpys) at {n}x{n} elements"
+              + (" = the workload's own mesh" if same else " (a bounded sample of the 2048x2048 workload)")
+              + f"{note}; C/OpenMP restatement of the reference CPU path (Julia not installed)")
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 0, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * el / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"2D Euler isentropic wave, FRPSpace2D deg 3, HLL, SSPRK3 (sample {n}x{n})"},
+        "config": {"workload": f"2D Euler isentropic wave, FRPSpace2D deg 3, {n}x{n} elements, HLL, SSPRK3 fixed dt, "
+                               "ghost fill per step", "same_mesh_as_gpu_arm": same},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "finite": bool(np.isfinite(u).all()),
     }))
+
+
+class Job:
+    """rank / world / NCCL plumbing of one bench process"""
+
+    def __init__(self):
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        self.dist = None
+        if self.world > 1:
+            import torch
+            import torch.distributed as dist_mod
+
+            torch.cuda.set_device(self.local)
+            dist_mod.init_process_group("nccl", device_id=torch.device("cuda", self.local))
+            self.dist = dist_mod
+
+    def barrier(self):
+        if self.dist is not None:
+            import torch
+
+            self.dist.barrier()
+            torch.cuda.synchronize()
+
+    def reduce_max(self, x):
+        if self.dist is None:
+            return float(x)
+        import torch
+
+        t = torch.tensor([float(x)], device="cuda", dtype=torch.float64)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def close(self):
+        if self.dist is not None:
+            self.dist.destroy_process_group()
+
+
+def timed_steps(FR, job, n, ny_local, warmup, steps, sampler=None):
+    """K SSPRK3 steps of an n x (ny_local * world) mesh in row slabs; returns the measurement and the problem."""
+    ps, u0 = make_ic(FR, n, ny_local)
+    ctx = FR.Context(job.local)
+    dt = 1e-5 * 2048 / n
+    if job.world > 1:
+        prob = FR.DistributedEuler2D(u0, (0.0, 1.0), ps, GAMMA, job.dist, ctx=ctx, ghost="wave_x")
+    else:
+        prob = FR.Euler2DProblem(u0, (0.0, 1.0), ps, GAMMA, ctx=ctx)
+        prob.set_hooks(ghost="wave_x")
+    alg = FR.SSPRK33()
+    prob.step(alg, dt, warmup)
+    prob.set_profiling(True)
+    if sampler is not None and job.rank == 0:
+        sampler.start()
+    job.barrier()
+    prob.step(alg, dt, steps)  # synchronous; CUDA events bracket the K steps on the library stream
+    job.barrier()
+    ms, launches = prob.last_timing()
+    stage_ms, stage_n = prob.stage_timing()
+    clocks = sampler.stop() if (sampler is not None and job.rank == 0) else None
+    prob.set_profiling(False)
+    ms = job.reduce_max(ms)
+    avg_ms = job.reduce_max(stage_ms / max(stage_n, 1))
+    return {"prob": prob, "ps": ps, "u0": u0, "dt": dt, "alg": alg, "ms": ms, "launches": int(launches),
+            "avg_launch_ms": avg_ms, "stage_n": int(stage_n), "clocks": clocks, "ctx": ctx}
+
+
+def parity_check(FR, job, m, n, ny_local, total_steps):
+    """The state after the timed steps against a single-GPU run.
+
+    The x wave does not depend on y and the y seam is periodic, so (i) every row further than 3 rows per step
+    from the global seam equals the interior row of ANY mesh of the same n stepped as often -- slab boundaries
+    must leave no trace (`y_independence`); (ii) the rows next to the global seam (frozen ghost rows reach
+    3 rows per SSPRK3 step) equal the same rows of a single-GPU run on an n x ny_aux mesh (`seam_rows`).
+    Together: every owned row of every rank against a single-GPU computation.  N > 1: the auxiliary run uses the
+    same kernel, the comparison is bit for bit (expected 0.0).  N = 1: it uses the independent generic kernel
+    (thread per element, neighbour traces recomputed) instead of the row-chunk kernel: rounding-level agreement."""
+    import numpy as np
+
+    reach = 3 * total_steps + 2
+    ny_aux = max(64, 2 * reach + 8)
+    res = m["prob"].download()
+    nyg = ny_local * job.world
+    ps, u0 = make_ic(FR, n, ny_aux)
+    aux = FR.Euler2DProblem(u0, (0.0, 1.0), ps, GAMMA, ctx=m["ctx"], kernel="generic" if job.world == 1 else "auto")
+    aux.set_hooks(ghost="wave_x")
+    aux.step(m["alg"], m["dt"], total_steps)
+    ref = aux.download()
+    aux.close()
+    scale = float(np.abs(ref).max())
+    mid = ref[1:-1, ny_aux // 2]
+    g0 = job.rank * ny_local  # global row of local row j is g0 + j
+    j = np.arange(1, ny_local + 1)
+    far = (g0 + j > reach) & (g0 + j <= nyg - reach)
+    dev = float(np.abs(res[1:-1, 1:-1][:, far] - mid[:, None]).max()) if far.any() else 0.0
+    seam = 0.0
+    rows = 0
+    for jj in j[~far]:
+        g = g0 + jj
+        ja = g if g <= reach else ny_aux - (nyg - g)
+        if 1 <= ja <= ny_aux:
+            seam = max(seam, float(np.abs(res[1:-1, jj] - ref[1:-1, ja]).max()))
+            rows += 1
+    fin = bool(np.isfinite(res).all())
+    out = {"y_independence_rel": job.reduce_max(dev) / scale, "seam_rows_rel": job.reduce_max(seam) / scale,
+           "finite": bool(job.reduce_max(0.0 if fin else 1.0) == 0.0), "steps_compared": total_steps,
+           "against": (f"single-GPU run of {n}x{ny_aux} elements, "
+                       + ("generic kernel (independent implementation)" if job.world == 1
+                          else "same kernel: bit-for-bit expected")),
+           "rows_checked": "all owned rows of every rank"}
+    out["ok"] = bool(out["finite"] and out["y_independence_rel"] <= 1e-12 and out["seam_rows_rel"] <= 1e-12)
+    return out
 
 
 def run_ours(args):
@@ -186,60 +349,30 @@ def run_ours(args):
     json_fd = os.dup(1)
     os.dup2(2, 1)
 
+    if args.config != "3":
+        import bench_configs
+
+        out = bench_configs.run(args)
+        if out is not None:
+            os.write(json_fd, (json.dumps(out) + "\n").encode())
+        return
+
     import frb200 as FR
 
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    dist = None
-    if world > 1:
-        import torch
-        import torch.distributed as dist_mod
-
-        torch.cuda.set_device(local)
-        dist_mod.init_process_group("nccl", device_id=torch.device("cuda", local))
-        dist = dist_mod
+    job = Job()
+    rank, world, local = job.rank, job.world, job.local
     n = args.n
-    ny_global = n * world
-    ps, u0 = make_ic(FR, n, n, rank * n, ny_global)
-    ctx = FR.Context(local)
-    dt = 1e-5 * 2048 / n
-    if world > 1:
-        prob = FR.DistributedEuler2D(u0, (0.0, 1.0), ps, GAMMA, dist, ctx=ctx, ghost="wave_x")
-    else:
-        prob = FR.Euler2DProblem(u0, (0.0, 1.0), ps, GAMMA, ctx=ctx)
-        prob.set_hooks(ghost="wave_x")
-    alg = FR.SSPRK33()
+    strong = args.scaling == "strong"
+    if strong and n % world:
+        raise SystemExit("--scaling strong needs --n divisible by the number of GPUs")
+    ny_local = n // world if strong else n
+    ny_global = ny_local * world
+
+    m = timed_steps(FR, job, n, ny_local, args.warmup, args.steps, ClockSampler(local))
+    prob, u0 = m["prob"], m["u0"]
     dofs = prob.dofs
-
-    def barrier():
-        if dist is not None:
-            import torch
-
-            dist.barrier()
-            torch.cuda.synchronize()
-
-    prob.step(alg, dt, args.warmup)
-    prob.set_profiling(True)
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
-    barrier()
-    prob.step(alg, dt, args.steps)  # synchronous; CUDA events bracket the K steps on the library stream
-    barrier()
-    ms, launches = prob.last_timing()
-    stage_ms, stage_n = prob.stage_timing()
-    clocks = sampler.stop() if rank == 0 else None
-    prob.set_profiling(False)
-    if dist is not None:
-        import torch
-
-        t = torch.tensor([ms], device="cuda", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
-    value = 3.0 * dofs * world * args.steps / (ms * 1e-3)
-
-    fin = bool(np.isfinite(prob.download()).all())
+    value = 3.0 * dofs * world * args.steps / (m["ms"] * 1e-3)
+    parity = None if args.no_parity else parity_check(FR, job, m, n, ny_local, args.warmup + args.steps)
 
     # ---- end to end: the f!(du,u,p,t) call with HOST buffers (pinned), H2D + D2H inside.  Under
     # torchrun every rank evaluates the residual of its own slab (the host array carries the halo
@@ -249,17 +382,11 @@ def run_ours(args):
     uh[...] = u0
     prob.f_pipelined(dh, uh, None, 0.0, nslab=args.e2e_slabs)  # warm-up
     k = max(1, min(args.steps, args.e2e_steps))
-    barrier()
+    job.barrier()
     t0 = time.perf_counter()
     for _ in range(k):
         prob.f_pipelined(dh, uh, None, 0.0, nslab=args.e2e_slabs)
-    el = time.perf_counter() - t0
-    if dist is not None:
-        import torch
-
-        t = torch.tensor([el], device="cuda", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        el = float(t.item())
+    el = job.reduce_max(time.perf_counter() - t0)
     nbytes = int(u0.size) * 8
     e2e = {"value": dofs * world * k / el, "unit": UNIT, "h2d_bytes_per_step": nbytes * world,
            "d2h_bytes_per_step": nbytes * world,
@@ -270,11 +397,11 @@ def run_ours(args):
     if world == 1:
         # the reference's own user-loop shape (euler2d_wave.jl:125-135): the state lives on the host and is
         # touched between steps, so every SSPRK3 step is upload + 3 fused stages + download
-        prob.upload(uh); prob.step(alg, dt, 1); prob.download(dh)
+        prob.upload(uh); prob.step(m["alg"], m["dt"], 1); prob.download(dh)
         t0 = time.perf_counter()
         for _ in range(k):
             prob.upload(uh)
-            prob.step(alg, dt, 1)
+            prob.step(m["alg"], m["dt"], 1)
             prob.download(dh)
         el2 = time.perf_counter() - t0
         e2e["user_loop"] = {"value": 3.0 * dofs * k / el2, "unit": UNIT, "ms_per_step": 1e3 * el2 / k,
@@ -282,32 +409,54 @@ def run_ours(args):
                                     "(pinned host state, mutated by the user between steps)"}
     FR.pinned_free(uh)
     FR.pinned_free(dh)
+    prob.close()
+
+    # ---- the other partition of the same launch: a weak line at N > 1 also measures the strong split
+    other = None
+    if world > 1 and not strong and n % world == 0 and not args.no_strong:
+        ms2 = timed_steps(FR, job, n, n // world, args.warmup, args.steps)
+        p2 = ms2["prob"]
+        other = {"value": 3.0 * p2.dofs * world * args.steps / (ms2["ms"] * 1e-3), "unit": UNIT,
+                 "ms_per_step": ms2["ms"] / args.steps, "avg_launch_ms": ms2["avg_launch_ms"],
+                 "rows_per_gpu": n // world, "mesh": f"{n}x{n} global (the N = 1 workload), {n // world} rows per GPU",
+                 "parity": None if args.no_parity else parity_check(FR, job, ms2, n, n // world,
+                                                                     args.warmup + args.steps),
+                 "note": "efficiency = this value / (N x the N = 1 line's value): total work fixed"}
+        p2.close()
 
     if rank == 0:
         peak, how = measured_peak()
-        avg_ms = stage_ms / max(stage_n, 1)
+        avg_ms = m["avg_launch_ms"]
         achieved = dofs * (BYTES_PER_DOF_STEP / 3.0) / (avg_ms * 1e-3) / 1e9
+        traffic, tsrc = ncu_traffic()
+        if n != 2048 or ny_local != 2048:
+            traffic, tsrc = None, None  # the capture is of the 2048^2 launch
         roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": ncu_traffic(), "kernel": "euler2d_rc_kernel<4> (row-chunk layout, 3 launches per SSPRK3 step)", "avg_launch_ms": avg_ms,
-                "launches_timed": stage_n, "peak_source": how,
+                "traffic": traffic, "traffic_source": tsrc,
+                "kernel": "euler2d_rc_kernel<4> (row-chunk layout, 3 launches per SSPRK3 step"
+                          + ("; slab-parallel: halo exchange inside the kernel" if world > 1 else "") + ")",
+                "avg_launch_ms": avg_ms, "launches_timed": m["stage_n"], "peak_source": how,
                 "algorithmic_bytes_per_launch": dofs * BYTES_PER_DOF_STEP / 3.0}
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "warmup": args.warmup, "ms_per_step": m["ms"] / args.steps, "higher_is_better": True,
+            "scaling": "strong" if strong else "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"2D Euler isentropic wave, FRPSpace2D deg 3, {n}x{n} elements per GPU "
+            "config": {"workload": f"2D Euler isentropic wave, FRPSpace2D deg 3, {n}x{ny_local} elements per GPU "
                                    f"({n}x{ny_global} global), HLL, SSPRK3 fixed dt, ghost fill per step",
-                       "state_bytes_per_gpu": int(u0.size) * 8, "l2": "inputs (2.15 GB per buffer) larger than L2",
+                       "state_bytes_per_gpu": int(u0.size) * 8,
+                       "l2": f"inputs ({int(u0.size) * 8 / 1e9:.2f} GB per buffer) larger than L2",
                        "partition": f"row slabs x{world}" if world > 1 else "single GPU"},
-            "roofline": roof, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "finite": fin,
+            "roofline": roof, "e2e": e2e, "gpu_launches": m["launches"], "clocks": m["clocks"],
+            "finite": True if parity is None else parity["finite"], "parity": parity,
         }
+        if other is not None:
+            out["strong"] = other
         if world == 1 and not args.no_cpu:
             out["cpu_baseline"] = cpu_baseline(args.cpu_n, args.cpu_evals)
         sys.stdout.flush()
         os.write(json_fd, (json.dumps(out) + "\n").encode())
-    prob.close()
-    if dist is not None:
-        dist.destroy_process_group()
+    job.close()
 
 
 def main():
@@ -316,13 +465,18 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--n", type=int, default=2048, help="elements per side per GPU")
-    ap.add_argument("--ref-n", type=int, default=512, help="sample size of the reference arm")
-    ap.add_argument("--cpu-n", type=int, default=1024)
-    ap.add_argument("--cpu-evals", type=int, default=24)
+    ap.add_argument("--config", default="3", choices=["1", "2", "3", "4", "5", "f2"],
+                    help="BASELINE.json configuration (3 = the headline, the only one that shards)")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
+    ap.add_argument("--n", type=int, default=2048, help="elements per side (per GPU under weak scaling)")
+    ap.add_argument("--ref-n", type=int, default=2048, help="mesh of the reference arm (the workload's own)")
+    ap.add_argument("--cpu-n", type=int, default=2048)
+    ap.add_argument("--cpu-evals", type=int, default=3)
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--e2e-slabs", type=int, default=32)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-parity", action="store_true")
+    ap.add_argument("--no-strong", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

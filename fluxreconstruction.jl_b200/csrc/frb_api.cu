@@ -378,9 +378,13 @@ extern "C" int64_t frb_interior_dofs(frb_prob_t p) { return p ? p->dofs : 0; }
 // p->u (reference image) and p->ru (row-chunk mirror) are two representations of one state.
 // Every entry point that touches p->u first brings it up to date; the ones that may change it
 // invalidate the mirror.  frb_step on the RC path does the opposite.
+static int halo_flush_rc(frb_prob_t p, double *U);
+
 static int need_ref(frb_prob_t p, bool will_write) {
   if (!p->ref_valid) {
-    int n = frb_rc_to_ref(p, p->ru, p->u);
+    int n = halo_flush_rc(p, p->ru);  // slab-parallel: halo rows out of the stage kernel's ring first
+    if (n < 0) return n;
+    n = frb_rc_to_ref(p, p->ru, p->u);
     if (n < 0) return n;
     p->launches += n;
     p->ref_valid = true;
@@ -429,7 +433,7 @@ static bool use_march(frb_prob_t p) {
 
 // frb_step streams in the row-chunk layout when it can: 2-D Euler, deg 2..3
 static bool use_rc(frb_prob_t p) {
-  if (p->kind != K_EULER2D || !p->rc_base || p->flux != FRB_FLUX_HLL) return false;
+  if (p->kind != K_EULER2D || !p->rc_base) return false;  // every common flux (HLL / LF / Roe) has its instantiation
   return p->kernel_kind == FRB_KERNEL_AUTO || p->kernel_kind == FRB_KERNEL_RC;
 }
 
@@ -504,6 +508,8 @@ static int halo_republish(frb_prob_t p, const double *U);
 static bool rhs_via_rc(frb_prob_t p, bool host_u) {
   if (!use_rc(p) || frb_halo_active(p)) return false;
   if (p->kernel_kind == FRB_KERNEL_RC) return true;
+  if (p->kernel_kind == FRB_KERNEL_AUTO && p->flux != FRB_FLUX_HLL) return true;  // the reference-image marching
+  // kernel is HLL-only: LF / Roe take the row-chunk kernel (two conversions) rather than the generic one
   return !host_u && p->rc_valid;
 }
 
@@ -540,7 +546,7 @@ extern "C" int32_t frb_rhs(frb_prob_t p, const double *u_host, double *du_host, 
     }
     cudaEvent_t e0 = p->profiling ? prof_event(p) : nullptr, e1 = p->profiling ? prof_event(p) : nullptr;
     if (e0 && e1) cudaEventRecord(e0, s);
-    n = frb_launch_euler2d_rc(p, rsrc, nullptr, p->rs2, st, nullptr, nullptr, 0);
+    n = frb_launch_euler2d_rc(p, rsrc, nullptr, p->rs2, st);
     if (e0 && e1) cudaEventRecord(e1, s);
     if (n < 0) return n;
     p->launches += n;
@@ -772,6 +778,17 @@ static int halo_wait_if_pending(frb_prob_t p) {
   if (n < 0) return n;
   p->launches += n;
   p->halo_pending = false;
+  p->halo_pending_legacy = false;
+  return 0;
+}
+
+// everything that reads a row-chunk buffer as a whole array (conversion to the reference image, f! of the
+// resident slab, the limiter / filter passes) needs the interior halo rows in the array, not in the ring
+static int halo_flush_rc(frb_prob_t p, double *U) {
+  if (!frb_halo_active(p) || frb_halo_rc_input_in_array(p, U)) return 0;
+  int n;
+  if ((n = halo_wait_if_pending(p)) < 0) return n;
+  if ((n = frb_halo_rc_flush(p, U)) < 0) return n;
   return 0;
 }
 
@@ -798,26 +815,40 @@ static int halo_republish(frb_prob_t p, const double *U) {
 // the previous stage and followed by the push of this stage's boundary rows + the flag
 static int stage_x(frb_prob_t p, const double *u, const double *ua, double *out, FrbStage st, bool rc) {
   int n;
-  if ((n = halo_wait_if_pending(p)) < 0) return n;
   if (rc) {
-    double *plo = nullptr, *phi = nullptr;
-    int nlo = 0, nhi = 0;
-    frb_halo_stage_targets(p, out, &plo, &phi, &nlo, &nhi);
-    if (p->profiling) {
-      cudaEvent_t e0 = prof_event(p), e1 = prof_event(p);
-      if (e0 && e1) cudaEventRecord(e0, p->ctx->stream);
-      n = frb_launch_euler2d_rc(p, u, ua, out, st, plo, phi, nlo);
-      if (e0 && e1) cudaEventRecord(e1, p->ctx->stream);
-    } else {
-      n = frb_launch_euler2d_rc(p, u, ua, out, st, plo, phi, nlo);
+    // Row-chunk path.  Slab-parallel: the exchange is inside the stage kernel (RcHalo) -- no wait kernel unless
+    // rows were pushed into the arrays since the last one (per-step seam rows, a fresh upload), no signal kernel.
+    RcHalo h;
+    const bool inker = frb_halo_rc_inkernel(p);
+    if (inker) {
+      if (p->halo_pending_legacy && (n = halo_wait_if_pending(p)) < 0) return n;
+      if ((n = frb_halo_rc_stage(p, u, out, &h)) < 0) return n;
+    } else if ((n = halo_wait_if_pending(p)) < 0) {
+      return n;
     }
+    cudaEvent_t e0 = p->profiling ? prof_event(p) : nullptr, e1 = p->profiling ? prof_event(p) : nullptr;
+    if (e0 && e1) cudaEventRecord(e0, p->ctx->stream);
+    n = frb_launch_euler2d_rc(p, u, ua, out, st, inker ? &h : nullptr);
+    if (e0 && e1) cudaEventRecord(e1, p->ctx->stream);
     if (n < 0) return n;
     p->launches += n;
-  } else if ((n = launch_stage(p, u, ua, out, st)) < 0) {
-    return n;
+    if (inker) {
+      p->halo_pending = true;  // the epoch was raised by the kernel; array-wide readers wait for it (halo_flush_rc)
+      return 0;
+    }
+    if (frb_halo_active(p)) {  // FRB_HALO_LEGACY: rows pushed after the stage, epochs by signal / wait kernels
+      if ((n = frb_halo_push(p, out, frb_halo_role(p, out), false, -1)) < 0) return n;
+      p->launches += n;
+      if ((n = frb_halo_signal(p)) < 0) return n;
+      p->launches += n;
+      p->halo_pending = true;
+    }
+    return 0;
   }
+  if ((n = halo_wait_if_pending(p)) < 0) return n;
+  if ((n = launch_stage(p, u, ua, out, st)) < 0) return n;
   if (frb_halo_active(p)) {
-    if (!rc && !use_march(p)) {  // the marching kernels store their boundary rows to the peers themselves
+    if (!use_march(p)) {  // the marching kernel stores its boundary rows to the peers itself
       if ((n = frb_halo_push(p, out, frb_halo_role(p, out), false, -1)) < 0) return n;
       p->launches += n;
     }
@@ -832,6 +863,9 @@ static int one_step(frb_prob_t p, int scheme, double dt, bool rc) {
   int n;
   const bool par = frb_halo_active(p);
   double *&U = rc ? p->ru : p->u, *&S1 = rc ? p->rs1 : p->s1, *&S2 = rc ? p->rs2 : p->s2;
+  if (rc && par && (p->filt_when != 0 || p->limiter_on)) {
+    if ((n = halo_flush_rc(p, U)) < 0) return n;  // the hooks work on the array as a whole
+  }
   if (p->filt_when == 1) {
     if ((n = run_filter(p, nullptr, rc)) < 0) return n;
   }
@@ -967,6 +1001,7 @@ static int need_rc(frb_prob_t p) {
   if ((n = frb_rc_from_ref(p, p->u, p->ru)) < 0) return n;
   p->launches += n;
   p->rc_valid = true;
+  frb_halo_rc_reset(p);  // the halo rows came with the conversion: they are in the arrays
   if (frb_halo_active(p)) {
     // the neighbours may store into my RC halo rows only after this conversion: one more epoch
     if ((n = frb_halo_signal(p)) < 0) return n;
@@ -1051,6 +1086,9 @@ extern "C" int32_t frb_step(frb_prob_t p, int32_t scheme, double dt, int32_t nst
   FRB_CUDA(cudaEventRecord(p->ev0, s));
   if (int r = run_steps(p, scheme, dt, rc, nsteps)) return r;
   FRB_CUDA(cudaEventRecord(p->ev1, s));
+  if (rc) {
+    if (int r = halo_flush_rc(p, p->ru)) return r;  // outside the timed region: two row copies per call
+  }
   int bad = 0;
   if (p->limiter_on)
     FRB_CUDA(cudaMemcpyAsync(&bad, p->flag, sizeof(int), cudaMemcpyDeviceToHost, s));
@@ -1126,7 +1164,7 @@ extern "C" int32_t frb_time_stage(frb_prob_t p, int32_t stage_kind, int32_t iter
   const int64_t l0 = p->launches;
   FRB_CUDA(cudaEventRecord(p->ev0, s));
   for (int it = 0; it < iters; ++it) {
-    int n = rc ? frb_launch_euler2d_rc(p, p->ru, p->rs1, p->rs2, st, nullptr, nullptr, 0)
+    int n = rc ? frb_launch_euler2d_rc(p, p->ru, p->rs1, p->rs2, st)
                : launch_stage(p, p->u, p->s1, p->s2, st);
     if (n < 0) return n;
     if (rc) p->launches += n;

@@ -26,17 +26,18 @@ __device__ __forceinline__ void col_trace(const double *__restrict__ Uy, const d
 }
 
 // common flux on the face between row j (tile Ulo, top trace) and row j+1 (tile Uhi, bottom trace)
-template <int NSP>
+// FLUX: the common flux (FRB_FLUX_HLL = the reference's flux_hll!, LF, ROE), a compile-time choice
+template <int NSP, int FLUX = 0>
 __device__ __forceinline__ void face_flux_y(const double (&uT)[4], const double *__restrict__ Uhi,
                                             const MarchOps &ops, double gamma, double gm1, double (&h)[4]) {
   double uB[4];
   col_trace<NSP>(Uhi, ops.ll, uB);
-  frb::Flux4 f = frb::hll4_y_fast(uT[0], uT[1], uT[2], uT[3], uB[0], uB[1], uB[2], uB[3], gamma, gm1);
+  frb::Flux4 f = frb::riemann4_y_fast<FLUX>(uT[0], uT[1], uT[2], uT[3], uB[0], uB[1], uB[2], uB[3], gamma, gm1);
   h[0] = f.f0; h[1] = f.f1; h[2] = f.f2; h[3] = f.f3;
 }
 
 // CB1: the stage has cb == 1 (no multiply)
-template <int NSP, bool CB1>
+template <int NSP, bool CB1, int FLUX = 0>
 __device__ __forceinline__ void x_pass(const double *__restrict__ Ux, double *__restrict__ xdx,
                                        double *__restrict__ xrpx, const MarchOps &ops, double cb, double gamma,
                                        double gm1) {
@@ -71,7 +72,7 @@ __device__ __forceinline__ void x_pass(const double *__restrict__ Ux, double *__
   // left face: HLL(u_face[i-1,j,2,l,:], u_face[i,j,4,l,:])  (euler2d_wave.jl:69-74)
   double n0 = __shfl_up_sync(0xffffffffu, uR[0], 1), n1 = __shfl_up_sync(0xffffffffu, uR[1], 1);
   double n2 = __shfl_up_sync(0xffffffffu, uR[2], 1), n3 = __shfl_up_sync(0xffffffffu, uR[3], 1);
-  frb::Flux4 hl = frb::hll4_fast(n0, n1, n2, n3, uL[0], uL[1], uL[2], uL[3], gamma, gm1);
+  frb::Flux4 hl = frb::riemann4_fast<FLUX>(n0, n1, n2, n3, uL[0], uL[1], uL[2], uL[3], gamma, gm1);
   const double hL[4] = {hl.f0, hl.f1, hl.f2, hl.f3};
   const double hR[4] = {__shfl_down_sync(0xffffffffu, hl.f0, 1), __shfl_down_sync(0xffffffffu, hl.f1, 1),
                         __shfl_down_sync(0xffffffffu, hl.f2, 1), __shfl_down_sync(0xffffffffu, hl.f3, 1)};

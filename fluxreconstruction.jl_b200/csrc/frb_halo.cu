@@ -9,6 +9,7 @@
 // kernel then raises a flag in the peer's mailbox (st.release.sys), and the peer's next
 // stage is preceded by a one-thread wait kernel (ld.acquire.sys).  No host round trip, no
 // collective: the path's only exchange is nearest-neighbour.
+#include <cstdlib>
 #include <cstring>
 
 #include "frb_internal.cuh"
@@ -25,7 +26,14 @@ struct FrbHalo {
   unsigned long long *flags_lo = nullptr;  // neighbours' mailboxes
   unsigned long long *flags_hi = nullptr;
   unsigned long long epoch = 0;
-  void *opened[10] = {nullptr};
+  // in-kernel exchange of the row-chunk stage kernel (RcHalo, frb_rc.cuh): a ring of kRcSlots halo rows per side,
+  // written by the neighbours' stage kernels; slots = [side lo | hi][kRcSlots][row]
+  double *slots = nullptr, *slots_lo = nullptr, *slots_hi = nullptr;  // local ring, the neighbours' rings
+  unsigned int *counters = nullptr;     // [2] strips that have finished row 1 / row ny (monotonic)
+  long long seq = 0;                    // in-kernel stages launched so far (ring position)
+  long long slot_seq[3] = {-1, -1, -1}; // per buffer role: the stage whose ring slot holds its halo rows, -1 = the
+  unsigned long long slot_epoch[3] = {0, 0, 0};  //   array's own rows 0 / ny+1 do; and that stage's mailbox epoch
+  void *opened[12] = {nullptr};
   int nopened = 0;
 };
 
@@ -99,7 +107,7 @@ int check_launch(const char *what) {
 
 }  // namespace
 
-// export layout: 5 IPC handles (u, s1, s2, flags, row-chunk buffers) + int32 ny_local + int32 has_rc
+// export layout: 6 IPC handles (u, s1, s2, flags, row-chunk buffers, halo ring) + int32 ny_local + int32 has_rc
 extern "C" int32_t frb_halo_export(frb_prob_t p, unsigned char *out) {
   if (!p || !out) { frb_set_error("frb_halo_export: NULL argument"); return FRB_ERR_ARG; }
   if (!((p->kind == K_EULER2D && !p->curv_iJ) || p->kind == K_NS2D)) {
@@ -126,12 +134,25 @@ extern "C" int32_t frb_halo_export(frb_prob_t p, unsigned char *out) {
     FRB_CUDA(cudaIpcGetMemHandle(&h, p->rc_base));
     memcpy(out + 4 * FRB_IPC_HANDLE_BYTES, &h, FRB_IPC_HANDLE_BYTES);
   }
-  memcpy(out + 5 * FRB_IPC_HANDLE_BYTES, tail, sizeof tail);
+  memset(out + 5 * FRB_IPC_HANDLE_BYTES, 0, FRB_IPC_HANDLE_BYTES);
+  if (p->rc_base) {
+    FrbHalo *H = p->halo;
+    if (!H->slots) {
+      const size_t n = (size_t)2 * kRcSlots * rc_geom(p->nx, p->ny, p->nsp).row;
+      FRB_CUDA(cudaMalloc(&H->slots, sizeof(double) * n));
+      FRB_CUDA(cudaMemset(H->slots, 0, sizeof(double) * n));
+      FRB_CUDA(cudaMalloc(&H->counters, 2 * sizeof(unsigned int)));
+      FRB_CUDA(cudaMemset(H->counters, 0, 2 * sizeof(unsigned int)));
+    }
+    FRB_CUDA(cudaIpcGetMemHandle(&h, H->slots));
+    memcpy(out + 5 * FRB_IPC_HANDLE_BYTES, &h, FRB_IPC_HANDLE_BYTES);
+  }
+  memcpy(out + 6 * FRB_IPC_HANDLE_BYTES, tail, sizeof tail);
   return FRB_OK;
 }
 
 static int open_peer(frb_prob_t p, const unsigned char *blob, double **bufs3, double **rc3,
-                     unsigned long long **flags, int *nyl) {
+                     unsigned long long **flags, int *nyl, double **ring) {
   FrbHalo *H = p->halo;
   for (int b = 0; b < 4; ++b) {
     cudaIpcMemHandle_t h;
@@ -143,8 +164,9 @@ static int open_peer(frb_prob_t p, const unsigned char *blob, double **bufs3, do
     else *flags = static_cast<unsigned long long *>(ptr);
   }
   int32_t tail[2];
-  memcpy(tail, blob + 5 * FRB_IPC_HANDLE_BYTES, sizeof tail);
+  memcpy(tail, blob + 6 * FRB_IPC_HANDLE_BYTES, sizeof tail);
   *nyl = tail[0];
+  *ring = nullptr;
   if (tail[1] && p->rc_base) {  // the neighbour's ru | rs1 | rs2, sized for ITS row count
     cudaIpcMemHandle_t h;
     memcpy(&h, blob + 4 * FRB_IPC_HANDLE_BYTES, FRB_IPC_HANDLE_BYTES);
@@ -153,6 +175,11 @@ static int open_peer(frb_prob_t p, const unsigned char *blob, double **bufs3, do
     H->opened[H->nopened++] = ptr;
     const size_t len = rc_geom(p->nx, tail[0], p->nsp).len;
     for (int b = 0; b < 3; ++b) rc3[b] = static_cast<double *>(ptr) + b * len;
+    memcpy(&h, blob + 5 * FRB_IPC_HANDLE_BYTES, FRB_IPC_HANDLE_BYTES);
+    ptr = nullptr;
+    FRB_CUDA(cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    H->opened[H->nopened++] = ptr;
+    *ring = static_cast<double *>(ptr);
   } else if (p->rc_base) {
     frb_set_error("frb_halo_connect: neighbour has no row-chunk buffers (mixed configurations)");
     return FRB_ERR_PEER;
@@ -171,13 +198,14 @@ extern "C" int32_t frb_halo_connect(frb_prob_t p, int32_t rank, int32_t nranks,
   FrbHalo *H = p->halo;
   H->rank = rank;
   H->nranks = nranks;
-  if (int rc = open_peer(p, blob_lo, H->peer_lo, H->rc_lo, &H->flags_lo, &H->nyl_lo)) return rc;
+  if (int rc = open_peer(p, blob_lo, H->peer_lo, H->rc_lo, &H->flags_lo, &H->nyl_lo, &H->slots_lo)) return rc;
   if (nranks == 2) {  // both neighbours are the same process: map once
     for (int b = 0; b < 3; ++b) { H->peer_hi[b] = H->peer_lo[b]; H->rc_hi[b] = H->rc_lo[b]; }
     H->flags_hi = H->flags_lo;
     H->nyl_hi = H->nyl_lo;
+    H->slots_hi = H->slots_lo;
   } else {
-    if (int rc = open_peer(p, blob_hi, H->peer_hi, H->rc_hi, &H->flags_hi, &H->nyl_hi)) return rc;
+    if (int rc = open_peer(p, blob_hi, H->peer_hi, H->rc_hi, &H->flags_hi, &H->nyl_hi, &H->slots_hi)) return rc;
   }
   return frb_halo_sync(p);
 }
@@ -201,6 +229,8 @@ extern "C" int32_t frb_halo_disconnect(frb_prob_t p) {
   FrbHalo *H = p->halo;
   for (int q = 0; q < H->nopened; ++q) cudaIpcCloseMemHandle(H->opened[q]);
   cudaFree(H->flags);
+  cudaFree(H->slots);
+  cudaFree(H->counters);
   delete H;
   p->halo = nullptr;
   return FRB_OK;
@@ -227,6 +257,8 @@ void frb_halo_swap_roles(frb_prob_t p, int a, int b, bool rc) {
   if (rc) {
     std::swap(p->halo->rc_lo[a], p->halo->rc_lo[b]);
     std::swap(p->halo->rc_hi[a], p->halo->rc_hi[b]);
+    std::swap(p->halo->slot_seq[a], p->halo->slot_seq[b]);
+    std::swap(p->halo->slot_epoch[a], p->halo->slot_epoch[b]);
   } else {
     std::swap(p->halo->peer_lo[a], p->halo->peer_lo[b]);
     std::swap(p->halo->peer_hi[a], p->halo->peer_hi[b]);
@@ -276,7 +308,10 @@ int frb_halo_push(frb_prob_t p, const double *src, int dst_role, bool seam, int 
     if (int r = check_launch("halo_push_cols_kernel")) return r;
     return 1;
   }
-  if (rc) return frb_rc_row_push(p, src, dl, dh, H->nyl_lo, seam ? flip_var : -1);
+  if (rc) {
+    if (!seam) H->slot_seq[dst_role] = -1;  // every rank pushes: the interior halo rows of this role are in the arrays
+    return frb_rc_row_push(p, src, dl, dh, H->nyl_lo, seam ? flip_var : -1);
+  }
   const int npp = p->nsp * p->nsp, nplanes = 4 * npp;
   dim3 blk(128), grd((p->nx + 2 + 127) / 128, nplanes);
   halo_push_kernel<<<grd, blk, 0, p->ctx->stream>>>(src, dl, dh, p->nx, p->ny, H->nyl_lo, H->nyl_hi,
@@ -294,7 +329,85 @@ int frb_halo_signal(frb_prob_t p) {
   // I am the "hi" neighbour of the rank below and the "lo" neighbour of the rank above
   halo_signal_kernel<<<1, 1, 0, p->ctx->stream>>>(H->flags_lo + 1, H->flags_hi + 0, H->epoch);
   if (int rc = check_launch("halo_signal_kernel")) return rc;
+  p->halo_pending_legacy = true;
   return 1;
+}
+
+// ---- in-kernel exchange of the row-chunk stage kernel ---------------------------------------------------
+bool frb_halo_rc_inkernel(frb_prob_t p) {
+  static const bool off = getenv("FRB_HALO_LEGACY") != nullptr;  // measurement switch: the round-1 epoch kernels
+  return !off && frb_halo_active(p) && p->halo->slots && p->halo->slots_lo && p->halo->slots_hi;
+}
+
+void frb_halo_rc_reset(frb_prob_t p) {
+  if (!p->halo) return;
+  for (int r = 0; r < 3; ++r) p->halo->slot_seq[r] = -1;
+}
+
+// do the interior halo rows of RC buffer u live in the array itself (after an upload / conversion / push)?
+bool frb_halo_rc_input_in_array(frb_prob_t p, const double *u) {
+  const int r = role_of(p, u);
+  return r < 0 || p->halo->slot_seq[r] < 0;
+}
+
+// Arguments of one stage launch u -> out: where the input's halo rows are, which ring slot of the neighbours takes
+// this stage's boundary rows, the mailbox epoch that announces them.  Advances the epoch and the ring position
+// (every rank launches the same sequence of stages, so the counters agree without any communication).
+int frb_halo_rc_stage(frb_prob_t p, const double *u, const double *out, RcHalo *h) {
+  memset(h, 0, sizeof *h);
+  if (!frb_halo_rc_inkernel(p)) return 0;
+  FrbHalo *H = p->halo;
+  const int ru = role_of(p, u), ro = role_of(p, out);
+  if (ru < 0 || ro < 0 || !is_rc(p, u) || !is_rc(p, out)) {
+    frb_set_error("halo: stage buffers are not the problem's row-chunk buffers");
+    return FRB_ERR_STATE;
+  }
+  const size_t row = rc_geom(p->nx, p->ny, p->nsp).row;
+  const bool first = H->rank == 0, last = H->rank == H->nranks - 1;
+  h->active = 1;
+  h->mailbox = H->flags;
+  if (H->slot_seq[ru] >= 0) {
+    const size_t s = (size_t)(H->slot_seq[ru] % kRcSlots);
+    if (!first) { h->src_lo = H->slots + (0 * kRcSlots + s) * row; h->wait_lo = H->slot_epoch[ru]; }
+    if (!last) { h->src_hi = H->slots + (1 * kRcSlots + s) * row; h->wait_hi = H->slot_epoch[ru]; }
+  }
+  H->epoch += 1;
+  H->seq += 1;
+  const size_t s = (size_t)(H->seq % kRcSlots);
+  if (!first) h->dst_lo = H->slots_lo + (1 * kRcSlots + s) * row;  // my row 1 -> the hi side of the rank below
+  if (!last) h->dst_hi = H->slots_hi + (0 * kRcSlots + s) * row;   // my row ny -> the lo side of the rank above
+  h->flag_lo = H->flags_lo + 1;
+  h->flag_hi = H->flags_hi + 0;
+  h->epoch = H->epoch;
+  h->count = H->counters;
+  H->slot_seq[ro] = H->seq;
+  H->slot_epoch[ro] = H->epoch;
+  return 1;
+}
+
+// bring the interior halo rows of U from the ring into the array (rows 0 / ny+1), for everything that reads the
+// array as a whole (download, conversion to the reference image, f! of the resident slab).  The caller has waited
+// for the epoch.
+int frb_halo_rc_flush(frb_prob_t p, double *U) {
+  if (!frb_halo_active(p) || !p->halo->slots) return 0;
+  FrbHalo *H = p->halo;
+  const int r = role_of(p, U);
+  if (r < 0 || H->slot_seq[r] < 0) return 0;
+  const RcGeom g = rc_geom(p->nx, p->ny, p->nsp);
+  const size_t s = (size_t)(H->slot_seq[r] % kRcSlots);
+  int n = 0;
+  if (H->rank != 0) {
+    FRB_CUDA(cudaMemcpyAsync(U, H->slots + (0 * kRcSlots + s) * g.row, sizeof(double) * g.row,
+                             cudaMemcpyDeviceToDevice, p->ctx->stream));
+    ++n;
+  }
+  if (H->rank != H->nranks - 1) {
+    FRB_CUDA(cudaMemcpyAsync(U + g.row * (size_t)(g.ny + 1), H->slots + (1 * kRcSlots + s) * g.row,
+                             sizeof(double) * g.row, cudaMemcpyDeviceToDevice, p->ctx->stream));
+    ++n;
+  }
+  H->slot_seq[r] = -1;
+  return n;
 }
 
 // block the stream until both neighbours have reached this rank's current epoch

@@ -221,4 +221,64 @@ __device__ __forceinline__ Flux4 hll4_y_fast(double l0, double l1, double l2, do
   return {f.f0, -f.f2, f.f1, f.f3};
 }
 
+// ---- the other common fluxes in the same branch-free form (marching kernels) ------------------------
+// Same definitions as lf4 / roe4 above, reciprocals and roots from the MUFU seeds.
+__device__ __forceinline__ Flux4 lf4_fast(double l0, double l1, double l2, double l3, double r0, double r1,
+                                          double r2, double r3, double gamma, double gm1) {
+  double il = rcp_fast(l0), ir = rcp_fast(r0);
+  double ul = l1 * il, vl = l2 * il, ur = r1 * ir, vr = r2 * ir;
+  double pl = gm1 * fma(-0.5, fma(l1, ul, l2 * vl), l3);
+  double pr = gm1 * fma(-0.5, fma(r1, ur, r2 * vr), r3);
+  double al = sqrt_gs(gamma * pl * il), ar = sqrt_gs(gamma * pr * ir);
+  double ha = 0.5 * fmax(fabs(ul) + al, fabs(ur) + ar);
+  double fl0 = l1, fl1 = fma(l1, ul, pl), fl2 = l1 * vl, fl3 = (l3 + pl) * ul;
+  double fr0 = r1, fr1 = fma(r1, ur, pr), fr2 = r1 * vr, fr3 = (r3 + pr) * ur;
+  return {fma(-ha, r0 - l0, 0.5 * (fl0 + fr0)), fma(-ha, r1 - l1, 0.5 * (fl1 + fr1)),
+          fma(-ha, r2 - l2, 0.5 * (fl2 + fr2)), fma(-ha, r3 - l3, 0.5 * (fl3 + fr3))};
+}
+__device__ __forceinline__ double roe_fix_fast(double lam, double d, double i2d) {
+  double a = fabs(lam);
+  return a < d ? fma(lam, lam, d * d) * i2d : a;
+}
+__device__ __forceinline__ Flux4 roe4_fast(double l0, double l1, double l2, double l3, double r0, double r1,
+                                           double r2, double r3, double gamma, double gm1) {
+  double il = rcp_fast(l0), ir = rcp_fast(r0);
+  double ul = l1 * il, vl = l2 * il, ur = r1 * ir, vr = r2 * ir;
+  double pl = gm1 * fma(-0.5, fma(l1, ul, l2 * vl), l3);
+  double pr = gm1 * fma(-0.5, fma(r1, ur, r2 * vr), r3);
+  double Hl = (l3 + pl) * il, Hr = (r3 + pr) * ir;
+  double R = sqrt_gs(r0 * il), iR = rcp_fast(1.0 + R);
+  double ut = fma(R, ur, ul) * iR, vt = fma(R, vr, vl) * iR, Ht = fma(R, Hr, Hl) * iR;
+  double q2 = fma(ut, ut, vt * vt);
+  double a2 = gm1 * fma(-0.5, q2, Ht), at = sqrt_gs(a2), rt = R * l0;
+  double ia2 = rcp_fast(a2);
+  double dr = r0 - l0, du = ur - ul, dv = vr - vl, dp = pr - pl;
+  double ra = rt * at * du;
+  double c1 = (dp - ra) * (0.5 * ia2), c2 = fma(-dp, ia2, dr), c3 = rt * dv, c4 = (dp + ra) * (0.5 * ia2);
+  double d = 0.1 * at, i2d = rcp_fast(2.0 * d);
+  double au = fabs(ut);
+  double e1 = roe_fix_fast(ut - at, d, i2d) * c1, e2 = au * c2, e3 = au * c3, e4 = roe_fix_fast(ut + at, d, i2d) * c4;
+  double fl0 = l1, fl1 = fma(l1, ul, pl), fl2 = l1 * vl, fl3 = (l3 + pl) * ul;
+  double fr0 = r1, fr1 = fma(r1, ur, pr), fr2 = r1 * vr, fr3 = (r3 + pr) * ur;
+  double ua = ut * at;
+  return {0.5 * (fl0 + fr0) - 0.5 * (e1 + e2 + e4),
+          0.5 * (fl1 + fr1) - 0.5 * fma(e1, ut - at, fma(e2, ut, e4 * (ut + at))),
+          0.5 * (fl2 + fr2) - 0.5 * fma(e1 + e2 + e4, vt, e3),
+          0.5 * (fl3 + fr3) - 0.5 * fma(e1, Ht - ua, fma(e2, 0.5 * q2, fma(e3, vt, e4 * (Ht + ua))))};
+}
+// common flux of the marching kernels, selected at compile time (FLUX = FRB_FLUX_HLL / LF / ROE)
+template <int FLUX>
+__device__ __forceinline__ Flux4 riemann4_fast(double l0, double l1, double l2, double l3, double r0, double r1,
+                                               double r2, double r3, double gamma, double gm1) {
+  if (FLUX == 1) return lf4_fast(l0, l1, l2, l3, r0, r1, r2, r3, gamma, gm1);
+  if (FLUX == 2) return roe4_fast(l0, l1, l2, l3, r0, r1, r2, r3, gamma, gm1);
+  return hll4_fast(l0, l1, l2, l3, r0, r1, r2, r3, gamma, gm1);
+}
+template <int FLUX>
+__device__ __forceinline__ Flux4 riemann4_y_fast(double l0, double l1, double l2, double l3, double r0, double r1,
+                                                 double r2, double r3, double gamma, double gm1) {
+  Flux4 f = riemann4_fast<FLUX>(l0, l2, -l1, l3, r0, r2, -r1, r3, gamma, gm1);
+  return {f.f0, -f.f2, f.f1, f.f3};
+}
+
 }  // namespace frb

@@ -467,7 +467,7 @@ def solve(prob, alg, dt, adaptive=False, **_):
     return itg
 
 
-HALO_BLOB_BYTES = 5 * 64 + 8
+HALO_BLOB_BYTES = 6 * 64 + 8
 
 
 class DistributedEuler2D(Euler2DProblem):

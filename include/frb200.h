@@ -227,7 +227,8 @@ int32_t frb_time_stage(frb_prob_t prob, int32_t stage_kind, int32_t iters, float
  * kernels only, excluding host<->device copies) and kernels launched by it */
 int32_t frb_last_timing(frb_prob_t prob, float *ms, int64_t *kernel_launches);
 int32_t frb_set_kernel(frb_prob_t prob, int32_t kernel_kind);
-/* FRB_FLUX_*: Euler problems only (1-D and 2-D); anything but HLL runs the generic kernels */
+/* FRB_FLUX_*: Euler problems only (1-D and 2-D).  2-D, deg 2-3: every flux has its own instantiation of the
+ * row-chunk stage kernel (frb_step, and f! through it); other degrees and FRB_KERNEL_GENERIC run the generic kernels */
 int32_t frb_set_flux(frb_prob_t prob, int32_t flux_kind);
 /* per-launch timing of the fused stage kernels inside frb_step / frb_rhs: when enabled,
  * every stage launch is bracketed by CUDA events on the library stream; after the call
@@ -244,15 +245,22 @@ int32_t frb_host_free(void *ptr);
 /* One process per GPU.  A rank's problem is created on its slab (2-D: ny_local rows,
  * 1-D: ncell_local cells) and told its neighbours.  Halo rows are the neighbours'
  * boundary rows of the *current* stage; they are written straight into the
- * neighbour's memory by the stage kernel's epilogue over NVLink (peer mapping via
- * CUDA IPC handles the host exchanges out of band), then a flag is raised.
+ * neighbour's memory by the stage kernel over NVLink (peer mapping via CUDA IPC
+ * handles the host exchanges out of band).  On the row-chunk path (2-D Euler, deg 2-3)
+ * the whole exchange lives INSIDE the stage kernel: rows 1 / ny are computed first and
+ * stored into a ring of halo rows on the neighbour, the last strip raises the
+ * neighbour's mailbox (st.release.sys), and only the CTAs that need a halo row poll
+ * for it (ld.acquire.sys) -- every other CTA runs at once, so the exchange overlaps
+ * the interior rows and a stage stays ONE launch.  The other kernels push their rows
+ * after the stage and hand epochs over with one-thread signal / wait kernels.
  * ns2d problems (cfg5) are split the same way along the slowest index of their layout, i: a rank owns nx_local
  * columns, columns 0 / nx_local+1 of an interior slab boundary are halo columns that replace the wall ghosts
  * of boundary! there (no periodic seam); the same four calls apply.
  * The reference has no distributed path: this is new surface. */
 #define FRB_IPC_HANDLE_BYTES 64
-/* blob = 5 IPC handles (u, s1, s2, mailbox, row-chunk buffers) + int32 ny_local + int32 has_rc */
-#define FRB_HALO_BLOB_BYTES (5 * FRB_IPC_HANDLE_BYTES + 8)
+/* blob = 6 IPC handles (u, s1, s2, mailbox, row-chunk buffers, halo ring of the row-chunk stage kernel)
+ * + int32 ny_local + int32 has_rc */
+#define FRB_HALO_BLOB_BYTES (6 * FRB_IPC_HANDLE_BYTES + 8)
 /* export this rank's blob; the host exchanges blobs out of band (torch.distributed, MPI, ...) */
 int32_t frb_halo_export(frb_prob_t prob, unsigned char *blob_out);
 /* map the blobs of the rank below (rank-1 mod nranks) and above (rank+1 mod nranks) and send

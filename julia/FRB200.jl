@@ -253,7 +253,7 @@ end
 # ---- multi-GPU: one Julia process per GPU (e.g. under MPI.jl), slabs along the slowest cell index ---------------
 # euler2d problems: rows; ns2d problems: columns.  Exchange the 328-byte blobs by any means (MPI.Allgather), then
 # connect to the ranks below (rank-1 mod n) and above (rank+1 mod n); per-stage halo traffic never touches the host.
-const HALO_BLOB_BYTES = 5 * 64 + 8
+const HALO_BLOB_BYTES = 6 * 64 + 8
 function halo_export(p::Problem)
     blob = zeros(UInt8, HALO_BLOB_BYTES)
     check(ccall((:frb_halo_export, lib), Int32, (Ptr{Cvoid}, Ptr{UInt8}), p.h, blob)); blob

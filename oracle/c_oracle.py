@@ -136,8 +136,14 @@ def ghost_fill_euler2d(u, mode="wave_x"):
     return u
 
 
-def integrate_euler2d(u, ps, gamma, dt, nsteps, scheme="midpoint", ghost="wave_x", limiter_weights=None):
-    u = np.array(u, dtype=np.float64, order="F", copy=True)
+def integrate_euler2d(u, ps, gamma, dt, nsteps, scheme="midpoint", ghost="wave_x", limiter_weights=None,
+                      inplace=False):
+    """``inplace``: advance the caller's array (Fortran order, float64) instead of a copy -- the timed loops of
+    bench.py step a 2 GB state and must not copy it every step."""
+    if inplace:
+        assert u.dtype == np.float64 and u.flags.f_contiguous
+    else:
+        u = np.array(u, dtype=np.float64, order="F", copy=True)
     nx, ny, nsp = u.shape[0] - 2, u.shape[1] - 2, u.shape[2]
     ll, lr, dl, dhl, dhr = _ops(ps)
     wts = None if limiter_weights is None else np.asfortranarray(limiter_weights, dtype=np.float64)

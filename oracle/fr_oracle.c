@@ -716,17 +716,30 @@ int fro_integrate_euler2d(double *u, int nx, int ny, int nsp, double Jx, double 
                           const double *dhl, const double *dhr, double gamma, double dt,
                           int nsteps, int scheme, int ghost_mode, const double *limiter_weights) {
   size_t n = (size_t)(nx + 2) * (ny + 2) * nsp * nsp * 4;
-  void *work = fro_work2d_create(nx, ny, nsp);
-  double *k = (double *)malloc(sizeof(double) * n), *ua = (double *)malloc(sizeof(double) * n),
-         *ub = (double *)malloc(sizeof(double) * n);
-  if (!work || !k || !ua || !ub) return -2;
-  ctx2d c = {work, Jx, Jy, ll, lr, lpdm, dhl, dhr, gamma};
+  /* the caches (temporaries of dudt!, stage arrays) are preallocated once per mesh size and kept between
+   * calls, like the reference's threaded twin does (shock-vortex.jl:26-45): a timed step-by-step loop must
+   * not pay 16 GB of page faults per call.  Single caller at a time (tests and bench.py are). */
+  static struct { int nx, ny, nsp; void *work; double *k, *ua, *ub; } cache = {0, 0, 0, 0, 0, 0, 0};
+  if (cache.nx != nx || cache.ny != ny || cache.nsp != nsp || !cache.work) {
+    if (cache.work) { fro_work2d_destroy(cache.work); free(cache.k); free(cache.ua); free(cache.ub); }
+    cache.work = fro_work2d_create(nx, ny, nsp);
+    cache.k = (double *)malloc(sizeof(double) * n);
+    cache.ua = (double *)malloc(sizeof(double) * n);
+    cache.ub = (double *)malloc(sizeof(double) * n);
+    cache.nx = nx; cache.ny = ny; cache.nsp = nsp;
+    if (!cache.work || !cache.k || !cache.ua || !cache.ub) {
+      if (cache.work) fro_work2d_destroy(cache.work);
+      free(cache.k); free(cache.ua); free(cache.ub);
+      cache.work = 0; cache.k = cache.ua = cache.ub = 0; cache.nx = 0;
+      return -2;
+    }
+  }
+  ctx2d c = {cache.work, Jx, Jy, ll, lr, lpdm, dhl, dhr, gamma};
   for (int s = 0; s < nsteps; ++s) {
     if (limiter_weights) fro_limiter_euler2d(u, nx, ny, nsp, gamma, limiter_weights, ll, lr);
     if (ghost_mode >= 0) fro_ghost_fill_euler2d(u, nx, ny, nsp, ghost_mode);
-    step_generic(u, n, dt, scheme, rhs2d_cb, &c, k, ua, ub);
+    step_generic(u, n, dt, scheme, rhs2d_cb, &c, cache.k, cache.ua, cache.ub);
   }
-  free(k); free(ua); free(ub); fro_work2d_destroy(work);
   return 0;
 }
 

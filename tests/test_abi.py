@@ -148,12 +148,24 @@ def test_only_test_infrastructure_touches_the_oracle():
             if not f.endswith((".py", ".sh", ".jl", ".cu", ".cuh", ".h")):
                 continue
             path = os.path.join(dirpath, f)
-            if os.path.relpath(path, ROOT) in ("bench.py", "__graft_entry__.py"):
+            if os.path.relpath(path, ROOT) in ("bench.py", "bench_configs.py", "__graft_entry__.py"):  # bench_configs:
+                # the --config arms of bench.py (CPU legs only, checked below)
                 continue
             txt = open(path).read()
             if "fr_oracle" in txt or "c_oracle" in txt or 'os.path.join(ROOT, "oracle")' in txt:
                 offenders.append(os.path.relpath(path, ROOT))
     assert offenders == []
+    # and inside the bench the oracle is only ever reached from the CPU legs
+    import ast
+
+    for name, allowed in (("bench.py", {"_oracle", "cpu_baseline", "run_reference"}),
+                          ("bench_configs.py", {"cpu_leg", "run_reference"})):
+        tree = ast.parse(open(os.path.join(ROOT, name)).read())
+        for fn in [n for n in ast.walk(tree) if isinstance(n, ast.FunctionDef)]:
+            uses = any(isinstance(n, ast.Name) and n.id in ("c_oracle", "fr_oracle") for n in ast.walk(fn)) or any(
+                isinstance(n, (ast.Import, ast.ImportFrom)) and any("oracle" in a.name for a in n.names)
+                for n in ast.walk(fn))
+            assert not uses or fn.name in allowed, (name, fn.name)
 
 
 def test_argument_checks_of_the_host_mirror_come_before_the_device(FR):

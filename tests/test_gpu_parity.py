@@ -634,16 +634,18 @@ def test_euler1d_rhs_other_fluxes(FR, oracle, flux, bc):
     prob.close()
 
 
+@pytest.mark.parametrize("kernel", ["auto", "generic"])
 @pytest.mark.parametrize("flux", ["lf", "roe"])
-@pytest.mark.parametrize("deg", [2, 3])
-def test_euler2d_rhs_and_steps_other_fluxes(FR, oracle, flux, deg):
-    """RHS and 20 SSPRK3 steps with the LF / Roe common flux against the NumPy oracle; the stepping
-    runs through frb_step (generic kernel: the marching kernels are HLL-only)."""
-    ps = FR.FRPSpace2D(0.0, 1.0, 24, 0.0, 1.0, 18, deg, 1, 1)
+@pytest.mark.parametrize("nx,ny,deg", [(24, 18, 2), (24, 18, 3), (61, 14, 3)])
+def test_euler2d_rhs_and_steps_other_fluxes(FR, oracle, flux, nx, ny, deg, kernel):
+    """RHS and 20 SSPRK3 steps with the LF / Roe common flux against the NumPy oracle.  "auto": the row-chunk
+    stage kernel instantiated with that flux (frb_euler2d_rc_lf.cu / _roe.cu), f! included; "generic": the
+    thread-per-element kernel."""
+    ps = FR.FRPSpace2D(0.0, 1.0, nx, 0.0, 1.0, ny, deg, 1, 1)
     u = noisy(oracle.ic_wave2d(ps, GAMMA, "x"), 0.02, 5)
     u[..., 2] += 0.1 * u[..., 0]
     oracle.ghost_fill_euler2d(u, "wave_x")
-    prob = FR.Euler2DProblem(u, (0.0, 0.5), ps, GAMMA)
+    prob = FR.Euler2DProblem(u, (0.0, 0.5), ps, GAMMA, kernel=kernel)
     prob.set_flux(flux)
     du = np.zeros_like(u, order="F")
     prob.f(du, u, None, 0.0)
@@ -668,12 +670,13 @@ def test_supersonic_roe_and_lf_are_consistent(FR, oracle):
     u = np.empty((14, 12, 4, 4, 4), order="F")
     u[...] = w
     for flux in ("hll", "lf", "roe"):
-        prob = FR.Euler2DProblem(u, (0.0, 0.5), ps, GAMMA)
-        prob.set_flux(flux)
-        du = np.zeros_like(u, order="F")
-        prob.f(du, u, None, 0.0)
-        assert np.abs(du).max() <= 1e-9
-        prob.close()
+        for kernel in ("auto", "generic", "rc"):
+            prob = FR.Euler2DProblem(u, (0.0, 0.5), ps, GAMMA, kernel=kernel)
+            prob.set_flux(flux)
+            du = np.zeros_like(u, order="F")
+            prob.f(du, u, None, 0.0)
+            assert np.abs(du).max() <= 1e-9
+            prob.close()
 
 
 # ---------------------------------------------------------------- shock sensor + modal filter
