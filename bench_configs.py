@@ -187,27 +187,40 @@ def run(args):
     stages = alg.stages
     # small problems: many steps per timed call, so that the call is not one launch latency
     inner = {"1": 2000, "2": 500, "4": 50, "5": 1, "f2": 1}[cfg]
-    prob.step(alg, dt, max(args.warmup, 3) * inner)
-    prob.upload(b["u0"])  # cfg5's forward Euler at the script's dt is beyond its stability limit at this size: the
-    # timed steps start from the initial state again and stay finite
+    # cfg5: forward Euler at the script's dt = cfl min(dx, dy) / 3 is beyond its stability limit on a fine p3 mesh
+    # (rounding noise grows ~4 x per step, the C oracle does the same), so the timed steps run in
+    # groups of `group` steps from the initial state (re-uploaded outside the timed region): the arithmetic is the
+    # same whatever the data, and the state stays finite
+    group = 4 if cfg == "5" else None
+    prob.step(alg, dt, (group or max(args.warmup, 3) * inner))
+    prob.upload(b["u0"])
     sampler = bench.ClockSampler(local)
     if rank == 0:
         sampler.start()
     job.barrier()
     nsteps = args.steps * inner
-    if cfg == "5":
-        nsteps = min(nsteps, 12)
-    prob.step(alg, dt, nsteps)
+    fin = True
+    if group:
+        ms, launches, done = 0.0, 0, 0
+        while done < nsteps:
+            k = min(group, nsteps - done)
+            prob.step(alg, dt, k)
+            m1, l1 = prob.last_timing()
+            ms += m1; launches += l1; done += k
+            fin = fin and bool(np.isfinite(prob.download()).all())
+            prob.upload(b["u0"])
+    else:
+        prob.step(alg, dt, nsteps)
+        ms, launches = prob.last_timing()
+        fin = bool(np.isfinite(prob.download()).all())
     job.barrier()
-    ms, launches = prob.last_timing()
     clocks = sampler.stop() if rank == 0 else None
     ms = job.reduce_max(ms)
-    fin = bool(np.isfinite(prob.download()).all())
     value = stages * dofs * world * nsteps / (ms * 1e-3)
     # per-stage timing (events around every stage launch; eager launches, so not for the one-launch loop of cfg1)
     prob.upload(b["u0"])
     prob.set_profiling(True)
-    prob.step(alg, dt, min(nsteps, 10))
+    prob.step(alg, dt, min(nsteps, group or 10))
     st_ms, st_n = prob.stage_timing()
     prob.set_profiling(False)
     avg = st_ms / max(st_n, 1)

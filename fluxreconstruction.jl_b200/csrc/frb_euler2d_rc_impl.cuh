@@ -11,6 +11,17 @@
 #include "frb_ptx.cuh"
 #include "frb_rc.cuh"
 
+// HALO (template parameter of the kernel): the slab-parallel code -- halo ring, mailbox polls, peer stores -- is
+// compiled into its own instantiations; single-domain launches run kernels without it (11 registers less, ~1 %)
+#define RC_HALO_ACTIVE(P) (HALO)
+// kernel experiment switches (scripts/build_variants.py): ring depth and CTAs per SM of the 16-B stage at p3
+#ifndef FRB_RC_NBUF16
+#define FRB_RC_NBUF16 3
+#endif
+#ifndef FRB_RC_MINB16
+#define FRB_RC_MINB16 3
+#endif
+
 namespace frbrc {
 
 
@@ -65,9 +76,9 @@ struct SmemRc {
 };
 
 // CB1: the stage has cb == 1 (u' = u + dt L(u), first stage of every scheme): no multiply
-template <int NSP, bool USEA, bool SAMEJ, int MINB, bool CB1, int FLUX>
+template <int NSP, bool USEA, bool SAMEJ, int MINB, bool CB1, int FLUX, bool HALO>
 __global__ void __launch_bounds__(NSP * 32, MINB) euler2d_rc_kernel(RcParams P, MarchOps ops) {
-  constexpr int NBUF = USEA ? 2 : 3;
+  constexpr int NBUF = USEA ? 2 : FRB_RC_NBUF16;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   using SM = SmemRc<NSP, NBUF, USEA>;
   SM &S = *reinterpret_cast<SM *>(smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u));
@@ -83,7 +94,7 @@ __global__ void __launch_bounds__(NSP * 32, MINB) euler2d_rc_kernel(RcParams P, 
   // row segment of this CTA.  Slab-parallel launches: rows 1 and ny are one-row segments of their own, first in
   // launch order, so that the rows the neighbours wait for leave in the first microseconds of the launch
   int ja, jb;
-  if (!P.h.active) {
+  if (!RC_HALO_ACTIVE(P)) {
     ja = 1 + blockIdx.y * P.rows_per_seg;
     jb = min(g.ny, ja + P.rows_per_seg - 1);
   } else if (blockIdx.y == 0) {
@@ -109,7 +120,7 @@ __global__ void __launch_bounds__(NSP * 32, MINB) euler2d_rc_kernel(RcParams P, 
   // Where row r of the input comes from: the array itself, or -- rows 0 / ny+1 of a slab whose neighbour stores
   // its boundary row into this rank's halo ring -- the local slot of the stage that produced the input.
   auto is_slot = [&](int r) -> bool {
-    return P.h.active && ((r == 0 && P.h.src_lo != nullptr) || (r == g.ny + 1 && P.h.src_hi != nullptr));
+    return RC_HALO_ACTIVE(P) && ((r == 0 && P.h.src_lo != nullptr) || (r == g.ny + 1 && P.h.src_hi != nullptr));
   };
   // thread 0: one bulk copy of the strip's chunk of row r into ring buffer b
   auto issue_bulk = [&](int b, int r) {
@@ -199,7 +210,8 @@ __global__ void __launch_bounds__(NSP * 32, MINB) euler2d_rc_kernel(RcParams P, 
       // of a value equals its tile offset
       double *const po = P.out + (size_t)j * g.row + strip_off + offy;
       // slab-parallel: row 1 / row ny also goes into the neighbour's halo ring (peer memory), warp-uniform
-      const bool to_lo = P.h.dst_lo != nullptr && j == 1, to_hi = P.h.dst_hi != nullptr && j == g.ny;
+      const bool to_lo = RC_HALO_ACTIVE(P) && P.h.dst_lo != nullptr && j == 1;
+      const bool to_hi = RC_HALO_ACTIVE(P) && P.h.dst_hi != nullptr && j == g.ny;
 #pragma unroll
       for (int m = 0; m < 4; ++m) {
         double v[NSP];
@@ -235,7 +247,7 @@ __global__ void __launch_bounds__(NSP * 32, MINB) euler2d_rc_kernel(RcParams P, 
     }
     __syncthreads();  // (B) every read of tile[buf], un, xd, xrp is done; every store of row j is issued
 
-    if (P.h.active && threadIdx.x == 0 && (j == 1 || j == g.ny)) {
+    if (RC_HALO_ACTIVE(P) && threadIdx.x == 0 && (j == 1 || j == g.ny)) {
       // this strip's part of a boundary row is out (locally and in the neighbour's ring), and the halo row next
       // to it has been consumed: count it, the last strip raises the neighbour's flag
       __threadfence_system();
@@ -279,9 +291,9 @@ static inline int rc_rows_per_seg(frb_prob_t p, const RcGeom &g, int ctas_per_sm
   return (g.ny + nseg - 1) / nseg;
 }
 
-template <int NSP, bool USEA, bool SAMEJ, int MINB, bool CB1, int FLUX>
+template <int NSP, bool USEA, bool SAMEJ, int MINB, bool CB1, int FLUX, bool HALO>
 int launch_rc(frb_prob_t p, RcParams rp, const MarchOps &mo) {
-  constexpr int NBUF = USEA ? 2 : 3;
+  constexpr int NBUF = USEA ? 2 : FRB_RC_NBUF16;
   rp.rows_per_seg = rc_rows_per_seg(p, rp.g, MINB, USEA);
   int segs = (rp.g.ny + rp.rows_per_seg - 1) / rp.rows_per_seg;
   if (rp.h.active) {  // rows 1 and ny as one-row segments (blockIdx.y 0, 1), rows 2 .. ny-1 in normal segments
@@ -295,37 +307,42 @@ int launch_rc(frb_prob_t p, RcParams rp, const MarchOps &mo) {
   static std::atomic<unsigned long long> attr_done{0};
   const unsigned long long dev_bit = 1ull << (p->ctx->device & 63);
   if (!(attr_done.load(std::memory_order_acquire) & dev_bit)) {
-    FRB_CUDA(cudaFuncSetAttribute(euler2d_rc_kernel<NSP, USEA, SAMEJ, MINB, CB1, FLUX>,
+    FRB_CUDA(cudaFuncSetAttribute(euler2d_rc_kernel<NSP, USEA, SAMEJ, MINB, CB1, FLUX, HALO>,
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    FRB_CUDA(cudaFuncSetAttribute(euler2d_rc_kernel<NSP, USEA, SAMEJ, MINB, CB1, FLUX>,
+    FRB_CUDA(cudaFuncSetAttribute(euler2d_rc_kernel<NSP, USEA, SAMEJ, MINB, CB1, FLUX, HALO>,
                                   cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     attr_done.fetch_or(dev_bit, std::memory_order_release);
   }
   dim3 grd(rp.g.ns, segs), blk(NSP * 32);
-  euler2d_rc_kernel<NSP, USEA, SAMEJ, MINB, CB1, FLUX><<<grd, blk, smem, p->ctx->stream>>>(rp, mo);
+  euler2d_rc_kernel<NSP, USEA, SAMEJ, MINB, CB1, FLUX, HALO><<<grd, blk, smem, p->ctx->stream>>>(rp, mo);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return frb_cuda_fail(e, "euler2d_rc_kernel", __FILE__, __LINE__);
   return 1;
 }
 
-template <int NSP, int MINB, int FLUX>
+template <int NSP, int MINB, int FLUX, bool HALO>
 int dispatch_rc(frb_prob_t p, const RcParams &rp, const MarchOps &mo, bool usea, bool samej) {
   if (usea)
-    return samej ? launch_rc<NSP, true, true, MINB, false, FLUX>(p, rp, mo)
-                 : launch_rc<NSP, true, false, MINB, false, FLUX>(p, rp, mo);
+    return samej ? launch_rc<NSP, true, true, MINB, false, FLUX, HALO>(p, rp, mo)
+                 : launch_rc<NSP, true, false, MINB, false, FLUX, HALO>(p, rp, mo);
+  constexpr int M16 = NSP == 4 ? FRB_RC_MINB16 : MINB;  // 16-B stages: no u_n tile, room for another CTA
   if (rp.cb == 1.0)
-    return samej ? launch_rc<NSP, false, true, MINB, true, FLUX>(p, rp, mo)
-                 : launch_rc<NSP, false, false, MINB, true, FLUX>(p, rp, mo);
-  return samej ? launch_rc<NSP, false, true, MINB, false, FLUX>(p, rp, mo)
-               : launch_rc<NSP, false, false, MINB, false, FLUX>(p, rp, mo);
+    return samej ? launch_rc<NSP, false, true, M16, true, FLUX, HALO>(p, rp, mo)
+                 : launch_rc<NSP, false, false, M16, true, FLUX, HALO>(p, rp, mo);
+  return samej ? launch_rc<NSP, false, true, M16, false, FLUX, HALO>(p, rp, mo)
+               : launch_rc<NSP, false, false, M16, false, FLUX, HALO>(p, rp, mo);
 }
 
 // one translation unit per common flux instantiates this (frb_euler2d_rc.cu: HLL, frb_euler2d_rc_lf.cu,
 // frb_euler2d_rc_roe.cu): the three builds run in parallel
 template <int FLUX>
 int dispatch_rc_flux(frb_prob_t p, const RcParams &rp, const MarchOps &mo, bool usea, bool samej) {
-  if (p->nsp == 4) return dispatch_rc<4, 3, FLUX>(p, rp, mo, usea, samej);
-  return dispatch_rc<3, 4, FLUX>(p, rp, mo, usea, samej);
+  if (rp.h.active) {
+    if (p->nsp == 4) return dispatch_rc<4, 3, FLUX, true>(p, rp, mo, usea, samej);
+    return dispatch_rc<3, 4, FLUX, true>(p, rp, mo, usea, samej);
+  }
+  if (p->nsp == 4) return dispatch_rc<4, 3, FLUX, false>(p, rp, mo, usea, samej);
+  return dispatch_rc<3, 4, FLUX, false>(p, rp, mo, usea, samej);
 }
 
 

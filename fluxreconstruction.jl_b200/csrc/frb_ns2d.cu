@@ -22,18 +22,28 @@
 // cell's interface slope uses dll and the right cell's dlr (:213-214,:244-245); slopes are not
 // rotated on y faces (:260); Mv of the LEFT state in the right state's time slope (:102).
 #include "frb_internal.cuh"
+#include "frb_physics.cuh"
 
 namespace {
 
+// Reciprocals: an IEEE FP64 division is a ~35-instruction subroutine on this part and the literal formulas
+// divide ~45 times per interface point and ~27 times per solution point -- half of all executed instructions
+// in the round-1 kernels (ncu: profiles/r02_cfg5.md).  Every state therefore carries 1/rho and 1/lambda, computed
+// once with the MUFU-seeded Newton reciprocal of the 2-D Euler path (frb::rcp_fast, ~1 ulp), and the closures
+// multiply.  The results move by an ulp or two: far inside the 1e-12 parity bound.
+using frb::rcp_fast;
+
 struct Prim4 {
-  double rho, U, V, lam;
+  double rho, U, V, lam, ir, il;  // ir = 1 / rho, il = 1 / lambda
 };
 __device__ __forceinline__ Prim4 conserve_prim(const double *w, double gm1) {
   Prim4 p;
   p.rho = w[0];
-  p.U = w[1] / w[0];
-  p.V = w[2] / w[0];
-  p.lam = 0.5 * w[0] / gm1 / (w[3] - 0.5 * (w[1] * w[1] + w[2] * w[2]) / w[0]);
+  p.ir = rcp_fast(w[0]);
+  p.U = w[1] * p.ir;
+  p.V = w[2] * p.ir;
+  p.il = 2.0 * gm1 * (w[3] - 0.5 * (w[1] * p.U + w[2] * p.V)) * p.ir;  // 1 / lambda = 2 (gamma - 1) rho e / rho
+  p.lam = rcp_fast(p.il);
   return p;
 }
 
@@ -43,31 +53,33 @@ struct Moments {
 };
 // (the recurrences multiply by h = 1/(2 lambda) instead of dividing by lambda: one reciprocal per
 // state instead of fifteen IEEE divisions; well inside the 1e-12 parity bound)
-__device__ __forceinline__ void moments_v(double V, double lam, double *Mv) {
-  const double h = 0.5 / lam;
+__device__ __forceinline__ void moments_v(double V, double il, double *Mv) {
+  const double h = 0.5 * il;
   Mv[0] = 1.0;
   Mv[1] = V;
 #pragma unroll
-  for (int i = 2; i <= 6; ++i) Mv[i] = V * Mv[i - 1] + (i - 1) * h * Mv[i - 2];
+  for (int i = 2; i <= 4; ++i) Mv[i] = V * Mv[i - 1] + (i - 1) * h * Mv[i - 2];  // <v^5>, <v^6> are never used
 }
-__device__ __forceinline__ void moments_half(double U, double lam, double *MuL, double *MuR) {
-  const double sl = sqrt(lam);
-  const double e = 0.5 * exp(-lam * U * U) / sqrt(3.14159265358979323846 * lam);
-  MuL[0] = 0.5 * erfc(-sl * U);
+__device__ __forceinline__ void moments_half(double U, double lam, double il, double *MuL, double *MuR) {
+  // one erfc per state: erfc of the non-negative argument (accurate where it is small), its mirror 2 - erfc
+  const double sl = sqrt(lam), x = sl * U;
+  const double ec = erfc(fabs(x)), eb = 2.0 - ec;
+  const double e = 0.5 * exp(-lam * U * U) * (0.56418958354775628695 * sl * il);  // / sqrt(pi lambda) = sqrt(lambda) / (sqrt(pi) lambda)
+  MuL[0] = 0.5 * (x >= 0.0 ? eb : ec);  // 0.5 erfc(-sqrt(lambda) U)
   MuL[1] = U * MuL[0] + e;
-  MuR[0] = 0.5 * erfc(sl * U);
+  MuR[0] = 0.5 * (x >= 0.0 ? ec : eb);  // 0.5 erfc(+sqrt(lambda) U)
   MuR[1] = U * MuR[0] - e;
-  const double h = 0.5 / lam;
+  const double h = 0.5 * il;
 #pragma unroll
   for (int i = 2; i <= 6; ++i) {
     MuL[i] = U * MuL[i - 1] + (i - 1) * h * MuL[i - 2];
     MuR[i] = U * MuR[i - 1] + (i - 1) * h * MuR[i - 2];
   }
 }
-__device__ __forceinline__ void mxi(double K, double lam, double *M) {
+__device__ __forceinline__ void mxi(double K, double il, double *M) {
   M[0] = 1.0;
-  M[1] = 0.5 * K / lam;
-  M[2] = (K * K + 2.0 * K) / (4.0 * lam * lam);
+  M[1] = 0.5 * K * il;
+  M[2] = 0.25 * (K * K + 2.0 * K) * (il * il);
 }
 // [KB] moments_conserve(Mu, Mv, Mw, a, b, d)
 __device__ __forceinline__ void mom_cons(const double *Mu, const double *Mv, const double *Mw, int a,
@@ -78,40 +90,64 @@ __device__ __forceinline__ void mom_cons(const double *Mu, const double *Mv, con
   uv[3] = 0.5 * (Mu[a + 2] * Mv[b] * Mw[d / 2] + Mu[a] * Mv[b + 2] * Mw[d / 2] +
                  Mu[a] * Mv[b] * Mw[(d + 2) / 2]);
 }
-// [KB] moments_conserve_slope(sl, Mu, Mv, Mw, a, b)
-__device__ __forceinline__ void mom_slope(const double *sl, const double *Mu, const double *Mv,
-                                          const double *Mw, int a, int b, double *au) {
-  double t0[4], t1[4], t2[4], t3[4], t4[4], t5[4];
-  mom_cons(Mu, Mv, Mw, a, b, 0, t0);
-  mom_cons(Mu, Mv, Mw, a + 1, b, 0, t1);
-  mom_cons(Mu, Mv, Mw, a, b + 1, 0, t2);
-  mom_cons(Mu, Mv, Mw, a + 2, b, 0, t3);
-  mom_cons(Mu, Mv, Mw, a, b + 2, 0, t4);
-  mom_cons(Mu, Mv, Mw, a, b, 2, t5);
-#pragma unroll
-  for (int m = 0; m < 4; ++m)
-    au[m] = sl[0] * t0[m] + sl[1] * t1[m] + sl[2] * t2[m] + 0.5 * sl[3] * (t3[m] + t4[m] + t5[m]);
+// [KB] moments_conserve_slope(sl, Mu, Mv, Mw, a, 0), factored.  Every call of the path has b = 0, so the v and xi
+// moments enter only through five constants of the state and the sum of six moments_conserve terms
+//   au = sl0 <psi u^a> + sl1 <psi u^(a+1)> + sl2 <psi v u^a> + sl3 <psi T u^a>,  T = (u^2 + v^2 + xi^2)/2,
+// psi = (1, u, v, T), collapses to (m_i = Mu[a + i], V_k = Mv[k], X_k = Mxi[k]):
+//   E_i = <T u^(a+i)>  = (m_(i+2) + A0 m_i)/2                 A0 = V2 + X1
+//   F   = <T v u^a>    = (V1 m_2 + B0 m_0)/2                  B0 = V3 + V1 X1
+//   Q   = <T^2 u^a>    = (m_4 + 2 A0 m_2 + C0 m_0)/4          C0 = V4 + X2 + 2 V2 X1
+// -- ~35 flops instead of ~100 per call (six calls per interface point), the same value to rounding
+// (checked against the literal form of the oracle, fr_oracle.py: moments_conserve_slope_2d).
+struct SlopeConst {
+  double V1, V2, A0, B0, C0;
+};
+__device__ __forceinline__ SlopeConst slope_const(const double *Mv, const double *Mw) {
+  SlopeConst c;
+  c.V1 = Mv[1];
+  c.V2 = Mv[2];
+  c.A0 = Mv[2] + Mw[1];
+  c.B0 = Mv[3] + Mv[1] * Mw[1];
+  c.C0 = Mv[4] + Mw[2] + 2.0 * Mv[2] * Mw[1];
+  return c;
+}
+__device__ __forceinline__ void mom_slope(const double *sl, const double *m, const SlopeConst &c, double *au) {
+  const double E0 = 0.5 * (m[2] + c.A0 * m[0]), E1 = 0.5 * (m[3] + c.A0 * m[1]);
+  const double F0 = 0.5 * (c.V1 * m[2] + c.B0 * m[0]);
+  const double Q0 = 0.25 * (m[4] + 2.0 * c.A0 * m[2] + c.C0 * m[0]);
+  const double k = sl[0] + sl[2] * c.V1;
+  au[0] = k * m[0] + sl[1] * m[1] + sl[3] * E0;
+  au[1] = k * m[1] + sl[1] * m[2] + sl[3] * E1;
+  au[2] = (sl[0] * c.V1 + sl[2] * c.V2) * m[0] + sl[1] * c.V1 * m[1] + sl[3] * F0;
+  au[3] = sl[0] * E0 + sl[1] * E1 + sl[2] * F0 + sl[3] * Q0;
+}
+// [KB] moments_conserve(Mu, Mv, Mw, a, 0, 0) in the same terms
+__device__ __forceinline__ void mom_cons0(const double *m, const SlopeConst &c, double *uv) {
+  uv[0] = m[0];
+  uv[1] = m[1];
+  uv[2] = m[0] * c.V1;
+  uv[3] = 0.5 * (m[2] + c.A0 * m[0]);
 }
 // [KB] pdf_slope(prim, sw, K)
-__device__ __forceinline__ void pdf_slope(const Prim4 &p, const double *sw, double K, double *sl) {
-  sl[3] = 4.0 * p.lam * p.lam / (K + 2.0) / p.rho *
-          (2.0 * sw[3] - 2.0 * p.U * sw[1] - 2.0 * p.V * sw[2] +
-           sw[0] * (p.U * p.U + p.V * p.V - 0.5 * (K + 2.0) / p.lam));
-  sl[2] = 2.0 * p.lam / p.rho * (sw[2] - p.V * sw[0]) - p.V * sl[3];
-  sl[1] = 2.0 * p.lam / p.rho * (sw[1] - p.U * sw[0]) - p.U * sl[3];
-  sl[0] = sw[0] / p.rho - p.U * sl[1] - p.V * sl[2] -
-          0.5 * (p.U * p.U + p.V * p.V + 0.5 * (K + 2.0) / p.lam) * sl[3];
+__device__ __forceinline__ void pdf_slope(const Prim4 &p, const double *sw, double K, double iK2, double *sl) {
+  const double q2 = p.U * p.U + p.V * p.V, hk = 0.5 * (K + 2.0) * p.il, l2r = 2.0 * p.lam * p.ir;
+  sl[3] = 4.0 * p.lam * p.lam * iK2 * p.ir *
+          (2.0 * sw[3] - 2.0 * p.U * sw[1] - 2.0 * p.V * sw[2] + sw[0] * (q2 - hk));
+  sl[2] = l2r * (sw[2] - p.V * sw[0]) - p.V * sl[3];
+  sl[1] = l2r * (sw[1] - p.U * sw[0]) - p.U * sl[3];
+  sl[0] = sw[0] * p.ir - p.U * sl[1] - p.V * sl[2] - 0.5 * (q2 + hk) * sl[3];
 }
 
 struct GasPar {
   double K, gamma, mu, omega, dt;
+  double gm1, iK2, iJx, iJy;  // gamma - 1, 1 / (K + 2), 1 / Jx, 1 / Jy: set by the launcher
 };
 
 // flux_gks!(fw, w, K, gamma, mu, omega, zeros(4))  (ns_cavity.jl:49-73): with zero slopes
 // a = A = 0, so fw = rho * <u psi>  (the Maxwellian's own moments: Mu[0] = 1, Mu[1] = U)
 __device__ __forceinline__ void gks_point_fluxes(const double *w, const GasPar &g, double *F, double *G) {
-  const Prim4 p = conserve_prim(w, g.gamma - 1.0);
-  const double h = 0.5 / p.lam;
+  const Prim4 p = conserve_prim(w, g.gm1);
+  const double h = 0.5 * p.il;
   const double U2 = p.U * p.U + h, V2 = p.V * p.V + h;      // <u^2>, <v^2>
   const double U3 = p.U * U2 + 2.0 * h * p.U;               // <u^3>
   const double V3 = p.V * V2 + 2.0 * h * p.V;
@@ -130,52 +166,50 @@ __device__ __forceinline__ void gks_point_fluxes(const double *w, const GasPar &
 // face-normal frame
 __device__ __forceinline__ void gks_face_flux(double *fw, const double *wL, const double *wR,
                                            const double *swL, const double *swR, GasPar g) {
-  const double gm1 = g.gamma - 1.0;
-  const Prim4 pL = conserve_prim(wL, gm1), pR = conserve_prim(wR, gm1);
-  double MuL1[7], MuR1[7], Mu1[7], Mv1[7], Mxi1[3];
-  double MuL2[7], MuR2[7], Mu2[7], Mv2[7], Mxi2[3];
-  moments_half(pL.U, pL.lam, MuL1, MuR1);
-  moments_half(pR.U, pR.lam, MuL2, MuR2);
+  const Prim4 pL = conserve_prim(wL, g.gm1), pR = conserve_prim(wR, g.gm1);
+  double MuL1[7], MuR1[7], Mu1[7], Mv1[5], Mxi1[3];
+  double MuL2[7], MuR2[7], Mu2[7], Mv2[5], Mxi2[3];
+  moments_half(pL.U, pL.lam, pL.il, MuL1, MuR1);
+  moments_half(pR.U, pR.lam, pR.il, MuL2, MuR2);
 #pragma unroll
   for (int i = 0; i <= 6; ++i) { Mu1[i] = MuL1[i] + MuR1[i]; Mu2[i] = MuL2[i] + MuR2[i]; }
-  moments_v(pL.V, pL.lam, Mv1);
-  moments_v(pR.V, pR.lam, Mv2);
-  mxi(g.K, pL.lam, Mxi1);
-  mxi(g.K, pR.lam, Mxi2);
+  moments_v(pL.V, pL.il, Mv1);
+  moments_v(pR.V, pR.il, Mv2);
+  mxi(g.K, pL.il, Mxi1);
+  mxi(g.K, pR.il, Mxi2);
+  const SlopeConst cL = slope_const(Mv1, Mxi1), cR = slope_const(Mv2, Mxi2);
+  const SlopeConst cLR = slope_const(Mv1, Mxi2);  // Mv1 with the right state's xi moments: as written in ns_cavity.jl:102
   double a0[4], b0[4], w[4];
-  mom_cons(MuL1, Mv1, Mxi1, 0, 0, 0, a0);
-  mom_cons(MuR2, Mv2, Mxi2, 0, 0, 0, b0);
+  mom_cons0(MuL1, cL, a0);
+  mom_cons0(MuR2, cR, b0);
 #pragma unroll
   for (int m = 0; m < 4; ++m) w[m] = pL.rho * a0[m] + pR.rho * b0[m];
-  const Prim4 pc = conserve_prim(w, gm1);
-  const double tau = g.mu * 2.0 * pow(pc.lam, 1.0 - g.omega) / pc.rho +
-                     2.0 * g.dt * fabs(pL.rho / pL.lam - pR.rho / pR.lam) / (pL.rho / pL.lam + pR.rho / pR.lam);
+  const Prim4 pc = conserve_prim(w, g.gm1);
+  // vhs_collision_time: mu 2 lambda^(1 - omega) / rho, the power as exp((1 - omega) log lambda)
+  const double eL = pL.rho * pL.il, eR = pR.rho * pR.il;
+  const double tau = g.mu * 2.0 * exp((1.0 - g.omega) * log(pc.lam)) * pc.ir + 2.0 * g.dt * fabs(eL - eR) * rcp_fast(eL + eR);
   double faL[4], faTL[4], faR[4], faTR[4], sw[4];
-  pdf_slope(pL, swL, g.K, faL);
-  mom_slope(faL, Mu1, Mv1, Mxi1, 1, 0, sw);
+  pdf_slope(pL, swL, g.K, g.iK2, faL);
+  mom_slope(faL, Mu1 + 1, cL, sw);
 #pragma unroll
   for (int m = 0; m < 4; ++m) sw[m] = -pL.rho * sw[m];
-  pdf_slope(pL, sw, g.K, faTL);
-  pdf_slope(pR, swR, g.K, faR);
-  mom_slope(faR, Mu2, Mv1, Mxi2, 1, 0, sw);  // Mv1: as written in ns_cavity.jl:102
+  pdf_slope(pL, sw, g.K, g.iK2, faTL);
+  pdf_slope(pR, swR, g.K, g.iK2, faR);
+  mom_slope(faR, Mu2 + 1, cLR, sw);
 #pragma unroll
   for (int m = 0; m < 4; ++m) sw[m] = -pR.rho * sw[m];
-  pdf_slope(pR, sw, g.K, faTR);
-  // Mt[1] = dt - Mt[4] = 0: the central-state term drops out; Mt[4] = dt
+  pdf_slope(pR, sw, g.K, g.iK2, faTR);
+  // Mt[1] = dt - Mt[4] = 0: the central-state term drops out; Mt[4] = dt cancels against the final / dt
   double MuvL[4], MauL[4], MauLT[4], MuvR[4], MauR[4], MauRT[4];
-  mom_cons(MuL1, Mv1, Mxi1, 1, 0, 0, MuvL);
-  mom_slope(faL, MuL1, Mv1, Mxi1, 2, 0, MauL);
-  mom_slope(faTL, MuL1, Mv1, Mxi1, 1, 0, MauLT);
-  mom_cons(MuR2, Mv2, Mxi2, 1, 0, 0, MuvR);
-  mom_slope(faR, MuR2, Mv2, Mxi2, 2, 0, MauR);
-  mom_slope(faTR, MuR2, Mv2, Mxi2, 1, 0, MauRT);
-  const double dt = g.dt;
+  mom_cons0(MuL1 + 1, cL, MuvL);
+  mom_slope(faL, MuL1 + 2, cL, MauL);
+  mom_slope(faTL, MuL1 + 1, cL, MauLT);
+  mom_cons0(MuR2 + 1, cR, MuvR);
+  mom_slope(faR, MuR2 + 2, cR, MauR);
+  mom_slope(faTR, MuR2 + 1, cR, MauRT);
 #pragma unroll
-  for (int m = 0; m < 4; ++m) {
-    double f = dt * pL.rho * MuvL[m] - tau * dt * pL.rho * MauL[m] - tau * dt * pL.rho * MauLT[m] +
-               dt * pR.rho * MuvR[m] - tau * dt * pR.rho * MauR[m] - tau * dt * pR.rho * MauRT[m];
-    fw[m] = f / dt;
-  }
+  for (int m = 0; m < 4; ++m)
+    fw[m] = pL.rho * (MuvL[m] - tau * (MauL[m] + MauLT[m])) + pR.rho * (MuvR[m] - tau * (MauR[m] + MauRT[m]));
 }
 
 template <int NSP>
@@ -242,7 +276,7 @@ ns_face_kernel(const double *__restrict__ u, double *__restrict__ fhx, double *_
   const double *eB = u + eoff<NSP>(j, i, nyg);
   // stride of the contracted index and offset of the fixed one inside an element block
   const int sq = yface ? 4 : 4 * NSP, base = yface ? 4 * NSP * r : 4 * r;
-  const double iJ = 1.0 / (yface ? Jy : Jx);
+  const double iJ = yface ? gas.iJy : gas.iJx;
   double wA[4], wB[4], sA[4], sB[4];
 #pragma unroll
   for (int m = 0; m < 4; ++m) {
@@ -257,15 +291,13 @@ ns_face_kernel(const double *__restrict__ u, double *__restrict__ fhx, double *_
     }
     wA[m] = a; wB[m] = b; sA[m] = c * iJ; sB[m] = d * iJ;
   }
-  double fw[4];
-  if (yface) {  // local_frame(w, 0, 1) = (w0, w2, -w1, w3); global_frame(f, 0, 1) = (f0, -f2, f1, f3)
-    const double lA[4] = {wA[0], wA[2], -wA[1], wA[3]}, lB[4] = {wB[0], wB[2], -wB[1], wB[3]};
-    double h[4];
-    gks_face_flux(h, lA, lB, sA, sB, gas);
-    fw[0] = h[0]; fw[1] = -h[2]; fw[2] = h[1]; fw[3] = h[3];
-  } else {
-    gks_face_flux(fw, wA, wB, sA, sB, gas);
-  }
+  // local_frame(w, 0, 1) = (w0, w2, -w1, w3) on y faces, global_frame(f, 0, 1) = (f0, -f2, f1, f3) on the way back:
+  // by selects, so that the flux routine is instantiated once (half the code: the kernel lives in the I-cache)
+  const double lA[4] = {wA[0], yface ? wA[2] : wA[1], yface ? -wA[1] : wA[2], wA[3]};
+  const double lB[4] = {wB[0], yface ? wB[2] : wB[1], yface ? -wB[1] : wB[2], wB[3]};
+  double h[4];
+  gks_face_flux(h, lA, lB, sA, sB, gas);
+  const double fw[4] = {h[0], yface ? -h[2] : h[1], yface ? h[1] : h[2], h[3]};
   double *o = yface ? fhy + 4 * (r + NSP * ((long long)(j - 1) + (long long)(ny + 1) * (i - 1)))
                     : fhx + 4 * (r + NSP * ((long long)(j - 1) + (long long)ny * (i - 1)));
   o[0] = fw[0]; o[1] = fw[1]; o[2] = fw[2]; o[3] = fw[3];
@@ -295,7 +327,7 @@ ns_elem_kernel(const double *__restrict__ u, const double *__restrict__ ua, doub
     double F[4], G[4];  // ns_cavity.jl:169-187
     gks_point_fluxes(w, gas, F, G);
 #pragma unroll
-    for (int m = 0; m < 4; ++m) { sF[el][pt][m] = F[m] / Jx; sG[el][pt][m] = G[m] / Jy; }
+    for (int m = 0; m < 4; ++m) { sF[el][pt][m] = F[m] * gas.iJx; sG[el][pt][m] = G[m] * gas.iJy; }
   }
   __syncthreads();
   if (!live) return;
@@ -316,8 +348,8 @@ ns_elem_kernel(const double *__restrict__ u, const double *__restrict__ ua, doub
       gB += fy * ops.ll[q]; gT += fy * ops.lr[q];
     }
     double du = r1 + r2;
-    du += (hl[m] / Jx - fL) * ops.dgl[k] + (hr[m] / Jx - fR) * ops.dgr[k];  // :271-274
-    du += (hb[m] / Jy - gB) * ops.dgl[l] + (ht[m] / Jy - gT) * ops.dgr[l];  // :275-278
+    du += (hl[m] * gas.iJx - fL) * ops.dgl[k] + (hr[m] * gas.iJx - fR) * ops.dgr[k];  // :271-274
+    du += (hb[m] * gas.iJy - gB) * ops.dgl[l] + (ht[m] * gas.iJy - gT) * ops.dgr[l];  // :275-278
     const double d = -du;
     double r;
     if (st.rhs_only) r = d;
@@ -387,7 +419,8 @@ int frb_launch_ns2d(frb_prob_t p, const double *u, const double *ua, double *out
     if (int rc = check_launch("ns_ring_stage_kernel")) return rc;
     n += 1;
   }
-  GasPar gas = {p->gks_K, p->gamma, p->gks_mu, p->gks_omega, p->gks_dt};
+  GasPar gas = {p->gks_K, p->gamma, p->gks_mu, p->gks_omega, p->gks_dt,
+                p->gamma - 1.0, 1.0 / (p->gks_K + 2.0), 1.0 / p->Jx, 1.0 / p->Jy};
   const long long nfx = (long long)p->nsp * p->ny * (p->nx + 1), nfy = (long long)p->nsp * (p->ny + 1) * p->nx;
   if (!p->ns_flux) FRB_CUDA(cudaMalloc(&p->ns_flux, sizeof(double) * 4 * (nfx + nfy)));
   double *fhx = p->ns_flux, *fhy = p->ns_flux + 4 * nfx;
