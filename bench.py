@@ -293,6 +293,29 @@ def timed_steps(FR, job, n, ny_local, warmup, steps, sampler=None):
             "avg_launch_ms": avg_ms, "stage_n": int(stage_n), "clocks": clocks, "ctx": ctx}
 
 
+def e2e_leg(FR, job, prob, u0, nslab, k):
+    """f!(du, u, p, t) through the C ABI with pinned HOST buffers, k calls, all ranks at once"""
+    uh = FR.pinned_empty(u0.shape)
+    dh = FR.pinned_empty(u0.shape)
+    uh[...] = u0
+    nslab = max(1, min(nslab, (u0.shape[1] - 2) // 2))
+    prob.f_pipelined(dh, uh, None, 0.0, nslab=nslab)  # warm-up
+    job.barrier()
+    t0 = time.perf_counter()
+    for _ in range(k):
+        prob.f_pipelined(dh, uh, None, 0.0, nslab=nslab)
+    el = job.reduce_max(time.perf_counter() - t0)
+    nbytes = int(u0.size) * 8
+    world = job.world
+    e2e = {"value": prob.dofs * world * k / el, "unit": UNIT, "h2d_bytes_per_step": nbytes * world,
+           "d2h_bytes_per_step": nbytes * world,
+           "call": f"frb_rhs_pipelined(prob, u_host, du_host, {nslab}): the f!(du,u,p,t) shape with pinned "
+                   "host buffers; upload, fused residual and download overlapped in row slabs"
+                   + (f"; {world} ranks, one slab each, concurrently" if world > 1 else ""),
+           "ms_per_call": 1e3 * el / k}
+    return e2e, uh, dh
+
+
 def parity_check(FR, job, m, n, ny_local, total_steps):
     """The state after the timed steps against a single-GPU run.
 
@@ -377,23 +400,8 @@ def run_ours(args):
     # ---- end to end: the f!(du,u,p,t) call with HOST buffers (pinned), H2D + D2H inside.  Under
     # torchrun every rank evaluates the residual of its own slab (the host array carries the halo
     # rows, as the reference's ghost cells do), all ranks at once: whole-job DOFs / max time.
-    uh = FR.pinned_empty(u0.shape)
-    dh = FR.pinned_empty(u0.shape)
-    uh[...] = u0
-    prob.f_pipelined(dh, uh, None, 0.0, nslab=args.e2e_slabs)  # warm-up
     k = max(1, min(args.steps, args.e2e_steps))
-    job.barrier()
-    t0 = time.perf_counter()
-    for _ in range(k):
-        prob.f_pipelined(dh, uh, None, 0.0, nslab=args.e2e_slabs)
-    el = job.reduce_max(time.perf_counter() - t0)
-    nbytes = int(u0.size) * 8
-    e2e = {"value": dofs * world * k / el, "unit": UNIT, "h2d_bytes_per_step": nbytes * world,
-           "d2h_bytes_per_step": nbytes * world,
-           "call": f"frb_rhs_pipelined(prob, u_host, du_host, {args.e2e_slabs}): the f!(du,u,p,t) shape with pinned "
-                   "host buffers; upload, fused residual and download overlapped in row slabs"
-                   + (f"; {world} ranks, one slab each, concurrently" if world > 1 else ""),
-           "ms_per_call": 1e3 * el / k}
+    e2e, uh, dh = e2e_leg(FR, job, prob, u0, args.e2e_slabs, k)
     if world == 1:
         # the reference's own user-loop shape (euler2d_wave.jl:125-135): the state lives on the host and is
         # touched between steps, so every SSPRK3 step is upload + 3 fused stages + download
@@ -422,6 +430,10 @@ def run_ours(args):
                  "parity": None if args.no_parity else parity_check(FR, job, ms2, n, n // world,
                                                                      args.warmup + args.steps),
                  "note": "efficiency = this value / (N x the N = 1 line's value): total work fixed"}
+        e2, uh2, dh2 = e2e_leg(FR, job, p2, ms2["u0"], args.e2e_slabs, k)
+        other["e2e"] = e2
+        FR.pinned_free(uh2)
+        FR.pinned_free(dh2)
         p2.close()
 
     if rank == 0:

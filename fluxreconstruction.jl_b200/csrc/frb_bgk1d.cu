@@ -14,6 +14,7 @@
 // model FRB_BGK_KINETIC_ADVECTION is the mol! of example/advection_kinetic.jl:73-128: the same residual with the
 // Maxwellian of prim = [rho, a, 1] (:80-88) -- only the epilogue of the moments kernel differs.
 // Both are L2 / HBM streams of the 50 MB state; nothing here is GEMM-shaped.
+#include <atomic>
 #include <cstdlib>
 
 #include "frb_internal.cuh"
@@ -180,184 +181,237 @@ constexpr int kFusedMaxVR = 4;
 #ifndef FRB_BGK_MINB
 #define FRB_BGK_MINB 2  // kernel experiment switch (scripts/build_variants.py)
 #endif
+__device__ __forceinline__ void cp_async16(void *smem, const void *gmem) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem)
+               : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+// Persistent: one CTA per SM slot walks over the cell blocks (tiles) t = blockIdx.x, + gridDim.x, ...  While a
+// tile is being worked on, the NEXT tile of u (and of u_n for a 24-B stage) streams into shared memory with
+// cp.async (LDGSTS, 16 B per thread and piece, every thread into its own slots: no barrier needed to read them
+// back).  The exposed DRAM / L2 latency of the first loads -- 37 % of all stall samples of the non-pipelined
+// version (profiles/r02_summary.md) -- is paid once per CTA instead of once per tile.
 template <int NSP, int VR>
 __global__ void __launch_bounds__(256, FRB_BGK_MINB)
 bgk1d_fused_kernel(const double *__restrict__ u, const double *__restrict__ ua, double *__restrict__ out,
                    const double *__restrict__ inv_j, const double *__restrict__ velo,
                    const double *__restrict__ wts, int ncell, int nu, double inv_tau, FrbOps ops, FrbStage st,
                    int model, double a) {
+  extern __shared__ __align__(16) double2 stage[];  // [VR * NSP][256] for u, then the same for u_n
   __shared__ double red[8][kFC / 2][2][NSP][3];
   __shared__ double prim_s[kFC][NSP][3];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int cp = lane & 3;                  // cell pair within the CTA
-  const int vg = warp * 8 + (lane >> 2);    // velocity group: velocities vg, vg + 64, ...
-  const int i = blockIdx.x * kFC + 2 * cp;  // first cell of the pair (ncell is even: in range or out as a pair)
-  const bool cell_ok = i < ncell;
-  const size_t vs = (size_t)ncell * nu;
-  const bool edge_lo = cp == 0, edge_hi = cell_ok && (cp == kFC / 2 - 1 || i + 2 >= ncell);
-  const int il = i == 0 ? ncell - 1 : i - 1, ir = i + 2 >= ncell ? 0 : i + 2;  // periodic halo cells
-
-  double2 w[VR][NSP];
   // flux trace of the halo cell next to the CTA's first / last pair, upwind side only: computed by the edge lanes
   // with the first loads, parked in shared memory until the update (registers are the scarce resource here)
   __shared__ double halo_s[2][VR][kFG];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int cp = lane & 3;                // cell pair within the CTA
+  const int vg = warp * 8 + (lane >> 2);  // velocity group: velocities vg, vg + 64, ...
+  const size_t vs = (size_t)ncell * nu;
+  const int ntiles = (ncell + kFC - 1) / kFC;
+  const bool with_a = st.use_a && !st.rhs_only;
+  double2 *const stage_a = stage + VR * NSP * 256;
+
+  auto prefetch = [&](const double *src, double2 *dst, int tile) {
+    const int i = tile * kFC + 2 * cp;
+    if (i < ncell) {
 #pragma unroll
-  for (int r = 0; r < VR; ++r) {
-    const int j = vg + kFG * r;
-    const bool ok = cell_ok && j < nu;
+      for (int r = 0; r < VR; ++r) {
+        const int j = vg + kFG * r;
+        if (j < nu) {
 #pragma unroll
-    for (int q = 0; q < NSP; ++q)
-      w[r][q] = ok ? *reinterpret_cast<const double2 *>(u + i + (size_t)ncell * j + vs * q) : make_double2(0.0, 0.0);
+          for (int q = 0; q < NSP; ++q) cp_async16(&dst[(r * NSP + q) * 256 + tid], src + i + (size_t)ncell * j + vs * q);
+        }
+      }
+    }
+    cp_async_commit();
+  };
+
+  int tile = blockIdx.x;
+  if (tile < ntiles) {
+    prefetch(u, stage, tile);
+    if (with_a) prefetch(ua, stage_a, tile);
   }
-  if (cell_ok && (edge_lo || edge_hi)) {
+  for (; tile < ntiles; tile += gridDim.x) {
+    const int i = tile * kFC + 2 * cp;  // first cell of the pair (ncell is even: in range or out as a pair)
+    const bool cell_ok = i < ncell;
+    const bool edge_lo = cp == 0, edge_hi = cell_ok && (cp == kFC / 2 - 1 || i + 2 >= ncell);
+    const int il = i == 0 ? ncell - 1 : i - 1, ir = i + 2 >= ncell ? 0 : i + 2;  // periodic halo cells
+
+    cp_async_wait_all();  // this thread's pieces of the tile (and of u_n) have landed
+    double2 w[VR][NSP];
+#pragma unroll
+    for (int r = 0; r < VR; ++r) {
+      const bool ok = cell_ok && vg + kFG * r < nu;
+#pragma unroll
+      for (int q = 0; q < NSP; ++q) w[r][q] = ok ? stage[(r * NSP + q) * 256 + tid] : make_double2(0.0, 0.0);
+    }
+    const int next = tile + gridDim.x;
+    if (next < ntiles) prefetch(u, stage, next);  // the slots were just read by their owner
+    if (cell_ok && (edge_lo || edge_hi)) {
+#pragma unroll
+      for (int r = 0; r < VR; ++r) {
+        const int j = vg + kFG * r;
+        if (j >= nu) continue;
+        const double v = velo[j];
+        if (edge_lo && v >= 0.0) {  // right trace of the flux of cell il
+          double fn[NSP];
+          const double sn = v * inv_j[il];
+#pragma unroll
+          for (int q = 0; q < NSP; ++q) fn[q] = sn * u[il + (size_t)ncell * j + vs * q];
+          halo_s[0][r][vg] = dotn<NSP>(fn, ops.lr);
+        }
+        if (edge_hi && !(v >= 0.0)) {  // left trace of the flux of cell ir
+          double fn[NSP];
+          const double sn = v * inv_j[ir];
+#pragma unroll
+          for (int q = 0; q < NSP; ++q) fn[q] = sn * u[ir + (size_t)ncell * j + vs * q];
+          halo_s[1][r][vg] = dotn<NSP>(fn, ops.ll);
+        }
+      }
+    }
+
+    // ---- moments (bgk_wave.jl:77-79): per thread over its velocities, then over the velocity groups
+    {
+      double m[2][NSP][3];
+#pragma unroll
+      for (int c = 0; c < 2; ++c)
+#pragma unroll
+        for (int q = 0; q < NSP; ++q) m[c][q][0] = m[c][q][1] = m[c][q][2] = 0.0;
+#pragma unroll
+      for (int r = 0; r < VR; ++r) {
+        const int j = vg + kFG * r;
+        const double v = j < nu ? velo[j] : 0.0, wt = j < nu ? wts[j] : 0.0;
+        const double wv = wt * v, wvv = wt * (v * v);
+#pragma unroll
+        for (int q = 0; q < NSP; ++q) {
+          m[0][q][0] += wt * w[r][q].x; m[0][q][1] += wv * w[r][q].x; m[0][q][2] += wvv * w[r][q].x;
+          m[1][q][0] += wt * w[r][q].y; m[1][q][1] += wv * w[r][q].y; m[1][q][2] += wvv * w[r][q].y;
+        }
+      }
+#pragma unroll
+      for (int c = 0; c < 2; ++c)
+#pragma unroll
+        for (int q = 0; q < NSP; ++q)
+#pragma unroll
+          for (int k = 0; k < 3; ++k) {
+            double x = m[c][q][k];
+            x += __shfl_xor_sync(0xffffffffu, x, 4);
+            x += __shfl_xor_sync(0xffffffffu, x, 8);
+            x += __shfl_xor_sync(0xffffffffu, x, 16);
+            if (lane < 4) red[warp][cp][c][q][k] = x;
+          }
+    }
+    __syncthreads();
+    if (tid < kFC * NSP) {
+      const int c = tid % kFC, q = tid / kFC;
+      double w0 = 0.0, w1 = 0.0, w2 = 0.0;
+#pragma unroll
+      for (int g = 0; g < 8; ++g) {
+        w0 += red[g][c >> 1][c & 1][q][0];
+        w1 += red[g][c >> 1][c & 1][q][1];
+        w2 += red[g][c >> 1][c & 1][q][2];
+      }
+      if (model == FRB_BGK_KINETIC_ADVECTION) {  // example/advection_kinetic.jl:80-88: prim = [rho, a, 1.0]
+        prim_s[c][q][0] = w0 * sqrt(1.0 / 3.14159265358979323846);
+        prim_s[c][q][1] = a;
+        prim_s[c][q][2] = 1.0;
+      } else {
+        w2 *= 0.5;
+        const double lam = 0.5 * w0 / (3.0 - 1.0) / (w2 - 0.5 * w1 * w1 / w0);  // conserve_prim(w, 3.0)
+        prim_s[c][q][0] = w0 * sqrt(lam / 3.14159265358979323846);               // rho * sqrt(lambda / pi)
+        prim_s[c][q][1] = w1 / w0;
+        prim_s[c][q][2] = lam;
+      }
+    }
+    __syncthreads();
+
+    // ---- update: every thread its own (2 cells, VR velocities, NSP points)
+    const double (*const pr)[NSP][3] = &prim_s[2 * cp];  // read from shared memory where used: 18 registers less
+    const double ij0 = cell_ok ? inv_j[i] : 0.0, ij1 = cell_ok ? inv_j[i + 1] : 0.0;
 #pragma unroll
     for (int r = 0; r < VR; ++r) {
       const int j = vg + kFG * r;
-      if (j >= nu) continue;
-      const double v = velo[j];
-      if (edge_lo && v >= 0.0) {  // right trace of the flux of cell il
-        double fn[NSP];
-        const double sn = v * inv_j[il];
+      const bool ok = cell_ok && j < nu;
+      const double v = j < nu ? velo[j] : 0.0;
+      const bool pos = v >= 0.0;  // heaviside delta, bgk_wave.jl:26
+      const size_t base = (size_t)i + (size_t)ncell * j;
+      const double s0 = v * ij0, s1 = v * ij1;  // v / J
+      double f0[NSP], f1[NSP];
 #pragma unroll
-        for (int q = 0; q < NSP; ++q) fn[q] = sn * u[il + (size_t)ncell * j + vs * q];
-        halo_s[0][r][vg] = dotn<NSP>(fn, ops.lr);
+      for (int q = 0; q < NSP; ++q) { f0[q] = s0 * w[r][q].x; f1[q] = s1 * w[r][q].y; }  // :85-88
+      const double fL0 = dotn<NSP>(f0, ops.ll), fR0 = dotn<NSP>(f0, ops.lr);              // interp_face! :99-101
+      const double fL1 = dotn<NSP>(f1, ops.ll), fR1 = dotn<NSP>(f1, ops.lr);
+      // upwind neighbour traces: the other cell of the pair, the adjacent lane's pair, or the halo cell
+      double upL = __shfl_up_sync(0xffffffffu, fR1, 1, 4);    // right trace of cell i - 1
+      double upR = __shfl_down_sync(0xffffffffu, fL0, 1, 4);  // left trace of cell i + 2
+      if (edge_lo && pos) upL = halo_s[0][r][vg];   // written by this very thread before the barriers
+      if (edge_hi && !pos) upR = halo_s[1][r][vg];
+      // f_interaction - own trace at the left / right face (:103-107): zero on the downwind side
+      const double cl0 = pos ? upL - fL0 : 0.0, cr0 = pos ? 0.0 : fL1 - fR0;
+      const double cl1 = pos ? fR0 - fL1 : 0.0, cr1 = pos ? 0.0 : upR - fR1;
+      double2 o[NSP];
+#pragma unroll
+      for (int p = 0; p < NSP; ++p) {
+        const double c0 = v - pr[0][p][1], c1 = v - pr[1][p][1];
+        const double M0 = pr[0][p][0] * exp_neg(-pr[0][p][2] * (c0 * c0));  // maxwellian
+        const double M1 = pr[1][p][0] * exp_neg(-pr[1][p][2] * (c1 * c1));
+        const double d0 = -(dotn<NSP>(f0, &ops.lpdm[p * FRB_NSPMAX]) + cl0 * ops.dgl[p] + cr0 * ops.dgr[p]) +
+                          (M0 - w[r][p].x) * inv_tau;
+        const double d1 = -(dotn<NSP>(f1, &ops.lpdm[p * FRB_NSPMAX]) + cl1 * ops.dgl[p] + cr1 * ops.dgr[p]) +
+                          (M1 - w[r][p].y) * inv_tau;
+        if (st.rhs_only) {
+          o[p] = make_double2(d0, d1);
+        } else {
+          double r0 = st.nested ? st.cb * (w[r][p].x + st.cdt * d0) : st.cb * w[r][p].x + st.cdt * d0;
+          double r1 = st.nested ? st.cb * (w[r][p].y + st.cdt * d1) : st.cb * w[r][p].y + st.cdt * d1;
+          if (with_a) {
+            const double2 an = stage_a[(r * NSP + p) * 256 + tid];  // u_n: landed with the tile (cp.async)
+            r0 = st.ca * an.x + r0;
+            r1 = st.ca * an.y + r1;
+          }
+          o[p] = make_double2(r0, r1);
+        }
       }
-      if (edge_hi && !(v >= 0.0)) {  // left trace of the flux of cell ir
-        double fn[NSP];
-        const double sn = v * inv_j[ir];
+      if (ok) {
 #pragma unroll
-        for (int q = 0; q < NSP; ++q) fn[q] = sn * u[ir + (size_t)ncell * j + vs * q];
-        halo_s[1][r][vg] = dotn<NSP>(fn, ops.ll);
+        for (int p = 0; p < NSP; ++p) *reinterpret_cast<double2 *>(out + base + vs * p) = o[p];
       }
     }
+    if (with_a && next < ntiles) prefetch(ua, stage_a, next);  // u_n of the next tile: its slots are free now
   }
+}
 
-  // ---- moments (bgk_wave.jl:77-79): per thread over its velocities, then over the velocity groups
-  double m[2][NSP][3];
-#pragma unroll
-  for (int c = 0; c < 2; ++c)
-#pragma unroll
-    for (int q = 0; q < NSP; ++q) m[c][q][0] = m[c][q][1] = m[c][q][2] = 0.0;
-#pragma unroll
-  for (int r = 0; r < VR; ++r) {
-    const int j = vg + kFG * r;
-    const double v = j < nu ? velo[j] : 0.0, wt = j < nu ? wts[j] : 0.0;
-    const double wv = wt * v, wvv = wt * (v * v);
-#pragma unroll
-    for (int q = 0; q < NSP; ++q) {
-      m[0][q][0] += wt * w[r][q].x; m[0][q][1] += wv * w[r][q].x; m[0][q][2] += wvv * w[r][q].x;
-      m[1][q][0] += wt * w[r][q].y; m[1][q][1] += wv * w[r][q].y; m[1][q][2] += wvv * w[r][q].y;
-    }
+template <int NSP, int VR>
+int launch_fused_vr(frb_prob_t p, const double *u, const double *ua, double *out, FrbStage st) {
+  const bool with_a = st.use_a && !st.rhs_only;
+  const size_t smem = sizeof(double2) * VR * NSP * 256 * (with_a ? 2 : 1);
+  static std::atomic<unsigned long long> attr_done{0};
+  const unsigned long long dev_bit = 1ull << (p->ctx->device & 63);
+  if (!(attr_done.load(std::memory_order_acquire) & dev_bit)) {
+    FRB_CUDA(cudaFuncSetAttribute(bgk1d_fused_kernel<NSP, VR>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)(sizeof(double2) * VR * NSP * 256 * 2)));
+    attr_done.fetch_or(dev_bit, std::memory_order_release);
   }
-#pragma unroll
-  for (int c = 0; c < 2; ++c)
-#pragma unroll
-    for (int q = 0; q < NSP; ++q)
-#pragma unroll
-      for (int k = 0; k < 3; ++k) {
-        double x = m[c][q][k];
-        x += __shfl_xor_sync(0xffffffffu, x, 4);
-        x += __shfl_xor_sync(0xffffffffu, x, 8);
-        x += __shfl_xor_sync(0xffffffffu, x, 16);
-        if (lane < 4) red[warp][cp][c][q][k] = x;
-      }
-  __syncthreads();
-  if (threadIdx.x < kFC * NSP) {
-    const int c = threadIdx.x % kFC, q = threadIdx.x / kFC;
-    double w0 = 0.0, w1 = 0.0, w2 = 0.0;
-#pragma unroll
-    for (int g = 0; g < 8; ++g) {
-      w0 += red[g][c >> 1][c & 1][q][0];
-      w1 += red[g][c >> 1][c & 1][q][1];
-      w2 += red[g][c >> 1][c & 1][q][2];
-    }
-    if (model == FRB_BGK_KINETIC_ADVECTION) {  // example/advection_kinetic.jl:80-88: prim = [rho, a, 1.0]
-      prim_s[c][q][0] = w0 * sqrt(1.0 / 3.14159265358979323846);
-      prim_s[c][q][1] = a;
-      prim_s[c][q][2] = 1.0;
-    } else {
-      w2 *= 0.5;
-      const double lam = 0.5 * w0 / (3.0 - 1.0) / (w2 - 0.5 * w1 * w1 / w0);  // conserve_prim(w, 3.0)
-      prim_s[c][q][0] = w0 * sqrt(lam / 3.14159265358979323846);               // rho * sqrt(lambda / pi)
-      prim_s[c][q][1] = w1 / w0;
-      prim_s[c][q][2] = lam;
-    }
-  }
-  __syncthreads();
-
-  // ---- update: every thread its own (2 cells, VR velocities, NSP points)
-  const double (*const pr)[NSP][3] = &prim_s[2 * cp];  // read from shared memory where used: 18 registers less
-  const double ij0 = cell_ok ? inv_j[i] : 0.0, ij1 = cell_ok ? inv_j[i + 1] : 0.0;
-#pragma unroll
-  for (int r = 0; r < VR; ++r) {
-    const int j = vg + kFG * r;
-    const bool ok = cell_ok && j < nu;
-    const double v = j < nu ? velo[j] : 0.0;
-    const bool pos = v >= 0.0;  // heaviside delta, bgk_wave.jl:26
-    const size_t base = (size_t)i + (size_t)ncell * j;
-    double2 an[NSP];
-    if (st.use_a && !st.rhs_only && ok) {
-#pragma unroll
-      for (int q = 0; q < NSP; ++q) an[q] = *reinterpret_cast<const double2 *>(ua + base + vs * q);
-    }
-    const double s0 = v * ij0, s1 = v * ij1;  // v / J
-    double f0[NSP], f1[NSP];
-#pragma unroll
-    for (int q = 0; q < NSP; ++q) { f0[q] = s0 * w[r][q].x; f1[q] = s1 * w[r][q].y; }  // :85-88
-    const double fL0 = dotn<NSP>(f0, ops.ll), fR0 = dotn<NSP>(f0, ops.lr);              // interp_face! :99-101
-    const double fL1 = dotn<NSP>(f1, ops.ll), fR1 = dotn<NSP>(f1, ops.lr);
-    // upwind neighbour traces: the other cell of the pair, the adjacent lane's pair, or the halo cell
-    double upL = __shfl_up_sync(0xffffffffu, fR1, 1, 4);    // right trace of cell i - 1
-    double upR = __shfl_down_sync(0xffffffffu, fL0, 1, 4);  // left trace of cell i + 2
-    if (edge_lo && pos) upL = halo_s[0][r][vg];   // written by this very thread before the barriers
-    if (edge_hi && !pos) upR = halo_s[1][r][vg];
-    // f_interaction - own trace at the left / right face (:103-107): zero on the downwind side
-    const double cl0 = pos ? upL - fL0 : 0.0, cr0 = pos ? 0.0 : fL1 - fR0;
-    const double cl1 = pos ? fR0 - fL1 : 0.0, cr1 = pos ? 0.0 : upR - fR1;
-    double2 o[NSP];
-#pragma unroll
-    for (int p = 0; p < NSP; ++p) {
-      const double c0 = v - pr[0][p][1], c1 = v - pr[1][p][1];
-      const double M0 = pr[0][p][0] * exp_neg(-pr[0][p][2] * (c0 * c0));  // maxwellian
-      const double M1 = pr[1][p][0] * exp_neg(-pr[1][p][2] * (c1 * c1));
-      const double d0 = -(dotn<NSP>(f0, &ops.lpdm[p * FRB_NSPMAX]) + cl0 * ops.dgl[p] + cr0 * ops.dgr[p]) +
-                        (M0 - w[r][p].x) * inv_tau;
-      const double d1 = -(dotn<NSP>(f1, &ops.lpdm[p * FRB_NSPMAX]) + cl1 * ops.dgl[p] + cr1 * ops.dgr[p]) +
-                        (M1 - w[r][p].y) * inv_tau;
-      if (st.rhs_only) {
-        o[p] = make_double2(d0, d1);
-      } else {
-        double r0 = st.nested ? st.cb * (w[r][p].x + st.cdt * d0) : st.cb * w[r][p].x + st.cdt * d0;
-        double r1 = st.nested ? st.cb * (w[r][p].y + st.cdt * d1) : st.cb * w[r][p].y + st.cdt * d1;
-        if (st.use_a) { r0 = st.ca * an[p].x + r0; r1 = st.ca * an[p].y + r1; }
-        o[p] = make_double2(r0, r1);
-      }
-    }
-    if (ok) {
-#pragma unroll
-      for (int p = 0; p < NSP; ++p) *reinterpret_cast<double2 *>(out + base + vs * p) = o[p];
-    }
-  }
+  const int ntiles = (p->ncell + kFC - 1) / kFC;
+  const int slots = p->ctx->sm_count * FRB_BGK_MINB;  // persistent: one CTA per resident slot
+  const dim3 grd(ntiles < slots ? ntiles : slots), blk(256);
+  bgk1d_fused_kernel<NSP, VR><<<grd, blk, smem, p->ctx->stream>>>(u, ua, out, p->J, p->velo, p->weights, p->ncell,
+                                                                   p->nu, 1.0 / p->tau, p->ops, st, p->bgk_model, p->a);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return frb_cuda_fail(e, "bgk1d_fused_kernel", __FILE__, __LINE__);
+  return 1;
 }
 
 template <int NSP>
 int launch_fused(frb_prob_t p, const double *u, const double *ua, double *out, FrbStage st) {
-  const int vr = (p->nu + kFG - 1) / kFG;
-  const dim3 grd((p->ncell + kFC - 1) / kFC), blk(256);
-  const double it = 1.0 / p->tau;
-#define FRB_BGK_FUSED(VR)                                                                                         \
-  bgk1d_fused_kernel<NSP, VR><<<grd, blk, 0, p->ctx->stream>>>(u, ua, out, p->J, p->velo, p->weights, p->ncell, \
-                                                                 p->nu, it, p->ops, st, p->bgk_model, p->a)
-  switch (vr) {
-    case 1: FRB_BGK_FUSED(1); break;
-    case 2: FRB_BGK_FUSED(2); break;
-    case 3: FRB_BGK_FUSED(3); break;
-    default: FRB_BGK_FUSED(4); break;
+  switch ((p->nu + kFG - 1) / kFG) {
+    case 1: return launch_fused_vr<NSP, 1>(p, u, ua, out, st);
+    case 2: return launch_fused_vr<NSP, 2>(p, u, ua, out, st);
+    case 3: return launch_fused_vr<NSP, 3>(p, u, ua, out, st);
+    default: return launch_fused_vr<NSP, 4>(p, u, ua, out, st);
   }
-#undef FRB_BGK_FUSED
-  cudaError_t e = cudaGetLastError();
-  if (e != cudaSuccess) return frb_cuda_fail(e, "bgk1d_fused_kernel", __FILE__, __LINE__);
-  return 1;
 }
 
 // the one-pass kernel needs 16-byte aligned cell pairs (even ncell), the velocity grid in registers

@@ -49,3 +49,14 @@ def test_curv_probe_record_has_the_roofline_object():
     spec.loader.exec_module(c)
     cpu = c.cpu_baseline(2, 48, 32, 1)  # the C/OpenMP restatement of the same residual, timed (tiny sample here)
     assert cpu["kind"] == "port" and cpu["unit"] == "DOF-updates/s" and cpu["value"] > 0 and cpu["cores"] >= 1
+
+
+def test_reference_arm_of_the_other_configurations():
+    """bench.py --impl reference --config {1,2,4}: the same line shape for the other BASELINE configurations."""
+    for cfg in ("1", "2", "4"):
+        r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--config", cfg,
+                            "--steps", "1", "--warmup", "0"], capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stderr[-2000:]
+        d = json.loads([ln for ln in r.stdout.splitlines() if ln.strip()][-1])
+        assert d["impl"] == "reference" and d["value"] > 0 and d["cpu_baseline"]["kind"] == "port"
+        assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["unit"] == "DOF-updates/s"

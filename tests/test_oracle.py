@@ -187,3 +187,43 @@ def test_golden_vectors(oracle, coracle):
     ps = oracle.FRPSpace1D(0.0, 1.0, 16, 2)
     du = coracle.rhs_bgk1d(np.asfortranarray(g["f0"]), ps.dx, g["velo"], g["weights"], ps.ll, ps.lr, ps.dl, ps.dhl, ps.dhr, 1e-2)
     assert np.allclose(du, g["du"], rtol=1e-11, atol=1e-12)
+
+
+def test_long_double_arbiter_agrees_with_the_fp64_oracle():
+    """oracle/fr_arbiter.c evaluates selected cells in x87 long double, cell-locally, with its own code for the
+    fluxes: a third, structurally independent evaluation.  On well-conditioned data it must agree with the FP64
+    oracle to rounding (a few ulp of the summed terms), for the 2-D Euler residual and the BGK residual."""
+    import c_oracle
+    import fr_oracle as o
+
+    g = 5.0 / 3.0
+    ps = o.FRPSpace2D(0.0, 1.0, 20, 0.0, 1.0, 30, 3, 1, 1)
+    rng = np.random.default_rng(1)
+    u0 = o.ic_wave2d(ps, g, "x")
+    u0 = np.asfortranarray(u0 * (1.0 + 0.02 * rng.standard_normal(u0.shape)))
+    u0[..., 2] += 0.1 * u0[..., 0]
+    o.ghost_fill_euler2d(u0, "wave_x")
+    ref = c_oracle.rhs_euler2d(u0, ps, g)
+    cells = [(i, j) for i in (1, 2, 10, 20) for j in (1, 15, 30)]
+    ex = c_oracle.arbiter_euler2d_cells(u0, ps, g, cells)
+    for c, (i, j) in enumerate(cells):
+        assert np.abs(ex[c] - ref[i, j]).max() <= 1e-14 * np.abs(ref).max()
+    # supersonic states: the upwind branches of HLL
+    prim = np.empty(ps.xpg.shape[:-1] + (4,))
+    prim[..., 0] = 1.0 + 0.1 * np.sin(2 * np.pi * ps.xpg[..., 0]) * np.cos(2 * np.pi * ps.xpg[..., 1])
+    prim[..., 1], prim[..., 2], prim[..., 3] = -3.0, 2.5, 1.0
+    us = np.asfortranarray(o.prim_conserve(prim, g))
+    ref = c_oracle.rhs_euler2d(us, ps, g)
+    ex = c_oracle.arbiter_euler2d_cells(us, ps, g, cells)
+    term = np.abs((us[..., 3] + 0.5) * 3.0).max() / min(ps.Jx, ps.Jy)  # the residual is a difference of terms this size
+    for c, (i, j) in enumerate(cells):
+        assert np.abs(ex[c] - ref[i, j]).max() <= 1e-14 * term
+    ps1 = o.FRPSpace1D(0.0, 1.0, 64, 2)
+    velo, w = o.vspace1d(-5.0, 5.0, 64)
+    f0 = o.ic_bgk1d(ps1, velo) * (1.0 + 0.05 * rng.standard_normal((64, 64, 3)))
+    dx = np.full(64, 1.0 / 64)
+    args = (dx, velo, w, ps1.ll, ps1.lr, ps1.dl, ps1.dhl, ps1.dhr, 1e-2)
+    du = c_oracle.rhs_bgk1d(f0, *args)
+    ex = c_oracle.arbiter_bgk1d_cells(f0, *args, [0, 1, 31, 63])
+    for c, i in enumerate([0, 1, 31, 63]):
+        assert np.abs(ex[c] - du[i]).max() <= 1e-13 * np.abs(du).max()
