@@ -62,19 +62,24 @@ def ncu_traffic(key="dram_bytes_per_launch"):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md).  The timed region of the
+    default run is ~70 ms, shorter than one start-up of nvidia-smi: the sampler is started BEFORE the warm-up
+    steps (`start`), polls every 20 ms with time stamps, and only the samples between `mark_begin` and `mark_end`
+    count; if the region was too short to catch one, the samples of the warm-up steps (the same kernels, back to
+    back with the timed ones) are reported and `window` says so."""
 
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+    Q = ("timestamp,index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
          "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, device):
         self.device, self.proc, self.lines = device, None, []
+        self.t0 = self.t1 = None
 
     def start(self):
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20",
                  "-i", str(self.device)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -83,33 +88,56 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.time(), line.strip()))
+
+    def mark_begin(self):
+        self.t0 = time.time()
+
+    def mark_end(self):
+        self.t1 = time.time()
 
     def stop(self):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        time.sleep(0.05)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
-        sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
-            f = [x.strip() for x in ln.split(",")]
-            if len(f) < 9:
-                continue
-            try:
-                sm.append(float(f[1])); mx.append(float(f[2]))
-            except ValueError:
-                continue
-            for nm, v in zip(names, f[5:9]):
-                if v.lower().startswith("active"):
-                    reasons.add(nm)
+
+        def collect(lo, hi):
+            sm, mx, pw, reasons = [], [], [], set()
+            for t, ln in self.lines:
+                if lo is not None and not (lo <= t <= hi):
+                    continue
+                f = [x.strip() for x in ln.split(",")]
+                if len(f) < 10:
+                    continue
+                try:
+                    sm.append(float(f[2])); mx.append(float(f[3])); pw.append(float(f[4]))
+                except ValueError:
+                    continue
+                for nm, v in zip(names, f[6:10]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nm)
+            return sm, mx, pw, reasons
+
+        # a line is stamped when it is read, one query (~10-20 ms) after the clocks were sampled
+        window = "timed region"
+        sm, mx, pw, reasons = collect(self.t0, (self.t1 or time.time()) + 0.03) if self.t0 else ([], [], [], set())
+        if not sm:
+            window = "warm-up + timed region (the timed region was shorter than one nvidia-smi poll)"
+            sm, mx, pw, reasons = collect(None, None)
+            # keep the samples under load only (idle samples before the first launch say nothing)
+            if pw:
+                lim = 0.6 * max(pw)
+                keep = [i for i, p_ in enumerate(pw) if p_ >= lim]
+                sm, mx = [sm[i] for i in keep], [mx[i] for i in keep]
         sm.sort()
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+                "samples": len(sm), "window": window, "reasons": sorted(reasons)}
 
 
 def make_ic(FR, n, ny_local):
@@ -276,12 +304,16 @@ def timed_steps(FR, job, n, ny_local, warmup, steps, sampler=None):
         prob = FR.Euler2DProblem(u0, (0.0, 1.0), ps, GAMMA, ctx=ctx)
         prob.set_hooks(ghost="wave_x")
     alg = FR.SSPRK33()
-    prob.step(alg, dt, warmup)
-    prob.set_profiling(True)
     if sampler is not None and job.rank == 0:
         sampler.start()
+    prob.step(alg, dt, warmup)
+    prob.set_profiling(True)
     job.barrier()
+    if sampler is not None:
+        sampler.mark_begin()
     prob.step(alg, dt, steps)  # synchronous; CUDA events bracket the K steps on the library stream
+    if sampler is not None:
+        sampler.mark_end()
     job.barrier()
     ms, launches = prob.last_timing()
     stage_ms, stage_n = prob.stage_timing()

@@ -197,7 +197,9 @@ def run(args):
     sampler = bench.ClockSampler(local)
     if rank == 0:
         sampler.start()
+        time.sleep(0.15)  # nvidia-smi start-up; these timed regions are milliseconds long
     job.barrier()
+    sampler.mark_begin()
     nsteps = args.steps * inner
     fin = True
     if group:
@@ -213,6 +215,7 @@ def run(args):
         prob.step(alg, dt, nsteps)
         ms, launches = prob.last_timing()
         fin = bool(np.isfinite(prob.download()).all())
+    sampler.mark_end()
     job.barrier()
     clocks = sampler.stop() if rank == 0 else None
     ms = job.reduce_max(ms)

@@ -1188,8 +1188,10 @@ extern "C" int32_t frb_last_timing(frb_prob_t p, float *ms, int64_t *kernel_laun
 
 extern "C" int32_t frb_set_kernel(frb_prob_t p, int32_t kind) {
   FRB_REQUIRE(p, FRB_ERR_ARG, "frb_set_kernel: prob is NULL");
-  FRB_REQUIRE(kind >= FRB_KERNEL_AUTO && kind <= FRB_KERNEL_RC, FRB_ERR_ARG,
+  FRB_REQUIRE(kind >= FRB_KERNEL_AUTO && kind <= FRB_KERNEL_BGK_ONE_PASS, FRB_ERR_ARG,
               "frb_set_kernel: unknown kernel kind");
+  if (kind == FRB_KERNEL_BGK_ONE_PASS)
+    FRB_REQUIRE(p->kind == K_BGK1D, FRB_ERR_STATE, "frb_set_kernel: the one-pass kernel belongs to bgk1d problems");
   if (kind == FRB_KERNEL_RC)
     FRB_REQUIRE(p->rc_base != nullptr, FRB_ERR_STATE, "frb_set_kernel: row-chunk kernel needs euler2d, deg 2..3");
   if (kind == FRB_KERNEL_MARCH)

@@ -4,8 +4,8 @@
 // through the periodic f2e / e2f tables (:42-67, :103-107), poly_derivative! (:114-116), correction
 // + relaxation (M - u)/tau (:122-128).  State u[cell, velocity, sp], cell fastest.
 //
-// One launch per stage where the velocity grid fits the register tile (bgk1d_fused_kernel, below: even ncell,
-// nu <= 256, deg 1..3 -- cfg4); otherwise two launches per stage:
+// Two launches per stage (the default), or one where the velocity grid fits a register tile (bgk1d_fused_kernel,
+// below: even ncell, nu <= 256, deg 1..3, FRB_BGK_ONE_PASS=1).  The two launches:
 //   bgk_moments_kernel  thread = (cell, sp): the three moments over the nu velocities in the
 //                       reference's summation order, 16 loads in flight per thread (the sum is a
 //                       serial chain, the loads are not); writes rho*sqrt(lambda/pi), U, lambda.
@@ -187,6 +187,7 @@ __device__ __forceinline__ void cp_async16(void *smem, const void *gmem) {
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_but_one() { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
 
 // Persistent: one CTA per SM slot walks over the cell blocks (tiles) t = blockIdx.x, + gridDim.x, ...  While a
 // tile is being worked on, the NEXT tile of u (and of u_n for a 24-B stage) streams into shared memory with
@@ -225,9 +226,11 @@ bgk1d_fused_kernel(const double *__restrict__ u, const double *__restrict__ ua, 
         }
       }
     }
-    cp_async_commit();
+    cp_async_commit();  // always: the sequence of groups is the same for every thread and every tile
   };
-
+  // Groups in flight, oldest first, at the top of tile t:  u(t) [, u_n(t)].  A 24-B stage waits for all but the
+  // youngest (u_n(t) keeps streaming through the moment phase), issues u(t + 1), and before the update waits
+  // again for all but the youngest (now u(t + 1)), i.e. for u_n(t); u_n(t + 1) is issued after the update.
   int tile = blockIdx.x;
   if (tile < ntiles) {
     prefetch(u, stage, tile);
@@ -239,7 +242,8 @@ bgk1d_fused_kernel(const double *__restrict__ u, const double *__restrict__ ua, 
     const bool edge_lo = cp == 0, edge_hi = cell_ok && (cp == kFC / 2 - 1 || i + 2 >= ncell);
     const int il = i == 0 ? ncell - 1 : i - 1, ir = i + 2 >= ncell ? 0 : i + 2;  // periodic halo cells
 
-    cp_async_wait_all();  // this thread's pieces of the tile (and of u_n) have landed
+    if (with_a) cp_async_wait_but_one();  // this thread's pieces of u(t) have landed
+    else cp_async_wait_all();
     double2 w[VR][NSP];
 #pragma unroll
     for (int r = 0; r < VR; ++r) {
@@ -248,7 +252,7 @@ bgk1d_fused_kernel(const double *__restrict__ u, const double *__restrict__ ua, 
       for (int q = 0; q < NSP; ++q) w[r][q] = ok ? stage[(r * NSP + q) * 256 + tid] : make_double2(0.0, 0.0);
     }
     const int next = tile + gridDim.x;
-    if (next < ntiles) prefetch(u, stage, next);  // the slots were just read by their owner
+    prefetch(u, stage, next < ntiles ? next : ntiles);  // the slots were just read by their owner (past the end: an empty group)
     if (cell_ok && (edge_lo || edge_hi)) {
 #pragma unroll
       for (int r = 0; r < VR; ++r) {
@@ -328,6 +332,7 @@ bgk1d_fused_kernel(const double *__restrict__ u, const double *__restrict__ ua, 
     __syncthreads();
 
     // ---- update: every thread its own (2 cells, VR velocities, NSP points)
+    if (with_a) cp_async_wait_but_one();  // u_n(t)
     const double (*const pr)[NSP][3] = &prim_s[2 * cp];  // read from shared memory where used: 18 registers less
     const double ij0 = cell_ok ? inv_j[i] : 0.0, ij1 = cell_ok ? inv_j[i + 1] : 0.0;
 #pragma unroll
@@ -379,7 +384,7 @@ bgk1d_fused_kernel(const double *__restrict__ u, const double *__restrict__ ua, 
         for (int p = 0; p < NSP; ++p) *reinterpret_cast<double2 *>(out + base + vs * p) = o[p];
       }
     }
-    if (with_a && next < ntiles) prefetch(ua, stage_a, next);  // u_n of the next tile: its slots are free now
+    if (with_a) prefetch(ua, stage_a, next < ntiles ? next : ntiles);  // u_n of the next tile: its slots are free now
   }
 }
 
@@ -392,6 +397,8 @@ int launch_fused_vr(frb_prob_t p, const double *u, const double *ua, double *out
   if (!(attr_done.load(std::memory_order_acquire) & dev_bit)) {
     FRB_CUDA(cudaFuncSetAttribute(bgk1d_fused_kernel<NSP, VR>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)(sizeof(double2) * VR * NSP * 256 * 2)));
+    // two CTAs of a 24-B stage need 2 x 107 KB: without the carve-out hint the driver may leave room for one only
+    FRB_CUDA(cudaFuncSetAttribute(bgk1d_fused_kernel<NSP, VR>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     attr_done.fetch_or(dev_bit, std::memory_order_release);
   }
   const int ntiles = (p->ncell + kFC - 1) / kFC;
@@ -417,8 +424,12 @@ int launch_fused(frb_prob_t p, const double *u, const double *ua, double *out, F
 // the one-pass kernel needs 16-byte aligned cell pairs (even ncell), the velocity grid in registers
 // (nu <= 256) and deg 1..3; everything else runs the two-launch form
 bool fused_ok(frb_prob_t p, const double *u, const double *ua, const double *out) {
-  static const bool off = getenv("FRB_BGK_TWO_PASS") != nullptr;
-  if (off || p->ncell % 2 || p->nu > kFG * kFusedMaxVR || p->nsp < 2 || p->nsp > 4) return false;
+  // Default: the two-launch form.  Measured at cfg4 (B200, 16-B / 24-B stage): two launches 45.7 / 56.3 us, one pass
+  // 46-50 / 64.5 us -- the state is L2-resident and neither form is memory-bound, so
+  // saving a pass over u buys nothing while the register tile costs occupancy.  frb_set_kernel(FRB_KERNEL_BGK_ONE_PASS) or
+  // FRB_BGK_ONE_PASS=1 select the one-pass kernel (same results; tests run both).
+  static const bool on = getenv("FRB_BGK_ONE_PASS") != nullptr && getenv("FRB_BGK_TWO_PASS") == nullptr;
+  if (!(on || p->kernel_kind == FRB_KERNEL_BGK_ONE_PASS) || p->ncell % 2 || p->nu > kFG * kFusedMaxVR || p->nsp < 2 || p->nsp > 4) return false;
   return u != out && (((uintptr_t)u | (uintptr_t)out | (uintptr_t)(ua ? ua : u)) & 15) == 0;
 }
 

@@ -36,6 +36,24 @@ __device__ __forceinline__ void face_flux_y(const double (&uT)[4], const double 
   h[0] = f.f0; h[1] = f.f1; h[2] = f.f2; h[3] = f.f3;
 }
 
+// The same face for a march in either direction (row-chunk kernel: odd segments march downwards so that the two
+// segments sharing a boundary read its rows at the same time and the second read is an L2 hit).  uOwn = trace of
+// the current row on the face towards the next row of the march, Unb = tile of that next row, lnb = the operator
+// of ITS trace on the face (ll when it lies above, lr when below).  The lower row is always the left state, so the
+// flux is bit for bit the one the upward march computes.
+template <int NSP, int FLUX = 0>
+__device__ __forceinline__ void face_flux_y_dir(const double (&uOwn)[4], const double *__restrict__ Unb,
+                                                const double *lnb, bool down, double gamma, double gm1,
+                                                double (&h)[4]) {
+  double uN[4];
+  col_trace<NSP>(Unb, lnb, uN);
+  double L[4], R[4];
+#pragma unroll
+  for (int m = 0; m < 4; ++m) { L[m] = down ? uN[m] : uOwn[m]; R[m] = down ? uOwn[m] : uN[m]; }
+  frb::Flux4 f = frb::riemann4_y_fast<FLUX>(L[0], L[1], L[2], L[3], R[0], R[1], R[2], R[3], gamma, gm1);
+  h[0] = f.f0; h[1] = f.f1; h[2] = f.f2; h[3] = f.f3;
+}
+
 // CB1: the stage has cb == 1 (no multiply)
 template <int NSP, bool CB1, int FLUX = 0>
 __device__ __forceinline__ void x_pass(const double *__restrict__ Ux, double *__restrict__ xdx,
@@ -92,8 +110,19 @@ __device__ __forceinline__ void x_pass(const double *__restrict__ Ux, double *__
 
 // first half of the y pass: G at the column's points and the top trace of the row
 template <int NSP>
+__device__ __forceinline__ void y_fluxes_dir(const double *__restrict__ Uy, const double *__restrict__ xrpy,
+                                             const double *lown, double (&g)[NSP][4], double (&uT)[4]);
+
+template <int NSP>
 __device__ __forceinline__ void y_fluxes(const double *__restrict__ Uy, const double *__restrict__ xrpy,
                                          const MarchOps &ops, double (&g)[NSP][4], double (&uT)[4]) {
+  y_fluxes_dir<NSP>(Uy, xrpy, ops.lr, g, uT);
+}
+
+// lown: the operator of the row's trace on the face towards the next row of the march (lr upwards, ll downwards)
+template <int NSP>
+__device__ __forceinline__ void y_fluxes_dir(const double *__restrict__ Uy, const double *__restrict__ xrpy,
+                                             const double *lown, double (&g)[NSP][4], double (&uT)[4]) {
   double w[NSP][4];
 #pragma unroll
   for (int m = 0; m < 4; ++m)
@@ -110,9 +139,9 @@ __device__ __forceinline__ void y_fluxes(const double *__restrict__ Uy, const do
   }
 #pragma unroll
   for (int m = 0; m < 4; ++m) {
-    double a = w[0][m] * ops.lr[0];
+    double a = w[0][m] * lown[0];
 #pragma unroll
-    for (int q2 = 1; q2 < NSP; ++q2) a = fma(w[q2][m], ops.lr[q2], a);
+    for (int q2 = 1; q2 < NSP; ++q2) a = fma(w[q2][m], lown[q2], a);
     uT[m] = a;
   }
 }

@@ -107,7 +107,16 @@ __global__ void __launch_bounds__(NSP * 32, MINB) euler2d_rc_kernel(RcParams P, 
     jb = min(g.ny - 1, ja + P.rows_per_seg - 1);
   }
   if (ja > jb) return;
-  const int ntiles = jb - ja + 3;  // rows ja-1 .. jb+1; tile q holds row ja-1+q in buffer q % NBUF
+  // Odd segments march DOWNWARDS (rows jb .. ja): two neighbouring segments then meet at their common boundary --
+  // both at the start or both at the end of their march -- and the halo rows each reads of the other arrive while
+  // the owner streams them: the second read is an L2 hit instead of a DRAM read a whole CTA lifetime later.
+#ifdef FRB_RC_UP_ONLY
+  const bool down = false;
+#else
+  const bool down = ((RC_HALO_ACTIVE(P) ? (int)blockIdx.y - 2 : (int)blockIdx.y) & 1) != 0 && jb > ja;
+#endif
+  const int row0 = down ? jb + 1 : ja - 1, rstep = down ? -1 : 1;  // tile q holds row row0 + rstep * q
+  const int ntiles = jb - ja + 3;  // rows ja-1 .. jb+1; tile q in buffer q % NBUF
   const bool owner = lane >= 1 && lane <= kRcOwn && i <= g.nx;
   const int own = owner ? 1 : 0;
   // the copy of my column in the neighbouring chunk (lane 1 -> lane 31 of strip s-1, lane 30 ->
@@ -150,14 +159,14 @@ __global__ void __launch_bounds__(NSP * 32, MINB) euler2d_rc_kernel(RcParams P, 
     const int npre = ntiles < NBUF ? ntiles : NBUF;
     if (threadIdx.x == 0) {
       for (int q = 0; q < npre; ++q)
-        if (!is_slot(ja - 1 + q)) issue_bulk(q, ja - 1 + q);
+        if (!is_slot(row0 + rstep * q)) issue_bulk(q, row0 + rstep * q);
       if (USEA) {
         mbar_expect_tx(bar_un, kTileBytes);
-        bulk_load(S.un, P.ua + (size_t)ja * g.row + strip_off, kTileBytes, bar_un);
+        bulk_load(S.un, P.ua + (size_t)(row0 + rstep) * g.row + strip_off, kTileBytes, bar_un);
       }
     }
     for (int q = 0; q < npre; ++q)  // after the bulk copies are in flight: these may have to wait for a neighbour
-      if (is_slot(ja - 1 + q)) fetch_slot(q, ja - 1 + q);
+      if (is_slot(row0 + rstep * q)) fetch_slot(q, row0 + rstep * q);
   }
 
   // per-thread views of a tile (= of a chunk): row view (x pass, l = t), column view (y pass, k = t)
@@ -168,26 +177,29 @@ __global__ void __launch_bounds__(NSP * 32, MINB) euler2d_rc_kernel(RcParams P, 
   double *const xrpx = S.xrp + offx;
   const double *const xrpy = S.xrp + offy;
 
-  // ---- prologue: common flux on the bottom face of row ja from tiles 0 (row ja-1) and 1
-  double hb[4];
+  // trace operators along the march: the current row's trace on the face towards the next row, the next row's on
+  // the same face (upwards: lr / ll; downwards: ll / lr)
+  const double *const lown = down ? ops.ll : ops.lr, *const lnb = down ? ops.lr : ops.ll;
+  // ---- prologue: common flux on the face behind the first row (tiles 0 and 1), carried along the march
+  double hc[4];
   {
     mbar_wait(&S.bar[0], 0);
     mbar_wait(&S.bar[1], 0);
-    double uT[4];
-    col_trace<NSP>(S.tile[0] + offy, ops.lr, uT);
-    face_flux_y<NSP, FLUX>(uT, S.tile[1] + offy, ops, gamma, gm1, hb);
+    double u0[4];
+    col_trace<NSP>(S.tile[0] + offy, lown, u0);  // tile 0 seen from its successor: same roles as in the loop
+    face_flux_y_dir<NSP, FLUX>(u0, S.tile[1] + offy, lnb, down, gamma, gm1, hc);
   }
   {
     // tile 0 is dead after the prologue: refill its buffer with tile NBUF
     __syncthreads();
     if (ntiles > NBUF) {
-      if (is_slot(ja - 1 + NBUF)) fetch_slot(0, ja - 1 + NBUF);
-      else if (threadIdx.x == 0) issue_bulk(0, ja - 1 + NBUF);
+      if (is_slot(row0 + rstep * NBUF)) fetch_slot(0, row0 + rstep * NBUF);
+      else if (threadIdx.x == 0) issue_bulk(0, row0 + rstep * NBUF);
     }
   }
 
   for (int q = 1; q <= ntiles - 2; ++q) {  // tile q = row j
-    const int j = ja - 1 + q;
+    const int j = row0 + rstep * q;
     const int buf = q % NBUF, nbuf = (q + 1) % NBUF;
     const double *const Ux = S.tile[0] + buf * kTile + offx;
     const double *const Uy = S.tile[0] + buf * kTile + offy;
@@ -200,11 +212,11 @@ __global__ void __launch_bounds__(NSP * 32, MINB) euler2d_rc_kernel(RcParams P, 
     // -------------------------------------------------------------- y pass: column k = t
     {
       double g4[NSP][4];  // G at the column's points, [l][m]
-      double uT[4], ht[4];
-      y_fluxes<NSP>(Uy, xrpy, ops, g4, uT);
-      // top face of row j: HLL between this row's top trace and row j+1's bottom trace
+      double uT[4], hf[4];
+      y_fluxes_dir<NSP>(Uy, xrpy, lown, g4, uT);
+      // the face ahead of row j: common flux between this row's trace and the next row's (already in the ring)
       mbar_wait(&S.bar[nbuf], ((q + 1) / NBUF) & 1);
-      face_flux_y<NSP, FLUX>(uT, S.tile[0] + nbuf * kTile + offy, ops, gamma, gm1, ht);
+      face_flux_y_dir<NSP, FLUX>(uT, S.tile[0] + nbuf * kTile + offy, lnb, down, gamma, gm1, hf);
       if (USEA) mbar_wait(bar_un, (q - 1) & 1);  // u_n row j (requested one row step ago)
       // four independent FMA chains per variable, stored as soon as they retire; the chunk offset
       // of a value equals its tile offset
@@ -217,7 +229,9 @@ __global__ void __launch_bounds__(NSP * 32, MINB) euler2d_rc_kernel(RcParams P, 
         double v[NSP];
 #pragma unroll
         for (int l = 0; l < NSP; ++l) {
-          double d = y_value<NSP, SAMEJ>(xdy[32 * NSP * (l + NSP * m)], g4, hb[m], ht[m], ops, l, m);
+          // bottom / top face of the row: the carried flux and the fresh one, by direction
+          double d = y_value<NSP, SAMEJ>(xdy[32 * NSP * (l + NSP * m)], g4, down ? hf[m] : hc[m],
+                                         down ? hc[m] : hf[m], ops, l, m);
           if (USEA) d = fma(P.ca, S.un[offy + 32 * NSP * (l + NSP * m)], d);
           v[l] = d;
         }
@@ -242,7 +256,7 @@ __global__ void __launch_bounds__(NSP * 32, MINB) euler2d_rc_kernel(RcParams P, 
             st_if(pp + 32 * NSP * (l + NSP * m) + dup_off, v[l], dup);
           }
         }
-        hb[m] = ht[m];
+        hc[m] = hf[m];
       }
     }
     __syncthreads();  // (B) every read of tile[buf], un, xd, xrp is done; every store of row j is issued
@@ -254,12 +268,12 @@ __global__ void __launch_bounds__(NSP * 32, MINB) euler2d_rc_kernel(RcParams P, 
       if (j == 1) halo_raise(P.h.count + 0, g.ns, P.h.flag_lo, P.h.epoch);
       if (j == g.ny) halo_raise(P.h.count + 1, g.ns, P.h.flag_hi, P.h.epoch);
     }
-    if (threadIdx.x == 0 && USEA && j + 1 <= jb) {
+    if (threadIdx.x == 0 && USEA && q + 1 <= ntiles - 2) {
       mbar_expect_tx(bar_un, kTileBytes);
-      bulk_load(S.un, P.ua + (size_t)(j + 1) * g.row + strip_off, kTileBytes, bar_un);
+      bulk_load(S.un, P.ua + (size_t)(j + rstep) * g.row + strip_off, kTileBytes, bar_un);
     }
     if (q + NBUF < ntiles) {
-      const int r = ja - 1 + q + NBUF;
+      const int r = row0 + rstep * (q + NBUF);
       if (is_slot(r)) fetch_slot(buf, r);
       else if (threadIdx.x == 0) issue_bulk(buf, r);
     }

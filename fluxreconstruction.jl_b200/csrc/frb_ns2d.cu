@@ -98,7 +98,7 @@ __device__ __forceinline__ void mom_cons(const double *Mu, const double *Mv, con
 //   F   = <T v u^a>    = (V1 m_2 + B0 m_0)/2                  B0 = V3 + V1 X1
 //   Q   = <T^2 u^a>    = (m_4 + 2 A0 m_2 + C0 m_0)/4          C0 = V4 + X2 + 2 V2 X1
 // -- ~35 flops instead of ~100 per call (six calls per interface point), the same value to rounding
-// (checked against the literal form of the oracle, fr_oracle.py: moments_conserve_slope_2d).
+// (checked against the literal form in tests/test_oracle_extras.py).
 struct SlopeConst {
   double V1, V2, A0, B0, C0;
 };

@@ -32,7 +32,7 @@ from ._lib import Context, check, fortran_ptr, lib, make_operators
 
 BC = {"dirichlet": 0, "period": 1}
 GHOST = {None: -1, "none": -1, "wave_x": 0, "wave_y": 1, "copy": 2, "periodic": 3, "cylinder": 4}
-KERNEL = {"auto": 0, "generic": 1, "march": 2, "rc": 3}
+KERNEL = {"auto": 0, "generic": 1, "march": 2, "rc": 3, "one_pass": 4}
 FLUX = {"hll": 0, "lf": 1, "roe": 2}
 
 
@@ -386,7 +386,7 @@ class BGKProblem(_Problem):
     ``model="advection"`` is the mol! of example/advection_kinetic.jl:73-132 instead: the same residual relaxing
     towards the Maxwellian of prim = [rho, a, 1] (the script's tau is 2e-3)."""
 
-    def __init__(self, f0, tspan, ps, velo, weights, tau=1e-2, ctx=None, model="bgk", a=1.0):
+    def __init__(self, f0, tspan, ps, velo, weights, tau=1e-2, ctx=None, model="bgk", a=1.0, kernel="auto"):
         super().__init__(f0, tspan, ctx)
         ncell, nu, nsp = self.u0.shape
         if nsp != ps.deg + 1 or nu != len(velo):
@@ -400,6 +400,8 @@ class BGKProblem(_Problem):
                                      float(tau), C.byref(self.h)))
         if model != "bgk":
             check(lib().frb_bgk1d_set_model(self.h, {"bgk": 0, "advection": 1}[model], float(a)))
+        if kernel != "auto":
+            self.set_kernel(kernel)  # "one_pass": the register-tile kernel instead of the two launches
         self.upload(self.u0)
 
 

@@ -56,9 +56,11 @@ enum { FRB_GHOST_NONE = -1, FRB_GHOST_WAVE_X = 0, FRB_GHOST_WAVE_Y = 1, FRB_GHOS
        FRB_GHOST_CYLINDER = 4 };
 /* eq_advection.jl (seam epsilon 1e-6) vs example/advection_lowlevel.jl (1e-8) */
 enum { FRB_ADV_PACKAGED = 0, FRB_ADV_LOWLEVEL = 1 };
-/* 2-D Euler kernel selection: AUTO picks the fused row-marching TMA kernel when
- * deg == 3, otherwise the generic per-element kernel */
-enum { FRB_KERNEL_AUTO = 0, FRB_KERNEL_GENERIC = 1, FRB_KERNEL_MARCH = 2, FRB_KERNEL_RC = 3 };
+/* kernel selection (frb_set_kernel).  2-D Euler: AUTO = the row-chunk streaming kernel for frb_step and the
+ * reference-image marching kernel for f! with host buffers (deg 2-3), the generic per-element kernel otherwise */
+enum { FRB_KERNEL_AUTO = 0, FRB_KERNEL_GENERIC = 1, FRB_KERNEL_MARCH = 2, FRB_KERNEL_RC = 3,
+       /* bgk1d problems only: the one-pass register-tile kernel instead of the two launches (same results) */
+       FRB_KERNEL_BGK_ONE_PASS = 4 };
 
 /* common (Riemann) flux of the Euler problems.  HLL is what the reference calls (flux_hll!,
  * eq_euler.jl:53, euler2d_wave.jl:73,80) and what the marching kernels implement; LF (Rusanov)

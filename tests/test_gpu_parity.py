@@ -344,12 +344,15 @@ def test_euler2d_freestream_and_conservation(FR, oracle):
 
 
 # ---------------------------------------------------------------- config 4: 1-D BGK
-@pytest.mark.parametrize("ncell,nu,deg", [(20, 100, 2), (64, 256, 2), (33, 28, 3)])
-def test_bgk_rhs(FR, oracle, ncell, nu, deg):
+@pytest.mark.parametrize("kernel", ["auto", "one_pass"])
+@pytest.mark.parametrize("ncell,nu,deg", [(20, 100, 2), (64, 256, 2), (33, 28, 3), (30, 70, 1), (8, 256, 3), (250, 200, 2)])
+def test_bgk_rhs(FR, oracle, ncell, nu, deg, kernel):
+    """both forms of the cfg4 stage: two launches ("auto") and the one-pass register-tile kernel (even ncell,
+    nu <= 256, deg 1..3; other shapes fall back to the two launches)"""
     ps = FR.FRPSpace1D(0.0, 1.0, ncell, deg)
     velo, wts = oracle.vspace1d(-5.0, 5.0, nu)
     f0 = noisy(oracle.ic_bgk1d(ps, velo), 0.01, 6)
-    prob = FR.BGKProblem(f0, (0.0, 1.0), ps, velo, wts, 1e-2)
+    prob = FR.BGKProblem(f0, (0.0, 1.0), ps, velo, wts, 1e-2, kernel=kernel)
     du = np.zeros_like(f0, order="F")
     prob.f(du, f0, None, 0.0)
     ref = oracle.rhs_bgk1d(f0, ps.dx, velo, wts, ps.ll, ps.lr, ps.dl, ps.dhl, ps.dhr, 1e-2)
@@ -357,12 +360,13 @@ def test_bgk_rhs(FR, oracle, ncell, nu, deg):
     prob.close()
 
 
-def test_bgk_steps(FR, oracle, coracle):
+@pytest.mark.parametrize("kernel", ["auto", "one_pass"])
+def test_bgk_steps(FR, oracle, coracle, kernel):
     ps = FR.FRPSpace1D(0.0, 1.0, 64, 2)
     velo, wts = oracle.vspace1d(-5.0, 5.0, 64)
     f0 = oracle.ic_bgk1d(ps, velo)
     dt = 0.1 * ps.dx[0] / 5.0
-    prob = FR.BGKProblem(f0, (0.0, 1.0), ps, velo, wts, 1e-2)
+    prob = FR.BGKProblem(f0, (0.0, 1.0), ps, velo, wts, 1e-2, kernel=kernel)
     itg = FR.init(prob, FR.Midpoint(), dt=dt)
     FR.step_(itg, 1000)
     ref = coracle.integrate_bgk1d(f0, ps.dx, velo, wts, ps.ll, ps.lr, ps.dl, ps.dhl, ps.dhr, 1e-2, dt, 1000, "midpoint")
@@ -376,7 +380,8 @@ def test_kinetic_advection(FR, oracle, deg):
     ps = FR.FRPSpace1D(-1.0, 1.0, 100, deg)
     velo, wts = oracle.vspace1d(-5.0, 5.0, 28)
     f0 = noisy(oracle.ic_kinetic_advection1d(ps, velo, 1.0), 0.01, 9)
-    prob = FR.BGKProblem(f0, (0.0, 0.5), ps, velo, wts, 2e-3, model="advection", a=1.0)
+    prob = FR.BGKProblem(f0, (0.0, 0.5), ps, velo, wts, 2e-3, model="advection", a=1.0,
+                         kernel="one_pass" if deg == 3 else "auto")
     du = np.zeros_like(f0, order="F")
     prob.f(du, f0, None, 0.0)
     args = (ps.dx, velo, wts, ps.ll, ps.lr, ps.dl, ps.dhl, ps.dhr, 2e-3)
@@ -568,14 +573,16 @@ def test_cfg4_full_size_bgk_against_the_long_double_arbiter(FR, oracle, coracle)
         args = (ps.dx, velo, wts, ps.ll, ps.lr, ps.dl, ps.dhl, ps.dhr, 1e-2)
         exact = coracle.arbiter_bgk1d_cells(f0, *args, cells)
         ref = coracle.rhs_bgk1d(f0, *args)
-        prob = FR.BGKProblem(f0, (0.0, 1.0), ps, velo, wts, 1e-2)
-        du = np.zeros_like(f0, order="F")
-        prob.f(du, f0, None, 0.0)
-        prob.close()
-        e_or, e_gpu = np.abs(ref[cells] - exact).max(), np.abs(du[cells] - exact).max()
-        print(f"cfg4 {name}: max|du| = {np.abs(exact).max():.3e}; |oracle - exact| = {e_or:.3e}; "
-              f"|gpu - exact| = {e_gpu:.3e}")
-        assert e_gpu <= 4.0 * e_or, (name, e_gpu, e_or)
+        e_or = np.abs(ref[cells] - exact).max()
+        for kernel in ("auto", "one_pass"):
+            prob = FR.BGKProblem(f0, (0.0, 1.0), ps, velo, wts, 1e-2, kernel=kernel)
+            du = np.zeros_like(f0, order="F")
+            prob.f(du, f0, None, 0.0)
+            prob.close()
+            e_gpu = np.abs(du[cells] - exact).max()
+            print(f"cfg4 {name} {kernel}: max|du| = {np.abs(exact).max():.3e}; |oracle - exact| = {e_or:.3e}; "
+                  f"|gpu - exact| = {e_gpu:.3e}")
+            assert e_gpu <= 4.0 * e_or, (name, kernel, e_gpu, e_or)
 
 
 def test_cfg4_full_size_bgk(FR, oracle, coracle):

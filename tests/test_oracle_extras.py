@@ -171,3 +171,35 @@ def test_kinetic_advection_model(oracle):
     M_adv = oracle.maxwellian(velo[None, :], np.stack([w[:, 0], np.ones(40), np.ones(40)], axis=-1))
     M_bgk = oracle.maxwellian(velo[None, :], oracle.conserve_prim(w, 3.0))
     assert np.allclose((du - d_bgk)[:, :, k], (M_adv - M_bgk) / 2e-3, rtol=1e-9, atol=1e-9)
+
+
+def test_factored_slope_moments_equal_the_literal_form():
+    """csrc/frb_ns2d.cu evaluates moments_conserve_slope(sl, Mu, Mv, Mxi, a, 0) in a factored form (all six calls of
+    ns_cavity.jl:75-145 have beta = 0): E_i = (m_(i+2) + A0 m_i)/2, F = (V1 m_2 + B0 m_0)/2,
+    Q = (m_4 + 2 A0 m_2 + C0 m_0)/4 with A0 = V2 + X1, B0 = V3 + V1 X1, C0 = V4 + X2 + 2 V2 X1.  The same algebra
+    in NumPy against the literal six-term sum of the oracle, incl. the mixed (Mv of one state, Mxi of the other) call."""
+    import numpy as np
+    import fr_oracle as o
+
+    rng = np.random.default_rng(0)
+    n = 500
+    mk = lambda: np.stack([1 + 0.2 * rng.random(n), 0.3 * rng.standard_normal(n), 0.3 * rng.standard_normal(n),  # noqa: E731
+                           1 + 0.3 * rng.random(n)], -1)
+    Mu, Mv, Mxi, MuL, _ = o.gauss_moments(mk(), 1.0)
+    Mu2, Mv2, Mxi2, _, MuR2 = o.gauss_moments(mk(), 1.0)
+    sl = rng.standard_normal((n, 4))
+
+    def fast(sl, m, a, V, X):
+        A0, B0, C0 = V[2] + X[1], V[3] + V[1] * X[1], V[4] + X[2] + 2 * V[2] * X[1]
+        E = lambda i: 0.5 * (m[a + i + 2] + A0 * m[a + i])  # noqa: E731
+        F = 0.5 * (V[1] * m[a + 2] + B0 * m[a])
+        Q = 0.25 * (m[a + 4] + 2 * A0 * m[a + 2] + C0 * m[a])
+        s0, s1, s2, s3 = (sl[:, q] for q in range(4))
+        k = s0 + s2 * V[1]
+        return np.stack([k * m[a] + s1 * m[a + 1] + s3 * E(0), k * m[a + 1] + s1 * m[a + 2] + s3 * E(1),
+                         (s0 * V[1] + s2 * V[2]) * m[a] + s1 * V[1] * m[a + 1] + s3 * F,
+                         s0 * E(0) + s1 * E(1) + s2 * F + s3 * Q], -1)
+
+    for M, V, X, a in ((Mu, Mv, Mxi, 1), (Mu2, Mv, Mxi2, 1), (MuL, Mv, Mxi, 2), (MuR2, Mv2, Mxi2, 2), (MuR2, Mv2, Mxi2, 1)):
+        ref = o.moments_conserve_slope_2d(sl, M, V, X, a, 0)
+        assert np.abs(fast(sl, M, a, V, X) - ref).max() <= 4e-15 * np.abs(ref).max()
