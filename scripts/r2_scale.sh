@@ -3,7 +3,7 @@
 # strong split and parity objects inside)
 mkdir -p gpurun_out
 export FRB_REQUIRE_GPUS=8
-timeout 900 python -m pytest tests/test_gpu_multi.py -m gpu -q -k "8] or 4-ssprk3 or rhs[4 or hooks[auto-limiter-4 or hooks[auto-filter-4 or cavity_slabs_match_oracle[4" > gpurun_out/r2_multi_tests_8.log 2>&1
+timeout 900 python -m pytest tests/test_gpu_multi.py -m gpu -q -k "two_rank_slabs or 8] or 4-ssprk3 or rhs[4 or hooks[auto-limiter-4 or hooks[auto-filter-4 or cavity_slabs_match_oracle[4" > gpurun_out/r2_multi_tests_8.log 2>&1
 tail -4 gpurun_out/r2_multi_tests_8.log
 for N in 8 4; do
   TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 2954$N"
