@@ -875,17 +875,23 @@ static int one_step(frb_prob_t p, int scheme, double dt, bool rc) {
   if (par && (p->filt_when == 1 || p->limiter_on)) {
     if ((n = halo_republish(p, U)) < 0) return n;  // the neighbours' halo copies of my rows 1 / ny are stale
   }
+  bool ring_done = false;
   if (p->ghost_mode != FRB_GHOST_NONE) {
     if (par) {
       if ((n = halo_wait_if_pending(p)) < 0) return n;  // neighbours are done with the last stage
-      n = rc ? frb_rc_ghost_x(p, U, p->ghost_mode) : frb_launch_ghost_x2d(p, U, p->ghost_mode);
+      if (rc) {  // x ghosts of u_n and the frozen ghost columns of the stage buffers in one launch
+        n = frb_rc_ghost_x_ring(p, U, S1, scheme != FRB_SCHEME_EULER ? S2 : nullptr, p->ghost_mode);
+        ring_done = true;
+      } else {
+        n = frb_launch_ghost_x2d(p, U, p->ghost_mode);
+      }
     } else {
       n = rc ? frb_rc_ghost_fill(p, U, p->ghost_mode) : frb_launch_ghost_fill2d(p, U, p->ghost_mode);
     }
     if (n < 0) return n;
     p->launches += n;
   }
-  if (p->kind == K_EULER2D) {
+  if (p->kind == K_EULER2D && !ring_done) {
     // ghosts are frozen across the stages of a step (du = 0 there): give the stage buffers the
     // same ring as u_n.  Rows owned by a neighbouring rank are excluded (the neighbour writes them).
     int nr = 1, rk = frb_halo_rank(p, &nr);
@@ -904,10 +910,8 @@ static int one_step(frb_prob_t p, int scheme, double dt, bool rc) {
     // the y half of the ghost fill crosses the global seam: first/last rank exchange their
     // boundary rows (frozen for the step, so they go into all three buffers of the peer)
     const int flip = p->ghost_mode == FRB_GHOST_WAVE_X ? 2 : -1;
-    for (int role = 0; role < 3; ++role) {
-      if ((n = frb_halo_push(p, U, role, true, flip)) < 0) return n;
-      p->launches += n;
-    }
+    if ((n = frb_halo_push_seam_all(p, U, flip)) < 0) return n;
+    p->launches += n;
     if ((n = frb_halo_signal(p)) < 0) return n;
     p->launches += n;
     p->halo_pending = true;

@@ -126,41 +126,59 @@ bgk_moments_kernel(const double *__restrict__ u, double *__restrict__ prim, int 
   prim[o + 2 * (size_t)ncell * nsp] = lam;
 }
 
-template <int NSP>
+// VPT velocities per thread (j, j + nu / VPT, ...): the Maxwellian parameters of the cell, the neighbour indices and
+// the constants of the exponential are fetched once for all of them -- the kernel is instruction-issue bound (ncu:
+// issue slots 71 % busy, 2/3 of the executed instructions are not FP64), so instructions per DOF are what counts.
+#ifndef FRB_BGK_VPT
+#define FRB_BGK_VPT 2
+#endif
+template <int NSP, int VPT>
 __global__ void __launch_bounds__(128)
 bgk1d_kernel(const double *__restrict__ u, const double *__restrict__ ua, double *__restrict__ out,
              const double *__restrict__ prim, const double *__restrict__ inv_j,
              const double *__restrict__ velo, int ncell, int nu, double inv_tau, FrbOps ops, FrbStage st) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  const int j = blockIdx.y;
   if (i >= ncell) return;
-  const double v = velo[j];
-  const bool pos = v >= 0.0;  // heaviside delta, bgk_wave.jl:26
   const size_t vs = (size_t)ncell * nu;
-  // only the upwind neighbour contributes: left cell for v >= 0, right cell otherwise (periodic)
-  const int in = pos ? (i == 0 ? ncell - 1 : i - 1) : (i == ncell - 1 ? 0 : i + 1);
-  const double sc = v * inv_j[i], sn = v * inv_j[in];  // v / J
-  double uc[NSP], f[NSP], fn[NSP];
-#pragma unroll
-  for (int q = 0; q < NSP; ++q) {
-    uc[q] = u[i + (size_t)ncell * j + vs * q];
-    f[q] = sc * uc[q];  // :85-88
-    fn[q] = sn * u[in + (size_t)ncell * j + vs * q];
-  }
-  const double fL = dotn<NSP>(f, ops.ll), fR = dotn<NSP>(f, ops.lr);  // interp_face! :99-101
-  // f_interaction at the left / right face of cell i (:103-107): own trace downwind, neighbour's upwind
-  const double cl = pos ? dotn<NSP>(fn, ops.lr) - fL : 0.0;   // fi0 - fL
-  const double cr = pos ? 0.0 : dotn<NSP>(fn, ops.ll) - fR;   // fi1 - fR
+  const int il = i == 0 ? ncell - 1 : i - 1, ir = i == ncell - 1 ? 0 : i + 1;  // periodic neighbours
+  const double ij = inv_j[i], ijl = inv_j[il], ijr = inv_j[ir];
+  double pre[NSP], U[NSP], lam[NSP];
 #pragma unroll
   for (int p = 0; p < NSP; ++p) {
     const size_t po = i + (size_t)ncell * p;
-    const double pre = prim[po], U = prim[po + (size_t)ncell * NSP], lam = prim[po + 2 * (size_t)ncell * NSP];
-    const double c = v - U;
-    const double M = pre * exp_neg(-lam * (c * c));  // maxwellian
-    const double rhs1 = dotn<NSP>(f, &ops.lpdm[p * FRB_NSPMAX]);  // poly_derivative! :114-116
-    const double du = -(rhs1 + cl * ops.dgl[p] + cr * ops.dgr[p]) + (M - uc[p]) * inv_tau;
-    const size_t idx = i + (size_t)ncell * j + vs * p;
-    out[idx] = stage_out(st, ua, idx, uc[p], du);
+    pre[p] = prim[po];
+    U[p] = prim[po + (size_t)ncell * NSP];
+    lam[p] = prim[po + 2 * (size_t)ncell * NSP];
+  }
+#pragma unroll
+  for (int s = 0; s < VPT; ++s) {
+    const int j = blockIdx.y + s * (nu / VPT);
+    const double v = velo[j];
+    const bool pos = v >= 0.0;  // heaviside delta, bgk_wave.jl:26
+    // only the upwind neighbour contributes: left cell for v >= 0, right cell otherwise (periodic)
+    const int in = pos ? il : ir;
+    const double sc = v * ij, sn = v * (pos ? ijl : ijr);  // v / J
+    const size_t row = (size_t)ncell * j;
+    double uc[NSP], f[NSP], fn[NSP];
+#pragma unroll
+    for (int q = 0; q < NSP; ++q) {
+      uc[q] = u[i + row + vs * q];
+      f[q] = sc * uc[q];  // :85-88
+      fn[q] = sn * u[in + row + vs * q];
+    }
+    const double fL = dotn<NSP>(f, ops.ll), fR = dotn<NSP>(f, ops.lr);  // interp_face! :99-101
+    // f_interaction at the left / right face of cell i (:103-107): own trace downwind, neighbour's upwind
+    const double cl = pos ? dotn<NSP>(fn, ops.lr) - fL : 0.0;   // fi0 - fL
+    const double cr = pos ? 0.0 : dotn<NSP>(fn, ops.ll) - fR;   // fi1 - fR
+#pragma unroll
+    for (int p = 0; p < NSP; ++p) {
+      const double c = v - U[p];
+      const double M = pre[p] * exp_neg(-lam[p] * (c * c));  // maxwellian
+      const double rhs1 = dotn<NSP>(f, &ops.lpdm[p * FRB_NSPMAX]);  // poly_derivative! :114-116
+      const double du = -(rhs1 + cl * ops.dgl[p] + cr * ops.dgr[p]) + (M - uc[p]) * inv_tau;
+      const size_t idx = i + row + vs * p;
+      out[idx] = stage_out(st, ua, idx, uc[p], du);
+    }
   }
 }
 
@@ -449,16 +467,28 @@ int frb_launch_bgk1d(frb_prob_t p, const double *u, const double *ua, double *ou
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return frb_cuda_fail(e, "bgk_moments_kernel", __FILE__, __LINE__);
   const double it = 1.0 / p->tau;
+  const bool multi = p->nu % FRB_BGK_VPT == 0;  // VPT velocities per thread when the grid divides, else one
+  if (multi) g2.y = p->nu / FRB_BGK_VPT;
+#define FRB_BGK_MAIN(N)                                                                                              \
+  case N:                                                                                                            \
+    if (multi)                                                                                                       \
+      bgk1d_kernel<N, FRB_BGK_VPT><<<g2, blk, 0, p->ctx->stream>>>(u, ua, out, p->prim, p->J, p->velo, p->ncell,     \
+                                                                   p->nu, it, p->ops, st);                          \
+    else                                                                                                             \
+      bgk1d_kernel<N, 1><<<g2, blk, 0, p->ctx->stream>>>(u, ua, out, p->prim, p->J, p->velo, p->ncell, p->nu, it,    \
+                                                         p->ops, st);                                               \
+    break;
   switch (p->nsp) {
-    case 2: bgk1d_kernel<2><<<g2, blk, 0, p->ctx->stream>>>(u, ua, out, p->prim, p->J, p->velo, p->ncell, p->nu, it, p->ops, st); break;
-    case 3: bgk1d_kernel<3><<<g2, blk, 0, p->ctx->stream>>>(u, ua, out, p->prim, p->J, p->velo, p->ncell, p->nu, it, p->ops, st); break;
-    case 4: bgk1d_kernel<4><<<g2, blk, 0, p->ctx->stream>>>(u, ua, out, p->prim, p->J, p->velo, p->ncell, p->nu, it, p->ops, st); break;
-    case 5: bgk1d_kernel<5><<<g2, blk, 0, p->ctx->stream>>>(u, ua, out, p->prim, p->J, p->velo, p->ncell, p->nu, it, p->ops, st); break;
-    case 6: bgk1d_kernel<6><<<g2, blk, 0, p->ctx->stream>>>(u, ua, out, p->prim, p->J, p->velo, p->ncell, p->nu, it, p->ops, st); break;
-    case 7: bgk1d_kernel<7><<<g2, blk, 0, p->ctx->stream>>>(u, ua, out, p->prim, p->J, p->velo, p->ncell, p->nu, it, p->ops, st); break;
-    case 8: bgk1d_kernel<8><<<g2, blk, 0, p->ctx->stream>>>(u, ua, out, p->prim, p->J, p->velo, p->ncell, p->nu, it, p->ops, st); break;
+    FRB_BGK_MAIN(2)
+    FRB_BGK_MAIN(3)
+    FRB_BGK_MAIN(4)
+    FRB_BGK_MAIN(5)
+    FRB_BGK_MAIN(6)
+    FRB_BGK_MAIN(7)
+    FRB_BGK_MAIN(8)
     default: frb_set_error("bgk1d: deg must be in 1..7"); return FRB_ERR_ARG;
   }
+#undef FRB_BGK_MAIN
   e = cudaGetLastError();
   if (e != cudaSuccess) return frb_cuda_fail(e, "bgk1d_kernel", __FILE__, __LINE__);
   return 2;

@@ -321,6 +321,24 @@ int frb_halo_push(frb_prob_t p, const double *src, int dst_role, bool seam, int 
   return 1;
 }
 
+// the frozen seam rows of a step into all three buffers of the seam neighbour: one launch on the row-chunk path
+int frb_halo_push_seam_all(frb_prob_t p, const double *src, int flip_var) {
+  if (!frb_halo_active(p)) return 0;
+  FrbHalo *H = p->halo;
+  const bool first = H->rank == 0, last = H->rank == H->nranks - 1;
+  if (!first && !last) return 0;
+  if (!is_rc(p, src)) {
+    int n = 0;
+    for (int role = 0; role < 3; ++role) {
+      int r = frb_halo_push(p, src, role, true, flip_var);
+      if (r < 0) return r;
+      n += r;
+    }
+    return n;
+  }
+  return frb_rc_row_push3(p, src, first ? H->rc_lo : nullptr, last ? H->rc_hi : nullptr, H->nyl_lo, flip_var);
+}
+
 // raise this rank's epoch in both neighbours' mailboxes, after everything queued so far
 int frb_halo_signal(frb_prob_t p) {
   if (!frb_halo_active(p)) return 0;

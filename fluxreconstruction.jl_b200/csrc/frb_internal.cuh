@@ -145,6 +145,10 @@ int frb_rc_to_ref(frb_prob_t p, const double *rc, double *ref, bool interior_onl
 int frb_rc_ghost_fill(frb_prob_t p, double *u, int mode);
 int frb_rc_ghost_x(frb_prob_t p, double *u, int mode);
 int frb_rc_ring_copy(frb_prob_t p, const double *src, double *dst, bool row0, bool rowN);
+int frb_rc_ghost_x_ring(frb_prob_t p, double *u, double *d1, double *d2, int mode);
+int frb_rc_row_push3(frb_prob_t p, const double *src, double *const *dst_lo, double *const *dst_hi, int nyl_lo,
+                     int flip_var);
+int frb_halo_push_seam_all(frb_prob_t p, const double *src, int flip_var);
 int frb_rc_limiter2d(frb_prob_t p, double *u);
 int frb_rc_row_push(frb_prob_t p, const double *src, double *dst_lo, double *dst_hi, int nyl_lo, int flip_var);
 int frb_launch_tri_euler(frb_prob_t p, const double *u, const double *ua, double *out, FrbStage st);

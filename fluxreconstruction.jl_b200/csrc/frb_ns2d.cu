@@ -306,13 +306,13 @@ ns_face_kernel(const double *__restrict__ u, double *__restrict__ fhx, double *_
   o[0] = fw[0]; o[1] = fw[1]; o[2] = fw[2]; o[3] = fw[3];
 }
 
+// (Issuing every global load before the first use -- state row, the four common fluxes, u_n: 92-116 registers --
+// was measured and dropped: 1.431 / 1.456 ms per 16-B / 24-B stage at 6 CTAs / SM against 1.421 / 1.480 for this
+// form at 64 registers and 8 CTAs / SM; profiles/r02_summary.md section D.)
 // ---- element kernel: thread = (solution point, element); a block holds EPB consecutive cells of a
 // column of the mesh (j fastest in memory)
-#ifndef FRB_NS_ELEM_MINB
-#define FRB_NS_ELEM_MINB 1  // kernel experiment switch (scripts/build_variants.py)
-#endif
 template <int NSP, int EPB>
-__global__ void __launch_bounds__(NSP * NSP * EPB, FRB_NS_ELEM_MINB)
+__global__ void __launch_bounds__(NSP * NSP * EPB)
 ns_elem_kernel(const double *__restrict__ u, const double *__restrict__ ua, double *__restrict__ out,
                const double *__restrict__ fhx, const double *__restrict__ fhy, int nx, int ny, double Jx,
                double Jy, GasPar gas, FrbOps ops, FrbStage st) {
@@ -325,28 +325,9 @@ ns_elem_kernel(const double *__restrict__ u, const double *__restrict__ ua, doub
   const bool live = j <= ny;
   double w[4] = {1.0, 0.0, 0.0, 1.0};
   const size_t eo = eoff<NSP>(live ? j : ny, i, nyg) + 4 * pt;
-  // every global load of the thread is issued here, before the first use: the state row, the four common fluxes of
-  // the point's row / column and u_n (32-byte rows each) -- one exposed DRAM latency per thread instead of two
-  // (ncu of the first version: 7.0 long-scoreboard stalls per issue, DRAM at 25 %)
-  double hl[4] = {0, 0, 0, 0}, hr[4] = {0, 0, 0, 0}, hb[4] = {0, 0, 0, 0}, ht[4] = {0, 0, 0, 0}, an[4] = {0, 0, 0, 0};
   if (live) {
-    const double2 *pw = reinterpret_cast<const double2 *>(u + eo);
-    const double2 *pl = reinterpret_cast<const double2 *>(fhx + 4 * (l + NSP * ((long long)(j - 1) + (long long)ny * (i - 1))));
-    const double2 *pr = reinterpret_cast<const double2 *>(fhx + 4 * (l + NSP * ((long long)(j - 1) + (long long)ny * i)));
-    const double2 *pb = reinterpret_cast<const double2 *>(fhy + 4 * (k + NSP * ((long long)(j - 1) + (long long)(ny + 1) * (i - 1))));
-    const double2 *pt2 = reinterpret_cast<const double2 *>(fhy + 4 * (k + NSP * ((long long)j + (long long)(ny + 1) * (i - 1))));
-    const double2 w01 = pw[0], w23 = pw[1], l01 = pl[0], l23 = pl[1], r01 = pr[0], r23 = pr[1];
-    const double2 b01 = pb[0], b23 = pb[1], t01 = pt2[0], t23 = pt2[1];
-    w[0] = w01.x; w[1] = w01.y; w[2] = w23.x; w[3] = w23.y;
-    hl[0] = l01.x; hl[1] = l01.y; hl[2] = l23.x; hl[3] = l23.y;
-    hr[0] = r01.x; hr[1] = r01.y; hr[2] = r23.x; hr[3] = r23.y;
-    hb[0] = b01.x; hb[1] = b01.y; hb[2] = b23.x; hb[3] = b23.y;
-    ht[0] = t01.x; ht[1] = t01.y; ht[2] = t23.x; ht[3] = t23.y;
-    if (ua && st.use_a && !st.rhs_only) {
-      const double2 *pa = reinterpret_cast<const double2 *>(ua + eo);
-      const double2 a01 = pa[0], a23 = pa[1];
-      an[0] = a01.x; an[1] = a01.y; an[2] = a23.x; an[3] = a23.y;
-    }
+#pragma unroll
+    for (int m = 0; m < 4; ++m) w[m] = u[eo + m];
   }
   {
     double F[4], G[4];  // ns_cavity.jl:169-187
@@ -356,7 +337,11 @@ ns_elem_kernel(const double *__restrict__ u, const double *__restrict__ ua, doub
   }
   __syncthreads();
   if (!live) return;
-  double o[4];
+  const double *hl = fhx + 4 * (l + NSP * ((long long)(j - 1) + (long long)ny * (i - 1)));
+  const double *hr = fhx + 4 * (l + NSP * ((long long)(j - 1) + (long long)ny * i));
+  const double *hb = fhy + 4 * (k + NSP * ((long long)(j - 1) + (long long)(ny + 1) * (i - 1)));
+  const double *ht = fhy + 4 * (k + NSP * ((long long)j + (long long)(ny + 1) * (i - 1)));
+  const double *a0 = ua ? ua + eo : nullptr;
 #pragma unroll
   for (int m = 0; m < 4; ++m) {
     double r1 = 0.0, r2 = 0.0, fL = 0.0, fR = 0.0, gB = 0.0, gT = 0.0;
@@ -376,13 +361,10 @@ ns_elem_kernel(const double *__restrict__ u, const double *__restrict__ ua, doub
     if (st.rhs_only) r = d;
     else {
       r = st.nested ? st.cb * (w[m] + st.cdt * d) : st.cb * w[m] + st.cdt * d;
-      if (st.use_a) r = st.ca * an[m] + r;
+      if (st.use_a) r = st.ca * a0[m] + r;
     }
-    o[m] = r;
+    out[eo + m] = r;
   }
-  double2 *po = reinterpret_cast<double2 *>(out + eo);
-  po[0] = make_double2(o[0], o[1]);
-  po[1] = make_double2(o[2], o[3]);
 }
 
 // the stage combination on the ghost ring (du = 0 there): dst = ca*ua + cb*src on whole ghost

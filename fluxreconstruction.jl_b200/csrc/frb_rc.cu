@@ -98,6 +98,41 @@ __global__ void rc_row_push_kernel(const double *__restrict__ src, double *__res
   if (dst_hi) dst_hi[off] = sg * src[off + g.row * (size_t)g.ny];
 }
 
+// slab-parallel per-step work in one launch each (strong scaling: a step is a few hundred microseconds, every
+// small launch counts).  (1) the x half of the ghost fill on u_n AND the copy of the frozen ghost columns into the
+// two stage buffers (rc_ghost_x_kernel + 2 x rc_ring_cols_kernel);
+__global__ void rc_ghost_x_ring_kernel(double *__restrict__ u, double *__restrict__ d1, double *__restrict__ d2,
+                                       RcGeom g, int npp, int srcL, int srcR, int flip_var) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  const int p = blockIdx.y;
+  if (j > g.ny + 1) return;
+  const double sg = (p / npp == flip_var) ? -1.0 : 1.0;
+  const double vl = sg * rc_load_col(u, g, srcL, j, p), vr = sg * rc_load_col(u, g, srcR, j, p);
+  rc_store_col(u, g, 0, j, p, vl);
+  rc_store_col(u, g, g.nx + 1, j, p, vr);
+  if (j >= 1 && j <= g.ny) {
+    if (d1) { rc_store_col(d1, g, 0, j, p, vl); rc_store_col(d1, g, g.nx + 1, j, p, vr); }
+    if (d2) { rc_store_col(d2, g, 0, j, p, vl); rc_store_col(d2, g, g.nx + 1, j, p, vr); }
+  }
+}
+// (2) the frozen seam rows of the step into all three buffers of the seam neighbour (3 x rc_row_push_kernel)
+struct RcPush3 {
+  double *lo[3], *hi[3];
+};
+__global__ void rc_row_push3_kernel(const double *__restrict__ src, RcPush3 d, RcGeom g, int nyl_lo, int npp,
+                                    int flip_var) {
+  const size_t off = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (off >= g.row) return;
+  const int plane = (int)(off % g.chunk) >> 5;
+  const double sg = (plane / npp == flip_var) ? -1.0 : 1.0;
+  const double v1 = sg * src[off + g.row], vn = sg * src[off + g.row * (size_t)g.ny];
+#pragma unroll
+  for (int r = 0; r < 3; ++r) {
+    if (d.lo[r]) d.lo[r][off + g.row * (size_t)(nyl_lo + 1)] = v1;
+    if (d.hi[r]) d.hi[r][off] = vn;
+  }
+}
+
 int check_launch_rc(const char *what) {
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return frb_cuda_fail(e, what, __FILE__, __LINE__);
@@ -169,6 +204,31 @@ int frb_rc_ghost_x(frb_prob_t p, double *u, int mode) {
     return FRB_ERR_ARG;
   }
   return r ? r : 1;
+}
+
+// x half of the ghost fill on u plus the frozen ghost columns of rows 1..ny into d1 / d2 (either may be NULL)
+int frb_rc_ghost_x_ring(frb_prob_t p, double *u, double *d1, double *d2, int mode) {
+  const RcGeom g = geom_of(p);
+  if (mode != FRB_GHOST_WAVE_X && mode != FRB_GHOST_WAVE_Y) {
+    frb_set_error("slab-parallel ghost fill supports the periodic wave modes");
+    return FRB_ERR_ARG;
+  }
+  dim3 blk(128), grd((g.ny + 2 + 127) / 128, g.nplanes);
+  rc_ghost_x_ring_kernel<<<grd, blk, 0, p->ctx->stream>>>(u, d1, d2, g, p->nsp * p->nsp, p->nx, 1,
+                                                           mode == FRB_GHOST_WAVE_X ? -1 : 1);
+  if (int r = check_launch_rc("rc_ghost_x_ring_kernel")) return r;
+  return 1;
+}
+
+int frb_rc_row_push3(frb_prob_t p, const double *src, double *const *dst_lo, double *const *dst_hi, int nyl_lo,
+                     int flip_var) {
+  const RcGeom g = geom_of(p);
+  RcPush3 d;
+  for (int r = 0; r < 3; ++r) { d.lo[r] = dst_lo ? dst_lo[r] : nullptr; d.hi[r] = dst_hi ? dst_hi[r] : nullptr; }
+  dim3 blk(256), grd((unsigned)((g.row + 255) / 256));
+  rc_row_push3_kernel<<<grd, blk, 0, p->ctx->stream>>>(src, d, g, nyl_lo, p->nsp * p->nsp, flip_var);
+  if (int r = check_launch_rc("rc_row_push3_kernel")) return r;
+  return 1;
 }
 
 int frb_rc_ring_copy(frb_prob_t p, const double *src, double *dst, bool row0, bool rowN) {

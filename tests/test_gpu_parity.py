@@ -869,3 +869,56 @@ def test_tableau_arguments_are_checked(FR, oracle):
     with pytest.raises(FR.FRBError, match="nstage"):
         prob.step(big, 1e-3, 1)
     prob.close()
+
+
+# ---------------------------------------------------------------- advisor findings of round 1
+def test_step_rejects_unknown_schemes_whatever_the_step_count(FR, oracle):
+    """frb_step validates `scheme` up front: the one-launch 1-D loop (nsteps >= 16) used to treat an unknown value
+    as SSPRK3 while the eager path returned FRB_ERR_ARG."""
+    import ctypes as C
+
+    ps = FR.FRPSpace1D(-1.0, 1.0, 100, 2)
+    prob = FR.FRAdvectionProblem(oracle.ic_advection1d(ps), (0.0, 1.0), ps, 1.0, "period", variant="lowlevel")
+    for nsteps in (1, 16, 100):
+        assert FR.lib().frb_step(prob.h, 7, C.c_double(1e-3), nsteps) == -1  # FRB_ERR_ARG
+    assert np.array_equal(prob.download(), oracle.ic_advection1d(ps))
+    prob.close()
+
+
+def test_solve_lands_on_the_end_of_tspan(FR, oracle, coracle):
+    """solve(prob, alg; adaptive=false, dt) takes a shortened last step when dt does not divide the span (the
+    reference's OrdinaryDiffEq does), instead of stopping short or overshooting."""
+    ps = FR.FRPSpace1D(-1.0, 1.0, 100, 2)
+    u0 = oracle.ic_advection1d(ps)
+    dt, t1 = 1e-3, 0.0105  # 10 full steps + half a step
+    prob = FR.FRAdvectionProblem(u0, (0.0, t1), ps, 1.0, "period", variant="lowlevel")
+    itg = FR.solve(prob, FR.Midpoint(), dt=dt)
+    assert itg.t == t1 and itg.iter == 11
+    ref = coracle.integrate_advection1d(u0, ps, 1.0, "period", "lowlevel", dt, 10, "midpoint")
+    ref = coracle.integrate_advection1d(ref, ps, 1.0, "period", "lowlevel", t1 - 10 * dt, 1, "midpoint")
+    assert rel(itg.u, ref) <= 1e-12
+    prob.close()
+
+
+def test_tableau_problems_free_their_stage_buffers(FR, oracle):
+    """frb_prob_destroy releases the k_i buffers frb_step_tableau allocates (6 x the state for Tsit5): a loop over
+    many problems, as a convergence study makes, must not accumulate device memory."""
+    import ctypes as C
+
+    drv = C.CDLL("libcuda.so.1")  # the library links cudart statically: ask the driver for the free memory
+    free0, total = C.c_size_t(), C.c_size_t()
+    ps = FR.FRPSpace2D(0.0, 1.0, 256, 0.0, 1.0, 256, 3, 1, 1)
+    u0 = oracle.ic_wave2d(ps, GAMMA, "x")
+
+    def one():
+        prob = FR.Euler2DProblem(u0, (0.0, 1.0), ps, GAMMA)
+        prob.step(FR.Tsit5(), 1e-5, 1)
+        prob.close()
+
+    one()
+    drv.cuMemGetInfo_v2(C.byref(free0), C.byref(total))
+    for _ in range(8):
+        one()
+    free1 = C.c_size_t()
+    drv.cuMemGetInfo_v2(C.byref(free1), C.byref(total))
+    assert free0.value - free1.value < 64 << 20, (free0.value, free1.value)  # 8 x 6 x 34 MB would be 1.6 GB
