@@ -467,7 +467,9 @@ int frb_launch_bgk1d(frb_prob_t p, const double *u, const double *ua, double *ou
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return frb_cuda_fail(e, "bgk_moments_kernel", __FILE__, __LINE__);
   const double it = 1.0 / p->tau;
-  const bool multi = p->nu % FRB_BGK_VPT == 0;  // VPT velocities per thread when the grid divides, else one
+  // VPT velocities per thread where it pays: measured at cfg4 (us per stage, VPT = 1 / 2 / 4): 16-B stage 45.2 /
+  // 43.5 / 43.8, 24-B stage 55.9 / 59.6-60.9 / 62.5 -- the u_n loads of a 24-B stage want the occupancy back
+  const bool multi = p->nu % FRB_BGK_VPT == 0 && !(st.use_a && !st.rhs_only);
   if (multi) g2.y = p->nu / FRB_BGK_VPT;
 #define FRB_BGK_MAIN(N)                                                                                              \
   case N:                                                                                                            \
