@@ -61,6 +61,7 @@ SIGNATURES = {
     "frb_state_device_ptr": (C.c_int32, [C.c_void_p, C.POINTER(C.c_void_p)]),
     "frb_rhs": (C.c_int32, [C.c_void_p, c_dp, c_dp, C.c_double]),
     "frb_rhs_pipelined": (C.c_int32, [C.c_void_p, c_dp, c_dp, C.c_int32]),
+    "frb_step_host": (C.c_int32, [C.c_void_p, c_dp, c_dp, C.c_int32, C.c_double, C.c_int32]),
     "frb_set_step_hooks": (C.c_int32, [C.c_void_p, C.c_int32, c_dp]),
     "frb_step": (C.c_int32, [C.c_void_p, C.c_int32, C.c_double, C.c_int32]),
     "frb_step_tableau": (C.c_int32, [C.c_void_p, C.c_int32, c_dp, c_dp, C.c_double, C.c_int32]),

@@ -154,7 +154,7 @@ extern "C" int32_t frb_prob_destroy(frb_prob_t p) {
   cudaStreamSynchronize(p->ctx->stream);
   frb_halo_disconnect(p);
   frb_march_release(p);
-  cudaFree(p->u); cudaFree(p->s1); cudaFree(p->s2); cudaFree(p->du); cudaFree(p->rc_base);
+  cudaFree(p->u); cudaFree(p->s1); cudaFree(p->s2); cudaFree(p->s3); cudaFree(p->du); cudaFree(p->rc_base);
   cudaFree(p->J); cudaFree(p->velo); cudaFree(p->weights); cudaFree(p->prim);
   cudaFree(p->lim_w); cudaFree(p->flag); cudaFree(p->loop_bar); cudaFree(p->filt); cudaFree(p->ns_flux);
   cudaFree(p->curv_iJ); cudaFree(p->curv_n1); cudaFree(p->curv_n2); cudaFree(p->curv_fpc); cudaFree(p->curv_flux); cudaFree(p->curv_vert);
@@ -1147,6 +1147,116 @@ extern "C" int32_t frb_step_tableau(frb_prob_t p, int32_t ns, const double *A, c
     frb_set_error("incorrect range of limiter parameter t");
     return FRB_ERR_NUMERIC;
   }
+  return FRB_OK;
+}
+
+// step!(itg) with the state on the HOST between steps (the reference's user loop, euler2d_wave.jl:125-135: the user
+// touches itg.u -- ghost fill, limiter, filter -- and calls step!).  The plain form is upload + frb_step + download:
+// the two copies run one after the other (2 x 39 ms at cfg3 for 3.3 ms of kernels).  Here the step streams through
+// the device in row slabs: slab k + 1 is on its way up while the stages run on the slabs that have arrived -- stage
+// s of slab k needs stage s - 1 of slabs k - 1 .. k + 1, so the last stage of slab k can run once slab k + n_stages
+// is on the device -- and finished slabs are on their way down: H2D and D2H overlap (PCIe full duplex).
+// The ghost cells are the caller's (filled on the host, as the reference's loop does) and frozen through the step;
+// step hooks (device ghost fill, limiter, filter), other fluxes / degrees and slab-parallel problems take the
+// plain path.  The new state is also the resident state afterwards.
+extern "C" int32_t frb_step_host(frb_prob_t p, const double *u_in, double *u_out, int32_t scheme, double dt,
+                                 int32_t nslab) {
+  FRB_REQUIRE(p && u_in && u_out, FRB_ERR_ARG, "frb_step_host: NULL argument");
+  FRB_REQUIRE(scheme >= FRB_SCHEME_EULER && scheme <= FRB_SCHEME_SSPRK3, FRB_ERR_ARG, "frb_step_host: unknown scheme");
+  const int nst = scheme == FRB_SCHEME_EULER ? 1 : scheme == FRB_SCHEME_MIDPOINT ? 2 : 3;
+  const bool streamed = p->kind == K_EULER2D && use_march(p) && !frb_halo_active(p) && p->ghost_mode == FRB_GHOST_NONE &&
+                        !p->limiter_on && p->filt_when == 0 && nslab > 1 && p->ny >= 2 * nslab;
+  if (!streamed) {
+    if (int rc = frb_state_upload(p, u_in)) return rc;
+    if (int rc = frb_step(p, scheme, dt, 1)) return rc;
+    return frb_state_download(p, u_out);
+  }
+  FRB_CUDA(cudaSetDevice(p->ctx->device));
+  cudaStream_t sc = p->ctx->stream, si = p->ctx->copy_in, so = p->ctx->copy_out;
+  if (!p->s3) FRB_CUDA(cudaMalloc(&p->s3, sizeof(double) * p->len));
+  while ((int)p->pipe_events.size() < 2 * nslab) {
+    cudaEvent_t e = nullptr;
+    FRB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    p->pipe_events.push_back(e);
+  }
+  cudaEvent_t *const ev_in = p->pipe_events.data(), *const ev_c = p->pipe_events.data() + nslab;
+  FRB_CUDA(cudaStreamSynchronize(sc));
+  double *const U = p->u, *const S1 = p->s1, *const S2 = p->s2, *const OUT = p->s3;
+  const size_t NXG = p->nx + 2, NE = NXG * (size_t)(p->ny + 2);
+  const int nplanes = 4 * p->nsp * p->nsp;
+  const size_t pitch = NE * sizeof(double);
+  const int rows = (p->ny + nslab - 1) / nslab;
+  auto lo = [&](int k) { return 1 + k * rows; };
+  auto hi = [&](int k) { return std::min(p->ny, lo(k) + rows - 1); };
+  int ns = 0;  // slabs that exist
+  while (ns < nslab && lo(ns) <= p->ny) ++ns;
+  // stage s of the scheme: input, u_n, output, coefficients (out = ca u_n + cb (u + cdt L(u)))
+  struct Stg { const double *in; const double *ua; double *out; FrbStage st; };
+  Stg stg[3];
+  if (scheme == FRB_SCHEME_EULER) {
+    stg[0] = {U, nullptr, OUT, {0.0, 1.0, dt, 0, 0, 0}};
+  } else if (scheme == FRB_SCHEME_MIDPOINT) {
+    stg[0] = {U, nullptr, S1, {0.0, 1.0, 0.5 * dt, 0, 0, 0}};
+    stg[1] = {S1, U, OUT, {1.0, 0.0, dt, 1, 0, 0}};
+  } else {
+    stg[0] = {U, nullptr, S1, {0.0, 1.0, dt, 0, 0, 0}};
+    stg[1] = {S1, U, S2, {0.75, 0.25, dt, 1, 0, 1}};
+    stg[2] = {S2, U, OUT, {1.0 / 3.0, 2.0 / 3.0, dt, 1, 0, 1}};
+  }
+  const int64_t l0 = p->launches;
+  prof_begin(p);
+  FRB_CUDA(cudaEventRecord(p->ev0, sc));
+  // uploads: slab k = rows lo(k) .. hi(k), plus the ghost row next to the first / last slab
+  for (int k = 0; k < ns; ++k) {
+    const int a = k == 0 ? 0 : lo(k), b = k == ns - 1 ? p->ny + 1 : hi(k);
+    const size_t off = NXG * (size_t)a, w = NXG * (size_t)(b - a + 1) * sizeof(double);
+    FRB_CUDA(cudaMemcpy2DAsync(U + off, pitch, u_in + off, pitch, w, nplanes, cudaMemcpyHostToDevice, si));
+    FRB_CUDA(cudaEventRecord(ev_in[k], si));
+  }
+  int rc = FRB_OK;
+  auto ring = [&](int k) -> int {  // frozen ghosts of slab k's rows into the stage buffers and the result
+    const int a = k == 0 ? 0 : lo(k), b = k == ns - 1 ? p->ny + 1 : hi(k);
+    int n = frb_launch_ring_rows2d(p, U, nst > 1 ? S1 : nullptr, nst > 2 ? S2 : nullptr, OUT, a, b);
+    if (n > 0) p->launches += n;
+    return n < 0 ? n : 0;
+  };
+  for (int w = 0; w < ns + nst - 1 && rc == FRB_OK; ++w) {
+    if (w == 0) {
+      FRB_CUDA(cudaStreamWaitEvent(sc, ev_in[0], 0));
+      if ((rc = ring(0)) != FRB_OK) break;
+    }
+    if (w + 1 < ns) {
+      FRB_CUDA(cudaStreamWaitEvent(sc, ev_in[w + 1], 0));
+      if ((rc = ring(w + 1)) != FRB_OK) break;
+    }
+    for (int s = 0; s < nst; ++s) {
+      const int k = w - s;
+      if (k < 0 || k >= ns) continue;
+      p->row_lo = lo(k);
+      p->row_hi = hi(k);
+      int n = launch_stage(p, stg[s].in, stg[s].ua, stg[s].out, stg[s].st);
+      p->row_lo = p->row_hi = 0;
+      if (n < 0) { rc = n; break; }
+      if (s == nst - 1) {  // slab k is final: on its way down
+        FRB_CUDA(cudaEventRecord(ev_c[k], sc));
+        FRB_CUDA(cudaStreamWaitEvent(so, ev_c[k], 0));
+        const int a = k == 0 ? 0 : lo(k), b = k == ns - 1 ? p->ny + 1 : hi(k);
+        const size_t off = NXG * (size_t)a, wd = NXG * (size_t)(b - a + 1) * sizeof(double);
+        FRB_CUDA(cudaMemcpy2DAsync(u_out + off, pitch, OUT + off, pitch, wd, nplanes, cudaMemcpyDeviceToHost, so));
+      }
+    }
+  }
+  FRB_CUDA(cudaEventRecord(p->ev1, sc));
+  FRB_CUDA(cudaStreamSynchronize(si));
+  FRB_CUDA(cudaStreamSynchronize(sc));
+  FRB_CUDA(cudaStreamSynchronize(so));
+  if (rc != FRB_OK) return rc;
+  std::swap(p->u, p->s3);  // the result is the resident state
+  p->ref_valid = true;
+  p->rc_valid = false;
+  FRB_CUDA(cudaEventElapsedTime(&p->last_ms, p->ev0, p->ev1));
+  p->last_launches = p->launches - l0;
+  prof_collect(p);
   return FRB_OK;
 }
 

@@ -74,6 +74,7 @@ struct frb_prob_s {
   double *u = nullptr;              // resident state  (u_n)
   double *s1 = nullptr, *s2 = nullptr;  // stage buffers
   double *du = nullptr;             // f! output (lazy)
+  double *s3 = nullptr;             // fourth state buffer of the pipelined host step (frb_step_host, lazy)
   std::vector<double *> rk_k;       // stage derivatives of frb_step_tableau (lazy)
   // row-chunk mirror of the 2-D Euler state (frb_rc.cuh): the layout frb_step streams in.  u is
   // the reference image the ABI exposes; exactly one of the two (or both) is current.
@@ -156,6 +157,7 @@ int frb_launch_ns2d(frb_prob_t p, const double *u, const double *ua, double *out
 int frb_launch_ghost_fill2d(frb_prob_t p, double *u, int mode);
 int frb_launch_ring_copy2d(frb_prob_t p, const double *src, double *dst, bool row0 = true, bool rowN = true);
 int frb_launch_ghost_x2d(frb_prob_t p, double *u, int mode);
+int frb_launch_ring_rows2d(frb_prob_t p, const double *src, double *d1, double *d2, double *d3, int ra, int rb);
 int frb_launch_lincomb(frb_prob_t p, double *out, const double *u, int n, double *const *k, const double *c,
                        double dt);
 // frb_halo.cu

@@ -188,6 +188,29 @@ __global__ void ring_copy_kernel(const double *__restrict__ src, double *__restr
   dst[idx] = src ? src[idx] : 0.0;
 }
 
+// ghost cells of rows ra..rb of every plane (rows 0 / ny+1 entirely, otherwise columns 0 and nx+1): src -> up to three
+// buffers.  The slab-wise form of ring_copy_kernel for the pipelined host step (frb_step_host).
+__global__ void ring_rows_kernel(const double *__restrict__ src, double *__restrict__ d1, double *__restrict__ d2,
+                                 double *__restrict__ d3, int nx, int ny, int ra) {
+  const int r = ra + blockIdx.x, p = blockIdx.y;
+  const int NXG = nx + 2;
+  const size_t base = (size_t)NXG * r + (size_t)NXG * (ny + 2) * p;
+  if (r == 0 || r == ny + 1) {
+    for (int i = threadIdx.x; i < NXG; i += blockDim.x) {
+      const double v = src[base + i];
+      if (d1) d1[base + i] = v;
+      if (d2) d2[base + i] = v;
+      if (d3) d3[base + i] = v;
+    }
+  } else if (threadIdx.x < 2) {
+    const int i = threadIdx.x == 0 ? 0 : NXG - 1;
+    const double v = src[base + i];
+    if (d1) d1[base + i] = v;
+    if (d2) d2[base + i] = v;
+    if (d3) d3[base + i] = v;
+  }
+}
+
 // positive_limiter(u[nsp,nsp,4], gamma, weights, ll, lr): dissipation.jl:125-206, density branch
 // One element at offset e with plane stride NE (reference image: NE = (nx+2)(ny+2); row-chunk
 // layout: NE = 32); dup >= 0 is the offset of the element's copy in the neighbouring chunk.
@@ -328,6 +351,14 @@ int frb_launch_ring_copy2d(frb_prob_t p, const double *src, double *dst, bool ro
   dim3 blk(128), grd((nring + 127) / 128, nplanes);
   ring_copy_kernel<<<grd, blk, 0, p->ctx->stream>>>(src, dst, p->nx, p->ny, nplanes, row0, rowN);
   if (int rc = check_launch2("ring_copy_kernel")) return rc;
+  return 1;
+}
+
+int frb_launch_ring_rows2d(frb_prob_t p, const double *src, double *d1, double *d2, double *d3, int ra, int rb) {
+  if (rb < ra) return 0;
+  dim3 blk(128), grd(rb - ra + 1, 4 * p->nsp * p->nsp);
+  ring_rows_kernel<<<grd, blk, 0, p->ctx->stream>>>(src, d1, d2, d3, p->nx, p->ny, ra);
+  if (int rc = check_launch2("ring_rows_kernel")) return rc;
   return 1;
 }
 

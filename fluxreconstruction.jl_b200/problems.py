@@ -169,6 +169,21 @@ class _Problem:
         check(lib().frb_rhs_pipelined(self.h, fortran_ptr(u), fortran_ptr(du), int(nslab)))
         return None
 
+    def step_host(self, u_in, u_out, alg, dt, nslab=32):
+        """step!(itg) with the state on the host between steps: ``u_out`` = one step of ``alg`` from ``u_in`` (host
+        arrays, may be the same).  2-D Euler problems stream the state through the device in ``nslab`` row slabs
+        (upload, stages and download overlapped); the ghost cells are the caller's and stay frozen.  Everything else
+        is upload + step + download."""
+        if u_in.shape != self.u0.shape or u_out.shape != self.u0.shape:
+            raise ValueError("step_host: array shape does not match the problem")
+        if hasattr(alg, "tableau"):
+            self.upload(u_in)
+            self.step(alg, dt, 1)
+            self.download(u_out)
+            return None
+        check(lib().frb_step_host(self.h, fortran_ptr(u_in), fortran_ptr(u_out), alg.code, float(dt), int(nslab)))
+        return None
+
     def rhs_resident(self, du=None):
         """L(u) of the resident state; left on the device (timing / chaining) unless ``du`` (a host
         array of the state's shape) is given."""

@@ -182,6 +182,15 @@ int32_t frb_rhs(frb_prob_t prob, const double *u_host, double *du_host, double t
 /* As frb_rhs with host pointers, but streams the 2-D state through the device in
  * row slabs so that H2D, compute and D2H overlap (euler2d only). */
 int32_t frb_rhs_pipelined(frb_prob_t prob, const double *u_host, double *du_host, int32_t nslab);
+/* step!(itg) with itg.u on the host between steps (the user loop of euler2d_wave.jl:125-135: the user fills the
+ * ghost cells / limits / filters the HOST array, then steps): u_out = one step of `scheme` from u_in, both host
+ * arrays in the reference image (they may be the same array).  2-D Euler, HLL, deg 2-3, no device step hooks: the
+ * state streams through the device in `nslab` row slabs -- upload of the next slab, the stages of the slabs that
+ * have arrived and the download of finished slabs overlap (PCIe full duplex); the ghost cells are the caller's and
+ * stay frozen through the step.  Every other case: upload + frb_step + download.  The result is also the resident
+ * state afterwards. */
+int32_t frb_step_host(frb_prob_t prob, const double *u_in_host, double *u_out_host, int32_t scheme, double dt,
+                      int32_t nslab);
 
 /* ---- step!(itg) ---------------------------------------------------------------- */
 /* what the user loop does around step! (euler2d_wave.jl:125-135, shock-vortex.jl:296-303):

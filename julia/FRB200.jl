@@ -190,6 +190,14 @@ rhs_pipelined!(prob::Problem; nslab = 32) = function (du, u, p, t)
                                   prob.h, parent(u), parent(du), nslab))
     nothing
 end
+# step!(itg) with itg.u on the host between steps (euler2d_wave.jl:125-135): u_out = one step from u_in, streamed
+# through the device in row slabs (upload, stages and download overlap); ghost cells are the caller's
+function step_host!(prob::Problem, u_out, u_in, scheme::Symbol, dt; nslab = 32)
+    GC.@preserve u_out u_in check(ccall((:frb_step_host, lib), Int32,
+        (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Int32, Float64, Int32),
+        prob.h, parent(u_in), parent(u_out), Int32(SCHEME[scheme]), dt, nslab))
+    u_out
+end
 # page-locked host arrays for the host-buffer paths
 function host_array(dims::Dims)
     r = Ref{Ptr{Cvoid}}(C_NULL)

@@ -922,3 +922,59 @@ def test_tableau_problems_free_their_stage_buffers(FR, oracle):
     free1 = C.c_size_t()
     drv.cuMemGetInfo_v2(C.byref(free1), C.byref(total))
     assert free0.value - free1.value < 64 << 20, (free0.value, free1.value)  # 8 x 6 x 34 MB would be 1.6 GB
+
+
+# ---------------------------------------------------------------- step!(itg) with the state on the host (frb_step_host)
+@pytest.mark.parametrize("scheme", ["euler", "midpoint", "ssprk3"])
+@pytest.mark.parametrize("nx,ny,deg,nslab", [(64, 96, 3, 5), (30, 41, 3, 16), (40, 24, 2, 2), (64, 64, 3, 32)])
+def test_step_host_streams_the_user_loop(FR, oracle, coracle, scheme, nx, ny, deg, nslab):
+    """The reference's user loop (euler2d_wave.jl:125-135: ghost fill on the HOST array, then step!): frb_step_host
+    streams the state through the device in row slabs -- upload, stages and download overlapped -- and must equal
+    upload + frb_step + download bit for bit, the oracle to 1e-12, and leave the result as the resident state."""
+    ps = FR.FRPSpace2D(0.0, 1.0, nx, 0.0, 1.0, ny, deg, 1, 1)
+    u = noisy(oracle.ic_wave2d(ps, GAMMA, "x"), 0.02, 61)
+    u[..., 2] += 0.05 * u[..., 0]
+    alg = {"euler": FR.Euler, "midpoint": FR.Midpoint, "ssprk3": FR.SSPRK33}[scheme]()
+    dt = 2e-4
+    prob = FR.Euler2DProblem(u, (0.0, 1.0), ps, GAMMA)
+    plain = FR.Euler2DProblem(u, (0.0, 1.0), ps, GAMMA, kernel="march")
+    uh = FR.pinned_empty(u.shape)
+    uh[...] = u
+    ref = u.copy(order="F")
+    for _ in range(3):  # three turns of the user loop, the state on the host in between
+        oracle.ghost_fill_euler2d(uh, "wave_x")
+        ref = coracle.integrate_euler2d(ref, ps, GAMMA, dt, 1, scheme, "wave_x")
+        plain.upload(np.asarray(uh))
+        plain.step(alg, dt, 1)
+        want = plain.download()
+        prob.step_host(uh, uh, alg, dt, nslab=nslab)  # in place: u_out is u_in
+        assert np.array_equal(np.asarray(uh), want)
+    assert rel(np.asarray(uh)[1:-1, 1:-1], ref[1:-1, 1:-1]) <= 1e-12
+    assert np.array_equal(prob.download(), np.asarray(uh))  # ... and it is the resident state
+    # the ghost cells came back as they went in (frozen through the step)
+    g = np.asarray(uh).copy()
+    oracle.ghost_fill_euler2d(g, "wave_x")
+    prob.close()
+    plain.close()
+    FR.pinned_free(uh)
+
+
+def test_step_host_falls_back_to_the_plain_path(FR, oracle, coracle):
+    """problems the streamed form does not cover (device step hooks here, other kinds, odd nx) take
+    upload + frb_step + download: same call, same result"""
+    ps = FR.FRPSpace2D(0.0, 1.0, 31, 0.0, 1.0, 20, 3, 1, 1)  # odd nx: no reference-image marching kernel
+    u = noisy(oracle.ic_wave2d(ps, GAMMA, "x"), 0.02, 67)
+    prob = FR.Euler2DProblem(u, (0.0, 1.0), ps, GAMMA)
+    prob.set_hooks(ghost="wave_x")
+    out = np.zeros_like(u, order="F")
+    prob.step_host(u, out, FR.SSPRK33(), 2e-4, nslab=4)
+    ref = coracle.integrate_euler2d(u, ps, GAMMA, 2e-4, 1, "ssprk3", "wave_x")
+    assert rel(out[1:-1, 1:-1], ref[1:-1, 1:-1]) <= 1e-12
+    prob.close()
+    ps1 = FR.FRPSpace1D(0.0, 1.0, 64, 3)
+    w0 = noisy(oracle.ic_sod1d(ps1, GAMMA), 0.02, 3)
+    p1 = FR.FREulerProblem(w0, (0.0, 0.1), ps1, GAMMA, "dirichlet")
+    o1 = np.zeros_like(w0, order="F")
+    p1.step_host(w0, o1, FR.Midpoint(), 1e-4)
+    assert rel(o1, coracle.integrate_euler1d(w0, ps1, GAMMA, "dirichlet", 1e-4, 1, "midpoint")) <= 1e-12
+    p1.close()
