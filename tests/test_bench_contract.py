@@ -60,3 +60,41 @@ def test_reference_arm_of_the_other_configurations():
         d = json.loads([ln for ln in r.stdout.splitlines() if ln.strip()][-1])
         assert d["impl"] == "reference" and d["value"] > 0 and d["cpu_baseline"]["kind"] == "port"
         assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["unit"] == "DOF-updates/s"
+
+
+def test_clock_sampler_counts_only_the_samples_inside_the_timed_window():
+    """bench.ClockSampler: nvidia-smi lines are stamped when read; only those between mark_begin and mark_end count,
+    with the warm-up samples under load as the stated fallback when the window caught none."""
+    import importlib.util as u
+    import time
+
+    spec = u.spec_from_file_location("bench", os.path.join(ROOT, "bench.py"))
+    b = u.module_from_spec(spec)
+    spec.loader.exec_module(b)
+
+    class FakeProc:
+        def terminate(self):
+            pass
+
+        def wait(self, timeout=None):
+            return 0
+
+    def line(sm, power, cap):
+        return f"2026/10/17 20:00:00.000, 0, {sm}, 1965, {power}, 0x4, Not Active, Not Active, Not Active, {cap}"
+
+    t = time.time()
+    s = b.ClockSampler(0)
+    s.proc = FakeProc()
+    s.lines = [(t - 1.0, line(345, 120.0, "Not Active")), (t - 0.5, line(1965, 600.0, "Not Active")),
+               (t + 0.01, line(1900, 650.0, "Active")), (t + 0.03, line(1850, 660.0, "Active")),
+               (t + 1.0, line(345, 110.0, "Not Active"))]
+    s.t0, s.t1 = t, t + 0.05
+    r = s.stop()
+    assert r["samples"] == 2 and r["sm_mhz"] in (1900.0, 1850.0) and r["reasons"] == ["sw_power_cap"]
+    assert r["window"] == "timed region" and r["sm_max_mhz"] == 1965.0
+    s2 = b.ClockSampler(0)
+    s2.proc = FakeProc()
+    s2.lines = s.lines[:2]
+    s2.t0, s2.t1 = t, t + 0.05
+    r2 = s2.stop()
+    assert r2["samples"] == 1 and r2["sm_mhz"] == 1965.0 and r2["window"].startswith("warm-up")
