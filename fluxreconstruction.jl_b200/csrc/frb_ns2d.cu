@@ -280,13 +280,24 @@ ns_face_kernel(const double *__restrict__ u, double *__restrict__ fhx, double *_
   // stride of the contracted index and offset of the fixed one inside an element block
   const int sq = yface ? 4 : 4 * NSP, base = yface ? 4 * NSP * r : 4 * r;
   const double iJ = yface ? gas.iJy : gas.iJx;
+  // the four variables of a point are 32 contiguous, 32-byte aligned bytes: two 16-byte loads per point and cell, all
+  // 4 NSP of them issued before the first use
+  double vA[NSP][4], vB[NSP][4];
+#pragma unroll
+  for (int q = 0; q < NSP; ++q) {
+    const double2 *pa = reinterpret_cast<const double2 *>(eA + base + sq * q);
+    const double2 *pb = reinterpret_cast<const double2 *>(eB + base + sq * q);
+    const double2 a01 = pa[0], a23 = pa[1], b01 = pb[0], b23 = pb[1];
+    vA[q][0] = a01.x; vA[q][1] = a01.y; vA[q][2] = a23.x; vA[q][3] = a23.y;
+    vB[q][0] = b01.x; vB[q][1] = b01.y; vB[q][2] = b23.x; vB[q][3] = b23.y;
+  }
   double wA[4], wB[4], sA[4], sB[4];
 #pragma unroll
   for (int m = 0; m < 4; ++m) {
     double a = 0, b = 0, c = 0, d = 0;
 #pragma unroll
     for (int q = 0; q < NSP; ++q) {
-      const double va = eA[base + sq * q + m], vb = eB[base + sq * q + m];
+      const double va = vA[q][m], vb = vB[q][m];
       a += va * ops.lr[q];   // trace of the lower cell on its upper face
       b += vb * ops.ll[q];   // trace of the upper cell on its lower face
       c += va * ops.dll[q];  // swL (the left cell's slope uses dll, :213)
@@ -303,12 +314,13 @@ ns_face_kernel(const double *__restrict__ u, double *__restrict__ fhx, double *_
   const double fw[4] = {h[0], yface ? -h[2] : h[1], yface ? h[1] : h[2], h[3]};
   double *o = yface ? fhy + 4 * (r + NSP * ((long long)(j - 1) + (long long)(ny + 1) * (i - 1)))
                     : fhx + 4 * (r + NSP * ((long long)(j - 1) + (long long)ny * (i - 1)));
-  o[0] = fw[0]; o[1] = fw[1]; o[2] = fw[2]; o[3] = fw[3];
+  reinterpret_cast<double2 *>(o)[0] = make_double2(fw[0], fw[1]);
+  reinterpret_cast<double2 *>(o)[1] = make_double2(fw[2], fw[3]);
 }
 
-// (Issuing every global load before the first use -- state row, the four common fluxes, u_n: 92-116 registers --
-// was measured and dropped: 1.431 / 1.456 ms per 16-B / 24-B stage at 6 CTAs / SM against 1.421 / 1.480 for this
-// form at 64 registers and 8 CTAs / SM; profiles/r02_summary.md section D.)
+// (Issuing every global load before the first use and / or 16-byte loads -- 80-116 registers -- were measured and
+// dropped: every variant is 5-10 % slower than this form at 64 registers and 8 CTAs / SM, although the same change
+// gained 16 % in the face kernel; profiles/r02_summary.md section D.)
 // ---- element kernel: thread = (solution point, element); a block holds EPB consecutive cells of a
 // column of the mesh (j fastest in memory)
 template <int NSP, int EPB>
