@@ -1168,6 +1168,12 @@ extern "C" int32_t frb_step_host(frb_prob_t p, const double *u_in, double *u_out
                         !p->limiter_on && p->filt_when == 0 && nslab > 1 && p->ny >= 2 * nslab;
   if (!streamed) {
     if (int rc = frb_state_upload(p, u_in)) return rc;
+    if (frb_halo_active(p)) {
+      // slab-parallel: every rank makes this call; the neighbours' halo rows of the new state are exchanged behind a
+      // neighbour barrier on the mailbox (nobody pushes into a buffer its owner is still uploading)
+      FRB_CUDA(cudaSetDevice(p->ctx->device));
+      if (int rc = halo_republish(p, p->u)) return rc;
+    }
     if (int rc = frb_step(p, scheme, dt, 1)) return rc;
     return frb_state_download(p, u_out);
   }

@@ -68,7 +68,10 @@ __device__ __forceinline__ double stage_out(const FrbStage &st, const double *ua
 // Block = 32 cells (lanes, coalesced) x kMomGroups velocity groups (warps): each warp sums its
 // contiguous slice of the velocity grid in order, the slices are combined in order through smem
 // (deterministic; the reference's `sum` has no specified order either).
-constexpr int kMomGroups = 8;
+#ifndef FRB_BGK_MOMGROUPS
+#define FRB_BGK_MOMGROUPS 8  // kernel experiment switch (scripts/build_variants.py)
+#endif
+constexpr int kMomGroups = FRB_BGK_MOMGROUPS;
 __global__ void __launch_bounds__(32 * kMomGroups)
 bgk_moments_kernel(const double *__restrict__ u, double *__restrict__ prim, int ncell, int nu, int nsp,
                    const double *__restrict__ velo, const double *__restrict__ wts, int model, double a) {

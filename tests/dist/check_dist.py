@@ -4,7 +4,7 @@ the N-rank result must equal the single-domain oracle on the same global mesh.
   python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 \
       --master-port 29511 tests/dist/check_dist.py [nx ny_global nsteps scheme kernel ghost hooks]
 
-hooks: "none" | "limiter" (positive_limiter before every step, shock-vortex.jl:298-303) | "filter" (modal filter
+hooks: "none" | "step_host" (frb_step_host per step) | "limiter" (positive_limiter before every step, shock-vortex.jl:298-303) | "filter" (modal filter
 after every step, :308-321) | "rhs" (also f!(du,u) of the resident slabs against the oracle residual)
 """
 import os
@@ -62,8 +62,15 @@ if wl is not None:
     prob.set_hooks(ghost=ghost, limiter_weights=wl)
 if hooks == "filter":
     prob.modal_filter(psl, 1e-3, when="after")
-prob.step(alg, dt, nsteps)
-res = prob.download()
+if hooks == "step_host":
+    # the user loop with the state on the host between steps: every rank calls frb_step_host on its slab (upload,
+    # halo rows re-sent behind a neighbour barrier, step with the device ghost hook, download)
+    res = ul.copy(order="F")
+    for _ in range(nsteps):
+        prob.step_host(res, res, alg, dt)
+else:
+    prob.step(alg, dt, nsteps)
+    res = prob.download()
 du_l = None
 if hooks == "rhs":
     du_l = np.zeros_like(ul, order="F")

@@ -72,6 +72,13 @@ def test_n_rank_slabs_with_step_hooks(world, kernel, hooks):
     _torchrun(world, 29525, "check_dist.py", 64, 96, 5, "ssprk3", kernel, "wave_x", hooks)
 
 
+@pytest.mark.parametrize("world", [2, 4])
+def test_n_rank_slabs_with_the_state_on_the_host_between_steps(world):
+    """frb_step_host on a connected problem: upload, halo rows re-sent behind a neighbour barrier, step, download"""
+    _need(world)
+    _torchrun(world, 29529, "check_dist.py", 64, 96, 4, "ssprk3", "auto", "wave_x", "step_host")
+
+
 @pytest.mark.parametrize("nx,ny,deg", [(33, 20, 2), (16, 12, 3)])
 def test_two_rank_cavity_slabs_match_oracle(nx, ny, deg):
     """cfg5 split in column slabs: RHS and 30 Euler steps of 2 ranks == the single-domain C oracle."""
