@@ -185,6 +185,68 @@ bgk1d_kernel(const double *__restrict__ u, const double *__restrict__ ua, double
   }
 }
 
+// Two adjacent cells per thread (even ncell): own values, u_n, the Maxwellian parameters and the result move as
+// 16-byte accesses, and one of the two upwind neighbours is the other cell of the pair (no load, its flux trace is
+// computed anyway) -- half the load, store and address instructions per DOF of the kernel above.
+template <int NSP>
+__global__ void __launch_bounds__(128)
+bgk1d_pair_kernel(const double *__restrict__ u, const double *__restrict__ ua, double *__restrict__ out,
+                  const double *__restrict__ prim, const double *__restrict__ inv_j,
+                  const double *__restrict__ velo, int ncell, int nu, double inv_tau, FrbOps ops, FrbStage st) {
+  const int i = 2 * (blockIdx.x * blockDim.x + threadIdx.x);  // cells i, i + 1
+  if (i >= ncell) return;
+  const int j = blockIdx.y;
+  const size_t vs = (size_t)ncell * nu, row = (size_t)ncell * j;
+  const double v = velo[j];
+  const bool pos = v >= 0.0;  // heaviside delta, bgk_wave.jl:26
+  // the one upwind neighbour outside the pair: cell i - 1 for v >= 0, cell i + 2 otherwise (periodic)
+  const int in = pos ? (i == 0 ? ncell - 1 : i - 1) : (i + 2 >= ncell ? 0 : i + 2);
+  const double2 ij = *reinterpret_cast<const double2 *>(inv_j + i);
+  const double s0 = v * ij.x, s1 = v * ij.y, sn = v * inv_j[in];  // v / J
+  double2 uc[NSP];
+  double f0[NSP], f1[NSP], fn[NSP];
+#pragma unroll
+  for (int q = 0; q < NSP; ++q) {
+    uc[q] = *reinterpret_cast<const double2 *>(u + i + row + vs * q);
+    fn[q] = sn * u[in + row + vs * q];
+  }
+#pragma unroll
+  for (int q = 0; q < NSP; ++q) { f0[q] = s0 * uc[q].x; f1[q] = s1 * uc[q].y; }  // :85-88
+  const double fL0 = dotn<NSP>(f0, ops.ll), fR0 = dotn<NSP>(f0, ops.lr);  // interp_face! :99-101
+  const double fL1 = dotn<NSP>(f1, ops.ll), fR1 = dotn<NSP>(f1, ops.lr);
+  // f_interaction - own trace at the left / right face (:103-107): zero on the downwind side
+  const double cl0 = pos ? dotn<NSP>(fn, ops.lr) - fL0 : 0.0, cr0 = pos ? 0.0 : fL1 - fR0;
+  const double cl1 = pos ? fR0 - fL1 : 0.0, cr1 = pos ? 0.0 : dotn<NSP>(fn, ops.ll) - fR1;
+  const bool with_a = st.use_a && !st.rhs_only;
+#pragma unroll
+  for (int p = 0; p < NSP; ++p) {
+    const size_t po = i + (size_t)ncell * p;
+    const double2 pre = *reinterpret_cast<const double2 *>(prim + po);
+    const double2 U = *reinterpret_cast<const double2 *>(prim + po + (size_t)ncell * NSP);
+    const double2 lam = *reinterpret_cast<const double2 *>(prim + po + 2 * (size_t)ncell * NSP);
+    const double c0 = v - U.x, c1 = v - U.y;
+    const double M0 = pre.x * exp_neg(-lam.x * (c0 * c0)), M1 = pre.y * exp_neg(-lam.y * (c1 * c1));  // maxwellian
+    const double d0 = -(dotn<NSP>(f0, &ops.lpdm[p * FRB_NSPMAX]) + cl0 * ops.dgl[p] + cr0 * ops.dgr[p]) +
+                      (M0 - uc[p].x) * inv_tau;
+    const double d1 = -(dotn<NSP>(f1, &ops.lpdm[p * FRB_NSPMAX]) + cl1 * ops.dgl[p] + cr1 * ops.dgr[p]) +
+                      (M1 - uc[p].y) * inv_tau;
+    const size_t idx = i + row + vs * p;
+    double2 o;
+    if (st.rhs_only) {
+      o = make_double2(d0, d1);
+    } else {
+      o.x = st.nested ? st.cb * (uc[p].x + st.cdt * d0) : st.cb * uc[p].x + st.cdt * d0;
+      o.y = st.nested ? st.cb * (uc[p].y + st.cdt * d1) : st.cb * uc[p].y + st.cdt * d1;
+      if (with_a) {
+        const double2 an = *reinterpret_cast<const double2 *>(ua + idx);
+        o.x = st.ca * an.x + o.x;
+        o.y = st.ca * an.y + o.y;
+      }
+    }
+    *reinterpret_cast<double2 *>(out + idx) = o;
+  }
+}
+
 // ---- one pass: moments, Maxwellian and the stage update from ONE read of u ----------------------------------
 // A CTA owns kFC = 8 cells x all nu velocities x NSP points and keeps them in REGISTERS: thread = (cell pair,
 // velocity group) holds u of 2 cells (16-byte loads: a warp instruction covers 8 rows of 64 bytes) x VR
@@ -465,11 +527,28 @@ int frb_launch_bgk1d(frb_prob_t p, const double *u, const double *ua, double *ou
     }
   }
   dim3 blk(128), g1((p->ncell + 31) / 32, p->nsp), g2((p->ncell + 127) / 128, p->nu);
+  // (a two-cells-per-lane form of the moments kernel with 16-byte loads was measured: 39.9 / 51.6 us per stage
+  // against 39.5 / 50.0 with this one -- dropped)
   bgk_moments_kernel<<<g1, 32 * kMomGroups, 0, p->ctx->stream>>>(u, p->prim, p->ncell, p->nu, p->nsp, p->velo, p->weights,
                                                                   p->bgk_model, p->a);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return frb_cuda_fail(e, "bgk_moments_kernel", __FILE__, __LINE__);
   const double it = 1.0 / p->tau;
+#ifndef FRB_BGK_NO_PAIR
+  // two cells per thread where the pairs are 16-byte aligned: even ncell, aligned buffers, deg 1..3
+  if (p->ncell % 2 == 0 && p->nsp <= 4 && u != out &&
+      (((uintptr_t)u | (uintptr_t)out | (uintptr_t)(ua ? ua : u) | (uintptr_t)p->prim | (uintptr_t)p->J) & 15) == 0) {
+    dim3 gp((p->ncell / 2 + 127) / 128, p->nu);
+    switch (p->nsp) {
+      case 2: bgk1d_pair_kernel<2><<<gp, blk, 0, p->ctx->stream>>>(u, ua, out, p->prim, p->J, p->velo, p->ncell, p->nu, it, p->ops, st); break;
+      case 3: bgk1d_pair_kernel<3><<<gp, blk, 0, p->ctx->stream>>>(u, ua, out, p->prim, p->J, p->velo, p->ncell, p->nu, it, p->ops, st); break;
+      default: bgk1d_pair_kernel<4><<<gp, blk, 0, p->ctx->stream>>>(u, ua, out, p->prim, p->J, p->velo, p->ncell, p->nu, it, p->ops, st); break;
+    }
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return frb_cuda_fail(e, "bgk1d_pair_kernel", __FILE__, __LINE__);
+    return 2;
+  }
+#endif
   // VPT velocities per thread where it pays: measured at cfg4 (us per stage, VPT = 1 / 2 / 4): 16-B stage 45.2 /
   // 43.5 / 43.8, 24-B stage 55.9 / 59.6-60.9 / 62.5 -- the u_n loads of a 24-B stage want the occupancy back
   const bool multi = p->nu % FRB_BGK_VPT == 0 && !(st.use_a && !st.rhs_only);
