@@ -80,7 +80,7 @@ def build(FR, cfg, ctx):
         return dict(prob=prob, u0=u0, alg=FR.Midpoint(), dt=0.1 * (1.0 / 8192) / 5.0, bytes=[16, 24], ps=ps, vs=vs,
                     workload="1D BGK, FRPSpace1D deg 2, 8192 cells x 256 velocities, Midpoint fixed dt "
                              "(example/bgk_wave.jl)",
-                    kernel="bgk1d_fused_kernel<3, 4> (moments, Maxwellian and stage from one read of u)")
+                    kernel="bgk_moments_kernel + bgk1d_pair_kernel<3> (two launches per stage; two adjacent cells per thread)")
     if cfg == "5":
         n = 1024
         ps = FR.FRPSpace2D(0.0, 1.0, n, 0.0, 1.0, n, 3, 1, 1)
