@@ -72,6 +72,15 @@ def test_n_rank_slabs_with_step_hooks(world, kernel, hooks):
     _torchrun(world, 29525, "check_dist.py", 64, 96, 5, "ssprk3", kernel, "wave_x", hooks)
 
 
+@pytest.mark.parametrize("nyg", [2, 4, 6, 10])
+def test_two_rank_slabs_of_one_two_three_rows(nyg):
+    """tiny slabs: 1, 2, 3 and 5 owned rows per rank -- the row-chunk kernel's boundary rows are one-row segments of
+    their own; with one owned row the same CTA consumes both halo rows and raises both flags"""
+    _need(2)
+    _torchrun(2, 29531, "check_dist.py", 64, nyg, 6, "ssprk3", "auto", "wave_x")
+    _torchrun(2, 29531, "check_dist.py", 31, nyg, 4, "midpoint", "rc", "wave_y")
+
+
 @pytest.mark.parametrize("world", [2, 4])
 def test_n_rank_slabs_with_the_state_on_the_host_between_steps(world):
     """frb_step_host on a connected problem: upload, halo rows re-sent behind a neighbour barrier, step, download"""
