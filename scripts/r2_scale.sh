@@ -3,7 +3,7 @@
 # parity objects and the e2e legs inside); FRB_SCALE_TESTS=1 adds the 2 / 4 / 8-rank parity tests
 mkdir -p gpurun_out
 if [ -n "$FRB_SCALE_TESTS" ]; then
-  FRB_REQUIRE_GPUS=8 timeout 900 python -m pytest tests/test_gpu_multi.py -m gpu -q -k "two_rank_slabs or 8] or 4-ssprk3 or rhs[4 or hooks[auto-limiter-4 or hooks[auto-filter-4 or cavity_slabs_match_oracle[4" > gpurun_out/r2_multi_tests_8.log 2>&1
+  FRB_REQUIRE_GPUS=8 timeout 900 python -m pytest tests/test_gpu_multi.py -m gpu -q -k "8] or 4-ssprk3 or rhs[4 or hooks[auto-limiter-4 or hooks[auto-filter-4 or cavity_slabs_match_oracle[4 or eight_rank or host_between_steps[4 or rows[16" > gpurun_out/r2_multi_tests_8.log 2>&1
   tail -4 gpurun_out/r2_multi_tests_8.log
 fi
 for N in ${FRB_SCALE_NS:-1 2 4 8}; do

@@ -81,6 +81,13 @@ def test_two_rank_slabs_of_one_two_three_rows(nyg):
     _torchrun(2, 29531, "check_dist.py", 31, nyg, 4, "midpoint", "rc", "wave_y")
 
 
+@pytest.mark.parametrize("nyg", [8, 16])
+def test_eight_rank_slabs_of_one_and_two_rows(nyg):
+    """eight slabs of one / two rows: every rank's only rows are boundary rows of both neighbours"""
+    _need(8)
+    _torchrun(8, 29533, "check_dist.py", 64, nyg, 6, "ssprk3", "auto", "wave_x")
+
+
 @pytest.mark.parametrize("world", [2, 4])
 def test_n_rank_slabs_with_the_state_on_the_host_between_steps(world):
     """frb_step_host on a connected problem: upload, halo rows re-sent behind a neighbour barrier, step, download"""
