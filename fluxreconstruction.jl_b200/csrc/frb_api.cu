@@ -1308,8 +1308,11 @@ extern "C" int32_t frb_last_timing(frb_prob_t p, float *ms, int64_t *kernel_laun
 
 extern "C" int32_t frb_set_kernel(frb_prob_t p, int32_t kind) {
   FRB_REQUIRE(p, FRB_ERR_ARG, "frb_set_kernel: prob is NULL");
-  FRB_REQUIRE(kind >= FRB_KERNEL_AUTO && kind <= FRB_KERNEL_BGK_ONE_PASS, FRB_ERR_ARG,
+  FRB_REQUIRE(kind >= FRB_KERNEL_AUTO && kind <= FRB_KERNEL_CURV_MARCH, FRB_ERR_ARG,
               "frb_set_kernel: unknown kernel kind");
+  if (kind == FRB_KERNEL_CURV_MARCH)
+    FRB_REQUIRE(p->kind == K_EULER2D && p->curv_iJ, FRB_ERR_STATE,
+                "frb_set_kernel: the one-launch marching kernel belongs to curvilinear euler2d problems");
   if (kind == FRB_KERNEL_BGK_ONE_PASS)
     FRB_REQUIRE(p->kind == K_BGK1D, FRB_ERR_STATE, "frb_set_kernel: the one-pass kernel belongs to bgk1d problems");
   if (kind == FRB_KERNEL_RC)

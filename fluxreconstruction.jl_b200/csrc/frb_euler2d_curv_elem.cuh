@@ -49,6 +49,9 @@ struct CurvGeom {
   int flux;      // FRB_FLUX_HLL (the scripts) | LF | ROE
 };
 
+int frb_launch_euler2d_curv_march(frb_prob_t p, const double *u, const double *ua, double *out, const CurvGeom &g,
+                                  const FrbStage &st);
+
 namespace frbcurv {
 
 struct W4 {
@@ -84,13 +87,39 @@ FRB_HD W4 flux_normal(int kind, W4 L, W4 R, double c, double s, double gamma, in
   return {f.f0, fma(-f.f2, s, f.f1 * c), fma(f.f1, s, f.f2 * c), f.f3};
 }
 
-template <int NSP>
-FRB_HD size_t plane(int k, int l, int m) {
-  return (size_t)(k + NSP * (l + NSP * m));
+// the same with the flux a compile-time choice (FLUX < 0: g.flux at run time): on the device every common flux in
+// its branch-free form (riemann4_fast) and the mirror state with MUFU-seeded reciprocals
+template <int FLUX>
+FRB_HD W4 flux_normal_t(int kind, W4 L, W4 R, double c, double s, double gamma, int wall) {
+#if defined(__CUDA_ARCH__)
+  if (FLUX < 0) return flux_normal(kind, L, R, c, s, gamma, wall);
+  const double gm1 = gamma - 1.0;
+  double l0 = L.a, l1 = fma(L.c, s, L.b * c), l2 = fma(-L.b, s, L.c * c), l3 = L.d;
+  const double r0 = R.a, r1 = fma(R.c, s, R.b * c), r2 = fma(-R.b, s, R.c * c), r3 = R.d;
+  if (wall) {
+    const double ir = frb::rcp_fast(r0), U = r1 * ir, V = r2 * ir;
+    const double lam = 0.5 * r0 * frb::rcp_fast(gm1 * (r3 - 0.5 * (r1 * r1 + r2 * r2) * ir));
+    const double t = lam - 1.0;
+    const double rn = (1.0 - t) * frb::rcp_fast(1.0 + t) * r0, ln = 2.0 - lam;
+    l0 = rn;
+    l1 = rn * (-U);
+    l2 = rn * V;
+    l3 = 0.5 * rn * frb::rcp_fast(ln * gm1) + 0.5 * rn * (U * U + V * V);
+  }
+  const frb::Flux4 f = frb::riemann4_fast<(FLUX < 0 ? 0 : FLUX)>(l0, l1, l2, l3, r0, r1, r2, r3, gamma, gm1);
+  return {f.f0, fma(-f.f2, s, f.f1 * c), fma(f.f1, s, f.f2 * c), f.f3};
+#else
+  return flux_normal(FLUX < 0 ? kind : FLUX, L, R, c, s, gamma, wall);
+#endif
 }
 
 template <int NSP>
-FRB_HD void load_trace_x(const double *__restrict__ u, size_t e, size_t NE, int p, const double *lq, double w[4]) {
+FRB_HD int plane(int k, int l, int m) {
+  return k + NSP * (l + NSP * m);
+}
+
+template <int NSP, typename IX>
+FRB_HD void load_trace_x(const double *__restrict__ u, IX e, IX NE, int p, const double *lq, double w[4]) {
 #pragma unroll
   for (int m = 0; m < 4; ++m) {  // dot(u[i,j,:,p,m], lq)
     double a = 0;
@@ -99,8 +128,8 @@ FRB_HD void load_trace_x(const double *__restrict__ u, size_t e, size_t NE, int 
     w[m] = a;
   }
 }
-template <int NSP>
-FRB_HD void load_trace_y(const double *__restrict__ u, size_t e, size_t NE, int p, const double *lq, double w[4]) {
+template <int NSP, typename IX>
+FRB_HD void load_trace_y(const double *__restrict__ u, IX e, IX NE, int p, const double *lq, double w[4]) {
 #pragma unroll
   for (int m = 0; m < 4; ++m) {  // dot(u[i,j,p,:,m], lq)
     double a = 0;
@@ -115,24 +144,27 @@ FRB_HD void load_trace_y(const double *__restrict__ u, size_t e, size_t NE, int 
 // The x face left of element (i, j) and the y face below it, flux point p, in one go: the four traces first
 // (64 loads without control flow in between, clamped to valid cells for the threads that own only one of the two
 // faces), then the two common fluxes.  do_x / do_y say which results exist (i <= nx + 1, j <= ny / i <= nx, j <= ny + 1).
-template <int NSP>
+// IX: the index type (size_t; unsigned when every array stays below 2^32 elements: a third fewer instructions
+// in kernels that are bound by instruction issue).  FLUX: see flux_normal_t.
+template <int NSP, typename IX = size_t, int FLUX = -1>
 FRB_HD void face_xy(int i, int j, int p, bool do_x, bool do_y, const double *__restrict__ u,
                     double *__restrict__ fx, double *__restrict__ fy, const CurvGeom &g, double gamma,
                     const FrbOps &ops) {
-  const size_t NXG = g.nx + 2, NE = NXG * (size_t)(g.ny + 2);
+  const IX NXG = g.nx + 2, NE = NXG * (IX)(g.ny + 2);
   const int jx = j <= g.ny ? j : g.ny, iy = i <= g.nx ? i : g.nx;
-  const size_t ex = i + NXG * jx, ey = iy + NXG * j;
+  const IX ex = i + NXG * jx, ey = iy + NXG * j;
   double xl[4], xr[4], yl[4], yr[4];
-  load_trace_x<NSP>(u, ex - 1, NE, p, ops.lr, xl);    // u_face[i-1, j, 2, p, :]
-  load_trace_x<NSP>(u, ex, NE, p, ops.ll, xr);        // u_face[i, j, 4, p, :]
-  load_trace_y<NSP>(u, ey - NXG, NE, p, ops.lr, yl);  // u_face[i, j-1, 3, p, :]
-  load_trace_y<NSP>(u, ey, NE, p, ops.ll, yr);        // u_face[i, j, 1, p, :]
-  const size_t f1 = (size_t)(i - 1) + (size_t)(g.nx + 1) * (jx - 1), s1 = (size_t)(g.nx + 1) * g.ny;
-  const size_t f2 = (size_t)(iy - 1) + (size_t)g.nx * (j - 1), s2 = (size_t)g.nx * (g.ny + 1);
+  load_trace_x<NSP, IX>(u, ex - 1, NE, p, ops.lr, xl);    // u_face[i-1, j, 2, p, :]
+  load_trace_x<NSP, IX>(u, ex, NE, p, ops.ll, xr);        // u_face[i, j, 4, p, :]
+  load_trace_y<NSP, IX>(u, ey - NXG, NE, p, ops.lr, yl);  // u_face[i, j-1, 3, p, :]
+  load_trace_y<NSP, IX>(u, ey, NE, p, ops.ll, yr);        // u_face[i, j, 1, p, :]
+  const IX f1 = (IX)(i - 1) + (IX)(g.nx + 1) * (jx - 1), s1 = (IX)(g.nx + 1) * g.ny;
+  const IX f2 = (IX)(iy - 1) + (IX)g.nx * (j - 1), s2 = (IX)g.nx * (g.ny + 1);
   const double c1 = g.n1[f1], d1 = g.n1[f1 + s1], c2 = g.n2[f2], d2 = g.n2[f2 + s2];
-  const W4 hx = flux_normal(g.flux, {xl[0], xl[1], xl[2], xl[3]}, {xr[0], xr[1], xr[2], xr[3]}, c1, d1, gamma,
-                            g.wall_xlo && i == 1);
-  const W4 hy = flux_normal(g.flux, {yl[0], yl[1], yl[2], yl[3]}, {yr[0], yr[1], yr[2], yr[3]}, c2, d2, gamma, 0);
+  const W4 hx = flux_normal_t<FLUX>(g.flux, {xl[0], xl[1], xl[2], xl[3]}, {xr[0], xr[1], xr[2], xr[3]}, c1, d1,
+                                    gamma, g.wall_xlo && i == 1);
+  const W4 hy = flux_normal_t<FLUX>(g.flux, {yl[0], yl[1], yl[2], yl[3]}, {yr[0], yr[1], yr[2], yr[3]}, c2, d2,
+                                    gamma, 0);
   if (do_x) {
     fx[f1 + s1 * (p + NSP * 0)] = hx.a;
     fx[f1 + s1 * (p + NSP * 1)] = hx.b;
@@ -171,17 +203,20 @@ struct RowCarry {
 // in registers (:138-142,150-157), f2 of the row into the element's tile for the y pass,
 // tile[((l NSP + k) 4 + m) ts] (ts = 32 lanes on the device, 1 on the host), and -- one flux point per row
 // owner -- the y common fluxes into fyt[((side NSP + p) 4 + m) ts].
-template <int NSP>
+// FOLD: the flux traces of the correction folded into the derivative matrix (FrbOps::dmod, as in the rectangular
+// marching kernels): sum_q lpdm[k][q] f[q] + (c F - f.ll) dgl[k] + (c F - f.lr) dgr[k]
+//                  = sum_q dmod[k][q] f[q] + c dgl[k] F + c dgr[k] F  -- a fifth fewer FP64 instructions per row.
+template <int NSP, typename IX = size_t, bool FOLD = false>
 FRB_HD void row_xpass(int i, int j, int l, const double *__restrict__ u, const double *__restrict__ fx,
                       const double *__restrict__ fy, const CurvGeom &g, double gamma, const FrbOps &ops,
                       double *__restrict__ tile, double *__restrict__ fyt, int ts, RowCarry<NSP> &c) {
   const int nx = g.nx, ny = g.ny;
-  const size_t NXG = nx + 2, NE = NXG * (size_t)(ny + 2);
-  const size_t e = i + NXG * j;
+  const IX NXG = nx + 2, NE = NXG * (IX)(ny + 2);
+  const IX e = i + NXG * j;
   const double gm1 = gamma - 1.0;
-  const size_t i1 = (size_t)(i - 1) + (size_t)(nx + 1) * (j - 1), s1 = (size_t)(nx + 1) * ny;
-  const size_t i2 = (size_t)(i - 1) + (size_t)nx * (j - 1), s2 = (size_t)nx * (ny + 1);
-  const size_t ifp = (size_t)(i - 1) + (size_t)nx * (j - 1), sfp = (size_t)nx * ny;
+  const IX i1 = (IX)(i - 1) + (IX)(nx + 1) * (j - 1), s1 = (IX)(nx + 1) * ny;
+  const IX i2 = (IX)(i - 1) + (IX)nx * (j - 1), s2 = (IX)nx * (ny + 1);
+  const IX ifp = (IX)(i - 1) + (IX)nx * (j - 1), sfp = (IX)nx * ny;
 
   // ---- loads
   double a[NSP][4], FxL[4], FxR[4], FyB[4], FyT[4], cxL[NSP], cxR[NSP];
@@ -265,22 +300,40 @@ FRB_HD void row_xpass(int i, int j, int l, const double *__restrict__ u, const d
       tile[(size_t)(((l * NSP + k) * 4) + m) * ts] = fma(a[k][3], G[m], a[k][1] * F[m]);
     }
   }
-#pragma unroll
-  for (int m = 0; m < 4; ++m) {
-    double t4 = 0, t2 = 0;  // f_face[i,j,4,l,m,1], f_face[i,j,2,l,m,1]
-#pragma unroll
-    for (int q = 0; q < NSP; ++q) {
-      t4 = fma(f1[q][m], ops.ll[q], t4);
-      t2 = fma(f1[q][m], ops.lr[q], t2);
-    }
+  if (FOLD) {
 #pragma unroll
     for (int k = 0; k < NSP; ++k) {
-      double d = f1[0][m] * ops.lpdm[k * FRB_NSPMAX];
+      cxL[k] *= ops.dgl[k];
+      cxR[k] *= ops.dgr[k];
+    }
+  }
 #pragma unroll
-      for (int q = 1; q < NSP; ++q) d = fma(f1[q][m], ops.lpdm[k * FRB_NSPMAX + q], d);
-      d += (cxL[k] * FxL[m] - t4) * ops.dgl[k];
-      d += (cxR[k] * FxR[m] - t2) * ops.dgr[k];
-      c.d[k][m] = d;
+  for (int m = 0; m < 4; ++m) {
+    if (FOLD) {
+#pragma unroll
+      for (int k = 0; k < NSP; ++k) {
+        double d = f1[0][m] * ops.dmod[k * FRB_NSPMAX];
+#pragma unroll
+        for (int q = 1; q < NSP; ++q) d = fma(f1[q][m], ops.dmod[k * FRB_NSPMAX + q], d);
+        d = fma(cxL[k], FxL[m], d);
+        c.d[k][m] = fma(cxR[k], FxR[m], d);
+      }
+    } else {
+      double t4 = 0, t2 = 0;  // f_face[i,j,4,l,m,1], f_face[i,j,2,l,m,1]
+#pragma unroll
+      for (int q = 0; q < NSP; ++q) {
+        t4 = fma(f1[q][m], ops.ll[q], t4);
+        t2 = fma(f1[q][m], ops.lr[q], t2);
+      }
+#pragma unroll
+      for (int k = 0; k < NSP; ++k) {
+        double d = f1[0][m] * ops.lpdm[k * FRB_NSPMAX];
+#pragma unroll
+        for (int q = 1; q < NSP; ++q) d = fma(f1[q][m], ops.lpdm[k * FRB_NSPMAX + q], d);
+        d += (cxL[k] * FxL[m] - t4) * ops.dgl[k];
+        d += (cxR[k] * FxR[m] - t2) * ops.dgr[k];
+        c.d[k][m] = d;
+      }
     }
     fyt[(size_t)(((0 * NSP + l) * 4) + m) * ts] = FyB[m];
     fyt[(size_t)(((1 * NSP + l) * 4) + m) * ts] = FyT[m];
@@ -291,12 +344,12 @@ FRB_HD void row_xpass(int i, int j, int l, const double *__restrict__ u, const d
 // s-derivative (:143-149), y-face corrections (:158-163; the common flux indexed by k, or by l in the scripts'
 // literal form) and the stage update out = ca u_n + cb u + cdt L(u) (the launcher maps rhs_only onto
 // ca = cb = 0, cdt = 1, so there is no branch here; u_n is fetched first, as one batch).
-template <int NSP>
+template <int NSP, typename IX = size_t, bool FOLD = false>
 FRB_HD void row_ypass(int i, int j, int l, const double *__restrict__ ua, double *__restrict__ out,
                       const CurvGeom &g, const FrbOps &ops, const FrbStage &st, const double *__restrict__ tile,
                       const double *__restrict__ fyt, int ts, const RowCarry<NSP> &c) {
-  const size_t NXG = g.nx + 2, NE = NXG * (size_t)(g.ny + 2);
-  const size_t e = i + NXG * j;
+  const IX NXG = g.nx + 2, NE = NXG * (IX)(g.ny + 2);
+  const IX e = i + NXG * j;
   double un[NSP][4];
 #pragma unroll
   for (int k = 0; k < NSP; ++k)
@@ -305,21 +358,31 @@ FRB_HD void row_ypass(int i, int j, int l, const double *__restrict__ ua, double
 #pragma unroll
   for (int k = 0; k < NSP; ++k) {
     const int yi = g.fy_row ? l : k;
+    const double gyL = c.cyL[k] * ops.dgl[l], gyR = c.cyR[k] * ops.dgr[l];  // FOLD
 #pragma unroll
     for (int m = 0; m < 4; ++m) {
-      double b = 0, t1 = 0, t3 = 0;  // rhs2, f_face[i,j,1,k,m,2], f_face[i,j,3,k,m,2]
-#pragma unroll
-      for (int q = 0; q < NSP; ++q) {
-        const double f2 = tile[(size_t)(((q * NSP + k) * 4) + m) * ts];
-        b = fma(f2, ops.lpdm[l * FRB_NSPMAX + q], b);
-        t1 = fma(f2, ops.ll[q], t1);
-        t3 = fma(f2, ops.lr[q], t3);
-      }
       const double FyB = fyt[(size_t)(((0 * NSP + yi) * 4) + m) * ts];
       const double FyT = fyt[(size_t)(((1 * NSP + yi) * 4) + m) * ts];
-      double d = c.d[k][m] + b;
-      d += (c.cyL[k] * FyB - t1) * ops.dgl[l];
-      d += (c.cyR[k] * FyT - t3) * ops.dgr[l];
+      double d = c.d[k][m];
+      if (FOLD) {
+#pragma unroll
+        for (int q = 0; q < NSP; ++q)
+          d = fma(tile[(size_t)(((q * NSP + k) * 4) + m) * ts], ops.dmod[l * FRB_NSPMAX + q], d);
+        d = fma(gyL, FyB, d);
+        d = fma(gyR, FyT, d);
+      } else {
+        double b = 0, t1 = 0, t3 = 0;  // rhs2, f_face[i,j,1,k,m,2], f_face[i,j,3,k,m,2]
+#pragma unroll
+        for (int q = 0; q < NSP; ++q) {
+          const double f2 = tile[(size_t)(((q * NSP + k) * 4) + m) * ts];
+          b = fma(f2, ops.lpdm[l * FRB_NSPMAX + q], b);
+          t1 = fma(f2, ops.ll[q], t1);
+          t3 = fma(f2, ops.lr[q], t3);
+        }
+        d += b;
+        d += (c.cyL[k] * FyB - t1) * ops.dgl[l];
+        d += (c.cyR[k] * FyT - t3) * ops.dgr[l];
+      }
       d = -d;
       out[e + NE * plane<NSP>(k, l, m)] = fma(st.ca, un[k][m], fma(st.cdt, d, st.cb * c.w[k][m]));
     }

@@ -32,7 +32,7 @@ from ._lib import Context, check, fortran_ptr, lib, make_operators
 
 BC = {"dirichlet": 0, "period": 1}
 GHOST = {None: -1, "none": -1, "wave_x": 0, "wave_y": 1, "copy": 2, "periodic": 3, "cylinder": 4}
-KERNEL = {"auto": 0, "generic": 1, "march": 2, "rc": 3, "one_pass": 4}
+KERNEL = {"auto": 0, "generic": 1, "march": 2, "rc": 3, "one_pass": 4, "curv_march": 5}
 FLUX = {"hll": 0, "lf": 1, "roe": 2}
 
 

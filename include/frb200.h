@@ -60,7 +60,11 @@ enum { FRB_ADV_PACKAGED = 0, FRB_ADV_LOWLEVEL = 1 };
  * reference-image marching kernel for f! with host buffers (deg 2-3), the generic per-element kernel otherwise */
 enum { FRB_KERNEL_AUTO = 0, FRB_KERNEL_GENERIC = 1, FRB_KERNEL_MARCH = 2, FRB_KERNEL_RC = 3,
        /* bgk1d problems only: the one-pass register-tile kernel instead of the two launches (same results) */
-       FRB_KERNEL_BGK_ONE_PASS = 4 };
+       FRB_KERNEL_BGK_ONE_PASS = 4,
+       /* curvilinear euler2d problems only: one row-marching launch per stage (state and metric read once, the
+        * common fluxes never leave the SM) instead of face kernel + element kernel (same results; stored metric,
+        * arrays below 2^32 elements) */
+       FRB_KERNEL_CURV_MARCH = 5 };
 
 /* common (Riemann) flux of the Euler problems.  HLL is what the reference calls (flux_hll!,
  * eq_euler.jl:53, euler2d_wave.jl:73,80) and what the marching kernels implement; LF (Rusanov)

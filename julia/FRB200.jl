@@ -243,7 +243,7 @@ end
 
 # ---- measurement ----------------------------------------------------------------------------------------------
 set_kernel!(p::Problem, kind::Symbol) = check(ccall((:frb_set_kernel, lib), Int32, (Ptr{Cvoid}, Int32), p.h,
-    Int32(Dict(:auto => 0, :generic => 1, :march => 2, :rc => 3, :one_pass => 4)[kind])))
+    Int32(Dict(:auto => 0, :generic => 1, :march => 2, :rc => 3, :one_pass => 4, :curv_march => 5)[kind])))
 function time_stage(p::Problem, stage_kind::Integer = 1, iters::Integer = 10)   # ms per fused stage launch
     ms = Ref{Float32}(0)
     check(ccall((:frb_time_stage, lib), Int32, (Ptr{Cvoid}, Int32, Int32, Ref{Float32}), p.h, stage_kind, iters, ms)); ms[]

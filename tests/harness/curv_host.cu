@@ -6,12 +6,14 @@
 
 #include "../../fluxreconstruction.jl_b200/csrc/frb_euler2d_curv_elem.cuh"
 
-template <int NSP>
+// IX / FOLD: the instantiation the kernels launch (unsigned indices, folded operators) or the literal one
+template <int NSP, typename IX, bool FOLD>
 static void run(const double *u, const double *ua, double *out, double *fx, double *fy, const CurvGeom &g,
                 double gamma, const FrbOps &ops, const FrbStage &st) {
   for (int j = 1; j <= g.ny + 1; ++j)
     for (int i = 1; i <= g.nx + 1; ++i)
-      for (int p = 0; p < NSP; ++p) frbcurv::face_xy<NSP>(i, j, p, j <= g.ny, i <= g.nx, u, fx, fy, g, gamma, ops);
+      for (int p = 0; p < NSP; ++p)
+        frbcurv::face_xy<NSP, IX>(i, j, p, j <= g.ny, i <= g.nx, u, fx, fy, g, gamma, ops);
   double tile[NSP * NSP * 4], fyt[2 * NSP * 4];
   FrbStage sk = st;  // the launcher's mapping of rhs_only (frb_launch_euler2d_curv)
   if (sk.rhs_only) { sk.ca = 0.0; sk.cb = 0.0; sk.cdt = 1.0; sk.use_a = 0; }
@@ -19,8 +21,10 @@ static void run(const double *u, const double *ua, double *out, double *fx, doub
   frbcurv::RowCarry<NSP> c[NSP];
   for (int j = 1; j <= g.ny; ++j)
     for (int i = 1; i <= g.nx; ++i) {  // the block barrier of the kernel = the boundary between the two loops
-      for (int l = 0; l < NSP; ++l) frbcurv::row_xpass<NSP>(i, j, l, u, fx, fy, g, gamma, ops, tile, fyt, 1, c[l]);
-      for (int l = 0; l < NSP; ++l) frbcurv::row_ypass<NSP>(i, j, l, ua, out, g, ops, sk, tile, fyt, 1, c[l]);
+      for (int l = 0; l < NSP; ++l)
+        frbcurv::row_xpass<NSP, IX, FOLD>(i, j, l, u, fx, fy, g, gamma, ops, tile, fyt, 1, c[l]);
+      for (int l = 0; l < NSP; ++l)
+        frbcurv::row_ypass<NSP, IX, FOLD>(i, j, l, ua, out, g, ops, sk, tile, fyt, 1, c[l]);
     }
 }
 
@@ -36,6 +40,9 @@ extern "C" int curv_host_stage(int nx, int ny, int nsp, const double *u, const d
     ops.ll[q] = ll[q]; ops.lr[q] = lr[q]; ops.dgl[q] = dgl[q]; ops.dgr[q] = dgr[q];
     for (int k = 0; k < nsp; ++k) ops.lpdm[q * FRB_NSPMAX + k] = lpdm[q + nsp * k];
   }
+  for (int k = 0; k < nsp; ++k)  // as make_operators of frb_api.cu
+    for (int q = 0; q < nsp; ++q)
+      ops.dmod[k * FRB_NSPMAX + q] = ops.lpdm[k * FRB_NSPMAX + q] - dgl[k] * ll[q] - dgr[k] * lr[q];
   CurvGeom g;
   g.nx = nx; g.ny = ny; g.iJ = iJ; g.n1 = n1; g.n2 = n2; g.fpc = fpc; g.vert = vert;
   for (int q = 0; q < FRB_NSPMAX; ++q) g.r[q] = (r && q < nsp) ? r[q] : 0.0;
@@ -43,10 +50,14 @@ extern "C" int curv_host_stage(int nx, int ny, int nsp, const double *u, const d
   g.wall_xlo = (flags & FRB_CURV_WALL_XLO) ? 1 : 0;
   g.flux = (flags >> 8) & 3;  // test-only: the flux kind rides in bits 8..9
   FrbStage st = {ca, cb, cdt, use_a, rhs_only, 0};
-  switch (nsp) {
-    case 2: run<2>(u, ua, out, fx, fy, g, gamma, ops, st); break;
-    case 3: run<3>(u, ua, out, fx, fy, g, gamma, ops, st); break;
-    case 4: run<4>(u, ua, out, fx, fy, g, gamma, ops, st); break;
+  const bool fast = (flags >> 10) & 1;  // test-only: the kernels' instantiation
+  switch (nsp * 2 + fast) {
+    case 4: run<2, size_t, false>(u, ua, out, fx, fy, g, gamma, ops, st); break;
+    case 6: run<3, size_t, false>(u, ua, out, fx, fy, g, gamma, ops, st); break;
+    case 8: run<4, size_t, false>(u, ua, out, fx, fy, g, gamma, ops, st); break;
+    case 5: run<2, unsigned, true>(u, ua, out, fx, fy, g, gamma, ops, st); break;
+    case 7: run<3, unsigned, true>(u, ua, out, fx, fy, g, gamma, ops, st); break;
+    case 9: run<4, unsigned, true>(u, ua, out, fx, fy, g, gamma, ops, st); break;
     default: return -1;
   }
   return 0;

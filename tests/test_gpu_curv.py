@@ -44,13 +44,18 @@ def cylinder(FR, nr, nth, deg):
     return ps, po, (n1[:nr], n2[: nr - 1])
 
 
+KERNELS = ["auto", "curv_march"]  # auto: face kernel + element kernel; curv_march: the one-launch marching kernel
+
+
+@pytest.mark.parametrize("kernel", KERNELS)
 @pytest.mark.parametrize("deg", [1, 2, 3])
 @pytest.mark.parametrize("fy", ["k", "l"])
-@pytest.mark.parametrize("nx,ny", [(30, 15), (33, 7), (1, 1)])
-def test_parallelogram_rhs(FR, deg, fy, nx, ny):
+@pytest.mark.parametrize("nx,ny", [(30, 15), (33, 7), (1, 1), (31, 2), (61, 3)])
+def test_parallelogram_rhs(FR, deg, fy, nx, ny, kernel):
     ps, po, (n1, n2) = parallelogram(FR, nx, ny, deg)
     u = rand_state((nx + 2, ny + 2, deg + 1, deg + 1), 11)
     prob = FR.Euler2DCurvProblem(u, (0.0, 1.0), ps, GAMMA, n1, n2, corr="sp", fy_index=fy)
+    prob.set_kernel(kernel)
     du = np.full_like(u, np.nan, order="F")
     prob.f(du, u, None, 0.0)
     ref = c.rhs_euler2d_curv(u, po, n1, n2, GAMMA, corr="sp", fy_index=fy)
@@ -59,15 +64,17 @@ def test_parallelogram_rhs(FR, deg, fy, nx, ny):
     prob.close()
 
 
+@pytest.mark.parametrize("kernel", KERNELS)
 @pytest.mark.parametrize("deg", [1, 2, 3])
 @pytest.mark.parametrize("fy", ["k", "l"])
-def test_cylinder_rhs(FR, deg, fy):
+def test_cylinder_rhs(FR, deg, fy, kernel):
     """dev/cylinder2.jl:52-164: flux-point factors from the literal Ji, mirror wall on the inner face."""
     nr, nth = 30, 40
     ps, po, (n1, n2) = cylinder(FR, nr, nth, deg)
     u = rand_state((nr + 1, nth + 2, deg + 1, deg + 1), 12)
     u[0] = np.nan  # the dummy column behind the wall is never read
     prob = FR.Euler2DCurvProblem(u, (0.0, 1.0), ps, GAMMA, None, None, corr="fp", fy_index=fy, wall_xlo=True)
+    prob.set_kernel(kernel)
     du = np.zeros_like(u, order="F")
     prob.f(du, u, None, 0.0)
     u0 = u.copy()
@@ -78,12 +85,14 @@ def test_cylinder_rhs(FR, deg, fy):
     prob.close()
 
 
+@pytest.mark.parametrize("kernel", KERNELS)
 @pytest.mark.parametrize("flux", ["lf", "roe"])
-def test_extra_fluxes_in_the_face_frame(FR, flux):
+def test_extra_fluxes_in_the_face_frame(FR, flux, kernel):
     nr, nth, deg = 12, 16, 2
     ps, po, (n1, n2) = cylinder(FR, nr, nth, deg)
     u = rand_state((nr + 1, nth + 2, deg + 1, deg + 1), 18)
     prob = FR.Euler2DCurvProblem(u, (0.0, 1.0), ps, GAMMA, corr="fp", fy_index="k", wall_xlo=True)
+    prob.set_kernel(kernel)
     prob.set_flux(flux)
     du = np.zeros_like(u, order="F")
     prob.f(du, u, None, 0.0)
@@ -111,6 +120,34 @@ def test_metric_from_vertices(FR, deg):
         prob.f(du2, u, None, 0.0)
         assert rel(du2, ref) <= RTOL_RHS
         prob.close()
+
+
+@pytest.mark.parametrize("rows", [1, 2, 4, 5, 37, 1000])
+@pytest.mark.parametrize("deg", [1, 2, 3])
+def test_marching_kernel_segment_lengths(FR, deg, rows, monkeypatch):
+    """The one-launch kernel with every split of the rows into segments (FRB_CURV_ROWS), several strips, a ragged
+    last strip and a ragged last segment: the residual and three SSPRK3 steps against the two-kernel form."""
+    nx, ny = 95, 37
+    ps, po, (n1, n2) = parallelogram(FR, nx, ny, deg)
+    u = rand_state((nx + 2, ny + 2, deg + 1, deg + 1), 21)
+    ref = c.rhs_euler2d_curv(u, po, n1, n2, GAMMA, corr="sp", fy_index="k")
+    monkeypatch.setenv("FRB_CURV_ROWS", str(rows))
+    got = {}
+    for kernel in KERNELS:
+        prob = FR.Euler2DCurvProblem(u, (0.0, 1.0), ps, GAMMA, n1, n2, corr="sp", fy_index="k")
+        prob.set_kernel(kernel)
+        du = np.full_like(u, np.nan, order="F")
+        prob.f(du, u, None, 0.0)
+        assert rel(du, ref) <= RTOL_RHS, kernel
+        _, n = prob.last_timing()
+        assert n == (2 if kernel == "auto" else 1)
+        itg = FR.init(prob, FR.SSPRK33(), dt=2e-4)
+        itg.set_hooks(ghost="periodic")
+        FR.step_(itg, 3)
+        got[kernel] = itg.u.copy()
+        prob.close()
+    assert np.isfinite(got["curv_march"]).all()
+    assert rel(got["curv_march"], got["auto"]) <= 1e-13
 
 
 def test_rectangular_mesh_equals_the_rectangular_problem(FR):
@@ -237,11 +274,17 @@ def test_unsupported_combinations_fail_loudly(FR):
     prob = FR.Euler2DCurvProblem(u, (0.0, 1.0), ps, GAMMA, n1, n2)
     with pytest.raises(FR.FRBError):
         prob.set_kernel("march")
+    prob.set_kernel("curv_march")
+    prob.set_metric("vertices")  # the marching kernel reads the stored metric only
+    with pytest.raises(FR.FRBError):
+        prob.f(np.zeros_like(u, order="F"), u, None, 0.0)
     prob.close()
     pr = FR.FRPSpace2D(0.0, 1.0, nx, 0.0, 1.0, ny, deg, 1, 1)
     p2 = FR.Euler2DProblem(u, (0.0, 1.0), pr, GAMMA)
     with pytest.raises(FR.FRBError):
         p2.set_hooks(ghost="cylinder")
+    with pytest.raises(FR.FRBError):
+        p2.set_kernel("curv_march")
     p2.close()
 
 
@@ -265,6 +308,11 @@ def test_large_mesh(FR):
     assert rel(du, ref) <= 1e-9
     ms, n = prob.last_timing()
     assert n == 2  # face kernel + element kernel
+    prob.set_kernel("curv_march")
+    du2 = np.zeros_like(u, order="F")
+    prob.f(du2, u, None, 0.0)
+    assert np.abs(du2 - ref).max() <= RTOL_RHS * terms
+    assert prob.last_timing()[1] == 1  # one marching launch
     prob.close()
 
 

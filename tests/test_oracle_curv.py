@@ -262,16 +262,20 @@ def host_stage():
     return run
 
 
+@pytest.mark.parametrize("fast", [0, 1 << 10])
 @pytest.mark.parametrize("deg", [1, 2, 3])
-def test_device_routines_on_the_cpu(host_stage, deg):
-    """face_x / face_y / element_var of csrc/frb_euler2d_curv_elem.cuh, the code the kernels run."""
+def test_device_routines_on_the_cpu(host_stage, deg, fast):
+    """face_xy / row_xpass / row_ypass of csrc/frb_euler2d_curv_elem.cuh, the code the kernels run: the literal
+    instantiation (size_t indices, the correction written as in the scripts) and the one the kernels launch
+    (fast: 32-bit indices, the flux traces folded into the derivative matrix -- rounding differs in the last bits)."""
+    tol = 1e-13 if fast else 1e-14
     nx, ny = 7, 5
     ps = c.CurvSpace2D(c.parallelogram_vertices(nx, ny), deg)
     n1, n2 = c.parallelogram_normals(nx, ny)
     u = rand_state((nx + 2, ny + 2, deg + 1, deg + 1), 5)
     for fy, flags in (("l", 1), ("k", 0)):
         ref = c.rhs_euler2d_curv(u, ps, n1, n2, GAMMA, corr="sp", fy_index=fy)
-        assert rel(host_stage(u, ps, n1, n2, None, flags), ref) < 1e-14
+        assert rel(host_stage(u, ps, n1, n2, None, flags | fast), ref) < tol
     nr, nth = 6, 8
     vv, dth = c.cspace2d_vertices(1.0, 6.0, nr, 0.0, np.pi, nth, 0, 1)
     ps = c.CurvSpace2D(c.embed_cylinder(vv), deg)
@@ -281,17 +285,17 @@ def test_device_routines_on_the_cpu(host_stage, deg):
     u = rand_state((nr + 1, nth + 2, deg + 1, deg + 1), 6)
     for fy, flags in (("l", 3), ("k", 2)):
         ref = c.rhs_euler2d_curv(u, ps, n1, n2, GAMMA, corr="fp", fpc=fpc, fy_index=fy, wall_xlo=True)
-        assert rel(host_stage(u, ps, n1, n2, fpc, flags), ref) < 1e-14
+        assert rel(host_stage(u, ps, n1, n2, fpc, flags | fast), ref) < tol
     # the metric evaluated from the vertices on the fly (frb_euler2d_curv_set_vertices) instead of the stored iJ
     ref = c.rhs_euler2d_curv(u, ps, n1, n2, GAMMA, corr="fp", fpc=fpc, fy_index="k", wall_xlo=True)
-    assert rel(host_stage(u, ps, n1, n2, fpc, 2, vertices=True), ref) < 1e-13
+    assert rel(host_stage(u, ps, n1, n2, fpc, 2 | fast, vertices=True), ref) < 1e-13
     for kind, name in ((1, "lf"), (2, "roe")):  # the extra common fluxes, in the face frame
         ref = c.rhs_euler2d_curv(u, ps, n1, n2, GAMMA, corr="fp", fpc=fpc, fy_index="k", wall_xlo=True, flux=name)
-        assert rel(host_stage(u, ps, n1, n2, fpc, 2 | (kind << 8)), ref) < 1e-13
+        assert rel(host_stage(u, ps, n1, n2, fpc, 2 | (kind << 8) | fast), ref) < 1e-13
     ua = rand_state(u.shape[:-1], 7)
     ref = 0.75 * ua + 0.25 * u + 0.25e-3 * c.rhs_euler2d_curv(u, ps, n1, n2, GAMMA, corr="fp", fpc=fpc, fy_index="k",
                                                                wall_xlo=True)
-    got = host_stage(u, ps, n1, n2, fpc, 2, stage=(0.75, 0.25, 0.25e-3, 1, 0), ua=ua)
+    got = host_stage(u, ps, n1, n2, fpc, 2 | fast, stage=(0.75, 0.25, 0.25e-3, 1, 0), ua=ua)
     assert np.abs(got[1:-1, 1:-1] - ref[1:-1, 1:-1]).max() < 1e-14
 
 
