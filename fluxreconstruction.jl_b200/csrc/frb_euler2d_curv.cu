@@ -121,6 +121,10 @@ int frb_launch_euler2d_curv(frb_prob_t p, const double *u, const double *ua, dou
       return FRB_ERR_STATE;
     }
   }
+  // default: one launch per stage, every block evaluates the fluxes of its own faces (frb_euler2d_curv_fused.cu);
+  // FRB_KERNEL_GENERIC (or FRB_CURV_TWO_KERNELS=1, read per launch) and the vertex metric take the two launches below
+  if (p->kernel_kind != FRB_KERNEL_GENERIC && !g.vert && getenv("FRB_CURV_TWO_KERNELS") == nullptr && p->ny <= 65535)
+    return frb_launch_euler2d_curv_fused(p, u, ua, out, g, st);
   const size_t nfx = (size_t)(p->nx + 1) * p->ny * p->nsp * 4, nfy = (size_t)p->nx * (p->ny + 1) * p->nsp * 4;
   if (!p->curv_flux) FRB_CUDA(cudaMalloc(&p->curv_flux, sizeof(double) * (nfx + nfy)));
   double *fx = p->curv_flux, *fy = p->curv_flux + nfx;

@@ -51,6 +51,8 @@ struct CurvGeom {
 
 int frb_launch_euler2d_curv_march(frb_prob_t p, const double *u, const double *ua, double *out, const CurvGeom &g,
                                   const FrbStage &st);
+int frb_launch_euler2d_curv_fused(frb_prob_t p, const double *u, const double *ua, double *out, const CurvGeom &g,
+                                  const FrbStage &st);
 
 namespace frbcurv {
 

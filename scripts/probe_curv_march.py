@@ -31,10 +31,10 @@ def main():
     prob = FR.Euler2DCurvProblem(u, (0.0, 1.0), ps, g, corr="sp", metric="stored")
     dofs = prob.dofs
     rows = [int(r) for r in os.environ.get("PROBE_ROWS", "0,16,32,43,64,86,128,256").split(",")]
-    variants = [("two kernels", {}), ("two kernels, 64-bit indices", {"FRB_CURV_IX64": "1"})] + [
+    variants = [("one launch (default)", {}), ("two kernels", {"FRB_CURV_TWO_KERNELS": "1"})] + [
         (f"march rows={r or 'auto'}", {"FRB_CURV_MARCH": "1"} | ({"FRB_CURV_ROWS": str(r)} if r else {})) for r in rows]
     for name, env in variants:
-        for k in ("FRB_CURV_MARCH", "FRB_CURV_ROWS", "FRB_CURV_IX64"):
+        for k in ("FRB_CURV_MARCH", "FRB_CURV_ROWS", "FRB_CURV_TWO_KERNELS"):
             os.environ.pop(k, None)
         os.environ.update(env)
         for kind, state_bytes in ((0, 16), (1, 24)):

@@ -44,7 +44,9 @@ def cylinder(FR, nr, nth, deg):
     return ps, po, (n1[:nr], n2[: nr - 1])
 
 
-KERNELS = ["auto", "curv_march"]  # auto: face kernel + element kernel; curv_march: the one-launch marching kernel
+# auto: one launch, every block evaluates the fluxes of its own faces; generic: face kernel + element kernel;
+# curv_march: the one-launch row-marching kernel
+KERNELS = ["auto", "generic", "curv_march"]
 
 
 @pytest.mark.parametrize("kernel", KERNELS)
@@ -140,14 +142,15 @@ def test_marching_kernel_segment_lengths(FR, deg, rows, monkeypatch):
         prob.f(du, u, None, 0.0)
         assert rel(du, ref) <= RTOL_RHS, kernel
         _, n = prob.last_timing()
-        assert n == (2 if kernel == "auto" else 1)
+        assert n == (2 if kernel == "generic" else 1)
         itg = FR.init(prob, FR.SSPRK33(), dt=2e-4)
         itg.set_hooks(ghost="periodic")
         FR.step_(itg, 3)
         got[kernel] = itg.u.copy()
         prob.close()
-    assert np.isfinite(got["curv_march"]).all()
-    assert rel(got["curv_march"], got["auto"]) <= 1e-13
+    for kernel in KERNELS[1:]:
+        assert np.isfinite(got[kernel]).all()
+        assert rel(got[kernel], got["auto"]) <= 1e-13
 
 
 def test_rectangular_mesh_equals_the_rectangular_problem(FR):
@@ -307,12 +310,13 @@ def test_large_mesh(FR):
     assert np.abs(du - ref).max() <= RTOL_RHS * terms
     assert rel(du, ref) <= 1e-9
     ms, n = prob.last_timing()
-    assert n == 2  # face kernel + element kernel
-    prob.set_kernel("curv_march")
-    du2 = np.zeros_like(u, order="F")
-    prob.f(du2, u, None, 0.0)
-    assert np.abs(du2 - ref).max() <= RTOL_RHS * terms
-    assert prob.last_timing()[1] == 1  # one marching launch
+    assert n == 1  # one launch
+    for kernel, launches in (("generic", 2), ("curv_march", 1)):
+        prob.set_kernel(kernel)
+        du2 = np.zeros_like(u, order="F")
+        prob.f(du2, u, None, 0.0)
+        assert np.abs(du2 - ref).max() <= RTOL_RHS * terms, kernel
+        assert prob.last_timing()[1] == launches
     prob.close()
 
 
