@@ -5,7 +5,9 @@
 //            later), so the state crosses DRAM about once; both y fluxes of the element -> fyt
 //   x faces  the row's traces are in the row owner's registers, the neighbours' come by __shfl (lanes 0 / 31 are
 //            the duplicate edge lanes of the rectangular row-chunk kernel)
-// then the x pass / y pass of the element kernel (frbcurv::row_ypass is called as is).  Against the two-kernel
+// then the x pass / y pass of the element kernel.  The column owners leave the block's own row in a shared-memory
+// tile, so the row owners do not load it a second time, and every global load of the block (metric, normals, the
+// three rows) is issued before the first use: one exposed DRAM latency per block.  Against the two-kernel
 // form (frb_euler2d_curv.cu: 2.71 GB of DRAM traffic per 16-B stage at 1024^2 p3) the common fluxes never leave
 // the SM and the state is read from DRAM once (1.6 GB algorithmic); every y face is evaluated by both rows that
 // share it, which costs about what the face kernel's second pass over the state cost in instructions.  Against
@@ -26,8 +28,10 @@ euler2d_curv_fused_kernel(const double *__restrict__ u, const double *__restrict
                           CurvGeom g, double gamma, FrbOps ops, FrbStage st) {
   using frbcurv::plane;
   using frbcurv::W4;
-  __shared__ double tile[NSP * NSP * 4 * 32];  // f2 of the block's elements, [l][k][m][lane]
-  __shared__ double fyt[2 * NSP * 4 * 32];     // y common fluxes below / above them, [side][p][m][lane]
+  // the block's row of elements, [plane(k, l, m)][lane]: first the state (written by the column owners, read by the
+  // row owners), then f2 (every row owner overwrites the values it has just read)
+  __shared__ double tile[NSP * NSP * 4 * 32];
+  __shared__ double fyt[2 * NSP * 4 * 32];  // y common fluxes below / above the elements, [side][p][m][lane]
   const int lane = threadIdx.x, l = threadIdx.y;
   const int nx = g.nx, ny = g.ny;
   const IX NXG = nx + 2, NE = NXG * (IX)(ny + 2);
@@ -41,9 +45,18 @@ euler2d_curv_fused_kernel(const double *__restrict__ u, const double *__restrict
   const IX s1 = (IX)(nx + 1) * ny, s2 = (IX)nx * (ny + 1), sfp = (IX)nx * ny;
   const IX i1 = ifx + (IX)(nx + 1) * (j - 1), i2 = ify + (IX)nx * (j - 1);
   const double gm1 = gamma - 1.0;
+  double *T = tile + lane;
+
+  // ---- every global load of the x pass and of the y faces first: one exposed DRAM latency per block
+  double a[NSP][4];  // the metric of point row l: a11, a21, a12, a22
+#pragma unroll
+  for (int k = 0; k < NSP; ++k)
+#pragma unroll
+    for (int m = 0; m < 4; ++m) a[k][m] = owned ? g.iJ[e + NE * plane<NSP>(k, l, m)] : 0.0;
+  const double n1c = g.n1[i1], n1s = g.n1[i1 + s1];
+  const double nbc = g.n2[i2], nbs = g.n2[i2 + s2], ntc = g.n2[i2 + nx], nts = g.n2[i2 + nx + s2];
 
   // ---- y faces j (below) and j+1 (above) at flux point p = l
-  const double nbc = g.n2[i2], nbs = g.n2[i2 + s2], ntc = g.n2[i2 + nx], nts = g.n2[i2 + nx + s2];
   {
     double vm[NSP][4], v0[NSP][4], vp[NSP][4];
 #pragma unroll
@@ -58,15 +71,16 @@ euler2d_curv_fused_kernel(const double *__restrict__ u, const double *__restrict
     double tm[4], b0[4], t0[4], bp[4];
 #pragma unroll
     for (int m = 0; m < 4; ++m) {
-      double a = 0, b = 0, c = 0, d = 0;  // the summation order of load_trace_y
+      double x = 0, b = 0, c = 0, d = 0;  // the summation order of load_trace_y
 #pragma unroll
       for (int q = 0; q < NSP; ++q) {
-        a = fma(vm[q][m], ops.lr[q], a);
+        T[plane<NSP>(l, q, m) * 32] = v0[q][m];  // point (k = l, row q) of the element
+        x = fma(vm[q][m], ops.lr[q], x);
         b = fma(v0[q][m], ops.ll[q], b);
         c = fma(v0[q][m], ops.lr[q], c);
         d = fma(vp[q][m], ops.ll[q], d);
       }
-      tm[m] = a; b0[m] = b; t0[m] = c; bp[m] = d;
+      tm[m] = x; b0[m] = b; t0[m] = c; bp[m] = d;
     }
     const W4 hb = frbcurv::flux_normal_t<FLUX>(g.flux, {tm[0], tm[1], tm[2], tm[3]}, {b0[0], b0[1], b0[2], b0[3]},
                                                nbc, nbs, gamma, 0);
@@ -78,20 +92,17 @@ euler2d_curv_fused_kernel(const double *__restrict__ u, const double *__restrict
     F[((1 * NSP + l) * 4 + 0) * 32] = ht.a; F[((1 * NSP + l) * 4 + 1) * 32] = ht.b;
     F[((1 * NSP + l) * 4 + 2) * 32] = ht.c; F[((1 * NSP + l) * 4 + 3) * 32] = ht.d;
   }
+  __syncthreads();  // the row of elements is in the tile
 
   // ---- x pass of point row l (the formulas of frbcurv::row_xpass, FOLD form), every lane: the edge lanes supply
   // traces and the flux of their left face
-  frbcurv::RowCarry<NSP> c;
+  double d[NSP][4], w[NSP][4], un[NSP][4], gyL[NSP], gyR[NSP];
   {
-    double a[NSP][4], cxL[NSP], cxR[NSP];
+    double cxL[NSP], cxR[NSP];
 #pragma unroll
     for (int k = 0; k < NSP; ++k)
 #pragma unroll
-      for (int m = 0; m < 4; ++m) {
-        c.w[k][m] = u[e + NE * plane<NSP>(k, l, m)];
-        a[k][m] = owned ? g.iJ[e + NE * plane<NSP>(k, l, m)] : 0.0;  // a11, a21, a12, a22
-      }
-    const double n1c = g.n1[i1], n1s = g.n1[i1 + s1];
+      for (int m = 0; m < 4; ++m) w[k][m] = T[plane<NSP>(k, l, m) * 32];
     if (g.fpc) {  // cylinder2.jl:155-158
       const IX ifp = (IX)(owned ? i - 1 : 0) + (IX)nx * (j - 1);
       const double xl = g.fpc[ifp + sfp * (l + NSP * 0)], xr = g.fpc[ifp + sfp * (l + NSP * 1)];
@@ -99,8 +110,8 @@ euler2d_curv_fused_kernel(const double *__restrict__ u, const double *__restrict
       for (int k = 0; k < NSP; ++k) {
         cxL[k] = xl * ops.dgl[k];
         cxR[k] = xr * ops.dgr[k];
-        c.cyL[k] = g.fpc[ifp + sfp * (k + NSP * 2)];
-        c.cyR[k] = g.fpc[ifp + sfp * (k + NSP * 3)];
+        gyL[k] = g.fpc[ifp + sfp * (k + NSP * 2)] * ops.dgl[l];
+        gyR[k] = g.fpc[ifp + sfp * (k + NSP * 3)] * ops.dgr[l];
       }
     } else {  // parallelogram.jl:145-148
       const double nrc = __shfl_down_sync(0xffffffffu, n1c, 1), nrs = __shfl_down_sync(0xffffffffu, n1s, 1);
@@ -108,8 +119,8 @@ euler2d_curv_fused_kernel(const double *__restrict__ u, const double *__restrict
       for (int k = 0; k < NSP; ++k) {
         cxL[k] = fma(a[k][2], n1s, a[k][0] * n1c) * ops.dgl[k];
         cxR[k] = fma(a[k][2], nrs, a[k][0] * nrc) * ops.dgr[k];
-        c.cyL[k] = fma(a[k][3], nbs, a[k][1] * nbc);
-        c.cyR[k] = fma(a[k][3], nts, a[k][1] * ntc);
+        gyL[k] = fma(a[k][3], nbs, a[k][1] * nbc) * ops.dgl[l];
+        gyR[k] = fma(a[k][3], nts, a[k][1] * ntc) * ops.dgr[l];
       }
     }
     double tl[4], tr[4], FxL[4], FxR[4];
@@ -118,8 +129,8 @@ euler2d_curv_fused_kernel(const double *__restrict__ u, const double *__restrict
       double x = 0, y = 0;  // the summation order of load_trace_x
 #pragma unroll
       for (int q = 0; q < NSP; ++q) {
-        x = fma(c.w[q][m], ops.ll[q], x);
-        y = fma(c.w[q][m], ops.lr[q], y);
+        x = fma(w[q][m], ops.ll[q], x);
+        y = fma(w[q][m], ops.lr[q], y);
       }
       tl[m] = x;
       tr[m] = __shfl_up_sync(0xffffffffu, y, 1);  // u_face[i-1, j, 2, l, m]
@@ -134,7 +145,7 @@ euler2d_curv_fused_kernel(const double *__restrict__ u, const double *__restrict
     double f1[NSP][4];
 #pragma unroll
     for (int k = 0; k < NSP; ++k) {
-      const double w0 = c.w[k][0], w1 = c.w[k][1], w2 = c.w[k][2], w3 = c.w[k][3];
+      const double w0 = w[k][0], w1 = w[k][1], w2 = w[k][2], w3 = w[k][3];
       const double r = frbcurv::rcp(w0), vx = w1 * r, vy = w2 * r;
       const double p = gm1 * (w3 - 0.5 * fma(w1, vx, w2 * vy));
       const double h = w3 + p;
@@ -143,22 +154,44 @@ euler2d_curv_fused_kernel(const double *__restrict__ u, const double *__restrict
 #pragma unroll
       for (int m = 0; m < 4; ++m) {
         f1[k][m] = fma(a[k][2], G[m], a[k][0] * F[m]);
-        tile[(((l * NSP + k) * 4) + m) * 32 + lane] = fma(a[k][3], G[m], a[k][1] * F[m]);
+        T[plane<NSP>(k, l, m) * 32] = fma(a[k][3], G[m], a[k][1] * F[m]);  // f2 over the state value just read
       }
     }
 #pragma unroll
     for (int m = 0; m < 4; ++m)
 #pragma unroll
       for (int k = 0; k < NSP; ++k) {
-        double d = f1[0][m] * ops.dmod[k * FRB_NSPMAX];
+        double x = f1[0][m] * ops.dmod[k * FRB_NSPMAX];
 #pragma unroll
-        for (int q = 1; q < NSP; ++q) d = fma(f1[q][m], ops.dmod[k * FRB_NSPMAX + q], d);
-        d = fma(cxL[k], FxL[m], d);
-        c.d[k][m] = fma(cxR[k], FxR[m], d);
+        for (int q = 1; q < NSP; ++q) x = fma(f1[q][m], ops.dmod[k * FRB_NSPMAX + q], x);
+        x = fma(cxL[k], FxL[m], x);
+        d[k][m] = fma(cxR[k], FxR[m], x);
       }
+#pragma unroll
+    for (int k = 0; k < NSP; ++k)
+#pragma unroll
+      for (int m = 0; m < 4; ++m) un[k][m] = (st.use_a && owned) ? ua[e + NE * plane<NSP>(k, l, m)] : 0.0;
   }
-  __syncthreads();
-  if (owned) frbcurv::row_ypass<NSP, IX, true>(i, j, l, ua, out, g, ops, st, tile + lane, fyt + lane, 32, c);
+  __syncthreads();  // the tile holds f2
+
+  // ---- y pass (the formulas of frbcurv::row_ypass, FOLD form) and the stage update
+  if (owned) {
+    const double *F = fyt + lane;
+#pragma unroll
+    for (int k = 0; k < NSP; ++k) {
+      const int yi = g.fy_row ? l : k;
+#pragma unroll
+      for (int m = 0; m < 4; ++m) {
+        double x = d[k][m];
+#pragma unroll
+        for (int q = 0; q < NSP; ++q) x = fma(T[plane<NSP>(k, q, m) * 32], ops.dmod[l * FRB_NSPMAX + q], x);
+        x = fma(gyL[k], F[((0 * NSP + yi) * 4 + m) * 32], x);
+        x = fma(gyR[k], F[((1 * NSP + yi) * 4 + m) * 32], x);
+        x = -x;
+        out[e + NE * plane<NSP>(k, l, m)] = fma(st.ca, un[k][m], fma(st.cdt, x, st.cb * w[k][m]));
+      }
+    }
+  }
 }
 
 }  // namespace
