@@ -48,7 +48,7 @@ PARITY_TESTS = {"1": "test_advection_rhs, test_advection_1000_steps: 1e-12 / 1e-
                 "2": "test_euler1d_cfg2_full_size_with_limiter: 1000 Midpoint steps at 4096 cells, 1e-9",
                 "4": "test_cfg4_full_size_bgk, test_cfg4_full_size_bgk_against_the_long_double_arbiter",
                 "5": "test_cfg5_full_size_ns_rhs: 1024^2 RHS, 1e-12",
-                "f2": "tests/test_gpu_curv.py: 12 cases incl. 1000 steps, 1e-9"}
+                "f2": "tests/test_gpu_curv.py: 148 cases over the three stage kernels incl. 1000 steps, 1e-9"}
 
 
 # ---- problem builders: (prob, alg, dt, stages, stage_bytes [per stage], hooks, host state) ---------------------
@@ -109,7 +109,7 @@ def build(FR, cfg, ctx):
                     workload="2D Euler on a sheared (45 degree) structured quadrilateral mesh, FRPSpace2D(base, deg 3), "
                              "1024x1024 elements, point-wise iJ, HLL in the face frame, SSPRK3, periodic ghost fill "
                              "(dev/parallelogram.jl:80-165 scaled)",
-                    kernel="euler2d_curv kernels (DESIGN 4.4)")
+                    kernel="euler2d_curv_fused_kernel<4, unsigned, HLL> (1 launch per stage, DESIGN 4.4)")
     raise SystemExit(f"unknown config {cfg}")
 
 

@@ -21,9 +21,12 @@
 namespace {
 
 constexpr int kOwn = 30;
+#ifndef FRB_CURV_FUSED_MINB
+#define FRB_CURV_FUSED_MINB 3  // blocks per SM the register budget is cut for (168 registers at p3)
+#endif
 
 template <int NSP, typename IX, int FLUX>
-__global__ void __launch_bounds__(32 * NSP, 3)
+__global__ void __launch_bounds__(32 * NSP, FRB_CURV_FUSED_MINB)
 euler2d_curv_fused_kernel(const double *__restrict__ u, const double *__restrict__ ua, double *__restrict__ out,
                           CurvGeom g, double gamma, FrbOps ops, FrbStage st) {
   using frbcurv::plane;

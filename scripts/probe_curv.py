@@ -2,11 +2,11 @@
 
     python scripts/probe_curv.py [nx ny deg iters]
 
-Prints one JSON line per stage kind: ms per fused stage (face + element kernel), DOF-updates/s and a
+Prints one JSON line per stage kind: ms per fused stage (the kernel frb_set_kernel selects), DOF-updates/s and a
 `roofline` object like bench.py's: achieved = algorithmic bytes (16 / 24 B of state + 8 B of metric per
 DOF-update) / stage time, peak = the measured HBM copy bandwidth of MEASURED_PEAKS.json
 (fallback: B200_PROFILING.md), traffic = the DRAM bytes per stage of the committed ncu capture
-(profiles/r01_curv.md; 1024^2 p3, 16-B stage only).  The CPU restatement of the same residual is timed by
+(profiles/r02_summary.md section F; 1024^2 p3, 16-B stage only).  The CPU restatement of the same residual is timed by
 tests/harness/cpu_baseline_curv.py (only tests/ may execute the oracle).
 """
 import json
@@ -36,7 +36,7 @@ def line(workload, dofs, state_bytes, ms, traffic=None):
             "gdof_per_s": round(dofs / ms / 1e6, 2), "algorithmic_GBps": round(achieved, 1),
             "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
                          "frac": round(achieved / peak, 4), "traffic": traffic, "peak_source": src,
-                         "kernel": "euler2d_curv_face_kernel + euler2d_curv_elem_kernel (2 launches per stage)"}}
+                         "kernel": "euler2d_curv_fused_kernel (1 launch per stage; vertex metric: face + element kernel)"}}
 
 
 def main():
@@ -59,7 +59,7 @@ def main():
             ms = prob.time_stage(kind, iters)
             captured = (nx, ny, deg, kind, corr, metric) == (1024, 1024, 3, 0, "sp", "stored")
             print(json.dumps(line(f"curv euler2d {nx}x{ny} p{deg} corr={corr} metric={metric}", dofs, state_bytes, ms,
-                                  2.709e9 if captured else None)), flush=True)
+                                  1.625e9 if captured else None)), flush=True)
         prob.close()
 
 
