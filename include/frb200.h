@@ -61,9 +61,10 @@ enum { FRB_ADV_PACKAGED = 0, FRB_ADV_LOWLEVEL = 1 };
 enum { FRB_KERNEL_AUTO = 0, FRB_KERNEL_GENERIC = 1, FRB_KERNEL_MARCH = 2, FRB_KERNEL_RC = 3,
        /* bgk1d problems only: the one-pass register-tile kernel instead of the two launches (same results) */
        FRB_KERNEL_BGK_ONE_PASS = 4,
-       /* curvilinear euler2d problems only: one row-marching launch per stage (state and metric read once, the
-        * common fluxes never leave the SM) instead of face kernel + element kernel (same results; stored metric,
-        * arrays below 2^32 elements) */
+       /* curvilinear euler2d problems (frb_euler2d_curv_create): AUTO = one launch per stage, every block evaluates
+        * the common fluxes of its own faces; GENERIC = face kernel + element kernel with the common fluxes through
+        * device memory (also what the vertex metric runs); CURV_MARCH = one launch that marches over the rows of a
+        * 30-element strip (stored metric, arrays below 2^32 elements).  Same results. */
        FRB_KERNEL_CURV_MARCH = 5 };
 
 /* common (Riemann) flux of the Euler problems.  HLL is what the reference calls (flux_hll!,
