@@ -7,7 +7,7 @@ from .spaces import *  # noqa: F401,F403
 from .unstruct import *  # noqa: F401,F403
 from .tools import *  # noqa: F401,F403
 from .problems import (  # noqa: F401
-    BGKProblem, DistributedEuler2D, DistributedNSCavity, Euler, Euler2DProblem, Euler2DCurvProblem, ExplicitRK, RK4, Tsit5, FRAdvectionProblem, FREulerProblem, Integrator, Midpoint, NSCavityProblem, SSPRK33, TriEulerProblem, init, ref_vhs_vis,
+    BGKProblem, DistributedEuler2D, DistributedEuler2DCurv, DistributedNSCavity, Euler, Euler2DProblem, Euler2DCurvProblem, ExplicitRK, RK4, Tsit5, FRAdvectionProblem, FREulerProblem, Integrator, Midpoint, NSCavityProblem, SSPRK33, TriEulerProblem, init, ref_vhs_vis,
     solve, step_,
 )
 from . import examples, partition  # noqa: F401

@@ -110,8 +110,10 @@ int check_launch(const char *what) {
 // export layout: 6 IPC handles (u, s1, s2, flags, row-chunk buffers, halo ring) + int32 ny_local + int32 has_rc
 extern "C" int32_t frb_halo_export(frb_prob_t p, unsigned char *out) {
   if (!p || !out) { frb_set_error("frb_halo_export: NULL argument"); return FRB_ERR_ARG; }
-  if (!((p->kind == K_EULER2D && !p->curv_iJ) || p->kind == K_NS2D)) {
-    frb_set_error("frb_halo_export: rectangular euler2d and ns2d problems only");
+  // curvilinear euler2d problems take the same row slabs (their metric, normals and factor tables are per-rank
+  // data of frb_euler2d_curv_create; the stage kernels read rows 0 / ny+1 of the state like any other row)
+  if (!(p->kind == K_EULER2D || p->kind == K_NS2D)) {
+    frb_set_error("frb_halo_export: euler2d and ns2d problems only");
     return FRB_ERR_STATE;
   }
   FRB_CUDA(cudaSetDevice(p->ctx->device));

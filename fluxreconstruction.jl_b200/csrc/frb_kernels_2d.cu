@@ -367,12 +367,12 @@ int frb_launch_ring_rows2d(frb_prob_t p, const double *src, double *d1, double *
 int frb_launch_ghost_x2d(frb_prob_t p, double *u, int mode) {
   const int npp = p->nsp * p->nsp, nplanes = 4 * npp;
   dim3 blk(128), gx((p->ny + 2 + 127) / 128, nplanes);
-  if (mode == FRB_GHOST_WAVE_X)
+  if (mode == FRB_GHOST_WAVE_X || mode == FRB_GHOST_PERIODIC)  // x half of :325 / :334 (the y half is the seam push)
     ghost_x_kernel<<<gx, blk, 0, p->ctx->stream>>>(u, p->nx, p->ny, nplanes, npp, p->nx, 1, -1, 1);
   else if (mode == FRB_GHOST_WAVE_Y)
     ghost_x_kernel<<<gx, blk, 0, p->ctx->stream>>>(u, p->nx, p->ny, nplanes, npp, p->nx, 1, 1, 1);
   else {
-    frb_set_error("slab-parallel ghost fill supports the periodic wave modes");
+    frb_set_error("slab-parallel ghost fill supports the periodic modes (wave_x, wave_y, periodic)");
     return FRB_ERR_ARG;
   }
   if (int rc = check_launch2("ghost_x_kernel")) return rc;

@@ -609,6 +609,24 @@ class TriEulerProblem(_Problem):
         return cls(u0, tspan, ct, ps.J, ps.lf, ps.cellNormals, ps.fpn, ps.dl, ps.phi, gamma, fpn_base=0, ctx=ctx)
 
 
+class DistributedEuler2DCurv(_SlabMixin, Euler2DCurvProblem):
+    """Row-slab parallel curvilinear 2-D Euler problem (SURVEY 8f-2 + 8e): one process per GPU, this rank holds rows
+    ``slab.start .. slab.stop`` of the global mesh in a local array [nx+2, ny_local+2, nsp, nsp, 4].  ``ps_local`` is
+    the ``FRPSpace2D(base, deg)`` of the rank's rows plus one ghost row on either side (the metric is per element, so
+    a space built from ``vertices[:, start-1 : stop+2]`` carries the global mesh's ``iJ`` of those rows bit for bit);
+    ``n1 = n1_global[:, start-1 : stop]``, ``n2 = n2_global[:, start-1 : stop+1]``.  Interior slab boundaries are
+    exchanged after every stage over NVLink, the global y seam follows the per-step periodic ghost fill of
+    dev/parallelogram.jl:201-205 (``ghost="periodic"``)."""
+
+    def __init__(self, u0_local, tspan, ps_local, gamma, dist, n1=None, n2=None, corr="sp", fy_index="k", ctx=None,
+                 ghost="periodic", kernel="auto"):
+        super().__init__(u0_local, tspan, ps_local, gamma, n1, n2, corr=corr, fy_index=fy_index, ctx=ctx)
+        if kernel != "auto":
+            self.set_kernel(kernel)
+        self.set_hooks(ghost=ghost)
+        self._connect(dist)
+
+
 class DistributedNSCavity(_SlabMixin, NSCavityProblem):
     """Column-slab parallel cavity (cfg5): one process per GPU, this rank holds columns ``slab.start .. slab.stop``
     of the global mesh in a local array [4, nsp, nsp, ny+2, nx_local+2] (``i`` is the slowest index of the

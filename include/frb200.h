@@ -269,6 +269,8 @@ int32_t frb_host_free(void *ptr);
  * for it (ld.acquire.sys) -- every other CTA runs at once, so the exchange overlaps
  * the interior rows and a stage stays ONE launch.  The other kernels push their rows
  * after the stage and hand epochs over with one-thread signal / wait kernels.
+ * Curvilinear euler2d problems (frb_euler2d_curv_create) take the same row slabs: every rank creates its problem
+ * from its own rows of iJ / n1 / n2 / fpc, ghost mode FRB_GHOST_PERIODIC; rows pushed after the stage.
  * ns2d problems (cfg5) are split the same way along the slowest index of their layout, i: a rank owns nx_local
  * columns, columns 0 / nx_local+1 of an interior slab boundary are halo columns that replace the wall ghosts
  * of boundary! there (no periodic seam); the same four calls apply.

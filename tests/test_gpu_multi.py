@@ -102,6 +102,16 @@ def test_two_rank_cavity_slabs_match_oracle(nx, ny, deg):
     _torchrun(2, 29519, "check_dist_ns.py", nx, ny, deg, 30)
 
 
+@pytest.mark.parametrize("world", [2, 4])
+@pytest.mark.parametrize("kernel,scheme,deg", [("auto", "ssprk3", 2), ("generic", "midpoint", 3),
+                                               ("curv_march", "euler", 1)])
+def test_n_rank_curvilinear_slabs_match_oracle(world, kernel, scheme, deg):
+    """Row slabs of a sheared mesh (SURVEY 8f-2 on 8e's partition): every stage kernel of the curvilinear path,
+    interior boundaries exchanged per stage, the periodic seam per step; 33 x 16 elements, 20 steps, 1e-10."""
+    _need(world)
+    _torchrun(world, 29541, "check_dist_curv.py", 33, 16, 20, scheme, deg, kernel)
+
+
 @pytest.mark.parametrize("world", [4, 8])
 def test_n_rank_cavity_slabs_match_oracle(world):
     _need(world)

@@ -329,3 +329,28 @@ def test_oracle_reproduces_the_golden_vectors(host_stage):
         assert rel(c.rhs_euler2d_curv(u, ps, n1, n2, GAMMA, corr="fp", fpc=fpc, fy_index=fy, wall_xlo=True), ref) < 1e-14
         assert rel(host_stage(u, ps, n1, n2, fpc, flags), ref) < 1e-13
     assert np.array_equal(c.ghost_fill_cylinder(u.copy(), deg + 1), g["cyl_ghost"])
+
+
+# ------------------------------------------------------------------------------- row slabs of a curvilinear mesh
+@pytest.mark.parametrize("world", [2, 3, 5])
+def test_slab_space_carries_the_global_metric(FR, world):
+    """What tests/dist/check_dist_curv.py hands to DistributedEuler2DCurv on every rank: the space built from the
+    slab's vertices has the global mesh's metric of those rows bit for bit, the normal tables slice by rows / faces."""
+    nx, nyg, deg = 9, 11, 2
+    v = c.parallelogram_vertices(nx, nyg)
+    pog = c.CurvSpace2D(v, deg)
+    n1g, n2g = c.parallelogram_normals(nx, nyg)
+    covered = []
+    for rank in range(world):
+        sl = FR.partition.slab(nyg, world, rank)
+        rows = slice(sl.start - 1, sl.stop + 2)
+        zl = np.zeros((nx + 2, sl.count + 2))
+        psl = FR.FRPSpace2D(FR.PSpace2D(0.0, 1.0, nx, 0.0, 0.5, sl.count, zl, zl, zl, zl, v[:, rows]), deg)
+        assert (psl.nx, psl.ny, psl.ngx, psl.ngy) == (nx, sl.count, 1, 1)
+        assert np.array_equal(psl.iJ, pog.iJ[:, rows])
+        n1l, n2l = n1g[:, sl.start - 1: sl.stop], n2g[:, sl.start - 1: sl.stop + 1]
+        assert n1l.shape == (nx + 1, sl.count, 2) and n2l.shape == (nx, sl.count + 1, 2)
+        f1, f2 = FR.face_normals(psl.vertices)
+        assert np.abs(f1 - n1l).max() < 1e-14 and np.abs(f2 - n2l).max() < 1e-14
+        covered += list(range(sl.start, sl.stop + 1))
+    assert covered == list(range(1, nyg + 1))
