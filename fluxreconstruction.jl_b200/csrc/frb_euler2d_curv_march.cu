@@ -1,33 +1,34 @@
-// 2-D Euler on curvilinear structured quadrilaterals, ONE launch per stage: a block owns a strip of
-// 30 elements and marches over a segment of element rows, so that the state is read once, the metric once and the
-// common fluxes never leave the SM (the two-kernel form of frb_euler2d_curv.cu reads the state twice and sends
-// fx / fy through HBM: 2.71 GB per 16-B stage at 1024^2 p3 against 1.61 GB algorithmic, profiles/r01_curv.md).
+// 2-D Euler on curvilinear structured quadrilaterals, one ROW-MARCHING launch per stage
+// (FRB_KERNEL_CURV_MARCH; not the default: frb_euler2d_curv_fused.cu is faster, profiles/r02_summary.md section F).
+// A block owns a strip of 30 elements and marches over a segment of element rows, so that the state is read once,
+// the metric once, every y flux is evaluated once and the common fluxes never leave the SM (1.68 GB of DRAM traffic
+// per 16-B stage at 1024^2 p3 against the 2.71 GB of round 1's two launches; 1.61 GB algorithmic).
 //
 // Reference semantics: dudt! of dev/parallelogram.jl:80-165 and dev/cylinder2.jl:52-164, as restated in
-// frb_euler2d_curv_elem.cuh (same layouts, same factors, same flux_normal, the formulas of row_xpass / row_ypass
-// term by term).
+// frb_euler2d_curv_elem.cuh (same layouts, same factors, the formulas of row_xpass / row_ypass in their FOLD form).
 //
 // thread = (lane = element of the strip, l = point row); lanes 1..30 own their element, lanes 0 / 31 are the
 // neighbours whose traces the x faces of the strip's edge elements need (the duplicate-lane form of the
-// rectangular row-chunk kernel).  The state images [plane][lane] (16 KB per row at p3) of three consecutive rows
-// live in a shared-memory ring filled by cp.async two rows ahead of the row in flight.  Per row jj = j0 .. j1-1:
+// rectangular row-chunk kernel).  Every global input arrives by cp.async as a shared-memory image [plane][lane]
+// (16 KB per row at p3) at least one phase before its use: the state of three consecutive rows (ring, two rows
+// ahead), the metric of two rows (one row ahead), u_n of the row in flight; only the normals (4 doubles per
+// thread and row) are plain loads, one row ahead in registers.  104 KB per block at p3: 2 blocks / SM.
+// Per row jj = j0 .. j1-1:
 //   A  row jj+1 has landed; its y traces at flux point p = l; common flux of y face jj+1 from the carried top
 //      trace of row jj and the bottom trace of row jj+1 -> fyt[(jj+1) & 1][p][m][lane] (fyt[jj & 1] holds face jj
 //      from the previous iteration);
 //      x pass of row jj: traces in registers, the neighbours' by __shfl, x-face fluxes, point fluxes iJ [F; G],
-//      r-derivative + x corrections, f2 of the row into the tile  (the formulas of frbcurv::row_xpass)
+//      r-derivative + x corrections; f2 of the row goes over the state values the row owner has just read (the
+//      ring slot of row jj becomes the f2 tile)
 //   B  y pass of row jj: s-derivative, y corrections from both fyt halves, stage update, store
-//      (the formulas of frbcurv::row_ypass)
-// The metric of the row (16 values per thread) and u_n are plain loads issued a phase before their use.
 //
-// Arithmetic form (what makes the kernel issue-bound rather than traffic-bound is the instruction count, so):
-// the flux traces of the correction are folded into the derivative matrix (FrbOps::dmod, as in the rectangular
-// marching kernels) and the stage coefficients into the operators,
+// Arithmetic form: the flux traces of the correction are folded into the derivative matrix (FrbOps::dmod, as in
+// the rectangular marching kernels) and the stage coefficients into the operators,
 //   out = ca u_n + cb u + sum_q f1[q] M[k][q] + cxL[k] gl[k] FxL + cxR[k] gr[k] FxR
 //                        + sum_q f2[q] M[l][q] + cyL[k] gl[l] FyB + cyR[k] gr[l] FyT,
 //   M = -cdt dmod, gl = -cdt dgl, gr = -cdt dgr  (CurvMarchOps, built by the launcher);
-// the common flux is a compile-time choice (riemann4_fast<FLUX>), reciprocals are MUFU-seeded, and the global
-// addresses of a row are walked with two 64-bit strides instead of one multiply per plane.
+// the common flux is a compile-time choice (riemann4_fast<FLUX>), reciprocals are MUFU-seeded, element indices are
+// unsigned 32-bit (the launcher checks the array size).
 #include "frb_euler2d_curv_elem.cuh"
 
 namespace {
